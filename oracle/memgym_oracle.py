@@ -1,0 +1,731 @@
+"""CPU oracle: a restatement of the reference Memory-Gym environments (TEST INFRASTRUCTURE ONLY).
+
+Not imported by the product package. Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may use it, and only as the checker /
+CPU baseline. It travels to the GPU box (``/root/reference`` does not), which is why the env logic
+is restated here instead of importing the reference.
+
+PARITY STATUS
+* env logic (state machines, RNG draw order, quirks): pinned — ``tests/golden/ref_*.npz`` hold
+  trajectories produced by the UNMODIFIED reference sources imported from /root/reference on top
+  of ``oracle/shims`` (``oracle/gen_golden.py``); ``tests/test_oracle_vs_reference_golden.py``
+  replays them through this module bit-for-bit.
+* raster: pinned against real-PyGame GIF known answers (``tests/test_raster_kat.py``) except the
+  pygame>=2.1.3 thick circle of the "stay" icon (4 px) — "parity unpinned" for those pixels.
+* RNG: the real ``numpy.random.Generator(PCG64(SeedSequence(seed)))`` the reference gets from
+  gymnasium 0.29 (``gymnasium/utils/seeding.py``), so draws are the reference's by construction.
+* ``info["reward"]`` is the left-to-right IEEE-double sum of the step rewards, i.e. what ``sum()``
+  returns on the Python 3.11 the reference documents (README.md:63); Python >= 3.12's ``sum`` is
+  compensated and can differ in the last bit.
+
+Each class cites the reference lines it follows. Frames are ``uint8[84][84][3]`` in pygame's
+``surfarray.array3d`` layout ``[x][y][c]``.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import assets
+from . import sdl_raster as R
+
+SCALE = 0.25
+SCREEN = int(336 * SCALE)
+
+
+def _frame_to_obs(px: np.ndarray) -> np.ndarray:
+    t = px.T
+    out = np.empty((px.shape[1], px.shape[0], 3), dtype=np.uint8)
+    out[..., 0] = t >> 16
+    out[..., 1] = t >> 8
+    out[..., 2] = t
+    return out
+
+
+def _paste(frame: np.ndarray, src: R.Surface, x: int, y: int) -> None:
+    """Colour-key blit of ``src`` with its top-left at (x, y), clipped (SDL_BlitSurface)."""
+    x0, y0 = max(x, 0), max(y, 0)
+    x1, y1 = min(x + src.w, frame.shape[1]), min(y + src.h, frame.shape[0])
+    if x1 <= x0 or y1 <= y0:
+        return
+    sv = src.px[y0 - y:y1 - y, x0 - x:x1 - x]
+    if src.colorkey is None:
+        frame[y0:y1, x0:x1] = sv
+    else:
+        np.copyto(frame[y0:y1, x0:x1], sv, where=sv != src.colorkey)
+
+
+class _OracleEnv:
+    """Seeding contract of gymnasium 0.29 ``Env.reset`` (seed given -> new PCG64; else continue)."""
+
+    def __init__(self):
+        self._rng = None
+
+    def _seed(self, seed):
+        if seed is not None:
+            self._rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        elif self._rng is None:
+            self._rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence()))
+        return self._rng
+
+    @classmethod
+    def process_reset_params(cls, options):
+        params = dict(cls.default_reset_parameters)
+        if options is not None:
+            for k, v in options.items():
+                assert k in params, "Provided reset parameter (" + str(k) + ") is not valid. Check spelling."
+                params[k] = v
+        cls._check_params(params)
+        return params
+
+    @classmethod
+    def _check_params(cls, params):
+        pass
+
+
+# --------------------------------------------------------------------------------------------------
+# kinematics  (character_controller.py)
+# --------------------------------------------------------------------------------------------------
+def _velocity_and_rotation(action, rotation):
+    """character_controller.py:100-121 — unit direction and the new rotation (degrees)."""
+    vx = -1 if action[0] == 1 else (1 if action[0] == 2 else 0)
+    vy = -1 if action[1] == 1 else (1 if action[1] == 2 else 0)
+    if action[0] == 1:
+        rotation = 90
+    if action[0] == 2:
+        rotation = 270
+    if action[1] == 1:
+        rotation = 0
+    if action[1] == 2:
+        rotation = 180
+    if vx and vy:
+        rotation = {(-1, -1): 45, (-1, 1): 135, (1, -1): 315, (1, 1): 225}[(vx, vy)]
+    return vx, vy, rotation
+
+
+def move_clamped(cx, cy, rotation, action, speed, radius, rect):
+    """CharacterController.step (character_controller.py:89-146). ``rect`` = (x, y, w, h)."""
+    vx, vy, rotation = _velocity_and_rotation(action, rotation)
+    if vx or vy:
+        n = math.sqrt(float(vx * vx + vy * vy))
+        # normalize() * speed, then int() per component (:124-126)
+        cx += int((vx / n) * speed)
+        cy += int((vy / n) * speed)
+    left, top, right, bottom = rect[0], rect[1], rect[0] + rect[2], rect[1] + rect[3]
+    cx = min(cx, right - radius)
+    cx = max(cx, left + radius)
+    cy = min(cy, bottom - radius)
+    cy = max(cy, top + radius)
+    return cx, cy, rotation
+
+
+def move_wrapped(cx, cy, rotation, action, speed, radius, rect):
+    """ScreenWrapCharacterController.step (character_controller.py:226-283): float velocity, the
+    Rect assignment truncates toward zero, then wrap at +-radius/2 beyond the rect."""
+    vx, vy, rotation = _velocity_and_rotation(action, rotation)
+    fx, fy = float(vx), float(vy)
+    if vx or vy:
+        n = math.sqrt(fx * fx + fy * fy)
+        fx, fy = (fx / n) * speed, (fy / n) * speed
+    cx, cy = int(float(cx) + fx), int(float(cy) + fy)
+    left, top, right, bottom = rect[0], rect[1], rect[0] + rect[2], rect[1] + rect[3]
+    off = radius * 0.5
+    x, y = cx, cy
+    if x > right + off:
+        x = left - off
+    if x < left - off:
+        x = right + off
+    if y > bottom + off:
+        y = top - off
+    if y < top - off:
+        y = bottom + off
+    return int(x), int(y), rotation
+
+
+# --------------------------------------------------------------------------------------------------
+# Mortar Mayhem family
+# --------------------------------------------------------------------------------------------------
+TILE = 56 * SCALE  # 14.0
+
+
+def calc_max_episode_steps(command_count, show_duration, show_delay, execution_duration, execution_delay):
+    """pygame_assets.py:420-436 (informational only; the caller passes delay/duration swapped)."""
+    clue = (show_duration + show_delay) * command_count
+    act = (execution_duration + execution_delay) * command_count
+    return clue + act - execution_delay + 1
+
+
+class MortarMayhemOracle(_OracleEnv):
+    """mortar_mayhem.py:15-369 (MortarMayhemEnv) on CharacterController + MortarArena + Command."""
+
+    env_id = "MortarMayhem-v0"
+    grid_locomotion = False
+    default_reset_parameters = {
+        "agent_scale": 1.0 * SCALE,
+        "agent_speed": 12.0 * SCALE,
+        "arena_size": 5,
+        "allowed_commands": 9,
+        "command_count": [10],
+        "command_show_duration": [3],
+        "command_show_delay": [1],
+        "explosion_duration": [6],
+        "explosion_delay": [18],
+        "visual_feedback": True,
+        "reward_command_failure": 0.0,
+        "reward_command_success": 0.1,
+        "reward_episode_success": 0.0,
+    }
+
+    @classmethod
+    def _check_params(cls, p):
+        assert p["allowed_commands"] >= 4 and p["allowed_commands"] <= 9
+        assert p["arena_size"] >= 2 and p["arena_size"] <= 6
+
+    # ---- geometry --------------------------------------------------------------------------------
+    def _setup_arena(self, size):
+        self.size = size
+        dim = int(TILE * size)
+        self.origin = SCREEN // 2 - (dim >> 1)  # arena.rect.center = (42, 42)
+        self.arena_rect = (self.origin, self.origin, dim, dim)
+        self.tiles_on = False
+
+    def _tile_centre(self, i, j):
+        # get_tile_global_position + translate (mortar_mayhem.py:238-242)
+        t = SCREEN // 2 - ((int(TILE * self.size)) >> 1) + TILE // 2
+        return TILE * i + t, TILE * j + t
+
+    def _normalize(self, cx, cy):
+        return ((cx - self.origin) // TILE, (cy - self.origin) // TILE)
+
+    def _agent_scale(self):
+        return self.p["agent_scale"]
+
+    # ---- reset -----------------------------------------------------------------------------------
+    def reset(self, seed=None, options=None):
+        rng = self._seed(seed)
+        p = self.p = self.process_reset_params(options)
+        self.max_episode_steps = calc_max_episode_steps(
+            max(p["command_count"]), max(p["command_show_duration"]), max(p["command_show_delay"]),
+            max(p["explosion_delay"]), max(p["explosion_duration"]))
+        self.rewards = []
+        self._setup_arena(p["arena_size"])
+        self.sprites = assets.agent_sprites(self._agent_scale())
+        self.radius = int(25 * self._agent_scale())
+        tile_id = int(rng.integers(0, self.size ** 2))
+        i, j = tile_id // self.size, tile_id % self.size
+        x, y = self._tile_centre(i, j)
+        self.cx, self.cy = int(x), int(y)
+        self.rotation = 0
+        self.pos = self._normalize(self.cx, self.cy)
+        if self.grid_locomotion:
+            self.gx, self.gy = int(self.pos[0]), int(self.pos[1])
+        # command sequence (:163-183)
+        self.n = int(rng.choice(p["command_count"]))
+        self.commands = []
+        sim = self.pos
+        for _ in range(self.n):
+            valid = []
+            for k in range(p["allowed_commands"]):
+                d = assets.COMMAND_DELTAS[k]
+                tx, ty = sim[0] + d[0], sim[1] + d[1]
+                if 0 <= tx < self.size and 0 <= ty < self.size:
+                    valid.append(k)
+            k = valid[int(rng.integers(0, len(valid)))]
+            self.commands.append(k)
+            sim = (sim[0] + assets.COMMAND_DELTAS[k][0], sim[1] + assets.COMMAND_DELTAS[k][1])
+        dur = int(rng.choice(p["command_show_duration"]))
+        delay = int(rng.choice(p["command_show_delay"]))
+        self.show = self._show_list(self.commands, dur, delay)
+        first = self.show.pop(0)
+        d0 = assets.COMMAND_DELTAS[self.commands[0]]
+        self.target = (self.pos[0] + d0[0], self.pos[1] + d0[1])
+        self.cc = self.cs = self.cv = 0
+        self.E = int(rng.choice(p["explosion_duration"]))
+        self.D = int(rng.choice(p["explosion_delay"]))
+        self.draw_cx, self.draw_cy, self.draw_rot = self.cx, self.cy, 0
+        return self._render(first, (self.cx, self.cy, 0)), {}
+
+    @staticmethod
+    def _show_list(commands, dur, delay):
+        out = []
+        for k in commands:
+            out += [k] * dur + [-1] * delay
+        return out
+
+    # ---- step ------------------------------------------------------------------------------------
+    def _move(self, action):
+        if self.grid_locomotion:
+            # GridCharacterController.step (character_controller.py:177-210)
+            if action == 1:
+                self.rotation = (self.rotation + 90) % 360
+            if action == 2:
+                self.rotation = (self.rotation - 90) % 360
+            if action == 3:
+                face = self.rotation // 90
+                last = self.size - 1
+                if face == 0 and self.gy > 0:
+                    self.gy -= 1
+                elif face == 3 and self.gx < last:
+                    self.gx += 1
+                elif face == 2 and self.gy < last:
+                    self.gy += 1
+                elif face == 1 and self.gx > 0:
+                    self.gx -= 1
+                x, y = self._tile_centre(self.gx, self.gy)
+                self.cx, self.cy = int(x), int(y)
+        else:
+            self.cx, self.cy, self.rotation = move_clamped(
+                self.cx, self.cy, self.rotation, action, self.p["agent_speed"], self.radius, self.arena_rect)
+
+    def step(self, action):
+        p = self.p
+        reward = 0
+        done = False
+        success = 0
+        icon = None
+        if self.show:
+            icon = self.show.pop(0)
+            sprite = (self.cx, self.cy, 0)
+        else:
+            self._move(action)
+            sprite = (self.cx, self.cy, self.rotation)
+            self.pos = self._normalize(self.cx, self.cy)
+            verify = self.cs % self.D == 0 and self.cs > 0
+            if verify and not self.tiles_on:
+                if self.cc < self.n:
+                    self.cc += 1
+                    self.tiles_on = True
+                    if self.pos == self.target:
+                        reward += p["reward_command_success"]
+                    else:
+                        done = True
+                        reward += p["reward_command_failure"]
+                if self.cc >= self.n:
+                    done = True
+                    success = 1
+                    reward += p["reward_episode_success"]
+                self.cs = 1
+            if self.tiles_on:
+                if self.cv % self.E == 0 and self.cv > 0:
+                    self.tiles_on = False
+                    self.cv = 0
+                    if self.cc < self.n:
+                        d = assets.COMMAND_DELTAS[self.commands[self.cc]]
+                        self.target = (self.target[0] + d[0], self.target[1] + d[1])
+                else:
+                    if not self.pos == self.target:
+                        done = True
+                        reward = p["reward_command_failure"]
+                    self.cv += 1
+            else:
+                self.cs += 1
+        self.rewards.append(reward)
+        info = {}
+        if done:
+            info = {"reward": _seq_sum(self.rewards), "length": len(self.rewards), "success": success,
+                    "commands_completed": (self.cc - 1 + success) / self.n}
+        return self._render(icon, sprite), reward, done, False, info
+
+    # ---- frame -----------------------------------------------------------------------------------
+    def _render(self, icon, sprite):
+        frame = np.zeros((SCREEN, SCREEN), dtype=np.uint32)
+        blue, red = assets.mortar_tile(SCALE, False), assets.mortar_tile(SCALE, True)
+        redden = self.tiles_on and self.p["visual_feedback"]
+        t = int(TILE)
+        for i in range(self.size):
+            for j in range(self.size):
+                tile = red if (redden and not self.target == (i, j)) else blue
+                frame[self.origin + t * j:self.origin + t * (j + 1), self.origin + t * i:self.origin + t * (i + 1)] = tile.px
+        cx, cy, rot = sprite
+        sp = self.sprites[rot // 45]
+        _paste(frame, sp, cx - (sp.w >> 1), cy - (sp.h >> 1))
+        if icon is not None:
+            surf = assets.command_icon("" if icon < 0 else assets.COMMAND_NAMES[icon], SCALE)
+            pos = assets.command_blit_pos(SCALE, SCREEN)
+            _paste(frame, surf, int(pos[0]), int(pos[1]))
+        return _frame_to_obs(frame)
+
+
+def _seq_sum(values):
+    total = 0
+    for v in values:
+        total = total + v
+    return total
+
+
+class GridMortarMayhemOracle(MortarMayhemOracle):
+    """mortar_mayhem_grid.py:15-375 (GridMortarMayhemEnv) on GridCharacterController."""
+
+    env_id = "MortarMayhem-Grid-v0"
+    grid_locomotion = True
+    default_reset_parameters = {
+        "agent_scale": 1.0 * SCALE,
+        "arena_size": 5,
+        "allowed_commands": 5,
+        "command_count": [10],
+        "command_show_duration": [3],
+        "command_show_delay": [1],
+        "explosion_duration": [2],
+        "explosion_delay": [6],
+        "visual_feedback": True,
+        "reward_command_failure": 0.0,
+        "reward_command_success": 0.1,
+        "reward_episode_success": 0.0,
+    }
+
+    def _agent_scale(self):
+        return SCALE  # GridCharacterController(SCALE, ...) ignores agent_scale (mortar_mayhem_grid.py:249)
+
+
+class EndlessMortarMayhemOracle(MortarMayhemOracle):
+    """endless_mortar_mayhem.py:15-373 (EndlessMortarMayhemEnv) on ScreenWrapCharacterController."""
+
+    env_id = "Endless-MortarMayhem-v0"
+    default_reset_parameters = {
+        "max_steps": -1,
+        "agent_scale": 1.0 * SCALE,
+        "agent_speed": 12.0 * SCALE,
+        "allowed_commands": 9,
+        "initial_command_count": 1,
+        "command_show_duration": [3],
+        "command_show_delay": [1],
+        "explosion_duration": [6],
+        "explosion_delay": [18],
+        "visual_feedback": True,
+        "reward_command_failure": 0.0,
+        "reward_command_success": 0.1,
+        "reward_new_command_success": 0.0,
+    }
+
+    def __init__(self):
+        super().__init__()
+        # pose of the sprite handle (rotated_agent_surface/rect) last returned by a controller. It is
+        # never cleared by reset() (:99, :277-278), and after reset it keeps pointing at the OLD
+        # controller's rect, i.e. it is frozen at the previous episode's last pose (quirk A.9#3).
+        self.stale = None
+
+    @classmethod
+    def _check_params(cls, p):
+        assert p["allowed_commands"] >= 4 and p["allowed_commands"] <= 9
+
+    def _draw_commands(self, rng, count):
+        return [int(v) for v in rng.integers(0, self.p["allowed_commands"], count)]
+
+    def _gt(self):
+        return np.asarray([*self.target]) / 5.0
+
+    def reset(self, seed=None, options=None):
+        rng = self._seed(seed)
+        p = self.p = self.process_reset_params(options)
+        self.t = 0
+        self.max_episode_steps = p["max_steps"]
+        self.rewards = []
+        self._setup_arena(6)
+        self.sprites = assets.agent_sprites(p["agent_scale"])
+        self.radius = int(25 * p["agent_scale"])
+        tile_id = int(rng.integers(0, 36))
+        off = rng.integers(-8 * SCALE, 8 * SCALE, 2)
+        x, y = self._tile_centre(tile_id // 6, tile_id % 6)
+        self.cx, self.cy = int(x + int(off[0])), int(y + int(off[1]))
+        self.rotation = 0
+        self.pos = self._normalize(self.cx, self.cy)
+        self.n = p["initial_command_count"]
+        self.commands = self._draw_commands(rng, self.n)
+        self.dur = int(rng.choice(p["command_show_duration"]))
+        self.delay = int(rng.choice(p["command_show_delay"]))
+        self.show = self._show_list(self.commands, self.dur, self.delay)
+        first = self.show.pop(0)
+        d0 = assets.COMMAND_DELTAS[self.commands[0]]
+        self.target = ((self.pos[0] + d0[0]) % 6, (self.pos[1] + d0[1]) % 6)
+        self.cc = self.cs = self.cv = 0
+        self.total_completed = 0
+        self.E = int(rng.choice(p["explosion_duration"]))
+        self.D = int(rng.choice(p["explosion_delay"]))
+        return self._render(first, (self.cx, self.cy, 0)), {"ground_truth": self._gt()}
+
+    def step(self, action):
+        p = self.p
+        reward = 0
+        done = False
+        icon = None
+        if self.show:
+            icon = self.show.pop(0)
+            if self.stale is None:
+                # first episode of this instance: get_rotated_sprite(0) of the live controller
+                self.stale = (self.cx, self.cy, 0)
+        else:
+            self.cx, self.cy, self.rotation = move_wrapped(
+                self.cx, self.cy, self.rotation, action, p["agent_speed"], self.radius, self.arena_rect)
+            self.stale = (self.cx, self.cy, self.rotation)
+            self.pos = self._normalize(self.cx, self.cy)
+            verify = self.cs % self.D == 0 and self.cs > 0
+            if verify and not self.tiles_on:
+                if self.cc < self.n:
+                    self.cc += 1
+                    self.tiles_on = True
+                    if self.pos == self.target:
+                        reward += p["reward_command_success"]
+                        self.total_completed += 1
+                        if self.cc == self.n:
+                            reward += p["reward_new_command_success"]
+                    else:
+                        done = True
+                        reward += p["reward_command_failure"]
+                if self.cc >= self.n:
+                    new = self._draw_commands(self._rng, 1)
+                    self.commands.append(new[0])
+                    self.n = len(self.commands)
+                    self.cc = self.cs = self.cv = 0
+                    self.show = self._show_list(new, self.dur, self.delay)
+                self.cs = 1
+            if self.tiles_on:
+                if self.cv % self.E == 0 and self.cv > 0:
+                    self.tiles_on = False
+                    self.cv = 0
+                    if self.cc < self.n:
+                        d = assets.COMMAND_DELTAS[self.commands[self.cc]]
+                        self.target = ((self.target[0] + d[0]) % 6, (self.target[1] + d[1]) % 6)
+                else:
+                    if not self.pos == self.target:
+                        done = True
+                        reward = p["reward_command_failure"]
+                    self.cv += 1
+            else:
+                self.cs += 1
+        self.t += 1
+        if self.t == self.max_episode_steps:
+            done = True
+        self.rewards.append(reward)
+        info = {"ground_truth": self._gt()}
+        if done:
+            info = {"reward": _seq_sum(self.rewards), "length": len(self.rewards),
+                    "commands_completed": self.total_completed,
+                    "max_command_sequence": len(self.commands) - 1 if len(self.commands) > 1 else 0,
+                    "ground_truth": self._gt()}
+        # (within an episode the agent cannot move during a show phase, so the handle's pose equals
+        # the live pose; only across a reset does it lag behind)
+        return self._render(icon, self.stale), reward, done, False, info
+
+
+# --------------------------------------------------------------------------------------------------
+# Mystery Path
+# --------------------------------------------------------------------------------------------------
+def generate_mystery_path(rng, n, start, end):
+    """pygame_assets.py:606-724 (MysteryPath.__init__): walls + noisy A*. Returns [end, ..., start]."""
+    wall = [[False] * n for _ in range(n)]
+    for i in range(n):
+        for j in range(n):
+            if 0 < i < n - 2 and 0 < j < n - 2:
+                if rng.integers(0, 100) < 33:
+                    wall[i][j] = True
+
+    def neighbours(i, j):  # Node.add_neighbors order (:465-472)
+        out = []
+        if i < n - 1:
+            out.append((i + 1, j))
+        if i > 0:
+            out.append((i - 1, j))
+        if j < n - 1:
+            out.append((i, j + 1))
+        if j > 0:
+            out.append((i, j - 1))
+        return out
+
+    def diagonals(i, j):  # (:474-481)
+        out = []
+        if i < n - 1 and j < n - 1:
+            out.append((i + 1, j + 1))
+        if i > 0 and j > 0:
+            out.append((i - 1, j - 1))
+        if i < n - 1 and j > 0:
+            out.append((i + 1, j - 1))
+        if i > 0 and j < n - 1:
+            out.append((i - 1, j + 1))
+        return out
+
+    near_ends = set(neighbours(*start)) | set(neighbours(*end))
+    ring = []
+    for i in range(n):
+        for j in range(n):
+            if i == 0 or i == n - 1 or j == 0 or j == n - 1:
+                if (i, j) == tuple(start) or (i, j) == tuple(end) or (i, j) in near_ends:
+                    continue
+                if any(wall[a][b] for a, b in neighbours(i, j)) or any(wall[a][b] for a, b in diagonals(i, j)):
+                    continue
+                ring.append((i, j))
+    for _ in range(int(rng.choice([4, 8]))):
+        if ring:
+            node = ring[int(rng.integers(0, len(ring)))]  # rng.choice(outer_nodes)
+            wall[node[0]][node[1]] = True
+            ring.remove(node)
+
+    start, end = tuple(start), tuple(end)
+    g = {start: 0}
+    f = {start: 0}
+    prev = {start: None}
+    open_set, closed = [start], set()
+    while True:
+        if not open_set:
+            raise Exception("No valid path found")
+        w = 0
+        for k in range(len(open_set)):
+            if f[open_set[k]] < f[open_set[0]]:
+                w = k
+                break
+        cur = open_set[w]
+        if cur == end:
+            path = [end]
+            while prev[path[-1]] is not None:
+                path.append(prev[path[-1]])
+            return path, wall
+        open_set.remove(cur)
+        closed.add(cur)
+        for nb in neighbours(*cur):
+            if nb in closed or wall[nb[0]][nb[1]]:
+                continue
+            cost = g[cur] + int(rng.integers(1, 9))
+            new_path = False
+            if nb in open_set:
+                if cost < g[nb]:
+                    new_path = True  # g_cost is NOT updated (reference bug :712)
+            else:
+                g[nb] = cost
+                new_path = True
+                open_set.append(nb)
+            if new_path:
+                h = math.sqrt((nb[0] - end[0]) ** 2 + abs(nb[1] - end[1]) ** 2)
+                f[nb] = g[nb] + h
+                prev[nb] = cur
+
+
+class MysteryPathOracle(_OracleEnv):
+    """mystery_path.py:15-276 (MysteryPathEnv)."""
+
+    env_id = "MysteryPath-v0"
+    default_reset_parameters = {
+        "max_steps": 512,
+        "agent_scale": 1.0 * SCALE,
+        "agent_speed": 12.0 * SCALE,
+        "cardinal_origin_choice": [0, 1, 2, 3],
+        "show_origin": False,
+        "show_goal": False,
+        "visual_feedback": True,
+        "reward_goal": 1.0,
+        "reward_fall_off": 0.0,
+        "reward_path_progress": 0.1,
+        "reward_step": 0.0,
+    }
+    GRID = 7
+    TILE = SCREEN / 7  # 12.0
+
+    def reset(self, seed=None, options=None):
+        rng = self._seed(seed)
+        p = self.p = self.process_reset_params(options)
+        self.t = 0
+        self.max_episode_steps = p["max_steps"]
+        self.rewards = []
+        g = self.GRID
+        side = rng.choice(p["cardinal_origin_choice"])
+        if side == 0:
+            self.start = (0, int(rng.integers(0, g)))
+            self.end = (g - 1, int(rng.integers(0, g)))
+        elif side == 1:
+            self.start = (g - 1, int(rng.integers(0, g)))
+            self.end = (0, int(rng.integers(0, g)))
+        elif side == 2:
+            self.start = (int(rng.integers(0, g)), 0)
+            self.end = (int(rng.integers(0, g)), g - 1)
+        else:
+            self.start = (int(rng.integers(0, g)), g - 1)
+            self.end = (int(rng.integers(0, g)), 0)
+        self.path, self.walls = generate_mystery_path(rng, g, self.start, self.end)
+        self.visited = set()
+        self.sprites = assets.agent_sprites(p["agent_scale"])
+        self.radius = int(25 * p["agent_scale"])
+        self.rotation = 0
+        self.cx = int(self.start[0] * self.TILE + self.radius)
+        self.cy = int(self.start[1] * self.TILE + self.radius)
+        self.off_path = False
+        self.num_fails = 0
+        self.cross_alpha = 0
+        self.cross_x = self.cross_y = 0  # fall_off_rect top-left
+        return self._render(cross=False), {}
+
+    def step(self, action):
+        p = self.p
+        reward = 0
+        done = False
+        success = 0
+        screen = (0, 0, SCREEN, SCREEN)
+        if not self.off_path:
+            self.cx, self.cy, self.rotation = move_clamped(
+                self.cx, self.cy, self.rotation, action, p["agent_speed"], self.radius, screen)
+        else:
+            self.cx = int(self.start[0] * self.TILE + self.radius)
+            self.cy = int(self.start[1] * self.TILE + self.radius)
+            self.cx, self.cy, self.rotation = move_clamped(
+                self.cx, self.cy, self.rotation, (0, 0), p["agent_speed"], self.radius, screen)
+        pos = (self.cx // self.TILE, self.cy // self.TILE)
+        if pos == self.end:
+            reward += p["reward_goal"]
+            done = True
+            success = 1
+        else:
+            on_path = False
+            for node in self.path:
+                if pos == node:
+                    on_path = True
+                    if node not in self.visited and node != self.start and node != self.end:
+                        reward += p["reward_path_progress"]
+                        self.visited.add(node)
+                    break
+            if not on_path:
+                reward += p["reward_fall_off"]
+                self.num_fails += 1
+                if p["visual_feedback"]:
+                    self.cross_alpha = 255
+                self.off_path = True
+            else:
+                self.cross_alpha = 0
+                self.off_path = False
+            cross = assets.fall_off_cross(SCALE)
+            self.cross_x, self.cross_y = self.cx - (cross.w >> 1), self.cy - (cross.h >> 1)
+        reward += p["reward_step"]
+        self.t += 1
+        if self.t == self.max_episode_steps:
+            done = True
+        self.rewards.append(reward)
+        info = {}
+        if done:
+            info = {"reward": _seq_sum(self.rewards), "length": len(self.rewards), "success": success,
+                    "num_fails": self.num_fails}
+        return self._render(cross=True), reward, done, False, info
+
+    def _render(self, cross):
+        frame = np.zeros((SCREEN, SCREEN), dtype=np.uint32)
+        t = int(self.TILE)
+        # MysteryPath.draw_to_surface (pygame_assets.py:749-758): path[0] is the goal, path[-1] the origin
+        last = len(self.path) - 1
+        for k, (i, j) in enumerate(self.path):
+            if k == 0 and self.p["show_goal"]:
+                frame[j * t:(j + 1) * t, i * t:(i + 1) * t] = R.map_rgb((0, 255, 0))
+            elif k == last and self.p["show_origin"]:
+                frame[j * t:(j + 1) * t, i * t:(i + 1) * t] = R.map_rgb((0, 0, 255))
+        sp = self.sprites[self.rotation // 45]
+        _paste(frame, sp, self.cx - (sp.w >> 1), self.cy - (sp.h >> 1))
+        if cross and self.cross_alpha == 255:
+            _paste(frame, assets.fall_off_cross(SCALE), self.cross_x, self.cross_y)
+        return _frame_to_obs(frame)
+
+
+ORACLES = {
+    "MortarMayhem-v0": MortarMayhemOracle,
+    "MortarMayhem-Grid-v0": GridMortarMayhemOracle,
+    "Endless-MortarMayhem-v0": EndlessMortarMayhemOracle,
+    "MysteryPath-v0": MysteryPathOracle,
+}
+
+
+def make(env_id):
+    return ORACLES[env_id]()
