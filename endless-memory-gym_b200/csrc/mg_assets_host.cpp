@@ -1,0 +1,231 @@
+// mg_assets_host.cpp — builds the static drawable assets of Memory Gym into one flat blob.
+//
+// What the reference rebuilds with pygame on every reset (agent sprites, character_controller.py:29-75;
+// 25 MortarTile surfaces, pygame_assets.py:316-343) or on every show-phase step (Command icon,
+// pygame_assets.py:254-304) is drawn here ONCE per option set with the raster of mg_raster_host.cpp
+// and stored as sparse opaque-pixel lists + full-frame background templates. The kernels only copy.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/memgym_b200.h"
+#include "mg_common.h"
+#include "mg_raster_host.h"
+
+using mgr::Surface;
+
+static const double SCALE = 0.25;  // mortar_mayhem.py:13 (every env module uses the same constant)
+
+namespace {
+
+struct Builder {
+    MgAssetHeader hdr;
+    std::vector<uint32_t> entries;
+    std::vector<std::vector<uint8_t>> templates;
+    int n_pal = 0;
+
+    Builder() {
+        memset(&hdr, 0, sizeof(hdr));
+        static const int fixed[][3] = {{0, 0, 0},    {250, 204, 153}, {250, 250, 250}, {50, 50, 50},
+                                       {255, 255, 255}, {255, 0, 0},     {55, 55, 55},    {48, 141, 70},
+                                       {255, 165, 0},   {0, 0, 255},     {0, 255, 0}};
+        for (auto& c : fixed) {
+            hdr.palette[n_pal][0] = (uint8_t)c[0];
+            hdr.palette[n_pal][1] = (uint8_t)c[1];
+            hdr.palette[n_pal][2] = (uint8_t)c[2];
+            n_pal++;
+        }
+    }
+
+    int pal_index(uint32_t px) {
+        uint8_t r = (px >> 16) & 255, g = (px >> 8) & 255, b = px & 255;
+        for (int i = 0; i < n_pal; ++i)
+            if (hdr.palette[i][0] == r && hdr.palette[i][1] == g && hdr.palette[i][2] == b) return i;
+        if (n_pal >= MG_MAX_PALETTE) return -1;
+        hdr.palette[n_pal][0] = r;
+        hdr.palette[n_pal][1] = g;
+        hdr.palette[n_pal][2] = b;
+        return n_pal++;
+    }
+
+    // opaque pixels of `s` (everything != colour key), column-major so neighbouring lanes of a warp
+    // touch neighbouring bytes of the [x][y][c] frame
+    bool add_sprite(int slot, const Surface& s) {
+        if (s.w > 255 || s.h > 255) return false;
+        MgSprite& sp = hdr.sprite[slot];
+        sp.first = (uint32_t)entries.size();
+        sp.w = (uint8_t)s.w;
+        sp.h = (uint8_t)s.h;
+        uint32_t cnt = 0;
+        for (int x = 0; x < s.w; ++x)
+            for (int y = 0; y < s.h; ++y) {
+                uint32_t v = s.at(x, y);
+                if (s.has_key && v == s.key) continue;
+                int pi = pal_index(v);
+                if (pi < 0) return false;
+                entries.push_back((uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)pi << 16));
+                cnt++;
+            }
+        if (cnt > 65535) return false;
+        sp.count = (uint16_t)cnt;
+        return true;
+    }
+
+    void add_template(int slot, const Surface& s) {
+        // pygame.surfarray.array3d layout: [x][y][c]
+        std::vector<uint8_t> t((size_t)MG_FRAME_BYTES);
+        for (int x = 0; x < MG_W; ++x)
+            for (int y = 0; y < MG_W; ++y) {
+                uint32_t v = s.at(x, y);
+                uint8_t* o = &t[((size_t)x * MG_W + y) * 3];
+                o[0] = (v >> 16) & 255;
+                o[1] = (v >> 8) & 255;
+                o[2] = v & 255;
+            }
+        if ((int)templates.size() <= slot) templates.resize(slot + 1);
+        templates[slot] = t;
+    }
+
+    long serialize(void* out, size_t cap) {
+        size_t off = (sizeof(MgAssetHeader) + 15) & ~(size_t)15;
+        hdr.magic = MG_ASSET_MAGIC;
+        hdr.entries_off = (uint32_t)off;
+        hdr.n_entries = (uint32_t)entries.size();
+        off += entries.size() * 4;
+        off = (off + 127) & ~(size_t)127;
+        for (size_t i = 0; i < templates.size() && i < 4; ++i) {
+            if (templates[i].empty()) continue;
+            hdr.tmpl_off[i] = (uint32_t)off;
+            off += MG_FRAME_BYTES;
+            off = (off + 127) & ~(size_t)127;
+        }
+        hdr.total_bytes = (uint32_t)off;
+        if (!out || cap < off) return (long)off;  // size query / too small: caller re-allocates
+        memset(out, 0, off);
+        memcpy(out, &hdr, sizeof(hdr));
+        memcpy((char*)out + hdr.entries_off, entries.data(), entries.size() * 4);
+        for (size_t i = 0; i < templates.size() && i < 4; ++i)
+            if (!templates[i].empty()) memcpy((char*)out + hdr.tmpl_off[i], templates[i].data(), MG_FRAME_BYTES);
+        return (long)off;
+    }
+};
+
+// character_controller.py:29-75 (create_character_sprites)
+bool build_agent(Builder& b, double scale, bool legacy) {
+    int radius = (int)(25 * scale), hands_x = (int)(18 * scale), hand_y = (int)(12 * scale);
+    int hand_r = (int)(10 * scale), outline = (int)(3 * scale), ext = 14;
+    int dim = radius * 2 + hand_r + ext;
+    if (dim < 1 || dim > 255) return false;
+    int c = dim / 2;
+    int lx0 = dim / 2 - hands_x, ly0 = hand_y + ext / 2, rx0 = dim / 2 + hands_x, ry0 = ly0;
+    int k = 0;
+    for (int ang = 360; ang > 0; ang -= 45, ++k) {
+        Surface s(dim, dim);
+        mgr::fill(s, 255);
+        s.has_key = true;
+        s.key = 255;
+        mgr::circle(s, mgr::rgb(250, 204, 153), c, c, radius, 0, legacy);
+        double lx, ly, rx, ry;
+        mgr::vec_rotate((double)(lx0 - c), (double)(ly0 - c), (double)ang, &lx, &ly);
+        mgr::vec_rotate((double)(rx0 - c), (double)(ry0 - c), (double)ang, &rx, &ry);
+        int lpx = (int)(lx + c), lpy = (int)(ly + c), rpx = (int)(rx + c), rpy = (int)(ry + c);
+        mgr::circle(s, mgr::rgb(250, 250, 250), lpx, lpy, hand_r, 0, legacy);
+        mgr::circle(s, mgr::rgb(250, 250, 250), rpx, rpy, hand_r, 0, legacy);
+        mgr::circle(s, mgr::rgb(50, 50, 50), lpx, lpy, hand_r, outline, legacy);
+        mgr::circle(s, mgr::rgb(50, 50, 50), rpx, rpy, hand_r, outline, legacy);
+        if (!b.add_sprite(MG_SPR_AGENT0 + k, s)) return false;
+    }
+    b.hdr.agent_dim = dim;
+    b.hdr.agent_radius = radius;
+    return true;
+}
+
+// pygame_assets.py:254-304 (Command.__init__), always built at SCALE
+bool build_icons(Builder& b, bool legacy) {
+    static const int angles[9] = {0, 270, 180, 90, -1, 315, 45, 225, 135};  // COMMANDS order; -1 = stay
+    double dim = 88 * SCALE;
+    int lw = (int)(8 * SCALE);
+    uint32_t white = mgr::rgb(255, 255, 255);
+    for (int k = 0; k < 9; ++k) {
+        Surface s((int)dim, (int)dim);
+        s.has_key = true;
+        s.key = 0;
+        if (angles[k] < 0) {
+            double radius = floor(dim / 2) - 4 * SCALE;
+            double x = dim - 12 * SCALE, y = floor(dim / 2) - 8 * SCALE;
+            mgr::circle(s, white, (int)radius, (int)radius, (int)radius, lw, legacy);
+            mgr::line(s, white, 0, (int)y, (int)x, (int)y, lw);
+            if (!b.add_sprite(MG_SPR_ICON0 + k, s)) return false;
+        } else {
+            double x1 = 2 * SCALE, x2 = 80 * SCALE, y1 = 40 * SCALE, y2 = 0;
+            mgr::line(s, white, (int)x1, (int)y1, (int)x2, (int)y1, lw);
+            mgr::line(s, white, (int)x2, (int)y1, (int)y1, (int)y2, lw);
+            mgr::line(s, white, (int)x2, (int)y1, (int)y1, (int)x2, lw);
+            Surface r = mgr::rotate(s, (double)angles[k]);
+            if (!b.add_sprite(MG_SPR_ICON0 + k, r)) return false;
+        }
+    }
+    // mortar_mayhem.py:363: blit at screen_dim // 2 - command.rect_dim // 2 (un-rotated size)
+    b.hdr.icon_x = b.hdr.icon_y = (int)(MG_W / 2 - floor(dim / 2));
+    return true;
+}
+
+// mystery_path.py:175-182
+bool build_cross(Builder& b) {
+    double dim = 40 * SCALE;
+    Surface s((int)dim, (int)dim);
+    s.has_key = true;
+    s.key = 0;
+    int d = (int)(dim - 1), lw = (int)(12 * SCALE);
+    mgr::line(s, mgr::rgb(255, 0, 0), 0, 0, d, d, lw);
+    mgr::line(s, mgr::rgb(255, 0, 0), d, 0, 0, d, lw);
+    return b.add_sprite(MG_SPR_CROSS, s);
+}
+
+// MortarArena drawn onto the 84x84 screen: pygame_assets.py:306-418 + mortar_mayhem.py:93-103
+void build_arena(Builder& b, int slot, int size, bool red) {
+    Surface scr(MG_W, MG_W);
+    int tile = (int)(56 * SCALE);
+    int dim = (int)(56 * SCALE * size);
+    int origin = MG_W / 2 - (dim >> 1);
+    uint32_t fillc = red ? mgr::rgb(81, 18, 26) : mgr::rgb(21, 43, 77);
+    uint32_t edge = red ? mgr::rgb(112, 24, 36) : mgr::rgb(29, 60, 107);
+    Surface t(tile, tile);
+    mgr::rect(t, fillc, 0, 0, tile, tile, 0, 0, -1, -1, -1, -1);
+    mgr::rect(t, edge, 0, 0, tile, tile, (int)(4 * SCALE), 0, -1, -1, -1, -1);
+    for (int i = 0; i < size; ++i)
+        for (int j = 0; j < size; ++j)
+            for (int y = 0; y < tile; ++y)
+                for (int x = 0; x < tile; ++x) {
+                    int X = origin + tile * i + x, Y = origin + tile * j + y;
+                    if (X >= 0 && X < MG_W && Y >= 0 && Y < MG_W) scr.at(X, Y) = t.at(x, y);
+                }
+    b.add_template(slot, scr);
+}
+
+}  // namespace
+
+extern "C" long mg_mm_build_assets(const mg_mm_params* p, int thick_circle_legacy, void* host_out, size_t capacity) {
+    if (!p) return MG_EINVAL;
+    int size = p->variant == MG_MM_ENDLESS ? 6 : p->arena_size;
+    if (size < 2 || size > 6) return MG_EINVAL;
+    Builder b;
+    // GridCharacterController is built with SCALE, ignoring agent_scale (mortar_mayhem_grid.py:249)
+    double agent_scale = p->variant == MG_MM_GRID ? SCALE : p->agent_scale;
+    if (!build_agent(b, agent_scale, thick_circle_legacy != 0)) return MG_EINVAL;
+    if (!build_icons(b, thick_circle_legacy != 0)) return MG_EINVAL;
+    build_arena(b, 0, size, false);
+    build_arena(b, 1, size, true);
+    return b.serialize(host_out, capacity);
+}
+
+extern "C" long mg_mp_build_assets(const mg_mp_params* p, void* host_out, size_t capacity) {
+    if (!p) return MG_EINVAL;
+    Builder b;
+    if (!build_agent(b, p->agent_scale, false)) return MG_EINVAL;
+    if (!build_cross(b)) return MG_EINVAL;
+    Surface black(MG_W, MG_W);
+    b.add_template(0, black);
+    return b.serialize(host_out, capacity);
+}

@@ -1,0 +1,147 @@
+// mg_common.h — layouts shared by the host asset builder, the env logic and the CUDA kernels.
+//
+// Everything here is plain data: the asset blob (sparse sprite pixel lists + background frame
+// templates) and the per-env state records that live in HBM as an array of fixed-size records
+// (one warp owns one env, so one record = one or two fully-coalesced 128-byte lines).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MG_HD __host__ __device__ __forceinline__
+#else
+#define MG_HD inline
+#endif
+
+#define MG_W 84                       // screen: int(336 * 0.25), mortar_mayhem.py:13,73
+#define MG_COL_BYTES (MG_W * 3)       // one x-column of the [x][y][c] frame = 252 contiguous bytes
+#define MG_FRAME_BYTES (MG_W * MG_W * 3)  // 21168 = 1323 * 16
+#define MG_FRAME_VEC16 (MG_FRAME_BYTES / 16)
+
+#define MG_ASSET_MAGIC 0x4d474131u  // "MGA1"
+#define MG_MAX_PALETTE 32
+
+// palette slots (RGB) used by the sprite lists; filled by the host builder
+enum {
+    MG_PAL_BLACK = 0,
+    MG_PAL_BODY = 1,      // (250,204,153) character_controller.py:58
+    MG_PAL_HAND = 2,      // (250,250,250)
+    MG_PAL_HAND_OUT = 3,  // (50,50,50)
+    MG_PAL_WHITE = 4,     // command icons
+    MG_PAL_RED = 5,       // fall-off cross (255,0,0)
+    MG_PAL_EXIT_CLOSED = 6,
+    MG_PAL_EXIT_OPEN = 7,
+    MG_PAL_COIN = 8,      // (255,165,0)
+    MG_PAL_BLUE = 9,      // (0,0,255) raw pixel 255
+    MG_PAL_GREEN = 10,    // (0,255,0)
+};
+
+// sprite = list of opaque pixels relative to the sprite's top-left: dx | dy<<8 | palette<<16
+struct MgSprite {
+    uint32_t first;  // index of the first entry in the blob's entry array
+    uint16_t count;
+    uint8_t w, h;
+};
+
+enum {
+    MG_SPR_AGENT0 = 0,   // 8 agent rotations (index = rotation // 45)
+    MG_SPR_ICON0 = 8,    // 9 command icons in Command.COMMANDS order (pygame_assets.py:242-252)
+    MG_SPR_CROSS = 17,   // mystery_path.py:175-182
+    MG_SPR_EXIT_CLOSED = 18,
+    MG_SPR_EXIT_OPEN = 19,
+    MG_SPR_COIN = 20,
+    MG_SPR_COUNT = 24
+};
+
+#define MG_MAX_DISC_R 40  // spotlight / coin disc tables (filled circle row spans)
+
+struct MgAssetHeader {
+    uint32_t magic;
+    uint32_t total_bytes;
+    uint32_t entries_off;  // byte offset of the uint32 entry array
+    uint32_t n_entries;
+    uint32_t tmpl_off[4];  // byte offsets (16-aligned) of up to 4 full-frame templates, 0 = absent
+    int32_t agent_dim;     // sprite side; blit top-left = centre - (dim >> 1)
+    int32_t agent_radius;  // int(25 * agent_scale)
+    int32_t icon_x, icon_y;  // command blit position (mortar_mayhem.py:363)
+    int32_t disc_off;      // byte offset of int8 disc tables: for r in 0..MG_MAX_DISC_R, 2*r rows of (xmin,xmax)
+    int32_t reserved[3];
+    MgSprite sprite[MG_SPR_COUNT];
+    uint8_t palette[MG_MAX_PALETTE][4];
+};
+
+// ---- PCG64 stream state (numpy.random.PCG64 + the bit generator's 32-bit buffer) ----------------
+struct MgRng {
+    uint64_t state_lo, state_hi;
+    uint64_t inc_lo, inc_hi;
+    uint32_t buf;      // uinteger
+    uint32_t has_buf;  // has_uint32
+};  // 40 bytes
+
+// ---- Mortar Mayhem family record (256 bytes) --------------------------------------------------
+#define MG_MM_MAXCMD 152
+struct MgMMState {
+    MgRng rng;             // 40
+    double ep_reward;      // left-to-right sum of step rewards
+    int32_t ep_len;
+    int32_t t;             // Endless: steps since reset
+    int32_t total_completed;  // Endless
+    int16_t cx, cy;        // agent.rect.center
+    int16_t draw_cx, draw_cy;  // Endless: pose of the last sprite handle (stale across resets)
+    uint8_t rot;           // rotation // 45
+    uint8_t draw_rot;
+    uint8_t has_draw;      // Endless: a sprite handle exists
+    uint8_t tiles_on;
+    int8_t gx, gy;         // Grid: agent.grid_position
+    int8_t tx, ty;         // _target_pos
+    int8_t px, py;         // normalized agent position at the last act step / reset
+    uint16_t n;            // len(_commands)
+    uint16_t cc;           // _current_command
+    uint16_t cs;           // _command_steps
+    uint16_t cv;           // _command_verify_step
+    uint16_t D, E;         // _explosion_delay, _explosion_duration
+    uint16_t show_pos, show_len;  // cursor into / length of the command visualisation queue
+    uint16_t show_dur, show_delay;
+    uint16_t show_base;    // index of the first command the queue shows
+    uint8_t live;          // an episode is running (0 after make() and after an un-reset done)
+    uint8_t pad[1];
+    uint8_t commands[MG_MM_MAXCMD];
+};
+
+// ---- Mystery Path record (128 bytes) -----------------------------------------------------------
+struct MgMPState {
+    MgRng rng;             // 40
+    double ep_reward;
+    int32_t ep_len;
+    int32_t t;
+    int32_t num_fails;
+    int16_t cx, cy;
+    int16_t cross_x, cross_y;  // fall_off_rect top-left
+    uint64_t path_mask;    // bit (i*7+j): node on the path
+    uint64_t visited;      // reward_visited
+    uint8_t rot;
+    uint8_t sx, sy, ex, ey;
+    uint8_t off_path;
+    uint8_t cross_on;      // fall_off_surface alpha == 255
+    uint8_t live;
+    uint8_t pad[32];
+};
+
+// frame description produced by the env logic and consumed by the rasteriser (MM family)
+struct MgMMFrame {
+    int red;        // tiles reddened (tiles_on && visual_feedback)
+    int tx, ty;     // the one tile that stays blue
+    int sx, sy;     // sprite centre
+    int srot;       // sprite index
+    int icon;       // -2: no command layer, -1: blank, 0..8 icon
+};
+
+struct MgMPFrame {
+    int sx, sy, srot;
+    int cross;      // draw the cross
+    int cross_x, cross_y;
+};
+
+static_assert(sizeof(MgRng) == 40, "MgRng layout");
+static_assert(sizeof(MgMMState) == 256, "MgMMState must be 256 bytes (MG_MM_STATE_BYTES)");
+static_assert(sizeof(MgMPState) == 128, "MgMPState must be 128 bytes (MG_MP_STATE_BYTES)");
+static_assert(sizeof(MgAssetHeader) % 8 == 0, "MgAssetHeader alignment");

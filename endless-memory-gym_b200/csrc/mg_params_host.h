@@ -1,0 +1,8 @@
+// mg_params_host.h — host-only: option validation and the kernel parameter blocks derived from them.
+#pragma once
+#include "mg_mm_logic.h"
+#include "mg_mp_logic.h"
+
+void mg_set_err(const char* msg);
+void mg_mm_derive(const mg_mm_params* p, MgMMK* k);
+void mg_mp_derive(const mg_mp_params* p, MgMPK* k);

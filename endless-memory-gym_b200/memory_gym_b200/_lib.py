@@ -1,0 +1,133 @@
+"""ctypes binding of ``libmemgym_b200.so`` (C ABI declared in ``include/memgym_b200.h``).
+
+The library is the product: every reset/step goes through it and there is no Python or CPU
+fallback — if the shared object is missing, or no CUDA device is usable, calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmemgym_b200.so")
+
+MG_ABI_VERSION = 1
+MG_OBS_BYTES = 84 * 84 * 3
+MG_INFO_COLS = 8
+MG_MAX_CHOICES = 16
+MG_MM_MAX_COMMANDS = 152
+MG_MM_STATE_BYTES = 256
+MG_MP_STATE_BYTES = 128
+MG_SS_STATE_BYTES = 2048
+MG_FLAG_AUTORESET = 1
+MG_MM_CONTINUOUS, MG_MM_GRID, MG_MM_ENDLESS = 0, 1, 2
+(MG_INFO_REWARD, MG_INFO_LENGTH, MG_INFO_SUCCESS, MG_INFO_A, MG_INFO_B, MG_INFO_GT0, MG_INFO_GT1) = range(7)
+
+
+class ChoiceList(C.Structure):
+    _fields_ = [("n", C.c_int32), ("v", C.c_int32 * MG_MAX_CHOICES)]
+
+    @classmethod
+    def of(cls, values):
+        values = [int(v) for v in values]
+        if not 1 <= len(values) <= MG_MAX_CHOICES:
+            raise ValueError(f"list-valued reset option must have 1..{MG_MAX_CHOICES} entries, got {len(values)}")
+        out = cls()
+        out.n = len(values)
+        for i, v in enumerate(values):
+            out.v[i] = v
+        return out
+
+
+class MMParams(C.Structure):
+    _fields_ = [
+        ("variant", C.c_int32), ("arena_size", C.c_int32), ("allowed_commands", C.c_int32),
+        ("visual_feedback", C.c_int32), ("max_steps", C.c_int32), ("initial_command_count", C.c_int32),
+        ("command_count", ChoiceList), ("command_show_duration", ChoiceList), ("command_show_delay", ChoiceList),
+        ("explosion_duration", ChoiceList), ("explosion_delay", ChoiceList),
+        ("agent_scale", C.c_double), ("agent_speed", C.c_double), ("reward_command_failure", C.c_double),
+        ("reward_command_success", C.c_double), ("reward_episode_success", C.c_double),
+    ]
+
+
+class MPParams(C.Structure):
+    _fields_ = [
+        ("max_steps", C.c_int32), ("show_origin", C.c_int32), ("show_goal", C.c_int32),
+        ("visual_feedback", C.c_int32), ("cardinal_origin_choice", ChoiceList),
+        ("agent_scale", C.c_double), ("agent_speed", C.c_double), ("reward_goal", C.c_double),
+        ("reward_fall_off", C.c_double), ("reward_path_progress", C.c_double), ("reward_step", C.c_double),
+    ]
+
+
+class SSParams(C.Structure):
+    _fields_ = [
+        ("max_steps", C.c_int32), ("initial_spawns", C.c_int32), ("num_spawns", C.c_int32),
+        ("visual_feedback", C.c_int32), ("black_background", C.c_int32), ("hide_chessboard", C.c_int32),
+        ("light_dim_off_duration", C.c_int32), ("light_threshold", C.c_int32), ("coins_visible", C.c_int32),
+        ("use_exit", C.c_int32), ("exit_visible", C.c_int32), ("agent_visible", C.c_int32),
+        ("sample_agent_position", C.c_int32), ("show_last_action", C.c_int32),
+        ("show_last_positive_reward", C.c_int32), ("pad0", C.c_int32), ("num_coins", ChoiceList),
+        ("initial_spawn_interval", C.c_double), ("spawn_interval_threshold", C.c_double),
+        ("spawn_interval_decay", C.c_double), ("spot_min_radius", C.c_double), ("spot_max_radius", C.c_double),
+        ("spot_min_speed", C.c_double), ("spot_max_speed", C.c_double), ("spot_damage", C.c_double),
+        ("coin_scale", C.c_double), ("exit_scale", C.c_double), ("agent_speed", C.c_double),
+        ("agent_health", C.c_double), ("agent_scale", C.c_double), ("reward_inside_spotlight", C.c_double),
+        ("reward_outside_spotlight", C.c_double), ("reward_death", C.c_double), ("reward_exit", C.c_double),
+        ("reward_max_steps", C.c_double), ("reward_coin", C.c_double),
+    ]
+
+
+class StepIO(C.Structure):
+    _fields_ = [
+        ("actions", C.c_void_p), ("obs", C.c_void_p), ("final_obs", C.c_void_p), ("reward", C.c_void_p),
+        ("done", C.c_void_p), ("info", C.c_void_p), ("ground_truth", C.c_void_p), ("reset_mask", C.c_void_p),
+        ("flags", C.c_uint32), ("warps_per_cta", C.c_uint32),
+    ]
+
+
+class MemGymError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once. Missing library = hard error (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MemGymError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C endless-memory-gym_b200/csrc`. memory_gym_b200 has no CPU / Python fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u64p = C.c_void_p, C.c_int, C.POINTER(C.c_uint64)
+    L.mg_abi_version.restype = i32
+    L.mg_last_error.restype = C.c_char_p
+    L.mg_device_info.argtypes = [C.POINTER(i32)] * 3 + [C.POINTER(C.c_size_t)]
+    L.mg_seed_pcg64.argtypes = [vp, i32, vp]
+    L.mg_selftest_pcg64_host.argtypes = [vp, vp, vp, vp, i32, vp, vp]
+    for fam, P in (("mm", MMParams), ("mp", MPParams), ("ss", SSParams)):
+        getattr(L, f"mg_{fam}_check_params").argtypes = [C.POINTER(P)]
+        getattr(L, f"mg_{fam}_reset").argtypes = [C.POINTER(P), vp, vp, vp, C.POINTER(StepIO), i32, vp]
+        getattr(L, f"mg_{fam}_step").argtypes = [C.POINTER(P), vp, vp, C.POINTER(StepIO), i32, vp]
+        b = getattr(L, f"mg_{fam}_build_assets")
+        b.restype = C.c_long
+        b.argtypes = [C.POINTER(P), i32, vp, C.c_size_t] if fam == "mm" else [C.POINTER(P), vp, C.c_size_t]
+    if L.mg_abi_version() != MG_ABI_VERSION:
+        raise MemGymError(f"ABI mismatch: library {L.mg_abi_version()}, binding {MG_ABI_VERSION}")
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return lib().mg_last_error().decode()
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    if rc < 0:
+        raise MemGymError(f"{what}: {last_error()} (code {rc})")
+    raise MemGymError(f"{what}: CUDA error {rc}: {last_error()}")

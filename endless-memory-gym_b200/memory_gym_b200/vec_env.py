@@ -1,0 +1,294 @@
+"""Batched Memory-Gym environments: the reference's gymnasium surface with a leading batch dim.
+
+``MemoryGymVecEnv`` mirrors the reference env classes (``reset(seed=, options=)`` /
+``step(action)`` / ``action_space`` / ``observation_space`` / ``default_reset_parameters`` /
+``process_reset_params`` / ``has_ground_truth_info`` / ``max_episode_steps`` / ``render`` / ``close``,
+e.g. ``memory_gym/mortar_mayhem.py:56-91,206-272,274-369``) for N parallel instances whose state
+lives in HBM. Every reset/step is ONE kernel launch through the C ABI of ``libmemgym_b200.so``;
+PyTorch only provides device memory and the CUDA stream. There is no CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import spaces
+from .specs import spec as _spec
+
+
+class _CudaBackend:
+    """The product path: ctypes calls into libmemgym_b200.so on the caller's current CUDA stream."""
+
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = L.lib()
+
+    def check_device(self, device):
+        if device.type != "cuda":
+            raise L.MemGymError(f"memory_gym_b200 runs on CUDA devices only (got device={device}); there is no CPU path")
+        if not torch.cuda.is_available():
+            raise L.MemGymError("no CUDA device available; memory_gym_b200 has no CPU fallback")
+
+    def stream(self, device):
+        return torch.cuda.current_stream(device).cuda_stream
+
+    def build_assets(self, family, params):
+        fn = getattr(self.lib, f"mg_{family}_build_assets")
+        args = (C.byref(params), 0) if family == "mm" else (C.byref(params),)
+        size = fn(*args, None, 0)
+        if size < 0:
+            raise L.MemGymError(f"mg_{family}_build_assets: {L.last_error()}")
+        buf = np.zeros(size, dtype=np.uint8)
+        got = fn(*args, buf.ctypes.data, size)
+        if got != size:
+            raise L.MemGymError(f"mg_{family}_build_assets: size changed {size} -> {got}")
+        return buf
+
+    def seed(self, seeds):
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        out = np.empty((seeds.shape[0], 4), dtype=np.uint64)
+        L.check(self.lib.mg_seed_pcg64(seeds.ctypes.data, seeds.shape[0], out.ctypes.data), "mg_seed_pcg64")
+        return out
+
+    def check_params(self, family, params):
+        L.check(getattr(self.lib, f"mg_{family}_check_params")(C.byref(params)), f"mg_{family}_check_params")
+
+    def reset(self, family, params, assets, state, rng4, io, n, stream):
+        L.check(getattr(self.lib, f"mg_{family}_reset")(C.byref(params), assets, state, rng4, C.byref(io), n, stream),
+                f"mg_{family}_reset")
+
+    def step(self, family, params, assets, state, io, n, stream):
+        L.check(getattr(self.lib, f"mg_{family}_step")(C.byref(params), assets, state, C.byref(io), n, stream),
+                f"mg_{family}_step")
+
+
+class MemoryGymVecEnv:
+    """N parallel instances of one Memory-Gym env id.
+
+    * ``reset(seed=None|int|sequence, options=None|dict) -> (obs uint8[N,84,84,3], info)``: an int
+      seed seeds env ``i`` with ``seed + env_offset + i``; ``None`` continues every env's stream
+      (first use: OS entropy), exactly like ``env.reset()`` in gymnasium 0.29.
+    * ``step(actions int64[N,2] | int64[N]) -> (obs, reward float64[N], done bool[N], truncated bool[N], info)``.
+      With ``auto_reset`` (default) finished envs are reset inside the same launch: ``obs`` is the new
+      episode's first frame, the terminal frame is in ``info["final_observation"]`` (if ``final_obs``)
+      and the episode statistics in ``info[<key>]`` (valid where ``done``).
+    Returned tensors are views of persistent device buffers that the next call overwrites.
+    Observation layout per env is pygame's ``surfarray.array3d``: ``[x][y][c]``.
+    """
+
+    metadata = {"render_modes": ["rgb_array"], "render_fps": 25}
+
+    def __init__(self, env_id, num_envs=1, device="cuda", auto_reset=True, final_obs=False, env_offset=0,
+                 warps_per_cta=0, _backend=None):
+        self.spec_ = _spec(env_id)
+        self.env_id = env_id
+        self.num_envs = int(num_envs)
+        if self.num_envs < 1:
+            raise ValueError("num_envs must be >= 1")
+        self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None and torch.cuda.is_available():
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._be = _backend if _backend is not None else _CudaBackend()
+        self._be.check_device(self.device)
+        self.auto_reset = bool(auto_reset)
+        self.env_offset = int(env_offset)
+        self.warps_per_cta = int(warps_per_cta)
+        self.default_reset_parameters = self.spec_.default_reset_parameters
+        self.has_ground_truth_info = self.spec_.has_ground_truth_info
+        nvec = self.spec_.action_nvec
+        self.single_action_space = spaces.Discrete(nvec[0]) if len(nvec) == 1 else spaces.MultiDiscrete(nvec)
+        self.single_observation_space = spaces.Box(low=0, high=255, shape=(84, 84, 3), dtype=np.uint8)
+        self.action_space, self.observation_space = self.single_action_space, self.single_observation_space
+        if self.has_ground_truth_info:
+            self.ground_truth_space = spaces.Box(low=0.0, high=1.0, shape=(2,), dtype=np.float32)
+        n, dev = self.num_envs, self.device
+        self.state = torch.zeros((n, self.spec_.state_bytes), dtype=torch.uint8, device=dev)
+        self.obs = torch.zeros((n, 84, 84, 3), dtype=torch.uint8, device=dev)
+        self.final_obs = torch.zeros((n, 84, 84, 3), dtype=torch.uint8, device=dev) if final_obs else None
+        self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.truncated = torch.zeros(n, dtype=torch.bool, device=dev)
+        self.info = torch.zeros((n, L.MG_INFO_COLS), dtype=torch.float64, device=dev)
+        self.ground_truth = torch.zeros((n, 2), dtype=torch.float64, device=dev) if self.has_ground_truth_info else None
+        self._actions_dev = torch.zeros((n, len(nvec)) if len(nvec) > 1 else (n,), dtype=torch.int64, device=dev)
+        self._io = L.StepIO()
+        self._io.obs = self.obs.data_ptr()
+        self._io.final_obs = self.final_obs.data_ptr() if final_obs else None
+        self._io.reward = self.reward.data_ptr()
+        self._io.done = self.done.data_ptr()
+        self._io.info = self.info.data_ptr()
+        self._io.ground_truth = self.ground_truth.data_ptr() if self.has_ground_truth_info else None
+        self._io.flags = L.MG_FLAG_AUTORESET if self.auto_reset else 0
+        self._io.warps_per_cta = self.warps_per_cta
+        self.reset_params = None
+        self._params = None
+        self._params_key = None
+        self._assets = None
+        self._seeded = False
+        self.max_episode_steps = None
+
+    # ---- reference-compatible helpers ----------------------------------------------------------------
+    def process_reset_params(self, reset_params):
+        return self.spec_.process_reset_params(reset_params)
+
+    def _set_options(self, options):
+        p = self.spec_.process_reset_params(options)
+        key = repr(sorted(p.items()))
+        if key != self._params_key:
+            params = self.spec_.to_struct(p)
+            self._be.check_params(self.spec_.family, params)
+            blob = self._be.build_assets(self.spec_.family, params)
+            # 128-byte aligned device copy (TMA bulk loads read the background templates from it)
+            raw = torch.empty(blob.shape[0] + 128, dtype=torch.uint8, device=self.device)
+            off = (-raw.data_ptr()) % 128
+            self._assets = raw[off:off + blob.shape[0]]
+            self._assets.copy_(torch.from_numpy(blob))
+            self._params, self._params_key = params, key
+        self.reset_params = p
+        self.max_episode_steps = self._max_episode_steps(p)
+
+    def _max_episode_steps(self, p):
+        if self.spec_.family == "mm" and self.spec_.variant != L.MG_MM_ENDLESS:
+            # calc_max_episode_steps (pygame_assets.py:420-436), called with delay/duration swapped
+            # (mortar_mayhem.py:222-226); informational only — the env has no step limit
+            cc, sd, sl = max(p["command_count"]), max(p["command_show_duration"]), max(p["command_show_delay"])
+            ed, el = max(p["explosion_delay"]), max(p["explosion_duration"])
+            return (sd + sl) * cc + (ed + el) * cc - el + 1
+        return p.get("max_steps")
+
+    def _seed_table(self, seed):
+        n = self.num_envs
+        if seed is None:
+            if self._seeded:
+                return None
+            seeds = np.frombuffer(os.urandom(8 * n), dtype=np.uint64)  # gymnasium: OS entropy on first use
+        elif isinstance(seed, (int, np.integer)):
+            seeds = np.uint64(int(seed) + self.env_offset) + np.arange(n, dtype=np.uint64)
+        else:
+            seeds = np.asarray(list(seed), dtype=np.uint64)
+            if seeds.shape != (n,):
+                raise ValueError(f"seed sequence must have {n} entries")
+        return torch.from_numpy(self._be.seed(seeds)).to(self.device)
+
+    # ---- gymnasium surface ---------------------------------------------------------------------------
+    def reset(self, seed=None, return_info=True, options=None, mask=None):
+        """Reset all envs (or those selected by ``mask``, a bool/uint8 tensor of shape [N])."""
+        self._set_options(options)
+        rng4 = self._seed_table(seed)
+        self._seeded = True
+        mask_t = None
+        if mask is not None:
+            mask_t = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+        self._io.reset_mask = mask_t.data_ptr() if mask_t is not None else None
+        self._io.actions = None
+        self._be.reset(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(),
+                       rng4.data_ptr() if rng4 is not None else None, self._io, self.num_envs,
+                       self._be.stream(self.device))
+        self._io.reset_mask = None
+        self._keep = (rng4, mask_t)  # keep the inputs alive until the stream has consumed them
+        info = {}
+        if self.has_ground_truth_info:
+            info["ground_truth"] = self.ground_truth
+        return self.obs, info
+
+    def step(self, actions):
+        if self._params is None:
+            raise L.MemGymError("step() called before reset()")
+        if isinstance(actions, torch.Tensor) and actions.device == self.device and actions.dtype == torch.int64 \
+                and actions.is_contiguous():
+            a = actions
+        else:
+            a = self._actions_dev
+            a.copy_(torch.as_tensor(np.asarray(actions) if not isinstance(actions, torch.Tensor) else actions)
+                    .reshape(a.shape), non_blocking=True)
+        if a.numel() != self._actions_dev.numel():
+            raise ValueError(f"actions must have shape {tuple(self._actions_dev.shape)}")
+        self._io.actions = a.data_ptr()
+        self._be.step(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(), self._io,
+                      self.num_envs, self._be.stream(self.device))
+        done = self.done.view(torch.bool)
+        info = {"episode": self.info, "_episode": done}
+        for k, col in self.spec_.info_keys.items():
+            info[k] = self.info[:, col]
+        if self.final_obs is not None:
+            info["final_observation"] = self.final_obs
+        if self.has_ground_truth_info:
+            info["ground_truth"] = self.ground_truth
+            info["final_ground_truth"] = self.info[:, L.MG_INFO_GT0:L.MG_INFO_GT1 + 1]
+        return self.obs, self.reward, done, self.truncated, info
+
+    def render(self):
+        """``rgb_array`` of the reference (mortar_mayhem.py:396): the observation transposed to [y][x][c]."""
+        return self.obs.permute(0, 2, 1, 3)
+
+    def close(self):
+        self.state = self.obs = self.final_obs = None
+
+    def state_dict(self):
+        """Snapshot of every env's state (PCG64 stream included) — restoring it resumes bit-exactly."""
+        return {"env_id": self.env_id, "state": self.state.clone(), "params": dict(self.reset_params or {}),
+                "obs": self.obs.clone()}
+
+    def load_state_dict(self, sd):
+        if sd["env_id"] != self.env_id or sd["state"].shape != self.state.shape:
+            raise ValueError("state_dict does not match this env")
+        self._set_options(sd["params"] or None)
+        self.state.copy_(sd["state"])
+        self.obs.copy_(sd["obs"])
+        self._seeded = True
+
+
+class MemoryGymEnv:
+    """Single-instance view with the reference's exact call protocol (step until done, then reset):
+    numpy observations, Python float rewards, dict infos. Thin wrapper over ``MemoryGymVecEnv(num_envs=1,
+    auto_reset=False)`` for drop-in use and for the parity tests; throughput comes from the batched class."""
+
+    def __init__(self, env_id, device="cuda", _backend=None):
+        self.vec = MemoryGymVecEnv(env_id, 1, device=device, auto_reset=False, _backend=_backend)
+        self.action_space, self.observation_space = self.vec.action_space, self.vec.observation_space
+        self.default_reset_parameters = self.vec.default_reset_parameters
+        self.has_ground_truth_info = self.vec.has_ground_truth_info
+        if self.has_ground_truth_info:
+            self.ground_truth_space = self.vec.ground_truth_space
+        self.metadata = self.vec.metadata
+
+    @property
+    def max_episode_steps(self):
+        return self.vec.max_episode_steps
+
+    def process_reset_params(self, reset_params):
+        return self.vec.process_reset_params(reset_params)
+
+    def reset(self, seed=None, return_info=True, options=None):
+        obs, info = self.vec.reset(seed=seed, options=options)
+        out = {}
+        if self.has_ground_truth_info:
+            out["ground_truth"] = info["ground_truth"][0].cpu().numpy()
+        return obs[0].cpu().numpy(), out
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.int64).reshape(self.vec._actions_dev.shape)
+        obs, reward, done, trunc, info = self.vec.step(a)
+        d = bool(done[0].item())
+        out = {}
+        if d:
+            row = info["episode"][0].cpu().numpy()
+            for k, col in self.vec.spec_.info_keys.items():
+                out[k] = float(row[col])
+            out["length"] = int(out["length"])
+            if self.has_ground_truth_info:
+                out["ground_truth"] = row[L.MG_INFO_GT0:L.MG_INFO_GT1 + 1].copy()
+        elif self.has_ground_truth_info:
+            out["ground_truth"] = info["ground_truth"][0].cpu().numpy()
+        return obs[0].cpu().numpy(), float(reward[0].item()), d, False, out
+
+    def render(self):
+        return self.vec.render()[0].cpu().numpy()
+
+    def close(self):
+        self.vec.close()

@@ -1,0 +1,227 @@
+/* memgym_b200.h — C ABI of libmemgym_b200.so: batched Memory-Gym reset/step on NVIDIA B200 (sm_100a).
+ *
+ * Drop-in boundary for ONE hot path of MarcoMeter/endless-memory-gym: `env.reset()` / `env.step()`
+ * of N independent environment instances, producing uint8 observations [N][84][84][3] (pygame
+ * `surfarray.array3d` layout, i.e. [x][y][c]), rewards, dones and episode statistics.
+ * The reference has no FFI (it is pure Python on pygame); each entry point below names the
+ * reference interface it replaces (paths relative to the reference checkout):
+ *
+ *   mg_mm_reset / mg_mm_step   <-  MortarMayhemEnv.reset/step          memory_gym/mortar_mayhem.py:206-272, 274-369
+ *                                  GridMortarMayhemEnv.reset/step      memory_gym/mortar_mayhem_grid.py:213-278, 280-375
+ *                                  EndlessMortarMayhemEnv.reset/step   memory_gym/endless_mortar_mayhem.py:194-259, 261-373
+ *                                  CharacterController.step & co.      memory_gym/character_controller.py:89-146, 177-210, 226-283
+ *                                  MortarArena / Command               memory_gym/pygame_assets.py:241-418
+ *   mg_mp_reset / mg_mp_step   <-  MysteryPathEnv.reset/step           memory_gym/mystery_path.py:130-200, 202-276
+ *                                  MysteryPath.__init__ (noisy A*)     memory_gym/pygame_assets.py:606-736
+ *   mg_ss_reset / mg_ss_step   <-  SearingSpotlightsEnv.reset/step     memory_gym/searing_spotlights.py:332-450, 452-562
+ *                                  Spotlight / Coin / Exit / sampler   memory_gym/pygame_assets.py:7-239
+ *   mg_*_build_assets          <-  CharacterController.create_character_sprites  character_controller.py:29-75,
+ *                                  Command.__init__ pygame_assets.py:254-304, MortarTile :316-343, Exit.draw :191-205,
+ *                                  Coin.draw :145-152, fall-off cross mystery_path.py:175-182
+ *                                  (i.e. the pygame draw/transform calls the reference makes per reset / per step)
+ *   mg_seed_pcg64              <-  gymnasium.utils.seeding.np_random(seed) = Generator(PCG64(SeedSequence(seed)))
+ *                                  (call site: super().reset(seed=seed), mortar_mayhem.py:217)
+ *
+ * Conventions
+ *   - every pointer marked "device" is CUDA device memory owned by the caller (e.g. a torch tensor);
+ *     the library never allocates or frees device memory and keeps no global state.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream). Calls are asynchronous.
+ *   - return value: 0 on success, a cudaError_t (> 0) from the launch, or a negative MG_E* code for
+ *     bad arguments. No exceptions cross this boundary.
+ *   - there is NO CPU implementation behind the reset/step symbols: without a CUDA device they fail.
+ */
+#ifndef MEMGYM_B200_H
+#define MEMGYM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_ABI_VERSION 1
+
+#define MG_SCREEN 84
+#define MG_OBS_BYTES (84 * 84 * 3) /* 21168 bytes per env, [x][y][c] */
+#define MG_INFO_COLS 8             /* doubles per env in the info matrix */
+#define MG_MAX_CHOICES 16          /* max length of a list-valued reset option */
+#define MG_MM_MAX_COMMANDS 152     /* capacity of the per-env command list */
+#define MG_MM_STATE_BYTES 256      /* one env record (Mortar Mayhem family) */
+#define MG_MP_STATE_BYTES 128      /* one env record (Mystery Path) */
+#define MG_SS_STATE_BYTES 2048     /* one env record (Searing Spotlights) */
+
+#define MG_EINVAL (-1)  /* bad argument / unsupported option value */
+#define MG_ENODEV (-2)  /* no usable CUDA device */
+
+/* info matrix columns (valid for env i only on steps where done[i] != 0) */
+#define MG_INFO_REWARD 0   /* sum of step rewards, left-to-right in double */
+#define MG_INFO_LENGTH 1   /* episode length in steps */
+#define MG_INFO_SUCCESS 2  /* MM/MM-Grid/MP/SS: success flag                                     */
+#define MG_INFO_A 3        /* MM: commands_completed (fraction); EMM: commands_completed (count); */
+                           /* MP: num_fails; SS: agent_health (fraction)                          */
+#define MG_INFO_B 4        /* EMM: max_command_sequence; SS: coins_collected (fraction)           */
+#define MG_INFO_GT0 5      /* Endless: ground_truth of the terminal step                          */
+#define MG_INFO_GT1 6
+
+/* mg_step_io.flags */
+#define MG_FLAG_AUTORESET 1u /* step: envs that finish are reset in the same call (their stream continues like  */
+                             /* `env.reset()` with seed=None); obs/ground_truth then hold the new episode's first */
+                             /* frame and the terminal frame goes to final_obs. Without it a finished env keeps   */
+                             /* its terminal frame and ignores further steps until mg_*_reset.                    */
+
+typedef struct mg_choice_list {
+    int32_t n;
+    int32_t v[MG_MAX_CHOICES];
+} mg_choice_list;
+
+/* ---- Mortar Mayhem family ------------------------------------------------------------------- */
+enum { MG_MM_CONTINUOUS = 0, MG_MM_GRID = 1, MG_MM_ENDLESS = 2 };
+
+/* Reset options, batch-uniform. Field names follow the reference's default_reset_parameters
+ * (mortar_mayhem.py:21-35, mortar_mayhem_grid.py:21-34, endless_mortar_mayhem.py:21-35). */
+typedef struct mg_mm_params {
+    int32_t variant;               /* MG_MM_* */
+    int32_t arena_size;            /* 2..6 (Endless: always 6) */
+    int32_t allowed_commands;      /* 4..9 */
+    int32_t visual_feedback;
+    int32_t max_steps;             /* Endless only; -1 = none */
+    int32_t initial_command_count; /* Endless only */
+    mg_choice_list command_count;  /* MM / MM-Grid */
+    mg_choice_list command_show_duration;
+    mg_choice_list command_show_delay;
+    mg_choice_list explosion_duration;
+    mg_choice_list explosion_delay;
+    double agent_scale;
+    double agent_speed;
+    double reward_command_failure;
+    double reward_command_success;
+    double reward_episode_success; /* Endless: reward_new_command_success */
+} mg_mm_params;
+
+/* ---- Mystery Path ---------------------------------------------------------------------------- */
+typedef struct mg_mp_params {
+    int32_t max_steps;
+    int32_t show_origin;
+    int32_t show_goal;
+    int32_t visual_feedback;
+    mg_choice_list cardinal_origin_choice;
+    double agent_scale;
+    double agent_speed;
+    double reward_goal;
+    double reward_fall_off;
+    double reward_path_progress;
+    double reward_step;
+} mg_mp_params;
+
+/* ---- Searing Spotlights ---------------------------------------------------------------------- */
+typedef struct mg_ss_params {
+    int32_t max_steps;
+    int32_t initial_spawns;
+    int32_t num_spawns;
+    int32_t visual_feedback;
+    int32_t black_background;
+    int32_t hide_chessboard;
+    int32_t light_dim_off_duration;
+    int32_t light_threshold;
+    int32_t coins_visible;
+    int32_t use_exit;
+    int32_t exit_visible;
+    int32_t agent_visible;
+    int32_t sample_agent_position;
+    int32_t show_last_action;
+    int32_t show_last_positive_reward;
+    int32_t pad0;
+    mg_choice_list num_coins;
+    double initial_spawn_interval;
+    double spawn_interval_threshold;
+    double spawn_interval_decay;
+    double spot_min_radius;
+    double spot_max_radius;
+    double spot_min_speed;
+    double spot_max_speed;
+    double spot_damage;
+    double coin_scale;
+    double exit_scale;
+    double agent_speed;
+    double agent_health;
+    double agent_scale;
+    double reward_inside_spotlight;
+    double reward_outside_spotlight;
+    double reward_death;
+    double reward_exit;
+    double reward_max_steps;
+    double reward_coin;
+} mg_ss_params;
+
+/* ---- per-call I/O (all device pointers; nullable ones are marked) ----------------------------- */
+typedef struct mg_step_io {
+    const int64_t* actions; /* [n][2] (MultiDiscrete([3,3])) or [n] (Discrete(4), MM-Grid); unused by reset */
+    uint8_t* obs;           /* [n][84][84][3] */
+    uint8_t* final_obs;     /* nullable: [n][84][84][3], terminal frame, written only where done (auto-reset) */
+    double* reward;         /* [n]; unused by reset */
+    uint8_t* done;          /* [n]; unused by reset */
+    double* info;           /* [n][MG_INFO_COLS], written only where done; unused by reset */
+    double* ground_truth;   /* nullable: [n][2] (Endless envs: target / 5.0, every step and reset) */
+    const uint8_t* reset_mask; /* reset only, nullable: [n], reset env i iff mask[i] != 0 */
+    uint32_t flags;         /* MG_FLAG_* */
+    uint32_t warps_per_cta; /* 0 = library default; tuning knob (frame buffers resident per SM) */
+} mg_step_io;
+
+/* ---- assets & seeding (host side) -------------------------------------------------------------- */
+/* Draw the static sprites / background templates for an option set with the library's own
+ * restatement of pygame's draw/transform routines and pack them into `host_out`. Returns the blob
+ * size in bytes (call with host_out = NULL to query), or a negative MG_E* code. The caller uploads
+ * the blob to 128-byte aligned device memory and passes it as `assets`.
+ * thick_circle_legacy != 0 selects the pygame <= 2.1.2 thick-circle algorithm for the "stay" icon. */
+long mg_mm_build_assets(const mg_mm_params* p, int thick_circle_legacy, void* host_out, size_t capacity);
+long mg_mp_build_assets(const mg_mp_params* p, void* host_out, size_t capacity);
+long mg_ss_build_assets(const mg_ss_params* p, void* host_out, size_t capacity);
+
+/* numpy SeedSequence(seed) -> PCG64 initial state for `n` seeds (host). out: n records of
+ * {state_lo, state_hi, inc_lo, inc_hi} (uint64 each). Bit-identical to
+ * numpy.random.PCG64(numpy.random.SeedSequence(seed)).state for 0 <= seed < 2^64. */
+int mg_seed_pcg64(const uint64_t* seeds, int n, uint64_t* out);
+
+/* Host-side self test hook for the 128-bit PCG64 / Lemire arithmetic the kernels use (the same
+ * __host__ __device__ code compiled for the CPU): starting from `state4` / {has_uint32, uinteger},
+ * performs `n_draws` bounded draws integers(lo[i], hi[i]) and, if out_uniform != NULL, one
+ * uniform(out_uniform[0], out_uniform[1]) whose result replaces out_uniform[0]. CPU test-suite only. */
+int mg_selftest_pcg64_host(uint64_t* state4, uint32_t* has_buf2, const int64_t* lo, const int64_t* hi,
+                           int n_draws, int64_t* out, double* out_uniform);
+
+/* ---- environment entry points ------------------------------------------------------------------ */
+/* state: device, n * MG_*_STATE_BYTES bytes, opaque to the caller (zero-initialise once = "make").
+ * rng4:  device, nullable: [n][4] uint64 from mg_seed_pcg64; where given (and selected by
+ *        reset_mask) the env's PCG64 stream is re-seeded before the reset draws, exactly like
+ *        `env.reset(seed=s)`; NULL continues each env's stream like `env.reset()`. */
+int mg_mm_reset(const mg_mm_params* p, const void* assets, void* state, const uint64_t* rng4,
+                const mg_step_io* io, int n, void* stream);
+int mg_mm_step(const mg_mm_params* p, const void* assets, void* state, const mg_step_io* io, int n,
+               void* stream);
+
+int mg_mp_reset(const mg_mp_params* p, const void* assets, void* state, const uint64_t* rng4,
+                const mg_step_io* io, int n, void* stream);
+int mg_mp_step(const mg_mp_params* p, const void* assets, void* state, const mg_step_io* io, int n,
+               void* stream);
+
+int mg_ss_reset(const mg_ss_params* p, const void* assets, void* state, const uint64_t* rng4,
+                const mg_step_io* io, int n, void* stream);
+int mg_ss_step(const mg_ss_params* p, const void* assets, void* state, const mg_step_io* io, int n,
+               void* stream);
+
+/* Option validation without a device: 0 if the reset/step kernels accept `p`, else MG_EINVAL with
+ * mg_last_error() naming the offending field. */
+int mg_mm_check_params(const mg_mm_params* p);
+int mg_mp_check_params(const mg_mp_params* p);
+int mg_ss_check_params(const mg_ss_params* p);
+
+/* Library / device introspection. */
+int mg_abi_version(void);
+int mg_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin);
+const char* mg_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEMGYM_B200_H */
