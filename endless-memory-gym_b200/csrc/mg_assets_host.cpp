@@ -189,8 +189,9 @@ void build_arena(Builder& b, int slot, int size, bool red) {
     int tile = (int)(56 * SCALE);
     int dim = (int)(56 * SCALE * size);
     int origin = MG_W / 2 - (dim >> 1);
-    uint32_t fillc = red ? mgr::rgb(81, 18, 26) : mgr::rgb(21, 43, 77);
-    uint32_t edge = red ? mgr::rgb(112, 24, 36) : mgr::rgb(29, 60, 107);
+    auto unpack = [](uint32_t c) { return mgr::rgb(c & 255, (c >> 8) & 255, (c >> 16) & 255); };
+    uint32_t fillc = unpack(red ? MG_RGB_TILE_FILL_ON : MG_RGB_TILE_FILL);
+    uint32_t edge = unpack(red ? MG_RGB_TILE_EDGE_ON : MG_RGB_TILE_EDGE);
     Surface t(tile, tile);
     mgr::rect(t, fillc, 0, 0, tile, tile, 0, 0, -1, -1, -1, -1);
     mgr::rect(t, edge, 0, 0, tile, tile, (int)(4 * SCALE), 0, -1, -1, -1, -1);

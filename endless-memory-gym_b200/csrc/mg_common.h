@@ -17,6 +17,12 @@
 #define MG_FRAME_BYTES (MG_W * MG_W * 3)  // 21168 = 1323 * 16
 #define MG_FRAME_VEC16 (MG_FRAME_BYTES / 16)
 
+// MortarTile colours (pygame_assets.py:323-329), packed 0x00BBGGRR = bytes R,G,B in memory order
+#define MG_RGB_TILE_FILL (21u | (43u << 8) | (77u << 16))
+#define MG_RGB_TILE_EDGE (29u | (60u << 8) | (107u << 16))
+#define MG_RGB_TILE_FILL_ON (81u | (18u << 8) | (26u << 16))
+#define MG_RGB_TILE_EDGE_ON (112u | (24u << 8) | (36u << 16))
+
 #define MG_ASSET_MAGIC 0x4d474131u  // "MGA1"
 #define MG_MAX_PALETTE 32
 

@@ -13,7 +13,8 @@
 
 struct MgAssetView {
     const MgAssetHeader* hdr;
-    const uint32_t* entries;
+    const uint32_t* entries;       // sprite pixel lists (the kernel re-points this at a shared-memory copy)
+    const uint8_t (*palette)[4];   // ditto
     const uint8_t* tmpl[4];
 };
 
@@ -22,6 +23,7 @@ MG_HD MgAssetView mg_asset_view(const void* blob) {
     const uint8_t* b = (const uint8_t*)blob;
     v.hdr = (const MgAssetHeader*)b;
     v.entries = (const uint32_t*)(b + v.hdr->entries_off);
+    v.palette = v.hdr->palette;
     for (int i = 0; i < 4; ++i) v.tmpl[i] = v.hdr->tmpl_off[i] ? b + v.hdr->tmpl_off[i] : nullptr;
     return v;
 }
@@ -35,7 +37,7 @@ MG_HD void mg_sprite_draw(Ctx& c, uint8_t* buf, const MgAssetView& a, int slot, 
         uint32_t v = e[i];
         int x = ax + (int)(v & 255u), y = ay + (int)((v >> 8) & 255u);
         if ((unsigned)x < (unsigned)MG_W && (unsigned)y < (unsigned)MG_W) {
-            const uint8_t* col = a.hdr->palette[(v >> 16) & 255u];
+            const uint8_t* col = a.palette[(v >> 16) & 255u];
             uint8_t* o = buf + x * MG_COL_BYTES + y * 3;
             o[0] = col[0];
             o[1] = col[1];
@@ -44,22 +46,39 @@ MG_HD void mg_sprite_draw(Ctx& c, uint8_t* buf, const MgAssetView& a, int slot, 
     }
 }
 
-// undo mg_sprite_draw: put the background template's bytes back
-template <class Ctx>
-MG_HD void mg_sprite_erase(Ctx& c, uint8_t* buf, const MgAssetView& a, int slot, int ax, int ay, const uint8_t* bg) {
+// undo mg_sprite_draw: put the background back. `bg(x, y)` returns the clean frame's 0x00BBGGRR at a pixel
+// (closed form per env type: no memory traffic on the un-patch path).
+template <class Ctx, class Bg>
+MG_HD void mg_sprite_erase(Ctx& c, uint8_t* buf, const MgAssetView& a, int slot, int ax, int ay, const Bg& bg) {
     const MgSprite sp = a.hdr->sprite[slot];
     const uint32_t* e = a.entries + sp.first;
     for (int i = c.lane; i < (int)sp.count; i += c.nl) {
         uint32_t v = e[i];
         int x = ax + (int)(v & 255u), y = ay + (int)((v >> 8) & 255u);
         if ((unsigned)x < (unsigned)MG_W && (unsigned)y < (unsigned)MG_W) {
-            int off = x * MG_COL_BYTES + y * 3;
-            buf[off] = bg[off];
-            buf[off + 1] = bg[off + 1];
-            buf[off + 2] = bg[off + 2];
+            uint32_t col = bg(x, y);
+            uint8_t* o = buf + x * MG_COL_BYTES + y * 3;
+            o[0] = (uint8_t)col;
+            o[1] = (uint8_t)(col >> 8);
+            o[2] = (uint8_t)(col >> 16);
         }
     }
 }
+
+// MortarArena background (pygame_assets.py:316-343,362-368): size x size tiles of 14 px, 1-px light frame
+struct MgArenaBg {
+    int origin, extent;
+    MG_HD uint32_t operator()(int x, int y) const {
+        unsigned u = (unsigned)(x - origin), v = (unsigned)(y - origin);
+        if (u >= (unsigned)extent || v >= (unsigned)extent) return 0u;
+        unsigned p = u % 14u, q = v % 14u;
+        bool edge = p == 0u || p == 13u || q == 0u || q == 13u;
+        return edge ? MG_RGB_TILE_EDGE : MG_RGB_TILE_FILL;
+    }
+};
+struct MgBlackBg {
+    MG_HD uint32_t operator()(int, int) const { return 0u; }
+};
 
 // copy the w x h pixel block at (x0, y0) from a full-frame template (clipped)
 template <class Ctx>
@@ -108,14 +127,15 @@ MG_HD void mg_mm_compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgMMF
 }
 
 template <class Ctx>
-MG_HD void mg_mm_restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgMMFrame& f, int agent_half, int icon_x,
-                         int icon_y) {
+MG_HD void mg_mm_restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgMMFrame& f, int origin, int size,
+                         int agent_half, int icon_x, int icon_y) {
     if (f.red) {
         c.copy_frame(buf, a.tmpl[0]);
         return;
     }
-    mg_sprite_erase(c, buf, a, MG_SPR_AGENT0 + f.srot, f.sx - agent_half, f.sy - agent_half, a.tmpl[0]);
-    if (f.icon >= 0) mg_sprite_erase(c, buf, a, MG_SPR_ICON0 + f.icon, icon_x, icon_y, a.tmpl[0]);
+    const MgArenaBg bg{origin, 14 * size};
+    mg_sprite_erase(c, buf, a, MG_SPR_AGENT0 + f.srot, f.sx - agent_half, f.sy - agent_half, bg);
+    if (f.icon >= 0) mg_sprite_erase(c, buf, a, MG_SPR_ICON0 + f.icon, icon_x, icon_y, bg);
 }
 
 // ---- Mystery Path ------------------------------------------------------------------------------
@@ -143,8 +163,9 @@ MG_HD void mg_mp_compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgMPD
 
 template <class Ctx>
 MG_HD void mg_mp_restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgMPDraw& d, int agent_half) {
-    mg_sprite_erase(c, buf, a, MG_SPR_AGENT0 + d.f.srot, d.f.sx - agent_half, d.f.sy - agent_half, a.tmpl[0]);
-    if (d.f.cross) mg_sprite_erase(c, buf, a, MG_SPR_CROSS, d.f.cross_x, d.f.cross_y, a.tmpl[0]);
+    const MgBlackBg bg;
+    mg_sprite_erase(c, buf, a, MG_SPR_AGENT0 + d.f.srot, d.f.sx - agent_half, d.f.sy - agent_half, bg);
+    if (d.f.cross) mg_sprite_erase(c, buf, a, MG_SPR_CROSS, d.f.cross_x, d.f.cross_y, bg);
     if (d.show_goal) mg_block_fill(c, buf, 12 * d.gx, 12 * d.gy, 12, 12, 0, 0, 0);
     if (d.show_origin) mg_block_fill(c, buf, 12 * d.ox, 12 * d.oy, 12, 12, 0, 0, 0);
 }

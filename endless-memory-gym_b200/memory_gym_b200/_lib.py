@@ -112,6 +112,7 @@ def lib():
         getattr(L, f"mg_{fam}_check_params").argtypes = [C.POINTER(P)]
         getattr(L, f"mg_{fam}_reset").argtypes = [C.POINTER(P), vp, vp, vp, C.POINTER(StepIO), i32, vp]
         getattr(L, f"mg_{fam}_step").argtypes = [C.POINTER(P), vp, vp, C.POINTER(StepIO), i32, vp]
+        getattr(L, f"mg_{fam}_step_many").argtypes = [C.POINTER(P), vp, vp, C.POINTER(StepIO), i32, i32, vp]
         b = getattr(L, f"mg_{fam}_build_assets")
         b.restype = C.c_long
         b.argtypes = [C.POINTER(P), i32, vp, C.c_size_t] if fam == "mm" else [C.POINTER(P), vp, C.c_size_t]

@@ -63,8 +63,14 @@ class _CudaBackend:
                 f"mg_{family}_reset")
 
     def step(self, family, params, assets, state, io, n, stream):
-        L.check(getattr(self.lib, f"mg_{family}_step")(C.byref(params), assets, state, C.byref(io), n, stream),
-                f"mg_{family}_step")
+        rc = getattr(self.lib, f"mg_{family}_step")(C.byref(params), assets, state, C.byref(io), n, stream)
+        if rc:
+            L.check(rc, f"mg_{family}_step")
+
+    def step_many(self, family, params, assets, state, ios, n_steps, n, stream):
+        rc = getattr(self.lib, f"mg_{family}_step_many")(C.byref(params), assets, state, ios, n_steps, n, stream)
+        if rc:
+            L.check(rc, f"mg_{family}_step_many")
 
 
 class MemoryGymVecEnv:
@@ -148,6 +154,8 @@ class MemoryGymVecEnv:
             off = (-raw.data_ptr()) % 128
             self._assets = raw[off:off + blob.shape[0]]
             self._assets.copy_(torch.from_numpy(blob))
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)  # the kernels' prologue reads the blob before stream order applies
             self._params, self._params_key = params, key
         self.reset_params = p
         self.max_episode_steps = self._max_episode_steps(p)
@@ -186,6 +194,7 @@ class MemoryGymVecEnv:
             mask_t = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
         self._io.reset_mask = mask_t.data_ptr() if mask_t is not None else None
         self._io.actions = None
+        self._io.obs = self.obs.data_ptr()
         self._be.reset(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(),
                        rng4.data_ptr() if rng4 is not None else None, self._io, self.num_envs,
                        self._be.stream(self.device))
@@ -196,7 +205,9 @@ class MemoryGymVecEnv:
             info["ground_truth"] = self.ground_truth
         return self.obs, info
 
-    def step(self, actions):
+    def step(self, actions, obs_out=None):
+        """``obs_out``: optional uint8[N,84,84,3] device tensor (e.g. a slot of a rollout buffer) that
+        receives this step's observations instead of the env's own ``obs`` buffer."""
         if self._params is None:
             raise L.MemGymError("step() called before reset()")
         if isinstance(actions, torch.Tensor) and actions.device == self.device and actions.dtype == torch.int64 \
@@ -209,6 +220,13 @@ class MemoryGymVecEnv:
         if a.numel() != self._actions_dev.numel():
             raise ValueError(f"actions must have shape {tuple(self._actions_dev.shape)}")
         self._io.actions = a.data_ptr()
+        obs = self.obs
+        if obs_out is not None:
+            if obs_out.shape != self.obs.shape or obs_out.dtype != torch.uint8 or obs_out.device != self.device \
+                    or not obs_out.is_contiguous():
+                raise ValueError("obs_out must be a contiguous uint8[N,84,84,3] tensor on the env's device")
+            obs = obs_out
+        self._io.obs = obs.data_ptr()
         self._be.step(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(), self._io,
                       self.num_envs, self._be.stream(self.device))
         done = self.done.view(torch.bool)
@@ -220,7 +238,50 @@ class MemoryGymVecEnv:
         if self.has_ground_truth_info:
             info["ground_truth"] = self.ground_truth
             info["final_ground_truth"] = self.info[:, L.MG_INFO_GT0:L.MG_INFO_GT1 + 1]
-        return self.obs, self.reward, done, self.truncated, info
+        return obs, self.reward, done, self.truncated, info
+
+    def rollout(self, actions, obs_out, reward_out, done_out, info_out=None):
+        """``T`` consecutive steps with given actions in ONE library call (``mg_*_step_many``: T kernel
+        launches enqueued back to back, no Python between them) — the reference's ``bench.py`` loop shape
+        (pre-sampled random actions) and scripted roll-outs.
+
+        ``actions`` int64[T, N, 2] (or [T, N]); ``obs_out`` uint8[T', N, 84, 84, 3] with T' >= 1 slots used
+        round-robin (a rollout ring); ``reward_out`` float64[T, N]; ``done_out`` bool/uint8[T, N];
+        ``info_out`` optional float64[T, N, 8] (else only the last finished episode's stats per env are kept)."""
+        if self._params is None:
+            raise L.MemGymError("rollout() called before reset()")
+        T = actions.shape[0]
+        for t_, name in ((actions, "actions"), (obs_out, "obs_out"), (reward_out, "reward_out"), (done_out, "done_out")):
+            if t_.device != self.device or not t_.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous tensor on the env's device")
+        if actions.dtype != torch.int64 or obs_out.dtype != torch.uint8 or reward_out.dtype != torch.float64 \
+                or done_out.element_size() != 1:
+            raise ValueError("dtypes: actions int64, obs_out uint8, reward_out float64, done_out bool/uint8")
+        if tuple(actions.shape[1:]) != tuple(self._actions_dev.shape) or tuple(obs_out.shape[1:]) != (self.num_envs, 84, 84, 3) \
+                or tuple(reward_out.shape) != (T, self.num_envs) or tuple(done_out.shape) != (T, self.num_envs):
+            raise ValueError("rollout buffer shapes do not match (T, num_envs)")
+        key = (T, actions.data_ptr(), obs_out.data_ptr(), obs_out.shape[0], reward_out.data_ptr(), done_out.data_ptr(),
+               info_out.data_ptr() if info_out is not None else 0)
+        if getattr(self, "_many_key", None) != key:
+            ios = (L.StepIO * T)()
+            a_stride = actions.stride(0) * 8
+            o_stride = obs_out.stride(0)
+            for t in range(T):
+                io = ios[t]
+                io.actions = actions.data_ptr() + t * a_stride
+                io.obs = obs_out.data_ptr() + (t % obs_out.shape[0]) * o_stride
+                io.final_obs = self._io.final_obs
+                io.reward = reward_out.data_ptr() + t * self.num_envs * 8
+                io.done = done_out.data_ptr() + t * self.num_envs
+                io.info = (info_out.data_ptr() + t * self.num_envs * L.MG_INFO_COLS * 8) if info_out is not None \
+                    else self._io.info
+                io.ground_truth = self._io.ground_truth
+                io.reset_mask = None
+                io.flags = self._io.flags
+                io.warps_per_cta = self._io.warps_per_cta
+            self._many_key, self._many_ios = key, ios
+        self._be.step_many(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(),
+                           self._many_ios, T, self.num_envs, self._be.stream(self.device))
 
     def render(self):
         """``rgb_array`` of the reference (mortar_mayhem.py:396): the observation transposed to [y][x][c]."""

@@ -200,15 +200,27 @@ int mg_mm_reset(const mg_mm_params* p, const void* assets, void* state, const ui
 int mg_mm_step(const mg_mm_params* p, const void* assets, void* state, const mg_step_io* io, int n,
                void* stream);
 
+/* `n_steps` consecutive steps in one call: step t uses ios[t] (its own actions / obs / reward / done
+ * pointers, e.g. slices of [T][N] rollout buffers) — n_steps kernel launches enqueued back to back. For
+ * scripted or pre-sampled actions (the reference's bench.py loop); warps_per_cta is taken from ios[0]. */
+int mg_mm_step_many(const mg_mm_params* p, const void* assets, void* state, const mg_step_io* ios, int n_steps,
+                    int n, void* stream);
+
 int mg_mp_reset(const mg_mp_params* p, const void* assets, void* state, const uint64_t* rng4,
                 const mg_step_io* io, int n, void* stream);
 int mg_mp_step(const mg_mp_params* p, const void* assets, void* state, const mg_step_io* io, int n,
                void* stream);
 
+int mg_mp_step_many(const mg_mp_params* p, const void* assets, void* state, const mg_step_io* ios, int n_steps,
+                    int n, void* stream);
+
 int mg_ss_reset(const mg_ss_params* p, const void* assets, void* state, const uint64_t* rng4,
                 const mg_step_io* io, int n, void* stream);
 int mg_ss_step(const mg_ss_params* p, const void* assets, void* state, const mg_step_io* io, int n,
                void* stream);
+
+int mg_ss_step_many(const mg_ss_params* p, const void* assets, void* state, const mg_step_io* ios, int n_steps,
+                    int n, void* stream);
 
 /* Option validation without a device: 0 if the reset/step kernels accept `p`, else MG_EINVAL with
  * mg_last_error() naming the offending field. */

@@ -19,7 +19,7 @@ struct HostCtx {
 // mirrors mg_env_kernel (mg_kernels.cu) with one "warp" and a persistent frame buffer
 template <class P>
 int run(const typename P::K& k, const void* assets, void* state, const uint64_t* rng4, const mg_step_io* io, int n,
-        int mode) {
+        int mode, int act_dims) {
     typedef typename P::State State;
     typedef typename P::Frame Frame;
     MgKIO q;
@@ -27,6 +27,8 @@ int run(const typename P::K& k, const void* assets, void* state, const uint64_t*
     q.rng4 = rng4;
     q.mode = mode;
     q.n = n;
+    q.stage_cap = 0;
+    q.act_dims = act_dims;
     const MgAssetView view = mg_asset_view(assets);
     static thread_local uint8_t buf[MG_FRAME_BYTES];
     HostCtx ctx;
@@ -35,7 +37,12 @@ int run(const typename P::K& k, const void* assets, void* state, const uint64_t*
         State* st = reinterpret_cast<State*>((uint8_t*)state + (size_t)env * sizeof(State));
         MgFrameJob job;
         Frame fr[2];
-        P::logic(k, q, env, *st, job, fr);
+        int a0 = 0, a1 = 0;
+        if (mode == MG_MODE_STEP) {
+            a0 = (int)io->actions[(size_t)env * act_dims];
+            if (act_dims > 1) a1 = (int)io->actions[(size_t)env * act_dims + 1];
+        }
+        P::logic(k, q, env, *st, a0, a1, job, fr);
         for (int fi = 0; fi < job.nframes; ++fi) {
             uint8_t* dst = (job.to_final[fi] ? io->final_obs : io->obs) + (size_t)env * MG_FRAME_BYTES;
             P::compose(ctx, buf, view, k, fr[fi]);
@@ -54,12 +61,12 @@ extern "C" int mgsim_mm(const mg_mm_params* p, const void* assets, void* state, 
     if (mg_mm_check_params(p)) return MG_EINVAL;
     MgMMK k;
     mg_mm_derive(p, &k);
-    return run<MMPolicy>(k, assets, state, rng4, io, n, mode);
+    return run<MMPolicy>(k, assets, state, rng4, io, n, mode, p->variant == MG_MM_GRID ? 1 : 2);
 }
 extern "C" int mgsim_mp(const mg_mp_params* p, const void* assets, void* state, const uint64_t* rng4,
                         const mg_step_io* io, int n, int mode) {
     if (mg_mp_check_params(p)) return MG_EINVAL;
     MgMPK k;
     mg_mp_derive(p, &k);
-    return run<MPPolicy>(k, assets, state, rng4, io, n, mode);
+    return run<MPPolicy>(k, assets, state, rng4, io, n, mode, 2);
 }

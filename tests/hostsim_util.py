@@ -64,3 +64,7 @@ class HostSimBackend:
     def step(self, family, params, assets, state, io, n, stream):
         rc = getattr(self.sim, f"mgsim_{family}")(C.byref(params), assets, state, None, C.byref(io), n, 1)
         assert rc == 0, rc
+
+    def step_many(self, family, params, assets, state, ios, n_steps, n, stream):
+        for t in range(n_steps):
+            self.step(family, params, assets, state, ios[t], n, stream)
