@@ -36,10 +36,10 @@ OBS_BYTES = 84 * 84 * 3
 STATE_BYTES = {"mm": 256, "mp": 128, "ss": 2048}
 
 
-def alg_bytes_per_env_step(family, n_act):
+def alg_bytes_per_env_step(family, n_act, steps_per_launch=1):
     """Algorithmic HBM bytes of one env-step: obs write + actions read + reward (f64) +
-    done + state record read and written."""
-    return OBS_BYTES + 8 * n_act + 8 + 1 + 2 * STATE_BYTES[family]
+    done + the state record read and written once per launch (a rollout launch keeps it on chip)."""
+    return OBS_BYTES + 8 * n_act + 8 + 1 + 2 * STATE_BYTES[family] / steps_per_launch
 
 
 # ---- CPU arm: the oracle (restated reference) in the shape of the reference's bench.py loop ------------
@@ -174,13 +174,13 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100000)
+    ap.add_argument("--warmup", type=int, default=256)
     ap.add_argument("--env", default="MortarMayhem-v0")
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--warps-per-cta", type=int, default=0)
-    ap.add_argument("--ring", type=int, default=0, help="obs rollout-ring slots (0 = enough to exceed L2)")
+    ap.add_argument("--chunk", type=int, default=128, help="steps per mg_*_rollout launch (= slots of the obs buffer)")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
@@ -212,10 +212,11 @@ def main():
     n_act = len(spec.action_nvec)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     T = K + W
-    POOL = min(T, 1024)  # i.i.d. action sets, cycled
+    POOL = min(T, args.chunk)  # steps per rollout launch; i.i.d. action sets, cycled
     acts = torch.randint(0, spec.action_nvec[0], (POOL,) + tuple(env._actions_dev.shape), generator=g, device=dev)
-    # obs go to a rollout ring larger than the 126 MB L2, so every step's frames really reach HBM
-    ring_n = args.ring or max(2, -(-160 * 2**20 // (n * OBS_BYTES)) + 1)
+    # obs go to a [chunk, N, 84, 84, 3] rollout buffer (step t of a launch -> slot t): every frame has its own
+    # address, the buffer (chunk x 86.7 MB) is far larger than the 126 MB L2, so every frame reaches HBM
+    ring_n = POOL
     ring = torch.empty((ring_n, n, 84, 84, 3), dtype=torch.uint8, device=dev)
     env.reset(seed=0)
 
@@ -233,7 +234,7 @@ def main():
         left = count
         while left > 0:
             c = min(left, POOL)
-            env.rollout(acts[:c], ring, rew_buf[:c], done_buf[:c])
+            env.rollout(acts[:c], ring[:c], rew_buf[:c], done_buf[:c])
             left -= c
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -317,9 +318,10 @@ def main():
         except OSError:
             pass
         peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        b_alg = alg_bytes_per_env_step(spec.family, n_act)
-        kernel_ms = ms / K  # one launch per step, launches back to back on one stream
-        achieved = n * b_alg / (kernel_ms * 1e-3) / 1e9
+        b_alg = alg_bytes_per_env_step(spec.family, n_act, POOL)
+        launches = -(-K // POOL)
+        kernel_ms = ms / launches  # launches back to back on one stream: event time / launches = launch duration
+        achieved = n * b_alg * K / (ms * 1e-3) / 1e9
         cpu = None
         if not args.no_cpu:
             v = cpu_throughput(args.env, 1, args.cpu_seconds) / 1e6
@@ -332,17 +334,20 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"{args.env}, {n} envs/GPU x {world} GPU, 84x84x3 uint8 obs, default options, "
                                    "seeds 0..N-1, uniform random actions, auto-reset on",
-                       "l2": f"obs written to a rollout ring of {ring_n} x {n * OBS_BYTES / 1e6:.1f} MB (> 126 MB L2)",
+                       "l2": f"each launch writes {ring_n} steps x {n * OBS_BYTES / 1e6:.1f} MB of obs to distinct slots "
+                             f"of a {ring_n * n * OBS_BYTES / 1e9:.1f} GB rollout buffer (>> 126 MB L2), no address rewritten "
+                             "within a launch",
+                       "steps_per_launch": ring_n,
                        "parallelism": f"env shards x{world}, no collective on the step path",
                        "warps_per_cta": args.warps_per_cta or "default"},
             "e2e": {"value": e2e_value, "unit": "M env-steps/s", "h2d_bytes_per_step": n * n_act * 8,
                     "d2h_bytes_per_step": n * (OBS_BYTES + 8 + 1), "steps": Ke,
                     "note": "actions pinned-host->device and obs+reward+done device->pinned-host every step "
                             "(D2H of step t overlaps step t+1); PCIe-bound"},
-            "gpu_launches": K,
+            "gpu_launches": -(-K // POOL),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "mg_env_kernel",
-                         "alg_bytes_per_env_step": b_alg, "kernel_ms": kernel_ms},
+                         "alg_bytes_per_env_step": b_alg, "kernel_ms": kernel_ms, "env_steps_per_launch": n * POOL},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

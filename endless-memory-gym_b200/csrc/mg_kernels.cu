@@ -1,21 +1,26 @@
-// mg_kernels.cu — the sm_100a reset/step kernels and their C-ABI launchers.
+// mg_kernels.cu — the sm_100a reset/step/rollout kernel and its C-ABI launchers.
 //
 // One launch per env type does, for every env of the batch: kinematics + tile collision, the env
 // state machine (incl. in-kernel PCG64 draws for auto-reset), and the rasterisation of the
 // 84x84x3 observation. ONE WARP OWNS ONE ENV:
-//   * the env's state record (256 B) is loaded/stored with one coalesced 8-byte access per lane
-//     into a per-warp shared-memory slot; lane 0 runs the (branchy, scalar) state machine there;
+//   * the env's state record is loaded/stored with one coalesced 8-byte access per lane into a per-warp
+//     shared-memory slot; lane 0 runs the (branchy, scalar) state machine there;
 //   * each warp keeps one 21168-byte frame buffer in shared memory that holds the clean background
-//     template between envs. A frame = patch a few hundred sprite bytes, then ONE
-//     `cp.async.bulk.global.shared::cta` (TMA bulk store, SASS UBLKCP) streams the whole frame to
-//     HBM as full 128-byte lines while the warp already runs the next env's state machine; when the
-//     bulk read of the buffer is done (`cp.async.bulk.wait_group.read`) the patch is undone.
+//     template between frames. A frame = patch a few hundred sprite bytes (sprite pixel lists + palette
+//     are staged in shared memory), then ONE `cp.async.bulk.global.shared::cta` (TMA bulk store, SASS
+//     UBLKCP) streams the whole frame to HBM as full lines while the warp already runs the next state
+//     machine; when the bulk read of the buffer is done (`cp.async.bulk.wait_group.read`) the patch is
+//     undone (closed-form background, no memory traffic).
 //   * background templates are brought in with `cp.async.bulk.shared::cluster.global` + mbarrier.
+//   * rollout mode (n_steps > 1): a warp runs ALL steps of its envs back to back with the record
+//     resident in shared memory — no kernel boundary, no inter-warp dependency, the HBM write stream
+//     never drains.
 // The grid is one CTA per SM (persistent over the env batch), up to 10 warps = 10 frame buffers
 // (212 KB of the 227 KB shared memory) so ~200 KB of stores are in flight per SM.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/memgym_b200.h"
@@ -23,11 +28,11 @@
 #include "mg_frame.h"
 #include "mg_mm_logic.h"
 #include "mg_mp_logic.h"
-#include "mg_policy.h"
 #include "mg_params_host.h"
+#include "mg_policy.h"
 
 #define MG_BUF_STRIDE 21248  // MG_FRAME_BYTES rounded up to 128
-#define MG_CTL_BYTES 128
+
 // ---- PTX wrappers (TMA bulk copies, mbarrier, proxy fence) ---------------------------------------
 __device__ __forceinline__ uint32_t mg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mg_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -38,6 +43,17 @@ __device__ __forceinline__ void mg_bulk_store(void* gdst, const void* ssrc, uint
 }
 __device__ __forceinline__ void mg_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void mg_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the newest `keep` bulk groups have fully completed (their global writes are performed)
+__device__ __forceinline__ void mg_bulk_wait_done(int keep) {
+    if (keep <= 0)
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    else if (keep == 1)
+        asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+    else if (keep == 2)
+        asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+    else
+        asm volatile("cp.async.bulk.wait_group 3;" ::: "memory");
+}
 __device__ __forceinline__ void mg_mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -60,6 +76,11 @@ __device__ __forceinline__ void mg_mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
     }
+}
+__device__ __forceinline__ uint64_t mg_now() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
 // execution context of mg_frame.h on the device: the 32 lanes of the warp that owns the env
@@ -103,20 +124,23 @@ __global__ void __launch_bounds__(320, 1)
     uint64_t* bar = reinterpret_cast<uint64_t*>(slot + kSlot - 8);
 
     // ---- prologue: touches only the (constant) asset blob, so under programmatic dependent launch it
-    // overlaps the tail of the previous step's kernel ----------------------------------------------------
+    // overlaps the tail of the previous kernel in the stream ---------------------------------------------
+    const bool tracing = q.io.trace != nullptr;
+    uint64_t tr0 = 0, tr1 = 0, tr2 = 0;
+    if (tracing) tr0 = mg_now();
     MgAssetView view = mg_asset_view(assets);
     MgWarpCtx ctx{lane, 32, mg_smem_u32(bar), 0u};
     if (lane == 0) mg_mbar_init(ctx.bar, 1);
     __syncwarp();
     const int total_warps = gridDim.x * nwarps;
-    int env = blockIdx.x * nwarps + warp;
+    int env = warp * gridDim.x + blockIdx.x;  // consecutive envs on different SMs: remainders spread evenly
     const bool active = env < q.n;
     if (active && lane == 0) {  // background template -> this warp's frame buffer (TMA, L2-resident source)
         mg_mbar_expect_tx(ctx.bar, MG_FRAME_BYTES);
         mg_bulk_load(buf, view.tmpl[0], MG_FRAME_BYTES, ctx.bar);
     }
     const int hw = (int)(sizeof(MgAssetHeader) / 4), ne = (int)view.hdr->n_entries;
-    if ((hw + ne) * 4 <= q.stage_cap) {  // sprite pixel lists + palette -> shared memory: compose/un-patch never wait on L2
+    if ((hw + ne) * 4 <= q.stage_cap) {  // sprite pixel lists + palette -> shared memory: compose never waits on L2
         const uint32_t* src = reinterpret_cast<const uint32_t*>(assets);
         uint32_t* dst = reinterpret_cast<uint32_t*>(stage);
         const uint32_t* esrc = view.entries;
@@ -127,11 +151,15 @@ __global__ void __launch_bounds__(320, 1)
         view.entries = dst + hw;
         view.palette = view.hdr->palette;
     }
+    if (tracing) tr1 = mg_now();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");  // previous kernel's state / obs writes are visible
     if (!active) return;
+    if (tracing) tr2 = mg_now();
 
-    // ---- first record + actions in flight while the template lands ------------------------------------
+    const int T = q.n_steps;
+    const bool stepping = q.mode == MG_MODE_STEP;
+    // ---- first record + first actions in flight while the template lands --------------------------------
     uint64_t pre[kPerLane];
     int64_t act0 = 0, act1 = 0;
     {
@@ -139,9 +167,10 @@ __global__ void __launch_bounds__(320, 1)
 #pragma unroll
         for (int j = 0; j < kPerLane; ++j)
             if (lane + 32 * j < kWords) pre[j] = g[lane + 32 * j];
-        if (lane == 0 && q.mode == MG_MODE_STEP) {
-            act0 = q.io.actions[(size_t)env * q.act_dims];
-            if (q.act_dims > 1) act1 = q.io.actions[(size_t)env * q.act_dims + 1];
+        if (lane == 0 && stepping) {
+            const int64_t* a = q.io.actions + (size_t)env * q.act_dims;
+            act0 = a[0];
+            if (q.act_dims > 1) act1 = a[1];
         }
     }
     mg_mbar_wait(ctx.bar, ctx.phase);
@@ -154,54 +183,77 @@ __global__ void __launch_bounds__(320, 1)
 #pragma unroll
         for (int j = 0; j < kPerLane; ++j)
             if (lane + 32 * j < kWords) s64[lane + 32 * j] = pre[j];
-        const int a0 = (int)act0, a1 = (int)act1;
         __syncwarp();
-        // prefetch the next env's record and actions: their latency hides behind this env's work
         const int nxt = env + total_warps;
-        if (nxt < q.n) {
-            const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)nxt * kStateBytes);
-#pragma unroll
-            for (int j = 0; j < kPerLane; ++j)
-                if (lane + 32 * j < kWords) pre[j] = g[lane + 32 * j];
-            if (lane == 0 && q.mode == MG_MODE_STEP) {
-                act0 = q.io.actions[(size_t)nxt * q.act_dims];
-                if (q.act_dims > 1) act1 = q.io.actions[(size_t)nxt * q.act_dims + 1];
+        for (int t = 0; t < T; ++t) {
+            const int a0 = (int)act0, a1 = (int)act1;
+            uint64_t* trow = tracing ? q.io.trace + (size_t)env * MG_TRACE_COLS : nullptr;
+            if (trow && lane == 0) {
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                trow[0] = tr0, trow[1] = tr1, trow[2] = tr2, trow[3] = mg_now(), trow[7] = smid;
             }
+            // prefetch what the next iteration needs (next step's actions; on the env's last step the next
+            // env's record and first actions): the latency hides behind this step's work
+            if (t + 1 < T) {
+                if (lane == 0) {
+                    const int64_t* a = q.io.actions + (size_t)(t + 1) * q.act_stride + (size_t)env * q.act_dims;
+                    act0 = a[0];
+                    if (q.act_dims > 1) act1 = a[1];
+                }
+            } else if (nxt < q.n) {
+                const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)nxt * kStateBytes);
+#pragma unroll
+                for (int j = 0; j < kPerLane; ++j)
+                    if (lane + 32 * j < kWords) pre[j] = g[lane + 32 * j];
+                if (lane == 0 && stepping) {
+                    const int64_t* a = q.io.actions + (size_t)nxt * q.act_dims;
+                    act0 = a[0];
+                    if (q.act_dims > 1) act1 = a[1];
+                }
+            }
+            if (lane == 0) P::logic(k, q, env, t, *st, a0, a1, *job, fr);
+            __syncwarp();
+            if (trow && lane == 0) trow[4] = mg_now();
+            const int nframes = job->nframes;
+            for (int fi = 0; fi < nframes; ++fi) {
+                const Frame f = fr[fi];
+                const bool to_final = job->to_final[fi] != 0;
+                uint8_t* dst = to_final ? q.io.final_obs + (size_t)env * MG_FRAME_BYTES
+                                        : q.io.obs + (size_t)(t % q.ring_n) * q.obs_stride + (size_t)env * MG_FRAME_BYTES;
+                if (pending) {
+                    if (lane == 0) mg_bulk_wait_read();
+                    __syncwarp();
+                    P::restore(ctx, buf, view, k, prev);
+                    __syncwarp();
+                }
+                P::compose(ctx, buf, view, k, f);
+                mg_fence_proxy_async();  // make this lane's patch visible to the async (TMA) proxy
+                __syncwarp();
+                if (lane == 0) {
+                    if (trow) trow[5] = mg_now();
+                    // rollout: the same address is rewritten ring_n steps later (final_obs: at the next done);
+                    // the earlier bulk write must have been performed before this one is issued
+                    if (T > 1) mg_bulk_wait_done(to_final ? 0 : q.ring_n - 1);
+                    mg_bulk_store(dst, buf, MG_FRAME_BYTES);
+                    mg_bulk_commit();
+                    if (trow) trow[6] = mg_now();
+                }
+                pending = true;
+                prev = f;
+            }
+            __syncwarp();  // job / frame slots are reused by the next step
         }
-        if (lane == 0) P::logic(k, q, env, *st, a0, a1, *job, fr);
-        __syncwarp();
         uint64_t* gw = reinterpret_cast<uint64_t*>(state + (size_t)env * kStateBytes);
 #pragma unroll
         for (int j = 0; j < kPerLane; ++j)
             if (lane + 32 * j < kWords) gw[lane + 32 * j] = s64[lane + 32 * j];
-        const int nframes = job->nframes;
-        for (int fi = 0; fi < nframes; ++fi) {
-            const Frame f = fr[fi];
-            uint8_t* dst = (job->to_final[fi] ? q.io.final_obs : q.io.obs) + (size_t)env * MG_FRAME_BYTES;
-            if (pending) {
-                if (lane == 0) mg_bulk_wait_read();
-                __syncwarp();
-                P::restore(ctx, buf, view, k, prev);
-                __syncwarp();
-            }
-            P::compose(ctx, buf, view, k, f);
-            mg_fence_proxy_async();  // make this lane's patch visible to the async (TMA) proxy
-            __syncwarp();
-            if (lane == 0) {
-                mg_bulk_store(dst, buf, MG_FRAME_BYTES);
-                mg_bulk_commit();
-            }
-            pending = true;
-            prev = f;
-        }
-        __syncwarp();  // slot is reused by the next env
+        __syncwarp();  // record slot is reused by the next env
     }
     if (pending && lane == 0) mg_bulk_wait_read();  // shared memory must outlive the bulk read
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-
-
 extern "C" int mg_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) {
@@ -228,29 +280,15 @@ extern "C" int mg_device_info(int* sm_count, int* cc_major, int* cc_minor, size_
     return 0;
 }
 
+struct MgLaunchPlan {
+    int ctas, wpc, stage_cap;
+    size_t smem;
+};
+
+// grid geometry: one CTA per SM, `wpc` warps = frame buffers each. For rollouts (every warp runs all steps of
+// its envs) the warp count that balances envs per warp best is chosen; for single steps, the most buffers.
 template <class P>
-static int launch_env(const typename P::K& k, const void* assets, void* state, const uint64_t* rng4,
-                      const mg_step_io* ios, int n_io, int n, int mode, int act_dims, void* stream, int default_wpc) {
-    if (!assets || !state || !ios || n < 0 || n_io < 1) {
-        mg_set_err("NULL pointer, negative n or empty io list");
-        return MG_EINVAL;
-    }
-    for (int t = 0; t < n_io; ++t) {
-        const mg_step_io* io = ios + t;
-        if (!io->obs || (mode == MG_MODE_STEP && (!io->actions || !io->reward || !io->done || !io->info))) {
-            mg_set_err("mg_step_io: obs (and for step: actions, reward, done, info) must be non-NULL");
-            return MG_EINVAL;
-        }
-        if (((uintptr_t)io->obs & 15) || (io->final_obs && ((uintptr_t)io->final_obs & 15))) {
-            mg_set_err("alignment: obs/final_obs must be 16-byte aligned");
-            return MG_EINVAL;
-        }
-    }
-    if (((uintptr_t)assets & 127) || ((uintptr_t)state & 7)) {
-        mg_set_err("alignment: assets 128 B, state 8 B");
-        return MG_EINVAL;
-    }
-    if (n == 0) return 0;
+static int plan_launch(int n, int wpc_req, int default_wpc, bool balance, MgLaunchPlan* out) {
     int dev = 0, sms = 0, smem_max = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
         sms <= 0) {
@@ -262,9 +300,21 @@ static int launch_env(const typename P::K& k, const void* assets, void* state, c
     constexpr int kSlot =
         (((int)sizeof(typename P::State) + 2 * (int)sizeof(typename P::Frame) + (int)sizeof(MgFrameJob) + 16 + 127) / 128) * 128;
     const int per_warp = MG_BUF_STRIDE + kSlot;
-    int wpc = ios->warps_per_cta ? (int)ios->warps_per_cta : default_wpc;
-    if (wpc > 10) wpc = 10;
-    while (wpc > 1 && wpc * per_warp > smem_max) wpc--;
+    int wmax = 10;
+    while (wmax > 1 && wmax * per_warp > smem_max) wmax--;
+    int wpc = wpc_req ? wpc_req : default_wpc;
+    if (wpc > wmax) wpc = wmax;
+    if (!wpc_req && balance && n > sms * wmax) {
+        double best = -1.0;
+        for (int w = wmax; w >= (wmax + 1) / 2; --w) {  // at least half the buffers stay in flight
+            long warps = (long)sms * w;
+            double eff = ((double)n / warps) / (double)((n + warps - 1) / warps);
+            if (eff > best + 0.02) {
+                best = eff;
+                wpc = w;
+            }
+        }
+    }
     int need = (n + sms - 1) / sms;  // spread small batches over all SMs
     if (wpc > need) wpc = need;
     if (wpc < 1) wpc = 1;
@@ -282,10 +332,20 @@ static int launch_env(const typename P::K& k, const void* assets, void* state, c
         cudaGetLastError();
         return (int)e;
     }
+    out->ctas = ctas;
+    out->wpc = wpc;
+    out->stage_cap = stage_cap;
+    out->smem = smem;
+    return 0;
+}
+
+template <class P>
+static int launch_one(const typename P::K& k, const MgKIO& q, const MgLaunchPlan& plan, const void* assets, void* state,
+                      void* stream) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ctas);
-    cfg.blockDim = dim3(wpc * 32);
-    cfg.dynamicSmemBytes = smem;
+    cfg.gridDim = dim3(plan.ctas);
+    cfg.blockDim = dim3(plan.wpc * 32);
+    cfg.dynamicSmemBytes = plan.smem;
     cfg.stream = (cudaStream_t)stream;
     // programmatic dependent launch: this kernel's prologue (asset staging, template loads) may overlap
     // the tail of the previous kernel in the stream; it calls griddepcontrol.wait before touching env data
@@ -293,23 +353,108 @@ static int launch_env(const typename P::K& k, const void* assets, void* state, c
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = getenv("MG_DISABLE_PDL") ? 0 : 1;  // debugging / measurement switch
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mg_env_kernel<P>, k, q, (const uint8_t*)assets, (uint8_t*)state);
+    if (e != cudaSuccess) {
+        mg_set_err(cudaGetErrorString(e));
+        cudaGetLastError();
+        return (int)e;
+    }
+    return 0;
+}
+
+static int check_common(const void* assets, const void* state, int n) {
+    if (!assets || !state || n < 0) {
+        mg_set_err("NULL pointer or negative n");
+        return MG_EINVAL;
+    }
+    if (((uintptr_t)assets & 127) || ((uintptr_t)state & 7)) {
+        mg_set_err("alignment: assets 128 B, state 8 B");
+        return MG_EINVAL;
+    }
+    return 0;
+}
+
+// reset / single steps: one launch per mg_step_io
+template <class P>
+static int launch_env(const typename P::K& k, const void* assets, void* state, const uint64_t* rng4,
+                      const mg_step_io* ios, int n_io, int n, int mode, int act_dims, void* stream, int default_wpc) {
+    if (check_common(assets, state, n)) return MG_EINVAL;
+    if (!ios || n_io < 1) {
+        mg_set_err("empty io list");
+        return MG_EINVAL;
+    }
+    for (int t = 0; t < n_io; ++t) {
+        const mg_step_io* io = ios + t;
+        if (!io->obs || (mode == MG_MODE_STEP && (!io->actions || !io->reward || !io->done || !io->info))) {
+            mg_set_err("mg_step_io: obs (and for step: actions, reward, done, info) must be non-NULL");
+            return MG_EINVAL;
+        }
+        if (((uintptr_t)io->obs & 15) || (io->final_obs && ((uintptr_t)io->final_obs & 15))) {
+            mg_set_err("alignment: obs/final_obs must be 16-byte aligned");
+            return MG_EINVAL;
+        }
+    }
+    if (n == 0) return 0;
+    MgLaunchPlan plan;
+    int rc = plan_launch<P>(n, (int)ios->warps_per_cta, default_wpc, false, &plan);
+    if (rc) return rc;
     for (int t = 0; t < n_io; ++t) {
         MgKIO q;
+        memset(&q, 0, sizeof(q));
         q.io = ios[t];
         q.rng4 = rng4;
         q.mode = mode;
         q.n = n;
-        q.stage_cap = stage_cap;
+        q.stage_cap = plan.stage_cap;
         q.act_dims = act_dims;
-        e = cudaLaunchKernelEx(&cfg, mg_env_kernel<P>, k, q, (const uint8_t*)assets, (uint8_t*)state);
-        if (e != cudaSuccess) {
-            mg_set_err(cudaGetErrorString(e));
-            cudaGetLastError();
-            return (int)e;
-        }
+        q.n_steps = 1;
+        q.ring_n = 1;
+        rc = launch_one<P>(k, q, plan, assets, state, stream);
+        if (rc) return rc;
     }
     return 0;
+}
+
+// rollout: ONE launch runs all n_steps steps
+template <class P>
+static int launch_rollout(const typename P::K& k, const void* assets, void* state, const mg_rollout_io* r, int n,
+                          int act_dims, void* stream, int default_wpc) {
+    if (check_common(assets, state, n)) return MG_EINVAL;
+    if (!r || !r->actions || !r->obs || !r->reward || !r->done || !r->info || r->n_steps < 1 || r->ring < 1) {
+        mg_set_err("mg_rollout_io: actions, obs, reward, done, info must be non-NULL; n_steps, ring >= 1");
+        return MG_EINVAL;
+    }
+    if (((uintptr_t)r->obs & 15) || (r->final_obs && ((uintptr_t)r->final_obs & 15))) {
+        mg_set_err("alignment: obs/final_obs must be 16-byte aligned");
+        return MG_EINVAL;
+    }
+    if (n == 0) return 0;
+    MgLaunchPlan plan;
+    int rc = plan_launch<P>(n, (int)r->warps_per_cta, default_wpc, true, &plan);
+    if (rc) return rc;
+    MgKIO q;
+    memset(&q, 0, sizeof(q));
+    q.io.actions = r->actions;
+    q.io.obs = r->obs;
+    q.io.final_obs = r->final_obs;
+    q.io.reward = r->reward;
+    q.io.done = r->done;
+    q.io.info = r->info;
+    q.io.ground_truth = r->ground_truth;
+    q.io.flags = r->flags | MG_FLAG_AUTORESET;  // a rollout without auto-reset would only idle finished envs
+    q.mode = MG_MODE_STEP;
+    q.n = n;
+    q.stage_cap = plan.stage_cap;
+    q.act_dims = act_dims;
+    q.n_steps = r->n_steps;
+    q.ring_n = r->ring;
+    q.act_stride = (int64_t)n * act_dims;
+    q.obs_stride = (int64_t)n * MG_FRAME_BYTES;
+    q.rew_stride = n;
+    q.done_stride = n;
+    q.info_stride = r->info_per_step ? (int64_t)n * MG_INFO_COLS : 0;
+    return launch_one<P>(k, q, plan, assets, state, stream);
 }
 
 static int mm_act_dims(const mg_mm_params* p) { return p->variant == MG_MM_GRID ? 1 : 2; }
@@ -332,6 +477,13 @@ extern "C" int mg_mm_step_many(const mg_mm_params* p, const void* assets, void* 
     mg_mm_derive(p, &k);
     return launch_env<MMPolicy>(k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, mm_act_dims(p), stream, 10);
 }
+extern "C" int mg_mm_rollout(const mg_mm_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
+                             void* stream) {
+    if (mg_mm_check_params(p)) return MG_EINVAL;
+    MgMMK k;
+    mg_mm_derive(p, &k);
+    return launch_rollout<MMPolicy>(k, assets, state, r, n, mm_act_dims(p), stream, 10);
+}
 
 extern "C" int mg_mp_reset(const mg_mp_params* p, const void* assets, void* state, const uint64_t* rng4,
                            const mg_step_io* io, int n, void* stream) {
@@ -351,25 +503,28 @@ extern "C" int mg_mp_step_many(const mg_mp_params* p, const void* assets, void* 
     mg_mp_derive(p, &k);
     return launch_env<MPPolicy>(k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, 2, stream, 10);
 }
+extern "C" int mg_mp_rollout(const mg_mp_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
+                             void* stream) {
+    if (mg_mp_check_params(p)) return MG_EINVAL;
+    MgMPK k;
+    mg_mp_derive(p, &k);
+    return launch_rollout<MPPolicy>(k, assets, state, r, n, 2, stream, 10);
+}
 
 // Searing Spotlights: not built yet — the symbols fail loudly.
-extern "C" int mg_ss_check_params(const mg_ss_params*) {
+static int ss_missing() {
     mg_set_err("SearingSpotlights kernels are not built yet");
     return MG_EINVAL;
 }
-extern "C" long mg_ss_build_assets(const mg_ss_params*, void*, size_t) {
-    mg_set_err("SearingSpotlights kernels are not built yet");
-    return MG_EINVAL;
-}
+extern "C" int mg_ss_check_params(const mg_ss_params*) { return ss_missing(); }
+extern "C" long mg_ss_build_assets(const mg_ss_params*, void*, size_t) { return ss_missing(); }
 extern "C" int mg_ss_reset(const mg_ss_params*, const void*, void*, const uint64_t*, const mg_step_io*, int, void*) {
-    mg_set_err("SearingSpotlights kernels are not built yet");
-    return MG_EINVAL;
+    return ss_missing();
 }
-extern "C" int mg_ss_step(const mg_ss_params*, const void*, void*, const mg_step_io*, int, void*) {
-    mg_set_err("SearingSpotlights kernels are not built yet");
-    return MG_EINVAL;
-}
+extern "C" int mg_ss_step(const mg_ss_params*, const void*, void*, const mg_step_io*, int, void*) { return ss_missing(); }
 extern "C" int mg_ss_step_many(const mg_ss_params*, const void*, void*, const mg_step_io*, int, int, void*) {
-    mg_set_err("SearingSpotlights kernels are not built yet");
-    return MG_EINVAL;
+    return ss_missing();
+}
+extern "C" int mg_ss_rollout(const mg_ss_params*, const void*, void*, const mg_rollout_io*, int, void*) {
+    return ss_missing();
 }

@@ -39,10 +39,11 @@ MG_HD int mg_pymod(int a, int b) {
 }
 MG_HD void mg_cmd_delta(int k, int& dx, int& dy) {
     // Command.COMMANDS, pygame_assets.py:242-252: right, down, left, up, stay, right_down, right_up, left_down, left_up
-    const int8_t DX[9] = {1, 0, -1, 0, 0, 1, 1, -1, -1};
-    const int8_t DY[9] = {0, 1, 0, -1, 0, 1, -1, 1, -1};
-    dx = DX[k];
-    dy = DY[k];
+    //   dx = { 1, 0,-1, 0, 0, 1, 1,-1,-1 }   dy = { 0, 1, 0,-1, 0, 1,-1, 1,-1 }   packed as (d + 1) in 2-bit fields
+    const uint32_t DX = 2u | (1u << 2) | (0u << 4) | (1u << 6) | (1u << 8) | (2u << 10) | (2u << 12) | (0u << 14) | (0u << 16);
+    const uint32_t DY = 1u | (2u << 2) | (1u << 4) | (0u << 6) | (1u << 8) | (2u << 10) | (0u << 12) | (2u << 14) | (0u << 16);
+    dx = (int)((DX >> (2 * k)) & 3u) - 1;
+    dy = (int)((DY >> (2 * k)) & 3u) - 1;
 }
 MG_HD int mg_choice(MgRng& r, const mg_choice_list& c) {
     return c.v[(int)mg_integers(r, 0, c.n)];
@@ -106,7 +107,7 @@ MG_HD int mg_mm_show_entry(const MgMMState& s, int e) {
 }
 
 // reset(): RNG draw order is part of the contract (mortar_mayhem.py:238,174,150-183,247-248,262-263)
-MG_HD void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, double* gt) {
+MG_HD_NOINLINE void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, double* gt) {
     const int size = k.size;
     const bool endless = k.p.variant == MG_MM_ENDLESS;
     MgRng r = s.rng;
@@ -141,15 +142,20 @@ MG_HD void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, double* g
         n = mg_choice(r, k.p.command_count);
         int simx = px, simy = py;
         for (int c = 0; c < n; ++c) {
-            uint8_t valid[9];
+            // available_commands: the first `allowed_commands` commands that keep the target inside the arena
+            // (bit q set = command q; a command is invalid iff it steps off the arena on x or on y)
+            uint32_t valid = (1u << k.p.allowed_commands) - 1u;
+            if (simx >= size - 1) valid &= ~0x061u;  // dx = +1: right, right_down, right_up
+            if (simx <= 0) valid &= ~0x184u;         // dx = -1: left, left_down, left_up
+            if (simy >= size - 1) valid &= ~0x0A2u;  // dy = +1: down, right_down, left_down
+            if (simy <= 0) valid &= ~0x148u;         // dy = -1: up, right_up, left_up
             int nv = 0;
-            for (int q = 0; q < k.p.allowed_commands; ++q) {
-                int dx, dy;
-                mg_cmd_delta(q, dx, dy);
-                int ax = simx + dx, ay = simy + dy;
-                if (ax >= 0 && ax < size && ay >= 0 && ay < size) valid[nv++] = (uint8_t)q;
-            }
-            int q = valid[(int)mg_integers(r, 0, nv)];
+            for (uint32_t m = valid; m; m &= m - 1u) nv++;
+            int pick = (int)mg_integers(r, 0, nv), q = 0;
+            MG_NOUNROLL
+            for (;; ++q)  // the pick-th set bit
+                if ((valid >> q) & 1u)
+                    if (pick-- == 0) break;
             s.commands[c] = (uint8_t)q;
             int dx, dy;
             mg_cmd_delta(q, dx, dy);

@@ -40,7 +40,7 @@ MG_HD int mg_mp_neighbours(int i, int j, int* out) {
 
 // MysteryPath.__init__: returns the path as a 49-bit mask, or 0 if A* ran out of open nodes
 // (the reference raises Exception("No valid path found"), pygame_assets.py:724)
-MG_HD uint64_t mg_mp_generate(MgRng& r, int sx, int sy, int ex, int ey) {
+MG_HD_NOINLINE uint64_t mg_mp_generate(MgRng& r, int sx, int sy, int ex, int ey) {
     const int n = MG_MP_GRID;
     uint64_t wall = 0;
     for (int i = 0; i < n; ++i)
@@ -152,7 +152,7 @@ MG_HD void mg_mp_draw(const MgMPK& k, const MgMPState& s, int cross, MgMPDraw& d
     d.gy = s.ey;
 }
 
-MG_HD void mg_mp_reset_env(const MgMPK& k, MgMPState& s, MgMPDraw& d) {
+MG_HD_NOINLINE void mg_mp_reset_env(const MgMPK& k, MgMPState& s, MgMPDraw& d) {
     const int g = MG_MP_GRID;
     MgRng r = s.rng;
     s.t = 0;

@@ -15,7 +15,7 @@ MG_HD mg_u128 mg_pcg_mult() {
     return ((mg_u128)0x2360ED051FC65DA4ull << 64) | (mg_u128)0x4385DF649FCCF645ull;
 }
 
-MG_HD uint64_t mg_next64(MgRng& r) {
+MG_HD_NOINLINE uint64_t mg_next64(MgRng& r) {
     mg_u128 s = ((mg_u128)r.state_hi << 64) | r.state_lo;
     mg_u128 inc = ((mg_u128)r.inc_hi << 64) | r.inc_lo;
     s = s * mg_pcg_mult() + inc;
@@ -38,7 +38,7 @@ MG_HD uint32_t mg_next32(MgRng& r) {
 }
 
 // Generator.integers(lo, hi) for int64 bounds with hi - lo <= 2^32 (all call sites of the reference)
-MG_HD int64_t mg_integers(MgRng& r, int64_t lo, int64_t hi) {
+MG_HD_NOINLINE int64_t mg_integers(MgRng& r, int64_t lo, int64_t hi) {
     uint64_t rng = (uint64_t)(hi - 1 - lo);
     if (rng == 0) return lo;
     if (rng == 0xFFFFFFFFull) return lo + (int64_t)mg_next32(r);

@@ -24,6 +24,10 @@ struct MgKIO {
     int32_t n;
     int32_t stage_cap; // kernel: shared-memory bytes available for staging the asset header + sprite lists
     int32_t act_dims; // int64 entries per env in io.actions (2 = MultiDiscrete([3,3]), 1 = Discrete(4))
+    // rollout (n_steps > 1): step t reads actions + t * act_stride and writes obs slot t % ring_n,
+    // reward/done/info rows t (strides in elements; info_stride 0 = one shared info matrix)
+    int32_t n_steps, ring_n;
+    int64_t act_stride, obs_stride, rew_stride, done_stride, info_stride;
 };
 
 struct MgFrameJob {      // what the logic lane hands to the warp: up to two frames for this env-step
@@ -34,8 +38,11 @@ struct MgFrameJob {      // what the logic lane hands to the warp: up to two fra
 // One env, one call: reset (mode RESET) or step (+ auto-reset) — the same control flow for every env type.
 // `E` supplies reset_env / step_env. a0/a1 are this env's (prefetched) action components.
 template <class E>
-MG_HDN void mg_env_logic(const typename E::K& k, const MgKIO& q, int env, typename E::State& s, int a0, int a1,
+MG_HDN void mg_env_logic(const typename E::K& k, const MgKIO& q, int env, int t, typename E::State& s, int a0, int a1,
                          MgFrameJob& job, typename E::Frame* fr) {
+    double* const reward_out = q.io.reward + (size_t)t * q.rew_stride + env;
+    uint8_t* const done_out = q.io.done + (size_t)t * q.done_stride + env;
+    double* const info_out = q.io.info + (size_t)t * q.info_stride + MG_INFO_COLS * (size_t)env;
     double* gt = q.io.ground_truth ? q.io.ground_truth + 2 * (size_t)env : nullptr;
     job.nframes = 0;
     if (q.mode == MG_MODE_RESET) {
@@ -55,14 +62,14 @@ MG_HDN void mg_env_logic(const typename E::K& k, const MgKIO& q, int env, typena
         return;
     }
     if (!s.live) {  // finished (or never reset): the step is ignored
-        q.io.reward[env] = 0.0;
-        q.io.done[env] = 1;
+        *reward_out = 0.0;
+        *done_out = 1;
         return;
     }
     double reward;
-    bool done = E::step_env(k, s, a0, a1, reward, q.io.info + MG_INFO_COLS * (size_t)env, fr[0], gt);
-    q.io.reward[env] = reward;
-    q.io.done[env] = done ? 1 : 0;
+    bool done = E::step_env(k, s, a0, a1, reward, info_out, fr[0], gt);
+    *reward_out = reward;
+    *done_out = done ? 1 : 0;
     job.nframes = 1;
     job.to_final[0] = 0;
     if (done && (q.io.flags & MG_FLAG_AUTORESET)) {
@@ -86,9 +93,9 @@ struct MMPolicy {
                                double* gt) {
         return mg_mm_step_env(k, s, a0, a1, reward, info, f, gt);
     }
-    static MG_HDN void logic(const K& k, const MgKIO& q, int env, State& s, int a0, int a1, MgFrameJob& job,
+    static MG_HDN void logic(const K& k, const MgKIO& q, int env, int t, State& s, int a0, int a1, MgFrameJob& job,
                              Frame* fr) {
-        mg_env_logic<MMPolicy>(k, q, env, s, a0, a1, job, fr);
+        mg_env_logic<MMPolicy>(k, q, env, t, s, a0, a1, job, fr);
     }
     template <class Ctx>
     static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K& k, const Frame& f) {
@@ -108,9 +115,9 @@ struct MPPolicy {
     static MG_HD bool step_env(const K& k, State& s, int a0, int a1, double& reward, double* info, Frame& f, double*) {
         return mg_mp_step_env(k, s, a0, a1, reward, info, f);
     }
-    static MG_HDN void logic(const K& k, const MgKIO& q, int env, State& s, int a0, int a1, MgFrameJob& job,
+    static MG_HDN void logic(const K& k, const MgKIO& q, int env, int t, State& s, int a0, int a1, MgFrameJob& job,
                              Frame* fr) {
-        mg_env_logic<MPPolicy>(k, q, env, s, a0, a1, job, fr);
+        mg_env_logic<MPPolicy>(k, q, env, t, s, a0, a1, job, fr);
     }
     template <class Ctx>
     static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f) {

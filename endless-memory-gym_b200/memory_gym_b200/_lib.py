@@ -81,7 +81,16 @@ class StepIO(C.Structure):
     _fields_ = [
         ("actions", C.c_void_p), ("obs", C.c_void_p), ("final_obs", C.c_void_p), ("reward", C.c_void_p),
         ("done", C.c_void_p), ("info", C.c_void_p), ("ground_truth", C.c_void_p), ("reset_mask", C.c_void_p),
-        ("flags", C.c_uint32), ("warps_per_cta", C.c_uint32),
+        ("flags", C.c_uint32), ("warps_per_cta", C.c_uint32), ("trace", C.c_void_p),
+    ]
+
+
+class RolloutIO(C.Structure):
+    _fields_ = [
+        ("actions", C.c_void_p), ("obs", C.c_void_p), ("final_obs", C.c_void_p), ("reward", C.c_void_p),
+        ("done", C.c_void_p), ("info", C.c_void_p), ("ground_truth", C.c_void_p),
+        ("n_steps", C.c_int32), ("ring", C.c_int32), ("info_per_step", C.c_int32), ("flags", C.c_uint32),
+        ("warps_per_cta", C.c_uint32), ("pad0", C.c_uint32),
     ]
 
 
@@ -113,6 +122,7 @@ def lib():
         getattr(L, f"mg_{fam}_reset").argtypes = [C.POINTER(P), vp, vp, vp, C.POINTER(StepIO), i32, vp]
         getattr(L, f"mg_{fam}_step").argtypes = [C.POINTER(P), vp, vp, C.POINTER(StepIO), i32, vp]
         getattr(L, f"mg_{fam}_step_many").argtypes = [C.POINTER(P), vp, vp, C.POINTER(StepIO), i32, i32, vp]
+        getattr(L, f"mg_{fam}_rollout").argtypes = [C.POINTER(P), vp, vp, C.POINTER(RolloutIO), i32, vp]
         b = getattr(L, f"mg_{fam}_build_assets")
         b.restype = C.c_long
         b.argtypes = [C.POINTER(P), i32, vp, C.c_size_t] if fam == "mm" else [C.POINTER(P), vp, C.c_size_t]

@@ -67,6 +67,11 @@ class _CudaBackend:
         if rc:
             L.check(rc, f"mg_{family}_step")
 
+    def rollout(self, family, params, assets, state, rio, n, stream):
+        rc = getattr(self.lib, f"mg_{family}_rollout")(C.byref(params), assets, state, C.byref(rio), n, stream)
+        if rc:
+            L.check(rc, f"mg_{family}_rollout")
+
     def step_many(self, family, params, assets, state, ios, n_steps, n, stream):
         rc = getattr(self.lib, f"mg_{family}_step_many")(C.byref(params), assets, state, ios, n_steps, n, stream)
         if rc:
@@ -240,14 +245,7 @@ class MemoryGymVecEnv:
             info["final_ground_truth"] = self.info[:, L.MG_INFO_GT0:L.MG_INFO_GT1 + 1]
         return obs, self.reward, done, self.truncated, info
 
-    def rollout(self, actions, obs_out, reward_out, done_out, info_out=None):
-        """``T`` consecutive steps with given actions in ONE library call (``mg_*_step_many``: T kernel
-        launches enqueued back to back, no Python between them) — the reference's ``bench.py`` loop shape
-        (pre-sampled random actions) and scripted roll-outs.
-
-        ``actions`` int64[T, N, 2] (or [T, N]); ``obs_out`` uint8[T', N, 84, 84, 3] with T' >= 1 slots used
-        round-robin (a rollout ring); ``reward_out`` float64[T, N]; ``done_out`` bool/uint8[T, N];
-        ``info_out`` optional float64[T, N, 8] (else only the last finished episode's stats per env are kept)."""
+    def _check_rollout_buffers(self, actions, obs_out, reward_out, done_out, info_out):
         if self._params is None:
             raise L.MemGymError("rollout() called before reset()")
         T = actions.shape[0]
@@ -260,6 +258,36 @@ class MemoryGymVecEnv:
         if tuple(actions.shape[1:]) != tuple(self._actions_dev.shape) or tuple(obs_out.shape[1:]) != (self.num_envs, 84, 84, 3) \
                 or tuple(reward_out.shape) != (T, self.num_envs) or tuple(done_out.shape) != (T, self.num_envs):
             raise ValueError("rollout buffer shapes do not match (T, num_envs)")
+        if info_out is not None and (tuple(info_out.shape) != (T, self.num_envs, L.MG_INFO_COLS)
+                                     or info_out.dtype != torch.float64 or not info_out.is_contiguous()):
+            raise ValueError("info_out must be a contiguous float64[T, N, 8] tensor")
+        return T
+
+    def rollout(self, actions, obs_out, reward_out, done_out, info_out=None):
+        """``T`` consecutive steps with given actions in ONE kernel launch (``mg_*_rollout``): every warp runs
+        all T steps of its envs back to back with the env record resident on chip. The reference's
+        ``bench.py`` loop shape (pre-sampled random actions) and scripted roll-outs. Always auto-resets.
+
+        ``actions`` int64[T, N, 2] (or [T, N]); ``obs_out`` uint8[R, N, 84, 84, 3], step t writes slot t % R
+        (R = T keeps every frame, a small R is a ring); ``reward_out`` float64[T, N]; ``done_out``
+        bool/uint8[T, N]; ``info_out`` optional float64[T, N, 8] (else ``self.info`` keeps each env's last
+        finished episode)."""
+        T = self._check_rollout_buffers(actions, obs_out, reward_out, done_out, info_out)
+        r = L.RolloutIO()
+        r.actions, r.obs = actions.data_ptr(), obs_out.data_ptr()
+        r.final_obs = self._io.final_obs
+        r.reward, r.done = reward_out.data_ptr(), done_out.data_ptr()
+        r.info = info_out.data_ptr() if info_out is not None else self._io.info
+        r.ground_truth = self._io.ground_truth
+        r.n_steps, r.ring, r.info_per_step = T, obs_out.shape[0], int(info_out is not None)
+        r.flags, r.warps_per_cta = L.MG_FLAG_AUTORESET, self.warps_per_cta
+        self._be.rollout(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(), r,
+                         self.num_envs, self._be.stream(self.device))
+
+    def step_many(self, actions, obs_out, reward_out, done_out, info_out=None):
+        """Same contract as ``rollout`` but as T separate step launches enqueued by one library call
+        (``mg_*_step_many``), honouring this env's ``auto_reset`` setting."""
+        T = self._check_rollout_buffers(actions, obs_out, reward_out, done_out, info_out)
         key = (T, actions.data_ptr(), obs_out.data_ptr(), obs_out.shape[0], reward_out.data_ptr(), done_out.data_ptr(),
                info_out.data_ptr() if info_out is not None else 0)
         if getattr(self, "_many_key", None) != key:

@@ -45,6 +45,7 @@ extern "C" {
 #define MG_SCREEN 84
 #define MG_OBS_BYTES (84 * 84 * 3) /* 21168 bytes per env, [x][y][c] */
 #define MG_INFO_COLS 8             /* doubles per env in the info matrix */
+#define MG_TRACE_COLS 8
 #define MG_MAX_CHOICES 16          /* max length of a list-valued reset option */
 #define MG_MM_MAX_COMMANDS 152     /* capacity of the per-env command list */
 #define MG_MM_STATE_BYTES 256      /* one env record (Mortar Mayhem family) */
@@ -166,7 +167,29 @@ typedef struct mg_step_io {
     const uint8_t* reset_mask; /* reset only, nullable: [n], reset env i iff mask[i] != 0 */
     uint32_t flags;         /* MG_FLAG_* */
     uint32_t warps_per_cta; /* 0 = library default; tuning knob (frame buffers resident per SM) */
+    uint64_t* trace;        /* nullable: [n][MG_TRACE_COLS] uint64, per-env phase timestamps (globaltimer ns):   */
+                            /* 0 kernel entry, 1 prologue done, 2 dependency wait done, 3 record in smem,      */
+                            /* 4 logic done, 5 frame composed, 6 bulk store issued, 7 SM id                      */
 } mg_step_io;
+
+/* A whole rollout in one launch: T = n_steps consecutive steps with given actions (the reference's bench.py
+ * loop with pre-sampled random actions; scripted policies). Every warp runs all T steps of its envs back to
+ * back with the env record resident on chip; finished envs are always auto-reset. */
+typedef struct mg_rollout_io {
+    const int64_t* actions; /* [T][n][2] or [T][n] */
+    uint8_t* obs;           /* [ring][n][84][84][3]: step t writes slot t % ring (a rollout ring / [T] buffer) */
+    uint8_t* final_obs;     /* nullable: [n][84][84][3], terminal frame of the env's LAST finished episode */
+    double* reward;         /* [T][n] */
+    uint8_t* done;          /* [T][n] */
+    double* info;           /* [T][n][MG_INFO_COLS] if info_per_step, else [n][MG_INFO_COLS] (last finished episode) */
+    double* ground_truth;   /* nullable: [n][2], of the last step */
+    int32_t n_steps;
+    int32_t ring;
+    int32_t info_per_step;
+    uint32_t flags;
+    uint32_t warps_per_cta; /* 0 = library picks the count that balances envs per warp */
+    uint32_t pad0;
+} mg_rollout_io;
 
 /* ---- assets & seeding (host side) -------------------------------------------------------------- */
 /* Draw the static sprites / background templates for an option set with the library's own
@@ -206,6 +229,9 @@ int mg_mm_step(const mg_mm_params* p, const void* assets, void* state, const mg_
 int mg_mm_step_many(const mg_mm_params* p, const void* assets, void* state, const mg_step_io* ios, int n_steps,
                     int n, void* stream);
 
+int mg_mm_rollout(const mg_mm_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
+                  void* stream);
+
 int mg_mp_reset(const mg_mp_params* p, const void* assets, void* state, const uint64_t* rng4,
                 const mg_step_io* io, int n, void* stream);
 int mg_mp_step(const mg_mp_params* p, const void* assets, void* state, const mg_step_io* io, int n,
@@ -214,6 +240,9 @@ int mg_mp_step(const mg_mp_params* p, const void* assets, void* state, const mg_
 int mg_mp_step_many(const mg_mp_params* p, const void* assets, void* state, const mg_step_io* ios, int n_steps,
                     int n, void* stream);
 
+int mg_mp_rollout(const mg_mp_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
+                  void* stream);
+
 int mg_ss_reset(const mg_ss_params* p, const void* assets, void* state, const uint64_t* rng4,
                 const mg_step_io* io, int n, void* stream);
 int mg_ss_step(const mg_ss_params* p, const void* assets, void* state, const mg_step_io* io, int n,
@@ -221,6 +250,9 @@ int mg_ss_step(const mg_ss_params* p, const void* assets, void* state, const mg_
 
 int mg_ss_step_many(const mg_ss_params* p, const void* assets, void* state, const mg_step_io* ios, int n_steps,
                     int n, void* stream);
+
+int mg_ss_rollout(const mg_ss_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
+                  void* stream);
 
 /* Option validation without a device: 0 if the reset/step kernels accept `p`, else MG_EINVAL with
  * mg_last_error() naming the offending field. */

@@ -23,6 +23,9 @@ int run(const typename P::K& k, const void* assets, void* state, const uint64_t*
     typedef typename P::State State;
     typedef typename P::Frame Frame;
     MgKIO q;
+    memset(&q, 0, sizeof(q));
+    q.n_steps = 1;
+    q.ring_n = 1;
     q.io = *io;
     q.rng4 = rng4;
     q.mode = mode;
@@ -42,7 +45,7 @@ int run(const typename P::K& k, const void* assets, void* state, const uint64_t*
             a0 = (int)io->actions[(size_t)env * act_dims];
             if (act_dims > 1) a1 = (int)io->actions[(size_t)env * act_dims + 1];
         }
-        P::logic(k, q, env, *st, a0, a1, job, fr);
+        P::logic(k, q, env, 0, *st, a0, a1, job, fr);
         for (int fi = 0; fi < job.nframes; ++fi) {
             uint8_t* dst = (job.to_final[fi] ? io->final_obs : io->obs) + (size_t)env * MG_FRAME_BYTES;
             P::compose(ctx, buf, view, k, fr[fi]);

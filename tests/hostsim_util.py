@@ -68,3 +68,19 @@ class HostSimBackend:
     def step_many(self, family, params, assets, state, ios, n_steps, n, stream):
         for t in range(n_steps):
             self.step(family, params, assets, state, ios[t], n, stream)
+
+    def rollout(self, family, params, assets, state, rio, n, stream):
+        """mg_*_rollout semantics on the host: T steps, step t -> obs slot t % ring."""
+        L = self.L
+        A = 1 if (family == "mm" and params.variant == L.MG_MM_GRID) else 2
+        for t in range(rio.n_steps):
+            io = L.StepIO()
+            io.actions = rio.actions + t * n * A * 8
+            io.obs = rio.obs + (t % rio.ring) * n * L.MG_OBS_BYTES
+            io.final_obs = rio.final_obs
+            io.reward = rio.reward + t * n * 8
+            io.done = rio.done + t * n
+            io.info = rio.info + (t * n * L.MG_INFO_COLS * 8 if rio.info_per_step else 0)
+            io.ground_truth = rio.ground_truth
+            io.flags = rio.flags | L.MG_FLAG_AUTORESET
+            self.step(family, params, assets, state, io, n, stream)

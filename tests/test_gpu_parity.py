@@ -98,9 +98,11 @@ def test_masked_reset_and_no_autoreset():
     env = mg.make("MortarMayhem-v0", num_envs=16, device=DEV, auto_reset=False)
     env.reset(seed=3)
     acts = _random_actions(env, 80, 5)
-    for t in range(80):
-        obs, r, d, _, _ = env.step(acts[t])
-    assert d.all()  # random play never survives the first verification; finished envs stay finished
+    for t in range(3000):
+        obs, r, d, _, _ = env.step(acts[t % 80])
+        if d.all():  # finished envs stay finished (done keeps being reported) until they are reset
+            break
+    assert d.all()
     before = obs.clone()
     mask = torch.zeros(16, dtype=torch.bool, device=DEV)
     mask[::2] = True
@@ -138,8 +140,9 @@ def test_abi_rejects_bad_arguments():
 
 @pytest.mark.parametrize("env_id", ["MortarMayhem-v0", "MortarMayhem-Grid-v0", "MysteryPath-v0"])
 def test_rollout_equals_step_loop(env_id):
-    """mg_*_step_many (T launches enqueued by one call, programmatic dependent launch between them) gives
-    exactly what T separate step() calls give."""
+    """mg_*_rollout (ONE launch, every warp runs all T steps of its envs) and mg_*_step_many (T launches
+    enqueued by one call, programmatic dependent launch between them) give exactly what T separate
+    step() calls give."""
     n, T = 500, 90
     opts = {"max_steps": 40} if env_id == "MysteryPath-v0" else None
     a = mg.make(env_id, num_envs=n, device=DEV)
@@ -152,6 +155,12 @@ def test_rollout_equals_step_loop(env_id):
     dn = torch.zeros((T, n), dtype=torch.bool, device=DEV)
     inf = torch.zeros((T, n, 8), dtype=torch.float64, device=DEV)
     a.rollout(acts, ring, rew, dn, inf)
+    c = mg.make(env_id, num_envs=n, device=DEV, warps_per_cta=3)
+    c.reset(seed=5, options=opts)
+    ring2, rew2, dn2, inf2 = torch.zeros_like(ring), torch.zeros_like(rew), torch.zeros_like(dn), torch.zeros_like(inf)
+    c.step_many(acts, ring2, rew2, dn2, inf2)
+    assert torch.equal(ring, ring2) and torch.equal(rew, rew2) and torch.equal(dn, dn2) and torch.equal(c.state, a.state)
+    assert torch.equal(inf[dn], inf2[dn])
     for t in range(T):
         o, r, d, _, info = b.step(acts[t])
         assert torch.equal(r, rew[t]) and torch.equal(d, dn[t]), t
