@@ -41,6 +41,17 @@ __device__ __forceinline__ void mg_bulk_store(void* gdst, const void* ssrc, uint
                  "r"(mg_smem_u32(ssrc)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mg_bulk_store_hint(void* gdst, const void* ssrc, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(
+                     __cvta_generic_to_global(gdst)),
+                 "r"(mg_smem_u32(ssrc)), "r"(bytes), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t mg_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void mg_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void mg_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // all but the newest `keep` bulk groups have fully completed (their global writes are performed)
@@ -159,6 +170,7 @@ __global__ void __launch_bounds__(320, 1)
 
     const int T = q.n_steps;
     const bool stepping = q.mode == MG_MODE_STEP;
+    const uint64_t evict_first = mg_policy_evict_first();
     // ---- first record + first actions in flight while the template lands --------------------------------
     uint64_t pre[kPerLane];
     int64_t act0 = 0, act1 = 0;
@@ -235,7 +247,10 @@ __global__ void __launch_bounds__(320, 1)
                     // rollout: the same address is rewritten ring_n steps later (final_obs: at the next done);
                     // the earlier bulk write must have been performed before this one is issued
                     if (T > 1) mg_bulk_wait_done(to_final ? 0 : q.ring_n - 1);
-                    mg_bulk_store(dst, buf, MG_FRAME_BYTES);
+                    if (q.io.flags & MG_FLAG_STREAM_OBS)
+                        mg_bulk_store_hint(dst, buf, MG_FRAME_BYTES, evict_first);
+                    else
+                        mg_bulk_store(dst, buf, MG_FRAME_BYTES);
                     mg_bulk_commit();
                     if (trow) trow[6] = mg_now();
                 }

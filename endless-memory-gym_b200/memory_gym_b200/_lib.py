@@ -20,6 +20,7 @@ MG_MM_STATE_BYTES = 256
 MG_MP_STATE_BYTES = 128
 MG_SS_STATE_BYTES = 2048
 MG_FLAG_AUTORESET = 1
+MG_FLAG_STREAM_OBS = 2
 MG_MM_CONTINUOUS, MG_MM_GRID, MG_MM_ENDLESS = 0, 1, 2
 (MG_INFO_REWARD, MG_INFO_LENGTH, MG_INFO_SUCCESS, MG_INFO_A, MG_INFO_B, MG_INFO_GT0, MG_INFO_GT1) = range(7)
 

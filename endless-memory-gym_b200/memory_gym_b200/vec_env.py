@@ -95,7 +95,7 @@ class MemoryGymVecEnv:
     metadata = {"render_modes": ["rgb_array"], "render_fps": 25}
 
     def __init__(self, env_id, num_envs=1, device="cuda", auto_reset=True, final_obs=False, env_offset=0,
-                 warps_per_cta=0, _backend=None):
+                 warps_per_cta=0, stream_obs=None, _backend=None):
         self.spec_ = _spec(env_id)
         self.env_id = env_id
         self.num_envs = int(num_envs)
@@ -134,7 +134,11 @@ class MemoryGymVecEnv:
         self._io.done = self.done.data_ptr()
         self._io.info = self.info.data_ptr()
         self._io.ground_truth = self.ground_truth.data_ptr() if self.has_ground_truth_info else None
-        self._io.flags = L.MG_FLAG_AUTORESET if self.auto_reset else 0
+        # stream_obs: write observations with an L2 evict-first policy. Default: on for rollout() (frames are
+        # not re-read soon; measured +13 % HBM write throughput), off for step() (the policy reads obs next).
+        self._stream_step = L.MG_FLAG_STREAM_OBS if stream_obs else 0
+        self._stream_rollout = L.MG_FLAG_STREAM_OBS if (stream_obs is None or stream_obs) else 0
+        self._io.flags = (L.MG_FLAG_AUTORESET if self.auto_reset else 0) | self._stream_step
         self._io.warps_per_cta = self.warps_per_cta
         self.reset_params = None
         self._params = None
@@ -280,7 +284,7 @@ class MemoryGymVecEnv:
         r.info = info_out.data_ptr() if info_out is not None else self._io.info
         r.ground_truth = self._io.ground_truth
         r.n_steps, r.ring, r.info_per_step = T, obs_out.shape[0], int(info_out is not None)
-        r.flags, r.warps_per_cta = L.MG_FLAG_AUTORESET, self.warps_per_cta
+        r.flags, r.warps_per_cta = L.MG_FLAG_AUTORESET | self._stream_rollout, self.warps_per_cta
         self._be.rollout(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(), r,
                          self.num_envs, self._be.stream(self.device))
 

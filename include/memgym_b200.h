@@ -71,6 +71,8 @@ extern "C" {
                              /* frame and the terminal frame goes to final_obs. Without it a finished env keeps   */
                              /* its terminal frame and ignores further steps until mg_*_reset.                    */
 
+#define MG_FLAG_STREAM_OBS 2u /* write observations with an L2 evict-first policy (they are not re-read soon) */
+
 typedef struct mg_choice_list {
     int32_t n;
     int32_t v[MG_MAX_CHOICES];

@@ -34,10 +34,10 @@ def run(n, wpc, reps=6, ring_mb=None):
     return us, n * 21705 / us / 1e3
 
 
-for n in (148, 1480, 2960, 4096, 8192, 16384, 32768, 65536):
-    for wpc in (10,):
-        us, gbs = run(n, wpc)
-        print(f"n={n:6d} wpc={wpc:2d}  {us:8.2f} us/step  {n / us:8.2f} M env-steps/s  {gbs:7.1f} GB/s", flush=True)
-for wpc in (1, 2, 4, 6, 8, 10):
+sizes = [int(v) for v in os.environ.get("SWEEP_N", "148,1480,4096,8192,32768").split(",")]
+for n in sizes:
+    us, gbs = run(n, 0)
+    print(f"n={n:6d} wpc=auto  {us:8.2f} us/step  {n / us:8.2f} M env-steps/s  {gbs:7.1f} GB/s", flush=True)
+for wpc in [int(v) for v in os.environ.get("SWEEP_WPC", "5,6,7,8,9,10").split(",")]:
     us, gbs = run(4096, wpc)
     print(f"n=  4096 wpc={wpc:2d}  {us:8.2f} us/step  {4096 / us:8.2f} M env-steps/s  {gbs:7.1f} GB/s", flush=True)
