@@ -38,3 +38,27 @@ def test_golden_batched_autoreset(name, backend):
 def test_rollout_vs_oracle(env_id, options, backend):
     episodes = rollout_vs_oracle(env_id, options, n_envs=8, steps=150, seed0=1000, device="cpu", backend=backend)
     assert episodes > 0
+
+
+def test_rollout_equals_step_loop_hostsim(backend):
+    """rollout() (slot t % ring, per-step reward/done/info rows) == T step() calls, on the host harness."""
+    import numpy as np
+    import torch
+    import memory_gym_b200 as mg
+    n, T = 6, 130
+    a = mg.MemoryGymVecEnv("MortarMayhem-v0", n, device="cpu", _backend=backend)
+    b = mg.MemoryGymVecEnv("MortarMayhem-v0", n, device="cpu", _backend=backend)
+    acts = torch.as_tensor(np.random.default_rng(1).integers(0, 3, (T, n, 2)))
+    a.reset(seed=9)
+    b.reset(seed=9)
+    ring = torch.zeros((4, n, 84, 84, 3), dtype=torch.uint8)
+    rew, dn = torch.zeros((T, n), dtype=torch.float64), torch.zeros((T, n), dtype=torch.bool)
+    inf = torch.zeros((T, n, 8), dtype=torch.float64)
+    a.rollout(acts, ring, rew, dn, inf)
+    for t in range(T):
+        o, r, d, _, info = b.step(acts[t])
+        assert torch.equal(r, rew[t]) and torch.equal(d, dn[t])
+        assert torch.equal(info["episode"][d], inf[t][d])
+        if t >= T - 4:
+            assert torch.equal(o, ring[t % 4])
+    assert dn.any() and torch.equal(a.state, b.state)
