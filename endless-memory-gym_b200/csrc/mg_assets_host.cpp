@@ -23,6 +23,9 @@ struct Builder {
     MgAssetHeader hdr;
     std::vector<uint32_t> entries;
     std::vector<std::vector<uint8_t>> templates;
+    std::vector<uint8_t> dense[MG_SPR_COUNT];  // w*h palette indices, 255 = transparent
+    std::vector<int8_t> discs;                 // filled-circle row spans (SS spotlights / coins)
+    std::vector<double> trig;                  // (cos, sin) of integer degrees
     int n_pal = 0;
 
     Builder() {
@@ -72,6 +75,54 @@ struct Builder {
         return true;
     }
 
+    // dense bitmap of the same sprite: O(1) "what does this sprite show at (u, v)" for per-pixel composition
+    bool add_dense(int slot, const Surface& s) {
+        dense[slot].assign((size_t)s.w * s.h, 255);
+        for (int y = 0; y < s.h; ++y)
+            for (int x = 0; x < s.w; ++x) {
+                uint32_t v = s.at(x, y);
+                if (s.has_key && v == s.key) continue;
+                int pi = pal_index(v);
+                if (pi < 0 || pi >= 255) return false;
+                dense[slot][(size_t)y * s.w + x] = (uint8_t)pi;
+            }
+        return true;
+    }
+
+    // pygame.draw.circle(filled) row spans for every radius the kernel may draw at run time: derived by
+    // running the primitive itself, so the tables cannot drift from it
+    void add_disc_tables() {
+        discs.clear();
+        for (int r = 1; r <= MG_MAX_DISC_R; ++r) {
+            Surface s(2 * r + 4, 2 * r + 4);
+            int c = r + 2;
+            mgr::circle(s, 1, c, c, r, 0, false);
+            for (int dy = -r; dy < r; ++dy) {
+                int lo = 1, hi = 0;  // empty row: xmin > xmax
+                bool any = false;
+                for (int x = 0; x < s.w; ++x)
+                    if (s.at(x, c + dy)) {
+                        if (!any) lo = x - c;
+                        hi = x - c;
+                        any = true;
+                    }
+                discs.push_back((int8_t)lo);
+                discs.push_back((int8_t)hi);
+            }
+        }
+    }
+
+    // pygame Vector2.rotate for integer degrees: exact quarter turns, else libm sin/cos of angle * pi / 180
+    void add_trig_table() {
+        trig.resize(720);
+        for (int a = 0; a < 360; ++a) {
+            double x, y;
+            mgr::vec_rotate(1.0, 0.0, (double)a, &x, &y);
+            trig[2 * a] = x;
+            trig[2 * a + 1] = y;
+        }
+    }
+
     void add_template(int slot, const Surface& s) {
         // pygame.surfarray.array3d layout: [x][y][c]
         std::vector<uint8_t> t((size_t)MG_FRAME_BYTES);
@@ -93,7 +144,27 @@ struct Builder {
         hdr.entries_off = (uint32_t)off;
         hdr.n_entries = (uint32_t)entries.size();
         off += entries.size() * 4;
+        for (int i = 0; i < MG_SPR_COUNT; ++i) {
+            hdr.dense_off[i] = 0;
+            if (dense[i].empty()) continue;
+            off = (off + 3) & ~(size_t)3;
+            hdr.dense_off[i] = (uint32_t)off;
+            off += dense[i].size();
+        }
+        hdr.disc_off = 0;
+        if (!discs.empty()) {
+            off = (off + 3) & ~(size_t)3;
+            hdr.disc_off = (uint32_t)off;
+            off += discs.size();
+        }
+        hdr.trig_off = 0;
+        if (!trig.empty()) {
+            off = (off + 7) & ~(size_t)7;
+            hdr.trig_off = (uint32_t)off;
+            off += trig.size() * sizeof(double);
+        }
         off = (off + 127) & ~(size_t)127;
+        hdr.stage_bytes = (uint32_t)off;
         for (size_t i = 0; i < templates.size() && i < 4; ++i) {
             if (templates[i].empty()) continue;
             hdr.tmpl_off[i] = (uint32_t)off;
@@ -105,6 +176,10 @@ struct Builder {
         memset(out, 0, off);
         memcpy(out, &hdr, sizeof(hdr));
         memcpy((char*)out + hdr.entries_off, entries.data(), entries.size() * 4);
+        for (int i = 0; i < MG_SPR_COUNT; ++i)
+            if (hdr.dense_off[i]) memcpy((char*)out + hdr.dense_off[i], dense[i].data(), dense[i].size());
+        if (hdr.disc_off) memcpy((char*)out + hdr.disc_off, discs.data(), discs.size());
+        if (hdr.trig_off) memcpy((char*)out + hdr.trig_off, trig.data(), trig.size() * sizeof(double));
         for (size_t i = 0; i < templates.size() && i < 4; ++i)
             if (!templates[i].empty()) memcpy((char*)out + hdr.tmpl_off[i], templates[i].data(), MG_FRAME_BYTES);
         return (long)off;
@@ -112,7 +187,7 @@ struct Builder {
 };
 
 // character_controller.py:29-75 (create_character_sprites)
-bool build_agent(Builder& b, double scale, bool legacy) {
+bool build_agent(Builder& b, double scale, bool legacy, bool with_dense = false) {
     int radius = (int)(25 * scale), hands_x = (int)(18 * scale), hand_y = (int)(12 * scale);
     int hand_r = (int)(10 * scale), outline = (int)(3 * scale), ext = 14;
     int dim = radius * 2 + hand_r + ext;
@@ -135,6 +210,7 @@ bool build_agent(Builder& b, double scale, bool legacy) {
         mgr::circle(s, mgr::rgb(50, 50, 50), lpx, lpy, hand_r, outline, legacy);
         mgr::circle(s, mgr::rgb(50, 50, 50), rpx, rpy, hand_r, outline, legacy);
         if (!b.add_sprite(MG_SPR_AGENT0 + k, s)) return false;
+        if (with_dense && !b.add_dense(MG_SPR_AGENT0 + k, s)) return false;
     }
     b.hdr.agent_dim = dim;
     b.hdr.agent_radius = radius;
@@ -226,6 +302,56 @@ extern "C" long mg_mp_build_assets(const mg_mp_params* p, void* host_out, size_t
     Builder b;
     if (!build_agent(b, p->agent_scale, false)) return MG_EINVAL;
     if (!build_cross(b)) return MG_EINVAL;
+    Surface black(MG_W, MG_W);
+    b.add_template(0, black);
+    return b.serialize(host_out, capacity);
+}
+
+namespace {
+// Exit.__init__ / Exit.draw (pygame_assets.py:169-205): rounded-top door, 1-px (int(2*scale)) black outline
+bool build_exit(Builder& b, double scale) {
+    int dim = (int)(20 * scale);
+    if (dim < 2 || dim > 255) return false;
+    int corner = (int)(10 * scale);
+    for (int open = 0; open < 2; ++open) {
+        Surface s(dim, dim);
+        mgr::fill(s, 255);
+        s.has_key = true;
+        s.key = 255;
+        uint32_t col = open ? mgr::rgb(48, 141, 70) : mgr::rgb(55, 55, 55);
+        mgr::rect(s, col, 0, 0, s.w, s.h, 0, 0, corner, corner, 0, 0);
+        mgr::rect(s, 0, 0, 0, s.w, s.h, (int)(2 * scale), 0, corner, corner, 0, 0);
+        int slot = open ? MG_SPR_EXIT_OPEN : MG_SPR_EXIT_CLOSED;
+        if (!b.add_sprite(slot, s) || !b.add_dense(slot, s)) return false;
+    }
+    return true;
+}
+}  // namespace
+
+namespace {
+// Coin.draw (pygame_assets.py:145-152): yellow disc, then an orange circle of width int(2 * scale) (0 = filled)
+bool build_coin(Builder& b, double scale) {
+    int r = (int)(10 * scale), w = (int)(2 * scale);
+    if (r < 0 || r > MG_MAX_DISC_R) return false;
+    int c = r + 1;
+    Surface s(2 * c, 2 * c);
+    mgr::fill(s, 255);
+    s.has_key = true;
+    s.key = 255;
+    mgr::circle(s, mgr::rgb(255, 255, 0), c, c, r, 0, false);
+    mgr::circle(s, mgr::rgb(255, 165, 0), c, c, r, w, false);
+    return b.add_sprite(MG_SPR_COIN, s) && b.add_dense(MG_SPR_COIN, s);
+}
+}  // namespace
+
+extern "C" long mg_ss_build_assets(const mg_ss_params* p, void* host_out, size_t capacity) {
+    if (!p) return MG_EINVAL;
+    Builder b;
+    if (!build_agent(b, p->agent_scale, false, true)) return MG_EINVAL;
+    if (!build_exit(b, p->exit_scale)) return MG_EINVAL;
+    if (!build_coin(b, p->coin_scale)) return MG_EINVAL;
+    b.add_disc_tables();
+    b.add_trig_table();
     Surface black(MG_W, MG_W);
     b.add_template(0, black);
     return b.serialize(host_out, capacity);

@@ -74,9 +74,13 @@ struct MgAssetHeader {
     int32_t agent_dim;     // sprite side; blit top-left = centre - (dim >> 1)
     int32_t agent_radius;  // int(25 * agent_scale)
     int32_t icon_x, icon_y;  // command blit position (mortar_mayhem.py:363)
-    int32_t disc_off;      // byte offset of int8 disc tables: for r in 0..MG_MAX_DISC_R, 2*r rows of (xmin,xmax)
-    int32_t reserved[3];
+    uint32_t disc_off;     // byte offset of the int8 filled-circle tables: radius r (1..MG_MAX_DISC_R) has 2r rows
+                           // dy = -r..r-1 of (xmin, xmax) relative to the centre, starting at row r*(r-1)
+    uint32_t trig_off;     // byte offset of double[360][2] = (cos, sin) of integer degrees (host libm)
+    uint32_t stage_bytes;  // bytes [0, stage_bytes) = header + sprite lists + dense bitmaps + tables (no templates)
+    uint32_t reserved;
     MgSprite sprite[MG_SPR_COUNT];
+    uint32_t dense_off[MG_SPR_COUNT];  // byte offset of a dense w*h palette-index bitmap (255 = transparent), 0 = none
     uint8_t palette[MG_MAX_PALETTE][4];
 };
 
@@ -137,6 +141,55 @@ struct MgMPState {
     uint8_t pad[32];
 };
 
+// ---- Searing Spotlights record (1024 bytes) -----------------------------------------------------
+#define MG_SS_MAXSPOTS 32
+#define MG_SS_MAXCOINS 16
+struct MgSSSpot {       // Spotlight (pygame_assets.py:61-131); positions are recomputed from the angles
+    double t, speed;
+    uint16_t a_start, a_target, a_offset;  // degrees, normalised to [0, 360)
+    uint8_t radius;
+    uint8_t done;
+};
+struct MgSSState {
+    MgRng rng;            // 40
+    double ep_reward;
+    double hp;            // current_agent_health
+    double last_reward;
+    int32_t ep_len, t;
+    int32_t spawn_timer, spawns_left;
+    int16_t cx, cy;
+    int16_t exit_x, exit_y;
+    int16_t red_w_max;    // widest health-loss rect drawn on the top bar so far
+    uint8_t rot;          // agent.rotation // 45
+    uint8_t alpha;        // spotlight_surface.get_alpha()
+    uint8_t n_spots;
+    uint8_t n_coins;      // coins still on the field
+    uint8_t num_coins;    // coins spawned this episode
+    uint8_t coins_collected;
+    uint8_t exit_open;
+    uint8_t last_a0, last_a1;  // last_action
+    uint8_t bar_c0, bar_c1;    // colours of the action boxes as currently drawn
+    uint8_t coin_bar;          // 0 not drawn yet, 1 yellow, 2 grey
+    uint8_t bg_blue, bg_red;   // sticky state of the two background surfaces: 0 chessboard, 1 white, 2 black
+    uint8_t live;
+    uint8_t pad0[5];
+    int16_t coins[MG_SS_MAXCOINS][2];
+    MgSSSpot spots[MG_SS_MAXSPOTS];
+    uint8_t pad1[80];
+};
+
+struct MgSSFrame {
+    int16_t sx, sy;
+    int16_t exit_x, exit_y;
+    int16_t red_w_max, red_now;
+    uint8_t srot, alpha, bg_kind, n_discs;   // bg_kind: 0 blue chessboard, 1 red chessboard, 2 white, 3 black
+    uint8_t n_coins, exit_open, bar_c0, bar_c1;
+    uint8_t coin_bar, pad[3];
+    int16_t coins[MG_SS_MAXCOINS][2];
+    int16_t disc_x[MG_SS_MAXSPOTS], disc_y[MG_SS_MAXSPOTS];
+    uint8_t disc_r[MG_SS_MAXSPOTS];
+};
+
 // frame description produced by the env logic and consumed by the rasteriser (MM family)
 struct MgMMFrame {
     int red;        // tiles reddened (tiles_on && visual_feedback)
@@ -155,4 +208,6 @@ struct MgMPFrame {
 static_assert(sizeof(MgRng) == 40, "MgRng layout");
 static_assert(sizeof(MgMMState) == 256, "MgMMState must be 256 bytes (MG_MM_STATE_BYTES)");
 static_assert(sizeof(MgMPState) == 128, "MgMPState must be 128 bytes (MG_MP_STATE_BYTES)");
+static_assert(sizeof(MgSSSpot) == 24, "MgSSSpot layout");
+static_assert(sizeof(MgSSState) == 1024, "MgSSState must be 1024 bytes (MG_SS_STATE_BYTES)");
 static_assert(sizeof(MgAssetHeader) % 8 == 0, "MgAssetHeader alignment");

@@ -12,21 +12,25 @@
 #include "mg_common.h"
 
 struct MgAssetView {
+    const uint8_t* base;           // bytes [0, hdr->stage_bytes) of the blob: global memory, or the kernel's
+                                   // shared-memory copy (header, sprite lists, dense bitmaps, tables)
     const MgAssetHeader* hdr;
-    const uint32_t* entries;       // sprite pixel lists (the kernel re-points this at a shared-memory copy)
-    const uint8_t (*palette)[4];   // ditto
-    const uint8_t* tmpl[4];
+    const uint32_t* entries;
+    const uint8_t (*palette)[4];
+    const uint8_t* tmpl[4];        // full-frame templates: always in global memory (TMA source)
 };
 
-MG_HD MgAssetView mg_asset_view(const void* blob) {
+// `data` = where the stageable prefix lives, `blob` = the whole blob in global memory
+MG_HD MgAssetView mg_asset_view2(const void* data, const void* blob) {
     MgAssetView v;
-    const uint8_t* b = (const uint8_t*)blob;
-    v.hdr = (const MgAssetHeader*)b;
-    v.entries = (const uint32_t*)(b + v.hdr->entries_off);
+    v.base = (const uint8_t*)data;
+    v.hdr = (const MgAssetHeader*)v.base;
+    v.entries = (const uint32_t*)(v.base + v.hdr->entries_off);
     v.palette = v.hdr->palette;
-    for (int i = 0; i < 4; ++i) v.tmpl[i] = v.hdr->tmpl_off[i] ? b + v.hdr->tmpl_off[i] : nullptr;
+    for (int i = 0; i < 4; ++i) v.tmpl[i] = v.hdr->tmpl_off[i] ? (const uint8_t*)blob + v.hdr->tmpl_off[i] : nullptr;
     return v;
 }
+MG_HD MgAssetView mg_asset_view(const void* blob) { return mg_asset_view2(blob, blob); }
 
 // colour-key blit of a sparse sprite with its top-left at (ax, ay), clipped to the screen
 template <class Ctx>
@@ -168,4 +172,175 @@ MG_HD void mg_mp_restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgMPD
     if (d.f.cross) mg_sprite_erase(c, buf, a, MG_SPR_CROSS, d.f.cross_x, d.f.cross_y, bg);
     if (d.show_goal) mg_block_fill(c, buf, 12 * d.gx, 12 * d.gy, 12, 12, 0, 0, 0);
     if (d.show_origin) mg_block_fill(c, buf, 12 * d.ox, 12 * d.oy, 12, 12, 0, 0, 0);
+}
+
+// ---- Searing Spotlights ----------------------------------------------------------------------------
+// The frame is a per-pixel function of the state: layers in painter's order
+// (searing_spotlights.py:526-542), the spotlight layer being a black surface with colour-keyed discs blended
+// with per-surface alpha (SDL BlitNtoNSurfaceAlphaKey: d += trunc((0 - d) * A / 255)).
+struct MgSSDrawK {
+    int n_layers;
+    int layers[6];
+    int cb_x, cb_w;
+    int show_last_action;
+    int has_coin_layer;   // coin_surface is None when num_coins == 0
+};
+
+MG_HD bool mg_disc_has(const int8_t* discs, int r, int x0, int y0, int x, int y) {
+    int dy = y - y0;
+    if (r < 1 || dy < -r || dy >= r) return false;
+    const int8_t* row = discs + 2 * (r * (r - 1) + dy + r);
+    int dx = x - x0;
+    return dx >= (int)row[0] && dx <= (int)row[1];
+}
+
+// colour of a dense sprite at screen pixel (x, y) when its top-left is (ax, ay); returns false if transparent
+MG_HD bool mg_dense_at(const MgAssetView& a, int slot, int ax, int ay, int x, int y, uint32_t& col) {
+    const MgSprite sp = a.hdr->sprite[slot];
+    unsigned u = (unsigned)(x - ax), v = (unsigned)(y - ay);
+    if (u >= (unsigned)sp.w || v >= (unsigned)sp.h) return false;
+    uint8_t pi = a.base[a.hdr->dense_off[slot] + v * sp.w + u];
+    if (pi == 255) return false;
+    const uint8_t* c = a.palette[pi];
+    col = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
+    return true;
+}
+
+MG_HD bool mg_ss_layer_at(const MgAssetView& a, const MgSSFrame& f, int layer, int x, int y, uint32_t& col) {
+    if (layer == 5) {  // MG_SS_L_AGENT
+        int half = a.hdr->agent_dim >> 1;
+        return mg_dense_at(a, MG_SPR_AGENT0 + f.srot, f.sx - half, f.sy - half, x, y, col);
+    }
+    if (layer == 4) {  // MG_SS_L_EXIT
+        int slot = f.exit_open ? MG_SPR_EXIT_OPEN : MG_SPR_EXIT_CLOSED;
+        const MgSprite sp = a.hdr->sprite[slot];
+        return mg_dense_at(a, slot, f.exit_x - (sp.w >> 1), f.exit_y - (sp.h >> 1), x, y, col);
+    }
+    if (layer == 3) {  // MG_SS_L_COIN: coins are drawn in list order, so the last one covering the pixel wins
+        const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
+        for (int c = (int)f.n_coins - 1; c >= 0; --c)
+            if (mg_dense_at(a, MG_SPR_COIN, f.coins[c][0] - (sp.w >> 1), f.coins[c][1] - (sp.h >> 1), x, y, col))
+                return true;
+        return false;
+    }
+    return false;
+}
+
+MG_HD uint32_t mg_ss_bg(int kind, int x, int y) {
+    if (kind == 2) return 0x00FFFFFFu;
+    if (kind == 3) return 0u;
+    // get_tiled_background_surface (pygame_assets.py:222-239): 12-px tiles, white where (tx + ty) is even
+    if ((((unsigned)x / 12u + (unsigned)y / 12u) & 1u) == 0u) return 0x00FFFFFFu;
+    return kind == 0 ? 0x00FF0000u /* (0,0,255) */ : 0x000000FFu /* (255,0,0) */;
+}
+
+// top bar (searing_spotlights.py:372-389, 465-468, 222-224, 518-523), y < 4
+MG_HD uint32_t mg_ss_bar(const MgSSDrawK& k, const MgSSFrame& f, int x) {
+    const uint32_t act[3] = {120u | (120u << 8) | (120u << 16), 116u | (1u << 8) | (113u << 16), 255u | (94u << 8) | (14u << 16)};
+    uint32_t c = 50u | (50u << 8) | (50u << 16);
+    if (x < 42) c = 0x0000FF00u;  // green health
+    if (k.show_last_action && x >= 42) c = act[x < 63 ? f.bar_c0 : f.bar_c1];
+    // health lost: red from the left; beyond the health half it only survives until the action boxes are repainted
+    if ((x < f.red_w_max && (x < 42 || !k.show_last_action)) || x < f.red_now) c = 0x000000FFu;
+    if (f.coin_bar && x >= k.cb_x && x < k.cb_x + k.cb_w) c = f.coin_bar == 1 ? (255u | (255u << 8)) : (50u | (50u << 8) | (50u << 16));
+    return c;
+}
+
+MG_HD uint32_t mg_ss_pixel(const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f, int x, int y) {
+    const int8_t* discs = (const int8_t*)(a.base + a.hdr->disc_off);
+    uint32_t col = 0;
+    for (int li = k.n_layers - 1; li >= 0; --li) {
+        int L = k.layers[li];
+        if (L == 2) {  // MG_SS_L_BAR
+            if (y < 4) return mg_ss_bar(k, f, x);
+        } else if (L == 1) {  // MG_SS_L_SPOT: what lies underneath, dimmed unless a spotlight disc covers the pixel
+            uint32_t under = 0;
+            bool found = false;
+            for (int lj = li - 1; lj >= 0 && !found; --lj) {
+                int M = k.layers[lj];
+                if (M == 0) {
+                    under = mg_ss_bg(f.bg_kind, x, y);
+                    found = true;
+                } else if (M == 2) {
+                    if (y < 4) {
+                        under = mg_ss_bar(k, f, x);
+                        found = true;
+                    }
+                } else if (M != 3 || k.has_coin_layer) {
+                    found = mg_ss_layer_at(a, f, M, x, y, under);
+                }
+            }
+            if (f.alpha == 0) return under;
+            for (int d = 0; d < (int)f.n_discs; ++d)
+                if (mg_disc_has(discs, f.disc_r[d], f.disc_x[d], f.disc_y[d], x, y)) return under;
+            if (f.alpha == 255) return 0u;
+            uint32_t A = f.alpha, r = under & 255u, g = (under >> 8) & 255u, b = (under >> 16) & 255u;
+            r -= r * A / 255u;
+            g -= g * A / 255u;
+            b -= b * A / 255u;
+            return r | (g << 8) | (b << 16);
+        } else if (L == 0) {
+            return mg_ss_bg(f.bg_kind, x, y);
+        } else if (L != 3 || k.has_coin_layer) {
+            if (mg_ss_layer_at(a, f, L, x, y, col)) return col;
+        }
+    }
+    return col;
+}
+
+MG_HD void mg_put_px(uint8_t* buf, int x, int y, uint32_t col) {
+    uint8_t* o = buf + x * MG_COL_BYTES + y * 3;
+    o[0] = (uint8_t)col;
+    o[1] = (uint8_t)(col >> 8);
+    o[2] = (uint8_t)(col >> 16);
+}
+
+// evaluate the frame function over a clipped rectangle
+template <class Ctx>
+MG_HD void mg_ss_rect(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f, int x0,
+                      int y0, int w, int h) {
+    int xa = x0 < 0 ? 0 : x0, ya = y0 < 0 ? 0 : y0;
+    int xb = x0 + w > MG_W ? MG_W : x0 + w, yb = y0 + h > MG_W ? MG_W : y0 + h;
+    if (xb <= xa || yb <= ya) return;
+    int rows = yb - ya, total = (xb - xa) * rows;
+    for (int i = c.lane; i < total; i += c.nl) {
+        int x = xa + i / rows, y = ya + i % rows;
+        mg_put_px(buf, x, y, mg_ss_pixel(a, k, f, x, y));
+    }
+}
+
+template <class Ctx>
+MG_HD void mg_ss_compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f) {
+    int spot_li = 0;
+    for (int li = 0; li < k.n_layers; ++li)
+        if (k.layers[li] == 1) spot_li = li;
+    if (f.alpha == 255) {
+        // lights fully off: everything under the spotlight layer is black except inside the discs
+        uint32_t* w = reinterpret_cast<uint32_t*>(buf);
+        for (int i = c.lane; i < MG_FRAME_BYTES / 4; i += c.nl) w[i] = 0u;
+        c.sync();
+        for (int d = 0; d < (int)f.n_discs; ++d) {
+            int r = f.disc_r[d];
+            mg_ss_rect(c, buf, a, k, f, f.disc_x[d] - r, f.disc_y[d] - r, 2 * r, 2 * r);
+        }
+        // layers above the spotlight layer
+        for (int li = spot_li + 1; li < k.n_layers; ++li) {
+            int L = k.layers[li];
+            if (L == 2) {
+                mg_ss_rect(c, buf, a, k, f, 0, 0, MG_W, 4);
+            } else if (L == 5) {
+                int dim = a.hdr->agent_dim;
+                mg_ss_rect(c, buf, a, k, f, f.sx - (dim >> 1), f.sy - (dim >> 1), dim, dim);
+            } else if (L == 4) {
+                const MgSprite sp = a.hdr->sprite[MG_SPR_EXIT_OPEN];
+                mg_ss_rect(c, buf, a, k, f, f.exit_x - (sp.w >> 1), f.exit_y - (sp.h >> 1), sp.w, sp.h);
+            } else if (L == 3 && k.has_coin_layer) {
+                const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
+                for (int q = 0; q < (int)f.n_coins; ++q)
+                    mg_ss_rect(c, buf, a, k, f, f.coins[q][0] - (sp.w >> 1), f.coins[q][1] - (sp.h >> 1), sp.w, sp.h);
+            }
+        }
+    } else {
+        mg_ss_rect(c, buf, a, k, f, 0, 0, MG_W, MG_W);
+    }
 }

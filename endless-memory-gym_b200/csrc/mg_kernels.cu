@@ -28,6 +28,7 @@
 #include "mg_frame.h"
 #include "mg_mm_logic.h"
 #include "mg_mp_logic.h"
+#include "mg_ss_logic.h"
 #include "mg_params_host.h"
 #include "mg_policy.h"
 
@@ -150,17 +151,13 @@ __global__ void __launch_bounds__(320, 1)
         mg_mbar_expect_tx(ctx.bar, MG_FRAME_BYTES);
         mg_bulk_load(buf, view.tmpl[0], MG_FRAME_BYTES, ctx.bar);
     }
-    const int hw = (int)(sizeof(MgAssetHeader) / 4), ne = (int)view.hdr->n_entries;
-    if ((hw + ne) * 4 <= q.stage_cap) {  // sprite pixel lists + palette -> shared memory: compose never waits on L2
+    const int stage_words = (int)(view.hdr->stage_bytes / 4);
+    if (stage_words * 4 <= q.stage_cap) {  // header, sprite lists, bitmaps, tables -> shared memory: compose never waits on L2
         const uint32_t* src = reinterpret_cast<const uint32_t*>(assets);
         uint32_t* dst = reinterpret_cast<uint32_t*>(stage);
-        const uint32_t* esrc = view.entries;
-        for (int i = threadIdx.x; i < hw; i += blockDim.x) dst[i] = src[i];
-        for (int i = threadIdx.x; i < ne; i += blockDim.x) dst[hw + i] = esrc[i];
+        for (int i = threadIdx.x; i < stage_words; i += blockDim.x) dst[i] = src[i];
         __syncthreads();
-        view.hdr = reinterpret_cast<const MgAssetHeader*>(stage);
-        view.entries = dst + hw;
-        view.palette = view.hdr->palette;
+        view = mg_asset_view2(stage, assets);
     }
     if (tracing) tr1 = mg_now();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -224,7 +221,7 @@ __global__ void __launch_bounds__(320, 1)
                     if (q.act_dims > 1) act1 = a[1];
                 }
             }
-            if (lane == 0) P::logic(k, q, env, t, *st, a0, a1, *job, fr);
+            if (lane == 0) P::logic(k, q, view, env, t, *st, a0, a1, *job, fr);
             __syncwarp();
             if (trow && lane == 0) trow[4] = mg_now();
             const int nframes = job->nframes;
@@ -526,20 +523,28 @@ extern "C" int mg_mp_rollout(const mg_mp_params* p, const void* assets, void* st
     return launch_rollout<MPPolicy>(k, assets, state, r, n, 2, stream, 10);
 }
 
-// Searing Spotlights: not built yet — the symbols fail loudly.
-static int ss_missing() {
-    mg_set_err("SearingSpotlights kernels are not built yet");
-    return MG_EINVAL;
+extern "C" int mg_ss_reset(const mg_ss_params* p, const void* assets, void* state, const uint64_t* rng4,
+                           const mg_step_io* io, int n, void* stream) {
+    if (mg_ss_check_params(p)) return MG_EINVAL;
+    MgSSK k;
+    mg_ss_derive(p, &k);
+    return launch_env<SSPolicy>(k, assets, state, rng4, io, 1, n, MG_MODE_RESET, 2, stream, 8);
 }
-extern "C" int mg_ss_check_params(const mg_ss_params*) { return ss_missing(); }
-extern "C" long mg_ss_build_assets(const mg_ss_params*, void*, size_t) { return ss_missing(); }
-extern "C" int mg_ss_reset(const mg_ss_params*, const void*, void*, const uint64_t*, const mg_step_io*, int, void*) {
-    return ss_missing();
+extern "C" int mg_ss_step(const mg_ss_params* p, const void* assets, void* state, const mg_step_io* io, int n,
+                          void* stream) {
+    return mg_ss_step_many(p, assets, state, io, 1, n, stream);
 }
-extern "C" int mg_ss_step(const mg_ss_params*, const void*, void*, const mg_step_io*, int, void*) { return ss_missing(); }
-extern "C" int mg_ss_step_many(const mg_ss_params*, const void*, void*, const mg_step_io*, int, int, void*) {
-    return ss_missing();
+extern "C" int mg_ss_step_many(const mg_ss_params* p, const void* assets, void* state, const mg_step_io* ios,
+                               int n_steps, int n, void* stream) {
+    if (mg_ss_check_params(p)) return MG_EINVAL;
+    MgSSK k;
+    mg_ss_derive(p, &k);
+    return launch_env<SSPolicy>(k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, 2, stream, 8);
 }
-extern "C" int mg_ss_rollout(const mg_ss_params*, const void*, void*, const mg_rollout_io*, int, void*) {
-    return ss_missing();
+extern "C" int mg_ss_rollout(const mg_ss_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
+                             void* stream) {
+    if (mg_ss_check_params(p)) return MG_EINVAL;
+    MgSSK k;
+    mg_ss_derive(p, &k);
+    return launch_rollout<SSPolicy>(k, assets, state, r, n, 2, stream, 8);
 }

@@ -133,3 +133,120 @@ void mg_mp_derive(const mg_mp_params* p, MgMPK* k) {
     k->step_diag = (int)(inv * p->agent_speed);
 }
 
+
+extern "C" int mg_ss_check_params(const mg_ss_params* p) {
+    if (!p) {
+        mg_set_err("params is NULL");
+        return MG_EINVAL;
+    }
+    if (!p->use_exit) {  // the reference crashes in reset (self.exit is undefined, searing_spotlights.py:416,432)
+        mg_set_err("use_exit=False is not supported (the reference raises AttributeError)");
+        return MG_EINVAL;
+    }
+    if (p->black_background) {
+        mg_set_err("black_background=True (spotlight borders) is not built yet");
+        return MG_EINVAL;
+    }
+    if (!check_list(p->num_coins, 1, MG_SS_MAXCOINS, "num_coins")) return MG_EINVAL;  // 0 coins: ZeroDivisionError at done (:553)
+    if (!(p->agent_health > 0.0)) {
+        mg_set_err("agent_health must be > 0");
+        return MG_EINVAL;
+    }
+    if (!(p->agent_speed >= 0.0 && p->agent_speed < 84.0)) {
+        mg_set_err("agent_speed must be in [0, 84)");
+        return MG_EINVAL;
+    }
+    int radius = (int)(25 * p->agent_scale), hand = (int)(10 * p->agent_scale);
+    if (!(p->agent_scale > 0.0) || radius * 2 + hand + 14 > 255 || radius > 38) {
+        mg_set_err("agent_scale out of range");
+        return MG_EINVAL;
+    }
+    int rlo = (int)p->spot_min_radius, rhi = (int)(p->spot_max_radius + 1);
+    if (rlo < 1 || rhi <= rlo || rhi - 1 > MG_MAX_DISC_R) {
+        mg_set_err("spot radius must satisfy 1 <= int(min) < int(max + 1) <= MG_MAX_DISC_R + 1");
+        return MG_EINVAL;
+    }
+    if (!(p->spot_min_speed > 0.0) || !(p->spot_max_speed >= p->spot_min_speed) || !(p->spot_max_speed <= 1.0)) {
+        mg_set_err("spot speeds must satisfy 0 < min <= max <= 1");
+        return MG_EINVAL;
+    }
+    if ((int)(10 * p->coin_scale) > MG_MAX_DISC_R || p->coin_scale < 0.0 || (int)(20 * p->exit_scale) < 2 ||
+        (int)(20 * p->exit_scale) > 84) {
+        mg_set_err("coin_scale / exit_scale out of range");
+        return MG_EINVAL;
+    }
+    if (p->initial_spawns < 0 || p->num_spawns < 0 || p->max_steps == 0) {
+        mg_set_err("initial_spawns, num_spawns must be >= 0 and max_steps != 0");
+        return MG_EINVAL;
+    }
+    if (p->light_dim_off_duration < 0 || p->light_dim_off_duration > 255) {
+        mg_set_err("light_dim_off_duration must be 0..255");
+        return MG_EINVAL;
+    }
+    // spotlights alive at once: the initial ones plus one per spawn interval within the longest traversal
+    int interval0 = (int)(p->initial_spawn_interval + p->spawn_interval_threshold);
+    if (p->num_spawns > 0 && interval0 < 1) {
+        mg_set_err("initial_spawn_interval + spawn_interval_threshold must be >= 1");
+        return MG_EINVAL;
+    }
+    double life = 1.0 / p->spot_min_speed + 2.0;
+    if (p->max_steps > 0 && (double)p->max_steps < life) life = (double)p->max_steps;
+    long spawned = p->num_spawns > 0 ? (long)(life / (interval0 > 0 ? interval0 : 1)) + 1 : 0;
+    if (spawned > p->num_spawns) spawned = p->num_spawns;
+    if (p->initial_spawns + spawned > MG_SS_MAXSPOTS) {
+        mg_set_err("too many concurrent spotlights for the env record (MG_SS_MAXSPOTS = 32)");
+        return MG_EINVAL;
+    }
+    return 0;
+}
+
+void mg_ss_derive(const mg_ss_params* p, MgSSK* k) {
+    memset(k, 0, sizeof(*k));
+    k->p = *p;
+    k->radius = (int)(25 * p->agent_scale);
+    double inv = 1.0 / sqrt(2.0);
+    k->step_axis = (int)(1.0 * p->agent_speed);
+    k->step_diag = (int)(inv * p->agent_speed);
+    k->coin_radius = (int)(10 * p->coin_scale);
+    k->spot_rlo = (int)p->spot_min_radius;
+    k->spot_rhi = (int)(p->spot_max_radius + 1);
+    k->interval0 = (int)(p->initial_spawn_interval + p->spawn_interval_threshold);
+    k->alpha_inc = p->light_dim_off_duration > 0 ? (int)(255.0 / p->light_dim_off_duration) : 0;
+    int q = MG_W / 4;
+    if (p->show_last_action) {
+        k->cb_x = (int)(q * 2.75);
+        k->cb_w = (int)(q * 0.5);
+    } else {
+        k->cb_x = (int)(q * 2);
+        k->cb_w = (int)(q * 2);
+    }
+    k->clamp_off = (int)(30 * 0.25);
+    k->exit_radius = 20 / 2 * p->exit_scale;
+    k->spawn_base = sqrt(pow(84.0, 2) + pow(84.0, 2)) / 2;
+    // painter's order: python list inserts of searing_spotlights.py:526-542 (an index past the end appends)
+    int order[6], n = 0;
+    auto insert = [&](int at, int v) {
+        if (at > n) at = n;
+        for (int i = n; i > at; --i) order[i] = order[i - 1];
+        order[at] = v;
+        n++;
+    };
+    order[n++] = MG_SS_L_BG;
+    order[n++] = MG_SS_L_SPOT;
+    order[n++] = MG_SS_L_BAR;
+    int sid = 1;
+    if (p->coins_visible)
+        insert(sid + 1, MG_SS_L_COIN);
+    else
+        insert(sid++, MG_SS_L_COIN);
+    if (p->exit_visible)
+        insert(sid + 2, MG_SS_L_EXIT);
+    else
+        insert(sid++, MG_SS_L_EXIT);
+    if (p->agent_visible)
+        insert(sid + 3, MG_SS_L_AGENT);
+    else
+        insert(sid++, MG_SS_L_AGENT);
+    k->n_layers = n;
+    for (int i = 0; i < n; ++i) k->layers[i] = order[i];
+}

@@ -7,6 +7,7 @@
 #include "mg_frame.h"
 #include "mg_mm_logic.h"
 #include "mg_mp_logic.h"
+#include "mg_ss_logic.h"
 
 #if defined(__CUDACC__)
 #define MG_HDN __host__ __device__
@@ -38,8 +39,8 @@ struct MgFrameJob {      // what the logic lane hands to the warp: up to two fra
 // One env, one call: reset (mode RESET) or step (+ auto-reset) — the same control flow for every env type.
 // `E` supplies reset_env / step_env. a0/a1 are this env's (prefetched) action components.
 template <class E>
-MG_HDN void mg_env_logic(const typename E::K& k, const MgKIO& q, int env, int t, typename E::State& s, int a0, int a1,
-                         MgFrameJob& job, typename E::Frame* fr) {
+MG_HDN void mg_env_logic(const typename E::K& k, const MgKIO& q, const MgAssetView& a, int env, int t,
+                         typename E::State& s, int a0, int a1, MgFrameJob& job, typename E::Frame* fr) {
     double* const reward_out = q.io.reward + (size_t)t * q.rew_stride + env;
     uint8_t* const done_out = q.io.done + (size_t)t * q.done_stride + env;
     double* const info_out = q.io.info + (size_t)t * q.info_stride + MG_INFO_COLS * (size_t)env;
@@ -56,7 +57,7 @@ MG_HDN void mg_env_logic(const typename E::K& k, const MgKIO& q, int env, int t,
             s.rng.buf = 0;
             s.rng.has_buf = 0;
         }
-        E::reset_env(k, s, fr[0], gt);
+        E::reset_env(k, a, s, fr[0], gt);
         job.nframes = 1;
         job.to_final[0] = 0;
         return;
@@ -67,7 +68,7 @@ MG_HDN void mg_env_logic(const typename E::K& k, const MgKIO& q, int env, int t,
         return;
     }
     double reward;
-    bool done = E::step_env(k, s, a0, a1, reward, info_out, fr[0], gt);
+    bool done = E::step_env(k, a, s, a0, a1, reward, info_out, fr[0], gt);
     *reward_out = reward;
     *done_out = done ? 1 : 0;
     job.nframes = 1;
@@ -78,7 +79,7 @@ MG_HDN void mg_env_logic(const typename E::K& k, const MgKIO& q, int env, int t,
             job.to_final[0] = 1;
             at = 1;
         }
-        E::reset_env(k, s, fr[at], gt);
+        E::reset_env(k, a, s, fr[at], gt);
         job.to_final[at] = 0;
         job.nframes = at + 1;
     }
@@ -88,14 +89,16 @@ struct MMPolicy {
     typedef MgMMK K;
     typedef MgMMState State;
     typedef MgMMFrame Frame;
-    static MG_HD void reset_env(const K& k, State& s, Frame& f, double* gt) { mg_mm_reset_env(k, s, f, gt); }
-    static MG_HD bool step_env(const K& k, State& s, int a0, int a1, double& reward, double* info, Frame& f,
-                               double* gt) {
+    static MG_HD void reset_env(const K& k, const MgAssetView&, State& s, Frame& f, double* gt) {
+        mg_mm_reset_env(k, s, f, gt);
+    }
+    static MG_HD bool step_env(const K& k, const MgAssetView&, State& s, int a0, int a1, double& reward, double* info,
+                               Frame& f, double* gt) {
         return mg_mm_step_env(k, s, a0, a1, reward, info, f, gt);
     }
-    static MG_HDN void logic(const K& k, const MgKIO& q, int env, int t, State& s, int a0, int a1, MgFrameJob& job,
-                             Frame* fr) {
-        mg_env_logic<MMPolicy>(k, q, env, t, s, a0, a1, job, fr);
+    static MG_HDN void logic(const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0, int a1,
+                             MgFrameJob& job, Frame* fr) {
+        mg_env_logic<MMPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
     }
     template <class Ctx>
     static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K& k, const Frame& f) {
@@ -111,13 +114,14 @@ struct MPPolicy {
     typedef MgMPK K;
     typedef MgMPState State;
     typedef MgMPDraw Frame;
-    static MG_HD void reset_env(const K& k, State& s, Frame& f, double*) { mg_mp_reset_env(k, s, f); }
-    static MG_HD bool step_env(const K& k, State& s, int a0, int a1, double& reward, double* info, Frame& f, double*) {
+    static MG_HD void reset_env(const K& k, const MgAssetView&, State& s, Frame& f, double*) { mg_mp_reset_env(k, s, f); }
+    static MG_HD bool step_env(const K& k, const MgAssetView&, State& s, int a0, int a1, double& reward, double* info,
+                               Frame& f, double*) {
         return mg_mp_step_env(k, s, a0, a1, reward, info, f);
     }
-    static MG_HDN void logic(const K& k, const MgKIO& q, int env, int t, State& s, int a0, int a1, MgFrameJob& job,
-                             Frame* fr) {
-        mg_env_logic<MPPolicy>(k, q, env, t, s, a0, a1, job, fr);
+    static MG_HDN void logic(const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0, int a1,
+                             MgFrameJob& job, Frame* fr) {
+        mg_env_logic<MPPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
     }
     template <class Ctx>
     static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f) {
@@ -127,4 +131,36 @@ struct MPPolicy {
     static MG_HD void restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f) {
         mg_mp_restore(c, buf, a, f, a.hdr->agent_dim >> 1);
     }
+};
+
+struct SSPolicy {
+    typedef MgSSK K;
+    typedef MgSSState State;
+    typedef MgSSFrame Frame;
+    static MG_HD const double* trig(const MgAssetView& a) { return (const double*)(a.base + a.hdr->trig_off); }
+    static MG_HD void reset_env(const K& k, const MgAssetView& a, State& s, Frame& f, double*) {
+        mg_ss_reset_env(k, trig(a), s, f);
+    }
+    static MG_HD bool step_env(const K& k, const MgAssetView& a, State& s, int a0, int a1, double& reward, double* info,
+                               Frame& f, double*) {
+        return mg_ss_step_env(k, trig(a), s, a0, a1, reward, info, f);
+    }
+    static MG_HDN void logic(const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0, int a1,
+                             MgFrameJob& job, Frame* fr) {
+        mg_env_logic<SSPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
+    }
+    template <class Ctx>
+    static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K& k, const Frame& f) {
+        MgSSDrawK d;
+        d.n_layers = k.n_layers;
+        for (int i = 0; i < 6; ++i) d.layers[i] = k.layers[i];
+        d.cb_x = k.cb_x;
+        d.cb_w = k.cb_w;
+        d.show_last_action = k.p.show_last_action;
+        d.has_coin_layer = 1;
+        mg_ss_compose(c, buf, a, d, f);
+    }
+    // every frame rewrites the whole buffer: nothing to undo
+    template <class Ctx>
+    static MG_HD void restore(Ctx&, uint8_t*, const MgAssetView&, const K&, const Frame&) {}
 };

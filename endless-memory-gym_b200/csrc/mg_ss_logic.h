@@ -1,0 +1,395 @@
+// mg_ss_logic.h — Searing Spotlights: reset + step state machine for ONE env record.
+//
+// Reference paths replaced:
+//   SearingSpotlightsEnv.reset/step/_step_*   memory_gym/searing_spotlights.py:187-242, 267-330, 332-450, 452-562
+//   Spotlight                                  memory_gym/pygame_assets.py:61-131   (fp64 lerp, int() centre, <= hit test)
+//   GridPositionSampler                        memory_gym/pygame_assets.py:7-59     (uniform over unmasked cells)
+//   Coin / Exit hit tests                      memory_gym/pygame_assets.py:154-167, 207-220
+//   CharacterController.step                   memory_gym/character_controller.py:89-146
+// All double arithmetic is mul/add/sqrt in the reference's order (compiled with -fmad=false /
+// -ffp-contract=off); sin/cos come from a host-libm table in the asset blob (pygame Vector2.rotate).
+// Reference quirks kept: every spawn interval is intervals[0] (list popped from the wrong end), and removing
+// a finished spotlight / collected coin while iterating skips the next element for that step (A.9#5, #6).
+#pragma once
+#include <math.h>
+
+#include "../../include/memgym_b200.h"
+#include "mg_common.h"
+#include "mg_mm_logic.h"  // kinematics
+#include "mg_pcg64.h"
+
+enum { MG_SS_L_BG = 0, MG_SS_L_SPOT = 1, MG_SS_L_BAR = 2, MG_SS_L_COIN = 3, MG_SS_L_EXIT = 4, MG_SS_L_AGENT = 5 };
+
+struct MgSSK {
+    mg_ss_params p;
+    int32_t radius;             // agent radius
+    int32_t step_axis, step_diag;
+    int32_t coin_radius;        // int(10 * coin_scale)
+    int32_t spot_rlo, spot_rhi; // integers(spot_min_radius, spot_max_radius + 1) with int()-truncated bounds
+    int32_t interval0;          // int(initial_spawn_interval + spawn_interval_threshold)
+    int32_t alpha_inc;          // int(255 / light_dim_off_duration)
+    int32_t cb_x, cb_w;         // last-positive-reward box on the top bar
+    int32_t n_layers;
+    int32_t layers[6];          // painter's order (searing_spotlights.py:526-542), MG_SS_L_*
+    int32_t clamp_off;          // int(30 * SCALE)
+    double exit_radius;         // 20 / 2 * exit_scale
+    double spawn_base;          // sqrt(84^2 + 84^2) / 2
+};
+
+// ---- GridPositionSampler: 84 rows x 84-bit occupancy masks ------------------------------------------
+struct MgSSSampler {
+    uint64_t lo[MG_W], hi[MG_W];  // column x of row y is blocked: bit x of (lo | hi << 64)
+    int32_t free_total;
+};
+
+MG_HD int mg_popc64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(v);
+#else
+    return __builtin_popcountll(v);
+#endif
+}
+
+MG_HD void mg_ss_sampler_reset(MgSSSampler& g) {
+    for (int y = 0; y < MG_W; ++y) g.lo[y] = g.hi[y] = 0;
+    g.free_total = MG_W * MG_W;
+}
+
+// block_spawn_position: cells with dx^2 + dy^2 < r^2 become unavailable
+MG_HD void mg_ss_block(MgSSSampler& g, int x, int y, int r) {
+    int y0 = y - r + 1 < 0 ? 0 : y - r + 1, y1 = y + r - 1 > MG_W - 1 ? MG_W - 1 : y + r - 1;
+    for (int yy = y0; yy <= y1; ++yy) {
+        int dy = yy - y, rem = r * r - dy * dy - 1;  // need dx^2 <= rem
+        int h = (int)sqrt((double)rem);
+        while (h * h > rem) --h;
+        while ((h + 1) * (h + 1) <= rem) ++h;
+        int xa = x - h < 0 ? 0 : x - h, xb = x + h > MG_W - 1 ? MG_W - 1 : x + h;
+        if (xa > xb) continue;
+        uint64_t mlo = 0, mhi = 0;
+        for (int c = xa; c <= xb; ++c) {
+            if (c < 64)
+                mlo |= 1ull << c;
+            else
+                mhi |= 1ull << (c - 64);
+        }
+        int before = mg_popc64(g.lo[yy]) + mg_popc64(g.hi[yy]);
+        g.lo[yy] |= mlo;
+        g.hi[yy] |= mhi;
+        g.free_total -= mg_popc64(g.lo[yy]) + mg_popc64(g.hi[yy]) - before;
+    }
+}
+
+// sample(block_radius): the cell_id-th free cell in row-major order, then block a disc around it.
+// Returns false when no cell is free (the reference raises from integers(0, 0)).
+MG_HD bool mg_ss_sample(MgSSSampler& g, MgRng& r, int block_radius, int& x, int& y) {
+    if (g.free_total <= 0) return false;
+    int k = (int)mg_integers(r, 0, g.free_total);
+    int row = 0;
+    for (; row < MG_W; ++row) {
+        int fr = MG_W - mg_popc64(g.lo[row]) - mg_popc64(g.hi[row]);
+        if (k < fr) break;
+        k -= fr;
+    }
+    int col = 0;
+    for (;; ++col) {
+        bool blocked = col < 64 ? ((g.lo[row] >> col) & 1ull) : ((g.hi[row] >> (col - 64)) & 1ull);
+        if (!blocked) {
+            if (k == 0) break;
+            --k;
+        }
+    }
+    x = col;
+    y = row;
+    mg_ss_block(g, x, y, block_radius);
+    return true;
+}
+
+// ---- spotlights -------------------------------------------------------------------------------------
+// Spotlight.__init__: radius, speed, then the three angle draws
+MG_HD void mg_ss_new_spot(const MgSSK& k, MgRng& r, MgSSSpot& sp) {
+    sp.radius = (uint8_t)mg_integers(r, k.spot_rlo, k.spot_rhi);
+    sp.speed = mg_uniform(r, k.p.spot_min_speed, k.p.spot_max_speed);
+    sp.t = 0.0;
+    sp.done = 0;
+    int start = (int)mg_integers(r, 0, 360);
+    int target = start + 180 + (int)mg_integers(r, -45, 45);
+    int offset = target + (int)mg_integers(r, -135, 135);
+    sp.a_start = (uint16_t)mg_pymod(start, 360);
+    sp.a_target = (uint16_t)mg_pymod(target, 360);
+    sp.a_offset = (uint16_t)mg_pymod(offset, 360);
+}
+
+// centre + Vector2(spawn_radius, 0).rotate(angle)
+MG_HD void mg_ss_on_circle(const double* trig, int angle, double spawn_radius, double& x, double& y) {
+    x = 42.0 + trig[2 * angle] * spawn_radius;
+    y = 42.0 + trig[2 * angle + 1] * spawn_radius;
+}
+
+// Spotlight.draw without the drawing + is_agent_inside: advances t, returns the circle centre and the hit flag
+MG_HD bool mg_ss_advance_spot(const MgSSK& k, const double* trig, MgSSSpot& sp, int ax, int ay, int& cx, int& cy) {
+    double R = k.spawn_base + (double)sp.radius;
+    double sx, sy, tx, ty, ox, oy;
+    mg_ss_on_circle(trig, sp.a_start, R, sx, sy);
+    mg_ss_on_circle(trig, sp.a_target, R, tx, ty);
+    mg_ss_on_circle(trig, sp.a_offset, R, ox, oy);
+    const double t = sp.t, u = 1.0 - t;
+    double lx = tx * u + ox * t, ly = ty * u + oy * t;  // target.lerp(offset, t)
+    double px = sx * u + lx * t, py = sy * u + ly * t;  // spawn.lerp(lerp_target, t)
+    cx = (int)px;
+    cy = (int)py;
+    sp.t = sp.t + sp.speed;
+    if (sp.t >= 1.0) {
+        sp.t = 1.0;
+        sp.done = 1;
+    }
+    double dx = (double)ax - px, dy = (double)ay - py;
+    return sqrt(dx * dx + dy * dy) <= (double)((int)sp.radius + k.radius);
+}
+
+MG_HD void mg_ss_clamp_spawn(const MgSSK& k, int& x, int& y) {
+    const int o = k.clamp_off;
+    if (x < o)
+        x = o;
+    else if (x > MG_W - o)
+        x = MG_W - o;
+    if (y < o)
+        y = o;
+    else if (y > MG_W - o)
+        y = MG_W - o;
+}
+
+MG_HD void mg_ss_frame_common(const MgSSState& s, int srot, MgSSFrame& f) {
+    f.sx = s.cx;
+    f.sy = s.cy;
+    f.srot = (uint8_t)srot;
+    f.exit_x = s.exit_x;
+    f.exit_y = s.exit_y;
+    f.exit_open = s.exit_open;
+    f.alpha = s.alpha;
+    f.red_w_max = s.red_w_max;
+    f.bar_c0 = s.bar_c0;
+    f.bar_c1 = s.bar_c1;
+    f.coin_bar = s.coin_bar;
+    f.n_coins = s.n_coins;
+    for (int c = 0; c < (int)s.n_coins; ++c) {
+        f.coins[c][0] = s.coins[c][0];
+        f.coins[c][1] = s.coins[c][1];
+    }
+}
+
+MG_HD uint8_t mg_ss_bg_kind(const MgSSState& s, int red) {
+    uint8_t st = red ? s.bg_red : s.bg_blue;
+    return st == 0 ? (uint8_t)(red ? 1 : 0) : (st == 1 ? (uint8_t)2 : (uint8_t)3);
+}
+
+// reset(): RNG draw order — rotation; agent cell + 2 offsets; per initial spotlight radius, speed, 3 angles;
+// num_coins; per coin cell + 2 offsets; exit cell + 2 offsets (searing_spotlights.py:354-414)
+MG_HD_NOINLINE void mg_ss_reset_env(const MgSSK& k, const double* trig, MgSSState& s, MgSSFrame& f) {
+    (void)trig;
+    MgRng r = s.rng;
+    s.t = 0;
+    s.ep_len = 0;
+    s.ep_reward = 0.0;
+    if (k.p.hide_chessboard) s.bg_blue = s.bg_red = 1;
+    MgSSSampler g;
+    mg_ss_sampler_reset(g);
+    s.last_a0 = s.last_a1 = 0;
+    s.rot = (uint8_t)mg_integers(r, 0, 8);  // choice([0, 45, ..., 315])
+    bool ok = true;
+    int x, y;
+    if (k.p.sample_agent_position) {
+        ok = mg_ss_sample(g, r, 28, x, y);
+        x += (int)mg_integers(r, 2, 4);
+        y += (int)mg_integers(r, 2, 4);
+    } else {
+        x = y = MG_W / 2;
+        mg_ss_block(g, x, y, 21);
+    }
+    s.cx = (int16_t)x;  // not clamped (searing_spotlights.py:364-369)
+    s.cy = (int16_t)y;
+    s.hp = k.p.agent_health;
+    s.red_w_max = 0;
+    s.bar_c0 = s.bar_c1 = 0;
+    s.coin_bar = 0;
+    s.last_reward = 0.0;
+    s.spawns_left = k.p.num_spawns;
+    s.spawn_timer = 0;
+    int a0 = k.p.light_threshold < 0 ? 0 : (k.p.light_threshold > 255 ? 255 : k.p.light_threshold);
+    s.alpha = (uint8_t)(k.p.light_dim_off_duration > 0 ? 0 : a0);
+    s.n_spots = 0;
+    for (int i = 0; i < k.p.initial_spawns; ++i) mg_ss_new_spot(k, r, s.spots[s.n_spots++]);
+    s.coins_collected = 0;
+    int nc = mg_choice(r, k.p.num_coins);
+    s.num_coins = (uint8_t)nc;
+    s.n_coins = 0;
+    for (int c = 0; c < nc && ok; ++c) {
+        ok = mg_ss_sample(g, r, 21, x, y);
+        x += (int)mg_integers(r, 2, 4);
+        y += (int)mg_integers(r, 2, 4);
+        mg_ss_clamp_spawn(k, x, y);
+        s.coins[s.n_coins][0] = (int16_t)x;
+        s.coins[s.n_coins][1] = (int16_t)y;
+        s.n_coins++;
+    }
+    if (ok) {
+        ok = mg_ss_sample(g, r, 21, x, y);
+        x += (int)mg_integers(r, 2, 4);
+        y += (int)mg_integers(r, 2, 4);
+        mg_ss_clamp_spawn(k, x, y);
+        s.exit_x = (int16_t)x;
+        s.exit_y = (int16_t)y;
+    }
+    s.exit_open = 0;
+    if (k.p.black_background) s.bg_blue = 2;
+    s.live = ok ? 1 : 0;  // sampler exhausted: the reference raises; here the env stays finished
+    s.rng = r;
+    mg_ss_frame_common(s, 0, f);  // the reset frame draws get_rotated_sprite(0)
+    f.n_discs = 0;
+    f.red_now = 0;
+    f.bg_kind = mg_ss_bg_kind(s, 0);
+}
+
+MG_HD_NOINLINE bool mg_ss_step_env(const MgSSK& k, const double* trig, MgSSState& s, int a0, int a1,
+                                   double& reward_out, double* info, MgSSFrame& f) {
+    int cx = s.cx, cy = s.cy, rot = s.rot;
+    // walkable_rect = (0, 16 * SCALE, 84, 84 - 16 * SCALE)
+    mg_move_clamped(cx, cy, rot, a0, a1, k.step_axis, k.step_diag, k.radius, 0, 4, MG_W, MG_W);
+    s.cx = (int16_t)cx;
+    s.cy = (int16_t)cy;
+    s.rot = (uint8_t)rot;
+    if (k.p.show_last_action) {  // the boxes show the PREVIOUS action, then last_action is updated
+        s.bar_c0 = s.last_a0;
+        s.bar_c1 = s.last_a1;
+        s.last_a0 = (uint8_t)a0;
+        s.last_a1 = (uint8_t)a1;
+    }
+    if ((int)s.alpha <= k.p.light_threshold) {
+        int a = k.p.light_dim_off_duration > 0 ? (int)s.alpha + k.alpha_inc : k.p.light_threshold;
+        s.alpha = (uint8_t)(a < 0 ? 0 : (a > 255 ? 255 : a));
+    }
+    double reward = 0.0;
+    // ---- spotlight task
+    double r = 0.0;
+    bool spot_done = false;
+    s.spawn_timer++;
+    if (s.spawns_left > 0 && s.spawn_timer >= k.interval0) {
+        if (s.n_spots < MG_SS_MAXSPOTS) mg_ss_new_spot(k, s.rng, s.spots[s.n_spots++]);
+        s.spawns_left--;
+        s.spawn_timer = 0;
+    }
+    int hit = 0, nd = 0;
+    for (int i = 0; i < (int)s.n_spots; ++i) {
+        if (s.spots[i].done) {
+            for (int j = i; j + 1 < (int)s.n_spots; ++j) s.spots[j] = s.spots[j + 1];
+            s.n_spots--;
+            // the element that slid into slot i is skipped this step, exactly like list.remove inside `for`
+        } else {
+            int dx, dy;
+            if (mg_ss_advance_spot(k, trig, s.spots[i], cx, cy, dx, dy)) hit++;
+            f.disc_x[nd] = (int16_t)dx;
+            f.disc_y[nd] = (int16_t)dy;
+            f.disc_r[nd] = s.spots[i].radius;
+            nd++;
+        }
+    }
+    int red_now = 0, bg_red = 0;
+    if (hit > 0) {
+        s.hp = s.hp - k.p.spot_damage;
+        r += k.p.reward_inside_spotlight;
+        int width = (int)((double)(MG_W / 2) * (1.0 - s.hp / k.p.agent_health));
+        if (width > MG_W) width = MG_W;
+        if (width > 0) {
+            red_now = width;
+            if (width > s.red_w_max) s.red_w_max = (int16_t)width;
+        }
+        bg_red = k.p.visual_feedback ? 1 : 0;
+    } else {
+        r += k.p.reward_outside_spotlight;
+    }
+    if (k.p.black_background) {
+        if (bg_red)
+            s.bg_red = 2;
+        else
+            s.bg_blue = 2;
+    }
+    if (s.hp <= 0.0) {
+        spot_done = true;
+        r += k.p.reward_death;
+    }
+    reward += r;
+    // ---- coin task
+    bool coins_done = true;
+    if (s.num_coins > 0) {
+        r = 0.0;
+        for (int i = 0; i < (int)s.n_coins; ++i) {
+            double dx = (double)cx - (double)s.coins[i][0], dy = (double)cy - (double)s.coins[i][1];
+            if (sqrt(dx * dx + dy * dy) <= (double)(k.coin_radius + k.radius)) {
+                for (int j = i; j + 1 < (int)s.n_coins; ++j) {
+                    s.coins[j][0] = s.coins[j + 1][0];
+                    s.coins[j][1] = s.coins[j + 1][1];
+                }
+                s.n_coins--;
+                r += k.p.reward_coin;
+                s.coins_collected++;
+            }
+        }
+        coins_done = s.n_coins == 0;
+        reward += r;
+    }
+    // ---- exit task
+    int success = 0;
+    bool exit_done = false;
+    if (k.p.use_exit) {
+        r = 0.0;
+        if (coins_done) {
+            s.exit_open = 1;
+            double dx = (double)cx - (double)s.exit_x, dy = (double)cy - (double)s.exit_y;
+            if (sqrt(dx * dx + dy * dy) <= k.exit_radius + (double)k.radius) {
+                exit_done = true;
+                r = k.p.reward_exit;
+            }
+        }
+        reward += r;
+    }
+    bool done = false;
+    if (spot_done) {
+        done = true;
+    } else if (coins_done) {
+        if (k.p.use_exit) {
+            if (exit_done) {
+                done = true;
+                success = 1;
+            }
+        } else if (s.num_coins > 0) {
+            done = true;
+            success = 1;
+        }
+    }
+    s.t++;
+    if (s.t == k.p.max_steps) done = true;
+    if (k.p.show_last_positive_reward) {
+        s.coin_bar = s.last_reward > 0.0 ? 1 : 2;
+        s.last_reward = reward;
+    }
+    s.ep_reward = s.ep_reward + reward;
+    s.ep_len++;
+    reward_out = reward;
+    mg_ss_frame_common(s, rot, f);
+    f.n_discs = (uint8_t)nd;
+    f.red_now = (int16_t)red_now;
+    f.bg_kind = mg_ss_bg_kind(s, bg_red);
+    if (done) {
+        s.live = 0;
+        if (info) {
+            info[MG_INFO_REWARD] = s.ep_reward;
+            info[MG_INFO_LENGTH] = (double)s.ep_len;
+            info[MG_INFO_SUCCESS] = (double)success;
+            info[MG_INFO_A] = s.hp / k.p.agent_health;
+            info[MG_INFO_B] = (double)s.coins_collected / (double)s.num_coins;
+            info[MG_INFO_GT0] = 0.0;
+            info[MG_INFO_GT1] = 0.0;
+            info[7] = 0.0;
+        }
+    }
+    return done;
+}

@@ -18,7 +18,7 @@ MG_MAX_CHOICES = 16
 MG_MM_MAX_COMMANDS = 152
 MG_MM_STATE_BYTES = 256
 MG_MP_STATE_BYTES = 128
-MG_SS_STATE_BYTES = 2048
+MG_SS_STATE_BYTES = 1024
 MG_FLAG_AUTORESET = 1
 MG_FLAG_STREAM_OBS = 2
 MG_MM_CONTINUOUS, MG_MM_GRID, MG_MM_ENDLESS = 0, 1, 2

@@ -50,7 +50,7 @@ extern "C" {
 #define MG_MM_MAX_COMMANDS 152     /* capacity of the per-env command list */
 #define MG_MM_STATE_BYTES 256      /* one env record (Mortar Mayhem family) */
 #define MG_MP_STATE_BYTES 128      /* one env record (Mystery Path) */
-#define MG_SS_STATE_BYTES 2048     /* one env record (Searing Spotlights) */
+#define MG_SS_STATE_BYTES 1024     /* one env record (Searing Spotlights) */
 
 #define MG_EINVAL (-1)  /* bad argument / unsupported option value */
 #define MG_ENODEV (-2)  /* no usable CUDA device */

@@ -719,11 +719,349 @@ class MysteryPathOracle(_OracleEnv):
         return _frame_to_obs(frame)
 
 
+# --------------------------------------------------------------------------------------------------
+# Searing Spotlights
+# --------------------------------------------------------------------------------------------------
+class _Spot:
+    """pygame_assets.py:61-131 (Spotlight)."""
+
+    def __init__(self, dim, radius, speed, rng):
+        self.speed = speed
+        self.t = 0
+        self.done = False
+        diagonal = math.sqrt(math.pow(dim, 2) + math.pow(dim, 2))
+        self.spawn_radius = diagonal / 2 + radius
+        self.radius = radius
+        start = rng.integers(0, 360)
+        target = start + 180 + rng.integers(-45, 45)
+        offset = target + rng.integers(-135, 135)
+        c = dim // 2
+        self.spawn = tuple(c + v for v in R.vec_rotate(float(self.spawn_radius), 0.0, float(start)))
+        self.target = tuple(c + v for v in R.vec_rotate(float(self.spawn_radius), 0.0, float(target)))
+        self.offset = tuple(c + v for v in R.vec_rotate(float(self.spawn_radius), 0.0, float(offset)))
+        self.cur = self.spawn
+
+    @staticmethod
+    def _lerp(a, b, t):
+        t = float(t)
+        return (a[0] * (1 - t) + b[0] * t, a[1] * (1 - t) + b[1] * t)
+
+    def advance(self):
+        """Spotlight.draw minus the drawing: returns the integer centre used for the circle."""
+        lt = self._lerp(self.target, self.offset, self.t)
+        self.cur = self._lerp(self.spawn, lt, self.t)
+        centre = (int(self.cur[0]), int(self.cur[1]))
+        self.t += self.speed
+        if self.t >= 1.0:
+            self.t = 1.0
+            self.done = True
+        return centre
+
+    def hits(self, cx, cy, agent_radius):
+        dx, dy = float(cx) - self.cur[0], float(cy) - self.cur[1]
+        return math.sqrt(dx * dx + dy * dy) <= self.radius + agent_radius
+
+
+class SearingSpotlightsOracle(_OracleEnv):
+    """searing_spotlights.py:15-562 (SearingSpotlightsEnv) on CharacterController, GridPositionSampler
+    (pygame_assets.py:7-59), Spotlight, Coin (:133-167), Exit (:169-220), tiled background (:222-239)."""
+
+    env_id = "SearingSpotlights-v0"
+    default_reset_parameters = {
+        "max_steps": 256, "initial_spawns": 4, "num_spawns": 30, "initial_spawn_interval": 30,
+        "spawn_interval_threshold": 10, "spawn_interval_decay": 0.95, "spot_min_radius": 30.0 * SCALE,
+        "spot_max_radius": 55.0 * SCALE, "spot_min_speed": 0.0025, "spot_max_speed": 0.0075, "spot_damage": 1.0,
+        "visual_feedback": True, "black_background": False, "hide_chessboard": False,
+        "light_dim_off_duration": 6, "light_threshold": 255, "num_coins": [1], "coin_scale": 1.5 * SCALE,
+        "coins_visible": False, "use_exit": True, "exit_scale": 2.0 * SCALE, "exit_visible": False,
+        "agent_speed": 12.0 * SCALE, "agent_health": 5, "agent_scale": 1.0 * SCALE, "agent_visible": False,
+        "sample_agent_position": True, "show_last_action": True, "show_last_positive_reward": True,
+        "reward_inside_spotlight": 0.0, "reward_outside_spotlight": 0.0, "reward_death": 0.0, "reward_exit": 1.0,
+        "reward_max_steps": 0.0, "reward_coin": 0.25,
+    }
+    BAR_H = int(16 * SCALE)
+
+    def __init__(self):
+        super().__init__()
+        # the two tiled backgrounds are built once per instance and mutated in place by reset/step
+        # (hide_chessboard -> white, black_background -> black): sticky across resets
+        self.bg_state = {"blue": "chess", "red": "chess"}
+
+    # ---- GridPositionSampler -----------------------------------------------------------------------
+    def _sample(self, rng, block_radius):
+        n = SCREEN
+        free = np.flatnonzero(~self.spawn_mask.reshape(-1))
+        cell = int(free[int(rng.integers(0, len(free)))])
+        y, x = cell // n, cell % n
+        self._block(x, y, block_radius)
+        return x, y
+
+    def _block(self, x, y, r=21):
+        n = SCREEN
+        yy, xx = np.ogrid[-y:n - y, -x:n - x]
+        self.spawn_mask[xx * xx + yy * yy < r * r] = True
+
+    @staticmethod
+    def _clamp_spawn(x, y, offset=30):
+        o = int(offset * SCALE)
+        x = o if x < o else (SCREEN - o if x > SCREEN - o else x)
+        y = o if y < o else (SCREEN - o if y > SCREEN - o else y)
+        return x, y
+
+    def _new_spot(self, rng):
+        p = self.p
+        radius = rng.integers(p["spot_min_radius"], p["spot_max_radius"] + 1)
+        speed = rng.uniform(p["spot_min_speed"], p["spot_max_speed"])
+        return _Spot(SCREEN, radius, speed, rng)
+
+    # ---- reset -------------------------------------------------------------------------------------
+    def reset(self, seed=None, options=None):
+        rng = self._seed(seed)
+        p = self.p = self.process_reset_params(options)
+        self.max_episode_steps = p["max_steps"]
+        self.t = 0
+        if p["hide_chessboard"]:
+            self.bg_state["blue"] = self.bg_state["red"] = "white"
+        self.spawn_mask = np.zeros((SCREEN, SCREEN), dtype=bool)
+        self.rewards = []
+        self.last_action = [0, 0]
+        rotation = int(rng.choice([0, 45, 90, 135, 180, 225, 270, 315]))
+        self.sprites = assets.agent_sprites(p["agent_scale"])
+        self.radius = int(25 * p["agent_scale"])
+        self.rotation = rotation
+        if p["sample_agent_position"]:
+            x, y = self._sample(rng, 28)
+            x, y = x + int(rng.integers(2, 4)), y + int(rng.integers(2, 4))
+        else:
+            x, y = SCREEN // 2, SCREEN // 2
+            self._block(x, y)
+        self.cx, self.cy = int(x), int(y)
+        self.agent_health = p["agent_health"]
+        self.hp = self.agent_health
+        q = int(SCREEN // 4)
+        self.q = q
+        # top bar: grey, green health on the first half, action boxes (searing_spotlights.py:372-389)
+        self.bar = np.zeros((self.BAR_H, SCREEN), dtype=np.uint32)
+        self.bar[:, :] = R.map_rgb((50, 50, 50))
+        self.bar[:, 0:q * 2] = R.map_rgb((0, 255, 0))
+        self.act_colors = [(120, 120, 120), (116, 1, 113), (255, 94, 14)]
+        if p["show_last_action"]:
+            self.bar[:, q * 2:q * 3] = R.map_rgb(self.act_colors[0])
+            self.bar[:, q * 3:q * 4] = R.map_rgb(self.act_colors[0])
+        if p["show_last_positive_reward"]:
+            self.last_reward = 0.0
+            if p["show_last_action"]:
+                self.coin_bar = (int(q * 2.75), int(q * 0.5))
+            else:
+                self.coin_bar = (int(q * 2), int(q * 2))
+        # spotlights: every interval is popped from the wrong end, so intervals[0] applies throughout (quirk A.9#5)
+        self.spawn_intervals = []
+        initial = p["initial_spawn_interval"]
+        for _ in range(p["num_spawns"]):
+            self.spawn_intervals.append(int(initial + p["spawn_interval_threshold"]))
+            initial = initial * math.pow(p["spawn_interval_decay"], 1)
+        self.alpha = 0 if p["light_dim_off_duration"] > 0 else max(0, min(255, p["light_threshold"]))
+        self.spots = []
+        self.spawn_timer = 0
+        for _ in range(p["initial_spawns"]):
+            self.spots.append(self._new_spot(rng))
+        self.coins_collected = 0
+        self.coins = []
+        self.num_coins = int(rng.choice(p["num_coins"])) if len(p["num_coins"]) > 0 else 0
+        self.coin_radius = int(10 * p["coin_scale"])
+        for _ in range(self.num_coins):
+            x, y = self._sample(rng, 21)
+            x, y = x + int(rng.integers(2, 4)), y + int(rng.integers(2, 4))
+            self.coins.append(self._clamp_spawn(x, y))
+        x, y = self._sample(rng, 21)
+        x, y = x + int(rng.integers(2, 4)), y + int(rng.integers(2, 4))
+        self.exit = self._clamp_spawn(x, y)
+        self.exit_open = False
+        self.exit_radius = 20 / 2 * p["exit_scale"]
+        self.bg = "blue"
+        if p["black_background"]:
+            self.bg_state["blue"] = "black"
+        return self._render([], 0), {}
+
+    # ---- step --------------------------------------------------------------------------------------
+    def step(self, action):
+        p = self.p
+        rng = self._rng
+        self.cx, self.cy, self.rotation = move_clamped(
+            self.cx, self.cy, self.rotation, action, p["agent_speed"], self.radius,
+            (0, self.BAR_H, SCREEN, SCREEN - self.BAR_H))
+        q = self.q
+        if p["show_last_action"]:
+            self.bar[:, q * 2:q * 3] = R.map_rgb(self.act_colors[int(self.last_action[0])])
+            self.bar[:, q * 3:q * 4] = R.map_rgb(self.act_colors[int(self.last_action[1])])
+            self.last_action = action
+        if self.alpha <= p["light_threshold"]:
+            if p["light_dim_off_duration"] > 0:
+                self.alpha = max(0, min(255, self.alpha + int(255 / p["light_dim_off_duration"])))
+            else:
+                self.alpha = max(0, min(255, p["light_threshold"]))
+        reward = 0.0
+        # -- spotlight task (:187-242)
+        r = 0.0
+        spot_done = False
+        self.spawn_timer += 1
+        if self.spawn_intervals:
+            if self.spawn_timer >= self.spawn_intervals[0]:
+                self.spots.append(self._new_spot(rng))
+                self.spawn_intervals.pop()
+                self.spawn_timer = 0
+        discs = []
+        hit = 0
+        i = 0
+        while i < len(self.spots):  # `for spot in list` with list.remove inside: the next element is skipped
+            spot = self.spots[i]
+            if spot.done:
+                self.spots.remove(spot)
+            else:
+                discs.append((spot.advance(), int(spot.radius)))
+                if spot.hits(self.cx, self.cy, self.radius):
+                    hit += 1
+            i += 1
+        if hit > 0:
+            self.hp -= p["spot_damage"]
+            r += p["reward_inside_spotlight"]
+            width = int(SCREEN // 2 * (1 - self.hp / self.agent_health))
+            if width > 0:
+                self.bar[:, 0:min(width, SCREEN)] = R.map_rgb((255, 0, 0))
+            self.bg = "red" if p["visual_feedback"] else "blue"
+        else:
+            self.bg = "blue"
+            r += p["reward_outside_spotlight"]
+        if p["black_background"]:
+            self.bg_state[self.bg] = "black"
+        if self.hp <= 0:
+            spot_done = True
+            r += p["reward_death"]
+        reward += r
+        # -- coin task (:288-311)
+        if self.num_coins > 0:
+            r = 0.0
+            i = 0
+            while i < len(self.coins):
+                c = self.coins[i]
+                dx, dy = float(self.cx) - float(c[0]), float(self.cy) - float(c[1])
+                if math.sqrt(dx * dx + dy * dy) <= self.coin_radius + self.radius:
+                    self.coins.remove(c)
+                    r += p["reward_coin"]
+                    self.coins_collected += 1
+                i += 1
+            coins_done = not self.coins
+            reward += r
+        else:
+            coins_done = True
+        # -- exit task (:313-330)
+        success = 0
+        exit_done = False
+        if p["use_exit"]:
+            r = 0.0
+            if coins_done:
+                self.exit_open = True
+                dx, dy = float(self.cx) - float(self.exit[0]), float(self.cy) - float(self.exit[1])
+                if math.sqrt(dx * dx + dy * dy) <= self.exit_radius + self.radius:
+                    exit_done = True
+                    r = p["reward_exit"]
+            reward += r
+        done = False
+        if spot_done:
+            done = True
+        elif coins_done:
+            if p["use_exit"]:
+                if exit_done:
+                    done = True
+                    success = 1
+            elif self.num_coins > 0:
+                done = True
+                success = 1
+        self.t += 1
+        if self.t == self.max_episode_steps:
+            done = True
+        if p["show_last_positive_reward"]:
+            x0, w = self.coin_bar
+            self.bar[:, x0:x0 + w] = R.map_rgb((255, 255, 0) if self.last_reward > 0 else (50, 50, 50))
+            self.last_reward = reward
+        self.rewards.append(reward)
+        info = {}
+        if done:
+            info = {"reward": _seq_sum(self.rewards), "length": len(self.rewards),
+                    "agent_health": self.hp / self.agent_health,
+                    "coins_collected": self.coins_collected / self.num_coins, "success": success}
+        return self._render(discs, self.rotation), reward, done, False, info
+
+    # ---- frame (searing_spotlights.py:526-543 / 419-437) ---------------------------------------------
+    def _layer_order(self):
+        p = self.p
+        layers = ["bg", "spot", "bar"]
+        sid = 1
+        if p["coins_visible"]:
+            layers.insert(sid + 1, "coin")
+        else:
+            layers.insert(sid, "coin")
+            sid += 1
+        if p["exit_visible"]:
+            layers.insert(sid + 2, "exit")
+        else:
+            layers.insert(sid, "exit")
+            sid += 1
+        if p["agent_visible"]:
+            layers.insert(sid + 3, "agent")
+        else:
+            layers.insert(sid, "agent")
+            sid += 1
+        return layers
+
+    def _render(self, discs, sprite_rot):
+        p = self.p
+        dst = R.Surface(SCREEN, SCREEN)
+        for layer in self._layer_order():
+            if layer == "bg":
+                st = self.bg_state[self.bg]
+                if st == "chess":
+                    src = assets.chessboard(SCREEN, (0, 0, 255) if self.bg == "blue" else (255, 0, 0), SCALE)
+                    dst.px[...] = src.px
+                else:
+                    dst.px[...] = R.map_rgb((255, 255, 255)) if st == "white" else 0
+            elif layer == "coin":
+                if self.num_coins > 0:
+                    cs = R.Surface(SCREEN, SCREEN)
+                    R.fill(cs, 255)
+                    cs.colorkey = 255
+                    for c in self.coins:
+                        R.circle(cs, (255, 255, 0), c, self.coin_radius)
+                        R.circle(cs, (255, 165, 0), c, self.coin_radius, int(2 * p["coin_scale"]))
+                    R.blit(cs, dst, (0, 0))
+            elif layer == "exit":
+                es = assets.exit_sprite(p["exit_scale"], self.exit_open)
+                R.blit(es, dst, (self.exit[0] - (es.w >> 1), self.exit[1] - (es.h >> 1)))
+            elif layer == "agent":
+                sp = self.sprites[sprite_rot // 45]
+                R.blit(sp, dst, (self.cx - (sp.w >> 1), self.cy - (sp.h >> 1)))
+            elif layer == "spot":
+                ss = R.Surface(SCREEN, SCREEN)
+                ss.colorkey = R.map_rgb((255, 0, 0))
+                ss.alpha = self.alpha
+                for centre, radius in discs:
+                    R.circle(ss, (255, 0, 0), centre, radius)
+                    if p["black_background"]:
+                        R.circle(ss, (255, 255, 255), centre, radius, 1)
+                R.blit(ss, dst, (0, 0))
+            elif layer == "bar":
+                bar = R.Surface(SCREEN, self.BAR_H)
+                bar.px[...] = self.bar
+                R.blit(bar, dst, (0, 0))
+        return R.array3d(dst)
+
+
 ORACLES = {
     "MortarMayhem-v0": MortarMayhemOracle,
     "MortarMayhem-Grid-v0": GridMortarMayhemOracle,
     "Endless-MortarMayhem-v0": EndlessMortarMayhemOracle,
     "MysteryPath-v0": MysteryPathOracle,
+    "SearingSpotlights-v0": SearingSpotlightsOracle,
 }
 
 

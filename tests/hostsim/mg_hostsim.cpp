@@ -6,6 +6,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "../../endless-memory-gym_b200/csrc/mg_params_host.h"
 #include "../../endless-memory-gym_b200/csrc/mg_policy.h"
 
@@ -22,6 +24,7 @@ int run(const typename P::K& k, const void* assets, void* state, const uint64_t*
         int mode, int act_dims) {
     typedef typename P::State State;
     typedef typename P::Frame Frame;
+    constexpr bool kCheckClean = !std::is_same<P, SSPolicy>::value;
     MgKIO q;
     memset(&q, 0, sizeof(q));
     q.n_steps = 1;
@@ -45,14 +48,14 @@ int run(const typename P::K& k, const void* assets, void* state, const uint64_t*
             a0 = (int)io->actions[(size_t)env * act_dims];
             if (act_dims > 1) a1 = (int)io->actions[(size_t)env * act_dims + 1];
         }
-        P::logic(k, q, env, 0, *st, a0, a1, job, fr);
+        P::logic(k, q, view, env, 0, *st, a0, a1, job, fr);
         for (int fi = 0; fi < job.nframes; ++fi) {
             uint8_t* dst = (job.to_final[fi] ? io->final_obs : io->obs) + (size_t)env * MG_FRAME_BYTES;
             P::compose(ctx, buf, view, k, fr[fi]);
             memcpy(dst, buf, MG_FRAME_BYTES);
             P::restore(ctx, buf, view, k, fr[fi]);
-            // the buffer must be clean again: catches any compose/restore asymmetry
-            if (memcmp(buf, view.tmpl[0], MG_FRAME_BYTES) != 0) return -100;
+            // the buffer must be clean again: catches any compose/restore asymmetry (envs with an un-patch path)
+            if (kCheckClean && memcmp(buf, view.tmpl[0], MG_FRAME_BYTES) != 0) return -100;
         }
     }
     return 0;
@@ -72,4 +75,11 @@ extern "C" int mgsim_mp(const mg_mp_params* p, const void* assets, void* state, 
     MgMPK k;
     mg_mp_derive(p, &k);
     return run<MPPolicy>(k, assets, state, rng4, io, n, mode, 2);
+}
+extern "C" int mgsim_ss(const mg_ss_params* p, const void* assets, void* state, const uint64_t* rng4,
+                        const mg_step_io* io, int n, int mode) {
+    if (mg_ss_check_params(p)) return MG_EINVAL;
+    MgSSK k;
+    mg_ss_derive(p, &k);
+    return run<SSPolicy>(k, assets, state, rng4, io, n, mode, 2);
 }

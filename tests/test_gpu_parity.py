@@ -10,7 +10,7 @@ from replay_util import replay_golden_batched, replay_golden_single, rollout_vs_
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts"]
+CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -32,6 +32,18 @@ def test_golden_batched_autoreset(name):
     ("Endless-MortarMayhem-v0", {"explosion_delay": [4], "explosion_duration": [2], "agent_speed": 5.0}, 64, 2),
     ("MysteryPath-v0", {"max_steps": 40, "show_goal": True, "show_origin": True}, 64, 1),
     ("MysteryPath-v0", {"visual_feedback": False, "agent_scale": 0.3, "max_steps": 64}, 64, 0),
+    ("SearingSpotlights-v0", {"max_steps": 60}, 64, 0),
+    ("SearingSpotlights-v0", {"max_steps": 50, "coins_visible": True, "exit_visible": True, "agent_visible": True,
+                              "num_coins": [2, 4], "agent_health": 3, "spot_damage": 0.7, "initial_spawns": 6,
+                              "spot_min_radius": 12.0, "spot_max_radius": 20.0, "spot_min_speed": 0.01,
+                              "spot_max_speed": 0.03, "reward_inside_spotlight": -0.1, "reward_outside_spotlight": 0.01,
+                              "reward_death": -1.0}, 48, 2),
+    ("SearingSpotlights-v0", {"max_steps": 45, "exit_visible": True, "hide_chessboard": True, "light_threshold": 100,
+                              "light_dim_off_duration": 3, "show_last_action": False, "visual_feedback": False,
+                              "initial_spawn_interval": 3, "spawn_interval_threshold": 2, "num_spawns": 9}, 48, 1),
+    ("SearingSpotlights-v0", {"max_steps": 40, "sample_agent_position": False, "light_dim_off_duration": 0,
+                              "show_last_positive_reward": False, "agent_visible": True, "coin_scale": 1.0,
+                              "exit_scale": 1.0, "agent_scale": 0.4, "agent_speed": 5.0, "num_coins": [3]}, 300, 8),
 ])
 def test_rollout_vs_oracle(env_id, options, n_envs, wpc):
     steps = 70 if n_envs > 100 else 150
@@ -47,7 +59,8 @@ def _random_actions(env, steps, seed):
 
 @pytest.mark.parametrize("env_id,n,options", [("MortarMayhem-v0", 4096, None),
                                               ("MysteryPath-v0", 8192, {"max_steps": 48}),
-                                              ("Endless-MortarMayhem-v0", 8192, None)])
+                                              ("Endless-MortarMayhem-v0", 8192, None),
+                                              ("SearingSpotlights-v0", 8192, {"max_steps": 40})])
 def test_full_size_properties(env_id, n, options):
     """At BASELINE.json's batch sizes: (1) bit-identical to the same envs run in small shards with other
     launch geometries (1 / 3 warps per CTA) — env i's result depends only on seed0+i and its actions;
@@ -138,13 +151,13 @@ def test_abi_rejects_bad_arguments():
     assert b"NULL" in lib.mg_last_error()
 
 
-@pytest.mark.parametrize("env_id", ["MortarMayhem-v0", "MortarMayhem-Grid-v0", "MysteryPath-v0"])
+@pytest.mark.parametrize("env_id", ["MortarMayhem-v0", "MortarMayhem-Grid-v0", "MysteryPath-v0", "SearingSpotlights-v0"])
 def test_rollout_equals_step_loop(env_id):
     """mg_*_rollout (ONE launch, every warp runs all T steps of its envs) and mg_*_step_many (T launches
     enqueued by one call, programmatic dependent launch between them) give exactly what T separate
     step() calls give."""
     n, T = 500, 90
-    opts = {"max_steps": 40} if env_id == "MysteryPath-v0" else None
+    opts = {"max_steps": 40} if env_id in ("MysteryPath-v0", "SearingSpotlights-v0") else None
     a = mg.make(env_id, num_envs=n, device=DEV)
     b = mg.make(env_id, num_envs=n, device=DEV)
     acts = _random_actions(a, T, 77)

@@ -84,15 +84,20 @@ def _decode(blob):
     tmpl_off = [int(v) for v in hdr[4:8]]
     ints = np.frombuffer(blob[32:32 + 8 * 4], dtype=np.int32)
     sprites_raw = np.frombuffer(blob[32 + 8 * 4:32 + 8 * 4 + 24 * 8], dtype=np.uint8).reshape(24, 8)
-    pal = np.frombuffer(blob[32 + 8 * 4 + 24 * 8:32 + 8 * 4 + 24 * 8 + 32 * 4], dtype=np.uint8).reshape(32, 4)
+    dense_off = np.frombuffer(blob[32 + 8 * 4 + 24 * 8:32 + 8 * 4 + 24 * 8 + 24 * 4], dtype=np.uint32)
+    p0 = 32 + 8 * 4 + 24 * 8 + 24 * 4
+    pal = np.frombuffer(blob[p0:p0 + 32 * 4], dtype=np.uint8).reshape(32, 4)
     entries = np.frombuffer(blob[entries_off:entries_off + 4 * n_entries], dtype=np.uint32)
     sprites = []
     for row in sprites_raw:
         first = int(np.frombuffer(row[:4].tobytes(), dtype=np.uint32)[0])
         count = int(np.frombuffer(row[4:6].tobytes(), dtype=np.uint16)[0])
         sprites.append((first, count, int(row[6]), int(row[7])))
+    uints = ints.view(np.uint32)
     return {"agent_dim": int(ints[0]), "agent_radius": int(ints[1]), "icon": (int(ints[2]), int(ints[3])),
-            "sprites": sprites, "pal": pal, "entries": entries, "tmpl_off": tmpl_off}
+            "disc_off": int(uints[4]), "trig_off": int(uints[5]), "stage_bytes": int(uints[6]),
+            "dense_off": [int(v) for v in dense_off], "sprites": sprites, "pal": pal, "entries": entries,
+            "tmpl_off": tmpl_off, "blob": blob}
 
 
 def _sprite_surface(dec, slot, key):
@@ -137,6 +142,52 @@ def test_mp_assets_match_oracle_raster():
     dec = _decode(blob)
     assert np.array_equal(_sprite_surface(dec, 17, 0), OA.fall_off_cross(0.25).px)
     assert not blob[dec["tmpl_off"][0]:dec["tmpl_off"][0] + 21168].any()
+
+
+def _dense_surface(dec, slot, key):
+    first, count, w, h = dec["sprites"][slot]
+    off = dec["dense_off"][slot]
+    idx = dec["blob"][off:off + w * h].reshape(h, w)
+    px = np.full((h, w), key, dtype=np.uint32)
+    for y in range(h):
+        for x in range(w):
+            if idx[y, x] != 255:
+                r, g, b = (int(c) for c in dec["pal"][idx[y, x]][:3])
+                px[y, x] = (r << 16) | (g << 8) | b
+    return px
+
+
+@pytest.mark.parametrize("opts", [None, {"agent_scale": 0.4, "coin_scale": 1.0, "exit_scale": 1.0}])
+def test_ss_assets_match_oracle_raster(opts):
+    import math
+    spec = SPECS["SearingSpotlights-v0"]
+    p = spec.process_reset_params(opts)
+    blob = _host().build_assets("ss", spec.to_struct(p))
+    dec = _decode(blob)
+    want = OA.agent_sprites(p["agent_scale"])
+    for k in range(8):
+        assert np.array_equal(_sprite_surface(dec, k, 255), want[k].px)
+        assert np.array_equal(_dense_surface(dec, k, 255), want[k].px)
+    for slot, is_open in ((18, False), (19, True)):
+        assert np.array_equal(_dense_surface(dec, slot, 255), OA.exit_sprite(p["exit_scale"], is_open).px)
+    # coin = what Coin.draw leaves on the coin surface, centred in a (2r+2)^2 sprite
+    r = int(10 * p["coin_scale"])
+    cs = R.Surface(2 * r + 2, 2 * r + 2)
+    R.fill(cs, 255)
+    R.circle(cs, (255, 255, 0), (r + 1, r + 1), r)
+    R.circle(cs, (255, 165, 0), (r + 1, r + 1), r, int(2 * p["coin_scale"]))
+    assert np.array_equal(_dense_surface(dec, 20, 255), cs.px)
+    # filled-circle row tables == the oracle primitive, for every radius
+    discs = np.frombuffer(blob[dec["disc_off"]:dec["disc_off"] + 2 * 40 * 41].tobytes(), dtype=np.int8).reshape(-1, 2)
+    for rad in range(1, 41):
+        rows = R.disc_rows(rad)
+        for dy in range(-rad, rad):
+            lo, hi = discs[rad * (rad - 1) + dy + rad]
+            assert (int(lo), int(hi)) == rows[dy], (rad, dy)
+    trig = np.frombuffer(blob[dec["trig_off"]:dec["trig_off"] + 720 * 8].tobytes(), dtype=np.float64).reshape(360, 2)
+    for a in range(360):
+        assert tuple(trig[a]) == R.vec_rotate(1.0, 0.0, float(a)), a
+    assert dec["stage_bytes"] % 128 == 0 and dec["stage_bytes"] <= dec["tmpl_off"][0]
 
 
 def test_option_validation_and_loud_failure_without_gpu():

@@ -7,7 +7,7 @@ import pytest
 from hostsim_util import HostSimBackend
 from replay_util import replay_golden_batched, replay_golden_single, rollout_vs_oracle
 
-CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts"]
+CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts"]
 
 
 @pytest.fixture(scope="module")
@@ -34,6 +34,18 @@ def test_golden_batched_autoreset(name, backend):
     ("Endless-MortarMayhem-v0", {"explosion_delay": [4], "explosion_duration": [2], "agent_speed": 5.0}),
     ("MysteryPath-v0", {"max_steps": 40, "show_goal": True}),
     ("MysteryPath-v0", {"visual_feedback": False, "agent_scale": 0.3, "max_steps": 64}),
+    ("SearingSpotlights-v0", {"max_steps": 60}),
+    ("SearingSpotlights-v0", {"max_steps": 50, "coins_visible": True, "exit_visible": True, "agent_visible": True,
+                              "num_coins": [2, 4], "agent_health": 3, "spot_damage": 0.7, "initial_spawns": 6,
+                              "spot_min_radius": 12.0, "spot_max_radius": 20.0, "spot_min_speed": 0.01,
+                              "spot_max_speed": 0.03, "reward_inside_spotlight": -0.1, "reward_outside_spotlight": 0.01,
+                              "reward_death": -1.0}),
+    ("SearingSpotlights-v0", {"max_steps": 45, "exit_visible": True, "hide_chessboard": True, "light_threshold": 100,
+                              "light_dim_off_duration": 3, "show_last_action": False, "visual_feedback": False,
+                              "initial_spawn_interval": 3, "spawn_interval_threshold": 2, "num_spawns": 9}),
+    ("SearingSpotlights-v0", {"max_steps": 40, "sample_agent_position": False, "light_dim_off_duration": 0,
+                              "show_last_positive_reward": False, "agent_visible": True, "coin_scale": 1.0,
+                              "exit_scale": 1.0, "agent_scale": 0.4, "agent_speed": 5.0, "num_coins": [3]}),
 ])
 def test_rollout_vs_oracle(env_id, options, backend):
     episodes = rollout_vs_oracle(env_id, options, n_envs=8, steps=150, seed0=1000, device="cpu", backend=backend)
