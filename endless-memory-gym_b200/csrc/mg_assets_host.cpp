@@ -24,7 +24,8 @@ struct Builder {
     std::vector<uint32_t> entries;
     std::vector<std::vector<uint8_t>> templates;
     std::vector<uint8_t> dense[MG_SPR_COUNT];  // w*h palette indices, 255 = transparent
-    std::vector<int8_t> discs;                 // filled-circle row spans (SS spotlights / coins)
+    std::vector<int8_t> discs;                 // filled-circle row spans, then column spans (SS spotlights)
+    bool discs_ok = true;
     std::vector<double> trig;                  // (cos, sin) of integer degrees
     int n_pal = 0;
 
@@ -106,6 +107,29 @@ struct Builder {
                         hi = x - c;
                         any = true;
                     }
+                discs.push_back((int8_t)lo);
+                discs.push_back((int8_t)hi);
+            }
+        }
+        // the same discs as COLUMN spans (dx = -r..r-1 -> ymin, ymax): a column of the [x][y][c] frame is
+        // contiguous memory, so the kernel fills discs column-wise. Appended after the row tables.
+        for (int r = 1; r <= MG_MAX_DISC_R; ++r) {
+            Surface s(2 * r + 4, 2 * r + 4);
+            int c = r + 2;
+            mgr::circle(s, 1, c, c, r, 0, false);
+            for (int dx = -r; dx < r; ++dx) {
+                int lo = 1, hi = 0, runs = 0;
+                bool prev = false;
+                for (int y = 0; y < s.h; ++y) {
+                    bool on = s.at(c + dx, y) != 0;
+                    if (on && !prev) {
+                        runs++;
+                        lo = y - c;
+                    }
+                    if (on) hi = y - c;
+                    prev = on;
+                }
+                if (runs > 1) discs_ok = false;  // a column must be one run (convex shape)
                 discs.push_back((int8_t)lo);
                 discs.push_back((int8_t)hi);
             }
@@ -351,6 +375,7 @@ extern "C" long mg_ss_build_assets(const mg_ss_params* p, void* host_out, size_t
     if (!build_exit(b, p->exit_scale)) return MG_EINVAL;
     if (!build_coin(b, p->coin_scale)) return MG_EINVAL;
     b.add_disc_tables();
+    if (!b.discs_ok) return MG_EINVAL;
     b.add_trig_table();
     Surface black(MG_W, MG_W);
     b.add_template(0, black);

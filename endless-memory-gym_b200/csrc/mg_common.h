@@ -22,6 +22,10 @@
 #define MG_FRAME_BYTES (MG_W * MG_W * 3)  // 21168 = 1323 * 16
 #define MG_FRAME_VEC16 (MG_FRAME_BYTES / 16)
 
+struct alignas(16) MgVec16 {
+    uint32_t x, y, z, w;
+};
+
 // MortarTile colours (pygame_assets.py:323-329), packed 0x00BBGGRR = bytes R,G,B in memory order
 #define MG_RGB_TILE_FILL (21u | (43u << 8) | (77u << 16))
 #define MG_RGB_TILE_EDGE (29u | (60u << 8) | (107u << 16))

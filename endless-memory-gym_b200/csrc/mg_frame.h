@@ -246,46 +246,105 @@ MG_HD uint32_t mg_ss_bar(const MgSSDrawK& k, const MgSSFrame& f, int x) {
     return c;
 }
 
-MG_HD uint32_t mg_ss_pixel(const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f, int x, int y) {
-    const int8_t* discs = (const int8_t*)(a.base + a.hdr->disc_off);
-    uint32_t col = 0;
-    for (int li = k.n_layers - 1; li >= 0; --li) {
-        int L = k.layers[li];
-        if (L == 2) {  // MG_SS_L_BAR
-            if (y < 4) return mg_ss_bar(k, f, x);
-        } else if (L == 1) {  // MG_SS_L_SPOT: what lies underneath, dimmed unless a spotlight disc covers the pixel
-            uint32_t under = 0;
-            bool found = false;
-            for (int lj = li - 1; lj >= 0 && !found; --lj) {
-                int M = k.layers[lj];
-                if (M == 0) {
-                    under = mg_ss_bg(f.bg_kind, x, y);
-                    found = true;
-                } else if (M == 2) {
-                    if (y < 4) {
-                        under = mg_ss_bar(k, f, x);
-                        found = true;
-                    }
-                } else if (M != 3 || k.has_coin_layer) {
-                    found = mg_ss_layer_at(a, f, M, x, y, under);
-                }
-            }
-            if (f.alpha == 0) return under;
-            for (int d = 0; d < (int)f.n_discs; ++d)
-                if (mg_disc_has(discs, f.disc_r[d], f.disc_x[d], f.disc_y[d], x, y)) return under;
-            if (f.alpha == 255) return 0u;
-            uint32_t A = f.alpha, r = under & 255u, g = (under >> 8) & 255u, b = (under >> 16) & 255u;
-            r -= r * A / 255u;
-            g -= g * A / 255u;
-            b -= b * A / 255u;
-            return r | (g << 8) | (b << 16);
-        } else if (L == 0) {
-            return mg_ss_bg(f.bg_kind, x, y);
-        } else if (L != 3 || k.has_coin_layer) {
-            if (mg_ss_layer_at(a, f, L, x, y, col)) return col;
+// Per-frame scene under the spotlight layer, resolved once per frame: among coin < exit < agent (their painter's
+// order is fixed by the insert logic of searing_spotlights.py:526-542) the ones BELOW the spotlight layer.
+struct MgSSUnder {
+    int ag_x0, ag_y0, ag_dim;      // agent sprite box (dim 0 = not below the spotlight layer)
+    int ex_x0, ex_y0, ex_w, ex_h;  // exit sprite box (w 0 = not below)
+    int co_w, co_h, n_coins;       // coin sprite size (n_coins 0 = none below)
+    const uint8_t* ag_bmp;
+    const uint8_t* ex_bmp;
+    const uint8_t* co_bmp;
+    int bg_kind;
+    int bar_below;                 // never with the reference's orders; kept for generality
+};
+
+MG_HD MgSSUnder mg_ss_scene(const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f, int spot_li) {
+    MgSSUnder u;
+    u.ag_dim = u.ex_w = u.ex_h = u.n_coins = u.bar_below = 0;
+    u.ag_x0 = u.ag_y0 = u.ex_x0 = u.ex_y0 = u.co_w = u.co_h = 0;
+    u.ag_bmp = u.ex_bmp = u.co_bmp = a.base;
+    u.bg_kind = f.bg_kind;
+    for (int lj = 1; lj < spot_li; ++lj) {
+        int M = k.layers[lj];
+        if (M == 5) {
+            u.ag_dim = a.hdr->agent_dim;
+            u.ag_x0 = f.sx - (u.ag_dim >> 1);
+            u.ag_y0 = f.sy - (u.ag_dim >> 1);
+            u.ag_bmp = a.base + a.hdr->dense_off[MG_SPR_AGENT0 + f.srot];
+        } else if (M == 4) {
+            int slot = f.exit_open ? MG_SPR_EXIT_OPEN : MG_SPR_EXIT_CLOSED;
+            const MgSprite sp = a.hdr->sprite[slot];
+            u.ex_w = sp.w;
+            u.ex_h = sp.h;
+            u.ex_x0 = f.exit_x - (sp.w >> 1);
+            u.ex_y0 = f.exit_y - (sp.h >> 1);
+            u.ex_bmp = a.base + a.hdr->dense_off[slot];
+        } else if (M == 3) {
+            const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
+            u.co_w = sp.w;
+            u.co_h = sp.h;
+            u.n_coins = f.n_coins;
+            u.co_bmp = a.base + a.hdr->dense_off[MG_SPR_COIN];
+        } else if (M == 2) {
+            u.bar_below = 1;
         }
     }
-    return col;
+    return u;
+}
+
+MG_HD uint32_t mg_pal(const MgAssetView& a, uint8_t pi) {
+    const uint8_t* c = a.palette[pi];
+    return (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
+}
+
+// colour of what lies UNDER the spotlight layer at (x, y): agent over exit over coins over the background
+MG_HD uint32_t mg_ss_under(const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f, const MgSSUnder& u, int x,
+                           int y) {
+    if (u.bar_below && y < 4) return mg_ss_bar(k, f, x);
+    unsigned du = (unsigned)(x - u.ag_x0), dv = (unsigned)(y - u.ag_y0);
+    if (du < (unsigned)u.ag_dim && dv < (unsigned)u.ag_dim) {
+        uint8_t pi = u.ag_bmp[dv * u.ag_dim + du];
+        if (pi != 255) return mg_pal(a, pi);
+    }
+    du = (unsigned)(x - u.ex_x0), dv = (unsigned)(y - u.ex_y0);
+    if (du < (unsigned)u.ex_w && dv < (unsigned)u.ex_h) {
+        uint8_t pi = u.ex_bmp[dv * u.ex_w + du];
+        if (pi != 255) return mg_pal(a, pi);
+    }
+    for (int c = u.n_coins - 1; c >= 0; --c) {  // coins are drawn in list order: the last one covering the pixel wins
+        du = (unsigned)(x - (f.coins[c][0] - (u.co_w >> 1))), dv = (unsigned)(y - (f.coins[c][1] - (u.co_h >> 1)));
+        if (du < (unsigned)u.co_w && dv < (unsigned)u.co_h) {
+            uint8_t pi = u.co_bmp[dv * u.co_w + du];
+            if (pi != 255) return mg_pal(a, pi);
+        }
+    }
+    return mg_ss_bg(u.bg_kind, x, y);
+}
+
+MG_HD uint32_t mg_ss_dim(uint32_t c, uint32_t A) {
+    uint32_t r = c & 255u, g = (c >> 8) & 255u, b = (c >> 16) & 255u;
+    r -= r * A / 255u;  // SDL: d + trunc((0 - d) * A / 255)
+    g -= g * A / 255u;
+    b -= b * A / 255u;
+    return r | (g << 8) | (b << 16);
+}
+
+// colour of the layers ABOVE the spotlight layer at (x, y) (visible coins / exit / agent, top bar); false = none
+MG_HD bool mg_ss_over(const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f, int spot_li, int x, int y,
+                      uint32_t& col) {
+    for (int li = k.n_layers - 1; li > spot_li; --li) {
+        int L = k.layers[li];
+        if (L == 2) {
+            if (y < 4) {
+                col = mg_ss_bar(k, f, x);
+                return true;
+            }
+        } else if (mg_ss_layer_at(a, f, L, x, y, col)) {
+            return true;
+        }
+    }
+    return false;
 }
 
 MG_HD void mg_put_px(uint8_t* buf, int x, int y, uint32_t col) {
@@ -295,52 +354,86 @@ MG_HD void mg_put_px(uint8_t* buf, int x, int y, uint32_t col) {
     o[2] = (uint8_t)(col >> 16);
 }
 
-// evaluate the frame function over a clipped rectangle
+// kind 0: under() dimmed by alpha, 1: under() undimmed, 2: over() where present — over a clipped rectangle
 template <class Ctx>
-MG_HD void mg_ss_rect(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f, int x0,
-                      int y0, int w, int h) {
+MG_HD void mg_ss_rect(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+                      const MgSSUnder& u, int spot_li, int kind, int x0, int y0, int w, int h) {
     int xa = x0 < 0 ? 0 : x0, ya = y0 < 0 ? 0 : y0;
     int xb = x0 + w > MG_W ? MG_W : x0 + w, yb = y0 + h > MG_W ? MG_W : y0 + h;
     if (xb <= xa || yb <= ya) return;
-    int rows = yb - ya, total = (xb - xa) * rows;
+    const int rows = yb - ya, total = (xb - xa) * rows;
+    const uint64_t inv = ((1ull << 24) + (uint64_t)rows - 1) / (uint64_t)rows;  // exact i / rows for i < 2^13
     for (int i = c.lane; i < total; i += c.nl) {
-        int x = xa + i / rows, y = ya + i % rows;
-        mg_put_px(buf, x, y, mg_ss_pixel(a, k, f, x, y));
+        int q = (int)(((uint64_t)i * inv) >> 24);
+        int x = xa + q, y = ya + (i - q * rows);
+        uint32_t col;
+        if (kind == 2) {
+            if (!mg_ss_over(a, k, f, spot_li, x, y, col)) continue;
+        } else {
+            col = mg_ss_under(a, k, f, u, x, y);
+            if (kind == 0) col = mg_ss_dim(col, f.alpha);
+        }
+        mg_put_px(buf, x, y, col);
+    }
+}
+
+// the pixels of one spotlight disc (clipped to the screen), column by column — a column of the frame is
+// contiguous memory: undimmed under()
+template <class Ctx>
+MG_HD void mg_ss_disc(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+                      const MgSSUnder& u, int x0, int y0, int r) {
+    if (r < 1) return;
+    const int8_t* cols = (const int8_t*)(a.base + a.hdr->disc_off) + 2 * MG_MAX_DISC_R * (MG_MAX_DISC_R + 1) +
+                         2 * r * (r - 1);
+    int xa = x0 - r < 0 ? 0 : x0 - r, xb = x0 + r > MG_W ? MG_W : x0 + r;  // [xa, xb) x [ya, yb): box on screen
+    int ya = y0 - r < 0 ? 0 : y0 - r, yb = y0 + r > MG_W ? MG_W : y0 + r;
+    if (xb <= xa || yb <= ya) return;
+    const int rows = yb - ya, total = (xb - xa) * rows;
+    const uint64_t inv = ((1ull << 24) + (uint64_t)rows - 1) / (uint64_t)rows;
+    for (int i = c.lane; i < total; i += c.nl) {
+        int q = (int)(((uint64_t)i * inv) >> 24);
+        int x = xa + q, y = ya + (i - q * rows);
+        int ci = x - x0 + r, dy = y - y0;
+        if (dy < (int)cols[2 * ci] || dy > (int)cols[2 * ci + 1]) continue;
+        mg_put_px(buf, x, y, mg_ss_under(a, k, f, u, x, y));
     }
 }
 
 template <class Ctx>
 MG_HD void mg_ss_compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f) {
-    int spot_li = 0;
+    int spot_li = 1;
     for (int li = 0; li < k.n_layers; ++li)
         if (k.layers[li] == 1) spot_li = li;
+    const MgSSUnder u = mg_ss_scene(a, k, f, spot_li);
+    // 1. everything the spotlight layer dims: black when the lights are fully off, else under() scaled by alpha
     if (f.alpha == 255) {
-        // lights fully off: everything under the spotlight layer is black except inside the discs
-        uint32_t* w = reinterpret_cast<uint32_t*>(buf);
-        for (int i = c.lane; i < MG_FRAME_BYTES / 4; i += c.nl) w[i] = 0u;
-        c.sync();
-        for (int d = 0; d < (int)f.n_discs; ++d) {
-            int r = f.disc_r[d];
-            mg_ss_rect(c, buf, a, k, f, f.disc_x[d] - r, f.disc_y[d] - r, 2 * r, 2 * r);
-        }
-        // layers above the spotlight layer
-        for (int li = spot_li + 1; li < k.n_layers; ++li) {
-            int L = k.layers[li];
-            if (L == 2) {
-                mg_ss_rect(c, buf, a, k, f, 0, 0, MG_W, 4);
-            } else if (L == 5) {
-                int dim = a.hdr->agent_dim;
-                mg_ss_rect(c, buf, a, k, f, f.sx - (dim >> 1), f.sy - (dim >> 1), dim, dim);
-            } else if (L == 4) {
-                const MgSprite sp = a.hdr->sprite[MG_SPR_EXIT_OPEN];
-                mg_ss_rect(c, buf, a, k, f, f.exit_x - (sp.w >> 1), f.exit_y - (sp.h >> 1), sp.w, sp.h);
-            } else if (L == 3 && k.has_coin_layer) {
-                const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
-                for (int q = 0; q < (int)f.n_coins; ++q)
-                    mg_ss_rect(c, buf, a, k, f, f.coins[q][0] - (sp.w >> 1), f.coins[q][1] - (sp.h >> 1), sp.w, sp.h);
-            }
-        }
+        MgVec16* w = reinterpret_cast<MgVec16*>(buf);
+        const MgVec16 z = {0u, 0u, 0u, 0u};
+        for (int i = c.lane; i < MG_FRAME_VEC16; i += c.nl) w[i] = z;
     } else {
-        mg_ss_rect(c, buf, a, k, f, 0, 0, MG_W, MG_W);
+        mg_ss_rect(c, buf, a, k, f, u, spot_li, f.alpha == 0 ? 1 : 0, 0, 0, MG_W, MG_W);
+    }
+    c.sync();
+    // 2. inside the colour-keyed discs the layers underneath show through unchanged
+    if (f.alpha != 0)
+        for (int d = 0; d < (int)f.n_discs; ++d) mg_ss_disc(c, buf, a, k, f, u, f.disc_x[d], f.disc_y[d], f.disc_r[d]);
+    c.sync();
+    // 3. layers above the spotlight layer, in painter's order (overlaps resolved per pixel by mg_ss_over)
+    for (int li = spot_li + 1; li < k.n_layers; ++li) {
+        int L = k.layers[li];
+        if (L == 2) {
+            mg_ss_rect(c, buf, a, k, f, u, spot_li, 2, 0, 0, MG_W, 4);
+        } else if (L == 5) {
+            int dim = a.hdr->agent_dim;
+            mg_ss_rect(c, buf, a, k, f, u, spot_li, 2, f.sx - (dim >> 1), f.sy - (dim >> 1), dim, dim);
+        } else if (L == 4) {
+            const MgSprite sp = a.hdr->sprite[MG_SPR_EXIT_OPEN];
+            mg_ss_rect(c, buf, a, k, f, u, spot_li, 2, f.exit_x - (sp.w >> 1), f.exit_y - (sp.h >> 1), sp.w, sp.h);
+        } else if (L == 3) {
+            const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
+            for (int q = 0; q < (int)f.n_coins; ++q)
+                mg_ss_rect(c, buf, a, k, f, u, spot_li, 2, f.coins[q][0] - (sp.w >> 1), f.coins[q][1] - (sp.h >> 1), sp.w,
+                           sp.h);
+        }
     }
 }

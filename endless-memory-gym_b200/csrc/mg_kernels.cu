@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(320, 1)
             if (trow && lane == 0) trow[4] = mg_now();
             const int nframes = job->nframes;
             for (int fi = 0; fi < nframes; ++fi) {
-                const Frame f = fr[fi];
+                const Frame& f = fr[fi];  // lives in the warp's shared slot until the next logic call
                 const bool to_final = job->to_final[fi] != 0;
                 uint8_t* dst = to_final ? q.io.final_obs + (size_t)env * MG_FRAME_BYTES
                                         : q.io.obs + (size_t)(t % q.ring_n) * q.obs_stride + (size_t)env * MG_FRAME_BYTES;

@@ -178,12 +178,17 @@ def test_ss_assets_match_oracle_raster(opts):
     R.circle(cs, (255, 165, 0), (r + 1, r + 1), r, int(2 * p["coin_scale"]))
     assert np.array_equal(_dense_surface(dec, 20, 255), cs.px)
     # filled-circle row tables == the oracle primitive, for every radius
-    discs = np.frombuffer(blob[dec["disc_off"]:dec["disc_off"] + 2 * 40 * 41].tobytes(), dtype=np.int8).reshape(-1, 2)
+    discs = np.frombuffer(blob[dec["disc_off"]:dec["disc_off"] + 4 * 40 * 41].tobytes(), dtype=np.int8).reshape(-1, 2)
     for rad in range(1, 41):
         rows = R.disc_rows(rad)
         for dy in range(-rad, rad):
             lo, hi = discs[rad * (rad - 1) + dy + rad]
             assert (int(lo), int(hi)) == rows[dy], (rad, dy)
+        # column spans (second table) describe the same pixel set
+        cols = discs[40 * 41 + rad * (rad - 1):40 * 41 + rad * (rad + 1)]
+        by_col = {(dx, dy) for dx in range(-rad, rad) for dy in range(int(cols[dx + rad][0]), int(cols[dx + rad][1]) + 1)}
+        by_row = {(dx, dy) for dy in range(-rad, rad) for dx in range(rows[dy][0], rows[dy][1] + 1)}
+        assert by_col == by_row, rad
     trig = np.frombuffer(blob[dec["trig_off"]:dec["trig_off"] + 720 * 8].tobytes(), dtype=np.float64).reshape(360, 2)
     for a in range(360):
         assert tuple(trig[a]) == R.vec_rotate(1.0, 0.0, float(a)), a
