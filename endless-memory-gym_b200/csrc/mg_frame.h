@@ -206,6 +206,11 @@ MG_HD bool mg_dense_at(const MgAssetView& a, int slot, int ax, int ay, int x, in
     return true;
 }
 
+MG_HD uint32_t mg_pal(const MgAssetView& a, uint8_t pi) {
+    const uint8_t* c = a.palette[pi];
+    return (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
+}
+
 MG_HD bool mg_ss_layer_at(const MgAssetView& a, const MgSSFrame& f, int layer, int x, int y, uint32_t& col) {
     if (layer == 5) {  // MG_SS_L_AGENT
         int half = a.hdr->agent_dim >> 1;
@@ -246,82 +251,6 @@ MG_HD uint32_t mg_ss_bar(const MgSSDrawK& k, const MgSSFrame& f, int x) {
     return c;
 }
 
-// Per-frame scene under the spotlight layer, resolved once per frame: among coin < exit < agent (their painter's
-// order is fixed by the insert logic of searing_spotlights.py:526-542) the ones BELOW the spotlight layer.
-struct MgSSUnder {
-    int ag_x0, ag_y0, ag_dim;      // agent sprite box (dim 0 = not below the spotlight layer)
-    int ex_x0, ex_y0, ex_w, ex_h;  // exit sprite box (w 0 = not below)
-    int co_w, co_h, n_coins;       // coin sprite size (n_coins 0 = none below)
-    const uint8_t* ag_bmp;
-    const uint8_t* ex_bmp;
-    const uint8_t* co_bmp;
-    int bg_kind;
-    int bar_below;                 // never with the reference's orders; kept for generality
-};
-
-MG_HD MgSSUnder mg_ss_scene(const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f, int spot_li) {
-    MgSSUnder u;
-    u.ag_dim = u.ex_w = u.ex_h = u.n_coins = u.bar_below = 0;
-    u.ag_x0 = u.ag_y0 = u.ex_x0 = u.ex_y0 = u.co_w = u.co_h = 0;
-    u.ag_bmp = u.ex_bmp = u.co_bmp = a.base;
-    u.bg_kind = f.bg_kind;
-    for (int lj = 1; lj < spot_li; ++lj) {
-        int M = k.layers[lj];
-        if (M == 5) {
-            u.ag_dim = a.hdr->agent_dim;
-            u.ag_x0 = f.sx - (u.ag_dim >> 1);
-            u.ag_y0 = f.sy - (u.ag_dim >> 1);
-            u.ag_bmp = a.base + a.hdr->dense_off[MG_SPR_AGENT0 + f.srot];
-        } else if (M == 4) {
-            int slot = f.exit_open ? MG_SPR_EXIT_OPEN : MG_SPR_EXIT_CLOSED;
-            const MgSprite sp = a.hdr->sprite[slot];
-            u.ex_w = sp.w;
-            u.ex_h = sp.h;
-            u.ex_x0 = f.exit_x - (sp.w >> 1);
-            u.ex_y0 = f.exit_y - (sp.h >> 1);
-            u.ex_bmp = a.base + a.hdr->dense_off[slot];
-        } else if (M == 3) {
-            const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
-            u.co_w = sp.w;
-            u.co_h = sp.h;
-            u.n_coins = f.n_coins;
-            u.co_bmp = a.base + a.hdr->dense_off[MG_SPR_COIN];
-        } else if (M == 2) {
-            u.bar_below = 1;
-        }
-    }
-    return u;
-}
-
-MG_HD uint32_t mg_pal(const MgAssetView& a, uint8_t pi) {
-    const uint8_t* c = a.palette[pi];
-    return (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
-}
-
-// colour of what lies UNDER the spotlight layer at (x, y): agent over exit over coins over the background
-MG_HD uint32_t mg_ss_under(const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f, const MgSSUnder& u, int x,
-                           int y) {
-    if (u.bar_below && y < 4) return mg_ss_bar(k, f, x);
-    unsigned du = (unsigned)(x - u.ag_x0), dv = (unsigned)(y - u.ag_y0);
-    if (du < (unsigned)u.ag_dim && dv < (unsigned)u.ag_dim) {
-        uint8_t pi = u.ag_bmp[dv * u.ag_dim + du];
-        if (pi != 255) return mg_pal(a, pi);
-    }
-    du = (unsigned)(x - u.ex_x0), dv = (unsigned)(y - u.ex_y0);
-    if (du < (unsigned)u.ex_w && dv < (unsigned)u.ex_h) {
-        uint8_t pi = u.ex_bmp[dv * u.ex_w + du];
-        if (pi != 255) return mg_pal(a, pi);
-    }
-    for (int c = u.n_coins - 1; c >= 0; --c) {  // coins are drawn in list order: the last one covering the pixel wins
-        du = (unsigned)(x - (f.coins[c][0] - (u.co_w >> 1))), dv = (unsigned)(y - (f.coins[c][1] - (u.co_h >> 1)));
-        if (du < (unsigned)u.co_w && dv < (unsigned)u.co_h) {
-            uint8_t pi = u.co_bmp[dv * u.co_w + du];
-            if (pi != 255) return mg_pal(a, pi);
-        }
-    }
-    return mg_ss_bg(u.bg_kind, x, y);
-}
-
 MG_HD uint32_t mg_ss_dim(uint32_t c, uint32_t A) {
     uint32_t r = c & 255u, g = (c >> 8) & 255u, b = (c >> 16) & 255u;
     r -= r * A / 255u;  // SDL: d + trunc((0 - d) * A / 255)
@@ -354,10 +283,85 @@ MG_HD void mg_put_px(uint8_t* buf, int x, int y, uint32_t col) {
     o[2] = (uint8_t)(col >> 16);
 }
 
-// kind 0: under() dimmed by alpha, 1: under() undimmed, 2: over() where present — over a clipped rectangle
+// is (x, y) inside one of the spotlight discs drawn this step?
+MG_HD bool mg_ss_lit(const int8_t* rows, const MgSSFrame& f, int x, int y) {
+    for (int d = 0; d < (int)f.n_discs; ++d)
+        if (mg_disc_has(rows, f.disc_r[d], f.disc_x[d], f.disc_y[d], x, y)) return true;
+    return false;
+}
+
+// background colours of this frame (white tile, coloured tile), optionally dimmed by the spotlight layer's alpha
+MG_HD void mg_ss_bg_colours(int kind, int alpha, uint32_t& c_even, uint32_t& c_odd) {
+    c_even = kind == 3 ? 0u : 0x00FFFFFFu;
+    c_odd = kind == 0 ? 0x00FF0000u : (kind == 1 ? 0x000000FFu : c_even);
+    if (alpha > 0) {
+        c_even = mg_ss_dim(c_even, (uint32_t)alpha);
+        c_odd = mg_ss_dim(c_odd, (uint32_t)alpha);
+    }
+}
+
+// one column run [ylo, yhi] of the tiled background (get_tiled_background_surface, pygame_assets.py:222-239:
+// 12-px tiles, the even ones white): contiguous bytes of the [x][y][c] frame
+MG_HD void mg_ss_bg_run(uint8_t* buf, int x, int ylo, int yhi, uint32_t c_even, uint32_t c_odd) {
+    unsigned ty = (unsigned)ylo / 12u, rem = (unsigned)ylo - ty * 12u;
+    unsigned par = ((unsigned)x / 12u + ty) & 1u;
+    uint8_t* o = buf + x * MG_COL_BYTES + ylo * 3;
+    for (int y = ylo; y <= yhi; ++y) {
+        uint32_t c = par ? c_odd : c_even;
+        o[0] = (uint8_t)c;
+        o[1] = (uint8_t)(c >> 8);
+        o[2] = (uint8_t)(c >> 16);
+        o += 3;
+        if (++rem == 12u) {
+            rem = 0;
+            par ^= 1u;
+        }
+    }
+}
+
+// background inside one spotlight disc (clipped), two lanes per column
 template <class Ctx>
-MG_HD void mg_ss_rect(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
-                      const MgSSUnder& u, int spot_li, int kind, int x0, int y0, int w, int h) {
+MG_HD void mg_ss_disc_bg(Ctx& c, uint8_t* buf, const MgAssetView& a, int x0, int y0, int r, uint32_t c_even,
+                         uint32_t c_odd) {
+    if (r < 1) return;
+    const int8_t* cols = (const int8_t*)(a.base + a.hdr->disc_off) + 2 * MG_MAX_DISC_R * (MG_MAX_DISC_R + 1) +
+                         2 * r * (r - 1);
+    int xa = x0 - r < 0 ? 0 : x0 - r, xb = x0 + r > MG_W ? MG_W : x0 + r;
+    for (int unit = c.lane; unit < 2 * (xb - xa); unit += c.nl) {
+        int x = xa + (unit >> 1), ci = x - x0 + r;
+        int ylo = y0 + (int)cols[2 * ci], yhi = y0 + (int)cols[2 * ci + 1];
+        if (ylo < 0) ylo = 0;
+        if (yhi > MG_W - 1) yhi = MG_W - 1;
+        if (ylo > yhi) continue;
+        int mid = (ylo + yhi + 1) >> 1;
+        if (unit & 1)
+            ylo = mid;
+        else
+            yhi = mid - 1;
+        if (ylo <= yhi) mg_ss_bg_run(buf, x, ylo, yhi, c_even, c_odd);
+    }
+}
+
+// colour-key blit of a sparse sprite UNDER the spotlight layer: lit pixels keep their colour, the others are dimmed
+template <class Ctx>
+MG_HD void mg_ss_sprite_under(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSFrame& f, int slot, int ax, int ay) {
+    const MgSprite sp = a.hdr->sprite[slot];
+    const uint32_t* e = a.entries + sp.first;
+    const int8_t* rows = (const int8_t*)(a.base + a.hdr->disc_off);
+    for (int i = c.lane; i < (int)sp.count; i += c.nl) {
+        uint32_t v = e[i];
+        int x = ax + (int)(v & 255u), y = ay + (int)((v >> 8) & 255u);
+        if ((unsigned)x >= (unsigned)MG_W || (unsigned)y >= (unsigned)MG_W) continue;
+        uint32_t col = mg_pal(a, (uint8_t)((v >> 16) & 255u));
+        if (f.alpha != 0 && !mg_ss_lit(rows, f, x, y)) col = mg_ss_dim(col, f.alpha);
+        mg_put_px(buf, x, y, col);
+    }
+}
+
+// over() where present, over a clipped rectangle (layers above the spotlight layer)
+template <class Ctx>
+MG_HD void mg_ss_rect_over(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+                           int spot_li, int x0, int y0, int w, int h) {
     int xa = x0 < 0 ? 0 : x0, ya = y0 < 0 ? 0 : y0;
     int xb = x0 + w > MG_W ? MG_W : x0 + w, yb = y0 + h > MG_W ? MG_W : y0 + h;
     if (xb <= xa || yb <= ya) return;
@@ -367,35 +371,7 @@ MG_HD void mg_ss_rect(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDraw
         int q = (int)(((uint64_t)i * inv) >> 24);
         int x = xa + q, y = ya + (i - q * rows);
         uint32_t col;
-        if (kind == 2) {
-            if (!mg_ss_over(a, k, f, spot_li, x, y, col)) continue;
-        } else {
-            col = mg_ss_under(a, k, f, u, x, y);
-            if (kind == 0) col = mg_ss_dim(col, f.alpha);
-        }
-        mg_put_px(buf, x, y, col);
-    }
-}
-
-// the pixels of one spotlight disc (clipped to the screen), column by column — a column of the frame is
-// contiguous memory: undimmed under()
-template <class Ctx>
-MG_HD void mg_ss_disc(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
-                      const MgSSUnder& u, int x0, int y0, int r) {
-    if (r < 1) return;
-    const int8_t* cols = (const int8_t*)(a.base + a.hdr->disc_off) + 2 * MG_MAX_DISC_R * (MG_MAX_DISC_R + 1) +
-                         2 * r * (r - 1);
-    int xa = x0 - r < 0 ? 0 : x0 - r, xb = x0 + r > MG_W ? MG_W : x0 + r;  // [xa, xb) x [ya, yb): box on screen
-    int ya = y0 - r < 0 ? 0 : y0 - r, yb = y0 + r > MG_W ? MG_W : y0 + r;
-    if (xb <= xa || yb <= ya) return;
-    const int rows = yb - ya, total = (xb - xa) * rows;
-    const uint64_t inv = ((1ull << 24) + (uint64_t)rows - 1) / (uint64_t)rows;
-    for (int i = c.lane; i < total; i += c.nl) {
-        int q = (int)(((uint64_t)i * inv) >> 24);
-        int x = xa + q, y = ya + (i - q * rows);
-        int ci = x - x0 + r, dy = y - y0;
-        if (dy < (int)cols[2 * ci] || dy > (int)cols[2 * ci + 1]) continue;
-        mg_put_px(buf, x, y, mg_ss_under(a, k, f, u, x, y));
+        if (mg_ss_over(a, k, f, spot_li, x, y, col)) mg_put_px(buf, x, y, col);
     }
 }
 
@@ -404,36 +380,61 @@ MG_HD void mg_ss_compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSD
     int spot_li = 1;
     for (int li = 0; li < k.n_layers; ++li)
         if (k.layers[li] == 1) spot_li = li;
-    const MgSSUnder u = mg_ss_scene(a, k, f, spot_li);
-    // 1. everything the spotlight layer dims: black when the lights are fully off, else under() scaled by alpha
+    uint32_t c_even, c_odd;
+    // 1. the background as the spotlight layer leaves it outside the discs: black when the lights are fully off,
+    //    else the tiled background scaled by alpha (alpha 0: unchanged)
     if (f.alpha == 255) {
         MgVec16* w = reinterpret_cast<MgVec16*>(buf);
         const MgVec16 z = {0u, 0u, 0u, 0u};
         for (int i = c.lane; i < MG_FRAME_VEC16; i += c.nl) w[i] = z;
     } else {
-        mg_ss_rect(c, buf, a, k, f, u, spot_li, f.alpha == 0 ? 1 : 0, 0, 0, MG_W, MG_W);
+        mg_ss_bg_colours(f.bg_kind, f.alpha, c_even, c_odd);
+        for (int unit = c.lane; unit < 2 * MG_W; unit += c.nl)
+            mg_ss_bg_run(buf, unit >> 1, (unit & 1) ? MG_W / 2 : 0, (unit & 1) ? MG_W - 1 : MG_W / 2 - 1, c_even, c_odd);
     }
     c.sync();
-    // 2. inside the colour-keyed discs the layers underneath show through unchanged
-    if (f.alpha != 0)
-        for (int d = 0; d < (int)f.n_discs; ++d) mg_ss_disc(c, buf, a, k, f, u, f.disc_x[d], f.disc_y[d], f.disc_r[d]);
-    c.sync();
-    // 3. layers above the spotlight layer, in painter's order (overlaps resolved per pixel by mg_ss_over)
+    // 2. inside the colour-keyed discs the background shows through unchanged
+    if (f.alpha != 0) {
+        mg_ss_bg_colours(f.bg_kind, 0, c_even, c_odd);
+        for (int d = 0; d < (int)f.n_discs; ++d) mg_ss_disc_bg(c, buf, a, f.disc_x[d], f.disc_y[d], f.disc_r[d], c_even, c_odd);
+        c.sync();
+    }
+    // 3. coins, exit, agent below the spotlight layer, in painter's order (dimmed outside the discs)
+    for (int lj = 1; lj < spot_li; ++lj) {
+        int M = k.layers[lj];
+        if (M == 3) {
+            const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
+            for (int q = 0; q < (int)f.n_coins; ++q) {
+                mg_ss_sprite_under(c, buf, a, f, MG_SPR_COIN, f.coins[q][0] - (sp.w >> 1), f.coins[q][1] - (sp.h >> 1));
+                c.sync();
+            }
+        } else if (M == 4) {
+            int slot = f.exit_open ? MG_SPR_EXIT_OPEN : MG_SPR_EXIT_CLOSED;
+            const MgSprite sp = a.hdr->sprite[slot];
+            mg_ss_sprite_under(c, buf, a, f, slot, f.exit_x - (sp.w >> 1), f.exit_y - (sp.h >> 1));
+            c.sync();
+        } else if (M == 5) {
+            int half = a.hdr->agent_dim >> 1;
+            mg_ss_sprite_under(c, buf, a, f, MG_SPR_AGENT0 + f.srot, f.sx - half, f.sy - half);
+            c.sync();
+        }
+    }
+    // 4. layers above the spotlight layer (overlaps resolved per pixel by mg_ss_over)
     for (int li = spot_li + 1; li < k.n_layers; ++li) {
         int L = k.layers[li];
         if (L == 2) {
-            mg_ss_rect(c, buf, a, k, f, u, spot_li, 2, 0, 0, MG_W, 4);
+            mg_ss_rect_over(c, buf, a, k, f, spot_li, 0, 0, MG_W, 4);
         } else if (L == 5) {
             int dim = a.hdr->agent_dim;
-            mg_ss_rect(c, buf, a, k, f, u, spot_li, 2, f.sx - (dim >> 1), f.sy - (dim >> 1), dim, dim);
+            mg_ss_rect_over(c, buf, a, k, f, spot_li, f.sx - (dim >> 1), f.sy - (dim >> 1), dim, dim);
         } else if (L == 4) {
             const MgSprite sp = a.hdr->sprite[MG_SPR_EXIT_OPEN];
-            mg_ss_rect(c, buf, a, k, f, u, spot_li, 2, f.exit_x - (sp.w >> 1), f.exit_y - (sp.h >> 1), sp.w, sp.h);
+            mg_ss_rect_over(c, buf, a, k, f, spot_li, f.exit_x - (sp.w >> 1), f.exit_y - (sp.h >> 1), sp.w, sp.h);
         } else if (L == 3) {
             const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
             for (int q = 0; q < (int)f.n_coins; ++q)
-                mg_ss_rect(c, buf, a, k, f, u, spot_li, 2, f.coins[q][0] - (sp.w >> 1), f.coins[q][1] - (sp.h >> 1), sp.w,
-                           sp.h);
+                mg_ss_rect_over(c, buf, a, k, f, spot_li, f.coins[q][0] - (sp.w >> 1), f.coins[q][1] - (sp.h >> 1), sp.w,
+                                sp.h);
         }
     }
 }

@@ -65,12 +65,15 @@ MG_HD void mg_ss_block(MgSSSampler& g, int x, int y, int r) {
         while ((h + 1) * (h + 1) <= rem) ++h;
         int xa = x - h < 0 ? 0 : x - h, xb = x + h > MG_W - 1 ? MG_W - 1 : x + h;
         if (xa > xb) continue;
+        // bits xa..xb of the 128-bit row mask
         uint64_t mlo = 0, mhi = 0;
-        for (int c = xa; c <= xb; ++c) {
-            if (c < 64)
-                mlo |= 1ull << c;
-            else
-                mhi |= 1ull << (c - 64);
+        if (xa < 64) {
+            int b = xb < 63 ? xb : 63;
+            mlo = (~0ull >> (63 - (b - xa))) << xa;
+        }
+        if (xb >= 64) {
+            int a2 = xa > 64 ? xa - 64 : 0, b2 = xb - 64;
+            mhi = (~0ull >> (63 - (b2 - a2))) << a2;
         }
         int before = mg_popc64(g.lo[yy]) + mg_popc64(g.hi[yy]);
         g.lo[yy] |= mlo;
