@@ -27,6 +27,7 @@ struct Builder {
     std::vector<int8_t> discs;                 // filled-circle row spans, then column spans (SS spotlights)
     bool discs_ok = true;
     std::vector<double> trig;                  // (cos, sin) of integer degrees
+    std::vector<uint8_t> rings;                // uint16 start[R + 2] + int8 (dx, dy) pairs of the width-1 circles
     int n_pal = 0;
 
     Builder() {
@@ -136,6 +137,29 @@ struct Builder {
         }
     }
 
+    // pygame.draw.circle(width=1) pixel sets (Spotlight border when black_background, pygame_assets.py:112-113)
+    void add_ring_tables() {
+        std::vector<uint16_t> start(MG_MAX_DISC_R + 2, 0);
+        std::vector<int8_t> px;
+        for (int r = 1; r <= MG_MAX_DISC_R; ++r) {
+            start[r] = (uint16_t)(px.size() / 2);
+            Surface s(2 * r + 4, 2 * r + 4);
+            int c = r + 2;
+            mgr::circle(s, 1, c, c, r, 1, false);
+            for (int x = 0; x < s.w; ++x)
+                for (int y = 0; y < s.h; ++y)
+                    if (s.at(x, y)) {
+                        px.push_back((int8_t)(x - c));
+                        px.push_back((int8_t)(y - c));
+                    }
+        }
+        start[MG_MAX_DISC_R + 1] = (uint16_t)(px.size() / 2);
+        start[0] = start[1];
+        rings.resize(start.size() * 2 + px.size());
+        memcpy(rings.data(), start.data(), start.size() * 2);
+        memcpy(rings.data() + start.size() * 2, px.data(), px.size());
+    }
+
     // pygame Vector2.rotate for integer degrees: exact quarter turns, else libm sin/cos of angle * pi / 180
     void add_trig_table() {
         trig.resize(720);
@@ -181,6 +205,12 @@ struct Builder {
             hdr.disc_off = (uint32_t)off;
             off += discs.size();
         }
+        hdr.ring_off = 0;
+        if (!rings.empty()) {
+            off = (off + 3) & ~(size_t)3;
+            hdr.ring_off = (uint32_t)off;
+            off += rings.size();
+        }
         hdr.trig_off = 0;
         if (!trig.empty()) {
             off = (off + 7) & ~(size_t)7;
@@ -203,6 +233,7 @@ struct Builder {
         for (int i = 0; i < MG_SPR_COUNT; ++i)
             if (hdr.dense_off[i]) memcpy((char*)out + hdr.dense_off[i], dense[i].data(), dense[i].size());
         if (hdr.disc_off) memcpy((char*)out + hdr.disc_off, discs.data(), discs.size());
+        if (hdr.ring_off) memcpy((char*)out + hdr.ring_off, rings.data(), rings.size());
         if (hdr.trig_off) memcpy((char*)out + hdr.trig_off, trig.data(), trig.size() * sizeof(double));
         for (size_t i = 0; i < templates.size() && i < 4; ++i)
             if (!templates[i].empty()) memcpy((char*)out + hdr.tmpl_off[i], templates[i].data(), MG_FRAME_BYTES);
@@ -377,6 +408,7 @@ extern "C" long mg_ss_build_assets(const mg_ss_params* p, void* host_out, size_t
     b.add_disc_tables();
     if (!b.discs_ok) return MG_EINVAL;
     b.add_trig_table();
+    if (p->black_background) b.add_ring_tables();
     Surface black(MG_W, MG_W);
     b.add_template(0, black);
     return b.serialize(host_out, capacity);

@@ -82,7 +82,8 @@ struct MgAssetHeader {
                            // dy = -r..r-1 of (xmin, xmax) relative to the centre, starting at row r*(r-1)
     uint32_t trig_off;     // byte offset of double[360][2] = (cos, sin) of integer degrees (host libm)
     uint32_t stage_bytes;  // bytes [0, stage_bytes) = header + sprite lists + dense bitmaps + tables (no templates)
-    uint32_t reserved;
+    uint32_t ring_off;     // byte offset of the 1-px circle outlines (pygame draw.circle width=1): uint16 start[MG_MAX_DISC_R + 2]
+                           // (in pixel pairs), then int8 (dx, dy) pairs; 0 = absent
     MgSprite sprite[MG_SPR_COUNT];
     uint32_t dense_off[MG_SPR_COUNT];  // byte offset of a dense w*h palette-index bitmap (255 = transparent), 0 = none
     uint8_t palette[MG_MAX_PALETTE][4];

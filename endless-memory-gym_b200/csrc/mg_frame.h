@@ -184,6 +184,7 @@ struct MgSSDrawK {
     int cb_x, cb_w;
     int show_last_action;
     int has_coin_layer;   // coin_surface is None when num_coins == 0
+    int border;           // black_background: every spotlight gets a white 1-px outline (Spotlight.has_border)
 };
 
 MG_HD bool mg_disc_has(const int8_t* discs, int r, int x0, int y0, int x, int y) {
@@ -418,6 +419,38 @@ MG_HD void mg_ss_compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSD
             mg_ss_sprite_under(c, buf, a, f, MG_SPR_AGENT0 + f.srot, f.sx - half, f.sy - half);
             c.sync();
         }
+    }
+    // 3b. black_background: white 1-px outlines on the spotlight surface (pygame_assets.py:112-113). An outline
+    //     pixel survives unless a LATER spotlight's disc is drawn over it; it is blended like any non-key pixel:
+    //     d + trunc((255 - d) * A / 255) over what lies underneath.
+    if (k.border && f.alpha != 0 && a.hdr->ring_off) {
+        const uint16_t* start = (const uint16_t*)(a.base + a.hdr->ring_off);
+        const int8_t* ring = (const int8_t*)(start + MG_MAX_DISC_R + 2);
+        const int8_t* rows = (const int8_t*)(a.base + a.hdr->disc_off);
+        for (int d = 0; d < (int)f.n_discs; ++d) {
+            int r = f.disc_r[d], n = (int)start[r + 1] - (int)start[r];
+            const int8_t* px = ring + 2 * (int)start[r];
+            for (int i = c.lane; i < n; i += c.nl) {
+                int x = f.disc_x[d] + (int)px[2 * i], y = f.disc_y[d] + (int)px[2 * i + 1];
+                if ((unsigned)x >= (unsigned)MG_W || (unsigned)y >= (unsigned)MG_W) continue;
+                bool covered = false;
+                for (int e = d + 1; e < (int)f.n_discs && !covered; ++e)
+                    covered = mg_disc_has(rows, f.disc_r[e], f.disc_x[e], f.disc_y[e], x, y);
+                if (covered) continue;
+                uint32_t under = mg_ss_bg(f.bg_kind, x, y), col;
+                for (int lj = spot_li - 1; lj > 0; --lj)
+                    if (mg_ss_layer_at(a, f, k.layers[lj], x, y, col)) {
+                        under = col;
+                        break;
+                    }
+                uint32_t A = f.alpha, cr = under & 255u, cg = (under >> 8) & 255u, cb = (under >> 16) & 255u;
+                cr += (255u - cr) * A / 255u;
+                cg += (255u - cg) * A / 255u;
+                cb += (255u - cb) * A / 255u;
+                mg_put_px(buf, x, y, cr | (cg << 8) | (cb << 16));
+            }
+        }
+        c.sync();
     }
     // 4. layers above the spotlight layer (overlaps resolved per pixel by mg_ss_over)
     for (int li = spot_li + 1; li < k.n_layers; ++li) {

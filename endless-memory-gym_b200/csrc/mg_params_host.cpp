@@ -143,10 +143,6 @@ extern "C" int mg_ss_check_params(const mg_ss_params* p) {
         mg_set_err("use_exit=False is not supported (the reference raises AttributeError)");
         return MG_EINVAL;
     }
-    if (p->black_background) {
-        mg_set_err("black_background=True (spotlight borders) is not built yet");
-        return MG_EINVAL;
-    }
     if (!check_list(p->num_coins, 1, MG_SS_MAXCOINS, "num_coins")) return MG_EINVAL;  // 0 coins: ZeroDivisionError at done (:553)
     if (!(p->agent_health > 0.0)) {
         mg_set_err("agent_health must be > 0");

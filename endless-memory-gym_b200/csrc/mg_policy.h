@@ -158,6 +158,7 @@ struct SSPolicy {
         d.cb_w = k.cb_w;
         d.show_last_action = k.p.show_last_action;
         d.has_coin_layer = 1;
+        d.border = k.p.black_background;
         mg_ss_compose(c, buf, a, d, f);
     }
     // every frame rewrites the whole buffer: nothing to undo

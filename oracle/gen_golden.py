@@ -45,6 +45,10 @@ CASES = {
                                           "light_dim_off_duration": 10, "coins_visible": True,
                                           "reward_inside_spotlight": -0.01, "reward_coin": 0.5,
                                           "agent_speed": 4.0}, 4, 450),
+    "ss_black": ("SearingSpotlights-v0", {"max_steps": 150, "black_background": True, "agent_visible": True,
+                                           "exit_visible": True, "light_threshold": 140, "light_dim_off_duration": 4,
+                                           "initial_spawns": 6, "spot_min_speed": 0.008, "spot_max_speed": 0.02,
+                                           "show_last_action": False, "num_coins": [2]}, 4, 320),
 }
 
 

@@ -10,7 +10,7 @@ from replay_util import replay_golden_batched, replay_golden_single, rollout_vs_
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts"]
+CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts", "ss_black"]
 
 
 @pytest.mark.parametrize("name", CASES)

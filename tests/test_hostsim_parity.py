@@ -7,7 +7,7 @@ import pytest
 from hostsim_util import HostSimBackend
 from replay_util import replay_golden_batched, replay_golden_single, rollout_vs_oracle
 
-CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts"]
+CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts", "ss_black"]
 
 
 @pytest.fixture(scope="module")

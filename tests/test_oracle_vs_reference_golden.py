@@ -6,7 +6,7 @@ import pytest
 from oracle import memgym_oracle as O
 from golden_util import action_for, crc, load_case
 
-CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts"]
+CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts", "ss_black"]
 
 
 @pytest.mark.parametrize("name", CASES)
