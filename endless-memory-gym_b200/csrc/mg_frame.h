@@ -376,50 +376,220 @@ MG_HD void mg_ss_rect_over(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgS
     }
 }
 
+// ---- base buffer + lit mask: the per-frame cost of Searing Spotlights is a masked 16-byte copy -----------------
+// Per warp: `base` = the scene UNDER the spotlight layer, undimmed (tiled background + coins/exit/agent that sit
+// below the layer), kept across frames and patched only where the scene changed; `lit` = 84 columns x 96 bits,
+// bit y of column x set iff a spotlight disc drawn this step covers (x, y). The frame is then
+// out[chunk] = lit ? base : dim(base), 16 bytes at a time, through two small per-CTA tables.
+#define MG_SS_CHUNKS MG_FRAME_VEC16  // 1323 16-byte chunks per frame
+
+struct MgSSBaseDesc {  // what `base` currently shows
+    int32_t valid;
+    int32_t lut_alpha;  // alpha the dim LUT was built for (-1: none)
+    int16_t sx, sy, exit_x, exit_y;
+    uint8_t srot, bg_kind, exit_open, n_coins;
+    int16_t coins[MG_SS_MAXCOINS][2];
+};
+
+struct MgSSWarpMem {
+    uint8_t base[21248];
+    uint32_t lit[MG_W * 3 + 4];
+    uint8_t dimlut[256];
+    MgSSBaseDesc desc;
+};
+
+struct MgSSCtaTables {
+    uint32_t chunk[MG_SS_CHUNKS + 1];  // x | y0 << 8 | phase << 16 of the first pixel a chunk touches
+    MgVec16 mask[3][64];               // byte mask of a chunk for (phase, 6 lit bits)
+};
+
+MG_HD void mg_ss_tables_init(MgSSCtaTables* t, int tid, int nthreads) {
+    for (int c = tid; c < MG_SS_CHUNKS; c += nthreads) {
+        int byte0 = 16 * c, p0 = byte0 / 3, phase = byte0 - 3 * p0;
+        t->chunk[c] = (uint32_t)(p0 / MG_W) | ((uint32_t)(p0 % MG_W) << 8) | ((uint32_t)phase << 16);
+    }
+    for (int i = tid; i < 3 * 64; i += nthreads) {
+        int phase = i / 64, bits = i % 64;
+        uint8_t m[16];
+        for (int j = 0; j < 16; ++j) m[j] = ((bits >> ((j + phase) / 3)) & 1) ? 0xFF : 0x00;
+        uint32_t w[4];
+        for (int q = 0; q < 4; ++q)
+            w[q] = (uint32_t)m[4 * q] | ((uint32_t)m[4 * q + 1] << 8) | ((uint32_t)m[4 * q + 2] << 16) |
+                   ((uint32_t)m[4 * q + 3] << 24);
+        MgVec16 v = {w[0], w[1], w[2], w[3]};
+        t->mask[phase][bits] = v;
+    }
+}
+
+// colour under the spotlight layer at (x, y) IGNORING the agent: exit over coins over the background
+MG_HD uint32_t mg_ss_under_no_agent(const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f, int spot_li, int x, int y) {
+    uint32_t col;
+    for (int lj = spot_li - 1; lj > 0; --lj) {
+        int M = k.layers[lj];
+        if (M == 5 || M == 2) continue;
+        if (mg_ss_layer_at(a, f, M, x, y, col)) return col;
+    }
+    return mg_ss_bg(f.bg_kind, x, y);
+}
+
+MG_HD bool mg_ss_layer_below(const MgSSDrawK& k, int spot_li, int layer) {
+    for (int lj = 1; lj < spot_li; ++lj)
+        if (k.layers[lj] == layer) return true;
+    return false;
+}
+
+// bring `base` up to date with frame f (full rebuild, or just move the agent)
 template <class Ctx>
-MG_HD void mg_ss_compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f) {
+MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+                             int spot_li) {
+    uint8_t* base = wm->base;
+    const MgSSBaseDesc d = wm->desc;
+    const bool agent_below = mg_ss_layer_below(k, spot_li, 5);
+    const int half = a.hdr->agent_dim >> 1;
+    bool same_rest = d.valid && d.bg_kind == f.bg_kind && d.exit_x == f.exit_x && d.exit_y == f.exit_y &&
+                     d.exit_open == f.exit_open && d.n_coins == f.n_coins;
+    for (int q = 0; same_rest && q < (int)f.n_coins; ++q)
+        same_rest = d.coins[q][0] == f.coins[q][0] && d.coins[q][1] == f.coins[q][1];
+    const bool same_agent = !agent_below || (d.sx == f.sx && d.sy == f.sy && d.srot == f.srot);
+    if (same_rest && same_agent) return;
+    if (same_rest) {
+        // only the agent moved: put back what it covered, then draw it at its new pose
+        const MgSprite sp = a.hdr->sprite[MG_SPR_AGENT0 + d.srot];
+        const uint32_t* e = a.entries + sp.first;
+        for (int i = c.lane; i < (int)sp.count; i += c.nl) {
+            uint32_t v = e[i];
+            int x = d.sx - half + (int)(v & 255u), y = d.sy - half + (int)((v >> 8) & 255u);
+            if ((unsigned)x < (unsigned)MG_W && (unsigned)y < (unsigned)MG_W)
+                mg_put_px(base, x, y, mg_ss_under_no_agent(a, k, f, spot_li, x, y));
+        }
+        c.sync();
+    } else {
+        uint32_t c_even, c_odd;
+        mg_ss_bg_colours(f.bg_kind, 0, c_even, c_odd);
+        for (int unit = c.lane; unit < 2 * MG_W; unit += c.nl)
+            mg_ss_bg_run(base, unit >> 1, (unit & 1) ? MG_W / 2 : 0, (unit & 1) ? MG_W - 1 : MG_W / 2 - 1, c_even, c_odd);
+        c.sync();
+        for (int lj = 1; lj < spot_li; ++lj) {  // coins, then exit (painter's order); the agent follows below
+            int M = k.layers[lj];
+            if (M == 3) {
+                const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
+                for (int q = 0; q < (int)f.n_coins; ++q) {
+                    mg_sprite_draw(c, base, a, MG_SPR_COIN, f.coins[q][0] - (sp.w >> 1), f.coins[q][1] - (sp.h >> 1));
+                    c.sync();
+                }
+            } else if (M == 4) {
+                int slot = f.exit_open ? MG_SPR_EXIT_OPEN : MG_SPR_EXIT_CLOSED;
+                const MgSprite sp = a.hdr->sprite[slot];
+                mg_sprite_draw(c, base, a, slot, f.exit_x - (sp.w >> 1), f.exit_y - (sp.h >> 1));
+                c.sync();
+            }
+        }
+    }
+    if (agent_below) {
+        mg_sprite_draw(c, base, a, MG_SPR_AGENT0 + f.srot, f.sx - half, f.sy - half);
+        c.sync();
+    }
+    if (c.lane == 0) {
+        MgSSBaseDesc& w = wm->desc;
+        w.valid = 1;
+        w.sx = f.sx, w.sy = f.sy, w.srot = f.srot;
+        w.bg_kind = f.bg_kind;
+        w.exit_x = f.exit_x, w.exit_y = f.exit_y, w.exit_open = f.exit_open;
+        w.n_coins = f.n_coins;
+        for (int q = 0; q < (int)f.n_coins; ++q) w.coins[q][0] = f.coins[q][0], w.coins[q][1] = f.coins[q][1];
+    }
+    c.sync();
+}
+
+// lit[x] = union over the discs of their column runs; every lane owns whole columns (no write conflicts)
+template <class Ctx>
+MG_HD void mg_ss_build_lit(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const MgSSFrame& f) {
+    const int8_t* cols_all = (const int8_t*)(a.base + a.hdr->disc_off) + 2 * MG_MAX_DISC_R * (MG_MAX_DISC_R + 1);
+    for (int x = c.lane; x < MG_W; x += c.nl) {
+        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        for (int d = 0; d < (int)f.n_discs; ++d) {
+            int r = f.disc_r[d], ci = x - (int)f.disc_x[d] + r;
+            if (r < 1 || (unsigned)ci >= (unsigned)(2 * r)) continue;
+            const int8_t* cols = cols_all + 2 * r * (r - 1);
+            int ylo = (int)f.disc_y[d] + (int)cols[2 * ci], yhi = (int)f.disc_y[d] + (int)cols[2 * ci + 1];
+            if (ylo < 0) ylo = 0;
+            if (yhi > MG_W - 1) yhi = MG_W - 1;
+            if (ylo > yhi) continue;
+            // bits ylo..yhi of a 96-bit value
+            for (int wi = 0; wi < 3; ++wi) {
+                int lo = ylo - 32 * wi, hi = yhi - 32 * wi;
+                if (hi < 0 || lo > 31) continue;
+                if (lo < 0) lo = 0;
+                if (hi > 31) hi = 31;
+                uint32_t m = (0xFFFFFFFFu >> (31 - (hi - lo))) << lo;
+                if (wi == 0)
+                    w0 |= m;
+                else if (wi == 1)
+                    w1 |= m;
+                else
+                    w2 |= m;
+            }
+        }
+        wm->lit[3 * x] = w0;
+        wm->lit[3 * x + 1] = w1;
+        wm->lit[3 * x + 2] = w2;
+    }
+    if (c.lane == 0) wm->lit[3 * MG_W] = wm->lit[3 * MG_W + 1] = wm->lit[3 * MG_W + 2] = 0;  // column 84: padding
+}
+
+// out = lit ? base : dim(base), 16 bytes at a time
+template <class Ctx>
+MG_HD void mg_ss_masked_copy(Ctx& c, uint8_t* out, const MgSSWarpMem* wm, const MgSSCtaTables* t, int alpha) {
+    const MgVec16* src = reinterpret_cast<const MgVec16*>(wm->base);
+    MgVec16* dst = reinterpret_cast<MgVec16*>(out);
+    if (alpha == 0) {
+        for (int i = c.lane; i < MG_SS_CHUNKS; i += c.nl) dst[i] = src[i];
+        return;
+    }
+    for (int i = c.lane; i < MG_SS_CHUNKS; i += c.nl) {
+        uint32_t dsc = t->chunk[i];
+        int x = (int)(dsc & 255u), y0 = (int)((dsc >> 8) & 255u), phase = (int)(dsc >> 16);
+        const uint32_t* L = wm->lit + 3 * x;
+        // 6 lit bits starting at row y0 of column x, continuing at row 0 of column x + 1
+        uint64_t lo = (uint64_t)L[0] | ((uint64_t)L[1] << 32);
+        uint64_t v = y0 < 32 ? (lo >> y0) : ((((uint64_t)L[1] | ((uint64_t)L[2] << 32))) >> (y0 - 32));
+        if (y0 + 6 > MG_W) v = (v & ((1ull << (MG_W - y0)) - 1ull)) | ((uint64_t)L[3] << (MG_W - y0));
+        MgVec16 m = t->mask[phase][(int)(v & 63ull)], b = src[i], o;
+        if (alpha == 255) {
+            o.x = b.x & m.x, o.y = b.y & m.y, o.z = b.z & m.z, o.w = b.w & m.w;
+        } else {
+            const uint8_t* lut = wm->dimlut;
+            uint32_t bw[4] = {b.x, b.y, b.z, b.w}, mw[4] = {m.x, m.y, m.z, m.w}, ow[4];
+            for (int q = 0; q < 4; ++q) {
+                uint32_t dm = (uint32_t)lut[bw[q] & 255u] | ((uint32_t)lut[(bw[q] >> 8) & 255u] << 8) |
+                              ((uint32_t)lut[(bw[q] >> 16) & 255u] << 16) | ((uint32_t)lut[bw[q] >> 24] << 24);
+                ow[q] = (bw[q] & mw[q]) | (dm & ~mw[q]);
+            }
+            o.x = ow[0], o.y = ow[1], o.z = ow[2], o.w = ow[3];
+        }
+        dst[i] = o;
+    }
+}
+
+template <class Ctx>
+MG_HD void mg_ss_compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+                         MgSSWarpMem* wm, const MgSSCtaTables* tables) {
     int spot_li = 1;
     for (int li = 0; li < k.n_layers; ++li)
         if (k.layers[li] == 1) spot_li = li;
-    uint32_t c_even, c_odd;
-    // 1. the background as the spotlight layer leaves it outside the discs: black when the lights are fully off,
-    //    else the tiled background scaled by alpha (alpha 0: unchanged)
-    if (f.alpha == 255) {
-        MgVec16* w = reinterpret_cast<MgVec16*>(buf);
-        const MgVec16 z = {0u, 0u, 0u, 0u};
-        for (int i = c.lane; i < MG_FRAME_VEC16; i += c.nl) w[i] = z;
-    } else {
-        mg_ss_bg_colours(f.bg_kind, f.alpha, c_even, c_odd);
-        for (int unit = c.lane; unit < 2 * MG_W; unit += c.nl)
-            mg_ss_bg_run(buf, unit >> 1, (unit & 1) ? MG_W / 2 : 0, (unit & 1) ? MG_W - 1 : MG_W / 2 - 1, c_even, c_odd);
+    // 1. the scene under the spotlight layer (kept across frames, patched where it changed)
+    mg_ss_update_base(c, wm, a, k, f, spot_li);
+    // 2. which pixels the colour-keyed discs leave untouched, and the dimming of the others
+    if (f.alpha != 0) mg_ss_build_lit(c, wm, a, f);
+    if (f.alpha != 0 && f.alpha != 255 && wm->desc.lut_alpha != (int)f.alpha) {
+        for (int v = c.lane; v < 256; v += c.nl) wm->dimlut[v] = (uint8_t)((uint32_t)v - (uint32_t)v * f.alpha / 255u);
+        c.sync();
+        if (c.lane == 0) wm->desc.lut_alpha = f.alpha;
     }
     c.sync();
-    // 2. inside the colour-keyed discs the background shows through unchanged
-    if (f.alpha != 0) {
-        mg_ss_bg_colours(f.bg_kind, 0, c_even, c_odd);
-        for (int d = 0; d < (int)f.n_discs; ++d) mg_ss_disc_bg(c, buf, a, f.disc_x[d], f.disc_y[d], f.disc_r[d], c_even, c_odd);
-        c.sync();
-    }
-    // 3. coins, exit, agent below the spotlight layer, in painter's order (dimmed outside the discs)
-    for (int lj = 1; lj < spot_li; ++lj) {
-        int M = k.layers[lj];
-        if (M == 3) {
-            const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
-            for (int q = 0; q < (int)f.n_coins; ++q) {
-                mg_ss_sprite_under(c, buf, a, f, MG_SPR_COIN, f.coins[q][0] - (sp.w >> 1), f.coins[q][1] - (sp.h >> 1));
-                c.sync();
-            }
-        } else if (M == 4) {
-            int slot = f.exit_open ? MG_SPR_EXIT_OPEN : MG_SPR_EXIT_CLOSED;
-            const MgSprite sp = a.hdr->sprite[slot];
-            mg_ss_sprite_under(c, buf, a, f, slot, f.exit_x - (sp.w >> 1), f.exit_y - (sp.h >> 1));
-            c.sync();
-        } else if (M == 5) {
-            int half = a.hdr->agent_dim >> 1;
-            mg_ss_sprite_under(c, buf, a, f, MG_SPR_AGENT0 + f.srot, f.sx - half, f.sy - half);
-            c.sync();
-        }
-    }
+    // 3. frame = lit ? base : base dimmed by alpha (SDL: d + trunc((0 - d) * A / 255))
+    mg_ss_masked_copy(c, buf, wm, tables, f.alpha);
+    c.sync();
     // 3b. black_background: white 1-px outlines on the spotlight surface (pygame_assets.py:112-113). An outline
     //     pixel survives unless a LATER spotlight's disc is drawn over it; it is blended like any non-key pixel:
     //     d + trunc((255 - d) * A / 255) over what lies underneath.

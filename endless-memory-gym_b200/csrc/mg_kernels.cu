@@ -129,7 +129,10 @@ __global__ void __launch_bounds__(320, 1)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     uint8_t* buf = smem + (size_t)warp * MG_BUF_STRIDE;
     uint8_t* slot = smem + (size_t)nwarps * MG_BUF_STRIDE + (size_t)warp * kSlot;
-    uint8_t* stage = smem + (size_t)nwarps * (MG_BUF_STRIDE + kSlot);
+    uint8_t* wextra = smem + (size_t)nwarps * (MG_BUF_STRIDE + kSlot) + (size_t)warp * P::kWarpExtra;
+    uint8_t* cextra = smem + (size_t)nwarps * (MG_BUF_STRIDE + kSlot + P::kWarpExtra);
+    uint8_t* stage = cextra + P::kCtaExtra;
+    const MgScratch scratch{wextra, cextra};
     State* st = reinterpret_cast<State*>(slot);
     Frame* fr = reinterpret_cast<Frame*>(slot + kStateBytes);
     MgFrameJob* job = reinterpret_cast<MgFrameJob*>(slot + kStateBytes + 2 * sizeof(Frame));
@@ -152,13 +155,16 @@ __global__ void __launch_bounds__(320, 1)
         mg_bulk_load(buf, view.tmpl[0], MG_FRAME_BYTES, ctx.bar);
     }
     const int stage_words = (int)(view.hdr->stage_bytes / 4);
-    if (stage_words * 4 <= q.stage_cap) {  // header, sprite lists, bitmaps, tables -> shared memory: compose never waits on L2
+    const bool staged = stage_words * 4 <= q.stage_cap;
+    if (staged) {  // header, sprite lists, bitmaps, tables -> shared memory: compose never waits on L2
         const uint32_t* src = reinterpret_cast<const uint32_t*>(assets);
         uint32_t* dst = reinterpret_cast<uint32_t*>(stage);
         for (int i = threadIdx.x; i < stage_words; i += blockDim.x) dst[i] = src[i];
-        __syncthreads();
-        view = mg_asset_view2(stage, assets);
     }
+    P::cta_init(cextra, threadIdx.x, blockDim.x);
+    P::warp_init(wextra, lane);
+    __syncthreads();
+    if (staged) view = mg_asset_view2(stage, assets);
     if (tracing) tr1 = mg_now();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");  // previous kernel's state / obs writes are visible
@@ -233,10 +239,10 @@ __global__ void __launch_bounds__(320, 1)
                 if (pending) {
                     if (lane == 0) mg_bulk_wait_read();
                     __syncwarp();
-                    P::restore(ctx, buf, view, k, prev);
+                    P::restore(ctx, buf, view, k, prev, scratch);
                     __syncwarp();
                 }
-                P::compose(ctx, buf, view, k, f);
+                P::compose(ctx, buf, view, k, f, scratch);
                 mg_fence_proxy_async();  // make this lane's patch visible to the async (TMA) proxy
                 __syncwarp();
                 if (lane == 0) {
@@ -311,9 +317,9 @@ static int plan_launch(int n, int wpc_req, int default_wpc, bool balance, MgLaun
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     constexpr int kSlot =
         (((int)sizeof(typename P::State) + 2 * (int)sizeof(typename P::Frame) + (int)sizeof(MgFrameJob) + 16 + 127) / 128) * 128;
-    const int per_warp = MG_BUF_STRIDE + kSlot;
+    const int per_warp = MG_BUF_STRIDE + kSlot + P::kWarpExtra;
     int wmax = 10;
-    while (wmax > 1 && wmax * per_warp > smem_max) wmax--;
+    while (wmax > 1 && wmax * per_warp + P::kCtaExtra + 16 * 1024 > smem_max) wmax--;  // leave room to stage the assets
     int wpc = wpc_req ? wpc_req : default_wpc;
     if (wpc > wmax) wpc = wmax;
     if (!wpc_req && balance && n > sms * wmax) {
@@ -332,7 +338,7 @@ static int plan_launch(int n, int wpc_req, int default_wpc, bool balance, MgLaun
     if (wpc < 1) wpc = 1;
     int ctas = (n + wpc - 1) / wpc;
     if (ctas > sms) ctas = sms;
-    size_t smem = (size_t)wpc * per_warp;
+    size_t smem = (size_t)wpc * per_warp + P::kCtaExtra;
     // what is left of the SM's shared memory (up to 48 KB) stages the asset header + sprite pixel lists
     int stage_cap = smem_max - (int)smem;
     if (stage_cap > 48 * 1024) stage_cap = 48 * 1024;

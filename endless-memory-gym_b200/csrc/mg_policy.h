@@ -85,7 +85,16 @@ MG_HDN void mg_env_logic(const typename E::K& k, const MgKIO& q, const MgAssetVi
     }
 }
 
+// per-warp / per-CTA scratch beyond the frame buffer and the record slot (Searing Spotlights' base buffer, tables)
+struct MgScratch {
+    uint8_t* warp;
+    const uint8_t* cta;
+};
+
 struct MMPolicy {
+    static constexpr int kWarpExtra = 0, kCtaExtra = 0;
+    static MG_HD void cta_init(uint8_t*, int, int) {}
+    static MG_HD void warp_init(uint8_t*, int) {}
     typedef MgMMK K;
     typedef MgMMState State;
     typedef MgMMFrame Frame;
@@ -101,16 +110,19 @@ struct MMPolicy {
         mg_env_logic<MMPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
     }
     template <class Ctx>
-    static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K& k, const Frame& f) {
+    static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K& k, const Frame& f, const MgScratch&) {
         mg_mm_compose(c, buf, a, f, k.origin, a.hdr->agent_dim >> 1, a.hdr->icon_x, a.hdr->icon_y);
     }
     template <class Ctx>
-    static MG_HD void restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const K& k, const Frame& f) {
+    static MG_HD void restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const K& k, const Frame& f, const MgScratch&) {
         mg_mm_restore(c, buf, a, f, k.origin, k.size, a.hdr->agent_dim >> 1, a.hdr->icon_x, a.hdr->icon_y);
     }
 };
 
 struct MPPolicy {
+    static constexpr int kWarpExtra = 0, kCtaExtra = 0;
+    static MG_HD void cta_init(uint8_t*, int, int) {}
+    static MG_HD void warp_init(uint8_t*, int) {}
     typedef MgMPK K;
     typedef MgMPState State;
     typedef MgMPDraw Frame;
@@ -124,16 +136,28 @@ struct MPPolicy {
         mg_env_logic<MPPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
     }
     template <class Ctx>
-    static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f) {
+    static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f, const MgScratch&) {
         mg_mp_compose(c, buf, a, f, a.hdr->agent_dim >> 1);
     }
     template <class Ctx>
-    static MG_HD void restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f) {
+    static MG_HD void restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f, const MgScratch&) {
         mg_mp_restore(c, buf, a, f, a.hdr->agent_dim >> 1);
     }
 };
 
 struct SSPolicy {
+    static constexpr int kWarpExtra = (int)((sizeof(MgSSWarpMem) + 127) / 128 * 128);
+    static constexpr int kCtaExtra = (int)((sizeof(MgSSCtaTables) + 127) / 128 * 128);
+    static MG_HD void cta_init(uint8_t* cta, int tid, int nthreads) {
+        mg_ss_tables_init(reinterpret_cast<MgSSCtaTables*>(cta), tid, nthreads);
+    }
+    static MG_HD void warp_init(uint8_t* warp, int lane) {
+        if (lane == 0) {
+            MgSSWarpMem* wm = reinterpret_cast<MgSSWarpMem*>(warp);
+            wm->desc.valid = 0;
+            wm->desc.lut_alpha = -1;
+        }
+    }
     typedef MgSSK K;
     typedef MgSSState State;
     typedef MgSSFrame Frame;
@@ -150,7 +174,7 @@ struct SSPolicy {
         mg_env_logic<SSPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
     }
     template <class Ctx>
-    static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K& k, const Frame& f) {
+    static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K& k, const Frame& f, const MgScratch& sc) {
         MgSSDrawK d;
         d.n_layers = k.n_layers;
         for (int i = 0; i < 6; ++i) d.layers[i] = k.layers[i];
@@ -159,9 +183,10 @@ struct SSPolicy {
         d.show_last_action = k.p.show_last_action;
         d.has_coin_layer = 1;
         d.border = k.p.black_background;
-        mg_ss_compose(c, buf, a, d, f);
+        mg_ss_compose(c, buf, a, d, f, reinterpret_cast<MgSSWarpMem*>(sc.warp),
+                      reinterpret_cast<const MgSSCtaTables*>(sc.cta));
     }
     // every frame rewrites the whole buffer: nothing to undo
     template <class Ctx>
-    static MG_HD void restore(Ctx&, uint8_t*, const MgAssetView&, const K&, const Frame&) {}
+    static MG_HD void restore(Ctx&, uint8_t*, const MgAssetView&, const K&, const Frame&, const MgScratch&) {}
 };

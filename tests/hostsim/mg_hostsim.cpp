@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <type_traits>
+#include <vector>
 
 #include "../../endless-memory-gym_b200/csrc/mg_params_host.h"
 #include "../../endless-memory-gym_b200/csrc/mg_policy.h"
@@ -18,13 +19,54 @@ struct HostCtx {
     void copy_frame(uint8_t* dst, const uint8_t* src) { memcpy(dst, src, MG_FRAME_BYTES); }
 };
 
-// mirrors mg_env_kernel (mg_kernels.cu) with one "warp" and a persistent frame buffer
+// mirrors mg_env_kernel (mg_kernels.cu) with one "warp": env-major loop, all n_steps steps of an env back to
+// back, a persistent frame buffer and persistent per-warp scratch (so incremental paths are exercised)
 template <class P>
-int run(const typename P::K& k, const void* assets, void* state, const uint64_t* rng4, const mg_step_io* io, int n,
-        int mode, int act_dims) {
+int run_q(const typename P::K& k, const void* assets, void* state, MgKIO q) {
     typedef typename P::State State;
     typedef typename P::Frame Frame;
     constexpr bool kCheckClean = !std::is_same<P, SSPolicy>::value;
+    const MgAssetView view = mg_asset_view(assets);
+    alignas(128) static thread_local uint8_t buf[MG_FRAME_BYTES];
+    static thread_local std::vector<uint8_t> wextra, cextra;  // the kernel's per-warp / per-CTA scratch
+    wextra.assign(P::kWarpExtra + 256, 0);
+    cextra.assign(P::kCtaExtra + 256, 0);
+    uint8_t* wx = wextra.data() + ((128 - ((uintptr_t)wextra.data() & 127)) & 127);  // 128-byte aligned like smem
+    uint8_t* cx = cextra.data() + ((128 - ((uintptr_t)cextra.data() & 127)) & 127);
+    P::cta_init(cx, 0, 1);
+    P::warp_init(wx, 0);
+    const MgScratch scratch{wx, cx};
+    HostCtx ctx;
+    ctx.copy_frame(buf, view.tmpl[0]);
+    for (int env = 0; env < q.n; ++env) {
+        State* st = reinterpret_cast<State*>((uint8_t*)state + (size_t)env * sizeof(State));
+        for (int t = 0; t < q.n_steps; ++t) {
+            MgFrameJob job;
+            Frame fr[2];
+            int a0 = 0, a1 = 0;
+            if (q.mode == MG_MODE_STEP) {
+                const int64_t* a = q.io.actions + (size_t)t * q.act_stride + (size_t)env * q.act_dims;
+                a0 = (int)a[0];
+                if (q.act_dims > 1) a1 = (int)a[1];
+            }
+            P::logic(k, q, view, env, t, *st, a0, a1, job, fr);
+            for (int fi = 0; fi < job.nframes; ++fi) {
+                uint8_t* dst = job.to_final[fi] ? q.io.final_obs + (size_t)env * MG_FRAME_BYTES
+                                                : q.io.obs + (size_t)(t % q.ring_n) * q.obs_stride + (size_t)env * MG_FRAME_BYTES;
+                P::compose(ctx, buf, view, k, fr[fi], scratch);
+                memcpy(dst, buf, MG_FRAME_BYTES);
+                P::restore(ctx, buf, view, k, fr[fi], scratch);
+                // the buffer must be clean again: catches any compose/restore asymmetry (envs with an un-patch path)
+                if (kCheckClean && memcmp(buf, view.tmpl[0], MG_FRAME_BYTES) != 0) return -100;
+            }
+        }
+    }
+    return 0;
+}
+
+template <class P>
+int run(const typename P::K& k, const void* assets, void* state, const uint64_t* rng4, const mg_step_io* io, int n,
+        int mode, int act_dims) {
     MgKIO q;
     memset(&q, 0, sizeof(q));
     q.n_steps = 1;
@@ -33,32 +75,33 @@ int run(const typename P::K& k, const void* assets, void* state, const uint64_t*
     q.rng4 = rng4;
     q.mode = mode;
     q.n = n;
-    q.stage_cap = 0;
     q.act_dims = act_dims;
-    const MgAssetView view = mg_asset_view(assets);
-    static thread_local uint8_t buf[MG_FRAME_BYTES];
-    HostCtx ctx;
-    ctx.copy_frame(buf, view.tmpl[0]);
-    for (int env = 0; env < n; ++env) {
-        State* st = reinterpret_cast<State*>((uint8_t*)state + (size_t)env * sizeof(State));
-        MgFrameJob job;
-        Frame fr[2];
-        int a0 = 0, a1 = 0;
-        if (mode == MG_MODE_STEP) {
-            a0 = (int)io->actions[(size_t)env * act_dims];
-            if (act_dims > 1) a1 = (int)io->actions[(size_t)env * act_dims + 1];
-        }
-        P::logic(k, q, view, env, 0, *st, a0, a1, job, fr);
-        for (int fi = 0; fi < job.nframes; ++fi) {
-            uint8_t* dst = (job.to_final[fi] ? io->final_obs : io->obs) + (size_t)env * MG_FRAME_BYTES;
-            P::compose(ctx, buf, view, k, fr[fi]);
-            memcpy(dst, buf, MG_FRAME_BYTES);
-            P::restore(ctx, buf, view, k, fr[fi]);
-            // the buffer must be clean again: catches any compose/restore asymmetry (envs with an un-patch path)
-            if (kCheckClean && memcmp(buf, view.tmpl[0], MG_FRAME_BYTES) != 0) return -100;
-        }
-    }
-    return 0;
+    return run_q<P>(k, assets, state, q);
+}
+
+template <class P>
+int run_rollout(const typename P::K& k, const void* assets, void* state, const mg_rollout_io* r, int n, int act_dims) {
+    MgKIO q;
+    memset(&q, 0, sizeof(q));
+    q.io.actions = r->actions;
+    q.io.obs = r->obs;
+    q.io.final_obs = r->final_obs;
+    q.io.reward = r->reward;
+    q.io.done = r->done;
+    q.io.info = r->info;
+    q.io.ground_truth = r->ground_truth;
+    q.io.flags = r->flags | MG_FLAG_AUTORESET;
+    q.mode = MG_MODE_STEP;
+    q.n = n;
+    q.act_dims = act_dims;
+    q.n_steps = r->n_steps;
+    q.ring_n = r->ring;
+    q.act_stride = (int64_t)n * act_dims;
+    q.obs_stride = (int64_t)n * MG_FRAME_BYTES;
+    q.rew_stride = n;
+    q.done_stride = n;
+    q.info_stride = r->info_per_step ? (int64_t)n * MG_INFO_COLS : 0;
+    return run_q<P>(k, assets, state, q);
 }
 }  // namespace
 
@@ -82,4 +125,22 @@ extern "C" int mgsim_ss(const mg_ss_params* p, const void* assets, void* state, 
     MgSSK k;
     mg_ss_derive(p, &k);
     return run<SSPolicy>(k, assets, state, rng4, io, n, mode, 2);
+}
+extern "C" int mgsim_mm_rollout(const mg_mm_params* p, const void* assets, void* state, const mg_rollout_io* r, int n) {
+    if (mg_mm_check_params(p)) return MG_EINVAL;
+    MgMMK k;
+    mg_mm_derive(p, &k);
+    return run_rollout<MMPolicy>(k, assets, state, r, n, p->variant == MG_MM_GRID ? 1 : 2);
+}
+extern "C" int mgsim_mp_rollout(const mg_mp_params* p, const void* assets, void* state, const mg_rollout_io* r, int n) {
+    if (mg_mp_check_params(p)) return MG_EINVAL;
+    MgMPK k;
+    mg_mp_derive(p, &k);
+    return run_rollout<MPPolicy>(k, assets, state, r, n, 2);
+}
+extern "C" int mgsim_ss_rollout(const mg_ss_params* p, const void* assets, void* state, const mg_rollout_io* r, int n) {
+    if (mg_ss_check_params(p)) return MG_EINVAL;
+    MgSSK k;
+    mg_ss_derive(p, &k);
+    return run_rollout<SSPolicy>(k, assets, state, r, n, 2);
 }

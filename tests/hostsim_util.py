@@ -70,17 +70,8 @@ class HostSimBackend:
             self.step(family, params, assets, state, ios[t], n, stream)
 
     def rollout(self, family, params, assets, state, rio, n, stream):
-        """mg_*_rollout semantics on the host: T steps, step t -> obs slot t % ring."""
-        L = self.L
-        A = 1 if (family == "mm" and params.variant == L.MG_MM_GRID) else 2
-        for t in range(rio.n_steps):
-            io = L.StepIO()
-            io.actions = rio.actions + t * n * A * 8
-            io.obs = rio.obs + (t % rio.ring) * n * L.MG_OBS_BYTES
-            io.final_obs = rio.final_obs
-            io.reward = rio.reward + t * n * 8
-            io.done = rio.done + t * n
-            io.info = rio.info + (t * n * L.MG_INFO_COLS * 8 if rio.info_per_step else 0)
-            io.ground_truth = rio.ground_truth
-            io.flags = rio.flags | L.MG_FLAG_AUTORESET
-            self.step(family, params, assets, state, io, n, stream)
+        """mg_*_rollout on the host: env-major, all T steps of an env back to back (like the kernel)."""
+        fn = getattr(self.sim, f"mgsim_{family}_rollout")
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        rc = fn(C.byref(params), assets, state, C.byref(rio), n)
+        assert rc == 0, rc

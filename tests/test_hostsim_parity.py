@@ -52,25 +52,35 @@ def test_rollout_vs_oracle(env_id, options, backend):
     assert episodes > 0
 
 
-def test_rollout_equals_step_loop_hostsim(backend):
-    """rollout() (slot t % ring, per-step reward/done/info rows) == T step() calls, on the host harness."""
+@pytest.mark.parametrize("env_id,opts", [("MortarMayhem-v0", None), ("MysteryPath-v0", {"max_steps": 50}),
+                                         ("SearingSpotlights-v0", {"max_steps": 60}),
+                                         ("SearingSpotlights-v0", {"max_steps": 45, "agent_visible": True,
+                                                                   "light_threshold": 90, "num_coins": [3]})])
+def test_rollout_equals_step_loop_hostsim(env_id, opts, backend):
+    """rollout() (env-major: all T steps of an env back to back, persistent per-warp scratch — exercises the
+    incremental frame paths; slot t % ring, per-step reward/done/info rows) == T step() calls."""
     import numpy as np
     import torch
     import memory_gym_b200 as mg
     n, T = 6, 130
-    a = mg.MemoryGymVecEnv("MortarMayhem-v0", n, device="cpu", _backend=backend)
-    b = mg.MemoryGymVecEnv("MortarMayhem-v0", n, device="cpu", _backend=backend)
+    a = mg.MemoryGymVecEnv(env_id, n, device="cpu", _backend=backend)
+    b = mg.MemoryGymVecEnv(env_id, n, device="cpu", _backend=backend)
     acts = torch.as_tensor(np.random.default_rng(1).integers(0, 3, (T, n, 2)))
-    a.reset(seed=9)
-    b.reset(seed=9)
+    a.reset(seed=9, options=opts)
+    b.reset(seed=9, options=opts)
     ring = torch.zeros((4, n, 84, 84, 3), dtype=torch.uint8)
     rew, dn = torch.zeros((T, n), dtype=torch.float64), torch.zeros((T, n), dtype=torch.bool)
     inf = torch.zeros((T, n, 8), dtype=torch.float64)
-    a.rollout(acts, ring, rew, dn, inf)
+    full = torch.zeros((T, n, 84, 84, 3), dtype=torch.uint8)
+    a.rollout(acts, full, rew, dn, inf)
+    a2 = mg.MemoryGymVecEnv(env_id, n, device="cpu", _backend=backend)
+    a2.reset(seed=9, options=opts)
+    a2.rollout(acts, ring, torch.zeros_like(rew), torch.zeros_like(dn), None)
     for t in range(T):
         o, r, d, _, info = b.step(acts[t])
         assert torch.equal(r, rew[t]) and torch.equal(d, dn[t])
         assert torch.equal(info["episode"][d], inf[t][d])
+        assert torch.equal(o, full[t]), (t, int((o != full[t]).sum()))
         if t >= T - 4:
             assert torch.equal(o, ring[t % 4])
     assert dn.any() and torch.equal(a.state, b.state)
