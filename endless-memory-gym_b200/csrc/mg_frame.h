@@ -284,13 +284,6 @@ MG_HD void mg_put_px(uint8_t* buf, int x, int y, uint32_t col) {
     o[2] = (uint8_t)(col >> 16);
 }
 
-// is (x, y) inside one of the spotlight discs drawn this step?
-MG_HD bool mg_ss_lit(const int8_t* rows, const MgSSFrame& f, int x, int y) {
-    for (int d = 0; d < (int)f.n_discs; ++d)
-        if (mg_disc_has(rows, f.disc_r[d], f.disc_x[d], f.disc_y[d], x, y)) return true;
-    return false;
-}
-
 // background colours of this frame (white tile, coloured tile), optionally dimmed by the spotlight layer's alpha
 MG_HD void mg_ss_bg_colours(int kind, int alpha, uint32_t& c_even, uint32_t& c_odd) {
     c_even = kind == 3 ? 0u : 0x00FFFFFFu;
@@ -320,62 +313,6 @@ MG_HD void mg_ss_bg_run(uint8_t* buf, int x, int ylo, int yhi, uint32_t c_even, 
     }
 }
 
-// background inside one spotlight disc (clipped), two lanes per column
-template <class Ctx>
-MG_HD void mg_ss_disc_bg(Ctx& c, uint8_t* buf, const MgAssetView& a, int x0, int y0, int r, uint32_t c_even,
-                         uint32_t c_odd) {
-    if (r < 1) return;
-    const int8_t* cols = (const int8_t*)(a.base + a.hdr->disc_off) + 2 * MG_MAX_DISC_R * (MG_MAX_DISC_R + 1) +
-                         2 * r * (r - 1);
-    int xa = x0 - r < 0 ? 0 : x0 - r, xb = x0 + r > MG_W ? MG_W : x0 + r;
-    for (int unit = c.lane; unit < 2 * (xb - xa); unit += c.nl) {
-        int x = xa + (unit >> 1), ci = x - x0 + r;
-        int ylo = y0 + (int)cols[2 * ci], yhi = y0 + (int)cols[2 * ci + 1];
-        if (ylo < 0) ylo = 0;
-        if (yhi > MG_W - 1) yhi = MG_W - 1;
-        if (ylo > yhi) continue;
-        int mid = (ylo + yhi + 1) >> 1;
-        if (unit & 1)
-            ylo = mid;
-        else
-            yhi = mid - 1;
-        if (ylo <= yhi) mg_ss_bg_run(buf, x, ylo, yhi, c_even, c_odd);
-    }
-}
-
-// colour-key blit of a sparse sprite UNDER the spotlight layer: lit pixels keep their colour, the others are dimmed
-template <class Ctx>
-MG_HD void mg_ss_sprite_under(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSFrame& f, int slot, int ax, int ay) {
-    const MgSprite sp = a.hdr->sprite[slot];
-    const uint32_t* e = a.entries + sp.first;
-    const int8_t* rows = (const int8_t*)(a.base + a.hdr->disc_off);
-    for (int i = c.lane; i < (int)sp.count; i += c.nl) {
-        uint32_t v = e[i];
-        int x = ax + (int)(v & 255u), y = ay + (int)((v >> 8) & 255u);
-        if ((unsigned)x >= (unsigned)MG_W || (unsigned)y >= (unsigned)MG_W) continue;
-        uint32_t col = mg_pal(a, (uint8_t)((v >> 16) & 255u));
-        if (f.alpha != 0 && !mg_ss_lit(rows, f, x, y)) col = mg_ss_dim(col, f.alpha);
-        mg_put_px(buf, x, y, col);
-    }
-}
-
-// over() where present, over a clipped rectangle (layers above the spotlight layer)
-template <class Ctx>
-MG_HD void mg_ss_rect_over(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
-                           int spot_li, int x0, int y0, int w, int h) {
-    int xa = x0 < 0 ? 0 : x0, ya = y0 < 0 ? 0 : y0;
-    int xb = x0 + w > MG_W ? MG_W : x0 + w, yb = y0 + h > MG_W ? MG_W : y0 + h;
-    if (xb <= xa || yb <= ya) return;
-    const int rows = yb - ya, total = (xb - xa) * rows;
-    const uint64_t inv = ((1ull << 24) + (uint64_t)rows - 1) / (uint64_t)rows;  // exact i / rows for i < 2^13
-    for (int i = c.lane; i < total; i += c.nl) {
-        int q = (int)(((uint64_t)i * inv) >> 24);
-        int x = xa + q, y = ya + (i - q * rows);
-        uint32_t col;
-        if (mg_ss_over(a, k, f, spot_li, x, y, col)) mg_put_px(buf, x, y, col);
-    }
-}
-
 // ---- base buffer + lit mask: the per-frame cost of Searing Spotlights is a masked 16-byte copy -----------------
 // Per warp: `base` = the scene UNDER the spotlight layer, undimmed (tiled background + coins/exit/agent that sit
 // below the layer), kept across frames and patched only where the scene changed; `lit` = 84 columns x 96 bits,
@@ -396,6 +333,7 @@ struct MgSSWarpMem {
     uint32_t lit[MG_W * 3 + 4];
     uint8_t dimlut[256];
     MgSSBaseDesc desc;
+    uint8_t step_tmp[96];  // MgSSStepTmp of the logic (mg_ss_logic.h)
 };
 
 struct MgSSCtaTables {
@@ -438,56 +376,79 @@ MG_HD bool mg_ss_layer_below(const MgSSDrawK& k, int spot_li, int layer) {
     return false;
 }
 
-// bring `base` up to date with frame f (full rebuild, or just move the agent)
+// the top bar into rows 0..3 of `base` (a column start is 4-byte aligned: 12 bytes = three words per column)
+template <class Ctx>
+MG_HD void mg_ss_draw_bar(Ctx& c, uint8_t* base, const MgSSDrawK& k, const MgSSFrame& f) {
+    for (int x = c.lane; x < MG_W; x += c.nl) {
+        uint32_t col = mg_ss_bar(k, f, x), r = col & 255u, g = (col >> 8) & 255u, b = (col >> 16) & 255u;
+        uint32_t* w = reinterpret_cast<uint32_t*>(base + x * MG_COL_BYTES);
+        w[0] = r | (g << 8) | (b << 16) | (r << 24);
+        w[1] = g | (b << 8) | (r << 16) | (g << 24);
+        w[2] = b | (r << 8) | (g << 16) | (b << 24);
+    }
+}
+
+template <class Ctx>
+MG_HD void mg_ss_draw_layer(Ctx& c, uint8_t* base, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f, int L) {
+    if (L == 3) {
+        const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
+        for (int q = 0; q < (int)f.n_coins; ++q) {
+            mg_sprite_draw(c, base, a, MG_SPR_COIN, f.coins[q][0] - (sp.w >> 1), f.coins[q][1] - (sp.h >> 1));
+            c.sync();
+        }
+    } else if (L == 4) {
+        int slot = f.exit_open ? MG_SPR_EXIT_OPEN : MG_SPR_EXIT_CLOSED;
+        const MgSprite sp = a.hdr->sprite[slot];
+        mg_sprite_draw(c, base, a, slot, f.exit_x - (sp.w >> 1), f.exit_y - (sp.h >> 1));
+        c.sync();
+    } else if (L == 5) {
+        int half = a.hdr->agent_dim >> 1;
+        mg_sprite_draw(c, base, a, MG_SPR_AGENT0 + f.srot, f.sx - half, f.sy - half);
+        c.sync();
+    } else if (L == 2) {
+        mg_ss_draw_bar(c, base, k, f);
+        c.sync();
+    }
+}
+
+// Bring `base` up to date with frame f. `base` = every layer EXCEPT the spotlight layer, in painter's order
+// (layers above the spotlight layer are never dimmed: their pixels are forced lit in the mask instead).
+// `simple` = the reference's default order (coins, exit, agent below the spotlight layer, bar on top): then a
+// frame that only moved the agent is a small patch; any other order rebuilds.
 template <class Ctx>
 MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
-                             int spot_li) {
+                             int spot_li, bool simple) {
     uint8_t* base = wm->base;
     const MgSSBaseDesc d = wm->desc;
-    const bool agent_below = mg_ss_layer_below(k, spot_li, 5);
     const int half = a.hdr->agent_dim >> 1;
-    bool same_rest = d.valid && d.bg_kind == f.bg_kind && d.exit_x == f.exit_x && d.exit_y == f.exit_y &&
+    bool same_rest = simple && d.valid && d.bg_kind == f.bg_kind && d.exit_x == f.exit_x && d.exit_y == f.exit_y &&
                      d.exit_open == f.exit_open && d.n_coins == f.n_coins;
     for (int q = 0; same_rest && q < (int)f.n_coins; ++q)
         same_rest = d.coins[q][0] == f.coins[q][0] && d.coins[q][1] == f.coins[q][1];
-    const bool same_agent = !agent_below || (d.sx == f.sx && d.sy == f.sy && d.srot == f.srot);
-    if (same_rest && same_agent) return;
+    const bool same_agent = d.sx == f.sx && d.sy == f.sy && d.srot == f.srot;
     if (same_rest) {
-        // only the agent moved: put back what it covered, then draw it at its new pose
-        const MgSprite sp = a.hdr->sprite[MG_SPR_AGENT0 + d.srot];
-        const uint32_t* e = a.entries + sp.first;
-        for (int i = c.lane; i < (int)sp.count; i += c.nl) {
-            uint32_t v = e[i];
-            int x = d.sx - half + (int)(v & 255u), y = d.sy - half + (int)((v >> 8) & 255u);
-            if ((unsigned)x < (unsigned)MG_W && (unsigned)y < (unsigned)MG_W)
-                mg_put_px(base, x, y, mg_ss_under_no_agent(a, k, f, spot_li, x, y));
+        if (!same_agent) {
+            // only the agent moved: put back what it covered, then draw it at its new pose
+            const MgSprite sp = a.hdr->sprite[MG_SPR_AGENT0 + d.srot];
+            const uint32_t* e = a.entries + sp.first;
+            for (int i = c.lane; i < (int)sp.count; i += c.nl) {
+                uint32_t v = e[i];
+                int x = d.sx - half + (int)(v & 255u), y = d.sy - half + (int)((v >> 8) & 255u);
+                if ((unsigned)x < (unsigned)MG_W && (unsigned)y < (unsigned)MG_W)
+                    mg_put_px(base, x, y, mg_ss_under_no_agent(a, k, f, spot_li, x, y));
+            }
+            c.sync();
+            mg_ss_draw_layer(c, base, a, k, f, 5);
         }
-        c.sync();
+        mg_ss_draw_layer(c, base, a, k, f, 2);  // the bar changes every step and sits on top
     } else {
         uint32_t c_even, c_odd;
         mg_ss_bg_colours(f.bg_kind, 0, c_even, c_odd);
         for (int unit = c.lane; unit < 2 * MG_W; unit += c.nl)
             mg_ss_bg_run(base, unit >> 1, (unit & 1) ? MG_W / 2 : 0, (unit & 1) ? MG_W - 1 : MG_W / 2 - 1, c_even, c_odd);
         c.sync();
-        for (int lj = 1; lj < spot_li; ++lj) {  // coins, then exit (painter's order); the agent follows below
-            int M = k.layers[lj];
-            if (M == 3) {
-                const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
-                for (int q = 0; q < (int)f.n_coins; ++q) {
-                    mg_sprite_draw(c, base, a, MG_SPR_COIN, f.coins[q][0] - (sp.w >> 1), f.coins[q][1] - (sp.h >> 1));
-                    c.sync();
-                }
-            } else if (M == 4) {
-                int slot = f.exit_open ? MG_SPR_EXIT_OPEN : MG_SPR_EXIT_CLOSED;
-                const MgSprite sp = a.hdr->sprite[slot];
-                mg_sprite_draw(c, base, a, slot, f.exit_x - (sp.w >> 1), f.exit_y - (sp.h >> 1));
-                c.sync();
-            }
-        }
-    }
-    if (agent_below) {
-        mg_sprite_draw(c, base, a, MG_SPR_AGENT0 + f.srot, f.sx - half, f.sy - half);
-        c.sync();
+        for (int li = 1; li < k.n_layers; ++li)
+            if (k.layers[li] != 1) mg_ss_draw_layer(c, base, a, k, f, k.layers[li]);
     }
     if (c.lane == 0) {
         MgSSBaseDesc& w = wm->desc;
@@ -503,10 +464,10 @@ MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, cons
 
 // lit[x] = union over the discs of their column runs; every lane owns whole columns (no write conflicts)
 template <class Ctx>
-MG_HD void mg_ss_build_lit(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const MgSSFrame& f) {
+MG_HD void mg_ss_build_lit(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const MgSSFrame& f, uint32_t forced_w0) {
     const int8_t* cols_all = (const int8_t*)(a.base + a.hdr->disc_off) + 2 * MG_MAX_DISC_R * (MG_MAX_DISC_R + 1);
     for (int x = c.lane; x < MG_W; x += c.nl) {
-        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        uint32_t w0 = forced_w0, w1 = 0, w2 = 0;  // forced: rows of a layer above the spotlight layer (top bar)
         for (int d = 0; d < (int)f.n_discs; ++d) {
             int r = f.disc_r[d], ci = x - (int)f.disc_x[d] + r;
             if (r < 1 || (unsigned)ci >= (unsigned)(2 * r)) continue;
@@ -537,13 +498,14 @@ MG_HD void mg_ss_build_lit(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const 
     if (c.lane == 0) wm->lit[3 * MG_W] = wm->lit[3 * MG_W + 1] = wm->lit[3 * MG_W + 2] = 0;  // column 84: padding
 }
 
-// out = lit ? base : dim(base), 16 bytes at a time
+// frame = lit ? base : dim(base), 16 bytes at a time, straight to the observation buffer (coalesced 128-bit
+// stores: consecutive lanes write consecutive chunks)
 template <class Ctx>
-MG_HD void mg_ss_masked_copy(Ctx& c, uint8_t* out, const MgSSWarpMem* wm, const MgSSCtaTables* t, int alpha) {
+MG_HD void mg_ss_masked_copy(Ctx& c, uint8_t* out, const MgSSWarpMem* wm, const MgSSCtaTables* t, int alpha, bool stream) {
     const MgVec16* src = reinterpret_cast<const MgVec16*>(wm->base);
     MgVec16* dst = reinterpret_cast<MgVec16*>(out);
     if (alpha == 0) {
-        for (int i = c.lane; i < MG_SS_CHUNKS; i += c.nl) dst[i] = src[i];
+        for (int i = c.lane; i < MG_SS_CHUNKS; i += c.nl) c.store16(dst + i, src[i], stream);
         return;
     }
     for (int i = c.lane; i < MG_SS_CHUNKS; i += c.nl) {
@@ -567,20 +529,47 @@ MG_HD void mg_ss_masked_copy(Ctx& c, uint8_t* out, const MgSSWarpMem* wm, const 
             }
             o.x = ow[0], o.y = ow[1], o.z = ow[2], o.w = ow[3];
         }
-        dst[i] = o;
+        c.store16(dst + i, o, stream);
     }
 }
 
+// One Searing-Spotlights frame -> `out` (the env's 21168 observation bytes in global memory)
 template <class Ctx>
-MG_HD void mg_ss_compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
-                         MgSSWarpMem* wm, const MgSSCtaTables* tables) {
-    int spot_li = 1;
-    for (int li = 0; li < k.n_layers; ++li)
+MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+                      MgSSWarpMem* wm, const MgSSCtaTables* tables, bool stream) {
+    int spot_li = 1, bar_li = 0;
+    for (int li = 0; li < k.n_layers; ++li) {
         if (k.layers[li] == 1) spot_li = li;
-    // 1. the scene under the spotlight layer (kept across frames, patched where it changed)
-    mg_ss_update_base(c, wm, a, k, f, spot_li);
-    // 2. which pixels the colour-keyed discs leave untouched, and the dimming of the others
-    if (f.alpha != 0) mg_ss_build_lit(c, wm, a, f);
+        if (k.layers[li] == 2) bar_li = li;
+    }
+    // the reference's default order: bg, coins, exit, agent, SPOT, bar
+    const bool simple = spot_li == k.n_layers - 2 && bar_li == k.n_layers - 1;
+    // 1. every layer but the spotlight layer (kept across frames, patched where it changed)
+    mg_ss_update_base(c, wm, a, k, f, spot_li, simple);
+    // 2. which pixels stay undimmed: the colour-keyed discs, and whatever is painted above the spotlight layer
+    if (f.alpha != 0) {
+        mg_ss_build_lit(c, wm, a, f, bar_li > spot_li ? 0xFu : 0u);
+        if (!simple) {
+            c.sync();
+            for (int li = spot_li + 1; li < k.n_layers; ++li) {
+                int L = k.layers[li];
+                int slot = L == 5 ? MG_SPR_AGENT0 + f.srot : (L == 4 ? (f.exit_open ? MG_SPR_EXIT_OPEN : MG_SPR_EXIT_CLOSED) : MG_SPR_COIN);
+                if (L != 3 && L != 4 && L != 5) continue;
+                const MgSprite sp = a.hdr->sprite[slot];
+                const uint32_t* e = a.entries + sp.first;
+                int reps = L == 3 ? (int)f.n_coins : 1;
+                for (int q = 0; q < reps; ++q) {
+                    int ax = L == 5 ? f.sx - (a.hdr->agent_dim >> 1) : (L == 4 ? f.exit_x - (sp.w >> 1) : f.coins[q][0] - (sp.w >> 1));
+                    int ay = L == 5 ? f.sy - (a.hdr->agent_dim >> 1) : (L == 4 ? f.exit_y - (sp.h >> 1) : f.coins[q][1] - (sp.h >> 1));
+                    for (int i = c.lane; i < (int)sp.count; i += c.nl) {
+                        int x = ax + (int)(e[i] & 255u), y = ay + (int)((e[i] >> 8) & 255u);
+                        if ((unsigned)x < (unsigned)MG_W && (unsigned)y < (unsigned)MG_W)
+                            c.atomic_or(&wm->lit[3 * x + (y >> 5)], 1u << (y & 31));
+                    }
+                }
+            }
+        }
+    }
     if (f.alpha != 0 && f.alpha != 255 && wm->desc.lut_alpha != (int)f.alpha) {
         for (int v = c.lane; v < 256; v += c.nl) wm->dimlut[v] = (uint8_t)((uint32_t)v - (uint32_t)v * f.alpha / 255u);
         c.sync();
@@ -588,12 +577,13 @@ MG_HD void mg_ss_compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSD
     }
     c.sync();
     // 3. frame = lit ? base : base dimmed by alpha (SDL: d + trunc((0 - d) * A / 255))
-    mg_ss_masked_copy(c, buf, wm, tables, f.alpha);
-    c.sync();
+    mg_ss_masked_copy(c, out, wm, tables, f.alpha, stream);
+    uint8_t* buf = out;
     // 3b. black_background: white 1-px outlines on the spotlight surface (pygame_assets.py:112-113). An outline
     //     pixel survives unless a LATER spotlight's disc is drawn over it; it is blended like any non-key pixel:
     //     d + trunc((255 - d) * A / 255) over what lies underneath.
     if (k.border && f.alpha != 0 && a.hdr->ring_off) {
+        c.sync();  // the outline bytes land after the vector stores of the other lanes
         const uint16_t* start = (const uint16_t*)(a.base + a.hdr->ring_off);
         const int8_t* ring = (const int8_t*)(start + MG_MAX_DISC_R + 2);
         const int8_t* rows = (const int8_t*)(a.base + a.hdr->disc_off);
@@ -608,6 +598,7 @@ MG_HD void mg_ss_compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSD
                     covered = mg_disc_has(rows, f.disc_r[e], f.disc_x[e], f.disc_y[e], x, y);
                 if (covered) continue;
                 uint32_t under = mg_ss_bg(f.bg_kind, x, y), col;
+                if (mg_ss_over(a, k, f, spot_li, x, y, col)) continue;  // painted over by a layer above the spotlights
                 for (int lj = spot_li - 1; lj > 0; --lj)
                     if (mg_ss_layer_at(a, f, k.layers[lj], x, y, col)) {
                         under = col;
@@ -621,23 +612,5 @@ MG_HD void mg_ss_compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSD
             }
         }
         c.sync();
-    }
-    // 4. layers above the spotlight layer (overlaps resolved per pixel by mg_ss_over)
-    for (int li = spot_li + 1; li < k.n_layers; ++li) {
-        int L = k.layers[li];
-        if (L == 2) {
-            mg_ss_rect_over(c, buf, a, k, f, spot_li, 0, 0, MG_W, 4);
-        } else if (L == 5) {
-            int dim = a.hdr->agent_dim;
-            mg_ss_rect_over(c, buf, a, k, f, spot_li, f.sx - (dim >> 1), f.sy - (dim >> 1), dim, dim);
-        } else if (L == 4) {
-            const MgSprite sp = a.hdr->sprite[MG_SPR_EXIT_OPEN];
-            mg_ss_rect_over(c, buf, a, k, f, spot_li, f.exit_x - (sp.w >> 1), f.exit_y - (sp.h >> 1), sp.w, sp.h);
-        } else if (L == 3) {
-            const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
-            for (int q = 0; q < (int)f.n_coins; ++q)
-                mg_ss_rect_over(c, buf, a, k, f, spot_li, f.coins[q][0] - (sp.w >> 1), f.coins[q][1] - (sp.h >> 1), sp.w,
-                                sp.h);
-        }
     }
 }

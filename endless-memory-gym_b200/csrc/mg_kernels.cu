@@ -32,7 +32,6 @@
 #include "mg_params_host.h"
 #include "mg_policy.h"
 
-#define MG_BUF_STRIDE 21248  // MG_FRAME_BYTES rounded up to 128
 
 // ---- PTX wrappers (TMA bulk copies, mbarrier, proxy fence) ---------------------------------------
 __device__ __forceinline__ uint32_t mg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,7 +98,18 @@ __device__ __forceinline__ uint64_t mg_now() {
 struct MgWarpCtx {
     int lane, nl;
     uint32_t bar, phase;
+    uint64_t policy;  // L2 evict-first cache policy
     __device__ __forceinline__ void sync() { __syncwarp(); }
+    // 128-bit store to global memory; `stream` = L2 evict-first (the frame is not re-read soon)
+    __device__ __forceinline__ void store16(MgVec16* p, const MgVec16& v, bool stream) {
+        if (stream)
+            asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(__cvta_generic_to_global(p)),
+                         "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
+                         : "memory");
+        else
+            *p = v;
+    }
+    __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
     // whole-frame template -> this warp's frame buffer, by TMA
     __device__ __forceinline__ void copy_frame(uint8_t* dst, const uint8_t* src) {
         mg_fence_proxy_async();  // earlier generic-proxy accesses to dst are ordered before the async write
@@ -127,10 +137,10 @@ __global__ void __launch_bounds__(320, 1)
     extern __shared__ __align__(128) uint8_t smem[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    uint8_t* buf = smem + (size_t)warp * MG_BUF_STRIDE;
-    uint8_t* slot = smem + (size_t)nwarps * MG_BUF_STRIDE + (size_t)warp * kSlot;
-    uint8_t* wextra = smem + (size_t)nwarps * (MG_BUF_STRIDE + kSlot) + (size_t)warp * P::kWarpExtra;
-    uint8_t* cextra = smem + (size_t)nwarps * (MG_BUF_STRIDE + kSlot + P::kWarpExtra);
+    uint8_t* buf = smem + (size_t)warp * P::kFrameBuf;
+    uint8_t* slot = smem + (size_t)nwarps * P::kFrameBuf + (size_t)warp * kSlot;
+    uint8_t* wextra = smem + (size_t)nwarps * (P::kFrameBuf + kSlot) + (size_t)warp * P::kWarpExtra;
+    uint8_t* cextra = smem + (size_t)nwarps * (P::kFrameBuf + kSlot + P::kWarpExtra);
     uint8_t* stage = cextra + P::kCtaExtra;
     const MgScratch scratch{wextra, cextra};
     State* st = reinterpret_cast<State*>(slot);
@@ -144,13 +154,13 @@ __global__ void __launch_bounds__(320, 1)
     uint64_t tr0 = 0, tr1 = 0, tr2 = 0;
     if (tracing) tr0 = mg_now();
     MgAssetView view = mg_asset_view(assets);
-    MgWarpCtx ctx{lane, 32, mg_smem_u32(bar), 0u};
+    MgWarpCtx ctx{lane, 32, mg_smem_u32(bar), 0u, mg_policy_evict_first()};
     if (lane == 0) mg_mbar_init(ctx.bar, 1);
     __syncwarp();
     const int total_warps = gridDim.x * nwarps;
     int env = warp * gridDim.x + blockIdx.x;  // consecutive envs on different SMs: remainders spread evenly
     const bool active = env < q.n;
-    if (active && lane == 0) {  // background template -> this warp's frame buffer (TMA, L2-resident source)
+    if (P::kFrameBuf && active && lane == 0) {  // background template -> this warp's frame buffer (TMA, L2-resident source)
         mg_mbar_expect_tx(ctx.bar, MG_FRAME_BYTES);
         mg_bulk_load(buf, view.tmpl[0], MG_FRAME_BYTES, ctx.bar);
     }
@@ -173,7 +183,7 @@ __global__ void __launch_bounds__(320, 1)
 
     const int T = q.n_steps;
     const bool stepping = q.mode == MG_MODE_STEP;
-    const uint64_t evict_first = mg_policy_evict_first();
+    const uint64_t evict_first = ctx.policy;
     // ---- first record + first actions in flight while the template lands --------------------------------
     uint64_t pre[kPerLane];
     int64_t act0 = 0, act1 = 0;
@@ -188,8 +198,10 @@ __global__ void __launch_bounds__(320, 1)
             if (q.act_dims > 1) act1 = a[1];
         }
     }
-    mg_mbar_wait(ctx.bar, ctx.phase);
-    ctx.phase ^= 1u;
+    if (P::kFrameBuf) {
+        mg_mbar_wait(ctx.bar, ctx.phase);
+        ctx.phase ^= 1u;
+    }
 
     bool pending = false;  // a bulk store is still reading `buf`; `prev` is the patch to undo afterwards
     Frame prev;
@@ -227,7 +239,7 @@ __global__ void __launch_bounds__(320, 1)
                     if (q.act_dims > 1) act1 = a[1];
                 }
             }
-            if (lane == 0) P::logic(k, q, view, env, t, *st, a0, a1, *job, fr);
+            P::logic(ctx, k, q, view, env, t, *st, a0, a1, *job, fr, scratch);
             __syncwarp();
             if (trow && lane == 0) trow[4] = mg_now();
             const int nframes = job->nframes;
@@ -236,6 +248,12 @@ __global__ void __launch_bounds__(320, 1)
                 const bool to_final = job->to_final[fi] != 0;
                 uint8_t* dst = to_final ? q.io.final_obs + (size_t)env * MG_FRAME_BYTES
                                         : q.io.obs + (size_t)(t % q.ring_n) * q.obs_stride + (size_t)env * MG_FRAME_BYTES;
+                if constexpr (P::kDirectStore) {
+                    if (trow && lane == 0) trow[5] = mg_now();
+                    P::emit(ctx, dst, view, k, f, scratch, (q.io.flags & MG_FLAG_STREAM_OBS) != 0);
+                    if (trow && lane == 0) trow[6] = mg_now();
+                    continue;
+                }
                 if (pending) {
                     if (lane == 0) mg_bulk_wait_read();
                     __syncwarp();
@@ -317,7 +335,7 @@ static int plan_launch(int n, int wpc_req, int default_wpc, bool balance, MgLaun
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     constexpr int kSlot =
         (((int)sizeof(typename P::State) + 2 * (int)sizeof(typename P::Frame) + (int)sizeof(MgFrameJob) + 16 + 127) / 128) * 128;
-    const int per_warp = MG_BUF_STRIDE + kSlot + P::kWarpExtra;
+    const int per_warp = P::kFrameBuf + kSlot + P::kWarpExtra;
     int wmax = 10;
     while (wmax > 1 && wmax * per_warp + P::kCtaExtra + 16 * 1024 > smem_max) wmax--;  // leave room to stage the assets
     int wpc = wpc_req ? wpc_req : default_wpc;
@@ -534,7 +552,7 @@ extern "C" int mg_ss_reset(const mg_ss_params* p, const void* assets, void* stat
     if (mg_ss_check_params(p)) return MG_EINVAL;
     MgSSK k;
     mg_ss_derive(p, &k);
-    return launch_env<SSPolicy>(k, assets, state, rng4, io, 1, n, MG_MODE_RESET, 2, stream, 8);
+    return launch_env<SSPolicy>(k, assets, state, rng4, io, 1, n, MG_MODE_RESET, 2, stream, 10);
 }
 extern "C" int mg_ss_step(const mg_ss_params* p, const void* assets, void* state, const mg_step_io* io, int n,
                           void* stream) {
@@ -545,12 +563,12 @@ extern "C" int mg_ss_step_many(const mg_ss_params* p, const void* assets, void* 
     if (mg_ss_check_params(p)) return MG_EINVAL;
     MgSSK k;
     mg_ss_derive(p, &k);
-    return launch_env<SSPolicy>(k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, 2, stream, 8);
+    return launch_env<SSPolicy>(k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, 2, stream, 10);
 }
 extern "C" int mg_ss_rollout(const mg_ss_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
                              void* stream) {
     if (mg_ss_check_params(p)) return MG_EINVAL;
     MgSSK k;
     mg_ss_derive(p, &k);
-    return launch_rollout<SSPolicy>(k, assets, state, r, n, 2, stream, 8);
+    return launch_rollout<SSPolicy>(k, assets, state, r, n, 2, stream, 10);
 }

@@ -93,6 +93,8 @@ struct MgScratch {
 
 struct MMPolicy {
     static constexpr int kWarpExtra = 0, kCtaExtra = 0;
+    static constexpr int kFrameBuf = 21248;      // per-warp TMA frame buffer (MG_FRAME_BYTES rounded up to 128)
+    static constexpr bool kDirectStore = false;  // frames leave through cp.async.bulk from the frame buffer
     static MG_HD void cta_init(uint8_t*, int, int) {}
     static MG_HD void warp_init(uint8_t*, int) {}
     typedef MgMMK K;
@@ -105,9 +107,10 @@ struct MMPolicy {
                                Frame& f, double* gt) {
         return mg_mm_step_env(k, s, a0, a1, reward, info, f, gt);
     }
-    static MG_HDN void logic(const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0, int a1,
-                             MgFrameJob& job, Frame* fr) {
-        mg_env_logic<MMPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
+    template <class Ctx>
+    static MG_HD void logic(Ctx& c, const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0,
+                            int a1, MgFrameJob& job, Frame* fr, const MgScratch&) {
+        if (c.lane == 0) mg_env_logic<MMPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
     }
     template <class Ctx>
     static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K& k, const Frame& f, const MgScratch&) {
@@ -121,6 +124,8 @@ struct MMPolicy {
 
 struct MPPolicy {
     static constexpr int kWarpExtra = 0, kCtaExtra = 0;
+    static constexpr int kFrameBuf = 21248;
+    static constexpr bool kDirectStore = false;
     static MG_HD void cta_init(uint8_t*, int, int) {}
     static MG_HD void warp_init(uint8_t*, int) {}
     typedef MgMPK K;
@@ -131,9 +136,10 @@ struct MPPolicy {
                                Frame& f, double*) {
         return mg_mp_step_env(k, s, a0, a1, reward, info, f);
     }
-    static MG_HDN void logic(const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0, int a1,
-                             MgFrameJob& job, Frame* fr) {
-        mg_env_logic<MPPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
+    template <class Ctx>
+    static MG_HD void logic(Ctx& c, const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0,
+                            int a1, MgFrameJob& job, Frame* fr, const MgScratch&) {
+        if (c.lane == 0) mg_env_logic<MPPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
     }
     template <class Ctx>
     static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f, const MgScratch&) {
@@ -148,6 +154,9 @@ struct MPPolicy {
 struct SSPolicy {
     static constexpr int kWarpExtra = (int)((sizeof(MgSSWarpMem) + 127) / 128 * 128);
     static constexpr int kCtaExtra = (int)((sizeof(MgSSCtaTables) + 127) / 128 * 128);
+    static constexpr int kFrameBuf = 0;         // no staging buffer: the frame is a masked copy of the base buffer
+    static constexpr bool kDirectStore = true;  // ... written straight to the observation with 128-bit stores
+    static_assert(sizeof(MgSSStepTmp) <= sizeof(((MgSSWarpMem*)0)->step_tmp), "MgSSWarpMem::step_tmp too small");
     static MG_HD void cta_init(uint8_t* cta, int tid, int nthreads) {
         mg_ss_tables_init(reinterpret_cast<MgSSCtaTables*>(cta), tid, nthreads);
     }
@@ -165,16 +174,69 @@ struct SSPolicy {
     static MG_HD void reset_env(const K& k, const MgAssetView& a, State& s, Frame& f, double*) {
         mg_ss_reset_env(k, trig(a), s, f);
     }
-    static MG_HD bool step_env(const K& k, const MgAssetView& a, State& s, int a0, int a1, double& reward, double* info,
-                               Frame& f, double*) {
-        return mg_ss_step_env(k, trig(a), s, a0, a1, reward, info, f);
-    }
-    static MG_HDN void logic(const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0, int a1,
-                             MgFrameJob& job, Frame* fr) {
-        mg_env_logic<SSPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
-    }
+
+    // Same control flow as mg_env_logic, but the step is split A (one lane) / B (one lane per spotlight) /
+    // C (one lane): spotlight motion + hit tests are the only per-step work that grows with the scene.
     template <class Ctx>
-    static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K& k, const Frame& f, const MgScratch& sc) {
+    static MG_HD void logic(Ctx& c, const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0,
+                            int a1, MgFrameJob& job, Frame* fr, const MgScratch& sc) {
+        MgSSStepTmp& tmp = *reinterpret_cast<MgSSStepTmp*>(reinterpret_cast<MgSSWarpMem*>(sc.warp)->step_tmp);
+        double* const reward_out = q.io.reward + (size_t)t * q.rew_stride + env;
+        uint8_t* const done_out = q.io.done + (size_t)t * q.done_stride + env;
+        double* const info_out = q.io.info + (size_t)t * q.info_stride + MG_INFO_COLS * (size_t)env;
+        if (c.lane == 0) {
+            job.nframes = 0;
+            tmp.action = 0;
+            if (q.mode == MG_MODE_RESET) {
+                if (!(q.io.reset_mask && !q.io.reset_mask[env])) {
+                    if (q.rng4) {  // env.reset(seed=s): a fresh PCG64 stream
+                        const uint64_t* r = q.rng4 + 4 * (size_t)env;
+                        s.rng.state_lo = r[0];
+                        s.rng.state_hi = r[1];
+                        s.rng.inc_lo = r[2];
+                        s.rng.inc_hi = r[3];
+                        s.rng.buf = 0;
+                        s.rng.has_buf = 0;
+                    }
+                    mg_ss_reset_env(k, trig(a), s, fr[0]);
+                    job.nframes = 1;
+                    job.to_final[0] = 0;
+                }
+            } else if (!s.live) {  // finished (or never reset): the step is ignored
+                *reward_out = 0.0;
+                *done_out = 1;
+            } else {
+                tmp.action = 2;
+                mg_ss_step_a(k, s, a0, a1, tmp);
+            }
+        }
+        c.sync();
+        if (tmp.action != 2) return;
+        mg_ss_step_b(c, k, trig(a), s, tmp, fr[0]);
+        c.sync();
+        if (c.lane == 0) {
+            double reward;
+            bool done = mg_ss_step_c(k, s, tmp, reward, info_out, fr[0]);
+            *reward_out = reward;
+            *done_out = done ? 1 : 0;
+            job.nframes = 1;
+            job.to_final[0] = 0;
+            if (done && (q.io.flags & MG_FLAG_AUTORESET)) {
+                int at = 0;
+                if (q.io.final_obs) {  // terminal frame -> final_obs, first frame of the next episode -> obs
+                    job.to_final[0] = 1;
+                    at = 1;
+                }
+                mg_ss_reset_env(k, trig(a), s, fr[at]);
+                job.to_final[at] = 0;
+                job.nframes = at + 1;
+            }
+        }
+    }
+
+    template <class Ctx>
+    static MG_HD void emit(Ctx& c, uint8_t* dst, const MgAssetView& a, const K& k, const Frame& f, const MgScratch& sc,
+                           bool stream) {
         MgSSDrawK d;
         d.n_layers = k.n_layers;
         for (int i = 0; i < 6; ++i) d.layers[i] = k.layers[i];
@@ -183,10 +245,12 @@ struct SSPolicy {
         d.show_last_action = k.p.show_last_action;
         d.has_coin_layer = 1;
         d.border = k.p.black_background;
-        mg_ss_compose(c, buf, a, d, f, reinterpret_cast<MgSSWarpMem*>(sc.warp),
-                      reinterpret_cast<const MgSSCtaTables*>(sc.cta));
+        mg_ss_emit(c, dst, a, d, f, reinterpret_cast<MgSSWarpMem*>(sc.warp), reinterpret_cast<const MgSSCtaTables*>(sc.cta),
+                   stream);
     }
-    // every frame rewrites the whole buffer: nothing to undo
+    // unused with kDirectStore
+    template <class Ctx>
+    static MG_HD void compose(Ctx&, uint8_t*, const MgAssetView&, const K&, const Frame&, const MgScratch&) {}
     template <class Ctx>
     static MG_HD void restore(Ctx&, uint8_t*, const MgAssetView&, const K&, const Frame&, const MgScratch&) {}
 };

@@ -252,14 +252,26 @@ MG_HD_NOINLINE void mg_ss_reset_env(const MgSSK& k, const double* trig, MgSSStat
     f.bg_kind = mg_ss_bg_kind(s, 0);
 }
 
-MG_HD_NOINLINE bool mg_ss_step_env(const MgSSK& k, const double* trig, MgSSState& s, int a0, int a1,
-                                   double& reward_out, double* info, MgSSFrame& f) {
+// step(), split so that the spotlights (the only per-step work that grows with the scene) advance in
+// parallel, one lane per spotlight: A (one lane) -> B (all lanes) -> C (one lane)
+struct MgSSStepTmp {
+    int32_t action;   // what the logic lane decided for this call: 0 idle, 1 reset, 2 step
+    int32_t cx, cy;   // agent centre after the move
+    int32_t n_proc;   // spotlights drawn this step
+    uint8_t proc[MG_SS_MAXSPOTS];  // their indices in s.spots
+    uint8_t hitf[MG_SS_MAXSPOTS];  // is_agent_inside per drawn spotlight
+};
+
+// A: agent move, top-bar bookkeeping, light dimming, spawn, and WHICH spotlights are drawn this step
+MG_HD_NOINLINE void mg_ss_step_a(const MgSSK& k, MgSSState& s, int a0, int a1, MgSSStepTmp& tmp) {
     int cx = s.cx, cy = s.cy, rot = s.rot;
     // walkable_rect = (0, 16 * SCALE, 84, 84 - 16 * SCALE)
     mg_move_clamped(cx, cy, rot, a0, a1, k.step_axis, k.step_diag, k.radius, 0, 4, MG_W, MG_W);
     s.cx = (int16_t)cx;
     s.cy = (int16_t)cy;
     s.rot = (uint8_t)rot;
+    tmp.cx = cx;
+    tmp.cy = cy;
     if (k.p.show_last_action) {  // the boxes show the PREVIOUS action, then last_action is updated
         s.bar_c0 = s.last_a0;
         s.bar_c1 = s.last_a1;
@@ -270,31 +282,48 @@ MG_HD_NOINLINE bool mg_ss_step_env(const MgSSK& k, const double* trig, MgSSState
         int a = k.p.light_dim_off_duration > 0 ? (int)s.alpha + k.alpha_inc : k.p.light_threshold;
         s.alpha = (uint8_t)(a < 0 ? 0 : (a > 255 ? 255 : a));
     }
-    double reward = 0.0;
-    // ---- spotlight task
-    double r = 0.0;
-    bool spot_done = false;
     s.spawn_timer++;
     if (s.spawns_left > 0 && s.spawn_timer >= k.interval0) {
         if (s.n_spots < MG_SS_MAXSPOTS) mg_ss_new_spot(k, s.rng, s.spots[s.n_spots++]);
         s.spawns_left--;
         s.spawn_timer = 0;
     }
-    int hit = 0, nd = 0;
+    // `for spot in self.spotlights: if spot.done: self.spotlights.remove(spot) else: draw + hit test`
+    int np = 0;
     for (int i = 0; i < (int)s.n_spots; ++i) {
         if (s.spots[i].done) {
             for (int j = i; j + 1 < (int)s.n_spots; ++j) s.spots[j] = s.spots[j + 1];
             s.n_spots--;
             // the element that slid into slot i is skipped this step, exactly like list.remove inside `for`
         } else {
-            int dx, dy;
-            if (mg_ss_advance_spot(k, trig, s.spots[i], cx, cy, dx, dy)) hit++;
-            f.disc_x[nd] = (int16_t)dx;
-            f.disc_y[nd] = (int16_t)dy;
-            f.disc_r[nd] = s.spots[i].radius;
-            nd++;
+            tmp.proc[np++] = (uint8_t)i;
         }
     }
+    tmp.n_proc = np;
+}
+
+// B: Spotlight.draw + is_agent_inside for every drawn spotlight (lane j takes the j-th one)
+template <class Ctx>
+MG_HD void mg_ss_step_b(Ctx& c, const MgSSK& k, const double* trig, MgSSState& s, MgSSStepTmp& tmp, MgSSFrame& f) {
+    for (int j = c.lane; j < tmp.n_proc; j += c.nl) {
+        MgSSSpot& sp = s.spots[tmp.proc[j]];
+        int dx, dy;
+        tmp.hitf[j] = mg_ss_advance_spot(k, trig, sp, tmp.cx, tmp.cy, dx, dy) ? 1 : 0;
+        f.disc_x[j] = (int16_t)dx;
+        f.disc_y[j] = (int16_t)dy;
+        f.disc_r[j] = sp.radius;
+    }
+}
+
+// C: health, coins, exit, done, episode statistics, frame description
+MG_HD_NOINLINE bool mg_ss_step_c(const MgSSK& k, MgSSState& s, const MgSSStepTmp& tmp, double& reward_out, double* info,
+                                 MgSSFrame& f) {
+    const int cx = tmp.cx, cy = tmp.cy, rot = s.rot, nd = tmp.n_proc;
+    double reward = 0.0;
+    double r = 0.0;
+    bool spot_done = false;
+    int hit = 0;
+    for (int j = 0; j < nd; ++j) hit += tmp.hitf[j];
     int red_now = 0, bg_red = 0;
     if (hit > 0) {
         s.hp = s.hp - k.p.spot_damage;
@@ -395,4 +424,17 @@ MG_HD_NOINLINE bool mg_ss_step_env(const MgSSK& k, const double* trig, MgSSState
         }
     }
     return done;
+}
+
+// the whole step on one lane (A, B, C in sequence)
+struct MgSerialCtx {
+    int lane = 0, nl = 1;
+};
+MG_HD bool mg_ss_step_env(const MgSSK& k, const double* trig, MgSSState& s, int a0, int a1, double& reward_out,
+                          double* info, MgSSFrame& f) {
+    MgSSStepTmp tmp;
+    MgSerialCtx c;
+    mg_ss_step_a(k, s, a0, a1, tmp);
+    mg_ss_step_b(c, k, trig, s, tmp, f);
+    return mg_ss_step_c(k, s, tmp, reward_out, info, f);
 }

@@ -16,6 +16,8 @@ namespace {
 struct HostCtx {
     int lane = 0, nl = 1;
     void sync() {}
+    void store16(MgVec16* p, const MgVec16& v, bool) { *p = v; }
+    void atomic_or(uint32_t* p, uint32_t v) { *p |= v; }
     void copy_frame(uint8_t* dst, const uint8_t* src) { memcpy(dst, src, MG_FRAME_BYTES); }
 };
 
@@ -49,10 +51,14 @@ int run_q(const typename P::K& k, const void* assets, void* state, MgKIO q) {
                 a0 = (int)a[0];
                 if (q.act_dims > 1) a1 = (int)a[1];
             }
-            P::logic(k, q, view, env, t, *st, a0, a1, job, fr);
+            P::logic(ctx, k, q, view, env, t, *st, a0, a1, job, fr, scratch);
             for (int fi = 0; fi < job.nframes; ++fi) {
                 uint8_t* dst = job.to_final[fi] ? q.io.final_obs + (size_t)env * MG_FRAME_BYTES
                                                 : q.io.obs + (size_t)(t % q.ring_n) * q.obs_stride + (size_t)env * MG_FRAME_BYTES;
+                if constexpr (P::kDirectStore) {
+                    P::emit(ctx, dst, view, k, fr[fi], scratch, false);
+                    continue;
+                }
                 P::compose(ctx, buf, view, k, fr[fi], scratch);
                 memcpy(dst, buf, MG_FRAME_BYTES);
                 P::restore(ctx, buf, view, k, fr[fi], scratch);
