@@ -328,23 +328,28 @@ struct MgSSBaseDesc {  // what `base` currently shows
     int16_t coins[MG_SS_MAXCOINS][2];
 };
 
+#define MG_SS_LIT_WORDS 224  // 84 * 84 = 7056 pixel bits (x-major, like the frame bytes) = 220.5 words, padded
 struct MgSSWarpMem {
     uint8_t base[21248];
-    uint32_t lit[MG_W * 3 + 4];
+    uint32_t lit[MG_SS_LIT_WORDS];
     uint8_t dimlut[256];
     MgSSBaseDesc desc;
     uint8_t step_tmp[96];  // MgSSStepTmp of the logic (mg_ss_logic.h)
 };
 
 struct MgSSCtaTables {
-    uint32_t chunk[MG_SS_CHUNKS + 1];  // x | y0 << 8 | phase << 16 of the first pixel a chunk touches
-    MgVec16 mask[3][64];               // byte mask of a chunk for (phase, 6 lit bits)
+    MgVec16 mask[3][64];                 // byte mask of a 16-byte chunk for (phase = chunk % 3, 6 lit bits)
+    uint32_t bar_lit[MG_SS_LIT_WORDS];   // lit bits of rows 0..3 of every column (the top bar is never dimmed)
 };
 
 MG_HD void mg_ss_tables_init(MgSSCtaTables* t, int tid, int nthreads) {
-    for (int c = tid; c < MG_SS_CHUNKS; c += nthreads) {
-        int byte0 = 16 * c, p0 = byte0 / 3, phase = byte0 - 3 * p0;
-        t->chunk[c] = (uint32_t)(p0 / MG_W) | ((uint32_t)(p0 % MG_W) << 8) | ((uint32_t)phase << 16);
+    for (int w = tid; w < MG_SS_LIT_WORDS; w += nthreads) {
+        uint32_t v = 0;
+        for (int b = 0; b < 32; ++b) {
+            int p = 32 * w + b;
+            if (p < MG_W * MG_W && p % MG_W < 4) v |= 1u << b;
+        }
+        t->bar_lit[w] = v;
     }
     for (int i = tid; i < 3 * 64; i += nthreads) {
         int phase = i / 64, bits = i % 64;
@@ -462,40 +467,34 @@ MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, cons
     c.sync();
 }
 
-// lit[x] = union over the discs of their column runs; every lane owns whole columns (no write conflicts)
+// lit = pixel bits (index 84 * x + y, the frame's own order) covered by a spotlight disc drawn this step, on top
+// of `init` (the rows of layers above the spotlight layer). One (disc, column) run per lane iteration, OR-ed in
+// with shared-memory atomics (a run of <= 80 bits touches at most 4 words).
 template <class Ctx>
-MG_HD void mg_ss_build_lit(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const MgSSFrame& f, uint32_t forced_w0) {
+MG_HD void mg_ss_build_lit(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const MgSSFrame& f, const uint32_t* init) {
+    for (int w = c.lane; w < MG_SS_LIT_WORDS; w += c.nl) wm->lit[w] = init ? init[w] : 0u;
+    c.sync();
     const int8_t* cols_all = (const int8_t*)(a.base + a.hdr->disc_off) + 2 * MG_MAX_DISC_R * (MG_MAX_DISC_R + 1);
-    for (int x = c.lane; x < MG_W; x += c.nl) {
-        uint32_t w0 = forced_w0, w1 = 0, w2 = 0;  // forced: rows of a layer above the spotlight layer (top bar)
-        for (int d = 0; d < (int)f.n_discs; ++d) {
-            int r = f.disc_r[d], ci = x - (int)f.disc_x[d] + r;
-            if (r < 1 || (unsigned)ci >= (unsigned)(2 * r)) continue;
-            const int8_t* cols = cols_all + 2 * r * (r - 1);
-            int ylo = (int)f.disc_y[d] + (int)cols[2 * ci], yhi = (int)f.disc_y[d] + (int)cols[2 * ci + 1];
+    for (int d = 0; d < (int)f.n_discs; ++d) {
+        const int r = f.disc_r[d], x0 = f.disc_x[d], y0 = f.disc_y[d];
+        if (r < 1) continue;
+        const int8_t* cols = cols_all + 2 * r * (r - 1);
+        int xa = x0 - r < 0 ? 0 : x0 - r, xb = x0 + r > MG_W ? MG_W : x0 + r;
+        for (int x = xa + c.lane; x < xb; x += c.nl) {
+            int ci = x - x0 + r;
+            int ylo = y0 + (int)cols[2 * ci], yhi = y0 + (int)cols[2 * ci + 1];
             if (ylo < 0) ylo = 0;
             if (yhi > MG_W - 1) yhi = MG_W - 1;
             if (ylo > yhi) continue;
-            // bits ylo..yhi of a 96-bit value
-            for (int wi = 0; wi < 3; ++wi) {
-                int lo = ylo - 32 * wi, hi = yhi - 32 * wi;
-                if (hi < 0 || lo > 31) continue;
-                if (lo < 0) lo = 0;
-                if (hi > 31) hi = 31;
-                uint32_t m = (0xFFFFFFFFu >> (31 - (hi - lo))) << lo;
-                if (wi == 0)
-                    w0 |= m;
-                else if (wi == 1)
-                    w1 |= m;
-                else
-                    w2 |= m;
+            int lo = MG_W * x + ylo, hi = MG_W * x + yhi;
+            for (int w = lo >> 5; w <= (hi >> 5); ++w) {
+                int bl = lo - 32 * w, bh = hi - 32 * w;
+                if (bl < 0) bl = 0;
+                if (bh > 31) bh = 31;
+                c.atomic_or(&wm->lit[w], (0xFFFFFFFFu >> (31 - (bh - bl))) << bl);
             }
         }
-        wm->lit[3 * x] = w0;
-        wm->lit[3 * x + 1] = w1;
-        wm->lit[3 * x + 2] = w2;
     }
-    if (c.lane == 0) wm->lit[3 * MG_W] = wm->lit[3 * MG_W + 1] = wm->lit[3 * MG_W + 2] = 0;  // column 84: padding
 }
 
 // frame = lit ? base : dim(base), 16 bytes at a time, straight to the observation buffer (coalesced 128-bit
@@ -509,14 +508,12 @@ MG_HD void mg_ss_masked_copy(Ctx& c, uint8_t* out, const MgSSWarpMem* wm, const 
         return;
     }
     for (int i = c.lane; i < MG_SS_CHUNKS; i += c.nl) {
-        uint32_t dsc = t->chunk[i];
-        int x = (int)(dsc & 255u), y0 = (int)((dsc >> 8) & 255u), phase = (int)(dsc >> 16);
-        const uint32_t* L = wm->lit + 3 * x;
-        // 6 lit bits starting at row y0 of column x, continuing at row 0 of column x + 1
-        uint64_t lo = (uint64_t)L[0] | ((uint64_t)L[1] << 32);
-        uint64_t v = y0 < 32 ? (lo >> y0) : ((((uint64_t)L[1] | ((uint64_t)L[2] << 32))) >> (y0 - 32));
-        if (y0 + 6 > MG_W) v = (v & ((1ull << (MG_W - y0)) - 1ull)) | ((uint64_t)L[3] << (MG_W - y0));
-        MgVec16 m = t->mask[phase][(int)(v & 63ull)], b = src[i], o;
+        // chunk i = bytes 16 i .. 16 i + 15 = pixels p0 .. p0 + 5, p0 = 16 i / 3 = 5 i + i / 3, starting `phase`
+        // = 16 i % 3 = i % 3 bytes into pixel p0
+        const unsigned q3 = ((unsigned)i * 43691u) >> 17, phase = (unsigned)i - 3u * q3, p0 = 5u * (unsigned)i + q3;
+        const unsigned w = p0 >> 5, sh = p0 & 31u;
+        const uint32_t v = c.funnel_r(wm->lit[w], wm->lit[w + 1], sh);  // 6 lit bits from the flat pixel bitmap
+        MgVec16 m = t->mask[phase][(int)(v & 63u)], b = src[i], o;
         if (alpha == 255) {
             o.x = b.x & m.x, o.y = b.y & m.y, o.z = b.z & m.z, o.w = b.w & m.w;
         } else {
@@ -548,7 +545,7 @@ MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDraw
     mg_ss_update_base(c, wm, a, k, f, spot_li, simple);
     // 2. which pixels stay undimmed: the colour-keyed discs, and whatever is painted above the spotlight layer
     if (f.alpha != 0) {
-        mg_ss_build_lit(c, wm, a, f, bar_li > spot_li ? 0xFu : 0u);
+        mg_ss_build_lit(c, wm, a, f, bar_li > spot_li ? tables->bar_lit : nullptr);
         if (!simple) {
             c.sync();
             for (int li = spot_li + 1; li < k.n_layers; ++li) {
@@ -564,7 +561,7 @@ MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDraw
                     for (int i = c.lane; i < (int)sp.count; i += c.nl) {
                         int x = ax + (int)(e[i] & 255u), y = ay + (int)((e[i] >> 8) & 255u);
                         if ((unsigned)x < (unsigned)MG_W && (unsigned)y < (unsigned)MG_W)
-                            c.atomic_or(&wm->lit[3 * x + (y >> 5)], 1u << (y & 31));
+                            c.atomic_or(&wm->lit[(MG_W * x + y) >> 5], 1u << ((MG_W * x + y) & 31));
                     }
                 }
             }

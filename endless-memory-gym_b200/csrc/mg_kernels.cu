@@ -110,6 +110,7 @@ struct MgWarpCtx {
             *p = v;
     }
     __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
+    __device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
     // whole-frame template -> this warp's frame buffer, by TMA
     __device__ __forceinline__ void copy_frame(uint8_t* dst, const uint8_t* src) {
         mg_fence_proxy_async();  // earlier generic-proxy accesses to dst are ordered before the async write
