@@ -381,6 +381,21 @@ MG_HD bool mg_ss_layer_below(const MgSSDrawK& k, int spot_li, int layer) {
     return false;
 }
 
+// The whole tiled background into a frame: a 12-px tile run of a column is 36 bytes = 9 aligned words with a
+// period-3 pattern (a column starts 4-byte aligned: 252 = 4 * 63). One (column, tile) unit per lane iteration.
+template <class Ctx>
+MG_HD void mg_ss_fill_bg(Ctx& c, uint8_t* base, uint32_t c_even, uint32_t c_odd) {
+    for (int unit = c.lane; unit < MG_W * 7; unit += c.nl) {
+        const int x = unit / 7, t = unit - 7 * x;
+        const uint32_t col = ((((unsigned)x / 12u) + (unsigned)t) & 1u) ? c_odd : c_even;
+        const uint32_t r = col & 255u, g = (col >> 8) & 255u, b = (col >> 16) & 255u;
+        const uint32_t w0 = r | (g << 8) | (b << 16) | (r << 24), w1 = g | (b << 8) | (r << 16) | (g << 24),
+                       w2 = b | (r << 8) | (g << 16) | (b << 24);
+        uint32_t* w = reinterpret_cast<uint32_t*>(base + x * MG_COL_BYTES + t * 36);
+        w[0] = w0, w[1] = w1, w[2] = w2, w[3] = w0, w[4] = w1, w[5] = w2, w[6] = w0, w[7] = w1, w[8] = w2;
+    }
+}
+
 // the top bar into rows 0..3 of `base` (a column start is 4-byte aligned: 12 bytes = three words per column)
 template <class Ctx>
 MG_HD void mg_ss_draw_bar(Ctx& c, uint8_t* base, const MgSSDrawK& k, const MgSSFrame& f) {
@@ -449,8 +464,7 @@ MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, cons
     } else {
         uint32_t c_even, c_odd;
         mg_ss_bg_colours(f.bg_kind, 0, c_even, c_odd);
-        for (int unit = c.lane; unit < 2 * MG_W; unit += c.nl)
-            mg_ss_bg_run(base, unit >> 1, (unit & 1) ? MG_W / 2 : 0, (unit & 1) ? MG_W - 1 : MG_W / 2 - 1, c_even, c_odd);
+        mg_ss_fill_bg(c, base, c_even, c_odd);
         c.sync();
         for (int li = 1; li < k.n_layers; ++li)
             if (k.layers[li] != 1) mg_ss_draw_layer(c, base, a, k, f, k.layers[li]);
@@ -507,26 +521,35 @@ MG_HD void mg_ss_masked_copy(Ctx& c, uint8_t* out, const MgSSWarpMem* wm, const 
         for (int i = c.lane; i < MG_SS_CHUNKS; i += c.nl) c.store16(dst + i, src[i], stream);
         return;
     }
-    for (int i = c.lane; i < MG_SS_CHUNKS; i += c.nl) {
-        // chunk i = bytes 16 i .. 16 i + 15 = pixels p0 .. p0 + 5, p0 = 16 i / 3 = 5 i + i / 3, starting `phase`
-        // = 16 i % 3 = i % 3 bytes into pixel p0
-        const unsigned q3 = ((unsigned)i * 43691u) >> 17, phase = (unsigned)i - 3u * q3, p0 = 5u * (unsigned)i + q3;
-        const unsigned w = p0 >> 5, sh = p0 & 31u;
-        const uint32_t v = c.funnel_r(wm->lit[w], wm->lit[w + 1], sh);  // 6 lit bits from the flat pixel bitmap
-        MgVec16 m = t->mask[phase][(int)(v & 63u)], b = src[i], o;
-        if (alpha == 255) {
-            o.x = b.x & m.x, o.y = b.y & m.y, o.z = b.z & m.z, o.w = b.w & m.w;
-        } else {
-            const uint8_t* lut = wm->dimlut;
-            uint32_t bw[4] = {b.x, b.y, b.z, b.w}, mw[4] = {m.x, m.y, m.z, m.w}, ow[4];
-            for (int q = 0; q < 4; ++q) {
-                uint32_t dm = (uint32_t)lut[bw[q] & 255u] | ((uint32_t)lut[(bw[q] >> 8) & 255u] << 8) |
-                              ((uint32_t)lut[(bw[q] >> 16) & 255u] << 16) | ((uint32_t)lut[bw[q] >> 24] << 24);
-                ow[q] = (bw[q] & mw[q]) | (dm & ~mw[q]);
+    // four chunks per lane in flight: all loads first, then the stores (the loop is latency-, not issue-bound)
+    for (int i0 = c.lane; i0 < MG_SS_CHUNKS; i0 += 4 * c.nl) {
+        MgVec16 o[4];
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * c.nl;
+            if (i >= MG_SS_CHUNKS) break;
+            // chunk i = bytes 16 i .. 16 i + 15 = pixels p0 .. p0 + 5, p0 = 16 i / 3 = 5 i + i / 3, starting `phase`
+            // = 16 i % 3 = i % 3 bytes into pixel p0
+            const unsigned q3 = ((unsigned)i * 43691u) >> 17, phase = (unsigned)i - 3u * q3, p0 = 5u * (unsigned)i + q3;
+            const unsigned w = p0 >> 5, sh = p0 & 31u;
+            const uint32_t v = c.funnel_r(wm->lit[w], wm->lit[w + 1], sh);  // 6 lit bits from the flat pixel bitmap
+            const MgVec16 m = t->mask[phase][(int)(v & 63u)], b = src[i];
+            if (alpha == 255) {
+                o[u].x = b.x & m.x, o[u].y = b.y & m.y, o[u].z = b.z & m.z, o[u].w = b.w & m.w;
+            } else {
+                const uint8_t* lut = wm->dimlut;
+                uint32_t bw[4] = {b.x, b.y, b.z, b.w}, mw[4] = {m.x, m.y, m.z, m.w}, ow[4];
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t dm = (uint32_t)lut[bw[q] & 255u] | ((uint32_t)lut[(bw[q] >> 8) & 255u] << 8) |
+                                  ((uint32_t)lut[(bw[q] >> 16) & 255u] << 16) | ((uint32_t)lut[bw[q] >> 24] << 24);
+                    ow[q] = (bw[q] & mw[q]) | (dm & ~mw[q]);
+                }
+                o[u].x = ow[0], o[u].y = ow[1], o[u].z = ow[2], o[u].w = ow[3];
             }
-            o.x = ow[0], o.y = ow[1], o.z = ow[2], o.w = ow[3];
         }
-        c.store16(dst + i, o, stream);
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * c.nl;
+            if (i < MG_SS_CHUNKS) c.store16(dst + i, o[u], stream);
+        }
     }
 }
 
@@ -542,7 +565,9 @@ MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDraw
     // the reference's default order: bg, coins, exit, agent, SPOT, bar
     const bool simple = spot_li == k.n_layers - 2 && bar_li == k.n_layers - 1;
     // 1. every layer but the spotlight layer (kept across frames, patched where it changed)
+    c.stamp(8);
     mg_ss_update_base(c, wm, a, k, f, spot_li, simple);
+    c.stamp(9);
     // 2. which pixels stay undimmed: the colour-keyed discs, and whatever is painted above the spotlight layer
     if (f.alpha != 0) {
         mg_ss_build_lit(c, wm, a, f, bar_li > spot_li ? tables->bar_lit : nullptr);
@@ -574,7 +599,9 @@ MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDraw
     }
     c.sync();
     // 3. frame = lit ? base : base dimmed by alpha (SDL: d + trunc((0 - d) * A / 255))
+    c.stamp(10);
     mg_ss_masked_copy(c, out, wm, tables, f.alpha, stream);
+    c.stamp(11);
     uint8_t* buf = out;
     // 3b. black_background: white 1-px outlines on the spotlight surface (pygame_assets.py:112-113). An outline
     //     pixel survives unless a LATER spotlight's disc is drawn over it; it is blended like any non-key pixel:

@@ -99,6 +99,10 @@ struct MgWarpCtx {
     int lane, nl;
     uint32_t bar, phase;
     uint64_t policy;  // L2 evict-first cache policy
+    uint64_t* trow;   // this env's trace row (mg_step_io.trace) or nullptr
+    __device__ __forceinline__ void stamp(int col) {
+        if (trow && lane == 0) trow[col] = mg_now();
+    }
     __device__ __forceinline__ void sync() { __syncwarp(); }
     // 128-bit store to global memory; `stream` = L2 evict-first (the frame is not re-read soon)
     __device__ __forceinline__ void store16(MgVec16* p, const MgVec16& v, bool stream) {
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(320, 1)
     uint64_t tr0 = 0, tr1 = 0, tr2 = 0;
     if (tracing) tr0 = mg_now();
     MgAssetView view = mg_asset_view(assets);
-    MgWarpCtx ctx{lane, 32, mg_smem_u32(bar), 0u, mg_policy_evict_first()};
+    MgWarpCtx ctx{lane, 32, mg_smem_u32(bar), 0u, mg_policy_evict_first(), nullptr};
     if (lane == 0) mg_mbar_init(ctx.bar, 1);
     __syncwarp();
     const int total_warps = gridDim.x * nwarps;
@@ -216,6 +220,7 @@ __global__ void __launch_bounds__(320, 1)
         for (int t = 0; t < T; ++t) {
             const int a0 = (int)act0, a1 = (int)act1;
             uint64_t* trow = tracing ? q.io.trace + (size_t)env * MG_TRACE_COLS : nullptr;
+            ctx.trow = trow;
             if (trow && lane == 0) {
                 unsigned smid;
                 asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));

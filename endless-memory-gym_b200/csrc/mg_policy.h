@@ -171,9 +171,6 @@ struct SSPolicy {
     typedef MgSSState State;
     typedef MgSSFrame Frame;
     static MG_HD const double* trig(const MgAssetView& a) { return (const double*)(a.base + a.hdr->trig_off); }
-    static MG_HD void reset_env(const K& k, const MgAssetView& a, State& s, Frame& f, double*) {
-        mg_ss_reset_env(k, trig(a), s, f);
-    }
 
     // Same control flow as mg_env_logic, but the step is split A (one lane) / B (one lane per spotlight) /
     // C (one lane): spotlight motion + hit tests are the only per-step work that grows with the scene.
@@ -184,6 +181,10 @@ struct SSPolicy {
         double* const reward_out = q.io.reward + (size_t)t * q.rew_stride + env;
         uint8_t* const done_out = q.io.done + (size_t)t * q.done_stride + env;
         double* const info_out = q.io.info + (size_t)t * q.info_stride + MG_INFO_COLS * (size_t)env;
+        // the sampler's row masks borrow the base buffer: a reset rebuilds the base anyway
+        MgSSWarpMem* wm = reinterpret_cast<MgSSWarpMem*>(sc.warp);
+        MgSSSampler& g = *reinterpret_cast<MgSSSampler*>(wm->base);
+        MgSSResetTmp& rt = *reinterpret_cast<MgSSResetTmp*>(wm->base + sizeof(MgSSSampler));
         if (c.lane == 0) {
             job.nframes = 0;
             tmp.action = 0;
@@ -198,9 +199,7 @@ struct SSPolicy {
                         s.rng.buf = 0;
                         s.rng.has_buf = 0;
                     }
-                    mg_ss_reset_env(k, trig(a), s, fr[0]);
-                    job.nframes = 1;
-                    job.to_final[0] = 0;
+                    tmp.action = 1;
                 }
             } else if (!s.live) {  // finished (or never reset): the step is ignored
                 *reward_out = 0.0;
@@ -211,6 +210,16 @@ struct SSPolicy {
             }
         }
         c.sync();
+        if (tmp.action == 1) {
+            if (c.lane == 0) wm->desc.valid = 0;
+            mg_ss_reset_env(c, k, s, fr[0], g, rt);
+            if (c.lane == 0) {
+                job.nframes = 1;
+                job.to_final[0] = 0;
+            }
+            c.sync();
+            return;
+        }
         if (tmp.action != 2) return;
         mg_ss_step_b(c, k, trig(a), s, tmp, fr[0]);
         c.sync();
@@ -221,16 +230,30 @@ struct SSPolicy {
             *done_out = done ? 1 : 0;
             job.nframes = 1;
             job.to_final[0] = 0;
+            tmp.action = 0;
             if (done && (q.io.flags & MG_FLAG_AUTORESET)) {
-                int at = 0;
-                if (q.io.final_obs) {  // terminal frame -> final_obs, first frame of the next episode -> obs
-                    job.to_final[0] = 1;
-                    at = 1;
-                }
-                mg_ss_reset_env(k, trig(a), s, fr[at]);
-                job.to_final[at] = 0;
-                job.nframes = at + 1;
+                tmp.action = 3;  // auto-reset: every lane joins the cooperative reset below
+                if (q.io.final_obs) job.to_final[0] = 1;  // terminal frame -> final_obs, next episode's first -> obs
             }
+        }
+        c.sync();
+        if (tmp.action == 3) {
+            // the terminal frame (if requested) must leave before the base buffer is borrowed by the sampler:
+            // it is emitted here, out of order with respect to the generic frame loop
+            const int at = q.io.final_obs ? 1 : 0;
+            if (at) {
+                emit(c, q.io.final_obs + (size_t)env * MG_FRAME_BYTES, a, k, fr[0], sc, false);
+                c.sync();
+            }
+            if (c.lane == 0) wm->desc.valid = 0;
+            mg_ss_reset_env(c, k, s, fr[at], g, rt);
+            if (c.lane == 0) {
+                // frame 0 (terminal) has already been written: hand only the reset frame to the frame loop
+                if (at) fr[0] = fr[1];
+                job.to_final[0] = 0;
+                job.nframes = 1;
+            }
+            c.sync();
         }
     }
 

@@ -39,7 +39,6 @@ struct MgSSK {
 // ---- GridPositionSampler: 84 rows x 84-bit occupancy masks ------------------------------------------
 struct MgSSSampler {
     uint64_t lo[MG_W], hi[MG_W];  // column x of row y is blocked: bit x of (lo | hi << 64)
-    int32_t free_total;
 };
 
 MG_HD int mg_popc64(uint64_t v) {
@@ -48,63 +47,6 @@ MG_HD int mg_popc64(uint64_t v) {
 #else
     return __builtin_popcountll(v);
 #endif
-}
-
-MG_HD void mg_ss_sampler_reset(MgSSSampler& g) {
-    for (int y = 0; y < MG_W; ++y) g.lo[y] = g.hi[y] = 0;
-    g.free_total = MG_W * MG_W;
-}
-
-// block_spawn_position: cells with dx^2 + dy^2 < r^2 become unavailable
-MG_HD void mg_ss_block(MgSSSampler& g, int x, int y, int r) {
-    int y0 = y - r + 1 < 0 ? 0 : y - r + 1, y1 = y + r - 1 > MG_W - 1 ? MG_W - 1 : y + r - 1;
-    for (int yy = y0; yy <= y1; ++yy) {
-        int dy = yy - y, rem = r * r - dy * dy - 1;  // need dx^2 <= rem
-        int h = (int)sqrt((double)rem);
-        while (h * h > rem) --h;
-        while ((h + 1) * (h + 1) <= rem) ++h;
-        int xa = x - h < 0 ? 0 : x - h, xb = x + h > MG_W - 1 ? MG_W - 1 : x + h;
-        if (xa > xb) continue;
-        // bits xa..xb of the 128-bit row mask
-        uint64_t mlo = 0, mhi = 0;
-        if (xa < 64) {
-            int b = xb < 63 ? xb : 63;
-            mlo = (~0ull >> (63 - (b - xa))) << xa;
-        }
-        if (xb >= 64) {
-            int a2 = xa > 64 ? xa - 64 : 0, b2 = xb - 64;
-            mhi = (~0ull >> (63 - (b2 - a2))) << a2;
-        }
-        int before = mg_popc64(g.lo[yy]) + mg_popc64(g.hi[yy]);
-        g.lo[yy] |= mlo;
-        g.hi[yy] |= mhi;
-        g.free_total -= mg_popc64(g.lo[yy]) + mg_popc64(g.hi[yy]) - before;
-    }
-}
-
-// sample(block_radius): the cell_id-th free cell in row-major order, then block a disc around it.
-// Returns false when no cell is free (the reference raises from integers(0, 0)).
-MG_HD bool mg_ss_sample(MgSSSampler& g, MgRng& r, int block_radius, int& x, int& y) {
-    if (g.free_total <= 0) return false;
-    int k = (int)mg_integers(r, 0, g.free_total);
-    int row = 0;
-    for (; row < MG_W; ++row) {
-        int fr = MG_W - mg_popc64(g.lo[row]) - mg_popc64(g.hi[row]);
-        if (k < fr) break;
-        k -= fr;
-    }
-    int col = 0;
-    for (;; ++col) {
-        bool blocked = col < 64 ? ((g.lo[row] >> col) & 1ull) : ((g.hi[row] >> (col - 64)) & 1ull);
-        if (!blocked) {
-            if (k == 0) break;
-            --k;
-        }
-    }
-    x = col;
-    y = row;
-    mg_ss_block(g, x, y, block_radius);
-    return true;
 }
 
 // ---- spotlights -------------------------------------------------------------------------------------
@@ -185,71 +127,175 @@ MG_HD uint8_t mg_ss_bg_kind(const MgSSState& s, int red) {
     return st == 0 ? (uint8_t)(red ? 1 : 0) : (st == 1 ? (uint8_t)2 : (uint8_t)3);
 }
 
+// ---- cooperative sampler: the 84 rows are spread over the lanes, one lane does the RNG draw and the scan ----
+struct MgSSResetTmp {
+    int32_t x, y, ok, nc;
+    int32_t part[32];  // free cells of rows 3 l .. 3 l + 2
+};
+
+template <class Ctx>
+MG_HD void mg_ss_block_coop(Ctx& c, MgSSSampler& g, int x, int y, int r) {
+    int y0 = y - r + 1 < 0 ? 0 : y - r + 1, y1 = y + r - 1 > MG_W - 1 ? MG_W - 1 : y + r - 1;
+    for (int yy = y0 + c.lane; yy <= y1; yy += c.nl) {
+        int dy = yy - y, rem = r * r - dy * dy - 1;  // need dx^2 <= rem
+        int h = (int)sqrt((double)rem);
+        while (h * h > rem) --h;
+        while ((h + 1) * (h + 1) <= rem) ++h;
+        int xa = x - h < 0 ? 0 : x - h, xb = x + h > MG_W - 1 ? MG_W - 1 : x + h;
+        if (xa > xb) continue;
+        uint64_t mlo = 0, mhi = 0;
+        if (xa < 64) {
+            int b = xb < 63 ? xb : 63;
+            mlo = (~0ull >> (63 - (b - xa))) << xa;
+        }
+        if (xb >= 64) {
+            int a2 = xa > 64 ? xa - 64 : 0, b2 = xb - 64;
+            mhi = (~0ull >> (63 - (b2 - a2))) << a2;
+        }
+        g.lo[yy] |= mlo;
+        g.hi[yy] |= mhi;
+    }
+}
+
+// the k-th (0-based) clear bit among bits 0..83 of (lo | hi << 64)
+MG_HD int mg_ss_kth_free(uint64_t lo, uint64_t hi, int k) {
+    uint64_t flo = ~lo, fhi = ~hi & ((1ull << (MG_W - 64)) - 1ull);
+    int base = 0;
+    uint64_t w = flo;
+    int n = mg_popc64(flo);
+    if (k >= n) {
+        k -= n;
+        w = fhi;
+        base = 64;
+    }
+    for (int half = 32; half >= 1; half >>= 1) {  // binary search on popcounts
+        uint64_t lowmask = (1ull << half) - 1ull;
+        int cnt = mg_popc64(w & lowmask);
+        if (k >= cnt) {
+            k -= cnt;
+            w >>= half;
+            base += half;
+        }
+    }
+    return base;
+}
+
+template <class Ctx>
+MG_HD void mg_ss_sample_coop(Ctx& c, MgSSSampler& g, MgSSState& s, MgSSResetTmp& rt, int block_radius) {
+    if (c.lane < 28) {  // 28 lanes x 3 rows
+        int n = 0;
+        for (int q = 0; q < 3; ++q) n += MG_W - mg_popc64(g.lo[3 * c.lane + q]) - mg_popc64(g.hi[3 * c.lane + q]);
+        rt.part[c.lane] = n;
+    }
+    if (c.nl == 1)  // a single lane runs the whole "warp" (host harness)
+        for (int l = 1; l < 28; ++l) {
+            int n = 0;
+            for (int q = 0; q < 3; ++q) n += MG_W - mg_popc64(g.lo[3 * l + q]) - mg_popc64(g.hi[3 * l + q]);
+            rt.part[l] = n;
+        }
+    c.sync();
+    if (c.lane == 0) {
+        int total = 0;
+        for (int l = 0; l < 28; ++l) total += rt.part[l];
+        if (total <= 0 || !rt.ok) {
+            rt.ok = 0;
+            rt.x = rt.y = 0;
+        } else {
+            int kk = (int)mg_integers(s.rng, 0, total);  // cell_id = rng.integers(0, len(spawn_area))
+            int l = 0;
+            for (; l < 27 && kk >= rt.part[l]; ++l) kk -= rt.part[l];
+            int row = 3 * l;
+            for (;; ++row) {
+                int fr = MG_W - mg_popc64(g.lo[row]) - mg_popc64(g.hi[row]);
+                if (kk < fr) break;
+                kk -= fr;
+            }
+            rt.x = mg_ss_kth_free(g.lo[row], g.hi[row], kk);
+            rt.y = row;
+        }
+    }
+    c.sync();
+    if (rt.ok) mg_ss_block_coop(c, g, rt.x, rt.y, block_radius);
+    c.sync();
+}
+
 // reset(): RNG draw order — rotation; agent cell + 2 offsets; per initial spotlight radius, speed, 3 angles;
-// num_coins; per coin cell + 2 offsets; exit cell + 2 offsets (searing_spotlights.py:354-414)
-MG_HD_NOINLINE void mg_ss_reset_env(const MgSSK& k, const double* trig, MgSSState& s, MgSSFrame& f) {
-    (void)trig;
-    MgRng r = s.rng;
-    s.t = 0;
-    s.ep_len = 0;
-    s.ep_reward = 0.0;
-    if (k.p.hide_chessboard) s.bg_blue = s.bg_red = 1;
-    MgSSSampler g;
-    mg_ss_sampler_reset(g);
-    s.last_a0 = s.last_a1 = 0;
-    s.rot = (uint8_t)mg_integers(r, 0, 8);  // choice([0, 45, ..., 315])
-    bool ok = true;
-    int x, y;
+// num_coins; per coin cell + 2 offsets; exit cell + 2 offsets (searing_spotlights.py:354-414).
+// Called by every lane of the warp; `g` / `rt` are per-warp scratch.
+template <class Ctx>
+MG_HD void mg_ss_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, MgSSSampler& g, MgSSResetTmp& rt) {
+    for (int y = c.lane; y < MG_W; y += c.nl) g.lo[y] = g.hi[y] = 0;
+    if (c.lane == 0) {
+        s.t = 0;
+        s.ep_len = 0;
+        s.ep_reward = 0.0;
+        if (k.p.hide_chessboard) s.bg_blue = s.bg_red = 1;
+        s.last_a0 = s.last_a1 = 0;
+        s.rot = (uint8_t)mg_integers(s.rng, 0, 8);  // choice([0, 45, ..., 315])
+        rt.ok = 1;
+    }
+    c.sync();
     if (k.p.sample_agent_position) {
-        ok = mg_ss_sample(g, r, 28, x, y);
-        x += (int)mg_integers(r, 2, 4);
-        y += (int)mg_integers(r, 2, 4);
+        mg_ss_sample_coop(c, g, s, rt, 28);
     } else {
-        x = y = MG_W / 2;
-        mg_ss_block(g, x, y, 21);
+        if (c.lane == 0) rt.x = rt.y = MG_W / 2;
+        c.sync();
+        mg_ss_block_coop(c, g, MG_W / 2, MG_W / 2, 21);
+        c.sync();
     }
-    s.cx = (int16_t)x;  // not clamped (searing_spotlights.py:364-369)
-    s.cy = (int16_t)y;
-    s.hp = k.p.agent_health;
-    s.red_w_max = 0;
-    s.bar_c0 = s.bar_c1 = 0;
-    s.coin_bar = 0;
-    s.last_reward = 0.0;
-    s.spawns_left = k.p.num_spawns;
-    s.spawn_timer = 0;
-    int a0 = k.p.light_threshold < 0 ? 0 : (k.p.light_threshold > 255 ? 255 : k.p.light_threshold);
-    s.alpha = (uint8_t)(k.p.light_dim_off_duration > 0 ? 0 : a0);
-    s.n_spots = 0;
-    for (int i = 0; i < k.p.initial_spawns; ++i) mg_ss_new_spot(k, r, s.spots[s.n_spots++]);
-    s.coins_collected = 0;
-    int nc = mg_choice(r, k.p.num_coins);
-    s.num_coins = (uint8_t)nc;
-    s.n_coins = 0;
-    for (int c = 0; c < nc && ok; ++c) {
-        ok = mg_ss_sample(g, r, 21, x, y);
-        x += (int)mg_integers(r, 2, 4);
-        y += (int)mg_integers(r, 2, 4);
-        mg_ss_clamp_spawn(k, x, y);
-        s.coins[s.n_coins][0] = (int16_t)x;
-        s.coins[s.n_coins][1] = (int16_t)y;
-        s.n_coins++;
+    if (c.lane == 0) {
+        int x = rt.x, y = rt.y;
+        if (k.p.sample_agent_position) {
+            x += (int)mg_integers(s.rng, 2, 4);
+            y += (int)mg_integers(s.rng, 2, 4);
+        }
+        s.cx = (int16_t)x;  // not clamped (searing_spotlights.py:364-369)
+        s.cy = (int16_t)y;
+        s.hp = k.p.agent_health;
+        s.red_w_max = 0;
+        s.bar_c0 = s.bar_c1 = 0;
+        s.coin_bar = 0;
+        s.last_reward = 0.0;
+        s.spawns_left = k.p.num_spawns;
+        s.spawn_timer = 0;
+        int a0 = k.p.light_threshold < 0 ? 0 : (k.p.light_threshold > 255 ? 255 : k.p.light_threshold);
+        s.alpha = (uint8_t)(k.p.light_dim_off_duration > 0 ? 0 : a0);
+        s.n_spots = 0;
+        for (int i = 0; i < k.p.initial_spawns; ++i) mg_ss_new_spot(k, s.rng, s.spots[s.n_spots++]);
+        s.coins_collected = 0;
+        rt.nc = mg_choice(s.rng, k.p.num_coins);
+        s.num_coins = (uint8_t)rt.nc;
+        s.n_coins = 0;
     }
-    if (ok) {
-        ok = mg_ss_sample(g, r, 21, x, y);
-        x += (int)mg_integers(r, 2, 4);
-        y += (int)mg_integers(r, 2, 4);
-        mg_ss_clamp_spawn(k, x, y);
-        s.exit_x = (int16_t)x;
-        s.exit_y = (int16_t)y;
+    c.sync();
+    const int nc = rt.nc;
+    for (int q = 0; q <= nc; ++q) {  // the coins, then the exit
+        mg_ss_sample_coop(c, g, s, rt, 21);
+        if (c.lane == 0 && rt.ok) {
+            int x = rt.x + (int)mg_integers(s.rng, 2, 4);
+            int y = rt.y + (int)mg_integers(s.rng, 2, 4);
+            mg_ss_clamp_spawn(k, x, y);
+            if (q < nc) {
+                s.coins[s.n_coins][0] = (int16_t)x;
+                s.coins[s.n_coins][1] = (int16_t)y;
+                s.n_coins++;
+            } else {
+                s.exit_x = (int16_t)x;
+                s.exit_y = (int16_t)y;
+            }
+        }
+        c.sync();
     }
-    s.exit_open = 0;
-    if (k.p.black_background) s.bg_blue = 2;
-    s.live = ok ? 1 : 0;  // sampler exhausted: the reference raises; here the env stays finished
-    s.rng = r;
-    mg_ss_frame_common(s, 0, f);  // the reset frame draws get_rotated_sprite(0)
-    f.n_discs = 0;
-    f.red_now = 0;
-    f.bg_kind = mg_ss_bg_kind(s, 0);
+    if (c.lane == 0) {
+        s.exit_open = 0;
+        if (k.p.black_background) s.bg_blue = 2;
+        s.live = rt.ok ? 1 : 0;  // sampler exhausted: the reference raises; here the env stays finished
+        mg_ss_frame_common(s, 0, f);  // the reset frame draws get_rotated_sprite(0)
+        f.n_discs = 0;
+        f.red_now = 0;
+        f.bg_kind = mg_ss_bg_kind(s, 0);
+    }
+    c.sync();
 }
 
 // step(), split so that the spotlights (the only per-step work that grows with the scene) advance in
@@ -426,15 +472,3 @@ MG_HD_NOINLINE bool mg_ss_step_c(const MgSSK& k, MgSSState& s, const MgSSStepTmp
     return done;
 }
 
-// the whole step on one lane (A, B, C in sequence)
-struct MgSerialCtx {
-    int lane = 0, nl = 1;
-};
-MG_HD bool mg_ss_step_env(const MgSSK& k, const double* trig, MgSSState& s, int a0, int a1, double& reward_out,
-                          double* info, MgSSFrame& f) {
-    MgSSStepTmp tmp;
-    MgSerialCtx c;
-    mg_ss_step_a(k, s, a0, a1, tmp);
-    mg_ss_step_b(c, k, trig, s, tmp, f);
-    return mg_ss_step_c(k, s, tmp, reward_out, info, f);
-}

@@ -45,7 +45,7 @@ extern "C" {
 #define MG_SCREEN 84
 #define MG_OBS_BYTES (84 * 84 * 3) /* 21168 bytes per env, [x][y][c] */
 #define MG_INFO_COLS 8             /* doubles per env in the info matrix */
-#define MG_TRACE_COLS 8
+#define MG_TRACE_COLS 16
 #define MG_MAX_CHOICES 16          /* max length of a list-valued reset option */
 #define MG_MM_MAX_COMMANDS 152     /* capacity of the per-env command list */
 #define MG_MM_STATE_BYTES 256      /* one env record (Mortar Mayhem family) */
@@ -171,7 +171,7 @@ typedef struct mg_step_io {
     uint32_t warps_per_cta; /* 0 = library default; tuning knob (frame buffers resident per SM) */
     uint64_t* trace;        /* nullable: [n][MG_TRACE_COLS] uint64, per-env phase timestamps (globaltimer ns):   */
                             /* 0 kernel entry, 1 prologue done, 2 dependency wait done, 3 record in smem,      */
-                            /* 4 logic done, 5 frame composed, 6 bulk store issued, 7 SM id                      */
+                            /* 4 logic done, 5 frame composed, 6 bulk store issued, 7 SM id, 8.. env-type specific  */
 } mg_step_io;
 
 /* A whole rollout in one launch: T = n_steps consecutive steps with given actions (the reference's bench.py

@@ -41,12 +41,12 @@ acts = torch.randint(0, env.spec_.action_nvec[0], (T,) + tuple(env._actions_dev.
 ring = torch.empty((6, n, 84, 84, 3), dtype=torch.uint8, device=dev)
 rew = torch.empty((T, n), dtype=torch.float64, device=dev)
 dn = torch.empty((T, n), dtype=torch.bool, device=dev)
-trace = torch.zeros((2, n, 8), dtype=torch.int64, device=dev)
-env.rollout(acts, ring, rew, dn)
+trace = torch.zeros((2, n, 16), dtype=torch.int64, device=dev)
+env.step_many(acts, ring, rew, dn)
 env._many_ios[T - 2].trace = trace[0].data_ptr()
 env._many_ios[T - 1].trace = trace[1].data_ptr()
 for _ in range(3):
-    env.rollout(acts, ring, rew, dn)
+    env.step_many(acts, ring, rew, dn)
 torch.cuda.synchronize()
 tr = trace.cpu().numpy().astype(np.int64)
 a, b = tr[0], tr[1]
@@ -58,6 +58,10 @@ names = ["entry->prologue", "prologue->depwait", "depwait->record", "record->log
 for k, nm in enumerate(names):
     d = (b[:, k + 1] - b[:, k]) / 1e3
     print(f"  {nm:20s} mean {d.mean():7.2f} us  p50 {np.median(d):7.2f}  p95 {np.percentile(d, 95):7.2f}  max {d.max():7.2f}")
+if b[:, 8].any():
+    for nm, i0, i1 in (("emit: update base", 8, 9), ("emit: lit + lut", 9, 10), ("emit: masked copy", 10, 11)):
+        d = (b[:, i1] - b[:, i0]) / 1e3
+        print(f"  {nm:20s} mean {d.mean():7.2f} us  p50 {np.median(d):7.2f}  p95 {np.percentile(d, 95):7.2f}  max {d.max():7.2f}")
 # per-warp chains: envs sharing a warp are n/total_warps apart in issue order
 t_issue = np.sort(b[:, 6] - b[:, 2].min()) / 1e3
 for q in (1, 10, 25, 50, 75, 90, 99, 100):
