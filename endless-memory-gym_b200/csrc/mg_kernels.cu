@@ -100,10 +100,17 @@ struct MgWarpCtx {
     uint32_t bar, phase;
     uint64_t policy;  // L2 evict-first cache policy
     uint64_t* trow;   // this env's trace row (mg_step_io.trace) or nullptr
+    int bar_id;       // named barrier of this team (teams of more than one warp), 0 = a single warp
     __device__ __forceinline__ void stamp(int col) {
         if (trow && lane == 0) trow[col] = mg_now();
     }
-    __device__ __forceinline__ void sync() { __syncwarp(); }
+    // all threads of the team that owns the env (one warp, or kTeamWarps warps on a named barrier)
+    __device__ __forceinline__ void sync() {
+        if (bar_id == 0)
+            __syncwarp();
+        else
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nl) : "memory");
+    }
     // 128-bit store to global memory; `stream` = L2 evict-first (the frame is not re-read soon)
     __device__ __forceinline__ void store16(MgVec16* p, const MgVec16& v, bool stream) {
         if (stream)
@@ -118,7 +125,7 @@ struct MgWarpCtx {
     // whole-frame template -> this warp's frame buffer, by TMA
     __device__ __forceinline__ void copy_frame(uint8_t* dst, const uint8_t* src) {
         mg_fence_proxy_async();  // earlier generic-proxy accesses to dst are ordered before the async write
-        __syncwarp();
+        sync();
         if (lane == 0) {
             mg_mbar_expect_tx(bar, MG_FRAME_BYTES);
             mg_bulk_load(dst, src, MG_FRAME_BYTES, bar);
@@ -129,23 +136,26 @@ struct MgWarpCtx {
 };
 
 // ---- the kernel ----------------------------------------------------------------------------------
+// A "team" = the threads that own one env at a time: one warp, or P::kTeamWarps warps on a named barrier for
+// env types whose per-frame work is instruction-bound (more warps per frame buffer hide more latency).
 template <class P>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(P::kMaxThreads, 1)
     mg_env_kernel(const __grid_constant__ typename P::K k, const __grid_constant__ MgKIO q,
                   const uint8_t* __restrict__ assets, uint8_t* __restrict__ state) {
     typedef typename P::State State;
     typedef typename P::Frame Frame;
+    constexpr int kTeam = 32 * P::kTeamWarps;          // threads per team
     constexpr int kStateBytes = (int)sizeof(State);
-    constexpr int kWords = kStateBytes / 8;           // 8-byte words per record
-    constexpr int kPerLane = (kWords + 31) / 32;       // words each lane moves
+    constexpr int kWords = kStateBytes / 8;             // 8-byte words per record
+    constexpr int kPerLane = (kWords + kTeam - 1) / kTeam;  // words each thread moves
     constexpr int kSlot = ((kStateBytes + 2 * (int)sizeof(Frame) + (int)sizeof(MgFrameJob) + 16 + 127) / 128) * 128;
     extern __shared__ __align__(128) uint8_t smem[];
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    uint8_t* buf = smem + (size_t)warp * P::kFrameBuf;
-    uint8_t* slot = smem + (size_t)nwarps * P::kFrameBuf + (size_t)warp * kSlot;
-    uint8_t* wextra = smem + (size_t)nwarps * (P::kFrameBuf + kSlot) + (size_t)warp * P::kWarpExtra;
-    uint8_t* cextra = smem + (size_t)nwarps * (P::kFrameBuf + kSlot + P::kWarpExtra);
+    const int lane = threadIdx.x % kTeam, team = threadIdx.x / kTeam, nteams = blockDim.x / kTeam;
+    uint8_t* buf = smem + (size_t)team * P::kFrameBuf;
+    uint8_t* slot = smem + (size_t)nteams * P::kFrameBuf + (size_t)team * kSlot;
+    uint8_t* wextra = smem + (size_t)nteams * (P::kFrameBuf + kSlot) + (size_t)team * P::kWarpExtra;
+    uint8_t* cextra = smem + (size_t)nteams * (P::kFrameBuf + kSlot + P::kWarpExtra);
     uint8_t* stage = cextra + P::kCtaExtra;
     const MgScratch scratch{wextra, cextra};
     State* st = reinterpret_cast<State*>(slot);
@@ -159,13 +169,12 @@ __global__ void __launch_bounds__(320, 1)
     uint64_t tr0 = 0, tr1 = 0, tr2 = 0;
     if (tracing) tr0 = mg_now();
     MgAssetView view = mg_asset_view(assets);
-    MgWarpCtx ctx{lane, 32, mg_smem_u32(bar), 0u, mg_policy_evict_first(), nullptr};
+    MgWarpCtx ctx{lane, kTeam, mg_smem_u32(bar), 0u, mg_policy_evict_first(), nullptr, P::kTeamWarps > 1 ? team + 1 : 0};
     if (lane == 0) mg_mbar_init(ctx.bar, 1);
-    __syncwarp();
-    const int total_warps = gridDim.x * nwarps;
-    int env = warp * gridDim.x + blockIdx.x;  // consecutive envs on different SMs: remainders spread evenly
+    const int total_teams = gridDim.x * nteams;
+    int env = team * gridDim.x + blockIdx.x;  // consecutive envs on different SMs: remainders spread evenly
     const bool active = env < q.n;
-    if (P::kFrameBuf && active && lane == 0) {  // background template -> this warp's frame buffer (TMA, L2-resident source)
+    if (P::kFrameBuf && active && lane == 0) {  // background template -> this team's frame buffer (TMA, L2-resident source)
         mg_mbar_expect_tx(ctx.bar, MG_FRAME_BYTES);
         mg_bulk_load(buf, view.tmpl[0], MG_FRAME_BYTES, ctx.bar);
     }
@@ -196,7 +205,7 @@ __global__ void __launch_bounds__(320, 1)
         const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)env * kStateBytes);
 #pragma unroll
         for (int j = 0; j < kPerLane; ++j)
-            if (lane + 32 * j < kWords) pre[j] = g[lane + 32 * j];
+            if (lane + kTeam * j < kWords) pre[j] = g[lane + kTeam * j];
         if (lane == 0 && stepping) {
             const int64_t* a = q.io.actions + (size_t)env * q.act_dims;
             act0 = a[0];
@@ -210,13 +219,13 @@ __global__ void __launch_bounds__(320, 1)
 
     bool pending = false;  // a bulk store is still reading `buf`; `prev` is the patch to undo afterwards
     Frame prev;
-    for (; env < q.n; env += total_warps) {
+    for (; env < q.n; env += total_teams) {
         uint64_t* s64 = reinterpret_cast<uint64_t*>(st);
 #pragma unroll
         for (int j = 0; j < kPerLane; ++j)
-            if (lane + 32 * j < kWords) s64[lane + 32 * j] = pre[j];
-        __syncwarp();
-        const int nxt = env + total_warps;
+            if (lane + kTeam * j < kWords) s64[lane + kTeam * j] = pre[j];
+        ctx.sync();
+        const int nxt = env + total_teams;
         for (int t = 0; t < T; ++t) {
             const int a0 = (int)act0, a1 = (int)act1;
             uint64_t* trow = tracing ? q.io.trace + (size_t)env * MG_TRACE_COLS : nullptr;
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(320, 1)
                 const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)nxt * kStateBytes);
 #pragma unroll
                 for (int j = 0; j < kPerLane; ++j)
-                    if (lane + 32 * j < kWords) pre[j] = g[lane + 32 * j];
+                    if (lane + kTeam * j < kWords) pre[j] = g[lane + kTeam * j];
                 if (lane == 0 && stepping) {
                     const int64_t* a = q.io.actions + (size_t)nxt * q.act_dims;
                     act0 = a[0];
@@ -246,11 +255,11 @@ __global__ void __launch_bounds__(320, 1)
                 }
             }
             P::logic(ctx, k, q, view, env, t, *st, a0, a1, *job, fr, scratch);
-            __syncwarp();
+            ctx.sync();
             if (trow && lane == 0) trow[4] = mg_now();
             const int nframes = job->nframes;
             for (int fi = 0; fi < nframes; ++fi) {
-                const Frame& f = fr[fi];  // lives in the warp's shared slot until the next logic call
+                const Frame& f = fr[fi];  // lives in the team's shared slot until the next logic call
                 const bool to_final = job->to_final[fi] != 0;
                 uint8_t* dst = to_final ? q.io.final_obs + (size_t)env * MG_FRAME_BYTES
                                         : q.io.obs + (size_t)(t % q.ring_n) * q.obs_stride + (size_t)env * MG_FRAME_BYTES;
@@ -262,13 +271,13 @@ __global__ void __launch_bounds__(320, 1)
                 }
                 if (pending) {
                     if (lane == 0) mg_bulk_wait_read();
-                    __syncwarp();
+                    ctx.sync();
                     P::restore(ctx, buf, view, k, prev, scratch);
-                    __syncwarp();
+                    ctx.sync();
                 }
                 P::compose(ctx, buf, view, k, f, scratch);
-                mg_fence_proxy_async();  // make this lane's patch visible to the async (TMA) proxy
-                __syncwarp();
+                mg_fence_proxy_async();  // make this thread's patch visible to the async (TMA) proxy
+                ctx.sync();
                 if (lane == 0) {
                     if (trow) trow[5] = mg_now();
                     // rollout: the same address is rewritten ring_n steps later (final_obs: at the next done);
@@ -284,13 +293,13 @@ __global__ void __launch_bounds__(320, 1)
                 pending = true;
                 prev = f;
             }
-            __syncwarp();  // job / frame slots are reused by the next step
+            ctx.sync();  // job / frame slots are reused by the next step
         }
         uint64_t* gw = reinterpret_cast<uint64_t*>(state + (size_t)env * kStateBytes);
 #pragma unroll
         for (int j = 0; j < kPerLane; ++j)
-            if (lane + 32 * j < kWords) gw[lane + 32 * j] = s64[lane + 32 * j];
-        __syncwarp();  // record slot is reused by the next env
+            if (lane + kTeam * j < kWords) gw[lane + kTeam * j] = s64[lane + kTeam * j];
+        ctx.sync();  // record slot is reused by the next env
     }
     if (pending && lane == 0) mg_bulk_wait_read();  // shared memory must outlive the bulk read
 }
@@ -343,6 +352,7 @@ static int plan_launch(int n, int wpc_req, int default_wpc, bool balance, MgLaun
         (((int)sizeof(typename P::State) + 2 * (int)sizeof(typename P::Frame) + (int)sizeof(MgFrameJob) + 16 + 127) / 128) * 128;
     const int per_warp = P::kFrameBuf + kSlot + P::kWarpExtra;
     int wmax = 10;
+    while (wmax > 1 && wmax * 32 * P::kTeamWarps > P::kMaxThreads) wmax--;
     while (wmax > 1 && wmax * per_warp + P::kCtaExtra + 16 * 1024 > smem_max) wmax--;  // leave room to stage the assets
     int wpc = wpc_req ? wpc_req : default_wpc;
     if (wpc > wmax) wpc = wmax;
@@ -386,7 +396,7 @@ static int launch_one(const typename P::K& k, const MgKIO& q, const MgLaunchPlan
                       void* stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.ctas);
-    cfg.blockDim = dim3(plan.wpc * 32);
+    cfg.blockDim = dim3(plan.wpc * 32 * P::kTeamWarps);
     cfg.dynamicSmemBytes = plan.smem;
     cfg.stream = (cudaStream_t)stream;
     // programmatic dependent launch: this kernel's prologue (asset staging, template loads) may overlap
@@ -484,6 +494,7 @@ static int launch_rollout(const typename P::K& k, const void* assets, void* stat
     q.io.done = r->done;
     q.io.info = r->info;
     q.io.ground_truth = r->ground_truth;
+    q.io.trace = r->trace;
     q.io.flags = r->flags | MG_FLAG_AUTORESET;  // a rollout without auto-reset would only idle finished envs
     q.mode = MG_MODE_STEP;
     q.n = n;

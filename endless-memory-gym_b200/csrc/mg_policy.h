@@ -93,7 +93,8 @@ struct MgScratch {
 
 struct MMPolicy {
     static constexpr int kWarpExtra = 0, kCtaExtra = 0;
-    static constexpr int kFrameBuf = 21248;      // per-warp TMA frame buffer (MG_FRAME_BYTES rounded up to 128)
+    static constexpr int kTeamWarps = 1, kMaxThreads = 320;
+    static constexpr int kFrameBuf = 21248;      // per-team TMA frame buffer (MG_FRAME_BYTES rounded up to 128)
     static constexpr bool kDirectStore = false;  // frames leave through cp.async.bulk from the frame buffer
     static MG_HD void cta_init(uint8_t*, int, int) {}
     static MG_HD void warp_init(uint8_t*, int) {}
@@ -124,6 +125,7 @@ struct MMPolicy {
 
 struct MPPolicy {
     static constexpr int kWarpExtra = 0, kCtaExtra = 0;
+    static constexpr int kTeamWarps = 1, kMaxThreads = 320;
     static constexpr int kFrameBuf = 21248;
     static constexpr bool kDirectStore = false;
     static MG_HD void cta_init(uint8_t*, int, int) {}
@@ -154,6 +156,7 @@ struct MPPolicy {
 struct SSPolicy {
     static constexpr int kWarpExtra = (int)((sizeof(MgSSWarpMem) + 127) / 128 * 128);
     static constexpr int kCtaExtra = (int)((sizeof(MgSSCtaTables) + 127) / 128 * 128);
+    static constexpr int kTeamWarps = 2, kMaxThreads = 512;  // instruction-bound frames: two warps share one env
     static constexpr int kFrameBuf = 0;         // no staging buffer: the frame is a masked copy of the base buffer
     static constexpr bool kDirectStore = true;  // ... written straight to the observation with 128-bit stores
     static_assert(sizeof(MgSSStepTmp) <= sizeof(((MgSSWarpMem*)0)->step_tmp), "MgSSWarpMem::step_tmp too small");

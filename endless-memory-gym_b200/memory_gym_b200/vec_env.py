@@ -285,6 +285,7 @@ class MemoryGymVecEnv:
         r.ground_truth = self._io.ground_truth
         r.n_steps, r.ring, r.info_per_step = T, obs_out.shape[0], int(info_out is not None)
         r.flags, r.warps_per_cta = L.MG_FLAG_AUTORESET | self._stream_rollout, self.warps_per_cta
+        r.trace = getattr(self, "_trace_ptr", None)
         self._be.rollout(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(), r,
                          self.num_envs, self._be.stream(self.device))
 

@@ -191,6 +191,7 @@ typedef struct mg_rollout_io {
     uint32_t flags;
     uint32_t warps_per_cta; /* 0 = library picks the count that balances envs per warp */
     uint32_t pad0;
+    uint64_t* trace;        /* nullable: [n][MG_TRACE_COLS] phase timestamps of each env's LAST step (see mg_step_io) */
 } mg_rollout_io;
 
 /* ---- assets & seeding (host side) -------------------------------------------------------------- */
