@@ -344,7 +344,7 @@ extern "C" long mg_mm_build_assets(const mg_mm_params* p, int thick_circle_legac
     if (size < 2 || size > 6) return MG_EINVAL;
     Builder b;
     // GridCharacterController is built with SCALE, ignoring agent_scale (mortar_mayhem_grid.py:249)
-    double agent_scale = p->variant == MG_MM_GRID ? SCALE : p->agent_scale;
+    double agent_scale = (p->variant == MG_MM_GRID || p->variant == MG_MM_B_GRID) ? SCALE : p->agent_scale;
     if (!build_agent(b, agent_scale, thick_circle_legacy != 0)) return MG_EINVAL;
     if (!build_icons(b, thick_circle_legacy != 0)) return MG_EINVAL;
     build_arena(b, 0, size, false);
@@ -355,7 +355,8 @@ extern "C" long mg_mm_build_assets(const mg_mm_params* p, int thick_circle_legac
 extern "C" long mg_mp_build_assets(const mg_mp_params* p, void* host_out, size_t capacity) {
     if (!p) return MG_EINVAL;
     Builder b;
-    if (!build_agent(b, p->agent_scale, false)) return MG_EINVAL;
+    // GridCharacterController(SCALE, ...) ignores agent_scale (mystery_path_grid.py:188)
+    if (!build_agent(b, p->variant == MG_MP_GRID ? SCALE : p->agent_scale, false)) return MG_EINVAL;
     if (!build_cross(b)) return MG_EINVAL;
     Surface black(MG_W, MG_W);
     b.add_template(0, black);

@@ -143,7 +143,8 @@ struct MgMPState {
     uint8_t off_path;
     uint8_t cross_on;      // fall_off_surface alpha == 255
     uint8_t live;
-    uint8_t pad[32];
+    int8_t gx, gy;         // MysteryPath-Grid: agent.grid_position
+    uint8_t pad[30];
 };
 
 // ---- Searing Spotlights record (1024 bytes) -----------------------------------------------------

@@ -495,6 +495,7 @@ static int launch_rollout(const typename P::K& k, const void* assets, void* stat
     q.io.info = r->info;
     q.io.ground_truth = r->ground_truth;
     q.io.trace = r->trace;
+    q.io.vector_obs = r->vector_obs;
     q.io.flags = r->flags | MG_FLAG_AUTORESET;  // a rollout without auto-reset would only idle finished envs
     q.mode = MG_MODE_STEP;
     q.n = n;
@@ -510,7 +511,8 @@ static int launch_rollout(const typename P::K& k, const void* assets, void* stat
     return launch_one<P>(k, q, plan, assets, state, stream);
 }
 
-static int mm_act_dims(const mg_mm_params* p) { return p->variant == MG_MM_GRID ? 1 : 2; }
+static int mm_act_dims(const mg_mm_params* p) { return mg_mm_is_grid(p->variant) ? 1 : 2; }
+static int mp_act_dims(const mg_mp_params* p) { return p->variant == MG_MP_GRID ? 1 : 2; }
 
 extern "C" int mg_mm_reset(const mg_mm_params* p, const void* assets, void* state, const uint64_t* rng4,
                            const mg_step_io* io, int n, void* stream) {
@@ -543,7 +545,7 @@ extern "C" int mg_mp_reset(const mg_mp_params* p, const void* assets, void* stat
     if (mg_mp_check_params(p)) return MG_EINVAL;
     MgMPK k;
     mg_mp_derive(p, &k);
-    return launch_env<MPPolicy>(k, assets, state, rng4, io, 1, n, MG_MODE_RESET, 2, stream, 10);
+    return launch_env<MPPolicy>(k, assets, state, rng4, io, 1, n, MG_MODE_RESET, mp_act_dims(p), stream, 10);
 }
 extern "C" int mg_mp_step(const mg_mp_params* p, const void* assets, void* state, const mg_step_io* io, int n,
                           void* stream) {
@@ -554,14 +556,14 @@ extern "C" int mg_mp_step_many(const mg_mp_params* p, const void* assets, void* 
     if (mg_mp_check_params(p)) return MG_EINVAL;
     MgMPK k;
     mg_mp_derive(p, &k);
-    return launch_env<MPPolicy>(k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, 2, stream, 10);
+    return launch_env<MPPolicy>(k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, mp_act_dims(p), stream, 10);
 }
 extern "C" int mg_mp_rollout(const mg_mp_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
                              void* stream) {
     if (mg_mp_check_params(p)) return MG_EINVAL;
     MgMPK k;
     mg_mp_derive(p, &k);
-    return launch_rollout<MPPolicy>(k, assets, state, r, n, 2, stream, 10);
+    return launch_rollout<MPPolicy>(k, assets, state, r, n, mp_act_dims(p), stream, 10);
 }
 
 extern "C" int mg_ss_reset(const mg_ss_params* p, const void* assets, void* state, const uint64_t* rng4,

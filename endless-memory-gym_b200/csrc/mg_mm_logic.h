@@ -29,6 +29,9 @@ struct MgMMK {
 
 #define MG_TILE 14  // int(56 * SCALE)
 
+MG_HD bool mg_mm_is_grid(int variant) { return variant == MG_MM_GRID || variant == MG_MM_B_GRID; }
+MG_HD bool mg_mm_is_task_b(int variant) { return variant == MG_MM_B || variant == MG_MM_B_GRID; }
+
 MG_HD int mg_floordiv(int a, int b) {
     int q = a / b;
     return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
@@ -120,7 +123,7 @@ MG_HD_NOINLINE void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, 
     int tile_id = (int)mg_integers(r, 0, size * size);
     int i = tile_id / size, j = tile_id % size;
     int cx = MG_TILE * i + k.origin + MG_TILE / 2, cy = MG_TILE * j + k.origin + MG_TILE / 2;
-    if (endless) {  // spawn offset, endless_mortar_mayhem.py:224
+    if (endless || k.p.variant == MG_MM_B) {  // spawn offset, endless_mortar_mayhem.py:224, mortar_mayhem_b.py:167
         int o0 = (int)mg_integers(r, -2, 2);
         int o1 = (int)mg_integers(r, -2, 2);
         cx += o0;
@@ -164,11 +167,18 @@ MG_HD_NOINLINE void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, 
         }
     }
     s.n = (uint16_t)n;
-    s.show_dur = (uint16_t)mg_choice(r, k.p.command_show_duration);
-    s.show_delay = (uint16_t)mg_choice(r, k.p.command_show_delay);
+    const bool task_b = mg_mm_is_task_b(k.p.variant);
     s.show_base = 0;
-    s.show_len = (uint16_t)(n * (s.show_dur + s.show_delay));
-    s.show_pos = 1;  // the first entry is consumed by the reset frame
+    if (task_b) {  // no command visualisation: the commands are observed as a vector (mortar_mayhem_b.py:176)
+        s.show_dur = s.show_delay = 0;
+        s.show_len = 0;
+        s.show_pos = 0;
+    } else {
+        s.show_dur = (uint16_t)mg_choice(r, k.p.command_show_duration);
+        s.show_delay = (uint16_t)mg_choice(r, k.p.command_show_delay);
+        s.show_len = (uint16_t)(n * (s.show_dur + s.show_delay));
+        s.show_pos = 1;  // the first entry is consumed by the reset frame
+    }
     int dx, dy;
     mg_cmd_delta(s.commands[0], dx, dy);
     int tx = px + dx, ty = py + dy;
@@ -182,7 +192,7 @@ MG_HD_NOINLINE void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, 
     s.E = (uint16_t)mg_choice(r, k.p.explosion_duration);
     s.D = (uint16_t)mg_choice(r, k.p.explosion_delay);
     s.rng = r;
-    mg_mm_frame(k, s, cx, cy, 0, mg_mm_show_entry(s, 0), f);
+    mg_mm_frame(k, s, cx, cy, 0, task_b ? -2 : mg_mm_show_entry(s, 0), f);
     if (gt) {
         gt[0] = (double)tx / 5.0;
         gt[1] = (double)ty / 5.0;
@@ -220,7 +230,7 @@ MG_HD bool mg_mm_step_env(const MgMMK& k, MgMMState& s, int a0, int a1, double& 
     } else {
         int cx = s.cx, cy = s.cy, rot = s.rot;
         const int lo = k.origin, hi = k.origin + MG_TILE * k.size;
-        if (k.p.variant == MG_MM_GRID) {
+        if (mg_mm_is_grid(k.p.variant)) {
             // GridCharacterController.step: 0 noop, 1 rotate left (+90), 2 rotate right (-90), 3 forward
             int gx = s.gx, gy = s.gy;
             if (a0 == 1) rot = (rot + 2) & 7;
@@ -357,4 +367,15 @@ MG_HD bool mg_mm_step_env(const MgMMK& k, MgMMState& s, int a0, int a1, double& 
         }
     }
     return done;
+}
+
+// MortarMayhemB: _encode_commands_one_hot (mortar_mayhem_b.py:102-131) — slot order stay, right, left, up, down,
+// right_down, right_up, left_down, left_up; written by every lane of the team
+template <class Ctx>
+MG_HD void mg_mm_write_vector(Ctx& c, const MgMMState& s, float* vec) {
+    const uint8_t slot[9] = {1, 4, 2, 3, 0, 5, 6, 7, 8};  // Command.COMMANDS index -> one-hot slot
+    for (int i = c.lane; i < MG_MM_B_VECTOR; i += c.nl) {
+        int cmd = i / 9, j = i - 9 * cmd;
+        vec[i] = (cmd < (int)s.n && slot[s.commands[cmd]] == j) ? 1.0f : 0.0f;
+    }
 }

@@ -22,18 +22,18 @@ struct MgMPK {
     int32_t pad;
 };
 
-#define MG_MP_GRID 7
+#define MG_MP_CELLS 7
 #define MG_MP_TILE 12  // screen_dim / grid_dim (mystery_path.py:76-78)
-#define MG_MP_NODES (MG_MP_GRID * MG_MP_GRID)
+#define MG_MP_NODES (MG_MP_CELLS * MG_MP_CELLS)
 
-MG_HD int mg_mp_id(int i, int j) { return i * MG_MP_GRID + j; }
+MG_HD int mg_mp_id(int i, int j) { return i * MG_MP_CELLS + j; }
 
 // 4-neighbours in Node.add_neighbors order (+x, -x, +y, -y), pygame_assets.py:465-472
 MG_HD int mg_mp_neighbours(int i, int j, int* out) {
     int c = 0;
-    if (i < MG_MP_GRID - 1) out[c++] = mg_mp_id(i + 1, j);
+    if (i < MG_MP_CELLS - 1) out[c++] = mg_mp_id(i + 1, j);
     if (i > 0) out[c++] = mg_mp_id(i - 1, j);
-    if (j < MG_MP_GRID - 1) out[c++] = mg_mp_id(i, j + 1);
+    if (j < MG_MP_CELLS - 1) out[c++] = mg_mp_id(i, j + 1);
     if (j > 0) out[c++] = mg_mp_id(i, j - 1);
     return c;
 }
@@ -41,7 +41,7 @@ MG_HD int mg_mp_neighbours(int i, int j, int* out) {
 // MysteryPath.__init__: returns the path as a 49-bit mask, or 0 if A* ran out of open nodes
 // (the reference raises Exception("No valid path found"), pygame_assets.py:724)
 MG_HD_NOINLINE uint64_t mg_mp_generate(MgRng& r, int sx, int sy, int ex, int ey) {
-    const int n = MG_MP_GRID;
+    const int n = MG_MP_CELLS;
     uint64_t wall = 0;
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j)
@@ -153,7 +153,7 @@ MG_HD void mg_mp_draw(const MgMPK& k, const MgMPState& s, int cross, MgMPDraw& d
 }
 
 MG_HD_NOINLINE void mg_mp_reset_env(const MgMPK& k, MgMPState& s, MgMPDraw& d) {
-    const int g = MG_MP_GRID;
+    const int g = MG_MP_CELLS;
     MgRng r = s.rng;
     s.t = 0;
     s.ep_len = 0;
@@ -180,6 +180,8 @@ MG_HD_NOINLINE void mg_mp_reset_env(const MgMPK& k, MgMPState& s, MgMPDraw& d) {
     s.rot = 0;
     s.cx = (int16_t)(sx * MG_MP_TILE + k.radius);
     s.cy = (int16_t)(sy * MG_MP_TILE + k.radius);
+    s.gx = (int8_t)sx;  // Grid: normalize(start * 12 + int(25 * SCALE)) (mystery_path_grid.py:186-188)
+    s.gy = (int8_t)sy;
     s.off_path = 0;
     s.num_fails = 0;
     s.cross_on = 0;
@@ -196,13 +198,41 @@ MG_HD bool mg_mp_step_env(const MgMPK& k, MgMPState& s, int a0, int a1, double& 
     bool done = false;
     int success = 0;
     int cx = s.cx, cy = s.cy, rot = s.rot;
-    if (s.off_path) {  // respawn on the origin tile, then a no-op controller step (mystery_path.py:216-220)
-        cx = s.sx * MG_MP_TILE + k.radius;
-        cy = s.sy * MG_MP_TILE + k.radius;
-        a0 = 0;
-        a1 = 0;
+    if (k.p.variant == MG_MP_GRID) {
+        // GridCharacterController.step (character_controller.py:177-210): 1 / 2 rotate by +-90, 3 forward;
+        // cell centres 12 i + 6 (MysteryPath.to_grid, pygame_assets.py:764-778)
+        int gx = s.gx, gy = s.gy;
+        if (s.off_path) {  // reset_position(start) then agent.step(0) (mystery_path_grid.py:218-221)
+            gx = s.sx;
+            gy = s.sy;
+            a0 = 0;
+        }
+        if (a0 == 1) rot = (rot + 2) & 7;
+        if (a0 == 2) rot = (rot + 6) & 7;
+        if (a0 == 3) {
+            int face = rot >> 1, last = MG_MP_CELLS - 1;
+            if (face == 0 && gy > 0)
+                gy--;
+            else if (face == 3 && gx < last)
+                gx++;
+            else if (face == 2 && gy < last)
+                gy++;
+            else if (face == 1 && gx > 0)
+                gx--;
+        }
+        s.gx = (int8_t)gx;
+        s.gy = (int8_t)gy;
+        cx = MG_MP_TILE * gx + MG_MP_TILE / 2;
+        cy = MG_MP_TILE * gy + MG_MP_TILE / 2;
+    } else {
+        if (s.off_path) {  // respawn on the origin tile, then a no-op controller step (mystery_path.py:216-220)
+            cx = s.sx * MG_MP_TILE + k.radius;
+            cy = s.sy * MG_MP_TILE + k.radius;
+            a0 = 0;
+            a1 = 0;
+        }
+        mg_move_clamped(cx, cy, rot, a0, a1, k.step_axis, k.step_diag, k.radius, 0, 0, MG_W, MG_W);
     }
-    mg_move_clamped(cx, cy, rot, a0, a1, k.step_axis, k.step_diag, k.radius, 0, 0, MG_W, MG_W);
     s.cx = (int16_t)cx;
     s.cy = (int16_t)cy;
     s.rot = (uint8_t)rot;
@@ -213,7 +243,7 @@ MG_HD bool mg_mp_step_env(const MgMPK& k, MgMPState& s, int a0, int a1, double& 
         success = 1;
     } else {
         int id = mg_mp_id(px, py);
-        bool on_path = px < MG_MP_GRID && py < MG_MP_GRID && ((s.path_mask >> id) & 1);
+        bool on_path = px < MG_MP_CELLS && py < MG_MP_CELLS && ((s.path_mask >> id) & 1);
         if (on_path) {
             bool is_start = (px == s.sx && py == s.sy);
             if (!((s.visited >> id) & 1) && !is_start) {

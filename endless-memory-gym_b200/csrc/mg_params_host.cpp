@@ -40,7 +40,7 @@ extern "C" int mg_mm_check_params(const mg_mm_params* p) {
         mg_set_err("params is NULL");
         return MG_EINVAL;
     }
-    if (p->variant < MG_MM_CONTINUOUS || p->variant > MG_MM_ENDLESS) {
+    if (p->variant < MG_MM_CONTINUOUS || p->variant > MG_MM_B_GRID) {
         mg_set_err("variant");
         return MG_EINVAL;
     }
@@ -60,18 +60,21 @@ extern "C" int mg_mm_check_params(const mg_mm_params* p) {
             mg_set_err("arena_size must be 2..6");
             return MG_EINVAL;
         }
-        if (!check_list(p->command_count, 1, MG_MM_MAX_COMMANDS, "command_count")) return MG_EINVAL;
+        const bool task_b = p->variant == MG_MM_B || p->variant == MG_MM_B_GRID;  // mortar_mayhem_b.py:52
+        if (!check_list(p->command_count, 1, task_b ? MG_MM_B_MAX_COMMANDS : MG_MM_MAX_COMMANDS, "command_count"))
+            return MG_EINVAL;
         max_n = list_max(p->command_count);
     }
-    if (!check_list(p->command_show_duration, 0, 4096, "command_show_duration")) return MG_EINVAL;
-    if (!check_list(p->command_show_delay, 0, 4096, "command_show_delay")) return MG_EINVAL;
+    const bool shows = !(p->variant == MG_MM_B || p->variant == MG_MM_B_GRID);
+    if (shows && !check_list(p->command_show_duration, 0, 4096, "command_show_duration")) return MG_EINVAL;
+    if (shows && !check_list(p->command_show_delay, 0, 4096, "command_show_delay")) return MG_EINVAL;
     if (!check_list(p->explosion_duration, 1, 65535, "explosion_duration")) return MG_EINVAL;
     if (!check_list(p->explosion_delay, 1, 65535, "explosion_delay")) return MG_EINVAL;
-    if (list_min(p->command_show_duration) + list_min(p->command_show_delay) < 1) {
+    if (shows && list_min(p->command_show_duration) + list_min(p->command_show_delay) < 1) {
         mg_set_err("command_show_duration + command_show_delay must be >= 1 (the reference pops an empty list otherwise)");
         return MG_EINVAL;
     }
-    if ((long)max_n * (list_max(p->command_show_duration) + list_max(p->command_show_delay)) > 65535) {
+    if (shows && (long)max_n * (list_max(p->command_show_duration) + list_max(p->command_show_delay)) > 65535) {
         mg_set_err("command visualisation queue longer than 65535 steps");
         return MG_EINVAL;
     }
@@ -79,7 +82,7 @@ extern "C" int mg_mm_check_params(const mg_mm_params* p) {
         mg_set_err("agent_speed must be in [0, 84)");
         return MG_EINVAL;
     }
-    if (p->variant != MG_MM_GRID) {
+    if (p->variant != MG_MM_GRID && p->variant != MG_MM_B_GRID) {
         int radius = (int)(25 * p->agent_scale), hand = (int)(10 * p->agent_scale);
         if (!(p->agent_scale > 0.0) || radius * 2 + hand + 14 > 255) {
             mg_set_err("agent_scale out of range");
@@ -94,7 +97,7 @@ void mg_mm_derive(const mg_mm_params* p, MgMMK* k) {
     k->p = *p;
     k->size = p->variant == MG_MM_ENDLESS ? 6 : p->arena_size;
     k->origin = MG_W / 2 - ((MG_TILE * k->size) >> 1);
-    double scale = p->variant == MG_MM_GRID ? 0.25 : p->agent_scale;
+    double scale = (p->variant == MG_MM_GRID || p->variant == MG_MM_B_GRID) ? 0.25 : p->agent_scale;
     k->radius = (int)(25 * scale);
     // velocity.normalize() * speed (character_controller.py:124): 1/sqrt(2) per diagonal component
     double inv = 1.0 / sqrt(2.0);
@@ -116,8 +119,12 @@ extern "C" int mg_mp_check_params(const mg_mp_params* p) {
         mg_set_err("agent_speed must be in [0, 84)");
         return MG_EINVAL;
     }
+    if (p->variant != MG_MP_CONTINUOUS && p->variant != MG_MP_GRID) {
+        mg_set_err("variant");
+        return MG_EINVAL;
+    }
     int radius = (int)(25 * p->agent_scale), hand = (int)(10 * p->agent_scale);
-    if (!(p->agent_scale > 0.0) || radius * 2 + hand + 14 > 255 || radius > 42) {
+    if (p->variant == MG_MP_CONTINUOUS && (!(p->agent_scale > 0.0) || radius * 2 + hand + 14 > 255 || radius > 42)) {
         mg_set_err("agent_scale out of range");
         return MG_EINVAL;
     }
@@ -127,7 +134,8 @@ extern "C" int mg_mp_check_params(const mg_mp_params* p) {
 void mg_mp_derive(const mg_mp_params* p, MgMPK* k) {
     memset(k, 0, sizeof(*k));
     k->p = *p;
-    k->radius = (int)(25 * p->agent_scale);
+    // GridMysteryPathEnv places the agent with the hard-coded int(25 * SCALE) (mystery_path_grid.py:186)
+    k->radius = p->variant == MG_MP_GRID ? (int)(25 * 0.25) : (int)(25 * p->agent_scale);
     double inv = 1.0 / sqrt(2.0);
     k->step_axis = (int)(1.0 * p->agent_speed);
     k->step_diag = (int)(inv * p->agent_speed);

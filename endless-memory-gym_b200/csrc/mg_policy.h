@@ -112,6 +112,11 @@ struct MMPolicy {
     static MG_HD void logic(Ctx& c, const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0,
                             int a1, MgFrameJob& job, Frame* fr, const MgScratch&) {
         if (c.lane == 0) mg_env_logic<MMPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
+        if (mg_mm_is_task_b(k.p.variant) && q.io.vector_obs) {
+            c.sync();
+            // a fresh episode (reset or auto-reset in this call): publish its command vector
+            if (s.live && s.ep_len == 0) mg_mm_write_vector(c, s, q.io.vector_obs + (size_t)MG_MM_B_VECTOR * env);
+        }
     }
     template <class Ctx>
     static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K& k, const Frame& f, const MgScratch&) {

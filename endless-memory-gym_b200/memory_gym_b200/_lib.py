@@ -21,7 +21,9 @@ MG_MP_STATE_BYTES = 128
 MG_SS_STATE_BYTES = 1024
 MG_FLAG_AUTORESET = 1
 MG_FLAG_STREAM_OBS = 2
-MG_MM_CONTINUOUS, MG_MM_GRID, MG_MM_ENDLESS = 0, 1, 2
+MG_MM_CONTINUOUS, MG_MM_GRID, MG_MM_ENDLESS, MG_MM_B, MG_MM_B_GRID = 0, 1, 2, 3, 4
+MG_MP_CONTINUOUS, MG_MP_GRID = 0, 1
+MG_MM_B_VECTOR = 180
 (MG_INFO_REWARD, MG_INFO_LENGTH, MG_INFO_SUCCESS, MG_INFO_A, MG_INFO_B, MG_INFO_GT0, MG_INFO_GT1) = range(7)
 
 
@@ -53,6 +55,7 @@ class MMParams(C.Structure):
 
 class MPParams(C.Structure):
     _fields_ = [
+        ("variant", C.c_int32), ("pad0", C.c_int32),
         ("max_steps", C.c_int32), ("show_origin", C.c_int32), ("show_goal", C.c_int32),
         ("visual_feedback", C.c_int32), ("cardinal_origin_choice", ChoiceList),
         ("agent_scale", C.c_double), ("agent_speed", C.c_double), ("reward_goal", C.c_double),
@@ -82,7 +85,7 @@ class StepIO(C.Structure):
     _fields_ = [
         ("actions", C.c_void_p), ("obs", C.c_void_p), ("final_obs", C.c_void_p), ("reward", C.c_void_p),
         ("done", C.c_void_p), ("info", C.c_void_p), ("ground_truth", C.c_void_p), ("reset_mask", C.c_void_p),
-        ("flags", C.c_uint32), ("warps_per_cta", C.c_uint32), ("trace", C.c_void_p),
+        ("flags", C.c_uint32), ("warps_per_cta", C.c_uint32), ("vector_obs", C.c_void_p), ("trace", C.c_void_p),
     ]
 
 
@@ -91,7 +94,7 @@ class RolloutIO(C.Structure):
         ("actions", C.c_void_p), ("obs", C.c_void_p), ("final_obs", C.c_void_p), ("reward", C.c_void_p),
         ("done", C.c_void_p), ("info", C.c_void_p), ("ground_truth", C.c_void_p),
         ("n_steps", C.c_int32), ("ring", C.c_int32), ("info_per_step", C.c_int32), ("flags", C.c_uint32),
-        ("warps_per_cta", C.c_uint32), ("pad0", C.c_uint32), ("trace", C.c_void_p),
+        ("warps_per_cta", C.c_uint32), ("pad0", C.c_uint32), ("trace", C.c_void_p), ("vector_obs", C.c_void_p),
     ]
 
 

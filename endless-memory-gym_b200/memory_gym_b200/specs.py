@@ -50,8 +50,8 @@ class EnvSpec:
             s.max_steps = int(p.get("max_steps", -1))
             s.initial_command_count = int(p.get("initial_command_count", 1))
             s.command_count = L.ChoiceList.of(p.get("command_count", [1]))
-            s.command_show_duration = L.ChoiceList.of(p["command_show_duration"])
-            s.command_show_delay = L.ChoiceList.of(p["command_show_delay"])
+            s.command_show_duration = L.ChoiceList.of(p.get("command_show_duration", [0]))
+            s.command_show_delay = L.ChoiceList.of(p.get("command_show_delay", [1]))
             s.explosion_duration = L.ChoiceList.of(p["explosion_duration"])
             s.explosion_delay = L.ChoiceList.of(p["explosion_delay"])
             s.agent_scale = float(p["agent_scale"])
@@ -63,13 +63,14 @@ class EnvSpec:
             return s
         if self.family == "mp":
             s = L.MPParams()
+            s.variant = self.variant
             s.max_steps = int(p["max_steps"])
             s.show_origin = int(bool(p["show_origin"]))
             s.show_goal = int(bool(p["show_goal"]))
             s.visual_feedback = int(bool(p["visual_feedback"]))
             s.cardinal_origin_choice = L.ChoiceList.of(p["cardinal_origin_choice"])
-            for k in ("agent_scale", "agent_speed", "reward_goal", "reward_fall_off", "reward_path_progress",
-                      "reward_step"):
+            s.agent_speed = float(p.get("agent_speed", 0.0))
+            for k in ("agent_scale", "reward_goal", "reward_fall_off", "reward_path_progress", "reward_step"):
                 setattr(s, k, float(p[k]))
             return s
         if self.family == "ss":
@@ -90,6 +91,12 @@ class EnvSpec:
 def _check_mm(p):
     assert p["allowed_commands"] >= 4 and p["allowed_commands"] <= 9
     assert p["arena_size"] >= 2 and p["arena_size"] <= 6
+
+
+def _check_mmb(p):
+    assert p["allowed_commands"] >= 4 and p["allowed_commands"] <= 9
+    assert p["arena_size"] >= 2 and p["arena_size"] <= 6
+    assert max(p["command_count"]) <= 20, "20 commands are allowed at maximum"
 
 
 def _check_emm(p):
@@ -127,6 +134,9 @@ _MMGRID_DEFAULTS = {
     "reward_episode_success": 0.0,
 }
 
+_MMB_DEFAULTS = {k: v for k, v in _MM_DEFAULTS.items() if k not in ("command_show_duration", "command_show_delay")}
+_MMBGRID_DEFAULTS = {k: v for k, v in _MMGRID_DEFAULTS.items() if k not in ("command_show_duration", "command_show_delay")}
+
 _EMM_DEFAULTS = {
     "max_steps": -1,
     "agent_scale": 1.0 * SCALE,
@@ -156,6 +166,9 @@ _MP_DEFAULTS = {
     "reward_path_progress": 0.1,
     "reward_step": 0.0,
 }
+
+_MPGRID_DEFAULTS = {k: v for k, v in _MP_DEFAULTS.items() if k != "agent_speed"}
+_MPGRID_DEFAULTS.update({"max_steps": 128, "reward_path_progress": 0.0})
 
 _SS_DEFAULTS = {
     "max_steps": 256,
@@ -212,14 +225,17 @@ SPECS = {
                 _check_mm),
         EnvSpec("Endless-MortarMayhem-v0", "mm", L.MG_MM_ENDLESS, _EMM_DEFAULTS, [3, 3], L.MG_MM_STATE_BYTES,
                 _EMM_INFO, _check_emm, has_ground_truth=True),
-        EnvSpec("MysteryPath-v0", "mp", 0, _MP_DEFAULTS, [3, 3], L.MG_MP_STATE_BYTES, _MP_INFO),
+        EnvSpec("MysteryPath-v0", "mp", L.MG_MP_CONTINUOUS, _MP_DEFAULTS, [3, 3], L.MG_MP_STATE_BYTES, _MP_INFO),
+        EnvSpec("MysteryPath-Grid-v0", "mp", L.MG_MP_GRID, _MPGRID_DEFAULTS, [4], L.MG_MP_STATE_BYTES, _MP_INFO),
+        EnvSpec("MortarMayhemB-v0", "mm", L.MG_MM_B, _MMB_DEFAULTS, [3, 3], L.MG_MM_STATE_BYTES, _MM_INFO, _check_mmb),
+        EnvSpec("MortarMayhemB-Grid-v0", "mm", L.MG_MM_B_GRID, _MMBGRID_DEFAULTS, [4], L.MG_MM_STATE_BYTES, _MM_INFO,
+                _check_mmb),
         EnvSpec("SearingSpotlights-v0", "ss", 0, _SS_DEFAULTS, [3, 3], L.MG_SS_STATE_BYTES, _SS_INFO),
     )
 }
 
 # ids the reference registers that this engine does not accelerate yet
-NOT_BUILT = ("Endless-SearingSpotlights-v0", "MortarMayhemB-v0", "MortarMayhemB-Grid-v0", "Endless-MysteryPath-v0",
-             "MysteryPath-Grid-v0")
+NOT_BUILT = ("Endless-SearingSpotlights-v0", "Endless-MysteryPath-v0")
 
 
 def spec(env_id: str) -> EnvSpec:

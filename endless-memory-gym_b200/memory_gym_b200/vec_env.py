@@ -126,6 +126,9 @@ class MemoryGymVecEnv:
         self.truncated = torch.zeros(n, dtype=torch.bool, device=dev)
         self.info = torch.zeros((n, L.MG_INFO_COLS), dtype=torch.float64, device=dev)
         self.ground_truth = torch.zeros((n, 2), dtype=torch.float64, device=dev) if self.has_ground_truth_info else None
+        # MortarMayhemB: Dict observation {"visual_observation", "vector_observation"} (mortar_mayhem_b.py:84-97)
+        self.task_b = self.spec_.family == "mm" and self.spec_.variant in (L.MG_MM_B, L.MG_MM_B_GRID)
+        self.vector_obs = torch.zeros((n, L.MG_MM_B_VECTOR), dtype=torch.float32, device=dev) if self.task_b else None
         self._actions_dev = torch.zeros((n, len(nvec)) if len(nvec) > 1 else (n,), dtype=torch.int64, device=dev)
         self._io = L.StepIO()
         self._io.obs = self.obs.data_ptr()
@@ -134,6 +137,7 @@ class MemoryGymVecEnv:
         self._io.done = self.done.data_ptr()
         self._io.info = self.info.data_ptr()
         self._io.ground_truth = self.ground_truth.data_ptr() if self.has_ground_truth_info else None
+        self._io.vector_obs = self.vector_obs.data_ptr() if self.task_b else None
         # stream_obs: write observations with an L2 evict-first policy. Default: on for rollout() (frames are
         # not re-read soon; measured +13 % HBM write throughput), off for step() (the policy reads obs next).
         self._stream_step = L.MG_FLAG_STREAM_OBS if stream_obs else 0
@@ -173,7 +177,8 @@ class MemoryGymVecEnv:
         if self.spec_.family == "mm" and self.spec_.variant != L.MG_MM_ENDLESS:
             # calc_max_episode_steps (pygame_assets.py:420-436), called with delay/duration swapped
             # (mortar_mayhem.py:222-226); informational only — the env has no step limit
-            cc, sd, sl = max(p["command_count"]), max(p["command_show_duration"]), max(p["command_show_delay"])
+            cc = max(p["command_count"])
+            sd, sl = max(p.get("command_show_duration", [0])), max(p.get("command_show_delay", [0]))
             ed, el = max(p["explosion_delay"]), max(p["explosion_duration"])
             return (sd + sl) * cc + (ed + el) * cc - el + 1
         return p.get("max_steps")
@@ -212,7 +217,12 @@ class MemoryGymVecEnv:
         info = {}
         if self.has_ground_truth_info:
             info["ground_truth"] = self.ground_truth
-        return self.obs, info
+        return self._wrap_obs(self.obs), info
+
+    def _wrap_obs(self, obs):
+        if self.task_b:
+            return {"visual_observation": obs, "vector_observation": self.vector_obs}
+        return obs
 
     def step(self, actions, obs_out=None):
         """``obs_out``: optional uint8[N,84,84,3] device tensor (e.g. a slot of a rollout buffer) that
@@ -247,7 +257,7 @@ class MemoryGymVecEnv:
         if self.has_ground_truth_info:
             info["ground_truth"] = self.ground_truth
             info["final_ground_truth"] = self.info[:, L.MG_INFO_GT0:L.MG_INFO_GT1 + 1]
-        return obs, self.reward, done, self.truncated, info
+        return self._wrap_obs(obs), self.reward, done, self.truncated, info
 
     def _check_rollout_buffers(self, actions, obs_out, reward_out, done_out, info_out):
         if self._params is None:
@@ -283,6 +293,7 @@ class MemoryGymVecEnv:
         r.reward, r.done = reward_out.data_ptr(), done_out.data_ptr()
         r.info = info_out.data_ptr() if info_out is not None else self._io.info
         r.ground_truth = self._io.ground_truth
+        r.vector_obs = self._io.vector_obs
         r.n_steps, r.ring, r.info_per_step = T, obs_out.shape[0], int(info_out is not None)
         r.flags, r.warps_per_cta = L.MG_FLAG_AUTORESET | self._stream_rollout, self.warps_per_cta
         r.trace = getattr(self, "_trace_ptr", None)
@@ -309,6 +320,7 @@ class MemoryGymVecEnv:
                 io.info = (info_out.data_ptr() + t * self.num_envs * L.MG_INFO_COLS * 8) if info_out is not None \
                     else self._io.info
                 io.ground_truth = self._io.ground_truth
+                io.vector_obs = self._io.vector_obs
                 io.reset_mask = None
                 io.flags = self._io.flags
                 io.warps_per_cta = self._io.warps_per_cta
@@ -326,7 +338,7 @@ class MemoryGymVecEnv:
     def state_dict(self):
         """Snapshot of every env's state (PCG64 stream included) — restoring it resumes bit-exactly."""
         return {"env_id": self.env_id, "state": self.state.clone(), "params": dict(self.reset_params or {}),
-                "obs": self.obs.clone()}
+                "obs": self.obs.clone(), "vector_obs": self.vector_obs.clone() if self.task_b else None}
 
     def load_state_dict(self, sd):
         if sd["env_id"] != self.env_id or sd["state"].shape != self.state.shape:
@@ -334,6 +346,8 @@ class MemoryGymVecEnv:
         self._set_options(sd["params"] or None)
         self.state.copy_(sd["state"])
         self.obs.copy_(sd["obs"])
+        if self.task_b:
+            self.vector_obs.copy_(sd["vector_obs"])
         self._seeded = True
 
 
@@ -363,7 +377,13 @@ class MemoryGymEnv:
         out = {}
         if self.has_ground_truth_info:
             out["ground_truth"] = info["ground_truth"][0].cpu().numpy()
-        return obs[0].cpu().numpy(), out
+        return self._np_obs(obs), out
+
+    @staticmethod
+    def _np_obs(obs):
+        if isinstance(obs, dict):
+            return {k: v[0].cpu().numpy() for k, v in obs.items()}
+        return obs[0].cpu().numpy()
 
     def step(self, action):
         a = np.asarray(action, dtype=np.int64).reshape(self.vec._actions_dev.shape)
@@ -379,7 +399,7 @@ class MemoryGymEnv:
                 out["ground_truth"] = row[L.MG_INFO_GT0:L.MG_INFO_GT1 + 1].copy()
         elif self.has_ground_truth_info:
             out["ground_truth"] = info["ground_truth"][0].cpu().numpy()
-        return obs[0].cpu().numpy(), float(reward[0].item()), d, False, out
+        return self._np_obs(obs), float(reward[0].item()), d, False, out
 
     def render(self):
         return self.vec.render()[0].cpu().numpy()

@@ -9,9 +9,12 @@
  *   mg_mm_reset / mg_mm_step   <-  MortarMayhemEnv.reset/step          memory_gym/mortar_mayhem.py:206-272, 274-369
  *                                  GridMortarMayhemEnv.reset/step      memory_gym/mortar_mayhem_grid.py:213-278, 280-375
  *                                  EndlessMortarMayhemEnv.reset/step   memory_gym/endless_mortar_mayhem.py:194-259, 261-373
+ *                                  MortarMayhemTaskBEnv.reset/step     memory_gym/mortar_mayhem_b.py:133-204, 206-290
+ *                                  GridMortarMayhemTaskBEnv.reset/step memory_gym/mortar_mayhem_b_grid.py:133-202, 204-288
  *                                  CharacterController.step & co.      memory_gym/character_controller.py:89-146, 177-210, 226-283
  *                                  MortarArena / Command               memory_gym/pygame_assets.py:241-418
  *   mg_mp_reset / mg_mp_step   <-  MysteryPathEnv.reset/step           memory_gym/mystery_path.py:130-200, 202-276
+ *                                  GridMysteryPathEnv.reset/step       memory_gym/mystery_path_grid.py:129-200, 202-276
  *                                  MysteryPath.__init__ (noisy A*)     memory_gym/pygame_assets.py:606-736
  *   mg_ss_reset / mg_ss_step   <-  SearingSpotlightsEnv.reset/step     memory_gym/searing_spotlights.py:332-450, 452-562
  *                                  Spotlight / Coin / Exit / sampler   memory_gym/pygame_assets.py:7-239
@@ -79,7 +82,9 @@ typedef struct mg_choice_list {
 } mg_choice_list;
 
 /* ---- Mortar Mayhem family ------------------------------------------------------------------- */
-enum { MG_MM_CONTINUOUS = 0, MG_MM_GRID = 1, MG_MM_ENDLESS = 2 };
+enum { MG_MM_CONTINUOUS = 0, MG_MM_GRID = 1, MG_MM_ENDLESS = 2, MG_MM_B = 3, MG_MM_B_GRID = 4 };
+#define MG_MM_B_MAX_COMMANDS 20   /* MortarMayhemB: commands are observed as a [20][9] one-hot vector */
+#define MG_MM_B_VECTOR 180
 
 /* Reset options, batch-uniform. Field names follow the reference's default_reset_parameters
  * (mortar_mayhem.py:21-35, mortar_mayhem_grid.py:21-34, endless_mortar_mayhem.py:21-35). */
@@ -103,7 +108,10 @@ typedef struct mg_mm_params {
 } mg_mm_params;
 
 /* ---- Mystery Path ---------------------------------------------------------------------------- */
+enum { MG_MP_CONTINUOUS = 0, MG_MP_GRID = 1 };
 typedef struct mg_mp_params {
+    int32_t variant;   /* MG_MP_* */
+    int32_t pad0;
     int32_t max_steps;
     int32_t show_origin;
     int32_t show_goal;
@@ -169,6 +177,7 @@ typedef struct mg_step_io {
     const uint8_t* reset_mask; /* reset only, nullable: [n], reset env i iff mask[i] != 0 */
     uint32_t flags;         /* MG_FLAG_* */
     uint32_t warps_per_cta; /* 0 = library default; tuning knob (frame buffers resident per SM) */
+    float* vector_obs;      /* nullable: [n][MG_MM_B_VECTOR] (MortarMayhemB: one-hot commands of the running episode) */
     uint64_t* trace;        /* nullable: [n][MG_TRACE_COLS] uint64, per-env phase timestamps (globaltimer ns):   */
                             /* 0 kernel entry, 1 prologue done, 2 dependency wait done, 3 record in smem,      */
                             /* 4 logic done, 5 frame composed, 6 bulk store issued, 7 SM id, 8.. env-type specific  */
@@ -192,6 +201,7 @@ typedef struct mg_rollout_io {
     uint32_t warps_per_cta; /* 0 = library picks the count that balances envs per warp */
     uint32_t pad0;
     uint64_t* trace;        /* nullable: [n][MG_TRACE_COLS] phase timestamps of each env's LAST step (see mg_step_io) */
+    float* vector_obs;      /* nullable: [n][MG_MM_B_VECTOR], as in mg_step_io (state after the last step) */
 } mg_rollout_io;
 
 /* ---- assets & seeding (host side) -------------------------------------------------------------- */

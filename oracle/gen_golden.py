@@ -45,6 +45,17 @@ CASES = {
                                           "light_dim_off_duration": 10, "coins_visible": True,
                                           "reward_inside_spotlight": -0.01, "reward_coin": 0.5,
                                           "agent_speed": 4.0}, 4, 450),
+    "mmb": ("MortarMayhemB-v0", None, 6, 300),
+    "mmb_opts": ("MortarMayhemB-v0", {"arena_size": 3, "allowed_commands": 7, "command_count": [2, 4, 20],
+                                       "explosion_duration": [2, 3], "explosion_delay": [4, 6], "visual_feedback": False,
+                                       "reward_command_failure": -0.3, "reward_episode_success": 2.0,
+                                       "agent_speed": 4.0}, 4, 260),
+    "mmbgrid": ("MortarMayhemB-Grid-v0", None, 6, 300),
+    "mpgrid": ("MysteryPath-Grid-v0", None, 6, 400),
+    "mpgrid_opts": ("MysteryPath-Grid-v0", {"max_steps": 60, "show_origin": True, "show_goal": True,
+                                             "cardinal_origin_choice": [0, 2], "reward_fall_off": -0.1,
+                                             "reward_path_progress": 0.2, "reward_step": -0.01,
+                                             "visual_feedback": False}, 4, 300),
     "ss_black": ("SearingSpotlights-v0", {"max_steps": 150, "black_background": True, "agent_visible": True,
                                            "exit_visible": True, "light_threshold": 140, "light_dim_off_duration": 4,
                                            "initial_spawns": 6, "spot_min_speed": 0.008, "spot_max_speed": 0.02,
@@ -65,7 +76,7 @@ def goal_seeking_actions(env_id, env, rng, e):
     """Seeded random actions; env instances with e % 3 != 0 follow a scripted expert (reading the
     reference env's internals) with 12 % random actions, so reward / success / growth branches are
     covered as well as the early-failure ones."""
-    grid = env_id == "MortarMayhem-Grid-v0"
+    grid = "Grid" in env_id
     rand = int(rng.integers(0, 4)) if grid else rng.integers(0, 3, 2)
     if e % 3 == 0 or rng.random() < 0.12:
         return rand
@@ -88,6 +99,18 @@ def goal_seeking_actions(env_id, env, rng, e):
             dy = (gy_c - cy + 42) % 84 - 42
             return np.asarray([_toward(0, dx, 2), _toward(0, dy, 2)])
         return np.asarray([_toward(cx, gx_c, 2), _toward(cy, gy_c, 2)])
+    if env_id == "MysteryPath-Grid-v0":
+        path = [(n.x, n.y) for n in env.mystery_path.path]
+        here = (int(env.agent.grid_position[0]), int(env.agent.grid_position[1]))
+        k = path.index(here) if here in path else len(path) - 1
+        nx, ny = path[max(k - 1, 0)]
+        want = 3 if nx > here[0] else 1 if nx < here[0] else 0 if ny < here[1] else 2  # E / W / N / S
+        face = env.agent.rotation // 90
+        if (nx, ny) == here:
+            return 0
+        if face == want:
+            return 3
+        return 1 if (want - face) % 4 in (1, 2) else 2
     if env_id == "MysteryPath-v0":
         path = [(n.x, n.y) for n in env.mystery_path.path]
         here = (cx // 12, cy // 12)
@@ -108,16 +131,29 @@ def goal_seeking_actions(env_id, env, rng, e):
     return rand
 
 
+def _split(obs):
+    """(visual frame, bytes of everything that must match) for plain and Dict observations."""
+    if isinstance(obs, dict):
+        vis, vec = obs["visual_observation"], obs["vector_observation"]
+        return vis, vis.tobytes() + np.asarray(vec, dtype=np.float32).tobytes(), np.asarray(vec, dtype=np.float32)
+    return obs, obs.tobytes(), None
+
+
 def run_case(name, make_env, env_id, options, n_envs, steps, seed0=100):
     rng = np.random.default_rng(zlib.crc32(name.encode()))
     rec = {k: [] for k in ("action", "reward", "done", "crc", "reset_crc")}
     frames, frame_idx = [], []
+    vecs, vec_idx = [], []
     infos = []
     for e in range(n_envs):
         env = make_env(env_id)
         obs, info = env.reset(seed=seed0 + e, options=options)
-        frames.append(obs.copy())
+        vis, blob, vec = _split(obs)
+        frames.append(vis.copy())
         frame_idx.append((e, -1))
+        if vec is not None:
+            vecs.append(vec.copy())
+            vec_idx.append((e, -1))
         a_l, r_l, d_l, c_l, rc_l = [], [], [], [], []
         ep_rewards = []
         for t in range(steps):
@@ -128,9 +164,10 @@ def run_case(name, make_env, env_id, options, n_envs, steps, seed0=100):
             a_l.append(np.asarray(a, dtype=np.int64).reshape(-1))
             r_l.append(float(reward))
             d_l.append(bool(done))
-            c_l.append(zlib.crc32(obs.tobytes()))
+            vis, blob, vec = _split(obs)
+            c_l.append(zlib.crc32(blob))
             if t % 37 == 0 or done:
-                frames.append(obs.copy())
+                frames.append(vis.copy())
                 frame_idx.append((e, t))
             rc = 0
             if done:
@@ -144,9 +181,13 @@ def run_case(name, make_env, env_id, options, n_envs, steps, seed0=100):
                 infos.append(row)
                 ep_rewards = []
                 obs, info = env.reset(options=options)  # seed=None: the stream continues
-                rc = zlib.crc32(obs.tobytes())
-                frames.append(obs.copy())
+                vis, blob, vec = _split(obs)
+                rc = zlib.crc32(blob)
+                frames.append(vis.copy())
                 frame_idx.append((e, -2 - t))
+                if vec is not None:
+                    vecs.append(vec.copy())
+                    vec_idx.append((e, -2 - t))
             rc_l.append(rc)
         for k, v in zip(("action", "reward", "done", "crc", "reset_crc"), (a_l, r_l, d_l, c_l, rc_l)):
             rec[k].append(np.asarray(v))
@@ -155,6 +196,9 @@ def run_case(name, make_env, env_id, options, n_envs, steps, seed0=100):
     out["reset_crc"] = out["reset_crc"].astype(np.uint32)
     out["frames"] = np.stack(frames)
     out["frame_idx"] = np.asarray(frame_idx, dtype=np.int64)
+    if vecs:
+        out["vecs"] = np.stack(vecs)
+        out["vec_idx"] = np.asarray(vec_idx, dtype=np.int64)
     out["seed0"] = np.asarray(seed0)
     import json
     out["infos_json"] = np.asarray(json.dumps(infos))

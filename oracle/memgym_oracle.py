@@ -161,6 +161,8 @@ class MortarMayhemOracle(_OracleEnv):
 
     env_id = "MortarMayhem-v0"
     grid_locomotion = False
+    task_b = False        # MortarMayhemB: no command visualisation, commands are given as a one-hot vector
+    spawn_offset = False  # MortarMayhemB: spawn jitter like the endless variant
     default_reset_parameters = {
         "agent_scale": 1.0 * SCALE,
         "agent_speed": 12.0 * SCALE,
@@ -206,7 +208,7 @@ class MortarMayhemOracle(_OracleEnv):
         rng = self._seed(seed)
         p = self.p = self.process_reset_params(options)
         self.max_episode_steps = calc_max_episode_steps(
-            max(p["command_count"]), max(p["command_show_duration"]), max(p["command_show_delay"]),
+            max(p["command_count"]), max(p.get("command_show_duration", [0])), max(p.get("command_show_delay", [0])),
             max(p["explosion_delay"]), max(p["explosion_duration"]))
         self.rewards = []
         self._setup_arena(p["arena_size"])
@@ -215,6 +217,9 @@ class MortarMayhemOracle(_OracleEnv):
         tile_id = int(rng.integers(0, self.size ** 2))
         i, j = tile_id // self.size, tile_id % self.size
         x, y = self._tile_centre(i, j)
+        if self.spawn_offset:  # mortar_mayhem_b.py:167-170
+            off = rng.integers(-8 * SCALE, 8 * SCALE, 2)
+            x, y = x + int(off[0]), y + int(off[1])
         self.cx, self.cy = int(x), int(y)
         self.rotation = 0
         self.pos = self._normalize(self.cx, self.cy)
@@ -234,17 +239,31 @@ class MortarMayhemOracle(_OracleEnv):
             k = valid[int(rng.integers(0, len(valid)))]
             self.commands.append(k)
             sim = (sim[0] + assets.COMMAND_DELTAS[k][0], sim[1] + assets.COMMAND_DELTAS[k][1])
-        dur = int(rng.choice(p["command_show_duration"]))
-        delay = int(rng.choice(p["command_show_delay"]))
-        self.show = self._show_list(self.commands, dur, delay)
-        first = self.show.pop(0)
+        if self.task_b:
+            self.show, first = [], None
+        else:
+            dur = int(rng.choice(p["command_show_duration"]))
+            delay = int(rng.choice(p["command_show_delay"]))
+            self.show = self._show_list(self.commands, dur, delay)
+            first = self.show.pop(0)
         d0 = assets.COMMAND_DELTAS[self.commands[0]]
         self.target = (self.pos[0] + d0[0], self.pos[1] + d0[1])
         self.cc = self.cs = self.cv = 0
         self.E = int(rng.choice(p["explosion_duration"]))
         self.D = int(rng.choice(p["explosion_delay"]))
         self.draw_cx, self.draw_cy, self.draw_rot = self.cx, self.cy, 0
-        return self._render(first, (self.cx, self.cy, 0)), {}
+        return self._obs(self._render(first, (self.cx, self.cy, 0))), {}
+
+    def _obs(self, frame):
+        if not self.task_b:
+            return frame
+        # _encode_commands_one_hot (mortar_mayhem_b.py:102-131): 20 x 9, slot order stay, right, left, up, down, ...
+        slot = {"stay": 0, "right": 1, "left": 2, "up": 3, "down": 4, "right_down": 5, "right_up": 6, "left_down": 7,
+                "left_up": 8}
+        vec = np.zeros(20 * 9, dtype=np.float32)
+        for c, k in enumerate(self.commands):
+            vec[9 * c + slot[assets.COMMAND_NAMES[k]]] = 1.0
+        return {"visual_observation": frame, "vector_observation": vec}
 
     @staticmethod
     def _show_list(commands, dur, delay):
@@ -325,7 +344,7 @@ class MortarMayhemOracle(_OracleEnv):
         if done:
             info = {"reward": _seq_sum(self.rewards), "length": len(self.rewards), "success": success,
                     "commands_completed": (self.cc - 1 + success) / self.n}
-        return self._render(icon, sprite), reward, done, False, info
+        return self._obs(self._render(icon, sprite)), reward, done, False, info
 
     # ---- frame -----------------------------------------------------------------------------------
     def _render(self, icon, sprite):
@@ -376,6 +395,56 @@ class GridMortarMayhemOracle(MortarMayhemOracle):
 
     def _agent_scale(self):
         return SCALE  # GridCharacterController(SCALE, ...) ignores agent_scale (mortar_mayhem_grid.py:249)
+
+
+class MortarMayhemBOracle(MortarMayhemOracle):
+    """mortar_mayhem_b.py:15-290 (MortarMayhemTaskBEnv): act-only variant, commands as a one-hot vector."""
+
+    env_id = "MortarMayhemB-v0"
+    task_b = True
+    spawn_offset = True
+    default_reset_parameters = {
+        "agent_scale": 1.0 * SCALE,
+        "agent_speed": 12.0 * SCALE,
+        "arena_size": 5,
+        "allowed_commands": 9,
+        "command_count": [10],
+        "explosion_duration": [6],
+        "explosion_delay": [18],
+        "visual_feedback": True,
+        "reward_command_failure": 0.0,
+        "reward_command_success": 0.1,
+        "reward_episode_success": 0.0,
+    }
+
+    @classmethod
+    def _check_params(cls, p):
+        assert p["allowed_commands"] >= 4 and p["allowed_commands"] <= 9
+        assert p["arena_size"] >= 2 and p["arena_size"] <= 6
+        assert max(p["command_count"]) <= 20, "20 commands are allowed at maximum"
+
+
+class GridMortarMayhemBOracle(MortarMayhemBOracle):
+    """mortar_mayhem_b_grid.py:15-290 (GridMortarMayhemTaskBEnv)."""
+
+    env_id = "MortarMayhemB-Grid-v0"
+    grid_locomotion = True
+    spawn_offset = False
+    default_reset_parameters = {
+        "agent_scale": 1.0 * SCALE,
+        "arena_size": 5,
+        "allowed_commands": 5,
+        "command_count": [10],
+        "explosion_duration": [2],
+        "explosion_delay": [6],
+        "visual_feedback": True,
+        "reward_command_failure": 0.0,
+        "reward_command_success": 0.1,
+        "reward_episode_success": 0.0,
+    }
+
+    def _agent_scale(self):
+        return SCALE
 
 
 class EndlessMortarMayhemOracle(MortarMayhemOracle):
@@ -650,7 +719,11 @@ class MysteryPathOracle(_OracleEnv):
         self.num_fails = 0
         self.cross_alpha = 0
         self.cross_x = self.cross_y = 0  # fall_off_rect top-left
+        self._after_reset()
         return self._render(cross=False), {}
+
+    def _after_reset(self):
+        pass
 
     def step(self, action):
         p = self.p
@@ -717,6 +790,99 @@ class MysteryPathOracle(_OracleEnv):
         if cross and self.cross_alpha == 255:
             _paste(frame, assets.fall_off_cross(SCALE), self.cross_x, self.cross_y)
         return _frame_to_obs(frame)
+
+
+class GridMysteryPathOracle(MysteryPathOracle):
+    """mystery_path_grid.py:15-280 (GridMysteryPathEnv): grid locomotion on the 7x7 path grid."""
+
+    env_id = "MysteryPath-Grid-v0"
+    default_reset_parameters = {
+        "max_steps": 128,
+        "agent_scale": 1.0 * SCALE,
+        "cardinal_origin_choice": [0, 1, 2, 3],
+        "show_origin": False,
+        "show_goal": False,
+        "visual_feedback": True,
+        "reward_goal": 1.0,
+        "reward_fall_off": 0.0,
+        "reward_path_progress": 0.0,
+        "reward_step": 0.0,
+    }
+
+    def process_reset_params(self, options):  # instance-level: adds the two keys the base class reads
+        p = dict(type(self).default_reset_parameters)
+        if options is not None:
+            for k, v in options.items():
+                assert k in p, "Provided reset parameter (" + str(k) + ") is not valid. Check spelling."
+                p[k] = v
+        p = dict(p)
+        p["_agent_scale_param"] = p["agent_scale"]
+        p["agent_scale"] = SCALE      # GridCharacterController(SCALE, ...) ignores agent_scale (:188)
+        p["agent_speed"] = 0.0
+        return p
+
+    def _after_reset(self):
+        self.gx, self.gy = self.start  # normalize(start * 12 + int(25 * SCALE))
+        self.cx, self.cy = 12 * self.gx + 6, 12 * self.gy + 6
+
+    def step(self, action):
+        p = self.p
+        reward = 0
+        done = False
+        success = 0
+        if self.off_path:  # reset_position(start) then a no-op controller step (:218-221)
+            self.gx, self.gy = self.start
+            action = 0
+        if action == 1:
+            self.rotation = (self.rotation + 90) % 360
+        if action == 2:
+            self.rotation = (self.rotation - 90) % 360
+        if action == 3:
+            face = self.rotation // 90
+            if face == 0 and self.gy > 0:
+                self.gy -= 1
+            elif face == 3 and self.gx < self.GRID - 1:
+                self.gx += 1
+            elif face == 2 and self.gy < self.GRID - 1:
+                self.gy += 1
+            elif face == 1 and self.gx > 0:
+                self.gx -= 1
+        self.cx, self.cy = 12 * self.gx + 6, 12 * self.gy + 6
+        pos = (self.gx, self.gy)
+        if pos == self.end:
+            reward += p["reward_goal"]
+            done = True
+            success = 1
+        else:
+            on_path = False
+            for node in self.path:
+                if pos == node:
+                    on_path = True
+                    if node not in self.visited and node != self.start and node != self.end:
+                        reward += p["reward_path_progress"]
+                        self.visited.add(node)
+                    break
+            if not on_path:
+                reward += p["reward_fall_off"]
+                self.num_fails += 1
+                if p["visual_feedback"]:
+                    self.cross_alpha = 255
+                self.off_path = True
+            else:
+                self.cross_alpha = 0
+                self.off_path = False
+            cross = assets.fall_off_cross(SCALE)
+            self.cross_x, self.cross_y = self.cx - (cross.w >> 1), self.cy - (cross.h >> 1)
+        reward += p["reward_step"]
+        self.rewards.append(reward)
+        self.t += 1
+        if self.t == self.max_episode_steps:
+            done = True
+        info = {}
+        if done:
+            info = {"reward": _seq_sum(self.rewards), "length": len(self.rewards), "success": success,
+                    "num_fails": self.num_fails}
+        return self._render(cross=True), reward, done, False, info
 
 
 # --------------------------------------------------------------------------------------------------
@@ -1062,6 +1228,9 @@ ORACLES = {
     "Endless-MortarMayhem-v0": EndlessMortarMayhemOracle,
     "MysteryPath-v0": MysteryPathOracle,
     "SearingSpotlights-v0": SearingSpotlightsOracle,
+    "MortarMayhemB-v0": MortarMayhemBOracle,
+    "MortarMayhemB-Grid-v0": GridMortarMayhemBOracle,
+    "MysteryPath-Grid-v0": GridMysteryPathOracle,
 }
 
 

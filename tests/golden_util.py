@@ -20,7 +20,15 @@ def load_case(name):
 
 
 def crc(obs) -> int:
+    """CRC of an observation; Dict observations (MortarMayhemB) hash visual then vector bytes."""
+    if isinstance(obs, dict):
+        return zlib.crc32(np.ascontiguousarray(obs["visual_observation"]).tobytes() +
+                          np.ascontiguousarray(obs["vector_observation"], dtype=np.float32).tobytes())
     return zlib.crc32(np.ascontiguousarray(obs).tobytes())
+
+
+def visual(obs):
+    return obs["visual_observation"] if isinstance(obs, dict) else obs
 
 
 def action_for(case, e, t):

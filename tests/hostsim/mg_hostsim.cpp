@@ -98,6 +98,7 @@ int run_rollout(const typename P::K& k, const void* assets, void* state, const m
     q.io.done = r->done;
     q.io.info = r->info;
     q.io.ground_truth = r->ground_truth;
+    q.io.vector_obs = r->vector_obs;
     q.io.flags = r->flags | MG_FLAG_AUTORESET;
     q.mode = MG_MODE_STEP;
     q.n = n;
@@ -118,14 +119,14 @@ extern "C" int mgsim_mm(const mg_mm_params* p, const void* assets, void* state, 
     if (mg_mm_check_params(p)) return MG_EINVAL;
     MgMMK k;
     mg_mm_derive(p, &k);
-    return run<MMPolicy>(k, assets, state, rng4, io, n, mode, p->variant == MG_MM_GRID ? 1 : 2);
+    return run<MMPolicy>(k, assets, state, rng4, io, n, mode, mg_mm_is_grid(p->variant) ? 1 : 2);
 }
 extern "C" int mgsim_mp(const mg_mp_params* p, const void* assets, void* state, const uint64_t* rng4,
                         const mg_step_io* io, int n, int mode) {
     if (mg_mp_check_params(p)) return MG_EINVAL;
     MgMPK k;
     mg_mp_derive(p, &k);
-    return run<MPPolicy>(k, assets, state, rng4, io, n, mode, 2);
+    return run<MPPolicy>(k, assets, state, rng4, io, n, mode, p->variant == MG_MP_GRID ? 1 : 2);
 }
 extern "C" int mgsim_ss(const mg_ss_params* p, const void* assets, void* state, const uint64_t* rng4,
                         const mg_step_io* io, int n, int mode) {
@@ -138,13 +139,13 @@ extern "C" int mgsim_mm_rollout(const mg_mm_params* p, const void* assets, void*
     if (mg_mm_check_params(p)) return MG_EINVAL;
     MgMMK k;
     mg_mm_derive(p, &k);
-    return run_rollout<MMPolicy>(k, assets, state, r, n, p->variant == MG_MM_GRID ? 1 : 2);
+    return run_rollout<MMPolicy>(k, assets, state, r, n, mg_mm_is_grid(p->variant) ? 1 : 2);
 }
 extern "C" int mgsim_mp_rollout(const mg_mp_params* p, const void* assets, void* state, const mg_rollout_io* r, int n) {
     if (mg_mp_check_params(p)) return MG_EINVAL;
     MgMPK k;
     mg_mp_derive(p, &k);
-    return run_rollout<MPPolicy>(k, assets, state, r, n, 2);
+    return run_rollout<MPPolicy>(k, assets, state, r, n, p->variant == MG_MP_GRID ? 1 : 2);
 }
 extern "C" int mgsim_ss_rollout(const mg_ss_params* p, const void* assets, void* state, const mg_rollout_io* r, int n) {
     if (mg_ss_check_params(p)) return MG_EINVAL;

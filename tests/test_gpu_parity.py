@@ -10,7 +10,8 @@ from replay_util import replay_golden_batched, replay_golden_single, rollout_vs_
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts", "ss_black"]
+CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts", "ss_black",
+         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -32,6 +33,9 @@ def test_golden_batched_autoreset(name):
     ("Endless-MortarMayhem-v0", {"explosion_delay": [4], "explosion_duration": [2], "agent_speed": 5.0}, 64, 2),
     ("MysteryPath-v0", {"max_steps": 40, "show_goal": True, "show_origin": True}, 64, 1),
     ("MysteryPath-v0", {"visual_feedback": False, "agent_scale": 0.3, "max_steps": 64}, 64, 0),
+    ("MortarMayhemB-v0", {"command_count": [1, 3], "explosion_delay": [4], "explosion_duration": [2]}, 64, 0),
+    ("MortarMayhemB-Grid-v0", {"arena_size": 4, "command_count": [2, 20]}, 64, 3),
+    ("MysteryPath-Grid-v0", {"max_steps": 30, "show_origin": True}, 64, 0),
     ("SearingSpotlights-v0", {"max_steps": 60}, 64, 0),
     ("SearingSpotlights-v0", {"max_steps": 50, "coins_visible": True, "exit_visible": True, "agent_visible": True,
                               "num_coins": [2, 4], "agent_health": 3, "spot_damage": 0.7, "initial_spawns": 6,

@@ -37,7 +37,7 @@ def test_struct_sizes_match_header():
     # sizes the C side asserts (mg_common.h static_asserts) and ctypes mirrors
     assert C.sizeof(L.ChoiceList) == 4 + 4 * L.MG_MAX_CHOICES
     assert C.sizeof(L.MMParams) == 24 + 5 * 68 + 4 + 5 * 8  # 4 bytes padding before the doubles
-    assert C.sizeof(L.StepIO) == 8 * 8 + 8 + 8
+    assert C.sizeof(L.StepIO) == 8 * 8 + 8 + 8 + 8
 
 
 def test_seed_sequence_matches_numpy():
@@ -214,4 +214,4 @@ def test_option_validation_and_loud_failure_without_gpu():
         with pytest.raises(L.MemGymError):
             mg.make("MortarMayhem-v0", num_envs=4)  # no CPU fallback
     with pytest.raises(NotImplementedError):
-        mg.make("MortarMayhemB-v0", num_envs=4)
+        mg.make("Endless-MysteryPath-v0", num_envs=4)

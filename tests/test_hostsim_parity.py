@@ -7,7 +7,8 @@ import pytest
 from hostsim_util import HostSimBackend
 from replay_util import replay_golden_batched, replay_golden_single, rollout_vs_oracle
 
-CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts", "ss_black"]
+CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts", "ss_black",
+         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts"]
 
 
 @pytest.fixture(scope="module")
@@ -34,6 +35,9 @@ def test_golden_batched_autoreset(name, backend):
     ("Endless-MortarMayhem-v0", {"explosion_delay": [4], "explosion_duration": [2], "agent_speed": 5.0}),
     ("MysteryPath-v0", {"max_steps": 40, "show_goal": True}),
     ("MysteryPath-v0", {"visual_feedback": False, "agent_scale": 0.3, "max_steps": 64}),
+    ("MortarMayhemB-v0", {"command_count": [1, 3], "explosion_delay": [4], "explosion_duration": [2]}),
+    ("MortarMayhemB-Grid-v0", {"arena_size": 4, "command_count": [2, 20]}),
+    ("MysteryPath-Grid-v0", {"max_steps": 30, "show_origin": True}),
     ("SearingSpotlights-v0", {"max_steps": 60}),
     ("SearingSpotlights-v0", {"max_steps": 50, "coins_visible": True, "exit_visible": True, "agent_visible": True,
                               "num_coins": [2, 4], "agent_health": 3, "spot_damage": 0.7, "initial_spawns": 6,
