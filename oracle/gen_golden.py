@@ -60,6 +60,21 @@ CASES = {
                                            "exit_visible": True, "light_threshold": 140, "light_dim_off_duration": 4,
                                            "initial_spawns": 6, "spot_min_speed": 0.008, "spot_max_speed": 0.02,
                                            "show_last_action": False, "num_coins": [2]}, 4, 320),
+    "ess": ("Endless-SearingSpotlights-v0", None, 6, 600),
+    "ess_opts": ("Endless-SearingSpotlights-v0", {"max_steps": 300, "steps_per_coin": 70, "initial_spawns": 2,
+                                                   "spawn_interval": 15, "agent_health": 6, "spot_damage": 0.5,
+                                                   "light_dim_off_duration": 10, "coin_show_duration": 12,
+                                                   "reward_inside_spotlight": -0.01, "reward_coin": 0.5,
+                                                   "agent_speed": 4.0, "agent_visible": True}, 4, 450),
+    "ess_black": ("Endless-SearingSpotlights-v0", {"black_background": True, "coins_visible": True,
+                                                    "light_threshold": 140, "light_dim_off_duration": 4,
+                                                    "initial_spawns": 5, "spot_min_speed": 0.008,
+                                                    "spot_max_speed": 0.02, "steps_per_coin": 90,
+                                                    "sample_agent_position": False, "show_last_positive_reward": False},
+                  4, 320),
+    "ess_nocoin": ("Endless-SearingSpotlights-v0", {"coin_enabled": False, "max_steps": 70, "initial_spawns": 6,
+                                                     "spot_min_speed": 0.01, "spot_max_speed": 0.03,
+                                                     "agent_health": 3}, 4, 200),
 }
 
 
@@ -125,6 +140,11 @@ def goal_seeking_actions(env_id, env, rng, e):
         if abs(cx - own_x) > 2:
             return np.asarray([_toward(cx, own_x, 1), 0])
         return np.asarray([0, _toward(cy, 12 * ny + 6, 1)])
+    if env_id == "Endless-SearingSpotlights-v0":
+        if env.coin is None:
+            return rand
+        goal = env.coin.location
+        return np.asarray([_toward(cx, int(goal[0]), 1), _toward(cy, int(goal[1]), 1)])
     if env_id == "SearingSpotlights-v0":
         goal = env.coins[0].location if env.coins else env.exit.location
         return np.asarray([_toward(cx, int(goal[0]), 1), _toward(cy, int(goal[1]), 1)])
@@ -139,15 +159,19 @@ def _split(obs):
     return obs, obs.tobytes(), None
 
 
-def run_case(name, make_env, env_id, options, n_envs, steps, seed0=100):
+def run_case(name, make_env, env_id, options, n_envs, steps, seed0=100, record_gt=False):
     rng = np.random.default_rng(zlib.crc32(name.encode()))
     rec = {k: [] for k in ("action", "reward", "done", "crc", "reset_crc")}
     frames, frame_idx = [], []
     vecs, vec_idx = [], []
     infos = []
+    gts, gt0s = [], []  # per-step info["ground_truth"] (envs that publish it every step) / the reset's
     for e in range(n_envs):
         env = make_env(env_id)
         obs, info = env.reset(seed=seed0 + e, options=options)
+        gt_l = []
+        if "ground_truth" in info:
+            gt0s.append(np.asarray(info["ground_truth"], dtype=np.float64))
         vis, blob, vec = _split(obs)
         frames.append(vis.copy())
         frame_idx.append((e, -1))
@@ -161,6 +185,8 @@ def run_case(name, make_env, env_id, options, n_envs, steps, seed0=100):
             obs, reward, done, trunc, info = env.step(a)
             assert trunc is False
             ep_rewards.append(reward)
+            if "ground_truth" in info:
+                gt_l.append(np.asarray(info["ground_truth"], dtype=np.float64))
             a_l.append(np.asarray(a, dtype=np.int64).reshape(-1))
             r_l.append(float(reward))
             d_l.append(bool(done))
@@ -191,6 +217,8 @@ def run_case(name, make_env, env_id, options, n_envs, steps, seed0=100):
             rc_l.append(rc)
         for k, v in zip(("action", "reward", "done", "crc", "reset_crc"), (a_l, r_l, d_l, c_l, rc_l)):
             rec[k].append(np.asarray(v))
+        if gt_l:
+            gts.append(np.stack(gt_l))
     out = {k: np.stack(v) for k, v in rec.items()}
     out["crc"] = out["crc"].astype(np.uint32)
     out["reset_crc"] = out["reset_crc"].astype(np.uint32)
@@ -199,6 +227,9 @@ def run_case(name, make_env, env_id, options, n_envs, steps, seed0=100):
     if vecs:
         out["vecs"] = np.stack(vecs)
         out["vec_idx"] = np.asarray(vec_idx, dtype=np.int64)
+    if record_gt and gts:
+        out["gt"] = np.stack(gts)      # [env][t][k]
+        out["gt_reset"] = np.stack(gt0s)
     out["seed0"] = np.asarray(seed0)
     import json
     out["infos_json"] = np.asarray(json.dumps(infos))
@@ -218,7 +249,7 @@ def main(argv):
     for name, (env_id, options, n_envs, steps) in CASES.items():
         if only and name not in only:
             continue
-        out = run_case(name, gymnasium.make, env_id, options, n_envs, steps)
+        out = run_case(name, gymnasium.make, env_id, options, n_envs, steps, record_gt=name.startswith(("ess", "emp")))
         path = os.path.join(OUT, f"ref_{name}.npz")
         np.savez_compressed(path, **out)
         print(name, env_id, "episodes:", int(out["done"].sum()), "frames:", len(out["frames"]),

@@ -1192,7 +1192,9 @@ class SearingSpotlightsOracle(_OracleEnv):
                 else:
                     dst.px[...] = R.map_rgb((255, 255, 255)) if st == "white" else 0
             elif layer == "coin":
-                if self.num_coins > 0:
+                if getattr(self, "coin_layer_opaque", False):
+                    dst.px[...] = 0
+                elif self.num_coins > 0:
                     cs = R.Surface(SCREEN, SCREEN)
                     R.fill(cs, 255)
                     cs.colorkey = 255
@@ -1222,6 +1224,196 @@ class SearingSpotlightsOracle(_OracleEnv):
         return R.array3d(dst)
 
 
+class EndlessSearingSpotlightsOracle(SearingSpotlightsOracle):
+    """endless_searing_spotlights.py:15-504 (EndlessSearingSpotlightsEnv): one respawning coin, no exit, constant
+    spawn interval, ``steps_per_coin`` time limit, coin layer above the spotlights for ``coin_show_duration`` steps
+    after every (re)spawn, ground truth = (agent centre, coin location) / 84 every step."""
+
+    env_id = "Endless-SearingSpotlights-v0"
+    default_reset_parameters = {
+        "max_steps": -1, "steps_per_coin": 160, "initial_spawns": 3, "spawn_interval": 50,
+        "spot_min_radius": 30.0 * SCALE, "spot_max_radius": 55.0 * SCALE, "spot_min_speed": 0.0025,
+        "spot_max_speed": 0.0075, "spot_damage": 1.0, "visual_feedback": True, "black_background": False,
+        "hide_chessboard": False, "light_dim_off_duration": 6, "light_threshold": 255, "coin_enabled": True,
+        "coin_scale": 1.5 * SCALE, "coin_show_duration": 6, "coins_visible": False, "agent_speed": 12.0 * SCALE,
+        "agent_health": 10, "agent_scale": 1.0 * SCALE, "agent_visible": False, "sample_agent_position": True,
+        "show_last_action": True, "show_last_positive_reward": True, "reward_inside_spotlight": 0.0,
+        "reward_outside_spotlight": 0.0, "reward_death": 0.0, "reward_coin": 0.25,
+    }
+
+    @classmethod
+    def _check_params(cls, p):
+        # step() paints the action boxes unconditionally with self.action_colors, which only exists after a
+        # reset with show_last_action (endless_searing_spotlights.py:349-354, 421-424): AttributeError otherwise
+        assert p["show_last_action"], "the reference crashes in step() without show_last_action"
+
+    def _gt(self):
+        coin = np.asarray(self.coin, dtype=np.float64) if self.p["coin_enabled"] else np.zeros(2)
+        return np.concatenate((np.asarray([self.cx, self.cy], dtype=np.float64), coin)) / SCREEN
+
+    def _spawn_coin(self, rng):
+        """_spawn_coin (:256-269): the sampler is reset, only the OLD coin's surroundings are blocked."""
+        self.spawn_mask = np.zeros((SCREEN, SCREEN), dtype=bool)
+        if self.coin is not None:
+            self._block(self.coin[0], self.coin[1], 28)
+        x, y = self._sample(rng, 28)
+        x, y = x + int(rng.integers(2, 4)), y + int(rng.integers(2, 4))
+        self.coin = self._clamp_spawn(x, y)
+
+    def reset(self, seed=None, options=None):
+        rng = self._seed(seed)
+        p = self.p = self.process_reset_params(options)
+        self.max_episode_steps = p["max_steps"]
+        self.t = 0
+        self.coin_t = 0
+        if p["hide_chessboard"]:
+            self.bg_state["blue"] = self.bg_state["red"] = "white"
+        self.spawn_mask = np.zeros((SCREEN, SCREEN), dtype=bool)
+        self.rewards = []
+        self.last_action = [0, 0]
+        rotation = int(rng.choice([0, 45, 90, 135, 180, 225, 270, 315]))
+        self.sprites = assets.agent_sprites(p["agent_scale"])
+        self.radius = int(25 * p["agent_scale"])
+        self.rotation = rotation
+        if p["sample_agent_position"]:
+            x, y = self._sample(rng, 28)
+            x, y = x + int(rng.integers(2, 4)), y + int(rng.integers(2, 4))
+        else:
+            x, y = SCREEN // 2, SCREEN // 2
+            self._block(x, y)
+        self.cx, self.cy = int(x), int(y)
+        self.agent_health = p["agent_health"]
+        self.hp = self.agent_health
+        q = self.q = int(SCREEN // 4)
+        # top bar: a fresh (black) surface, green health half, action boxes (:345-360) — no grey fill here
+        self.bar = np.zeros((self.BAR_H, SCREEN), dtype=np.uint32)
+        self.bar[:, 0:q * 2] = R.map_rgb((0, 255, 0))
+        self.act_colors = [(120, 120, 120), (116, 1, 113), (255, 94, 14)]
+        self.bar[:, q * 2:q * 3] = R.map_rgb(self.act_colors[0])
+        self.bar[:, q * 3:q * 4] = R.map_rgb(self.act_colors[0])
+        if p["show_last_positive_reward"]:
+            self.last_reward = 0.0
+            self.coin_bar = (int(q * 2.75), int(q * 0.5))
+        self.alpha = 0 if p["light_dim_off_duration"] > 0 else max(0, min(255, p["light_threshold"]))
+        self.spots = []
+        self.spawn_timer = 0
+        for _ in range(p["initial_spawns"]):
+            self.spots.append(self._new_spot(rng))
+        self.coins_collected = 0
+        self.coin = None
+        self.coin_radius = int(10 * p["coin_scale"])
+        if p["coin_enabled"]:
+            self._spawn_coin(rng)
+        self.bg = "blue"
+        if p["black_background"]:
+            self.bg_state["blue"] = "black"
+        return self._render([], 0), {"ground_truth": self._gt()}
+
+    def step(self, action):
+        p = self.p
+        rng = self._rng
+        self.cx, self.cy, self.rotation = move_clamped(
+            self.cx, self.cy, self.rotation, action, p["agent_speed"], self.radius,
+            (0, self.BAR_H, SCREEN, SCREEN - self.BAR_H))
+        q = self.q
+        self.bar[:, q * 2:q * 3] = R.map_rgb(self.act_colors[int(self.last_action[0])])
+        self.bar[:, q * 3:q * 4] = R.map_rgb(self.act_colors[int(self.last_action[1])])
+        self.last_action = action
+        if self.alpha <= p["light_threshold"]:
+            if p["light_dim_off_duration"] > 0:
+                self.alpha = max(0, min(255, self.alpha + int(255 / p["light_dim_off_duration"])))
+            else:
+                self.alpha = max(0, min(255, p["light_threshold"]))
+        reward = 0.0
+        # -- spotlight task (:179-234): a new spotlight every spawn_interval steps, forever
+        r = 0.0
+        spot_done = False
+        self.spawn_timer += 1
+        if self.spawn_timer >= p["spawn_interval"]:
+            self.spots.append(self._new_spot(rng))
+            self.spawn_timer = 0
+        discs = []
+        hit = 0
+        i = 0
+        while i < len(self.spots):
+            spot = self.spots[i]
+            if spot.done:
+                self.spots.remove(spot)
+            else:
+                discs.append((spot.advance(), int(spot.radius)))
+                if spot.hits(self.cx, self.cy, self.radius):
+                    hit += 1
+            i += 1
+        if hit > 0:
+            self.hp -= p["spot_damage"]
+            r += p["reward_inside_spotlight"]
+            width = int(SCREEN // 2 * (1 - self.hp / self.agent_health))
+            if width > 0:
+                self.bar[:, 0:min(width, SCREEN)] = R.map_rgb((255, 0, 0))
+            self.bg = "red" if p["visual_feedback"] else "blue"
+        else:
+            self.bg = "blue"
+            r += p["reward_outside_spotlight"]
+        if p["black_background"]:
+            self.bg_state[self.bg] = "black"
+        if self.hp <= 0:
+            spot_done = True
+            r += p["reward_death"]
+        reward += r
+        # -- coin task (:271-292)
+        if p["coin_enabled"]:
+            r = 0.0
+            dx, dy = float(self.cx) - float(self.coin[0]), float(self.cy) - float(self.coin[1])
+            if math.sqrt(dx * dx + dy * dy) <= self.coin_radius + self.radius:
+                r += p["reward_coin"]
+                self.coins_collected += 1
+                self.coin_t = 0
+                self._spawn_coin(rng)
+            reward += r
+        done = spot_done
+        self.t += 1
+        self.coin_t += 1
+        if self.coin_t == p["steps_per_coin"] and p["coin_enabled"]:
+            done = True
+        if self.t == self.max_episode_steps:
+            done = True
+        if p["show_last_positive_reward"]:
+            x0, w = self.coin_bar
+            self.bar[:, x0:x0 + w] = R.map_rgb((255, 255, 0) if self.last_reward > 0 else (50, 50, 50))
+            self.last_reward = reward
+        self.rewards.append(reward)
+        info = {"ground_truth": self._gt()}
+        if done:
+            info = {"reward": _seq_sum(self.rewards), "length": len(self.rewards),
+                    "agent_health": self.hp / self.agent_health, "coins_collected": self.coins_collected,
+                    "ground_truth": self._gt()}
+        return self._render(discs, self.rotation), reward, done, False, info
+
+    # ---- frame (:376-391 / 463-478): the coin layer sits above the spotlights while the coin is fresh ----
+    def _layer_order(self):
+        p = self.p
+        layers = ["bg", "spot", "bar"]
+        sid = 1
+        if p["coins_visible"] or self.coin_t < p["coin_show_duration"]:
+            layers.insert(sid + 1, "coin")
+        else:
+            layers.insert(sid, "coin")
+            sid += 1
+        if p["agent_visible"]:
+            layers.insert(sid + 3, "agent")
+        else:
+            layers.insert(sid, "agent")
+            sid += 1
+        return layers
+
+    def _render(self, discs, sprite_rot):
+        # coin_surface is a fresh opaque black surface when the coin is disabled (never filled / colour-keyed)
+        self.num_coins = 1
+        self.coins = [self.coin] if self.p["coin_enabled"] else []
+        self.coin_layer_opaque = not self.p["coin_enabled"]
+        return super()._render(discs, sprite_rot)
+
+
 ORACLES = {
     "MortarMayhem-v0": MortarMayhemOracle,
     "MortarMayhem-Grid-v0": GridMortarMayhemOracle,
@@ -1231,6 +1423,7 @@ ORACLES = {
     "MortarMayhemB-v0": MortarMayhemBOracle,
     "MortarMayhemB-Grid-v0": GridMortarMayhemBOracle,
     "MysteryPath-Grid-v0": GridMysteryPathOracle,
+    "Endless-SearingSpotlights-v0": EndlessSearingSpotlightsOracle,
 }
 
 

@@ -7,7 +7,7 @@ from oracle import memgym_oracle as O
 from golden_util import action_for, crc, load_case, visual
 
 CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts", "ss_black",
-         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts"]
+         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts", "ess", "ess_opts", "ess_black", "ess_nocoin"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -19,8 +19,10 @@ def test_oracle_replays_reference(name):
     infos = {(r["env"], r["t"]): r for r in case["infos"]}
     for e in range(n_envs):
         env = O.make(case["env_id"])
-        obs, _ = env.reset(seed=case["seed0"] + e, options=case["options"])
+        obs, info = env.reset(seed=case["seed0"] + e, options=case["options"])
         assert np.array_equal(visual(obs), case["frames"][case["frame_map"][(e, -1)]])
+        if "gt" in case:
+            assert np.array_equal(np.asarray(info["ground_truth"], dtype=np.float64), case["gt_reset"][e])
         for t in range(steps):
             obs, reward, done, trunc, info = env.step(action_for(case, e, t))
             assert trunc is False
@@ -30,6 +32,8 @@ def test_oracle_replays_reference(name):
                 want = case["frames"][case["frame_map"][(e, t)]]
                 assert np.array_equal(visual(obs), want), (e, t, int((visual(obs) != want).sum()))
             assert crc(obs) == int(case["crc"][e, t]), (e, t)
+            if "gt" in case:
+                assert np.array_equal(np.asarray(info["ground_truth"], dtype=np.float64), case["gt"][e, t]), (e, t)
             if done:
                 ref = infos[(e, t)]
                 assert float(info["reward"]) == ref["reward_seq_sum"]
