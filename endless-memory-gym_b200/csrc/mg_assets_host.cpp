@@ -404,7 +404,7 @@ extern "C" long mg_ss_build_assets(const mg_ss_params* p, void* host_out, size_t
     if (!p) return MG_EINVAL;
     Builder b;
     if (!build_agent(b, p->agent_scale, false, true)) return MG_EINVAL;
-    if (!build_exit(b, p->exit_scale)) return MG_EINVAL;
+    if (p->variant != MG_SS_ENDLESS && !build_exit(b, p->exit_scale)) return MG_EINVAL;
     if (!build_coin(b, p->coin_scale)) return MG_EINVAL;
     b.add_disc_tables();
     if (!b.discs_ok) return MG_EINVAL;

@@ -181,7 +181,8 @@ struct MgSSState {
     uint8_t pad0[5];
     int16_t coins[MG_SS_MAXCOINS][2];
     MgSSSpot spots[MG_SS_MAXSPOTS];
-    uint8_t pad1[80];
+    int32_t coin_t;            // Endless: steps since the coin (re)spawned
+    uint8_t pad1[76];
 };
 
 struct MgSSFrame {
@@ -190,7 +191,10 @@ struct MgSSFrame {
     int16_t red_w_max, red_now;
     uint8_t srot, alpha, bg_kind, n_discs;   // bg_kind: 0 blue chessboard, 1 red chessboard, 2 white, 3 black
     uint8_t n_coins, exit_open, bar_c0, bar_c1;
-    uint8_t coin_bar, pad[3];
+    uint8_t coin_bar;
+    uint8_t coin_above;   // Endless: the coin layer sits above the spotlight layer this frame (layers_alt order)
+    uint8_t coin_black;   // Endless without a coin: the (never cleared) coin surface is an opaque black layer
+    uint8_t pad[1];
     int16_t coins[MG_SS_MAXCOINS][2];
     int16_t disc_x[MG_SS_MAXSPOTS], disc_y[MG_SS_MAXSPOTS];
     uint8_t disc_r[MG_SS_MAXSPOTS];

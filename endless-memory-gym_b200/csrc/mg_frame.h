@@ -223,6 +223,10 @@ MG_HD bool mg_ss_layer_at(const MgAssetView& a, const MgSSFrame& f, int layer, i
         return mg_dense_at(a, slot, f.exit_x - (sp.w >> 1), f.exit_y - (sp.h >> 1), x, y, col);
     }
     if (layer == 3) {  // MG_SS_L_COIN: coins are drawn in list order, so the last one covering the pixel wins
+        if (f.coin_black) {  // Endless with coin_enabled=False: an opaque black surface
+            col = 0u;
+            return true;
+        }
         const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
         for (int c = (int)f.n_coins - 1; c >= 0; --c)
             if (mg_dense_at(a, MG_SPR_COIN, f.coins[c][0] - (sp.w >> 1), f.coins[c][1] - (sp.h >> 1), x, y, col))
@@ -325,6 +329,7 @@ struct MgSSBaseDesc {  // what `base` currently shows
     int32_t lut_alpha;  // alpha the dim LUT was built for (-1: none)
     int16_t sx, sy, exit_x, exit_y;
     uint8_t srot, bg_kind, exit_open, n_coins;
+    uint8_t coin_above, pad[3];  // which painter's order `base` was built in
     int16_t coins[MG_SS_MAXCOINS][2];
 };
 
@@ -410,7 +415,10 @@ MG_HD void mg_ss_draw_bar(Ctx& c, uint8_t* base, const MgSSDrawK& k, const MgSSF
 
 template <class Ctx>
 MG_HD void mg_ss_draw_layer(Ctx& c, uint8_t* base, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f, int L) {
-    if (L == 3) {
+    if (L == 3 && f.coin_black) {
+        mg_ss_fill_bg(c, base, 0u, 0u);
+        c.sync();
+    } else if (L == 3) {
         const MgSprite sp = a.hdr->sprite[MG_SPR_COIN];
         for (int q = 0; q < (int)f.n_coins; ++q) {
             mg_sprite_draw(c, base, a, MG_SPR_COIN, f.coins[q][0] - (sp.w >> 1), f.coins[q][1] - (sp.h >> 1));
@@ -441,7 +449,7 @@ MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, cons
     uint8_t* base = wm->base;
     const MgSSBaseDesc d = wm->desc;
     const int half = a.hdr->agent_dim >> 1;
-    bool same_rest = simple && d.valid && d.bg_kind == f.bg_kind && d.exit_x == f.exit_x && d.exit_y == f.exit_y &&
+    bool same_rest = simple && d.valid && d.coin_above == f.coin_above && d.bg_kind == f.bg_kind && d.exit_x == f.exit_x && d.exit_y == f.exit_y &&
                      d.exit_open == f.exit_open && d.n_coins == f.n_coins;
     for (int q = 0; same_rest && q < (int)f.n_coins; ++q)
         same_rest = d.coins[q][0] == f.coins[q][0] && d.coins[q][1] == f.coins[q][1];
@@ -476,6 +484,7 @@ MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, cons
         w.bg_kind = f.bg_kind;
         w.exit_x = f.exit_x, w.exit_y = f.exit_y, w.exit_open = f.exit_open;
         w.n_coins = f.n_coins;
+        w.coin_above = f.coin_above;
         for (int q = 0; q < (int)f.n_coins; ++q) w.coins[q][0] = f.coins[q][0], w.coins[q][1] = f.coins[q][1];
     }
     c.sync();
@@ -577,6 +586,10 @@ MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDraw
                 int L = k.layers[li];
                 int slot = L == 5 ? MG_SPR_AGENT0 + f.srot : (L == 4 ? (f.exit_open ? MG_SPR_EXIT_OPEN : MG_SPR_EXIT_CLOSED) : MG_SPR_COIN);
                 if (L != 3 && L != 4 && L != 5) continue;
+                if (L == 3 && f.coin_black) {  // an opaque layer above the spotlights: nothing is dimmed
+                    for (int w = c.lane; w < MG_SS_LIT_WORDS; w += c.nl) wm->lit[w] = 0xFFFFFFFFu;
+                    continue;
+                }
                 const MgSprite sp = a.hdr->sprite[slot];
                 const uint32_t* e = a.entries + sp.first;
                 int reps = L == 3 ? (int)f.n_coins : 1;

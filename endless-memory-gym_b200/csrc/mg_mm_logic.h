@@ -363,7 +363,7 @@ MG_HD bool mg_mm_step_env(const MgMMK& k, MgMMState& s, int a0, int a1, double& 
             }
             info[MG_INFO_GT0] = (double)s.tx / 5.0;
             info[MG_INFO_GT1] = (double)s.ty / 5.0;
-            info[7] = 0.0;
+            info[7] = info[8] = info[9] = 0.0;
         }
     }
     return done;

@@ -279,7 +279,7 @@ MG_HD bool mg_mp_step_env(const MgMPK& k, MgMPState& s, int a0, int a1, double& 
             info[MG_INFO_B] = 0.0;
             info[MG_INFO_GT0] = 0.0;
             info[MG_INFO_GT1] = 0.0;
-            info[7] = 0.0;
+            info[7] = info[8] = info[9] = 0.0;
         }
     }
     return done;

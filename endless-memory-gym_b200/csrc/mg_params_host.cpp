@@ -147,11 +147,28 @@ extern "C" int mg_ss_check_params(const mg_ss_params* p) {
         mg_set_err("params is NULL");
         return MG_EINVAL;
     }
-    if (!p->use_exit) {  // the reference crashes in reset (self.exit is undefined, searing_spotlights.py:416,432)
+    const bool endless = p->variant == MG_SS_ENDLESS;
+    if (p->variant != MG_SS_FINITE && !endless) {
+        mg_set_err("variant must be MG_SS_FINITE or MG_SS_ENDLESS");
+        return MG_EINVAL;
+    }
+    if (endless) {
+        // step() paints the action boxes with self.action_colors unconditionally, which only a reset with
+        // show_last_action creates (endless_searing_spotlights.py:349-354, 421-424): AttributeError otherwise
+        if (!p->show_last_action) {
+            mg_set_err("show_last_action=False is not supported (the reference raises AttributeError in step)");
+            return MG_EINVAL;
+        }
+        if (p->spawn_interval < 1) {
+            mg_set_err("spawn_interval must be >= 1");
+            return MG_EINVAL;
+        }
+    }
+    if (!endless && !p->use_exit) {  // the reference crashes in reset (self.exit is undefined, searing_spotlights.py:416,432)
         mg_set_err("use_exit=False is not supported (the reference raises AttributeError)");
         return MG_EINVAL;
     }
-    if (!check_list(p->num_coins, 1, MG_SS_MAXCOINS, "num_coins")) return MG_EINVAL;  // 0 coins: ZeroDivisionError at done (:553)
+    if (!endless && !check_list(p->num_coins, 1, MG_SS_MAXCOINS, "num_coins")) return MG_EINVAL;  // 0 coins: ZeroDivisionError at done (:553)
     if (!(p->agent_health > 0.0)) {
         mg_set_err("agent_health must be > 0");
         return MG_EINVAL;
@@ -174,8 +191,8 @@ extern "C" int mg_ss_check_params(const mg_ss_params* p) {
         mg_set_err("spot speeds must satisfy 0 < min <= max <= 1");
         return MG_EINVAL;
     }
-    if ((int)(10 * p->coin_scale) > MG_MAX_DISC_R || p->coin_scale < 0.0 || (int)(20 * p->exit_scale) < 2 ||
-        (int)(20 * p->exit_scale) > 84) {
+    if ((int)(10 * p->coin_scale) > MG_MAX_DISC_R || p->coin_scale < 0.0 ||
+        (!endless && ((int)(20 * p->exit_scale) < 2 || (int)(20 * p->exit_scale) > 84))) {
         mg_set_err("coin_scale / exit_scale out of range");
         return MG_EINVAL;
     }
@@ -188,15 +205,15 @@ extern "C" int mg_ss_check_params(const mg_ss_params* p) {
         return MG_EINVAL;
     }
     // spotlights alive at once: the initial ones plus one per spawn interval within the longest traversal
-    int interval0 = (int)(p->initial_spawn_interval + p->spawn_interval_threshold);
-    if (p->num_spawns > 0 && interval0 < 1) {
+    int interval0 = endless ? p->spawn_interval : (int)(p->initial_spawn_interval + p->spawn_interval_threshold);
+    if (!endless && p->num_spawns > 0 && interval0 < 1) {
         mg_set_err("initial_spawn_interval + spawn_interval_threshold must be >= 1");
         return MG_EINVAL;
     }
     double life = 1.0 / p->spot_min_speed + 2.0;
     if (p->max_steps > 0 && (double)p->max_steps < life) life = (double)p->max_steps;
-    long spawned = p->num_spawns > 0 ? (long)(life / (interval0 > 0 ? interval0 : 1)) + 1 : 0;
-    if (spawned > p->num_spawns) spawned = p->num_spawns;
+    long spawned = (endless || p->num_spawns > 0) ? (long)(life / (interval0 > 0 ? interval0 : 1)) + 1 : 0;
+    if (!endless && spawned > p->num_spawns) spawned = p->num_spawns;
     if (p->initial_spawns + spawned > MG_SS_MAXSPOTS) {
         mg_set_err("too many concurrent spotlights for the env record (MG_SS_MAXSPOTS = 32)");
         return MG_EINVAL;
@@ -235,6 +252,31 @@ void mg_ss_derive(const mg_ss_params* p, MgSSK* k) {
         order[at] = v;
         n++;
     };
+    k->endless = p->variant == MG_SS_ENDLESS ? 1 : 0;
+    if (k->endless) {
+        // endless_searing_spotlights.py:376-391 / 463-478: bg, spot, bar; coin above the spotlights while visible or
+        // fresh (layers_alt) else below (layers); then the agent. No exit layer.
+        for (int fresh = 0; fresh < 2; ++fresh) {
+            n = 0;
+            order[n++] = MG_SS_L_BG;
+            order[n++] = MG_SS_L_SPOT;
+            order[n++] = MG_SS_L_BAR;
+            int sid = 1;
+            if (p->coins_visible || fresh)
+                insert(sid + 1, MG_SS_L_COIN);
+            else
+                insert(sid++, MG_SS_L_COIN);
+            if (p->agent_visible)
+                insert(sid + 3, MG_SS_L_AGENT);
+            else
+                insert(sid++, MG_SS_L_AGENT);
+            for (int i = 0; i < n; ++i) (fresh ? k->layers_alt : k->layers)[i] = order[i];
+        }
+        k->n_layers = n;
+        k->cb_x = (int)(q * 2.75);
+        k->cb_w = (int)(q * 0.5);
+        return;
+    }
     order[n++] = MG_SS_L_BG;
     order[n++] = MG_SS_L_SPOT;
     order[n++] = MG_SS_L_BAR;
@@ -252,5 +294,5 @@ void mg_ss_derive(const mg_ss_params* p, MgSSK* k) {
     else
         insert(sid++, MG_SS_L_AGENT);
     k->n_layers = n;
-    for (int i = 0; i < n; ++i) k->layers[i] = order[i];
+    for (int i = 0; i < n; ++i) k->layers[i] = k->layers_alt[i] = order[i];
 }

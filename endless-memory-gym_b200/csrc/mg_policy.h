@@ -44,7 +44,7 @@ MG_HDN void mg_env_logic(const typename E::K& k, const MgKIO& q, const MgAssetVi
     double* const reward_out = q.io.reward + (size_t)t * q.rew_stride + env;
     uint8_t* const done_out = q.io.done + (size_t)t * q.done_stride + env;
     double* const info_out = q.io.info + (size_t)t * q.info_stride + MG_INFO_COLS * (size_t)env;
-    double* gt = q.io.ground_truth ? q.io.ground_truth + 2 * (size_t)env : nullptr;
+    double* gt = q.io.ground_truth ? q.io.ground_truth + MG_GT_COLS * (size_t)env : nullptr;
     job.nframes = 0;
     if (q.mode == MG_MODE_RESET) {
         if (q.io.reset_mask && !q.io.reset_mask[env]) return;
@@ -189,6 +189,7 @@ struct SSPolicy {
         double* const reward_out = q.io.reward + (size_t)t * q.rew_stride + env;
         uint8_t* const done_out = q.io.done + (size_t)t * q.done_stride + env;
         double* const info_out = q.io.info + (size_t)t * q.info_stride + MG_INFO_COLS * (size_t)env;
+        double* const gt = q.io.ground_truth ? q.io.ground_truth + MG_GT_COLS * (size_t)env : nullptr;
         // the sampler's row masks borrow the base buffer: a reset rebuilds the base anyway
         MgSSWarpMem* wm = reinterpret_cast<MgSSWarpMem*>(sc.warp);
         MgSSSampler& g = *reinterpret_cast<MgSSSampler*>(wm->base);
@@ -220,7 +221,10 @@ struct SSPolicy {
         c.sync();
         if (tmp.action == 1) {
             if (c.lane == 0) wm->desc.valid = 0;
-            mg_ss_reset_env(c, k, s, fr[0], g, rt);
+            if (k.endless)
+                mg_ess_reset_env(c, k, s, fr[0], g, rt, gt);
+            else
+                mg_ss_reset_env(c, k, s, fr[0], g, rt);
             if (c.lane == 0) {
                 job.nframes = 1;
                 job.to_final[0] = 0;
@@ -231,9 +235,19 @@ struct SSPolicy {
         if (tmp.action != 2) return;
         mg_ss_step_b(c, k, trig(a), s, tmp, fr[0]);
         c.sync();
+        MgESSCarry carry;  // lane 0's registers carry C1's results to C2
+        if (k.endless) {
+            if (c.lane == 0 && mg_ess_step_c1(k, s, tmp, carry)) {
+                tmp.action = 4;  // coin collected: the team respawns it on the (now invalid) base buffer
+                wm->desc.valid = 0;
+            }
+            c.sync();
+            if (tmp.action == 4) mg_ess_spawn_coin(c, k, s, g, rt, true);
+        }
         if (c.lane == 0) {
             double reward;
-            bool done = mg_ss_step_c(k, s, tmp, reward, info_out, fr[0]);
+            bool done = k.endless ? mg_ess_step_c2(k, s, tmp, carry, reward, info_out, fr[0], gt)
+                                  : mg_ss_step_c(k, s, tmp, reward, info_out, fr[0]);
             *reward_out = reward;
             *done_out = done ? 1 : 0;
             job.nframes = 1;
@@ -254,7 +268,10 @@ struct SSPolicy {
                 c.sync();
             }
             if (c.lane == 0) wm->desc.valid = 0;
-            mg_ss_reset_env(c, k, s, fr[at], g, rt);
+            if (k.endless)
+                mg_ess_reset_env(c, k, s, fr[at], g, rt, gt);
+            else
+                mg_ss_reset_env(c, k, s, fr[at], g, rt);
             if (c.lane == 0) {
                 // frame 0 (terminal) has already been written: hand only the reset frame to the frame loop
                 if (at) fr[0] = fr[1];
@@ -270,7 +287,7 @@ struct SSPolicy {
                            bool stream) {
         MgSSDrawK d;
         d.n_layers = k.n_layers;
-        for (int i = 0; i < 6; ++i) d.layers[i] = k.layers[i];
+        for (int i = 0; i < 6; ++i) d.layers[i] = f.coin_above ? k.layers_alt[i] : k.layers[i];
         d.cb_x = k.cb_x;
         d.cb_w = k.cb_w;
         d.show_last_action = k.p.show_last_action;

@@ -31,6 +31,8 @@ struct MgSSK {
     int32_t cb_x, cb_w;         // last-positive-reward box on the top bar
     int32_t n_layers;
     int32_t layers[6];          // painter's order (searing_spotlights.py:526-542), MG_SS_L_*
+    int32_t layers_alt[6];      // Endless: the order while the coin is fresh (coin layer above the spotlights)
+    int32_t endless;            // Endless-SearingSpotlights-v0
     int32_t clamp_off;          // int(30 * SCALE)
     double exit_radius;         // 20 / 2 * exit_scale
     double spawn_base;          // sqrt(84^2 + 84^2) / 2
@@ -104,6 +106,8 @@ MG_HD void mg_ss_clamp_spawn(const MgSSK& k, int& x, int& y) {
 }
 
 MG_HD void mg_ss_frame_common(const MgSSState& s, int srot, MgSSFrame& f) {
+    f.coin_above = 0;
+    f.coin_black = 0;
     f.sx = s.cx;
     f.sy = s.cy;
     f.srot = (uint8_t)srot;
@@ -329,7 +333,13 @@ MG_HD_NOINLINE void mg_ss_step_a(const MgSSK& k, MgSSState& s, int a0, int a1, M
         s.alpha = (uint8_t)(a < 0 ? 0 : (a > 255 ? 255 : a));
     }
     s.spawn_timer++;
-    if (s.spawns_left > 0 && s.spawn_timer >= k.interval0) {
+    if (k.endless) {  // a new spotlight every spawn_interval steps, forever (endless_searing_spotlights.py:189-194)
+        if (s.spawn_timer >= k.p.spawn_interval) {
+            // (a full record would drop the spawn WITH its five draws; mg_ss_check_params rules that out)
+            if (s.n_spots < MG_SS_MAXSPOTS) mg_ss_new_spot(k, s.rng, s.spots[s.n_spots++]);
+            s.spawn_timer = 0;
+        }
+    } else if (s.spawns_left > 0 && s.spawn_timer >= k.interval0) {
         if (s.n_spots < MG_SS_MAXSPOTS) mg_ss_new_spot(k, s.rng, s.spots[s.n_spots++]);
         s.spawns_left--;
         s.spawn_timer = 0;
@@ -466,9 +476,202 @@ MG_HD_NOINLINE bool mg_ss_step_c(const MgSSK& k, MgSSState& s, const MgSSStepTmp
             info[MG_INFO_B] = (double)s.coins_collected / (double)s.num_coins;
             info[MG_INFO_GT0] = 0.0;
             info[MG_INFO_GT1] = 0.0;
-            info[7] = 0.0;
+            info[7] = info[8] = info[9] = 0.0;
         }
     }
     return done;
 }
 
+// ---- Endless Searing Spotlights (endless_searing_spotlights.py) ---------------------------------------
+MG_HD void mg_ess_frame(const MgSSK& k, const MgSSState& s, int srot, MgSSFrame& f) {
+    mg_ss_frame_common(s, srot, f);
+    // coin layer order (:380-385, 467-472): above the spotlights while visible or fresh
+    f.coin_above = (k.p.coins_visible || s.coin_t < k.p.coin_show_duration) ? 1 : 0;
+    f.coin_black = k.p.coin_enabled ? 0 : 1;
+    f.exit_x = f.exit_y = -100;  // no exit layer in this variant
+}
+
+MG_HD void mg_ess_ground_truth(const MgSSK& k, const MgSSState& s, double* gt) {
+    // np.concatenate((agent.rect.center, coin.location)) / screen_dim (:403-407, 484-501)
+    gt[0] = (double)s.cx / 84.0;
+    gt[1] = (double)s.cy / 84.0;
+    gt[2] = k.p.coin_enabled ? (double)s.coins[0][0] / 84.0 : 0.0;
+    gt[3] = k.p.coin_enabled ? (double)s.coins[0][1] / 84.0 : 0.0;
+}
+
+// _spawn_coin (:256-269): fresh sampler, only the OLD coin's surroundings blocked, sample(28) + two offsets
+template <class Ctx>
+MG_HD void mg_ess_spawn_coin(Ctx& c, const MgSSK& k, MgSSState& s, MgSSSampler& g, MgSSResetTmp& rt, bool have_old) {
+    for (int y = c.lane; y < MG_W; y += c.nl) g.lo[y] = g.hi[y] = 0;
+    if (c.lane == 0) rt.ok = 1;
+    c.sync();
+    if (have_old) {
+        mg_ss_block_coop(c, g, s.coins[0][0], s.coins[0][1], 28);
+        c.sync();
+    }
+    mg_ss_sample_coop(c, g, s, rt, 28);
+    if (c.lane == 0) {
+        int x = rt.x + (int)mg_integers(s.rng, 2, 4);
+        int y = rt.y + (int)mg_integers(s.rng, 2, 4);
+        mg_ss_clamp_spawn(k, x, y);
+        s.coins[0][0] = (int16_t)x;
+        s.coins[0][1] = (int16_t)y;
+        s.n_coins = 1;
+    }
+    c.sync();
+}
+
+// reset(): RNG draw order — rotation; agent cell + 2 offsets; per initial spotlight radius, speed, 3 angles;
+// coin cell + 2 offsets (:294-407)
+template <class Ctx>
+MG_HD void mg_ess_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, MgSSSampler& g, MgSSResetTmp& rt,
+                            double* gt) {
+    for (int y = c.lane; y < MG_W; y += c.nl) g.lo[y] = g.hi[y] = 0;
+    if (c.lane == 0) {
+        s.t = 0;
+        s.coin_t = 0;
+        s.ep_len = 0;
+        s.ep_reward = 0.0;
+        if (k.p.hide_chessboard) s.bg_blue = s.bg_red = 1;
+        s.last_a0 = s.last_a1 = 0;
+        s.rot = (uint8_t)mg_integers(s.rng, 0, 8);
+        rt.ok = 1;
+    }
+    c.sync();
+    if (k.p.sample_agent_position) {
+        mg_ss_sample_coop(c, g, s, rt, 28);
+    } else {
+        if (c.lane == 0) rt.x = rt.y = MG_W / 2;
+        c.sync();
+    }
+    if (c.lane == 0) {
+        int x = rt.x, y = rt.y;
+        if (k.p.sample_agent_position) {
+            x += (int)mg_integers(s.rng, 2, 4);
+            y += (int)mg_integers(s.rng, 2, 4);
+        }
+        s.cx = (int16_t)x;
+        s.cy = (int16_t)y;
+        s.hp = k.p.agent_health;
+        s.red_w_max = 0;
+        s.bar_c0 = s.bar_c1 = 0;
+        s.coin_bar = 0;
+        s.last_reward = 0.0;
+        s.spawns_left = 0;
+        s.spawn_timer = 0;
+        int a0 = k.p.light_threshold < 0 ? 0 : (k.p.light_threshold > 255 ? 255 : k.p.light_threshold);
+        s.alpha = (uint8_t)(k.p.light_dim_off_duration > 0 ? 0 : a0);
+        s.n_spots = 0;
+        for (int i = 0; i < k.p.initial_spawns; ++i) mg_ss_new_spot(k, s.rng, s.spots[s.n_spots++]);
+        s.coins_collected = 0;
+        s.num_coins = 1;
+        s.n_coins = 0;
+        s.exit_open = 0;
+        s.exit_x = s.exit_y = -100;
+    }
+    c.sync();
+    if (k.p.coin_enabled) mg_ess_spawn_coin(c, k, s, g, rt, false);
+    if (c.lane == 0) {
+        if (k.p.black_background) s.bg_blue = 2;
+        s.live = rt.ok ? 1 : 0;
+        mg_ess_frame(k, s, 0, f);  // the reset frame draws get_rotated_sprite(0)
+        f.n_discs = 0;
+        f.red_now = 0;
+        f.bg_kind = mg_ss_bg_kind(s, 0);
+        if (gt) mg_ess_ground_truth(k, s, gt);
+    }
+    c.sync();
+}
+
+// C1 (one lane): health / background after the spotlights moved, and the coin hit test. Returns true when the
+// coin was collected: the warp then respawns it cooperatively (mg_ess_spawn_coin) before C2 runs.
+struct MgESSCarry {
+    double reward;
+    int32_t red_now, bg_red, spot_done;
+};
+MG_HD_NOINLINE bool mg_ess_step_c1(const MgSSK& k, MgSSState& s, const MgSSStepTmp& tmp, MgESSCarry& cy) {
+    const int cx = tmp.cx, cyy = tmp.cy, nd = tmp.n_proc;
+    double reward = 0.0, r = 0.0;
+    int hit = 0;
+    for (int j = 0; j < nd; ++j) hit += tmp.hitf[j];
+    cy.red_now = 0;
+    cy.bg_red = 0;
+    cy.spot_done = 0;
+    if (hit > 0) {
+        s.hp = s.hp - k.p.spot_damage;
+        r += k.p.reward_inside_spotlight;
+        int width = (int)((double)(MG_W / 2) * (1.0 - s.hp / k.p.agent_health));
+        if (width > MG_W) width = MG_W;
+        if (width > 0) {
+            cy.red_now = width;
+            if (width > s.red_w_max) s.red_w_max = (int16_t)width;
+        }
+        cy.bg_red = k.p.visual_feedback ? 1 : 0;
+    } else {
+        r += k.p.reward_outside_spotlight;
+    }
+    if (k.p.black_background) {
+        if (cy.bg_red)
+            s.bg_red = 2;
+        else
+            s.bg_blue = 2;
+    }
+    if (s.hp <= 0.0) {
+        cy.spot_done = 1;
+        r += k.p.reward_death;
+    }
+    reward += r;
+    bool collected = false;
+    if (k.p.coin_enabled) {
+        r = 0.0;
+        double dx = (double)cx - (double)s.coins[0][0], dy = (double)cyy - (double)s.coins[0][1];
+        if (sqrt(dx * dx + dy * dy) <= (double)(k.coin_radius + k.radius)) {
+            r += k.p.reward_coin;
+            s.coins_collected++;
+            s.coin_t = 0;
+            collected = true;
+        }
+        reward += r;
+    }
+    cy.reward = reward;
+    return collected;
+}
+
+// C2 (one lane): time limits, top bar, episode statistics, frame description, ground truth
+MG_HD_NOINLINE bool mg_ess_step_c2(const MgSSK& k, MgSSState& s, const MgSSStepTmp& tmp, const MgESSCarry& cy,
+                                   double& reward_out, double* info, MgSSFrame& f, double* gt) {
+    const double reward = cy.reward;
+    bool done = cy.spot_done != 0;
+    s.t++;
+    s.coin_t++;
+    if (s.coin_t == k.p.steps_per_coin && k.p.coin_enabled) done = true;
+    if (s.t == k.p.max_steps) done = true;
+    if (k.p.show_last_positive_reward) {
+        s.coin_bar = s.last_reward > 0.0 ? 1 : 2;
+        s.last_reward = reward;
+    }
+    s.ep_reward = s.ep_reward + reward;
+    s.ep_len++;
+    reward_out = reward;
+    mg_ess_frame(k, s, s.rot, f);
+    f.n_discs = (uint8_t)tmp.n_proc;
+    f.red_now = (int16_t)cy.red_now;
+    f.bg_kind = mg_ss_bg_kind(s, cy.bg_red);
+    double g4[4];
+    mg_ess_ground_truth(k, s, g4);
+    if (gt)
+        for (int i = 0; i < 4; ++i) gt[i] = g4[i];
+    if (done) {
+        s.live = 0;
+        if (info) {
+            info[MG_INFO_REWARD] = s.ep_reward;
+            info[MG_INFO_LENGTH] = (double)s.ep_len;
+            info[MG_INFO_SUCCESS] = 0.0;
+            info[MG_INFO_A] = s.hp / k.p.agent_health;
+            info[MG_INFO_B] = (double)s.coins_collected;
+            for (int i = 0; i < 4; ++i) info[MG_INFO_GT0 + i] = g4[i];
+            info[MG_INFO_C] = 0.0;
+        }
+    }
+    return done;
+}

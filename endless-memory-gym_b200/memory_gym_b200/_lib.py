@@ -11,9 +11,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmemgym_b200.so")
 
-MG_ABI_VERSION = 1
+MG_ABI_VERSION = 2
 MG_OBS_BYTES = 84 * 84 * 3
-MG_INFO_COLS = 8
+MG_INFO_COLS = 10
+MG_GT_COLS = 4
 MG_MAX_CHOICES = 16
 MG_MM_MAX_COMMANDS = 152
 MG_MM_STATE_BYTES = 256
@@ -24,7 +25,9 @@ MG_FLAG_STREAM_OBS = 2
 MG_MM_CONTINUOUS, MG_MM_GRID, MG_MM_ENDLESS, MG_MM_B, MG_MM_B_GRID = 0, 1, 2, 3, 4
 MG_MP_CONTINUOUS, MG_MP_GRID = 0, 1
 MG_MM_B_VECTOR = 180
-(MG_INFO_REWARD, MG_INFO_LENGTH, MG_INFO_SUCCESS, MG_INFO_A, MG_INFO_B, MG_INFO_GT0, MG_INFO_GT1) = range(7)
+(MG_INFO_REWARD, MG_INFO_LENGTH, MG_INFO_SUCCESS, MG_INFO_A, MG_INFO_B, MG_INFO_GT0, MG_INFO_GT1, MG_INFO_GT2,
+ MG_INFO_GT3, MG_INFO_C) = range(10)
+MG_SS_FINITE, MG_SS_ENDLESS = 0, 1
 
 
 class ChoiceList(C.Structure):
@@ -70,7 +73,7 @@ class SSParams(C.Structure):
         ("light_dim_off_duration", C.c_int32), ("light_threshold", C.c_int32), ("coins_visible", C.c_int32),
         ("use_exit", C.c_int32), ("exit_visible", C.c_int32), ("agent_visible", C.c_int32),
         ("sample_agent_position", C.c_int32), ("show_last_action", C.c_int32),
-        ("show_last_positive_reward", C.c_int32), ("pad0", C.c_int32), ("num_coins", ChoiceList),
+        ("show_last_positive_reward", C.c_int32), ("variant", C.c_int32), ("num_coins", ChoiceList),
         ("initial_spawn_interval", C.c_double), ("spawn_interval_threshold", C.c_double),
         ("spawn_interval_decay", C.c_double), ("spot_min_radius", C.c_double), ("spot_max_radius", C.c_double),
         ("spot_min_speed", C.c_double), ("spot_max_speed", C.c_double), ("spot_damage", C.c_double),
@@ -78,6 +81,8 @@ class SSParams(C.Structure):
         ("agent_health", C.c_double), ("agent_scale", C.c_double), ("reward_inside_spotlight", C.c_double),
         ("reward_outside_spotlight", C.c_double), ("reward_death", C.c_double), ("reward_exit", C.c_double),
         ("reward_max_steps", C.c_double), ("reward_coin", C.c_double),
+        ("steps_per_coin", C.c_int32), ("spawn_interval", C.c_int32), ("coin_enabled", C.c_int32),
+        ("coin_show_duration", C.c_int32),
     ]
 
 

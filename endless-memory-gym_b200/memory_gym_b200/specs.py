@@ -3,7 +3,8 @@ reference, so an `options` dict written for the reference works unchanged.
 
 Reference: ``memory_gym/__init__.py:13-60`` (ids), ``default_reset_parameters`` /
 ``process_reset_params`` of each env class (``mortar_mayhem.py:21-54``, ``mortar_mayhem_grid.py:21-55``,
-``endless_mortar_mayhem.py:21-53``, ``mystery_path.py:21-52``, ``searing_spotlights.py:22-80``).
+``endless_mortar_mayhem.py:21-53``, ``mystery_path.py:21-52``, ``searing_spotlights.py:22-80``,
+``endless_searing_spotlights.py:22-75``).
 """
 from __future__ import annotations
 
@@ -16,7 +17,7 @@ class EnvSpec:
     """Static description of one env id: option defaults, spaces, and the C-ABI family behind it."""
 
     def __init__(self, env_id, family, variant, defaults, action_nvec, state_bytes, info_keys, check=None,
-                 has_ground_truth=False):
+                 has_ground_truth=False, gt_dim=2):
         self.id = env_id
         self.family = family            # "mm" | "mp" | "ss": mg_<family>_reset / _step
         self.variant = variant
@@ -26,6 +27,7 @@ class EnvSpec:
         self.info_keys = info_keys      # name -> column of the info matrix
         self._check = check
         self.has_ground_truth_info = has_ground_truth
+        self.gt_dim = gt_dim            # columns of info["ground_truth"] (ground_truth_space.shape[0])
 
     def process_reset_params(self, reset_params):
         """Same contract as the reference's ``process_reset_params``: unknown key -> AssertionError,
@@ -75,15 +77,20 @@ class EnvSpec:
             return s
         if self.family == "ss":
             s = L.SSParams()
+            # keys the other Searing-Spotlights variant does not have: neutral values the kernels never read
+            absent = {"num_coins": [1], "use_exit": True, "steps_per_coin": 0, "spawn_interval": 0, "coin_enabled": 1,
+                      "coin_show_duration": 0}
             for name, ctype in L.SSParams._fields_:
-                if name == "pad0":
+                if name == "variant":
+                    s.variant = self.variant
                     continue
+                v = p[name] if name in p else absent.get(name, 0)
                 if name == "num_coins":
-                    s.num_coins = L.ChoiceList.of(p["num_coins"])
+                    s.num_coins = L.ChoiceList.of(v)
                 elif ctype is L.C.c_int32:
-                    setattr(s, name, int(p[name]))
+                    setattr(s, name, int(v))
                 else:
-                    setattr(s, name, float(p[name]))
+                    setattr(s, name, float(v))
             return s
         raise KeyError(self.family)
 
@@ -208,6 +215,38 @@ _SS_DEFAULTS = {
     "reward_coin": 0.25,
 }
 
+_ESS_DEFAULTS = {
+    "max_steps": -1,
+    "steps_per_coin": 160,
+    "initial_spawns": 3,
+    "spawn_interval": 50,
+    "spot_min_radius": 30.0 * SCALE,
+    "spot_max_radius": 55.0 * SCALE,
+    "spot_min_speed": 0.0025,
+    "spot_max_speed": 0.0075,
+    "spot_damage": 1.0,
+    "visual_feedback": True,
+    "black_background": False,
+    "hide_chessboard": False,
+    "light_dim_off_duration": 6,
+    "light_threshold": 255,
+    "coin_enabled": True,
+    "coin_scale": 1.5 * SCALE,
+    "coin_show_duration": 6,
+    "coins_visible": False,
+    "agent_speed": 12.0 * SCALE,
+    "agent_health": 10,
+    "agent_scale": 1.0 * SCALE,
+    "agent_visible": False,
+    "sample_agent_position": True,
+    "show_last_action": True,
+    "show_last_positive_reward": True,
+    "reward_inside_spotlight": 0.0,
+    "reward_outside_spotlight": 0.0,
+    "reward_death": 0.0,
+    "reward_coin": 0.25,
+}
+
 _MM_INFO = {"reward": L.MG_INFO_REWARD, "length": L.MG_INFO_LENGTH, "success": L.MG_INFO_SUCCESS,
             "commands_completed": L.MG_INFO_A}
 _EMM_INFO = {"reward": L.MG_INFO_REWARD, "length": L.MG_INFO_LENGTH, "commands_completed": L.MG_INFO_A,
@@ -216,6 +255,8 @@ _MP_INFO = {"reward": L.MG_INFO_REWARD, "length": L.MG_INFO_LENGTH, "success": L
             "num_fails": L.MG_INFO_A}
 _SS_INFO = {"reward": L.MG_INFO_REWARD, "length": L.MG_INFO_LENGTH, "success": L.MG_INFO_SUCCESS,
             "agent_health": L.MG_INFO_A, "coins_collected": L.MG_INFO_B}
+_ESS_INFO = {"reward": L.MG_INFO_REWARD, "length": L.MG_INFO_LENGTH, "agent_health": L.MG_INFO_A,
+             "coins_collected": L.MG_INFO_B}
 
 SPECS = {
     s.id: s for s in (
@@ -230,12 +271,14 @@ SPECS = {
         EnvSpec("MortarMayhemB-v0", "mm", L.MG_MM_B, _MMB_DEFAULTS, [3, 3], L.MG_MM_STATE_BYTES, _MM_INFO, _check_mmb),
         EnvSpec("MortarMayhemB-Grid-v0", "mm", L.MG_MM_B_GRID, _MMBGRID_DEFAULTS, [4], L.MG_MM_STATE_BYTES, _MM_INFO,
                 _check_mmb),
-        EnvSpec("SearingSpotlights-v0", "ss", 0, _SS_DEFAULTS, [3, 3], L.MG_SS_STATE_BYTES, _SS_INFO),
+        EnvSpec("SearingSpotlights-v0", "ss", L.MG_SS_FINITE, _SS_DEFAULTS, [3, 3], L.MG_SS_STATE_BYTES, _SS_INFO),
+        EnvSpec("Endless-SearingSpotlights-v0", "ss", L.MG_SS_ENDLESS, _ESS_DEFAULTS, [3, 3], L.MG_SS_STATE_BYTES,
+                _ESS_INFO, has_ground_truth=True, gt_dim=4),
     )
 }
 
 # ids the reference registers that this engine does not accelerate yet
-NOT_BUILT = ("Endless-SearingSpotlights-v0", "Endless-MysteryPath-v0")
+NOT_BUILT = ("Endless-MysteryPath-v0",)
 
 
 def spec(env_id: str) -> EnvSpec:

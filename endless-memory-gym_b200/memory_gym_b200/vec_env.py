@@ -116,7 +116,7 @@ class MemoryGymVecEnv:
         self.single_observation_space = spaces.Box(low=0, high=255, shape=(84, 84, 3), dtype=np.uint8)
         self.action_space, self.observation_space = self.single_action_space, self.single_observation_space
         if self.has_ground_truth_info:
-            self.ground_truth_space = spaces.Box(low=0.0, high=1.0, shape=(2,), dtype=np.float32)
+            self.ground_truth_space = spaces.Box(low=0.0, high=1.0, shape=(self.spec_.gt_dim,), dtype=np.float32)
         n, dev = self.num_envs, self.device
         self.state = torch.zeros((n, self.spec_.state_bytes), dtype=torch.uint8, device=dev)
         self.obs = torch.zeros((n, 84, 84, 3), dtype=torch.uint8, device=dev)
@@ -125,7 +125,9 @@ class MemoryGymVecEnv:
         self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.truncated = torch.zeros(n, dtype=torch.bool, device=dev)
         self.info = torch.zeros((n, L.MG_INFO_COLS), dtype=torch.float64, device=dev)
-        self.ground_truth = torch.zeros((n, 2), dtype=torch.float64, device=dev) if self.has_ground_truth_info else None
+        # the library writes [n][MG_GT_COLS]; the env publishes the columns its reference counterpart has
+        self._gt_full = torch.zeros((n, L.MG_GT_COLS), dtype=torch.float64, device=dev) if self.has_ground_truth_info else None
+        self.ground_truth = self._gt_full[:, :self.spec_.gt_dim] if self.has_ground_truth_info else None
         # MortarMayhemB: Dict observation {"visual_observation", "vector_observation"} (mortar_mayhem_b.py:84-97)
         self.task_b = self.spec_.family == "mm" and self.spec_.variant in (L.MG_MM_B, L.MG_MM_B_GRID)
         self.vector_obs = torch.zeros((n, L.MG_MM_B_VECTOR), dtype=torch.float32, device=dev) if self.task_b else None
@@ -136,7 +138,7 @@ class MemoryGymVecEnv:
         self._io.reward = self.reward.data_ptr()
         self._io.done = self.done.data_ptr()
         self._io.info = self.info.data_ptr()
-        self._io.ground_truth = self.ground_truth.data_ptr() if self.has_ground_truth_info else None
+        self._io.ground_truth = self._gt_full.data_ptr() if self.has_ground_truth_info else None
         self._io.vector_obs = self.vector_obs.data_ptr() if self.task_b else None
         # stream_obs: write observations with an L2 evict-first policy. Default: on for rollout() (frames are
         # not re-read soon; measured +13 % HBM write throughput), off for step() (the policy reads obs next).
@@ -256,7 +258,7 @@ class MemoryGymVecEnv:
             info["final_observation"] = self.final_obs
         if self.has_ground_truth_info:
             info["ground_truth"] = self.ground_truth
-            info["final_ground_truth"] = self.info[:, L.MG_INFO_GT0:L.MG_INFO_GT1 + 1]
+            info["final_ground_truth"] = self.info[:, L.MG_INFO_GT0:L.MG_INFO_GT0 + self.spec_.gt_dim]
         return self._wrap_obs(obs), self.reward, done, self.truncated, info
 
     def _check_rollout_buffers(self, actions, obs_out, reward_out, done_out, info_out):
@@ -274,7 +276,7 @@ class MemoryGymVecEnv:
             raise ValueError("rollout buffer shapes do not match (T, num_envs)")
         if info_out is not None and (tuple(info_out.shape) != (T, self.num_envs, L.MG_INFO_COLS)
                                      or info_out.dtype != torch.float64 or not info_out.is_contiguous()):
-            raise ValueError("info_out must be a contiguous float64[T, N, 8] tensor")
+            raise ValueError(f"info_out must be a contiguous float64[T, N, {L.MG_INFO_COLS}] tensor")
         return T
 
     def rollout(self, actions, obs_out, reward_out, done_out, info_out=None):
@@ -284,7 +286,7 @@ class MemoryGymVecEnv:
 
         ``actions`` int64[T, N, 2] (or [T, N]); ``obs_out`` uint8[R, N, 84, 84, 3], step t writes slot t % R
         (R = T keeps every frame, a small R is a ring); ``reward_out`` float64[T, N]; ``done_out``
-        bool/uint8[T, N]; ``info_out`` optional float64[T, N, 8] (else ``self.info`` keeps each env's last
+        bool/uint8[T, N]; ``info_out`` optional float64[T, N, MG_INFO_COLS] (else ``self.info`` keeps each env's last
         finished episode)."""
         T = self._check_rollout_buffers(actions, obs_out, reward_out, done_out, info_out)
         r = L.RolloutIO()
@@ -396,7 +398,7 @@ class MemoryGymEnv:
                 out[k] = float(row[col])
             out["length"] = int(out["length"])
             if self.has_ground_truth_info:
-                out["ground_truth"] = row[L.MG_INFO_GT0:L.MG_INFO_GT1 + 1].copy()
+                out["ground_truth"] = row[L.MG_INFO_GT0:L.MG_INFO_GT0 + self.vec.spec_.gt_dim].copy()
         elif self.has_ground_truth_info:
             out["ground_truth"] = info["ground_truth"][0].cpu().numpy()
         return self._np_obs(obs), float(reward[0].item()), d, False, out

@@ -17,6 +17,7 @@
  *                                  GridMysteryPathEnv.reset/step       memory_gym/mystery_path_grid.py:129-200, 202-276
  *                                  MysteryPath.__init__ (noisy A*)     memory_gym/pygame_assets.py:606-736
  *   mg_ss_reset / mg_ss_step   <-  SearingSpotlightsEnv.reset/step     memory_gym/searing_spotlights.py:332-450, 452-562
+ *                                  EndlessSearingSpotlightsEnv.reset/step  memory_gym/endless_searing_spotlights.py:294-407, 409-504
  *                                  Spotlight / Coin / Exit / sampler   memory_gym/pygame_assets.py:7-239
  *   mg_*_build_assets          <-  CharacterController.create_character_sprites  character_controller.py:29-75,
  *                                  Command.__init__ pygame_assets.py:254-304, MortarTile :316-343, Exit.draw :191-205,
@@ -43,11 +44,12 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 1
+#define MG_ABI_VERSION 2
 
 #define MG_SCREEN 84
 #define MG_OBS_BYTES (84 * 84 * 3) /* 21168 bytes per env, [x][y][c] */
-#define MG_INFO_COLS 8             /* doubles per env in the info matrix */
+#define MG_INFO_COLS 10            /* doubles per env in the info matrix */
+#define MG_GT_COLS 4               /* doubles per env in the ground-truth matrix */
 #define MG_TRACE_COLS 16
 #define MG_MAX_CHOICES 16          /* max length of a list-valued reset option */
 #define MG_MM_MAX_COMMANDS 152     /* capacity of the per-env command list */
@@ -63,10 +65,14 @@ extern "C" {
 #define MG_INFO_LENGTH 1   /* episode length in steps */
 #define MG_INFO_SUCCESS 2  /* MM/MM-Grid/MP/SS: success flag                                     */
 #define MG_INFO_A 3        /* MM: commands_completed (fraction); EMM: commands_completed (count); */
-                           /* MP: num_fails; SS: agent_health (fraction)                          */
-#define MG_INFO_B 4        /* EMM: max_command_sequence; SS: coins_collected (fraction)           */
-#define MG_INFO_GT0 5      /* Endless: ground_truth of the terminal step                          */
+                           /* MP: num_fails; SS/ESS: agent_health (fraction)                      */
+#define MG_INFO_B 4        /* EMM: max_command_sequence; SS: coins_collected (fraction);          */
+                           /* ESS: coins_collected (count)                                        */
+#define MG_INFO_GT0 5      /* Endless: ground_truth of the terminal step, MG_GT_COLS columns 5..8  */
 #define MG_INFO_GT1 6
+#define MG_INFO_GT2 7
+#define MG_INFO_GT3 8
+#define MG_INFO_C 9        /* EMP: tiles_visited                                                  */
 
 /* mg_step_io.flags */
 #define MG_FLAG_AUTORESET 1u /* step: envs that finish are reset in the same call (their stream continues like  */
@@ -126,6 +132,10 @@ typedef struct mg_mp_params {
 } mg_mp_params;
 
 /* ---- Searing Spotlights ---------------------------------------------------------------------- */
+enum { MG_SS_FINITE = 0, MG_SS_ENDLESS = 1 };
+/* Field names follow default_reset_parameters (searing_spotlights.py:22-64, endless_searing_spotlights.py:22-58);
+ * the endless variant ignores num_spawns, the three spawn-interval fields, num_coins, the exit fields,
+ * reward_exit and reward_max_steps. */
 typedef struct mg_ss_params {
     int32_t max_steps;
     int32_t initial_spawns;
@@ -142,7 +152,7 @@ typedef struct mg_ss_params {
     int32_t sample_agent_position;
     int32_t show_last_action;
     int32_t show_last_positive_reward;
-    int32_t pad0;
+    int32_t variant;               /* MG_SS_* */
     mg_choice_list num_coins;
     double initial_spawn_interval;
     double spawn_interval_threshold;
@@ -163,6 +173,11 @@ typedef struct mg_ss_params {
     double reward_exit;
     double reward_max_steps;
     double reward_coin;
+    /* Endless-SearingSpotlights-v0 only (endless_searing_spotlights.py:22-58) */
+    int32_t steps_per_coin;
+    int32_t spawn_interval;
+    int32_t coin_enabled;
+    int32_t coin_show_duration;
 } mg_ss_params;
 
 /* ---- per-call I/O (all device pointers; nullable ones are marked) ----------------------------- */
@@ -173,7 +188,8 @@ typedef struct mg_step_io {
     double* reward;         /* [n]; unused by reset */
     uint8_t* done;          /* [n]; unused by reset */
     double* info;           /* [n][MG_INFO_COLS], written only where done; unused by reset */
-    double* ground_truth;   /* nullable: [n][2] (Endless envs: target / 5.0, every step and reset) */
+    double* ground_truth;   /* nullable: [n][MG_GT_COLS], every step and reset (Endless envs: EMM target / 5.0 in  */
+                            /* columns 0..1; ESS (agent x, y, coin x, y) / 84; unused columns are left alone)   */
     const uint8_t* reset_mask; /* reset only, nullable: [n], reset env i iff mask[i] != 0 */
     uint32_t flags;         /* MG_FLAG_* */
     uint32_t warps_per_cta; /* 0 = library default; tuning knob (frame buffers resident per SM) */
@@ -193,7 +209,7 @@ typedef struct mg_rollout_io {
     double* reward;         /* [T][n] */
     uint8_t* done;          /* [T][n] */
     double* info;           /* [T][n][MG_INFO_COLS] if info_per_step, else [n][MG_INFO_COLS] (last finished episode) */
-    double* ground_truth;   /* nullable: [n][2], of the last step */
+    double* ground_truth;   /* nullable: [n][MG_GT_COLS], of the last step */
     int32_t n_steps;
     int32_t ring;
     int32_t info_per_step;

@@ -21,8 +21,10 @@ def replay_golden_single(name, device, backend, max_envs=None):
     infos = {(r["env"], r["t"]): r for r in case["infos"]}
     for e in range(n_envs if max_envs is None else min(n_envs, max_envs)):
         env = make_single(case["env_id"], device, backend)
-        obs, _ = env.reset(seed=case["seed0"] + e, options=case["options"])
+        obs, info = env.reset(seed=case["seed0"] + e, options=case["options"])
         assert np.array_equal(visual(obs), case["frames"][case["frame_map"][(e, -1)]]), (name, e, "reset frame")
+        if "gt" in case:
+            assert np.array_equal(info["ground_truth"], case["gt_reset"][e]), (name, e, "reset ground truth")
         for t in range(steps):
             obs, reward, done, trunc, info = env.step(action_for(case, e, t))
             assert trunc is False
@@ -32,6 +34,8 @@ def replay_golden_single(name, device, backend, max_envs=None):
                 want = case["frames"][case["frame_map"][(e, t)]]
                 assert np.array_equal(visual(obs), want), (name, e, t, int((visual(obs) != want).sum()))
             assert crc(obs) == int(case["crc"][e, t]), (name, e, t)
+            if "gt" in case:
+                assert np.array_equal(info["ground_truth"], case["gt"][e, t]), (name, e, t, "ground truth")
             if done:
                 ref = infos[(e, t)]
                 assert float(info["reward"]) == ref["reward_seq_sum"], (name, e, t)
@@ -71,6 +75,10 @@ def replay_golden_batched(name, device, backend):
         assert not trunc.any()
         assert np.array_equal(reward, case["reward"][:, t]), (name, t)
         assert np.array_equal(done, case["done"][:, t].astype(bool)), (name, t)
+        if "gt" in case:  # done envs: ground truth of the terminal step; obs/ground_truth belong to the new episode
+            gt, fgt = info["ground_truth"].cpu().numpy(), info["final_ground_truth"].cpu().numpy()
+            for e in range(n_envs):
+                assert np.array_equal(fgt[e] if done[e] else gt[e], case["gt"][e, t]), (name, e, t, "ground truth")
         for e in range(n_envs):
             if done[e]:
                 if not env.task_b:  # (the terminal frame's CRC of a Dict obs also covers the old command vector)

@@ -11,7 +11,7 @@ from replay_util import replay_golden_batched, replay_golden_single, rollout_vs_
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts", "ss_black",
-         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts"]
+         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts", "ess", "ess_opts", "ess_black", "ess_nocoin"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -48,6 +48,17 @@ def test_golden_batched_autoreset(name):
     ("SearingSpotlights-v0", {"max_steps": 40, "sample_agent_position": False, "light_dim_off_duration": 0,
                               "show_last_positive_reward": False, "agent_visible": True, "coin_scale": 1.0,
                               "exit_scale": 1.0, "agent_scale": 0.4, "agent_speed": 5.0, "num_coins": [3]}, 300, 8),
+    ("Endless-SearingSpotlights-v0", {"steps_per_coin": 40}, 64, 0),
+    ("Endless-SearingSpotlights-v0", {"max_steps": 55, "coins_visible": True, "agent_visible": True, "agent_health": 3,
+                                      "spot_damage": 0.7, "initial_spawns": 6, "spawn_interval": 7,
+                                      "spot_min_radius": 12.0, "spot_max_radius": 20.0, "spot_min_speed": 0.01,
+                                      "spot_max_speed": 0.03, "reward_inside_spotlight": -0.1,
+                                      "reward_outside_spotlight": 0.01, "reward_death": -1.0, "coin_scale": 1.0}, 48, 2),
+    ("Endless-SearingSpotlights-v0", {"steps_per_coin": 30, "hide_chessboard": True, "light_threshold": 100,
+                                      "light_dim_off_duration": 3, "visual_feedback": False, "coin_show_duration": 20,
+                                      "sample_agent_position": False, "agent_scale": 0.4, "agent_speed": 5.0}, 300, 8),
+    ("Endless-SearingSpotlights-v0", {"coin_enabled": False, "max_steps": 35, "agent_visible": True,
+                                      "coins_visible": True, "light_dim_off_duration": 0}, 48, 1),
 ])
 def test_rollout_vs_oracle(env_id, options, n_envs, wpc):
     steps = 70 if n_envs > 100 else 150
@@ -64,7 +75,8 @@ def _random_actions(env, steps, seed):
 @pytest.mark.parametrize("env_id,n,options", [("MortarMayhem-v0", 4096, None),
                                               ("MysteryPath-v0", 8192, {"max_steps": 48}),
                                               ("Endless-MortarMayhem-v0", 8192, None),
-                                              ("SearingSpotlights-v0", 8192, {"max_steps": 40})])
+                                              ("SearingSpotlights-v0", 8192, {"max_steps": 40}),
+                                              ("Endless-SearingSpotlights-v0", 8192, {"steps_per_coin": 40})])
 def test_full_size_properties(env_id, n, options):
     """At BASELINE.json's batch sizes: (1) bit-identical to the same envs run in small shards with other
     launch geometries (1 / 3 warps per CTA) — env i's result depends only on seed0+i and its actions;
@@ -155,13 +167,14 @@ def test_abi_rejects_bad_arguments():
     assert b"NULL" in lib.mg_last_error()
 
 
-@pytest.mark.parametrize("env_id", ["MortarMayhem-v0", "MortarMayhem-Grid-v0", "MysteryPath-v0", "SearingSpotlights-v0"])
+@pytest.mark.parametrize("env_id", ["MortarMayhem-v0", "MortarMayhem-Grid-v0", "MysteryPath-v0", "SearingSpotlights-v0",
+                                    "Endless-SearingSpotlights-v0"])
 def test_rollout_equals_step_loop(env_id):
     """mg_*_rollout (ONE launch, every warp runs all T steps of its envs) and mg_*_step_many (T launches
     enqueued by one call, programmatic dependent launch between them) give exactly what T separate
     step() calls give."""
     n, T = 500, 90
-    opts = {"max_steps": 40} if env_id in ("MysteryPath-v0", "SearingSpotlights-v0") else None
+    opts = {"max_steps": 40} if env_id in ("MysteryPath-v0", "SearingSpotlights-v0", "Endless-SearingSpotlights-v0") else None
     a = mg.make(env_id, num_envs=n, device=DEV)
     b = mg.make(env_id, num_envs=n, device=DEV)
     acts = _random_actions(a, T, 77)
@@ -170,7 +183,7 @@ def test_rollout_equals_step_loop(env_id):
     ring = torch.zeros((3, n, 84, 84, 3), dtype=torch.uint8, device=DEV)
     rew = torch.zeros((T, n), dtype=torch.float64, device=DEV)
     dn = torch.zeros((T, n), dtype=torch.bool, device=DEV)
-    inf = torch.zeros((T, n, 8), dtype=torch.float64, device=DEV)
+    inf = torch.zeros((T, n, mg._lib.MG_INFO_COLS), dtype=torch.float64, device=DEV)
     a.rollout(acts, ring, rew, dn, inf)
     c = mg.make(env_id, num_envs=n, device=DEV, warps_per_cta=3)
     c.reset(seed=5, options=opts)

@@ -8,7 +8,7 @@ from hostsim_util import HostSimBackend
 from replay_util import replay_golden_batched, replay_golden_single, rollout_vs_oracle
 
 CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts", "ss_black",
-         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts"]
+         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts", "ess", "ess_opts", "ess_black", "ess_nocoin"]
 
 
 @pytest.fixture(scope="module")
@@ -50,6 +50,17 @@ def test_golden_batched_autoreset(name, backend):
     ("SearingSpotlights-v0", {"max_steps": 40, "sample_agent_position": False, "light_dim_off_duration": 0,
                               "show_last_positive_reward": False, "agent_visible": True, "coin_scale": 1.0,
                               "exit_scale": 1.0, "agent_scale": 0.4, "agent_speed": 5.0, "num_coins": [3]}),
+    ("Endless-SearingSpotlights-v0", {"steps_per_coin": 40}),
+    ("Endless-SearingSpotlights-v0", {"max_steps": 55, "coins_visible": True, "agent_visible": True, "agent_health": 3,
+                                      "spot_damage": 0.7, "initial_spawns": 6, "spawn_interval": 7,
+                                      "spot_min_radius": 12.0, "spot_max_radius": 20.0, "spot_min_speed": 0.01,
+                                      "spot_max_speed": 0.03, "reward_inside_spotlight": -0.1,
+                                      "reward_outside_spotlight": 0.01, "reward_death": -1.0, "coin_scale": 1.0}),
+    ("Endless-SearingSpotlights-v0", {"steps_per_coin": 30, "hide_chessboard": True, "light_threshold": 100,
+                                      "light_dim_off_duration": 3, "visual_feedback": False, "coin_show_duration": 20,
+                                      "sample_agent_position": False, "agent_scale": 0.4, "agent_speed": 5.0}),
+    ("Endless-SearingSpotlights-v0", {"coin_enabled": False, "max_steps": 35, "agent_visible": True,
+                                      "coins_visible": True, "light_dim_off_duration": 0}),
 ])
 def test_rollout_vs_oracle(env_id, options, backend):
     episodes = rollout_vs_oracle(env_id, options, n_envs=8, steps=150, seed0=1000, device="cpu", backend=backend)
@@ -59,7 +70,8 @@ def test_rollout_vs_oracle(env_id, options, backend):
 @pytest.mark.parametrize("env_id,opts", [("MortarMayhem-v0", None), ("MysteryPath-v0", {"max_steps": 50}),
                                          ("SearingSpotlights-v0", {"max_steps": 60}),
                                          ("SearingSpotlights-v0", {"max_steps": 45, "agent_visible": True,
-                                                                   "light_threshold": 90, "num_coins": [3]})])
+                                                                   "light_threshold": 90, "num_coins": [3]}),
+                                         ("Endless-SearingSpotlights-v0", {"steps_per_coin": 40, "agent_speed": 5.0})])
 def test_rollout_equals_step_loop_hostsim(env_id, opts, backend):
     """rollout() (env-major: all T steps of an env back to back, persistent per-warp scratch — exercises the
     incremental frame paths; slot t % ring, per-step reward/done/info rows) == T step() calls."""
@@ -74,7 +86,7 @@ def test_rollout_equals_step_loop_hostsim(env_id, opts, backend):
     b.reset(seed=9, options=opts)
     ring = torch.zeros((4, n, 84, 84, 3), dtype=torch.uint8)
     rew, dn = torch.zeros((T, n), dtype=torch.float64), torch.zeros((T, n), dtype=torch.bool)
-    inf = torch.zeros((T, n, 8), dtype=torch.float64)
+    inf = torch.zeros((T, n, mg._lib.MG_INFO_COLS), dtype=torch.float64)
     full = torch.zeros((T, n, 84, 84, 3), dtype=torch.uint8)
     a.rollout(acts, full, rew, dn, inf)
     a2 = mg.MemoryGymVecEnv(env_id, n, device="cpu", _backend=backend)
