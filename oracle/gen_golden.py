@@ -75,6 +75,16 @@ CASES = {
     "ess_nocoin": ("Endless-SearingSpotlights-v0", {"coin_enabled": False, "max_steps": 70, "initial_spawns": 6,
                                                      "spot_min_speed": 0.01, "spot_max_speed": 0.03,
                                                      "agent_health": 3}, 4, 200),
+    "emp": ("Endless-MysteryPath-v0", None, 6, 700),
+    "emp_opts": ("Endless-MysteryPath-v0", {"max_steps": 150, "show_background": True, "show_stamina": True,
+                                             "camera_offset_scale": 2.3, "stamina_level": 12, "reward_fall_off": -0.1,
+                                             "reward_path_progress_dense": 0.05, "reward_step": -0.01,
+                                             "agent_speed": 5.0, "show_origin": True}, 4, 450),
+    "emp_nopast": ("Endless-MysteryPath-v0", {"show_past_path": False, "visual_feedback": False,
+                                               "camera_offset_scale": 0.0, "agent_scale": 0.4, "agent_speed": 2.0,
+                                               "stamina_level": 40}, 4, 400),
+    "emp_cam": ("Endless-MysteryPath-v0", {"camera_offset_scale": 7.0, "show_background": True, "agent_speed": 4.0,
+                                            "stamina_level": 30}, 4, 500),
 }
 
 
@@ -91,6 +101,23 @@ def goal_seeking_actions(env_id, env, rng, e):
     """Seeded random actions; env instances with e % 3 != 0 follow a scripted expert (reading the
     reference env's internals) with 12 % random actions, so reward / success / growth branches are
     covered as well as the early-failure ones."""
+    if env_id == "Endless-MysteryPath-v0":
+        # Discrete(4): 0 no-op, 1 right, 2 up, 3 down — follow current_node.next_node where that is possible
+        rand = int(rng.integers(0, 4))
+        if e % 3 == 0 or rng.random() < (0.03 if e % 3 == 1 else 0.08):
+            return rand
+        cy = env.agent.rect.center[1]
+        cur, nxt = env.current_node, env.current_node.next_node
+        own_y = 12 * cur.y + 6
+        if nxt.x > cur.x:
+            if abs(cy - own_y) > 3:  # stay clear of the row boundary while moving right
+                return 2 if cy > own_y else 3
+            return 1
+        if nxt.y < cur.y:
+            return 2
+        if nxt.y > cur.y:
+            return 3
+        return rand  # a westward link cannot be followed (no "left" action)
     grid = "Grid" in env_id
     rand = int(rng.integers(0, 4)) if grid else rng.integers(0, 3, 2)
     if e % 3 == 0 or rng.random() < 0.12:

@@ -120,6 +120,16 @@ def move_clamped(cx, cy, rotation, action, speed, radius, rect):
     return cx, cy, rotation
 
 
+def move_free(cx, cy, rotation, action, speed):
+    """CharacterController.step without a boundary rect (endless_mystery_path.py:299)."""
+    vx, vy, rotation = _velocity_and_rotation(action, rotation)
+    if vx or vy:
+        n = math.sqrt(float(vx * vx + vy * vy))
+        cx += int((vx / n) * speed)
+        cy += int((vy / n) * speed)
+    return cx, cy, rotation
+
+
 def move_wrapped(cx, cy, rotation, action, speed, radius, rect):
     """ScreenWrapCharacterController.step (character_controller.py:226-283): float velocity, the
     Rect assignment truncates toward zero, then wrap at +-radius/2 beyond the rect."""
@@ -1414,6 +1424,231 @@ class EndlessSearingSpotlightsOracle(SearingSpotlightsOracle):
         return super()._render(discs, sprite_rot)
 
 
+# --------------------------------------------------------------------------------------------------
+# Endless Mystery Path
+# --------------------------------------------------------------------------------------------------
+class EndlessMysteryPathOracle(_OracleEnv):
+    """endless_mystery_path.py:16-444 (EndlessMysteryPathEnv) on EndlessMysteryPath
+    (pygame_assets.py:495-604: 7x7 MysteryPath segments joined by transition tiles, 8 columns per segment),
+    CharacterController.step without a boundary rect, a camera that follows the agent's x velocity."""
+
+    env_id = "Endless-MysteryPath-v0"
+    default_reset_parameters = {
+        "max_steps": -1, "agent_scale": 1.0 * SCALE, "agent_speed": 12.0 * SCALE, "show_origin": False,
+        "show_past_path": True, "show_background": False, "show_stamina": False, "visual_feedback": True,
+        "camera_offset_scale": 5.0, "stamina_level": 20, "reward_fall_off": 0.0, "reward_path_progress": 0.1,
+        "reward_path_progress_dense": 0.0, "reward_step": 0.0,
+    }
+    GRID = 7
+    TILE = SCREEN // 7  # 12
+    SEG = 8             # columns per segment incl. the transition tile (segment_length)
+    ACTIONS = ([0, 0], [2, 0], [0, 1], [0, 2])  # Discrete(4): no-op, right, up, down (:283-291)
+
+    # ---- EndlessMysteryPath.add_path_segment (pygame_assets.py:559-604) -----------------------------
+    def _add_segment(self, rng):
+        g = self.GRID
+        if self.seg_start is None:
+            self.seg_start = (0, int(rng.integers(0, g)))
+        else:
+            self.seg_start = (0, self.seg_end[1])
+        self.seg_end = (g - 1, int(rng.integers(0, g)))
+        path, _ = generate_mystery_path(rng, g, self.seg_start, self.seg_end)  # [end, ..., start]
+        k = len(self.segments)
+        shift = 0 if k == 0 else k * g + k
+        nodes = [(x + shift, y) for x, y in reversed(path)]
+        k += 1
+        nodes.append((self.seg_end[0] + k + (k - 1) * g, self.seg_end[1]))  # the transition tile
+        self.segments.append(nodes)
+
+    def _node(self, ref):
+        return self.segments[ref[0]][ref[1]]
+
+    def _prev(self, ref):
+        s, i = ref
+        if i > 0:
+            return (s, i - 1)
+        return (s - 1, len(self.segments[s - 1]) - 1) if s > 0 else None
+
+    def _next(self, ref):
+        s, i = ref
+        if i + 1 < len(self.segments[s]):
+            return (s, i + 1)
+        return (s + 1, 0) if s + 1 < len(self.segments) else None
+
+    def _update_direction(self):
+        nx = self._next(self.current)
+        x = self._node(nx)[0] - self._node(self.current)[0]
+        y = self._node(nx)[1] - self._node(self.current)[1]
+        if x == 1:
+            self.target_direction = np.asarray([1, 0, 0])
+        elif y == -1:
+            self.target_direction = np.asarray([0, 1, 0])
+        elif y == 1:
+            self.target_direction = np.asarray([0, 0, 1])
+        # a westward link leaves the previous direction in place
+
+    def reset(self, seed=None, options=None):
+        rng = self._seed(seed)
+        p = self.p = self.process_reset_params(options)
+        self.t = 0
+        self.max_episode_steps = p["max_steps"]
+        self.rewards = []
+        self.segments, self.seg_start, self.seg_end = [], None, None
+        for _ in range(3):
+            self._add_segment(rng)
+        self.reward_visited = {self.segments[0][0]}
+        self.stamina_visited = set()
+        self.start = self.segments[0][0]
+        cos = max(0, min(5.5, p["camera_offset_scale"]))
+        self.camera_offset = -self.TILE * cos
+        self.camera_x = self.camera_offset
+        self.bg_scroll = 0
+        self.sprites = assets.agent_sprites(p["agent_scale"])
+        self.radius = int(25 * p["agent_scale"])
+        self.rotation = 270
+        self.vx = 0
+        self.cx = self.start[0] * self.TILE + self.radius
+        self.cy = self.start[1] * self.TILE + self.radius
+        self.agent_draw_x = (self.cx - (self.sprites[0].w >> 1)) - self.camera_offset
+        self.pos = (self.cx // self.TILE, self.cy // self.TILE)
+        self.current = (0, 0)
+        self._update_direction()
+        self.off_path = False
+        self.num_fails = 0
+        self.fall_off_locations = []
+        self.stamina = p["stamina_level"]
+        self.max_x = 0
+        self.tiles_visited = 0
+        self.max_visible_stamina = p["stamina_level"]
+        self.bar_height = int(SCREEN * (1 - (max(self.stamina, self.max_visible_stamina) / self.max_visible_stamina)))
+        self.cross_alpha = 0
+        self.cross_x = self.cross_y = 0
+        return self._render(), {"ground_truth": self.target_direction}
+
+    def step(self, action):
+        p = self.p
+        rng = self._rng
+        action = self.ACTIONS[int(action)]
+        reward = 0
+        done = False
+        if not self.off_path:
+            before = self.cx
+            self.cx, self.cy, self.rotation = move_free(self.cx, self.cy, self.rotation, action, p["agent_speed"])
+            self.vx = self.cx - before
+            self.camera_x += float(self.vx)
+            self.bg_scroll -= float(self.vx)
+            if abs(self.bg_scroll) >= self.TILE:
+                remainder = abs(self.bg_scroll) % abs(float(self.vx))
+                sign = self.bg_scroll / abs(self.bg_scroll)
+                self.bg_scroll = remainder * sign
+        else:
+            self.cx = self.start[0] * self.TILE + self.radius
+            self.cy = self.start[1] * self.TILE + self.radius
+            self.vx = 0
+            self.camera_x = self.camera_offset
+            self.bg_scroll = 0
+        self.pos = (self.cx // self.TILE, self.cy // self.TILE)
+        seg = int(self.pos[0]) // self.SEG
+        nodes = self.segments[seg]
+        if seg > len(self.segments) - 2:
+            self._add_segment(rng)
+        on_path = False
+        for i, node in enumerate(nodes):
+            if self.pos == node:
+                on_path = True
+                self.current = (seg, i)
+                if node not in self.reward_visited and node != self.start:
+                    reward += p["reward_path_progress"]
+                    self.tiles_visited += 1
+                    self.reward_visited.add(node)
+                if node not in self.stamina_visited and node != self.start:
+                    reward += p["reward_path_progress_dense"]
+                    self.stamina = p["stamina_level"]
+                    self.stamina_visited.add(node)
+                break
+        if not on_path:
+            reward += p["reward_fall_off"]
+            self.num_fails += 1
+            if p["visual_feedback"]:
+                self.cross_alpha = 255
+            self.off_path = True
+            if self.pos[0] < self.max_x:
+                done = True
+            elif self.pos in self.fall_off_locations:
+                done = True
+            else:
+                self.fall_off_locations.append(self.pos)
+            self.stamina_visited = set()
+            self.stamina = p["stamina_level"]
+        else:
+            self.cross_alpha = 0
+            self.off_path = False
+        # fall_off_rect.center = (cx - camera_x, cy): a 10x10 rect, floats C-cast
+        self.cross_x = R.cint(self.cx - self.camera_x) - 5
+        self.cross_y = self.cy - 5
+        # (`max_x_reached > previous_max_x` can never hold here: fall_off_locations is never cleared, :390-391)
+        reward += p["reward_step"]
+        self.stamina -= 1
+        if self.stamina == 0:
+            done = True
+        self.t += 1
+        if self.t == self.max_episode_steps:
+            done = True
+        self._update_direction()
+        if self.pos[0] > self.max_x and on_path:
+            self.max_x = self.pos[0]
+        self.rewards.append(reward)
+        if done:
+            info = {"reward": _seq_sum(self.rewards), "length": len(self.rewards), "num_fails": self.num_fails,
+                    "max_x": self.max_x, "tiles_visited": self.tiles_visited, "ground_truth": self.target_direction}
+        else:
+            info = {"ground_truth": self.target_direction}
+        self.bar_height = int(SCREEN * (1 - (min(self.stamina, self.max_visible_stamina) / self.max_visible_stamina)))
+        return self._render(), reward, done, False, info
+
+    # ---- _draw_surfaces / _draw_past_path (:111-160) ---------------------------------------------------
+    def _render(self):
+        p = self.p
+        T = self.TILE
+        dst = R.Surface(SCREEN, SCREEN)
+        if p["show_background"]:
+            col = R.Surface(T, T * self.GRID)  # draw_column_tile_surface (pygame_assets.py:801-818)
+            for i in range(self.GRID):
+                R.fill_rect(col, R.map_rgb((125, 177, 250)), 0, i * T, T, T)
+                tile = R.Surface(T, T)
+                R.fill(tile, (125, 177, 250))
+                R.rect(tile, (210, 210, 210), (0, 0, T, T), 1)
+                R.blit(tile, col, (0, i * T))
+            for i in range(math.ceil(SCREEN / T) + 2):
+                R.blit(col, dst, (i * T + self.bg_scroll - T, 0))
+        if p["show_past_path"]:
+            x = self.pos[0] - 1
+            if x >= 0:
+                depth = int(p["camera_offset_scale"])
+                past_x = max(0, x - depth)
+                ref = self._prev(self.current)
+                while x >= past_x and x >= 0:
+                    if ref is None:
+                        break
+                    x, y = self._node(ref)
+                    draw_x = x * T - self.camera_x
+                    R.rect(dst, (255, 255, 255), (draw_x, y * T, T, T))
+                    R.rect(dst, (210, 210, 210), (draw_x, y * T, T, T), 1)
+                    if x == past_x:
+                        break
+                    ref = self._prev(ref)
+        sp = self.sprites[self.rotation // 45]
+        R.blit(sp, dst, (self.agent_draw_x, self.cy - (sp.h >> 1)))
+        if p["show_stamina"]:
+            bar = R.Surface(int(16 * SCALE), SCREEN)
+            R.fill(bar, (0, 255, 0))
+            R.rect(bar, (255, 0, 0), (0, 0, 16 * SCALE, self.bar_height))
+            R.blit(bar, dst, (SCREEN - 16 * SCALE, 0))
+        if p["visual_feedback"] and self.cross_alpha == 255:
+            R.blit(assets.fall_off_cross(SCALE), dst, (self.cross_x, self.cross_y))
+        return R.array3d(dst)
+
+
 ORACLES = {
     "MortarMayhem-v0": MortarMayhemOracle,
     "MortarMayhem-Grid-v0": GridMortarMayhemOracle,
@@ -1424,6 +1659,7 @@ ORACLES = {
     "MortarMayhemB-Grid-v0": GridMortarMayhemBOracle,
     "MysteryPath-Grid-v0": GridMysteryPathOracle,
     "Endless-SearingSpotlights-v0": EndlessSearingSpotlightsOracle,
+    "Endless-MysteryPath-v0": EndlessMysteryPathOracle,
 }
 
 
