@@ -363,6 +363,17 @@ extern "C" long mg_mp_build_assets(const mg_mp_params* p, void* host_out, size_t
     return b.serialize(host_out, capacity);
 }
 
+// Endless Mystery Path: the agent sprites + the fall-off cross (endless_mystery_path.py:203-211) on black
+extern "C" long mg_ep_build_assets(const mg_ep_params* p, void* host_out, size_t capacity) {
+    if (!p) return MG_EINVAL;
+    Builder b;
+    if (!build_agent(b, p->agent_scale, false)) return MG_EINVAL;
+    if (!build_cross(b)) return MG_EINVAL;
+    Surface black(MG_W, MG_W);
+    b.add_template(0, black);
+    return b.serialize(host_out, capacity);
+}
+
 namespace {
 // Exit.__init__ / Exit.draw (pygame_assets.py:169-205): rounded-top door, 1-px (int(2*scale)) black outline
 bool build_exit(Builder& b, double scale) {

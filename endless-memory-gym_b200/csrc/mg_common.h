@@ -147,6 +147,46 @@ struct MgMPState {
     uint8_t pad[30];
 };
 
+// ---- Endless Mystery Path record (2048 bytes) ---------------------------------------------------
+// One path segment = a 7x7 MysteryPath + its transition tile (pygame_assets.py:559-604), 8 columns wide.
+// Cells are indexed x_local * 7 + y (x_local 0..6); bit 49 of the visited masks is the transition tile.
+#define MG_EP_MAXSEG 45
+#define MG_EP_MAXFALL 24
+struct MgEPSegment {
+    uint64_t path;      // bits 0..48: cell on the path; bits 56..58 start_y, 60..62 end_y
+    uint64_t reward_visited;
+    uint64_t stamina_visited;
+    uint64_t next[2];   // 2 bits per cell: where next_node lies (0 east, 1 north = y-1, 2 south = y+1, 3 west)
+};
+struct MgEPState {
+    MgRng rng;             // 40
+    double ep_reward;
+    double camera_x;       // accumulated in double like the reference (camera_offset may be fractional)
+    int32_t ep_len, t, num_fails, stamina, max_x, tiles_visited;
+    int32_t cx, cy;        // agent.rect.center (x grows without bound)
+    int32_t bg_scroll;     // -bg_scroll of the reference: 0 <= v < 12, a multiple of the x velocity
+    int32_t n_segments;
+    int32_t cur_x;         // current_node: global column, row
+    uint8_t cur_y, rot, off_path, cross_on, live, dir, pad0[2];  // dir: target_direction 0 east, 1 north, 2 south
+    int16_t cross_x, cross_y;  // fall_off_rect top-left
+    uint16_t n_fall, pad1;
+    int16_t fall[MG_EP_MAXFALL][2];  // fall_off_locations (normalised x, y)
+    uint8_t pad2[36];
+    MgEPSegment seg[MG_EP_MAXSEG];
+};
+
+#define MG_EP_MAXTILES 72
+struct MgEPFrame {
+    int32_t sx, sy, srot;       // sprite top-left on screen, sprite index
+    int32_t cross, cross_x, cross_y;
+    int32_t bar_h;              // stamina bar: red rows from the top; -1 = no bar
+    int32_t bg_off;             // show_background: screen x where a column of icy tiles starts; -1000 = black
+    int32_t n_tiles;            // past-path tiles that touch the screen
+    int32_t pad;
+    int8_t tile_x[MG_EP_MAXTILES];   // screen x of the tile's left edge (-11..83)
+    uint8_t tile_y[MG_EP_MAXTILES];  // tile row 0..6
+};
+
 // ---- Searing Spotlights record (1024 bytes) -----------------------------------------------------
 #define MG_SS_MAXSPOTS 32
 #define MG_SS_MAXCOINS 16
@@ -218,6 +258,8 @@ struct MgMPFrame {
 static_assert(sizeof(MgRng) == 40, "MgRng layout");
 static_assert(sizeof(MgMMState) == 256, "MgMMState must be 256 bytes (MG_MM_STATE_BYTES)");
 static_assert(sizeof(MgMPState) == 128, "MgMPState must be 128 bytes (MG_MP_STATE_BYTES)");
+static_assert(sizeof(MgEPSegment) == 40, "MgEPSegment layout");
+static_assert(sizeof(MgEPState) == 2048, "MgEPState must be 2048 bytes (MG_EP_STATE_BYTES)");
 static_assert(sizeof(MgSSSpot) == 24, "MgSSSpot layout");
 static_assert(sizeof(MgSSState) == 1024, "MgSSState must be 1024 bytes (MG_SS_STATE_BYTES)");
 static_assert(sizeof(MgAssetHeader) % 8 == 0, "MgAssetHeader alignment");

@@ -174,6 +174,88 @@ MG_HD void mg_mp_restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgMPD
     if (d.show_origin) mg_block_fill(c, buf, 12 * d.ox, 12 * d.oy, 12, 12, 0, 0, 0);
 }
 
+// ---- Endless Mystery Path -----------------------------------------------------------------------
+// _draw_surfaces (endless_mystery_path.py:137-160): [scrolling icy columns | black] -> past-path tiles -> agent
+// -> stamina bar -> fall-off cross.
+// Past-path tiles (:131-133): a white 12x12 rect, then a 1-px (210,210,210) frame. pygame draws the frame only
+// when the CLIPPED rect is wider than 2 px, else it fills the clipped rect with the frame colour.
+template <class Ctx>
+MG_HD void mg_ep_tiles(Ctx& c, uint8_t* buf, const MgEPFrame& f, bool erase) {
+    const int units = f.n_tiles * 12;  // one (tile, column) = 36 contiguous bytes per lane iteration
+    for (int u = c.lane; u < units; u += c.nl) {
+        const int t = u / 12, cl = u - 12 * t;
+        const int tx = f.tile_x[t], x = tx + cl;
+        if ((unsigned)x >= (unsigned)MG_W) continue;
+        const int xa = tx < 0 ? 0 : tx, xb = tx + 12 > MG_W ? MG_W : tx + 12;
+        const bool all_edge = !(2 < xb - xa) || cl == 0 || cl == 11;
+        uint8_t* o = buf + x * MG_COL_BYTES + (int)f.tile_y[t] * 36;
+        for (int v = 0; v < 12; ++v) {
+            uint8_t g = erase ? 0 : ((all_edge || v == 0 || v == 11) ? 210 : 255);
+            o[3 * v] = g, o[3 * v + 1] = g, o[3 * v + 2] = g;
+        }
+    }
+}
+
+// draw_column_tile_surface (pygame_assets.py:782-818) blitted every 12 px from `off` (<= 0): icy (125,177,250) tiles
+// with a 1-px (210,210,210) frame
+template <class Ctx>
+MG_HD void mg_ep_background(Ctx& c, uint8_t* buf, int off) {
+    for (int x = c.lane; x < MG_W; x += c.nl) {
+        const unsigned u = (unsigned)(x - off) % 12u;
+        const bool edge = u == 0u || u == 11u;
+        uint8_t* o = buf + x * MG_COL_BYTES;
+        for (int y = 0, v = 0; y < MG_W; ++y) {
+            const bool e = edge || v == 0 || v == 11;
+            o[0] = e ? 210 : 125, o[1] = e ? 210 : 177, o[2] = e ? 210 : 250;
+            o += 3;
+            if (++v == 12) v = 0;
+        }
+    }
+}
+
+// stamina_surface (:424-428): 4 x 84, green with `bar_h` red rows from the top, blitted at (80, 0)
+template <class Ctx>
+MG_HD void mg_ep_bar(Ctx& c, uint8_t* buf, int bar_h, bool erase) {
+    for (int i = c.lane; i < 4 * MG_W; i += c.nl) {
+        const int x = MG_W - 4 + i / MG_W, y = i % MG_W;
+        uint8_t* o = buf + x * MG_COL_BYTES + y * 3;
+        o[0] = (!erase && y < bar_h) ? 255 : 0;
+        o[1] = (!erase && y >= bar_h) ? 255 : 0;
+        o[2] = 0;
+    }
+}
+
+template <class Ctx>
+MG_HD void mg_ep_compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgEPFrame& f) {
+    if (f.bg_off > -1000) {
+        mg_ep_background(c, buf, f.bg_off);
+        c.sync();
+    }
+    if (f.n_tiles) {
+        mg_ep_tiles(c, buf, f, false);
+        c.sync();
+    }
+    mg_sprite_draw(c, buf, a, MG_SPR_AGENT0 + f.srot, f.sx, f.sy);
+    if (f.bar_h >= 0) {
+        c.sync();
+        mg_ep_bar(c, buf, f.bar_h, false);
+    }
+    if (f.cross) {
+        c.sync();
+        mg_sprite_draw(c, buf, a, MG_SPR_CROSS, f.cross_x, f.cross_y);
+    }
+}
+
+template <class Ctx>
+MG_HD void mg_ep_restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgEPFrame& f) {
+    if (f.bg_off > -1000) return;  // the next frame repaints every pixel
+    const MgBlackBg bg;
+    if (f.cross) mg_sprite_erase(c, buf, a, MG_SPR_CROSS, f.cross_x, f.cross_y, bg);
+    if (f.bar_h >= 0) mg_ep_bar(c, buf, 0, true);
+    mg_sprite_erase(c, buf, a, MG_SPR_AGENT0 + f.srot, f.sx, f.sy, bg);
+    if (f.n_tiles) mg_ep_tiles(c, buf, f, true);
+}
+
 // ---- Searing Spotlights ----------------------------------------------------------------------------
 // The frame is a per-pixel function of the state: layers in painter's order
 // (searing_spotlights.py:526-542), the spotlight layer being a black surface with colour-keyed discs blended

@@ -28,6 +28,7 @@
 #include "mg_frame.h"
 #include "mg_mm_logic.h"
 #include "mg_mp_logic.h"
+#include "mg_ep_logic.h"
 #include "mg_ss_logic.h"
 #include "mg_params_host.h"
 #include "mg_policy.h"
@@ -564,6 +565,32 @@ extern "C" int mg_mp_rollout(const mg_mp_params* p, const void* assets, void* st
     MgMPK k;
     mg_mp_derive(p, &k);
     return launch_rollout<MPPolicy>(k, assets, state, r, n, mp_act_dims(p), stream, 10);
+}
+
+extern "C" int mg_ep_reset(const mg_ep_params* p, const void* assets, void* state, const uint64_t* rng4,
+                           const mg_step_io* io, int n, void* stream) {
+    if (mg_ep_check_params(p)) return MG_EINVAL;
+    MgEPK k;
+    mg_ep_derive(p, &k);
+    return launch_env<EPPolicy>(k, assets, state, rng4, io, 1, n, MG_MODE_RESET, 1, stream, 10);
+}
+extern "C" int mg_ep_step(const mg_ep_params* p, const void* assets, void* state, const mg_step_io* io, int n,
+                          void* stream) {
+    return mg_ep_step_many(p, assets, state, io, 1, n, stream);
+}
+extern "C" int mg_ep_step_many(const mg_ep_params* p, const void* assets, void* state, const mg_step_io* ios,
+                               int n_steps, int n, void* stream) {
+    if (mg_ep_check_params(p)) return MG_EINVAL;
+    MgEPK k;
+    mg_ep_derive(p, &k);
+    return launch_env<EPPolicy>(k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, 1, stream, 10);
+}
+extern "C" int mg_ep_rollout(const mg_ep_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
+                             void* stream) {
+    if (mg_ep_check_params(p)) return MG_EINVAL;
+    MgEPK k;
+    mg_ep_derive(p, &k);
+    return launch_rollout<EPPolicy>(k, assets, state, r, n, 1, stream, 10);
 }
 
 extern "C" int mg_ss_reset(const mg_ss_params* p, const void* assets, void* state, const uint64_t* rng4,

@@ -40,7 +40,9 @@ MG_HD int mg_mp_neighbours(int i, int j, int* out) {
 
 // MysteryPath.__init__: returns the path as a 49-bit mask, or 0 if A* ran out of open nodes
 // (the reference raises Exception("No valid path found"), pygame_assets.py:724)
-MG_HD_NOINLINE uint64_t mg_mp_generate(MgRng& r, int sx, int sy, int ex, int ey) {
+// `order` (optional, MG_MP_NODES entries) receives the path's cell ids from the end node back to the start node.
+MG_HD_NOINLINE uint64_t mg_mp_generate(MgRng& r, int sx, int sy, int ex, int ey, uint8_t* order = nullptr,
+                                       int* n_order = nullptr) {
     const int n = MG_MP_CELLS;
     uint64_t wall = 0;
     for (int i = 0; i < n; ++i)
@@ -107,7 +109,13 @@ MG_HD_NOINLINE uint64_t mg_mp_generate(MgRng& r, int sx, int sy, int ex, int ey)
         int cur = open[w];
         if (cur == end) {
             uint64_t path = 0;
-            for (int at = end; at >= 0; at = prev[at]) path |= 1ull << at;
+            int cnt = 0;
+            for (int at = end; at >= 0; at = prev[at]) {
+                path |= 1ull << at;
+                if (order) order[cnt] = (uint8_t)at;
+                cnt++;
+            }
+            if (n_order) *n_order = cnt;
             return path;
         }
         for (int t = w; t + 1 < nopen; ++t) open[t] = open[t + 1];

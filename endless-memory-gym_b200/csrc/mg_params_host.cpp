@@ -142,6 +142,49 @@ void mg_mp_derive(const mg_mp_params* p, MgMPK* k) {
 }
 
 
+extern "C" int mg_ep_check_params(const mg_ep_params* p) {
+    if (!p) {
+        mg_set_err("params is NULL");
+        return MG_EINVAL;
+    }
+    if (!(p->agent_speed >= 0.0 && p->agent_speed < 84.0)) {
+        mg_set_err("agent_speed must be in [0, 84)");
+        return MG_EINVAL;
+    }
+    int radius = (int)(25 * p->agent_scale), hand = (int)(10 * p->agent_scale);
+    if (!(p->agent_scale > 0.0) || radius * 2 + hand + 14 > 255 || radius > 38) {
+        mg_set_err("agent_scale out of range");
+        return MG_EINVAL;
+    }
+    if (p->stamina_level < 1 || p->max_steps == 0) {
+        mg_set_err("stamina_level must be >= 1 and max_steps != 0");
+        return MG_EINVAL;
+    }
+    // depth of the drawn past path = int(camera_offset_scale) is NOT clamped by the reference (only the camera is)
+    if (!(p->camera_offset_scale > -1.0 && p->camera_offset_scale < 17.0)) {
+        mg_set_err("camera_offset_scale must be in (-1, 17)");
+        return MG_EINVAL;
+    }
+    return 0;
+}
+
+void mg_ep_derive(const mg_ep_params* p, MgEPK* k) {
+    memset(k, 0, sizeof(*k));
+    k->p = *p;
+    k->radius = (int)(25 * p->agent_scale);
+    k->step_axis = (int)(1.0 * p->agent_speed);
+    double cos_ = p->camera_offset_scale;
+    cos_ = cos_ < 0.0 ? 0.0 : (cos_ > 5.5 ? 5.5 : cos_);  // max(0, min(5.5, scale)) (:213)
+    k->camera_offset = -12.0 * cos_;
+    // sprite side = 2 * radius + int(10 * scale) + 14... taken from the asset header at run time; here only the
+    // episode-constant blit x: agent.rect.topleft[0] - camera_offset with rect.centerx = radius (:219-222)
+    int hand = (int)(10 * p->agent_scale);
+    int dim = k->radius * 2 + hand + 14;
+    k->agent_half = dim >> 1;
+    k->agent_draw_x = (int)((double)(k->radius - k->agent_half) - k->camera_offset);
+    k->depth = (int)p->camera_offset_scale;
+}
+
 extern "C" int mg_ss_check_params(const mg_ss_params* p) {
     if (!p) {
         mg_set_err("params is NULL");

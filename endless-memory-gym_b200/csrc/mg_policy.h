@@ -7,6 +7,7 @@
 #include "mg_frame.h"
 #include "mg_mm_logic.h"
 #include "mg_mp_logic.h"
+#include "mg_ep_logic.h"
 #include "mg_ss_logic.h"
 
 #if defined(__CUDACC__)
@@ -101,6 +102,7 @@ struct MMPolicy {
     typedef MgMMK K;
     typedef MgMMState State;
     typedef MgMMFrame Frame;
+    static MG_HD bool restores_clean(const K&) { return true; }
     static MG_HD void reset_env(const K& k, const MgAssetView&, State& s, Frame& f, double* gt) {
         mg_mm_reset_env(k, s, f, gt);
     }
@@ -138,6 +140,7 @@ struct MPPolicy {
     typedef MgMPK K;
     typedef MgMPState State;
     typedef MgMPDraw Frame;
+    static MG_HD bool restores_clean(const K&) { return true; }
     static MG_HD void reset_env(const K& k, const MgAssetView&, State& s, Frame& f, double*) { mg_mp_reset_env(k, s, f); }
     static MG_HD bool step_env(const K& k, const MgAssetView&, State& s, int a0, int a1, double& reward, double* info,
                                Frame& f, double*) {
@@ -155,6 +158,40 @@ struct MPPolicy {
     template <class Ctx>
     static MG_HD void restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f, const MgScratch&) {
         mg_mp_restore(c, buf, a, f, a.hdr->agent_dim >> 1);
+    }
+};
+
+struct EPPolicy {
+    static constexpr int kWarpExtra = 0, kCtaExtra = 0;
+    static constexpr int kTeamWarps = 1, kMaxThreads = 320;
+    static constexpr int kFrameBuf = 21248;
+    static constexpr bool kDirectStore = false;
+    static MG_HD void cta_init(uint8_t*, int, int) {}
+    static MG_HD void warp_init(uint8_t*, int) {}
+    typedef MgEPK K;
+    typedef MgEPState State;
+    typedef MgEPFrame Frame;
+    // with show_background every frame repaints the whole buffer instead of un-patching it
+    static MG_HD bool restores_clean(const K& k) { return !k.p.show_background; }
+    static MG_HD void reset_env(const K& k, const MgAssetView&, State& s, Frame& f, double* gt) {
+        mg_ep_reset_env(k, s, f, gt);
+    }
+    static MG_HD bool step_env(const K& k, const MgAssetView&, State& s, int a0, int, double& reward, double* info,
+                               Frame& f, double* gt) {
+        return mg_ep_step_env(k, s, a0, reward, info, f, gt);
+    }
+    template <class Ctx>
+    static MG_HD void logic(Ctx& c, const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0,
+                            int a1, MgFrameJob& job, Frame* fr, const MgScratch&) {
+        if (c.lane == 0) mg_env_logic<EPPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
+    }
+    template <class Ctx>
+    static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f, const MgScratch&) {
+        mg_ep_compose(c, buf, a, f);
+    }
+    template <class Ctx>
+    static MG_HD void restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f, const MgScratch&) {
+        mg_ep_restore(c, buf, a, f);
     }
 };
 
@@ -178,6 +215,7 @@ struct SSPolicy {
     typedef MgSSK K;
     typedef MgSSState State;
     typedef MgSSFrame Frame;
+    static MG_HD bool restores_clean(const K&) { return false; }
     static MG_HD const double* trig(const MgAssetView& a) { return (const double*)(a.base + a.hdr->trig_off); }
 
     // Same control flow as mg_env_logic, but the step is split A (one lane) / B (one lane per spotlight) /

@@ -20,6 +20,8 @@ MG_MM_MAX_COMMANDS = 152
 MG_MM_STATE_BYTES = 256
 MG_MP_STATE_BYTES = 128
 MG_SS_STATE_BYTES = 1024
+MG_EP_STATE_BYTES = 2048
+MG_EP_MAX_SEGMENTS = 45
 MG_FLAG_AUTORESET = 1
 MG_FLAG_STREAM_OBS = 2
 MG_MM_CONTINUOUS, MG_MM_GRID, MG_MM_ENDLESS, MG_MM_B, MG_MM_B_GRID = 0, 1, 2, 3, 4
@@ -86,6 +88,17 @@ class SSParams(C.Structure):
     ]
 
 
+class EPParams(C.Structure):
+    _fields_ = [
+        ("max_steps", C.c_int32), ("show_origin", C.c_int32), ("show_past_path", C.c_int32),
+        ("show_background", C.c_int32), ("show_stamina", C.c_int32), ("visual_feedback", C.c_int32),
+        ("stamina_level", C.c_int32), ("pad0", C.c_int32),
+        ("agent_scale", C.c_double), ("agent_speed", C.c_double), ("camera_offset_scale", C.c_double),
+        ("reward_fall_off", C.c_double), ("reward_path_progress", C.c_double),
+        ("reward_path_progress_dense", C.c_double), ("reward_step", C.c_double),
+    ]
+
+
 class StepIO(C.Structure):
     _fields_ = [
         ("actions", C.c_void_p), ("obs", C.c_void_p), ("final_obs", C.c_void_p), ("reward", C.c_void_p),
@@ -126,7 +139,7 @@ def lib():
     L.mg_device_info.argtypes = [C.POINTER(i32)] * 3 + [C.POINTER(C.c_size_t)]
     L.mg_seed_pcg64.argtypes = [vp, i32, vp]
     L.mg_selftest_pcg64_host.argtypes = [vp, vp, vp, vp, i32, vp, vp]
-    for fam, P in (("mm", MMParams), ("mp", MPParams), ("ss", SSParams)):
+    for fam, P in (("mm", MMParams), ("mp", MPParams), ("ss", SSParams), ("ep", EPParams)):
         getattr(L, f"mg_{fam}_check_params").argtypes = [C.POINTER(P)]
         getattr(L, f"mg_{fam}_reset").argtypes = [C.POINTER(P), vp, vp, vp, C.POINTER(StepIO), i32, vp]
         getattr(L, f"mg_{fam}_step").argtypes = [C.POINTER(P), vp, vp, C.POINTER(StepIO), i32, vp]

@@ -19,7 +19,7 @@ class EnvSpec:
     def __init__(self, env_id, family, variant, defaults, action_nvec, state_bytes, info_keys, check=None,
                  has_ground_truth=False, gt_dim=2):
         self.id = env_id
-        self.family = family            # "mm" | "mp" | "ss": mg_<family>_reset / _step
+        self.family = family            # "mm" | "mp" | "ss" | "ep": mg_<family>_reset / _step
         self.variant = variant
         self.default_reset_parameters = defaults
         self.action_nvec = action_nvec  # [3, 3] = MultiDiscrete([3, 3]); [4] = Discrete(4)
@@ -91,6 +91,13 @@ class EnvSpec:
                     setattr(s, name, int(v))
                 else:
                     setattr(s, name, float(v))
+            return s
+        if self.family == "ep":
+            s = L.EPParams()
+            for name, ctype in L.EPParams._fields_:
+                if name == "pad0":
+                    continue
+                setattr(s, name, int(p[name]) if ctype is L.C.c_int32 else float(p[name]))
             return s
         raise KeyError(self.family)
 
@@ -247,6 +254,23 @@ _ESS_DEFAULTS = {
     "reward_coin": 0.25,
 }
 
+_EMP_DEFAULTS = {
+    "max_steps": -1,
+    "agent_scale": 1.0 * SCALE,
+    "agent_speed": 12.0 * SCALE,
+    "show_origin": False,
+    "show_past_path": True,
+    "show_background": False,
+    "show_stamina": False,
+    "visual_feedback": True,
+    "camera_offset_scale": 5.0,
+    "stamina_level": 20,
+    "reward_fall_off": 0.0,
+    "reward_path_progress": 0.1,
+    "reward_path_progress_dense": 0.0,
+    "reward_step": 0.0,
+}
+
 _MM_INFO = {"reward": L.MG_INFO_REWARD, "length": L.MG_INFO_LENGTH, "success": L.MG_INFO_SUCCESS,
             "commands_completed": L.MG_INFO_A}
 _EMM_INFO = {"reward": L.MG_INFO_REWARD, "length": L.MG_INFO_LENGTH, "commands_completed": L.MG_INFO_A,
@@ -257,6 +281,8 @@ _SS_INFO = {"reward": L.MG_INFO_REWARD, "length": L.MG_INFO_LENGTH, "success": L
             "agent_health": L.MG_INFO_A, "coins_collected": L.MG_INFO_B}
 _ESS_INFO = {"reward": L.MG_INFO_REWARD, "length": L.MG_INFO_LENGTH, "agent_health": L.MG_INFO_A,
              "coins_collected": L.MG_INFO_B}
+_EMP_INFO = {"reward": L.MG_INFO_REWARD, "length": L.MG_INFO_LENGTH, "num_fails": L.MG_INFO_A, "max_x": L.MG_INFO_B,
+             "tiles_visited": L.MG_INFO_C}
 
 SPECS = {
     s.id: s for s in (
@@ -274,11 +300,13 @@ SPECS = {
         EnvSpec("SearingSpotlights-v0", "ss", L.MG_SS_FINITE, _SS_DEFAULTS, [3, 3], L.MG_SS_STATE_BYTES, _SS_INFO),
         EnvSpec("Endless-SearingSpotlights-v0", "ss", L.MG_SS_ENDLESS, _ESS_DEFAULTS, [3, 3], L.MG_SS_STATE_BYTES,
                 _ESS_INFO, has_ground_truth=True, gt_dim=4),
+        EnvSpec("Endless-MysteryPath-v0", "ep", 0, _EMP_DEFAULTS, [4], L.MG_EP_STATE_BYTES, _EMP_INFO,
+                has_ground_truth=True, gt_dim=3),
     )
 }
 
 # ids the reference registers that this engine does not accelerate yet
-NOT_BUILT = ("Endless-MysteryPath-v0",)
+NOT_BUILT = ()
 
 
 def spec(env_id: str) -> EnvSpec:

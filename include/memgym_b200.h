@@ -19,6 +19,8 @@
  *   mg_ss_reset / mg_ss_step   <-  SearingSpotlightsEnv.reset/step     memory_gym/searing_spotlights.py:332-450, 452-562
  *                                  EndlessSearingSpotlightsEnv.reset/step  memory_gym/endless_searing_spotlights.py:294-407, 409-504
  *                                  Spotlight / Coin / Exit / sampler   memory_gym/pygame_assets.py:7-239
+ *   mg_ep_reset / mg_ep_step   <-  EndlessMysteryPathEnv.reset/step    memory_gym/endless_mystery_path.py:192-268, 270-444
+ *                                  EndlessMysteryPath (segments)       memory_gym/pygame_assets.py:495-604
  *   mg_*_build_assets          <-  CharacterController.create_character_sprites  character_controller.py:29-75,
  *                                  Command.__init__ pygame_assets.py:254-304, MortarTile :316-343, Exit.draw :191-205,
  *                                  Coin.draw :145-152, fall-off cross mystery_path.py:175-182
@@ -56,6 +58,8 @@ extern "C" {
 #define MG_MM_STATE_BYTES 256      /* one env record (Mortar Mayhem family) */
 #define MG_MP_STATE_BYTES 128      /* one env record (Mystery Path) */
 #define MG_SS_STATE_BYTES 1024     /* one env record (Searing Spotlights) */
+#define MG_EP_STATE_BYTES 2048     /* one env record (Endless Mystery Path) */
+#define MG_EP_MAX_SEGMENTS 45      /* capacity of the per-env path: 45 segments x 8 columns = 360 columns */
 
 #define MG_EINVAL (-1)  /* bad argument / unsupported option value */
 #define MG_ENODEV (-2)  /* no usable CUDA device */
@@ -65,9 +69,9 @@ extern "C" {
 #define MG_INFO_LENGTH 1   /* episode length in steps */
 #define MG_INFO_SUCCESS 2  /* MM/MM-Grid/MP/SS: success flag                                     */
 #define MG_INFO_A 3        /* MM: commands_completed (fraction); EMM: commands_completed (count); */
-                           /* MP: num_fails; SS/ESS: agent_health (fraction)                      */
+                           /* MP/EMP: num_fails; SS/ESS: agent_health (fraction)                  */
 #define MG_INFO_B 4        /* EMM: max_command_sequence; SS: coins_collected (fraction);          */
-                           /* ESS: coins_collected (count)                                        */
+                           /* ESS: coins_collected (count); EMP: max_x                            */
 #define MG_INFO_GT0 5      /* Endless: ground_truth of the terminal step, MG_GT_COLS columns 5..8  */
 #define MG_INFO_GT1 6
 #define MG_INFO_GT2 7
@@ -180,6 +184,28 @@ typedef struct mg_ss_params {
     int32_t coin_show_duration;
 } mg_ss_params;
 
+/* ---- Endless Mystery Path --------------------------------------------------------------------- */
+/* Field names follow default_reset_parameters (endless_mystery_path.py:22-37). Actions: Discrete(4)
+ * (0 no-op, 1 right, 2 up, 3 down). show_origin has no effect in the reference (:151, the condition can
+ * never hold) and is accepted for compatibility only. */
+typedef struct mg_ep_params {
+    int32_t max_steps;
+    int32_t show_origin;
+    int32_t show_past_path;
+    int32_t show_background;
+    int32_t show_stamina;
+    int32_t visual_feedback;
+    int32_t stamina_level;
+    int32_t pad0;
+    double agent_scale;
+    double agent_speed;
+    double camera_offset_scale;
+    double reward_fall_off;
+    double reward_path_progress;
+    double reward_path_progress_dense;
+    double reward_step;
+} mg_ep_params;
+
 /* ---- per-call I/O (all device pointers; nullable ones are marked) ----------------------------- */
 typedef struct mg_step_io {
     const int64_t* actions; /* [n][2] (MultiDiscrete([3,3])) or [n] (Discrete(4), MM-Grid); unused by reset */
@@ -189,7 +215,8 @@ typedef struct mg_step_io {
     uint8_t* done;          /* [n]; unused by reset */
     double* info;           /* [n][MG_INFO_COLS], written only where done; unused by reset */
     double* ground_truth;   /* nullable: [n][MG_GT_COLS], every step and reset (Endless envs: EMM target / 5.0 in  */
-                            /* columns 0..1; ESS (agent x, y, coin x, y) / 84; unused columns are left alone)   */
+                            /* columns 0..1; ESS (agent x, y, coin x, y) / 84; EMP one-hot (east, north, south)  */
+                            /* of the next path tile in columns 0..2; unused columns are left alone)           */
     const uint8_t* reset_mask; /* reset only, nullable: [n], reset env i iff mask[i] != 0 */
     uint32_t flags;         /* MG_FLAG_* */
     uint32_t warps_per_cta; /* 0 = library default; tuning knob (frame buffers resident per SM) */
@@ -229,6 +256,7 @@ typedef struct mg_rollout_io {
 long mg_mm_build_assets(const mg_mm_params* p, int thick_circle_legacy, void* host_out, size_t capacity);
 long mg_mp_build_assets(const mg_mp_params* p, void* host_out, size_t capacity);
 long mg_ss_build_assets(const mg_ss_params* p, void* host_out, size_t capacity);
+long mg_ep_build_assets(const mg_ep_params* p, void* host_out, size_t capacity);
 
 /* numpy SeedSequence(seed) -> PCG64 initial state for `n` seeds (host). out: n records of
  * {state_lo, state_hi, inc_lo, inc_hi} (uint64 each). Bit-identical to
@@ -283,11 +311,23 @@ int mg_ss_step_many(const mg_ss_params* p, const void* assets, void* state, cons
 int mg_ss_rollout(const mg_ss_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
                   void* stream);
 
+int mg_ep_reset(const mg_ep_params* p, const void* assets, void* state, const uint64_t* rng4,
+                const mg_step_io* io, int n, void* stream);
+int mg_ep_step(const mg_ep_params* p, const void* assets, void* state, const mg_step_io* io, int n,
+               void* stream);
+
+int mg_ep_step_many(const mg_ep_params* p, const void* assets, void* state, const mg_step_io* ios, int n_steps,
+                    int n, void* stream);
+
+int mg_ep_rollout(const mg_ep_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
+                  void* stream);
+
 /* Option validation without a device: 0 if the reset/step kernels accept `p`, else MG_EINVAL with
  * mg_last_error() naming the offending field. */
 int mg_mm_check_params(const mg_mm_params* p);
 int mg_mp_check_params(const mg_mp_params* p);
 int mg_ss_check_params(const mg_ss_params* p);
+int mg_ep_check_params(const mg_ep_params* p);
 
 /* Library / device introspection. */
 int mg_abi_version(void);

@@ -29,7 +29,7 @@ template <class P>
 int run_q(const typename P::K& k, const void* assets, void* state, MgKIO q) {
     typedef typename P::State State;
     typedef typename P::Frame Frame;
-    constexpr bool kCheckClean = !std::is_same<P, SSPolicy>::value;
+    const bool kCheckClean = P::restores_clean(k);
     const MgAssetView view = mg_asset_view(assets);
     alignas(128) static thread_local uint8_t buf[MG_FRAME_BYTES];
     static thread_local std::vector<uint8_t> wextra, cextra;  // the kernel's per-warp / per-CTA scratch
@@ -134,6 +134,19 @@ extern "C" int mgsim_ss(const mg_ss_params* p, const void* assets, void* state, 
     MgSSK k;
     mg_ss_derive(p, &k);
     return run<SSPolicy>(k, assets, state, rng4, io, n, mode, 2);
+}
+extern "C" int mgsim_ep(const mg_ep_params* p, const void* assets, void* state, const uint64_t* rng4,
+                        const mg_step_io* io, int n, int mode) {
+    if (mg_ep_check_params(p)) return MG_EINVAL;
+    MgEPK k;
+    mg_ep_derive(p, &k);
+    return run<EPPolicy>(k, assets, state, rng4, io, n, mode, 1);
+}
+extern "C" int mgsim_ep_rollout(const mg_ep_params* p, const void* assets, void* state, const mg_rollout_io* r, int n) {
+    if (mg_ep_check_params(p)) return MG_EINVAL;
+    MgEPK k;
+    mg_ep_derive(p, &k);
+    return run_rollout<EPPolicy>(k, assets, state, r, n, 1);
 }
 extern "C" int mgsim_mm_rollout(const mg_mm_params* p, const void* assets, void* state, const mg_rollout_io* r, int n) {
     if (mg_mm_check_params(p)) return MG_EINVAL;

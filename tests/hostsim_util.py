@@ -39,7 +39,7 @@ class HostSimBackend:
         self._host = _CudaBackend.__new__(_CudaBackend)  # host-side helpers (assets, seeding, validation)
         self._host.lib = L.lib()
         vp = C.c_void_p
-        for fam, P in (("mm", L.MMParams), ("mp", L.MPParams), ("ss", L.SSParams)):
+        for fam, P in (("mm", L.MMParams), ("mp", L.MPParams), ("ss", L.SSParams), ("ep", L.EPParams)):
             getattr(self.sim, f"mgsim_{fam}").argtypes = [C.POINTER(P), vp, vp, vp, C.POINTER(L.StepIO), C.c_int, C.c_int]
 
     def check_device(self, device):

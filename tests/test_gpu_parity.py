@@ -11,7 +11,8 @@ from replay_util import replay_golden_batched, replay_golden_single, rollout_vs_
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts", "ss_black",
-         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts", "ess", "ess_opts", "ess_black", "ess_nocoin"]
+         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts", "ess", "ess_opts", "ess_black", "ess_nocoin",
+         "emp", "emp_opts", "emp_nopast", "emp_cam"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -48,6 +49,13 @@ def test_golden_batched_autoreset(name):
     ("SearingSpotlights-v0", {"max_steps": 40, "sample_agent_position": False, "light_dim_off_duration": 0,
                               "show_last_positive_reward": False, "agent_visible": True, "coin_scale": 1.0,
                               "exit_scale": 1.0, "agent_scale": 0.4, "agent_speed": 5.0, "num_coins": [3]}, 300, 8),
+    ("Endless-MysteryPath-v0", None, 64, 0),
+    ("Endless-MysteryPath-v0", {"camera_offset_scale": 0.0, "stamina_level": 9, "reward_fall_off": -0.3,
+                                "reward_path_progress_dense": 0.02, "reward_step": -0.001}, 64, 3),
+    ("Endless-MysteryPath-v0", {"camera_offset_scale": 1.7, "show_background": True, "show_stamina": True,
+                                "agent_speed": 13.0, "max_steps": 30, "agent_scale": 0.5}, 300, 9),
+    ("Endless-MysteryPath-v0", {"camera_offset_scale": 9.0, "agent_speed": 7.0, "stamina_level": 35,
+                                "show_stamina": True, "visual_feedback": False}, 48, 1),
     ("Endless-SearingSpotlights-v0", {"steps_per_coin": 40}, 64, 0),
     ("Endless-SearingSpotlights-v0", {"max_steps": 55, "coins_visible": True, "agent_visible": True, "agent_health": 3,
                                       "spot_damage": 0.7, "initial_spawns": 6, "spawn_interval": 7,
@@ -76,7 +84,8 @@ def _random_actions(env, steps, seed):
                                               ("MysteryPath-v0", 8192, {"max_steps": 48}),
                                               ("Endless-MortarMayhem-v0", 8192, None),
                                               ("SearingSpotlights-v0", 8192, {"max_steps": 40}),
-                                              ("Endless-SearingSpotlights-v0", 8192, {"steps_per_coin": 40})])
+                                              ("Endless-SearingSpotlights-v0", 8192, {"steps_per_coin": 40}),
+                                              ("Endless-MysteryPath-v0", 8192, None)])
 def test_full_size_properties(env_id, n, options):
     """At BASELINE.json's batch sizes: (1) bit-identical to the same envs run in small shards with other
     launch geometries (1 / 3 warps per CTA) — env i's result depends only on seed0+i and its actions;
@@ -168,7 +177,7 @@ def test_abi_rejects_bad_arguments():
 
 
 @pytest.mark.parametrize("env_id", ["MortarMayhem-v0", "MortarMayhem-Grid-v0", "MysteryPath-v0", "SearingSpotlights-v0",
-                                    "Endless-SearingSpotlights-v0"])
+                                    "Endless-SearingSpotlights-v0", "Endless-MysteryPath-v0"])
 def test_rollout_equals_step_loop(env_id):
     """mg_*_rollout (ONE launch, every warp runs all T steps of its envs) and mg_*_step_many (T launches
     enqueued by one call, programmatic dependent launch between them) give exactly what T separate

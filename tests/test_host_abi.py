@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     text = open(os.path.join(ROOT, "include", "memgym_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     names = sorted(set(re.findall(r"\b(mg_[a-z0-9_]+)\s*\(", text)))
-    assert len(names) == 23
+    assert len(names) == 29
     lib = L.lib()
     for n in names:
         assert hasattr(lib, n), n
@@ -213,5 +213,12 @@ def test_option_validation_and_loud_failure_without_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(L.MemGymError):
             mg.make("MortarMayhem-v0", num_envs=4)  # no CPU fallback
-    with pytest.raises(NotImplementedError):
-        mg.make("Endless-MysteryPath-v0", num_envs=4)
+    # all 10 ids the reference registers (memory_gym/__init__.py:13-60) are built
+    assert len(mg.registered_ids()) == 10 and not mg.NOT_BUILT
+    ess = SPECS["Endless-SearingSpotlights-v0"]
+    with pytest.raises(L.MemGymError):  # the reference crashes in step() without show_last_action
+        be.check_params("ss", ess.to_struct(ess.process_reset_params({"show_last_action": False})))
+    emp = SPECS["Endless-MysteryPath-v0"]
+    with pytest.raises(L.MemGymError):
+        be.check_params("ep", emp.to_struct(emp.process_reset_params({"stamina_level": 0})))
+    assert C.sizeof(L.EPParams) == 8 * 4 + 7 * 8

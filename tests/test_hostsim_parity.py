@@ -8,7 +8,8 @@ from hostsim_util import HostSimBackend
 from replay_util import replay_golden_batched, replay_golden_single, rollout_vs_oracle
 
 CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts", "ss_black",
-         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts", "ess", "ess_opts", "ess_black", "ess_nocoin"]
+         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts", "ess", "ess_opts", "ess_black", "ess_nocoin",
+         "emp", "emp_opts", "emp_nopast", "emp_cam"]
 
 
 @pytest.fixture(scope="module")
@@ -50,6 +51,13 @@ def test_golden_batched_autoreset(name, backend):
     ("SearingSpotlights-v0", {"max_steps": 40, "sample_agent_position": False, "light_dim_off_duration": 0,
                               "show_last_positive_reward": False, "agent_visible": True, "coin_scale": 1.0,
                               "exit_scale": 1.0, "agent_scale": 0.4, "agent_speed": 5.0, "num_coins": [3]}),
+    ("Endless-MysteryPath-v0", None),
+    ("Endless-MysteryPath-v0", {"camera_offset_scale": 0.0, "stamina_level": 9, "reward_fall_off": -0.3,
+                                "reward_path_progress_dense": 0.02, "reward_step": -0.001}),
+    ("Endless-MysteryPath-v0", {"camera_offset_scale": 1.7, "show_background": True, "show_stamina": True,
+                                "agent_speed": 13.0, "max_steps": 30, "agent_scale": 0.5}),
+    ("Endless-MysteryPath-v0", {"camera_offset_scale": 9.0, "agent_speed": 7.0, "stamina_level": 35,
+                                "show_stamina": True, "visual_feedback": False}),
     ("Endless-SearingSpotlights-v0", {"steps_per_coin": 40}),
     ("Endless-SearingSpotlights-v0", {"max_steps": 55, "coins_visible": True, "agent_visible": True, "agent_health": 3,
                                       "spot_damage": 0.7, "initial_spawns": 6, "spawn_interval": 7,
@@ -71,7 +79,9 @@ def test_rollout_vs_oracle(env_id, options, backend):
                                          ("SearingSpotlights-v0", {"max_steps": 60}),
                                          ("SearingSpotlights-v0", {"max_steps": 45, "agent_visible": True,
                                                                    "light_threshold": 90, "num_coins": [3]}),
-                                         ("Endless-SearingSpotlights-v0", {"steps_per_coin": 40, "agent_speed": 5.0})])
+                                         ("Endless-SearingSpotlights-v0", {"steps_per_coin": 40, "agent_speed": 5.0}),
+                                         ("Endless-MysteryPath-v0", {"show_stamina": True}),
+                                         ("Endless-MysteryPath-v0", {"show_background": True, "agent_speed": 5.0})])
 def test_rollout_equals_step_loop_hostsim(env_id, opts, backend):
     """rollout() (env-major: all T steps of an env back to back, persistent per-warp scratch — exercises the
     incremental frame paths; slot t % ring, per-step reward/done/info rows) == T step() calls."""
@@ -81,7 +91,8 @@ def test_rollout_equals_step_loop_hostsim(env_id, opts, backend):
     n, T = 6, 130
     a = mg.MemoryGymVecEnv(env_id, n, device="cpu", _backend=backend)
     b = mg.MemoryGymVecEnv(env_id, n, device="cpu", _backend=backend)
-    acts = torch.as_tensor(np.random.default_rng(1).integers(0, 3, (T, n, 2)))
+    nvec = mg.spec(env_id).action_nvec
+    acts = torch.as_tensor(np.random.default_rng(1).integers(0, nvec[0], (T, n, 2) if len(nvec) > 1 else (T, n)))
     a.reset(seed=9, options=opts)
     b.reset(seed=9, options=opts)
     ring = torch.zeros((4, n, 84, 84, 3), dtype=torch.uint8)
