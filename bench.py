@@ -33,7 +33,8 @@ for p in (ROOT, os.path.join(ROOT, "endless-memory-gym_b200")):
 
 METRIC = "million env-steps/sec"
 OBS_BYTES = 84 * 84 * 3
-STATE_BYTES = {"mm": 256, "mp": 128, "ss": 1024}
+GRID_IDS = ("MortarMayhem-Grid-v0", "MortarMayhemB-Grid-v0", "MysteryPath-Grid-v0", "Endless-MysteryPath-v0")  # Discrete(4)
+STATE_BYTES = {"mm": 256, "mp": 128, "ss": 1024, "ep": 2048}
 
 
 def alg_bytes_per_env_step(family, n_act, steps_per_launch=1):
@@ -49,7 +50,7 @@ def _cpu_worker(args):
     from oracle import memgym_oracle as O
     env = O.make(env_id)
     rng = np.random.default_rng(seed)
-    grid = env_id == "MortarMayhem-Grid-v0"
+    grid = env_id in GRID_IDS
     steps = 0
     t0 = time.perf_counter()
     env.reset(seed=seed)
@@ -126,7 +127,7 @@ def _ref_worker(args):
     from oracle import memgym_oracle as O
     env = O.make(env_id)
     rng = np.random.default_rng(seed)
-    grid = env_id == "MortarMayhem-Grid-v0"
+    grid = env_id in GRID_IDS
     env.reset(seed=seed)
     t0 = None
     for i in range(warm + timed):
