@@ -521,6 +521,17 @@ MG_HD void mg_ss_draw_layer(Ctx& c, uint8_t* base, const MgAssetView& a, const M
     }
 }
 
+// the whole base buffer from scratch (after a reset, a background change, or in a non-default layer order): cold
+template <class Ctx>
+MG_HD_NOINLINE void mg_ss_rebuild_base(Ctx& c, uint8_t* base, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f) {
+    uint32_t c_even, c_odd;
+    mg_ss_bg_colours(f.bg_kind, 0, c_even, c_odd);
+    mg_ss_fill_bg(c, base, c_even, c_odd);
+    c.sync();
+    for (int li = 1; li < k.n_layers; ++li)
+        if (k.layers[li] != 1) mg_ss_draw_layer(c, base, a, k, f, k.layers[li]);
+}
+
 // Bring `base` up to date with frame f. `base` = every layer EXCEPT the spotlight layer, in painter's order
 // (layers above the spotlight layer are never dimmed: their pixels are forced lit in the mask instead).
 // `simple` = the reference's default order (coins, exit, agent below the spotlight layer, bar on top): then a
@@ -548,16 +559,13 @@ MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, cons
                     mg_put_px(base, x, y, mg_ss_under_no_agent(a, k, f, spot_li, x, y));
             }
             c.sync();
-            mg_ss_draw_layer(c, base, a, k, f, 5);
+            mg_sprite_draw(c, base, a, MG_SPR_AGENT0 + f.srot, f.sx - half, f.sy - half);
+            c.sync();
         }
-        mg_ss_draw_layer(c, base, a, k, f, 2);  // the bar changes every step and sits on top
-    } else {
-        uint32_t c_even, c_odd;
-        mg_ss_bg_colours(f.bg_kind, 0, c_even, c_odd);
-        mg_ss_fill_bg(c, base, c_even, c_odd);
+        mg_ss_draw_bar(c, base, k, f);  // the bar changes every step and sits on top
         c.sync();
-        for (int li = 1; li < k.n_layers; ++li)
-            if (k.layers[li] != 1) mg_ss_draw_layer(c, base, a, k, f, k.layers[li]);
+    } else {
+        mg_ss_rebuild_base(c, base, a, k, f);
     }
     if (c.lane == 0) {
         MgSSBaseDesc& w = wm->desc;
@@ -603,15 +611,12 @@ MG_HD void mg_ss_build_lit(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const 
 }
 
 // frame = lit ? base : dim(base), 16 bytes at a time, straight to the observation buffer (coalesced 128-bit
-// stores: consecutive lanes write consecutive chunks)
-template <class Ctx>
-MG_HD void mg_ss_masked_copy(Ctx& c, uint8_t* out, const MgSSWarpMem* wm, const MgSSCtaTables* t, int alpha, bool stream) {
+// stores: consecutive lanes write consecutive chunks). kLut = false: alpha == 255 (dimmed = black), the steady
+// state of an episode; kLut = true: 0 < alpha < 255 through the per-alpha table (the light-dimming ramp).
+template <bool kLut, class Ctx>
+MG_HD void mg_ss_masked_copy_t(Ctx& c, uint8_t* out, const MgSSWarpMem* wm, const MgSSCtaTables* t, bool stream) {
     const MgVec16* src = reinterpret_cast<const MgVec16*>(wm->base);
     MgVec16* dst = reinterpret_cast<MgVec16*>(out);
-    if (alpha == 0) {
-        for (int i = c.lane; i < MG_SS_CHUNKS; i += c.nl) c.store16(dst + i, src[i], stream);
-        return;
-    }
     // four chunks per lane in flight: all loads first, then the stores (the loop is latency-, not issue-bound)
     for (int i0 = c.lane; i0 < MG_SS_CHUNKS; i0 += 4 * c.nl) {
         MgVec16 o[4];
@@ -624,7 +629,7 @@ MG_HD void mg_ss_masked_copy(Ctx& c, uint8_t* out, const MgSSWarpMem* wm, const 
             const unsigned w = p0 >> 5, sh = p0 & 31u;
             const uint32_t v = c.funnel_r(wm->lit[w], wm->lit[w + 1], sh);  // 6 lit bits from the flat pixel bitmap
             const MgVec16 m = t->mask[phase][(int)(v & 63u)], b = src[i];
-            if (alpha == 255) {
+            if (!kLut) {
                 o[u].x = b.x & m.x, o[u].y = b.y & m.y, o[u].z = b.z & m.z, o[u].w = b.w & m.w;
             } else {
                 const uint8_t* lut = wm->dimlut;
@@ -644,64 +649,60 @@ MG_HD void mg_ss_masked_copy(Ctx& c, uint8_t* out, const MgSSWarpMem* wm, const 
     }
 }
 
-// One Searing-Spotlights frame -> `out` (the env's 21168 observation bytes in global memory)
+// the cold variants: alpha == 0 (plain copy, the reset frame) and the dimming ramp
 template <class Ctx>
-MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
-                      MgSSWarpMem* wm, const MgSSCtaTables* tables, bool stream) {
-    int spot_li = 1, bar_li = 0;
-    for (int li = 0; li < k.n_layers; ++li) {
-        if (k.layers[li] == 1) spot_li = li;
-        if (k.layers[li] == 2) bar_li = li;
+MG_HD_NOINLINE void mg_ss_masked_copy_cold(Ctx& c, uint8_t* out, MgSSWarpMem* wm, const MgSSCtaTables* t, int alpha,
+                                           bool stream) {
+    if (alpha == 0) {
+        const MgVec16* src = reinterpret_cast<const MgVec16*>(wm->base);
+        MgVec16* dst = reinterpret_cast<MgVec16*>(out);
+        for (int i = c.lane; i < MG_SS_CHUNKS; i += c.nl) c.store16(dst + i, src[i], stream);
+        return;
     }
-    // the reference's default order: bg, coins, exit, agent, SPOT, bar
-    const bool simple = spot_li == k.n_layers - 2 && bar_li == k.n_layers - 1;
-    // 1. every layer but the spotlight layer (kept across frames, patched where it changed)
-    c.stamp(8);
-    mg_ss_update_base(c, wm, a, k, f, spot_li, simple);
-    c.stamp(9);
-    // 2. which pixels stay undimmed: the colour-keyed discs, and whatever is painted above the spotlight layer
-    if (f.alpha != 0) {
-        mg_ss_build_lit(c, wm, a, f, bar_li > spot_li ? tables->bar_lit : nullptr);
-        if (!simple) {
-            c.sync();
-            for (int li = spot_li + 1; li < k.n_layers; ++li) {
-                int L = k.layers[li];
-                int slot = L == 5 ? MG_SPR_AGENT0 + f.srot : (L == 4 ? (f.exit_open ? MG_SPR_EXIT_OPEN : MG_SPR_EXIT_CLOSED) : MG_SPR_COIN);
-                if (L != 3 && L != 4 && L != 5) continue;
-                if (L == 3 && f.coin_black) {  // an opaque layer above the spotlights: nothing is dimmed
-                    for (int w = c.lane; w < MG_SS_LIT_WORDS; w += c.nl) wm->lit[w] = 0xFFFFFFFFu;
-                    continue;
-                }
-                const MgSprite sp = a.hdr->sprite[slot];
-                const uint32_t* e = a.entries + sp.first;
-                int reps = L == 3 ? (int)f.n_coins : 1;
-                for (int q = 0; q < reps; ++q) {
-                    int ax = L == 5 ? f.sx - (a.hdr->agent_dim >> 1) : (L == 4 ? f.exit_x - (sp.w >> 1) : f.coins[q][0] - (sp.w >> 1));
-                    int ay = L == 5 ? f.sy - (a.hdr->agent_dim >> 1) : (L == 4 ? f.exit_y - (sp.h >> 1) : f.coins[q][1] - (sp.h >> 1));
-                    for (int i = c.lane; i < (int)sp.count; i += c.nl) {
-                        int x = ax + (int)(e[i] & 255u), y = ay + (int)((e[i] >> 8) & 255u);
-                        if ((unsigned)x < (unsigned)MG_W && (unsigned)y < (unsigned)MG_W)
-                            c.atomic_or(&wm->lit[(MG_W * x + y) >> 5], 1u << ((MG_W * x + y) & 31));
-                    }
-                }
+    if (wm->desc.lut_alpha != alpha) {
+        c.sync();
+        for (int v = c.lane; v < 256; v += c.nl) wm->dimlut[v] = (uint8_t)((uint32_t)v - (uint32_t)v * (uint32_t)alpha / 255u);
+        if (c.lane == 0) wm->desc.lut_alpha = alpha;
+        c.sync();
+    }
+    mg_ss_masked_copy_t<true>(c, out, wm, t, stream);
+}
+
+// non-default layer orders: pixels of the sprites painted ABOVE the spotlight layer are never dimmed (cold)
+template <class Ctx>
+MG_HD_NOINLINE void mg_ss_lit_over(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+                                   int spot_li) {
+    for (int li = spot_li + 1; li < k.n_layers; ++li) {
+        int L = k.layers[li];
+        int slot = L == 5 ? MG_SPR_AGENT0 + f.srot : (L == 4 ? (f.exit_open ? MG_SPR_EXIT_OPEN : MG_SPR_EXIT_CLOSED) : MG_SPR_COIN);
+        if (L != 3 && L != 4 && L != 5) continue;
+        if (L == 3 && f.coin_black) {  // an opaque layer above the spotlights: nothing is dimmed
+            for (int w = c.lane; w < MG_SS_LIT_WORDS; w += c.nl) wm->lit[w] = 0xFFFFFFFFu;
+            continue;
+        }
+        const MgSprite sp = a.hdr->sprite[slot];
+        const uint32_t* e = a.entries + sp.first;
+        int reps = L == 3 ? (int)f.n_coins : 1;
+        for (int q = 0; q < reps; ++q) {
+            int ax = L == 5 ? f.sx - (a.hdr->agent_dim >> 1) : (L == 4 ? f.exit_x - (sp.w >> 1) : f.coins[q][0] - (sp.w >> 1));
+            int ay = L == 5 ? f.sy - (a.hdr->agent_dim >> 1) : (L == 4 ? f.exit_y - (sp.h >> 1) : f.coins[q][1] - (sp.h >> 1));
+            for (int i = c.lane; i < (int)sp.count; i += c.nl) {
+                int x = ax + (int)(e[i] & 255u), y = ay + (int)((e[i] >> 8) & 255u);
+                if ((unsigned)x < (unsigned)MG_W && (unsigned)y < (unsigned)MG_W)
+                    c.atomic_or(&wm->lit[(MG_W * x + y) >> 5], 1u << ((MG_W * x + y) & 31));
             }
         }
     }
-    if (f.alpha != 0 && f.alpha != 255 && wm->desc.lut_alpha != (int)f.alpha) {
-        for (int v = c.lane; v < 256; v += c.nl) wm->dimlut[v] = (uint8_t)((uint32_t)v - (uint32_t)v * f.alpha / 255u);
-        c.sync();
-        if (c.lane == 0) wm->desc.lut_alpha = f.alpha;
-    }
-    c.sync();
-    // 3. frame = lit ? base : base dimmed by alpha (SDL: d + trunc((0 - d) * A / 255))
-    c.stamp(10);
-    mg_ss_masked_copy(c, out, wm, tables, f.alpha, stream);
-    c.stamp(11);
-    uint8_t* buf = out;
+}
+
+// black_background: every spotlight has a white 1-px outline (pygame_assets.py:112-113) (cold)
+template <class Ctx>
+MG_HD_NOINLINE void mg_ss_outlines(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+                                   int spot_li) {
     // 3b. black_background: white 1-px outlines on the spotlight surface (pygame_assets.py:112-113). An outline
     //     pixel survives unless a LATER spotlight's disc is drawn over it; it is blended like any non-key pixel:
     //     d + trunc((255 - d) * A / 255) over what lies underneath.
-    if (k.border && f.alpha != 0 && a.hdr->ring_off) {
+    {
         c.sync();  // the outline bytes land after the vector stores of the other lanes
         const uint16_t* start = (const uint16_t*)(a.base + a.hdr->ring_off);
         const int8_t* ring = (const int8_t*)(start + MG_MAX_DISC_R + 2);
@@ -732,4 +733,39 @@ MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDraw
         }
         c.sync();
     }
+}
+
+// One Searing-Spotlights frame -> `out` (the env's 21168 observation bytes in global memory)
+template <class Ctx>
+MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+                      MgSSWarpMem* wm, const MgSSCtaTables* tables, bool stream) {
+    int spot_li = 1, bar_li = 0;
+    for (int li = 0; li < k.n_layers; ++li) {
+        if (k.layers[li] == 1) spot_li = li;
+        if (k.layers[li] == 2) bar_li = li;
+    }
+    // the reference's default order: bg, coins, exit, agent, SPOT, bar
+    const bool simple = spot_li == k.n_layers - 2 && bar_li == k.n_layers - 1;
+    // 1. every layer but the spotlight layer (kept across frames, patched where it changed)
+    c.stamp(8);
+    mg_ss_update_base(c, wm, a, k, f, spot_li, simple);
+    c.stamp(9);
+    // 2. which pixels stay undimmed: the colour-keyed discs, and whatever is painted above the spotlight layer
+    if (f.alpha != 0) {
+        mg_ss_build_lit(c, wm, a, f, bar_li > spot_li ? tables->bar_lit : nullptr);
+        if (!simple) {
+            c.sync();
+            mg_ss_lit_over(c, wm, a, k, f, spot_li);
+        }
+    }
+    c.sync();
+    // 3. frame = lit ? base : base dimmed by alpha (SDL: d + trunc((0 - d) * A / 255))
+    c.stamp(10);
+    if (f.alpha == 255)
+        mg_ss_masked_copy_t<false>(c, out, wm, tables, stream);
+    else
+        mg_ss_masked_copy_cold(c, out, wm, tables, f.alpha, stream);
+    c.stamp(11);
+    // 3b. black_background: white 1-px outlines on the spotlight surface
+    if (k.border && f.alpha != 0 && a.hdr->ring_off) mg_ss_outlines(c, out, a, k, f, spot_li);
 }

@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     Frame* fr = reinterpret_cast<Frame*>(slot + kStateBytes);
     MgFrameJob* job = reinterpret_cast<MgFrameJob*>(slot + kStateBytes + 2 * sizeof(Frame));
     uint64_t* bar = reinterpret_cast<uint64_t*>(slot + kSlot - 8);
+    uint32_t* grab = reinterpret_cast<uint32_t*>(slot + kSlot - 16);  // next env index, broadcast to the team
 
     // ---- prologue: touches only the (constant) asset blob, so under programmatic dependent launch it
     // overlaps the tail of the previous kernel in the stream ---------------------------------------------
@@ -193,7 +194,23 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     if (tracing) tr1 = mg_now();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");  // previous kernel's state / obs writes are visible
-    if (!active) return;
+    // dynamic scheduling: after its first (static) env a team takes the next unclaimed env from a global counter,
+    // so a team held up by an auto-reset ends up with fewer envs. The last team to leave re-arms the counter.
+    uint32_t* const sched = q.io.sched;
+    const auto team_exit = [&]() {
+        if (sched && lane == 0) {
+            __threadfence();
+            if (atomicAdd(sched + 1, 1u) == (uint32_t)(gridDim.x * nteams) - 1u) {
+                sched[0] = 0u;
+                sched[1] = 0u;
+                __threadfence();
+            }
+        }
+    };
+    if (!active) {
+        team_exit();
+        return;
+    }
     if (tracing) tr2 = mg_now();
 
     const int T = q.n_steps;
@@ -220,13 +237,13 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
 
     bool pending = false;  // a bulk store is still reading `buf`; `prev` is the patch to undo afterwards
     Frame prev;
-    for (; env < q.n; env += total_teams) {
+    while (env < q.n) {
         uint64_t* s64 = reinterpret_cast<uint64_t*>(st);
 #pragma unroll
         for (int j = 0; j < kPerLane; ++j)
             if (lane + kTeam * j < kWords) s64[lane + kTeam * j] = pre[j];
         ctx.sync();
-        const int nxt = env + total_teams;
+        int nxt = env + total_teams;
         for (int t = 0; t < T; ++t) {
             const int a0 = (int)act0, a1 = (int)act1;
             uint64_t* trow = tracing ? q.io.trace + (size_t)env * MG_TRACE_COLS : nullptr;
@@ -238,12 +255,16 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
             }
             // prefetch what the next iteration needs (next step's actions; on the env's last step the next
             // env's record and first actions): the latency hides behind this step's work
+            uint32_t grabbed = 0;
             if (t + 1 < T) {
                 if (lane == 0) {
                     const int64_t* a = q.io.actions + (size_t)(t + 1) * q.act_stride + (size_t)env * q.act_dims;
                     act0 = a[0];
                     if (q.act_dims > 1) act1 = a[1];
                 }
+            } else if (sched) {
+                // claim the next env now; the index is first needed after the logic below (latency hidden)
+                if (lane == 0) grabbed = atomicAdd(sched, 1u);
             } else if (nxt < q.n) {
                 const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)nxt * kStateBytes);
 #pragma unroll
@@ -256,8 +277,27 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
                 }
             }
             P::logic(ctx, k, q, view, env, t, *st, a0, a1, *job, fr, scratch);
+            if (sched && t + 1 == T && P::kTeamWarps > 1 && lane == 0) *grab = grabbed;
             ctx.sync();
             if (trow && lane == 0) trow[4] = mg_now();
+            if (sched && t + 1 == T) {  // dynamic scheduling: the next env's record + first actions, prefetched now
+                if constexpr (P::kTeamWarps > 1)
+                    grabbed = *grab;
+                else
+                    grabbed = __shfl_sync(0xffffffffu, grabbed, 0);
+                nxt = total_teams + (int)grabbed;
+                if (nxt < q.n) {
+                    const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)nxt * kStateBytes);
+#pragma unroll
+                    for (int j = 0; j < kPerLane; ++j)
+                        if (lane + kTeam * j < kWords) pre[j] = g[lane + kTeam * j];
+                    if (lane == 0 && stepping) {
+                        const int64_t* a = q.io.actions + (size_t)nxt * q.act_dims;
+                        act0 = a[0];
+                        if (q.act_dims > 1) act1 = a[1];
+                    }
+                }
+            }
             const int nframes = job->nframes;
             for (int fi = 0; fi < nframes; ++fi) {
                 const Frame& f = fr[fi];  // lives in the team's shared slot until the next logic call
@@ -301,8 +341,10 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
         for (int j = 0; j < kPerLane; ++j)
             if (lane + kTeam * j < kWords) gw[lane + kTeam * j] = s64[lane + kTeam * j];
         ctx.sync();  // record slot is reused by the next env
+        env = nxt;
     }
     if (pending && lane == 0) mg_bulk_wait_read();  // shared memory must outlive the bulk read
+    team_exit();
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -497,6 +539,7 @@ static int launch_rollout(const typename P::K& k, const void* assets, void* stat
     q.io.ground_truth = r->ground_truth;
     q.io.trace = r->trace;
     q.io.vector_obs = r->vector_obs;
+    q.io.sched = r->sched;
     q.io.flags = r->flags | MG_FLAG_AUTORESET;  // a rollout without auto-reset would only idle finished envs
     q.mode = MG_MODE_STEP;
     q.n = n;
@@ -593,12 +636,17 @@ extern "C" int mg_ep_rollout(const mg_ep_params* p, const void* assets, void* st
     return launch_rollout<EPPolicy>(k, assets, state, r, n, 1, stream, 10);
 }
 
+// the endless variant is its own kernel instantiation: neither carries the other's code (I-cache footprint)
+#define MG_SS_DISPATCH(fn, ...)                                     \
+    if (k.endless) return fn<ESSPolicy>(__VA_ARGS__);               \
+    return fn<SSPolicy>(__VA_ARGS__);
+
 extern "C" int mg_ss_reset(const mg_ss_params* p, const void* assets, void* state, const uint64_t* rng4,
                            const mg_step_io* io, int n, void* stream) {
     if (mg_ss_check_params(p)) return MG_EINVAL;
     MgSSK k;
     mg_ss_derive(p, &k);
-    return launch_env<SSPolicy>(k, assets, state, rng4, io, 1, n, MG_MODE_RESET, 2, stream, 10);
+    MG_SS_DISPATCH(launch_env, k, assets, state, rng4, io, 1, n, MG_MODE_RESET, 2, stream, 10);
 }
 extern "C" int mg_ss_step(const mg_ss_params* p, const void* assets, void* state, const mg_step_io* io, int n,
                           void* stream) {
@@ -609,12 +657,12 @@ extern "C" int mg_ss_step_many(const mg_ss_params* p, const void* assets, void* 
     if (mg_ss_check_params(p)) return MG_EINVAL;
     MgSSK k;
     mg_ss_derive(p, &k);
-    return launch_env<SSPolicy>(k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, 2, stream, 10);
+    MG_SS_DISPATCH(launch_env, k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, 2, stream, 10);
 }
 extern "C" int mg_ss_rollout(const mg_ss_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
                              void* stream) {
     if (mg_ss_check_params(p)) return MG_EINVAL;
     MgSSK k;
     mg_ss_derive(p, &k);
-    return launch_rollout<SSPolicy>(k, assets, state, r, n, 2, stream, 10);
+    MG_SS_DISPATCH(launch_rollout, k, assets, state, r, n, 2, stream, 10);
 }

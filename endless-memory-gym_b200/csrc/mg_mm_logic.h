@@ -152,13 +152,17 @@ MG_HD_NOINLINE void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, 
             if (simx <= 0) valid &= ~0x184u;         // dx = -1: left, left_down, left_up
             if (simy >= size - 1) valid &= ~0x0A2u;  // dy = +1: down, right_down, left_down
             if (simy <= 0) valid &= ~0x148u;         // dy = -1: up, right_up, left_up
+#if defined(__CUDA_ARCH__)
+            const int nv = __popc(valid);
+            const int q = (int)__fns(valid, 0u, (int)mg_integers(r, 0, nv) + 1);  // the pick-th set bit
+#else
             int nv = 0;
             for (uint32_t m = valid; m; m &= m - 1u) nv++;
             int pick = (int)mg_integers(r, 0, nv), q = 0;
-            MG_NOUNROLL
             for (;; ++q)  // the pick-th set bit
                 if ((valid >> q) & 1u)
                     if (pick-- == 0) break;
+#endif
             s.commands[c] = (uint8_t)q;
             int dx, dy;
             mg_cmd_delta(q, dx, dy);

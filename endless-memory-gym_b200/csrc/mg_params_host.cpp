@@ -286,6 +286,12 @@ void mg_ss_derive(const mg_ss_params* p, MgSSK* k) {
     }
     k->clamp_off = (int)(30 * 0.25);
     k->exit_radius = 20 / 2 * p->exit_scale;
+    {   // Exit.is_agent_inside (pygame_assets.py:207-220): distance <= radius + agent.radius on integer coordinates
+        const double T = k->exit_radius + (double)k->radius;
+        int d2 = -1;
+        while (d2 + 1 <= 2 * 200 * 200 && sqrt((double)(d2 + 1)) <= T) ++d2;
+        k->exit_d2max = d2;
+    }
     k->spawn_base = sqrt(pow(84.0, 2) + pow(84.0, 2)) / 2;
     // painter's order: python list inserts of searing_spotlights.py:526-542 (an index past the end appends)
     int order[6], n = 0;

@@ -195,10 +195,12 @@ struct EPPolicy {
     }
 };
 
-struct SSPolicy {
+template <int TW, bool kEndless>
+struct SSPolicyT {
     static constexpr int kWarpExtra = (int)((sizeof(MgSSWarpMem) + 127) / 128 * 128);
     static constexpr int kCtaExtra = (int)((sizeof(MgSSCtaTables) + 127) / 128 * 128);
-    static constexpr int kTeamWarps = 2, kMaxThreads = 512;  // instruction-bound frames: two warps share one env
+    // instruction / latency-bound frames: TW warps share one env (more warps per base buffer hide more latency)
+    static constexpr int kTeamWarps = TW, kMaxThreads = TW <= 2 ? 512 : 256 * TW;
     static constexpr int kFrameBuf = 0;         // no staging buffer: the frame is a masked copy of the base buffer
     static constexpr bool kDirectStore = true;  // ... written straight to the observation with 128-bit stores
     static_assert(sizeof(MgSSStepTmp) <= sizeof(((MgSSWarpMem*)0)->step_tmp), "MgSSWarpMem::step_tmp too small");
@@ -259,7 +261,7 @@ struct SSPolicy {
         c.sync();
         if (tmp.action == 1) {
             if (c.lane == 0) wm->desc.valid = 0;
-            if (k.endless)
+            if constexpr (kEndless)
                 mg_ess_reset_env(c, k, s, fr[0], g, rt, gt);
             else
                 mg_ss_reset_env(c, k, s, fr[0], g, rt);
@@ -274,7 +276,7 @@ struct SSPolicy {
         mg_ss_step_b(c, k, trig(a), s, tmp, fr[0]);
         c.sync();
         MgESSCarry carry;  // lane 0's registers carry C1's results to C2
-        if (k.endless) {
+        if constexpr (kEndless) {
             if (c.lane == 0 && mg_ess_step_c1(k, s, tmp, carry)) {
                 tmp.action = 4;  // coin collected: the team respawns it on the (now invalid) base buffer
                 wm->desc.valid = 0;
@@ -284,8 +286,11 @@ struct SSPolicy {
         }
         if (c.lane == 0) {
             double reward;
-            bool done = k.endless ? mg_ess_step_c2(k, s, tmp, carry, reward, info_out, fr[0], gt)
-                                  : mg_ss_step_c(k, s, tmp, reward, info_out, fr[0]);
+            bool done;
+            if constexpr (kEndless)
+                done = mg_ess_step_c2(k, s, tmp, carry, reward, info_out, fr[0], gt);
+            else
+                done = mg_ss_step_c(k, s, tmp, reward, info_out, fr[0]);
             *reward_out = reward;
             *done_out = done ? 1 : 0;
             job.nframes = 1;
@@ -302,11 +307,11 @@ struct SSPolicy {
             // it is emitted here, out of order with respect to the generic frame loop
             const int at = q.io.final_obs ? 1 : 0;
             if (at) {
-                emit(c, q.io.final_obs + (size_t)env * MG_FRAME_BYTES, a, k, fr[0], sc, false);
+                emit_cold(c, q.io.final_obs + (size_t)env * MG_FRAME_BYTES, a, k, fr[0], sc);
                 c.sync();
             }
             if (c.lane == 0) wm->desc.valid = 0;
-            if (k.endless)
+            if constexpr (kEndless)
                 mg_ess_reset_env(c, k, s, fr[at], g, rt, gt);
             else
                 mg_ss_reset_env(c, k, s, fr[at], g, rt);
@@ -320,9 +325,7 @@ struct SSPolicy {
         }
     }
 
-    template <class Ctx>
-    static MG_HD void emit(Ctx& c, uint8_t* dst, const MgAssetView& a, const K& k, const Frame& f, const MgScratch& sc,
-                           bool stream) {
+    static MG_HD MgSSDrawK draw_k(const K& k, const Frame& f) {
         MgSSDrawK d;
         d.n_layers = k.n_layers;
         for (int i = 0; i < 6; ++i) d.layers[i] = f.coin_above ? k.layers_alt[i] : k.layers[i];
@@ -331,8 +334,21 @@ struct SSPolicy {
         d.show_last_action = k.p.show_last_action;
         d.has_coin_layer = 1;
         d.border = k.p.black_background;
-        mg_ss_emit(c, dst, a, d, f, reinterpret_cast<MgSSWarpMem*>(sc.warp), reinterpret_cast<const MgSSCtaTables*>(sc.cta),
-                   stream);
+        return d;
+    }
+    // the hot copy: inlined once into the kernel's frame loop
+    template <class Ctx>
+    static MG_HD void emit(Ctx& c, uint8_t* dst, const MgAssetView& a, const K& k, const Frame& f, const MgScratch& sc,
+                           bool stream) {
+        mg_ss_emit(c, dst, a, draw_k(k, f), f, reinterpret_cast<MgSSWarpMem*>(sc.warp),
+                   reinterpret_cast<const MgSSCtaTables*>(sc.cta), stream);
+    }
+    // terminal frames (one per episode): an out-of-line copy keeps the hot loop's code small
+    template <class Ctx>
+    static MG_HD_NOINLINE void emit_cold(Ctx& c, uint8_t* dst, const MgAssetView& a, const K& k, const Frame& f,
+                                         const MgScratch& sc) {
+        mg_ss_emit(c, dst, a, draw_k(k, f), f, reinterpret_cast<MgSSWarpMem*>(sc.warp),
+                   reinterpret_cast<const MgSSCtaTables*>(sc.cta), false);
     }
     // unused with kDirectStore
     template <class Ctx>
@@ -340,3 +356,5 @@ struct SSPolicy {
     template <class Ctx>
     static MG_HD void restore(Ctx&, uint8_t*, const MgAssetView&, const K&, const Frame&, const MgScratch&) {}
 };
+typedef SSPolicyT<2, false> SSPolicy;
+typedef SSPolicyT<2, true> ESSPolicy;

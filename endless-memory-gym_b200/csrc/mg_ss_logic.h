@@ -34,6 +34,7 @@ struct MgSSK {
     int32_t layers_alt[6];      // Endless: the order while the coin is fresh (coin layer above the spotlights)
     int32_t endless;            // Endless-SearingSpotlights-v0
     int32_t clamp_off;          // int(30 * SCALE)
+    int32_t exit_d2max;         // largest integer d2 with sqrt(d2) <= exit_radius + agent radius (host-computed)
     double exit_radius;         // 20 / 2 * exit_scale
     double spawn_base;          // sqrt(84^2 + 84^2) / 2
 };
@@ -53,7 +54,7 @@ MG_HD int mg_popc64(uint64_t v) {
 
 // ---- spotlights -------------------------------------------------------------------------------------
 // Spotlight.__init__: radius, speed, then the three angle draws
-MG_HD void mg_ss_new_spot(const MgSSK& k, MgRng& r, MgSSSpot& sp) {
+MG_HD_NOINLINE void mg_ss_new_spot(const MgSSK& k, MgRng& r, MgSSSpot& sp) {
     sp.radius = (uint8_t)mg_integers(r, k.spot_rlo, k.spot_rhi);
     sp.speed = mg_uniform(r, k.p.spot_min_speed, k.p.spot_max_speed);
     sp.t = 0.0;
@@ -70,6 +71,16 @@ MG_HD void mg_ss_new_spot(const MgSSK& k, MgRng& r, MgSSSpot& sp) {
 MG_HD void mg_ss_on_circle(const double* trig, int angle, double spawn_radius, double& x, double& y) {
     x = 42.0 + trig[2 * angle] * spawn_radius;
     y = 42.0 + trig[2 * angle + 1] * spawn_radius;
+}
+
+// sqrt(v) <= R for an integer R >= 0, bit-exact without the square root in all but a sliver of cases: sqrt is
+// correctly rounded and monotonic, so v <= R^2 implies sqrt(v) <= sqrt(R^2) = R, and v > R^2 (1 + 2^-50) implies
+// sqrt(v) > R (1 + 2^-51 - ...) which rounds above R; only in between does the rounded root decide.
+MG_HD bool mg_within(double v, int R) {
+    const double r2 = (double)(R * R);
+    if (v <= r2) return true;
+    if (v > r2 * (1.0 + 8.8817841970012523e-16)) return false;
+    return sqrt(v) <= (double)R;
 }
 
 // Spotlight.draw without the drawing + is_agent_inside: advances t, returns the circle centre and the hit flag
@@ -90,7 +101,7 @@ MG_HD bool mg_ss_advance_spot(const MgSSK& k, const double* trig, MgSSSpot& sp, 
         sp.done = 1;
     }
     double dx = (double)ax - px, dy = (double)ay - py;
-    return sqrt(dx * dx + dy * dy) <= (double)((int)sp.radius + k.radius);
+    return mg_within(dx * dx + dy * dy, (int)sp.radius + k.radius);
 }
 
 MG_HD void mg_ss_clamp_spawn(const MgSSK& k, int& x, int& y) {
@@ -138,7 +149,7 @@ struct MgSSResetTmp {
 };
 
 template <class Ctx>
-MG_HD void mg_ss_block_coop(Ctx& c, MgSSSampler& g, int x, int y, int r) {
+MG_HD_NOINLINE void mg_ss_block_coop(Ctx& c, MgSSSampler& g, int x, int y, int r) {
     int y0 = y - r + 1 < 0 ? 0 : y - r + 1, y1 = y + r - 1 > MG_W - 1 ? MG_W - 1 : y + r - 1;
     for (int yy = y0 + c.lane; yy <= y1; yy += c.nl) {
         int dy = yy - y, rem = r * r - dy * dy - 1;  // need dx^2 <= rem
@@ -185,7 +196,7 @@ MG_HD int mg_ss_kth_free(uint64_t lo, uint64_t hi, int k) {
 }
 
 template <class Ctx>
-MG_HD void mg_ss_sample_coop(Ctx& c, MgSSSampler& g, MgSSState& s, MgSSResetTmp& rt, int block_radius) {
+MG_HD_NOINLINE void mg_ss_sample_coop(Ctx& c, MgSSSampler& g, MgSSState& s, MgSSResetTmp& rt, int block_radius) {
     if (c.lane < 28) {  // 28 lanes x 3 rows
         int n = 0;
         for (int q = 0; q < 3; ++q) n += MG_W - mg_popc64(g.lo[3 * c.lane + q]) - mg_popc64(g.hi[3 * c.lane + q]);
@@ -227,7 +238,7 @@ MG_HD void mg_ss_sample_coop(Ctx& c, MgSSSampler& g, MgSSState& s, MgSSResetTmp&
 // num_coins; per coin cell + 2 offsets; exit cell + 2 offsets (searing_spotlights.py:354-414).
 // Called by every lane of the warp; `g` / `rt` are per-warp scratch.
 template <class Ctx>
-MG_HD void mg_ss_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, MgSSSampler& g, MgSSResetTmp& rt) {
+MG_HD_NOINLINE void mg_ss_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, MgSSSampler& g, MgSSResetTmp& rt) {
     for (int y = c.lane; y < MG_W; y += c.nl) g.lo[y] = g.hi[y] = 0;
     if (c.lane == 0) {
         s.t = 0;
@@ -410,8 +421,9 @@ MG_HD_NOINLINE bool mg_ss_step_c(const MgSSK& k, MgSSState& s, const MgSSStepTmp
     if (s.num_coins > 0) {
         r = 0.0;
         for (int i = 0; i < (int)s.n_coins; ++i) {
-            double dx = (double)cx - (double)s.coins[i][0], dy = (double)cy - (double)s.coins[i][1];
-            if (sqrt(dx * dx + dy * dy) <= (double)(k.coin_radius + k.radius)) {
+            // Vector2.distance_to on integer coordinates: sqrt(d2) <= R  <=>  d2 <= R^2 exactly
+            const int dx = cx - (int)s.coins[i][0], dy = cy - (int)s.coins[i][1], R = k.coin_radius + k.radius;
+            if (dx * dx + dy * dy <= R * R) {
                 for (int j = i; j + 1 < (int)s.n_coins; ++j) {
                     s.coins[j][0] = s.coins[j + 1][0];
                     s.coins[j][1] = s.coins[j + 1][1];
@@ -431,8 +443,8 @@ MG_HD_NOINLINE bool mg_ss_step_c(const MgSSK& k, MgSSState& s, const MgSSStepTmp
         r = 0.0;
         if (coins_done) {
             s.exit_open = 1;
-            double dx = (double)cx - (double)s.exit_x, dy = (double)cy - (double)s.exit_y;
-            if (sqrt(dx * dx + dy * dy) <= k.exit_radius + (double)k.radius) {
+            const int dx = cx - (int)s.exit_x, dy = cy - (int)s.exit_y;
+            if (dx * dx + dy * dy <= k.exit_d2max) {  // sqrt(d2) <= exit_radius + radius, threshold found on the host
                 exit_done = true;
                 r = k.p.reward_exit;
             }
@@ -501,7 +513,7 @@ MG_HD void mg_ess_ground_truth(const MgSSK& k, const MgSSState& s, double* gt) {
 
 // _spawn_coin (:256-269): fresh sampler, only the OLD coin's surroundings blocked, sample(28) + two offsets
 template <class Ctx>
-MG_HD void mg_ess_spawn_coin(Ctx& c, const MgSSK& k, MgSSState& s, MgSSSampler& g, MgSSResetTmp& rt, bool have_old) {
+MG_HD_NOINLINE void mg_ess_spawn_coin(Ctx& c, const MgSSK& k, MgSSState& s, MgSSSampler& g, MgSSResetTmp& rt, bool have_old) {
     for (int y = c.lane; y < MG_W; y += c.nl) g.lo[y] = g.hi[y] = 0;
     if (c.lane == 0) rt.ok = 1;
     c.sync();
@@ -524,7 +536,7 @@ MG_HD void mg_ess_spawn_coin(Ctx& c, const MgSSK& k, MgSSState& s, MgSSSampler& 
 // reset(): RNG draw order — rotation; agent cell + 2 offsets; per initial spotlight radius, speed, 3 angles;
 // coin cell + 2 offsets (:294-407)
 template <class Ctx>
-MG_HD void mg_ess_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, MgSSSampler& g, MgSSResetTmp& rt,
+MG_HD_NOINLINE void mg_ess_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, MgSSSampler& g, MgSSResetTmp& rt,
                             double* gt) {
     for (int y = c.lane; y < MG_W; y += c.nl) g.lo[y] = g.hi[y] = 0;
     if (c.lane == 0) {
@@ -624,8 +636,8 @@ MG_HD_NOINLINE bool mg_ess_step_c1(const MgSSK& k, MgSSState& s, const MgSSStepT
     bool collected = false;
     if (k.p.coin_enabled) {
         r = 0.0;
-        double dx = (double)cx - (double)s.coins[0][0], dy = (double)cyy - (double)s.coins[0][1];
-        if (sqrt(dx * dx + dy * dy) <= (double)(k.coin_radius + k.radius)) {
+        const int dx = cx - (int)s.coins[0][0], dy = cyy - (int)s.coins[0][1], R = k.coin_radius + k.radius;
+        if (dx * dx + dy * dy <= R * R) {
             r += k.p.reward_coin;
             s.coins_collected++;
             s.coin_t = 0;

@@ -104,6 +104,7 @@ class StepIO(C.Structure):
         ("actions", C.c_void_p), ("obs", C.c_void_p), ("final_obs", C.c_void_p), ("reward", C.c_void_p),
         ("done", C.c_void_p), ("info", C.c_void_p), ("ground_truth", C.c_void_p), ("reset_mask", C.c_void_p),
         ("flags", C.c_uint32), ("warps_per_cta", C.c_uint32), ("vector_obs", C.c_void_p), ("trace", C.c_void_p),
+        ("sched", C.c_void_p),
     ]
 
 
@@ -113,6 +114,7 @@ class RolloutIO(C.Structure):
         ("done", C.c_void_p), ("info", C.c_void_p), ("ground_truth", C.c_void_p),
         ("n_steps", C.c_int32), ("ring", C.c_int32), ("info_per_step", C.c_int32), ("flags", C.c_uint32),
         ("warps_per_cta", C.c_uint32), ("pad0", C.c_uint32), ("trace", C.c_void_p), ("vector_obs", C.c_void_p),
+        ("sched", C.c_void_p),
     ]
 
 

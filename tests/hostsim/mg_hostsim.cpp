@@ -133,6 +133,7 @@ extern "C" int mgsim_ss(const mg_ss_params* p, const void* assets, void* state, 
     if (mg_ss_check_params(p)) return MG_EINVAL;
     MgSSK k;
     mg_ss_derive(p, &k);
+    if (k.endless) return run<ESSPolicy>(k, assets, state, rng4, io, n, mode, 2);
     return run<SSPolicy>(k, assets, state, rng4, io, n, mode, 2);
 }
 extern "C" int mgsim_ep(const mg_ep_params* p, const void* assets, void* state, const uint64_t* rng4,
@@ -164,5 +165,6 @@ extern "C" int mgsim_ss_rollout(const mg_ss_params* p, const void* assets, void*
     if (mg_ss_check_params(p)) return MG_EINVAL;
     MgSSK k;
     mg_ss_derive(p, &k);
+    if (k.endless) return run_rollout<ESSPolicy>(k, assets, state, r, n, 2);
     return run_rollout<SSPolicy>(k, assets, state, r, n, 2);
 }
