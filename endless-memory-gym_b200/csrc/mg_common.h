@@ -11,10 +11,12 @@
 // one out-of-line copy: keeps the (rarely taken, single-lane) reset / RNG paths small in the I-cache
 #define MG_HD_NOINLINE __host__ __device__ __noinline__
 #define MG_NOUNROLL _Pragma("unroll 1")
+#define MG_UNROLL _Pragma("unroll")
 #else
 #define MG_HD inline
 #define MG_HD_NOINLINE inline
 #define MG_NOUNROLL
+#define MG_UNROLL
 #endif
 
 #define MG_W 84                       // screen: int(336 * 0.25), mortar_mayhem.py:13,73

@@ -93,29 +93,33 @@ MG_HD bool mg_ep_prev(const MgEPState& s, int x, int y, int& px, int& py) {
     return false;
 }
 
-// EndlessMysteryPath.add_path_segment: draws the start row (first segment only), the end row, then the A* path
-MG_HD_NOINLINE bool mg_ep_add_segment(MgRng& r, MgEPState& s) {
-    if (s.n_segments >= MG_EP_MAXSEG) return false;
+// EndlessMysteryPath.add_path_segment: draws the start row (first segment only), the end row, then the A* path.
+// Called by every lane of the warp (mg_mp_generate_coop); the stream in the record advances even when it fails.
+template <class Ctx>
+MG_HD_NOINLINE bool mg_ep_add_segment_coop(Ctx& c, MgEPState& s, MgGenMem& m, const MgGenCta& tab) {
+    const int ns = s.n_segments;
+    if (ns >= MG_EP_MAXSEG) return false;
     const int g7 = MG_MP_CELLS;
-    int sy = s.n_segments == 0 ? (int)mg_integers(r, 0, g7) : mg_ep_end_y(s.seg[s.n_segments - 1]);
-    int ey = (int)mg_integers(r, 0, g7);
-    uint8_t order[MG_MP_NODES];
-    int n = 0;
-    uint64_t mask = mg_mp_generate(r, 0, sy, g7 - 1, ey, order, &n);  // order = [end, ..., start]
-    if (!mask) return false;
-    MgEPSegment& g = s.seg[s.n_segments];
-    g.path = mask | ((uint64_t)sy << 56) | ((uint64_t)ey << 60);
-    g.reward_visited = 0;
-    g.stamina_visited = 0;
-    g.next[0] = g.next[1] = 0;  // the end node's next is the transition tile: east = 0
-    for (int q = n - 1; q >= 1; --q) {  // order[q] -> order[q - 1]
-        int a = order[q], b = order[q - 1];
-        int ax = a / g7, ay = a % g7, bx = b / g7, by = b % g7;
-        uint64_t code = bx == ax + 1 ? 0u : (by == ay - 1 ? 1u : (by == ay + 1 ? 2u : 3u));
-        g.next[a >> 5] |= code << (2 * (a & 31));
+    MgRngR r = mg_rr_load(s.rng);
+    const int sy = ns == 0 ? mg_rr_integers(r, 0, g7) : mg_ep_end_y(s.seg[ns - 1]);
+    const int ey = mg_rr_integers(r, 0, g7);
+    uint64_t nx[2] = {0, 0};
+    const uint64_t mask = mg_mp_generate_coop(c, r, 0, sy, g7 - 1, ey, tab, nx);
+    const uint64_t n0 = nx[0], n1 = nx[1];  // the end node's next is the transition tile: east = 0
+    if (c.lane == 0) {
+        mg_rr_store(r, s.rng);
+        if (mask) {
+            MgEPSegment& g = s.seg[ns];
+            g.path = mask | ((uint64_t)sy << 56) | ((uint64_t)ey << 60);
+            g.reward_visited = 0;
+            g.stamina_visited = 0;
+            g.next[0] = n0;
+            g.next[1] = n1;
+            s.n_segments = ns + 1;
+        }
     }
-    s.n_segments++;
-    return true;
+    c.sync();
+    return mask != 0;
 }
 
 MG_HD void mg_ep_update_direction(MgEPState& s) {
@@ -178,43 +182,51 @@ MG_HD int mg_ep_bar_height(int stamina, int max_visible, bool at_reset) {
     return (int)((double)MG_W * (1.0 - ((double)v / (double)max_visible)));
 }
 
-MG_HD_NOINLINE void mg_ep_reset_env(const MgEPK& k, MgEPState& s, MgEPFrame& f, double* gt) {
-    MgRng r = s.rng;
-    s.t = 0;
-    s.ep_len = 0;
-    s.ep_reward = 0.0;
-    s.n_segments = 0;
+template <class Ctx>
+MG_HD_NOINLINE void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, double* gt, MgGenMem& m,
+                                     const MgGenCta& tab) {
+    c.stamp(12);
+    if (c.lane == 0) {
+        s.t = 0;
+        s.ep_len = 0;
+        s.ep_reward = 0.0;
+        s.n_segments = 0;
+    }
+    c.sync();
     bool ok = true;
-    for (int q = 0; q < 3 && ok; ++q) ok = mg_ep_add_segment(r, s);
-    s.rng = r;
-    const int sy = ok ? mg_ep_start_y(s.seg[0]) : 0;
-    if (ok) s.seg[0].reward_visited |= 1ull << mg_mp_id(0, sy);  // the first node yields no reward (:529)
-    s.camera_x = k.camera_offset;
-    s.bg_scroll = 0;
-    s.rot = 6;  // CharacterController(..., 270): sprite 270 // 45
-    s.cx = 0 * MG_MP_TILE + k.radius;
-    s.cy = sy * MG_MP_TILE + k.radius;
-    s.cur_x = 0;
-    s.cur_y = (uint8_t)sy;
-    s.dir = 0;
-    if (ok) mg_ep_update_direction(s);
-    s.off_path = 0;
-    s.num_fails = 0;
-    s.n_fall = 0;
-    s.stamina = k.p.stamina_level;
-    s.max_x = 0;
-    s.tiles_visited = 0;
-    s.cross_on = 0;
-    s.cross_x = s.cross_y = 0;
-    s.live = ok ? 1 : 0;  // "No valid path found": the reference raises; here the env stays finished
-    mg_ep_frame(k, s, mg_ep_bar_height(s.stamina, k.p.stamina_level, true), f);
-    if (gt) mg_ep_ground_truth(s, gt);
+    for (int q = 0; q < 3 && ok; ++q) ok = mg_ep_add_segment_coop(c, s, m, tab);
+    c.stamp(13);
+    if (c.lane == 0) {
+        const int sy = ok ? mg_ep_start_y(s.seg[0]) : 0;
+        if (ok) s.seg[0].reward_visited |= 1ull << mg_mp_id(0, sy);  // the first node yields no reward (:529)
+        s.camera_x = k.camera_offset;
+        s.bg_scroll = 0;
+        s.rot = 6;  // CharacterController(..., 270): sprite 270 // 45
+        s.cx = 0 * MG_MP_TILE + k.radius;
+        s.cy = sy * MG_MP_TILE + k.radius;
+        s.cur_x = 0;
+        s.cur_y = (uint8_t)sy;
+        s.dir = 0;
+        if (ok) mg_ep_update_direction(s);
+        s.off_path = 0;
+        s.num_fails = 0;
+        s.n_fall = 0;
+        s.stamina = k.p.stamina_level;
+        s.max_x = 0;
+        s.tiles_visited = 0;
+        s.cross_on = 0;
+        s.cross_x = s.cross_y = 0;
+        s.live = ok ? 1 : 0;  // "No valid path found": the reference raises; here the env stays finished
+        mg_ep_frame(k, s, mg_ep_bar_height(s.stamina, k.p.stamina_level, true), f);
+        if (gt) mg_ep_ground_truth(s, gt);
+    }
+    c.sync();
+    c.stamp(14);
 }
 
-MG_HD_NOINLINE bool mg_ep_step_env(const MgEPK& k, MgEPState& s, int action, double& reward_out, double* info,
-                                   MgEPFrame& f, double* gt) {
-    double reward = 0.0;
-    bool done = false;
+// step(), first half (one lane): the move. Returns true when the path needs another segment before the second
+// half runs (the warp then generates it cooperatively).
+MG_HD_NOINLINE bool mg_ep_step_pre(const MgEPK& k, MgEPState& s, int action) {
     const int start_y = mg_ep_start_y(s.seg[0]);
     if (!s.off_path) {
         // Discrete(4) -> [0,0], [2,0], [0,1], [0,2] (:283-291); CharacterController.step, no boundary
@@ -239,14 +251,18 @@ MG_HD_NOINLINE bool mg_ep_step_env(const MgEPK& k, MgEPState& s, int action, dou
         s.camera_x = k.camera_offset;
         s.bg_scroll = 0;
     }
+    const int sg = mg_ep_floordiv12(s.cx) / MG_EP_SEG;
+    return sg > s.n_segments - 2;
+}
+
+// step(), second half (one lane). `capped`: a segment was needed but the record is full
+MG_HD_NOINLINE bool mg_ep_step_post(const MgEPK& k, MgEPState& s, bool capped, double& reward_out, double* info,
+                                    MgEPFrame& f, double* gt) {
+    double reward = 0.0;
+    bool done = false;
+    const int start_y = mg_ep_start_y(s.seg[0]);
     const int px = mg_ep_floordiv12(s.cx), py = mg_ep_floordiv12(s.cy);
     const int sg = px / MG_EP_SEG;
-    bool capped = false;
-    if (sg > s.n_segments - 2) {
-        MgRng r = s.rng;
-        if (!mg_ep_add_segment(r, s)) capped = true;
-        s.rng = r;
-    }
     const bool on_path = mg_ep_on_path(s, px, py) && sg < s.n_segments;
     if (on_path) {
         s.cur_x = px;

@@ -97,6 +97,7 @@ __device__ __forceinline__ uint64_t mg_now() {
 
 // execution context of mg_frame.h on the device: the 32 lanes of the warp that owns the env
 struct MgWarpCtx {
+    static constexpr int kLanes = 32;  // lanes of a single-warp team (cooperative code sized at compile time)
     int lane, nl;
     uint32_t bar, phase;
     uint64_t policy;  // L2 evict-first cache policy
@@ -122,6 +123,10 @@ struct MgWarpCtx {
             *p = v;
     }
     __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
+    // warp reductions (single-warp teams only): every lane gets the result
+    __device__ __forceinline__ uint32_t reduce_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
+    __device__ __forceinline__ uint32_t reduce_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
+    __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
     __device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
     // whole-frame template -> this warp's frame buffer, by TMA
     __device__ __forceinline__ void copy_frame(uint8_t* dst, const uint8_t* src) {
@@ -396,7 +401,7 @@ static int plan_launch(int n, int wpc_req, int default_wpc, bool balance, MgLaun
     const int per_warp = P::kFrameBuf + kSlot + P::kWarpExtra;
     int wmax = 10;
     while (wmax > 1 && wmax * 32 * P::kTeamWarps > P::kMaxThreads) wmax--;
-    while (wmax > 1 && wmax * per_warp + P::kCtaExtra + 16 * 1024 > smem_max) wmax--;  // leave room to stage the assets
+    while (wmax > 1 && wmax * per_warp + P::kCtaExtra + P::kStageReserve > smem_max) wmax--;  // leave room to stage the assets
     int wpc = wpc_req ? wpc_req : default_wpc;
     if (wpc > wmax) wpc = wmax;
     if (!wpc_req && balance && n > sms * wmax) {

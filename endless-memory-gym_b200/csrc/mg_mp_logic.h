@@ -8,6 +8,7 @@
 // The order and number of RNG draws is part of the contract.
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #include "../../include/memgym_b200.h"
 #include "mg_common.h"
@@ -28,121 +29,239 @@ struct MgMPK {
 
 MG_HD int mg_mp_id(int i, int j) { return i * MG_MP_CELLS + j; }
 
-// 4-neighbours in Node.add_neighbors order (+x, -x, +y, -y), pygame_assets.py:465-472
-MG_HD int mg_mp_neighbours(int i, int j, int* out) {
-    int c = 0;
-    if (i < MG_MP_CELLS - 1) out[c++] = mg_mp_id(i + 1, j);
-    if (i > 0) out[c++] = mg_mp_id(i - 1, j);
-    if (j < MG_MP_CELLS - 1) out[c++] = mg_mp_id(i, j + 1);
-    if (j > 0) out[c++] = mg_mp_id(i, j - 1);
-    return c;
+// ---- warp-cooperative path generator ------------------------------------------------------------------
+// MysteryPath.__init__ (pygame_assets.py:606-736) for the 32 lanes of the warp that owns the env. Every lane
+// carries the same register copy of the PCG64 stream and makes the same draws (no broadcast needed). The A*
+// bookkeeping lives in REGISTERS, two cells per lane (cell = lane + 32 j): a packed key (insertion order | g cost |
+// cell), f, the predecessor. The two list scans of an A* iteration — "head of the open list" and "first open node
+// better than the head" — are warp min-reductions over those keys; the set of open / closed / wall cells is a
+// 49-bit mask every lane holds.
+//
+// The reference never updates g_cost when it finds a cheaper way to an open node (:712), so g and f = g + h of a
+// node are fixed at insertion; the Euclidean h comes from a per-CTA table of correctly rounded square roots.
+// A single-lane context (the CPU test harness) runs the same code with all 49 cells on its one lane.
+#define MG_MP_SQRT_N 80  // d2 <= 6^2 + 6^2 = 72
+struct MgGenCta {
+    double sqrt_d2[MG_MP_SQRT_N];
+};
+struct MgGenMem {      // per-warp hand-over words of the cooperative control flow (mg_env_logic_coop)
+    int32_t action;    // what lane 0 decided for this call
+    int32_t flag;      // env-type specific: "needs a segment", "done"
+};
+MG_HD void mg_gen_cta_init(MgGenCta* t, int tid, int nthreads) {
+    for (int i = tid; i < MG_MP_SQRT_N; i += nthreads) t->sqrt_d2[i] = sqrt((double)i);
 }
 
-// MysteryPath.__init__: returns the path as a 49-bit mask, or 0 if A* ran out of open nodes
-// (the reference raises Exception("No valid path found"), pygame_assets.py:724)
-// `order` (optional, MG_MP_NODES entries) receives the path's cell ids from the end node back to the start node.
-MG_HD_NOINLINE uint64_t mg_mp_generate(MgRng& r, int sx, int sy, int ex, int ey, uint8_t* order = nullptr,
-                                       int* n_order = nullptr) {
-    const int n = MG_MP_CELLS;
+MG_HD int mg_popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+// the n-th (0-based) set bit of a 32-bit mask
+MG_HD int mg_nth_set_bit(uint32_t mask, int n) {
+#if defined(__CUDA_ARCH__)
+    return (int)__fns(mask, 0u, n + 1);
+#else
+    for (int b = 0; b < 32; ++b)
+        if ((mask >> b) & 1u) {
+            if (n == 0) return b;
+            --n;
+        }
+    return 32;
+#endif
+}
+
+// outer-ring cells in the reference's scan order (ascending i * 7 + j): q = 0..23
+MG_HD int mg_mp_ring_id(int q) {
+    if (q < MG_MP_CELLS) return q;
+    if (q < 17) return MG_MP_CELLS * (1 + ((q - 7) >> 1)) + (((q - 7) & 1) ? MG_MP_CELLS - 1 : 0);
+    return 42 + (q - 17);
+}
+// the cell's 8-neighbourhood as a 49-bit mask
+MG_HD uint64_t mg_mp_nbr8(int i, int j) {
+    const uint64_t cols = (uint64_t)(((7u << j) >> 1) & 0x7Fu);  // columns j-1 .. j+1 inside the grid
+    uint64_t m = 0;
+    for (int di = -1; di <= 1; ++di)
+        if ((unsigned)(i + di) < (unsigned)MG_MP_CELLS) m |= cols << (MG_MP_CELLS * (i + di));
+    return m & ~(1ull << mg_mp_id(i, j));
+}
+// the cell's 4-neighbourhood as a 49-bit mask
+MG_HD uint64_t mg_mp_nbr4(int i, int j) {
+    uint64_t m = 0;
+    if (i < MG_MP_CELLS - 1) m |= 1ull << mg_mp_id(i + 1, j);
+    if (i > 0) m |= 1ull << mg_mp_id(i - 1, j);
+    if (j < MG_MP_CELLS - 1) m |= 1ull << mg_mp_id(i, j + 1);
+    if (j > 0) m |= 1ull << mg_mp_id(i, j - 1);
+    return m;
+}
+
+MG_HD uint32_t mg_f64_lo(double v) {
+    uint64_t b;
+    memcpy(&b, &v, 8);
+    return (uint32_t)b;
+}
+MG_HD uint32_t mg_f64_hi(double v) {
+    uint64_t b;
+    memcpy(&b, &v, 8);
+    return (uint32_t)(b >> 32);
+}
+MG_HD double mg_f64_make(uint32_t lo, uint32_t hi) {
+    const uint64_t b = ((uint64_t)hi << 32) | lo;
+    double v;
+    memcpy(&v, &b, 8);
+    return v;
+}
+
+#define MG_GEN_NOKEY 0xFFFFFFFFu
+#define MG_GEN_NOPREV 0xFF
+
+// Returns the path as a 49-bit mask (0 if A* ran out of open nodes: the reference raises "No valid path found",
+// pygame_assets.py:724). next2 (optional, two words): 2 bits per path cell = where its successor on the path lies
+// (0 east = x+1, 1 north = y-1, 2 south = y+1, 3 west = x-1). Called by every lane with identical arguments; the
+// results are uniform.
+template <class Ctx>
+MG_HD uint64_t mg_mp_generate_coop(Ctx& c, MgRngR& r, int sx, int sy, int ex, int ey, const MgGenCta& tab,
+                                   uint64_t* next2 = nullptr) {
+    constexpr int n = MG_MP_CELLS, NL = Ctx::kLanes, PER = (MG_MP_NODES + NL - 1) / NL;
+    // interior walls (:640-647): 16 draws in scan order
     uint64_t wall = 0;
-    for (int i = 0; i < n; ++i)
-        for (int j = 0; j < n; ++j)
-            if (i > 0 && i < n - 2 && j > 0 && j < n - 2)
-                if (mg_integers(r, 0, 100) < 33) wall |= 1ull << mg_mp_id(i, j);
+    MG_NOUNROLL
+    for (int id = mg_mp_id(1, 1); id <= mg_mp_id(n - 3, n - 3); ++id) {
+        const int j = id % n;
+        if (j < 1 || j > n - 3) continue;
+        if (mg_rr_integers(r, 0, 100) < 33) wall |= 1ull << id;
+    }
     const int start = mg_mp_id(sx, sy), end = mg_mp_id(ex, ey);
-    int nb[4];
-    uint64_t near_ends = 0;
-    int c = mg_mp_neighbours(sx, sy, nb);
-    for (int q = 0; q < c; ++q) near_ends |= 1ull << nb[q];
-    c = mg_mp_neighbours(ex, ey, nb);
-    for (int q = 0; q < c; ++q) near_ends |= 1ull << nb[q];
-    // outer-ring wall candidates (:650-669)
-    uint8_t ring[24];
-    int nring = 0;
-    for (int i = 0; i < n; ++i)
-        for (int j = 0; j < n; ++j) {
-            if (!(i == 0 || i == n - 1 || j == 0 || j == n - 1)) continue;
-            int id = mg_mp_id(i, j);
-            if (id == start || id == end || ((near_ends >> id) & 1)) continue;
-            bool blocked = false;
-            for (int di = -1; di <= 1 && !blocked; ++di)
-                for (int dj = -1; dj <= 1; ++dj) {
-                    if (!di && !dj) continue;
-                    int a = i + di, b = j + dj;
-                    if (a < 0 || a >= n || b < 0 || b >= n) continue;
-                    if ((wall >> mg_mp_id(a, b)) & 1) {
-                        blocked = true;
-                        break;
-                    }
-                }
-            if (!blocked) ring[nring++] = (uint8_t)id;
-        }
-    int picks = mg_integers(r, 0, 2) ? 8 : 4;  // choice([4, 8])
-    for (int q = 0; q < picks; ++q) {
-        if (nring > 0) {
-            int w = (int)mg_integers(r, 0, nring);  // choice(outer_nodes); one candidate draws nothing
-            wall |= 1ull << ring[w];
-            for (int t = w; t + 1 < nring; ++t) ring[t] = ring[t + 1];
-            nring--;
-        }
+    // outer-ring wall candidates (:650-669): not the ends, not next to them, no wall in the 8-neighbourhood
+    const uint64_t keep_free = (1ull << start) | (1ull << end) | mg_mp_nbr4(sx, sy) | mg_mp_nbr4(ex, ey);
+    uint32_t elig = 0;
+    for (int q = c.lane; q < 24; q += NL) {
+        const int id = mg_mp_ring_id(q);
+        if (!((keep_free >> id) & 1ull) && !(wall & mg_mp_nbr8(id / n, id % n))) elig |= 1u << q;
     }
-    // noisy A* (:681-724)
-    int g[MG_MP_NODES];
-    double f[MG_MP_NODES];
-    int8_t prev[MG_MP_NODES];
-    uint8_t open[MG_MP_NODES];
-    int nopen = 0;
-    uint64_t in_open = 0, closed = 0;
-    g[start] = 0;
-    f[start] = 0.0;
-    prev[start] = -1;
-    open[nopen++] = (uint8_t)start;
-    in_open |= 1ull << start;
+    elig = c.reduce_or(elig);
+    int nring = mg_popc32(elig);
+    const int picks = mg_rr_integers(r, 0, 2) ? 8 : 4;  // choice([4, 8])
+    MG_NOUNROLL
+    for (int q = 0; q < picks && nring > 0; ++q) {
+        const int b = mg_nth_set_bit(elig, mg_rr_integers(r, 0, nring));  // choice(outer_nodes); one candidate draws nothing
+        wall |= 1ull << mg_mp_ring_id(b);
+        elig &= ~(1u << b);
+        nring--;
+    }
+    // noisy A* (:681-724). Per cell of this lane: key = insertion order << 15 | g << 6 | cell (g <= 48 * 8)
+    uint32_t key[PER];
+    double h[PER], f[PER];
+    uint32_t prev[PER];
+    MG_UNROLL
+    for (int j = 0; j < PER; ++j) {
+        const int cell = c.lane + NL * j;
+        int d2 = 0;
+        if (cell < MG_MP_NODES) {
+            const int dx = cell / n - ex, dy = cell % n - ey;
+            d2 = dx * dx + dy * dy;
+        }
+        h[j] = tab.sqrt_d2[d2];
+        f[j] = 0.0;
+        key[j] = cell == start ? (uint32_t)start : MG_GEN_NOKEY;  // order 0, g 0
+        prev[j] = MG_GEN_NOPREV;
+    }
+    uint64_t open = 1ull << start, closed = 0;
+    uint32_t counter = 1, head_key = (uint32_t)start;
+    double fh = 0.0;  // f of open[0]
+    bool need_head = false;
+    uint64_t path = 0;
     for (;;) {
-        if (nopen == 0) return 0;
-        int w = 0;
-        for (int q = 0; q < nopen; ++q)
-            if (f[open[q]] < f[open[0]]) {  // first node better than the head, not the best one
-                w = q;
-                break;
+        if (!open) return 0;
+        if (need_head) {  // open[0] was taken: the open node inserted first is the new head
+            uint32_t best = MG_GEN_NOKEY;
+    MG_UNROLL
+            for (int j = 0; j < PER; ++j) {
+                const int cell = c.lane + NL * j;
+                if (cell < MG_MP_NODES && ((open >> cell) & 1ull) && key[j] < best) best = key[j];
             }
-        int cur = open[w];
-        if (cur == end) {
-            uint64_t path = 0;
-            int cnt = 0;
-            for (int at = end; at >= 0; at = prev[at]) {
-                path |= 1ull << at;
-                if (order) order[cnt] = (uint8_t)at;
-                cnt++;
-            }
-            if (n_order) *n_order = cnt;
-            return path;
+            head_key = c.reduce_min(best);
+            const int head = (int)(head_key & 63u), hj = head / NL;
+            double fl = 0.0;
+    MG_UNROLL
+            for (int j = 0; j < PER; ++j)
+                if (j == hj) fl = f[j];
+            fh = mg_f64_make(c.shfl(mg_f64_lo(fl), head % NL), c.shfl(mg_f64_hi(fl), head % NL));
+            need_head = false;
         }
-        for (int t = w; t + 1 < nopen; ++t) open[t] = open[t + 1];
-        nopen--;
-        in_open &= ~(1ull << cur);
+        // the first node of the list with f < f(open[0]), else open[0] (:685-690)
+        uint32_t cand = MG_GEN_NOKEY;
+    MG_UNROLL
+        for (int j = 0; j < PER; ++j) {
+            const int cell = c.lane + NL * j;
+            if (cell < MG_MP_NODES && ((open >> cell) & 1ull) && f[j] < fh && key[j] < cand) cand = key[j];
+        }
+        cand = c.reduce_min(cand);
+        const uint32_t cur_key = cand == MG_GEN_NOKEY ? head_key : cand;
+        const int cur = (int)(cur_key & 63u), gc = (int)((cur_key >> 6) & 511u);
+        if (cur_key == head_key) need_head = true;
+        if (cur == end) break;
+        open &= ~(1ull << cur);
         closed |= 1ull << cur;
-        int cn = mg_mp_neighbours(cur / n, cur % n, nb);
-        for (int q = 0; q < cn; ++q) {
-            int v = nb[q];
-            if (((closed >> v) & 1) || ((wall >> v) & 1)) continue;
-            int cost = g[cur] + (int)mg_integers(r, 1, 9);
-            bool new_path = false;
-            if ((in_open >> v) & 1) {
-                if (cost < g[v]) new_path = true;  // g_cost is not updated (reference bug, :712)
-            } else {
-                g[v] = cost;
-                new_path = true;
-                open[nopen++] = (uint8_t)v;
-                in_open |= 1ull << v;
+        const int ci = cur / n, cj = cur % n;
+        // neighbours in Node.add_neighbors order (+x, -x, +y, -y), pygame_assets.py:465-472
+        MG_NOUNROLL
+        for (int q = 0; q < 4; ++q) {
+            const int vi = ci + (q == 0 ? 1 : (q == 1 ? -1 : 0)), vj = cj + (q == 2 ? 1 : (q == 3 ? -1 : 0));
+            if ((unsigned)vi >= (unsigned)n || (unsigned)vj >= (unsigned)n) continue;
+            const int v = mg_mp_id(vi, vj);
+            if (((closed | wall) >> v) & 1ull) continue;
+            const uint32_t cost = (uint32_t)(gc + mg_rr_integers(r, 1, 9));
+            const bool is_open = ((open >> v) & 1ull) != 0;
+    MG_UNROLL
+            for (int j = 0; j < PER; ++j) {
+                if (c.lane + NL * j != v) continue;  // the lane that owns cell v
+                if (is_open) {
+                    // a cheaper way to an open node: g_cost is NOT updated (reference bug, :712), so f stays
+                    // what it was; only the predecessor changes
+                    if (cost < ((key[j] >> 6) & 511u)) prev[j] = (uint32_t)cur;
+                } else {
+                    key[j] = (counter << 15) | (cost << 6) | (uint32_t)v;
+                    f[j] = (double)cost + h[j];
+                    prev[j] = (uint32_t)cur;
+                }
             }
-            if (new_path) {
-                int dx = v / n - ex, dy = v % n - ey;
-                f[v] = (double)g[v] + sqrt((double)(dx * dx + dy * dy));
-                prev[v] = (int8_t)cur;
+            if (!is_open) {
+                counter++;
+                open |= 1ull << v;
             }
         }
     }
+    // walk back from the end node: each predecessor comes from the lane that owns the cell
+    for (int at = end; at != MG_GEN_NOPREV;) {
+        path |= 1ull << at;
+        const int aj = at / NL;
+        uint32_t p = MG_GEN_NOPREV;
+    MG_UNROLL
+        for (int j = 0; j < PER; ++j)
+            if (j == aj) p = prev[j];
+        at = (int)c.shfl(p, at % NL);
+    }
+    if (next2) {
+        uint64_t n0 = 0, n1 = 0;
+    MG_UNROLL
+        for (int j = 0; j < PER; ++j) {
+            const int b = c.lane + NL * j;
+            if (b >= MG_MP_NODES || !((path >> b) & 1ull) || prev[j] == MG_GEN_NOPREV) continue;
+            const int a = (int)prev[j];  // a -> b on the path
+            const int ax = a / n, ay = a % n, bx = b / n, by = b % n;
+            const uint64_t code = bx == ax + 1 ? 0u : (by == ay - 1 ? 1u : (by == ay + 1 ? 2u : 3u));
+            if (a >> 5)
+                n1 |= code << (2 * (a & 31));
+            else
+                n0 |= code << (2 * (a & 31));
+        }
+        next2[0] = (uint64_t)c.reduce_or((uint32_t)n0) | ((uint64_t)c.reduce_or((uint32_t)(n0 >> 32)) << 32);
+        next2[1] = (uint64_t)c.reduce_or((uint32_t)n1) | ((uint64_t)c.reduce_or((uint32_t)(n1 >> 32)) << 32);
+    }
+    return path;
 }
 
 MG_HD void mg_mp_draw(const MgMPK& k, const MgMPState& s, int cross, MgMPDraw& d) {
@@ -160,15 +279,14 @@ MG_HD void mg_mp_draw(const MgMPK& k, const MgMPState& s, int cross, MgMPDraw& d
     d.gy = s.ey;
 }
 
-MG_HD_NOINLINE void mg_mp_reset_env(const MgMPK& k, MgMPState& s, MgMPDraw& d) {
+// reset(): called by every lane of the warp (uniform draws on a register copy of the stream, lane 0 writes)
+template <class Ctx>
+MG_HD_NOINLINE void mg_mp_reset_coop(Ctx& c, const MgMPK& k, MgMPState& s, MgMPDraw& d, MgGenMem& m, const MgGenCta& tab) {
     const int g = MG_MP_CELLS;
-    MgRng r = s.rng;
-    s.t = 0;
-    s.ep_len = 0;
-    s.ep_reward = 0.0;
-    int side = mg_choice(r, k.p.cardinal_origin_choice);
-    int a = (int)mg_integers(r, 0, g);
-    int b = (int)mg_integers(r, 0, g);
+    MgRngR r = mg_rr_load(s.rng);
+    const int side = k.p.cardinal_origin_choice.v[mg_rr_integers(r, 0, k.p.cardinal_origin_choice.n)];
+    const int a = mg_rr_integers(r, 0, g);
+    const int b = mg_rr_integers(r, 0, g);
     int sx, sy, ex, ey;
     if (side == 0) {
         sx = 0, sy = a, ex = g - 1, ey = b;
@@ -179,25 +297,32 @@ MG_HD_NOINLINE void mg_mp_reset_env(const MgMPK& k, MgMPState& s, MgMPDraw& d) {
     } else {
         sx = a, sy = g - 1, ex = b, ey = 0;
     }
-    s.sx = (uint8_t)sx;
-    s.sy = (uint8_t)sy;
-    s.ex = (uint8_t)ex;
-    s.ey = (uint8_t)ey;
-    s.path_mask = mg_mp_generate(r, sx, sy, ex, ey);
-    s.visited = 0;
-    s.rot = 0;
-    s.cx = (int16_t)(sx * MG_MP_TILE + k.radius);
-    s.cy = (int16_t)(sy * MG_MP_TILE + k.radius);
-    s.gx = (int8_t)sx;  // Grid: normalize(start * 12 + int(25 * SCALE)) (mystery_path_grid.py:186-188)
-    s.gy = (int8_t)sy;
-    s.off_path = 0;
-    s.num_fails = 0;
-    s.cross_on = 0;
-    s.cross_x = 0;
-    s.cross_y = 0;
-    s.live = s.path_mask ? 1 : 0;  // no path: the reference raises; here the env stays finished
-    s.rng = r;
-    mg_mp_draw(k, s, 0, d);
+    const uint64_t mask = mg_mp_generate_coop(c, r, sx, sy, ex, ey, tab);
+    if (c.lane == 0) {
+        s.t = 0;
+        s.ep_len = 0;
+        s.ep_reward = 0.0;
+        s.sx = (uint8_t)sx;
+        s.sy = (uint8_t)sy;
+        s.ex = (uint8_t)ex;
+        s.ey = (uint8_t)ey;
+        s.path_mask = mask;
+        s.visited = 0;
+        s.rot = 0;
+        s.cx = (int16_t)(sx * MG_MP_TILE + k.radius);
+        s.cy = (int16_t)(sy * MG_MP_TILE + k.radius);
+        s.gx = (int8_t)sx;  // Grid: normalize(start * 12 + int(25 * SCALE)) (mystery_path_grid.py:186-188)
+        s.gy = (int8_t)sy;
+        s.off_path = 0;
+        s.num_fails = 0;
+        s.cross_on = 0;
+        s.cross_x = 0;
+        s.cross_y = 0;
+        s.live = mask ? 1 : 0;  // no path: the reference raises; here the env stays finished
+        mg_rr_store(r, s.rng);
+        mg_mp_draw(k, s, 0, d);
+    }
+    c.sync();
 }
 
 MG_HD bool mg_mp_step_env(const MgMPK& k, MgMPState& s, int a0, int a1, double& reward_out, double* info,

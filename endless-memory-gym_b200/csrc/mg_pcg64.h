@@ -65,3 +65,49 @@ MG_HD double mg_uniform(MgRng& r, double a, double b) {
     return a + prod;
 #endif
 }
+
+// ---- register-resident copy of the stream ---------------------------------------------------------
+// For code that EVERY lane of a warp runs redundantly (the cooperative resets: each lane holds the same state,
+// makes the same draws, lane 0 writes the stream back). Fully inlined: the state never leaves registers.
+struct MgRngR {
+    uint64_t lo, hi, ilo, ihi;
+    uint32_t buf, has;
+};
+MG_HD MgRngR mg_rr_load(const MgRng& r) { return MgRngR{r.state_lo, r.state_hi, r.inc_lo, r.inc_hi, r.buf, r.has_buf}; }
+MG_HD void mg_rr_store(const MgRngR& q, MgRng& r) {
+    r.state_lo = q.lo, r.state_hi = q.hi, r.buf = q.buf, r.has_buf = q.has;
+}
+MG_HD uint64_t mg_rr_next64(MgRngR& r) {
+    mg_u128 s = (((mg_u128)r.hi << 64) | r.lo) * mg_pcg_mult() + (((mg_u128)r.ihi << 64) | r.ilo);
+    r.lo = (uint64_t)s;
+    r.hi = (uint64_t)(s >> 64);
+    uint64_t x = r.hi ^ r.lo;
+    unsigned rot = (unsigned)(r.hi >> 58);
+    return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+MG_HD uint32_t mg_rr_next32(MgRngR& r) {
+    if (r.has) {
+        r.has = 0;
+        return r.buf;
+    }
+    uint64_t v = mg_rr_next64(r);
+    r.has = 1;
+    r.buf = (uint32_t)(v >> 32);
+    return (uint32_t)v;
+}
+// Generator.integers(lo, hi), 0 < hi - lo < 2^32 (same draw semantics as mg_integers)
+MG_HD int mg_rr_integers(MgRngR& r, int lo, int hi) {
+    const uint32_t rng = (uint32_t)(hi - 1 - lo);
+    if (rng == 0) return lo;
+    const uint32_t excl = rng + 1u;
+    uint64_t m = (uint64_t)mg_rr_next32(r) * excl;
+    uint32_t left = (uint32_t)m;
+    if (left < excl) {
+        const uint32_t thr = (0xFFFFFFFFu - rng) % excl;
+        while (left < thr) {
+            m = (uint64_t)mg_rr_next32(r) * excl;
+            left = (uint32_t)m;
+        }
+    }
+    return lo + (int)(m >> 32);
+}

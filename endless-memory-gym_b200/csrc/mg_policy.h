@@ -92,8 +92,69 @@ struct MgScratch {
     const uint8_t* cta;
 };
 
+// The same control flow for env types whose reset is WARP-COOPERATIVE (Mystery Path family: the path generator
+// runs on all lanes). Called by every lane; lane 0 runs the scalar parts and hands its decisions to the warp
+// through the per-warp scratch (MgGenMem::action / flag). `E` supplies reset_coop / step_coop.
+template <class E, class Ctx>
+MG_HD void mg_env_logic_coop(Ctx& c, const typename E::K& k, const MgKIO& q, const MgAssetView& a, int env, int t,
+                             typename E::State& s, int a0, int a1, MgFrameJob& job, typename E::Frame* fr,
+                             const MgScratch& sc) {
+    MgGenMem& m = *reinterpret_cast<MgGenMem*>(sc.warp);
+    double* const reward_out = q.io.reward + (size_t)t * q.rew_stride + env;
+    uint8_t* const done_out = q.io.done + (size_t)t * q.done_stride + env;
+    double* const info_out = q.io.info + (size_t)t * q.info_stride + MG_INFO_COLS * (size_t)env;
+    double* gt = q.io.ground_truth ? q.io.ground_truth + MG_GT_COLS * (size_t)env : nullptr;
+    if (c.lane == 0) {
+        int action = 0;
+        job.nframes = 0;
+        if (q.mode == MG_MODE_RESET) {
+            if (!(q.io.reset_mask && !q.io.reset_mask[env])) {
+                if (q.rng4) {  // env.reset(seed=s): a fresh PCG64 stream
+                    const uint64_t* r = q.rng4 + 4 * (size_t)env;
+                    s.rng.state_lo = r[0];
+                    s.rng.state_hi = r[1];
+                    s.rng.inc_lo = r[2];
+                    s.rng.inc_hi = r[3];
+                    s.rng.buf = 0;
+                    s.rng.has_buf = 0;
+                }
+                action = 1;
+            }
+        } else if (!s.live) {  // finished (or never reset): the step is ignored
+            *reward_out = 0.0;
+            *done_out = 1;
+        } else {
+            action = 2;
+        }
+        m.action = action;
+    }
+    c.sync();
+    const int action = m.action;
+    if (action == 0) return;
+    if (action == 1) {
+        E::reset_coop(c, k, a, s, fr[0], gt, sc);
+        if (c.lane == 0) {
+            job.nframes = 1;
+            job.to_final[0] = 0;
+        }
+        return;
+    }
+    const bool done = E::step_coop(c, k, a, s, a0, a1, reward_out, done_out, info_out, fr[0], gt, sc);
+    int at = 0;
+    if (done && (q.io.flags & MG_FLAG_AUTORESET)) {
+        if (q.io.final_obs) at = 1;  // terminal frame -> final_obs, first frame of the next episode -> obs
+        E::reset_coop(c, k, a, s, fr[at], gt, sc);
+    }
+    if (c.lane == 0) {
+        job.to_final[0] = at;
+        job.to_final[at] = 0;
+        job.nframes = at + 1;
+    }
+}
+
 struct MMPolicy {
     static constexpr int kWarpExtra = 0, kCtaExtra = 0;
+    static constexpr int kStageReserve = 16 * 1024;  // shared memory kept free for the staged asset prefix
     static constexpr int kTeamWarps = 1, kMaxThreads = 320;
     static constexpr int kFrameBuf = 21248;      // per-team TMA frame buffer (MG_FRAME_BYTES rounded up to 128)
     static constexpr bool kDirectStore = false;  // frames leave through cp.async.bulk from the frame buffer
@@ -131,25 +192,42 @@ struct MMPolicy {
 };
 
 struct MPPolicy {
-    static constexpr int kWarpExtra = 0, kCtaExtra = 0;
+    static constexpr int kWarpExtra = (int)((sizeof(MgGenMem) + 127) / 128 * 128);
+    static constexpr int kCtaExtra = (int)((sizeof(MgGenCta) + 127) / 128 * 128);
+    static constexpr int kStageReserve = 8 * 1024;
     static constexpr int kTeamWarps = 1, kMaxThreads = 320;
     static constexpr int kFrameBuf = 21248;
     static constexpr bool kDirectStore = false;
-    static MG_HD void cta_init(uint8_t*, int, int) {}
+    static MG_HD void cta_init(uint8_t* cta, int tid, int nthreads) {
+        mg_gen_cta_init(reinterpret_cast<MgGenCta*>(cta), tid, nthreads);
+    }
     static MG_HD void warp_init(uint8_t*, int) {}
     typedef MgMPK K;
     typedef MgMPState State;
     typedef MgMPDraw Frame;
     static MG_HD bool restores_clean(const K&) { return true; }
-    static MG_HD void reset_env(const K& k, const MgAssetView&, State& s, Frame& f, double*) { mg_mp_reset_env(k, s, f); }
-    static MG_HD bool step_env(const K& k, const MgAssetView&, State& s, int a0, int a1, double& reward, double* info,
-                               Frame& f, double*) {
-        return mg_mp_step_env(k, s, a0, a1, reward, info, f);
+    template <class Ctx>
+    static MG_HD void reset_coop(Ctx& c, const K& k, const MgAssetView&, State& s, Frame& f, double*, const MgScratch& sc) {
+        mg_mp_reset_coop(c, k, s, f, *reinterpret_cast<MgGenMem*>(sc.warp), *reinterpret_cast<const MgGenCta*>(sc.cta));
+    }
+    template <class Ctx>
+    static MG_HD bool step_coop(Ctx& c, const K& k, const MgAssetView&, State& s, int a0, int a1, double* reward_out,
+                                uint8_t* done_out, double* info, Frame& f, double*, const MgScratch& sc) {
+        MgGenMem& m = *reinterpret_cast<MgGenMem*>(sc.warp);
+        if (c.lane == 0) {
+            double reward;
+            const bool done = mg_mp_step_env(k, s, a0, a1, reward, info, f);
+            *reward_out = reward;
+            *done_out = done ? 1 : 0;
+            m.flag = done ? 1 : 0;
+        }
+        c.sync();
+        return m.flag != 0;
     }
     template <class Ctx>
     static MG_HD void logic(Ctx& c, const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0,
-                            int a1, MgFrameJob& job, Frame* fr, const MgScratch&) {
-        if (c.lane == 0) mg_env_logic<MPPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
+                            int a1, MgFrameJob& job, Frame* fr, const MgScratch& sc) {
+        mg_env_logic_coop<MPPolicy>(c, k, q, a, env, t, s, a0, a1, job, fr, sc);
     }
     template <class Ctx>
     static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f, const MgScratch&) {
@@ -162,28 +240,49 @@ struct MPPolicy {
 };
 
 struct EPPolicy {
-    static constexpr int kWarpExtra = 0, kCtaExtra = 0;
+    static constexpr int kWarpExtra = (int)((sizeof(MgGenMem) + 127) / 128 * 128);
+    static constexpr int kCtaExtra = (int)((sizeof(MgGenCta) + 127) / 128 * 128);
+    static constexpr int kStageReserve = 8 * 1024;
     static constexpr int kTeamWarps = 1, kMaxThreads = 320;
     static constexpr int kFrameBuf = 21248;
     static constexpr bool kDirectStore = false;
-    static MG_HD void cta_init(uint8_t*, int, int) {}
+    static MG_HD void cta_init(uint8_t* cta, int tid, int nthreads) {
+        mg_gen_cta_init(reinterpret_cast<MgGenCta*>(cta), tid, nthreads);
+    }
     static MG_HD void warp_init(uint8_t*, int) {}
     typedef MgEPK K;
     typedef MgEPState State;
     typedef MgEPFrame Frame;
     // with show_background every frame repaints the whole buffer instead of un-patching it
     static MG_HD bool restores_clean(const K& k) { return !k.p.show_background; }
-    static MG_HD void reset_env(const K& k, const MgAssetView&, State& s, Frame& f, double* gt) {
-        mg_ep_reset_env(k, s, f, gt);
+    template <class Ctx>
+    static MG_HD void reset_coop(Ctx& c, const K& k, const MgAssetView&, State& s, Frame& f, double* gt, const MgScratch& sc) {
+        mg_ep_reset_coop(c, k, s, f, gt, *reinterpret_cast<MgGenMem*>(sc.warp), *reinterpret_cast<const MgGenCta*>(sc.cta));
     }
-    static MG_HD bool step_env(const K& k, const MgAssetView&, State& s, int a0, int, double& reward, double* info,
-                               Frame& f, double* gt) {
-        return mg_ep_step_env(k, s, a0, reward, info, f, gt);
+    // the step may have to extend the path (add_path_segment, endless_mystery_path.py:300-302): the move runs on
+    // one lane, the segment on the warp, the rest of the step on one lane again
+    template <class Ctx>
+    static MG_HD bool step_coop(Ctx& c, const K& k, const MgAssetView&, State& s, int a0, int, double* reward_out,
+                                uint8_t* done_out, double* info, Frame& f, double* gt, const MgScratch& sc) {
+        MgGenMem& m = *reinterpret_cast<MgGenMem*>(sc.warp);
+        if (c.lane == 0) m.flag = mg_ep_step_pre(k, s, a0) ? 1 : 0;
+        c.sync();
+        bool capped = false;
+        if (m.flag) capped = !mg_ep_add_segment_coop(c, s, m, *reinterpret_cast<const MgGenCta*>(sc.cta));
+        if (c.lane == 0) {
+            double reward;
+            const bool done = mg_ep_step_post(k, s, capped, reward, info, f, gt);
+            *reward_out = reward;
+            *done_out = done ? 1 : 0;
+            m.flag = done ? 1 : 0;
+        }
+        c.sync();
+        return m.flag != 0;
     }
     template <class Ctx>
     static MG_HD void logic(Ctx& c, const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0,
-                            int a1, MgFrameJob& job, Frame* fr, const MgScratch&) {
-        if (c.lane == 0) mg_env_logic<EPPolicy>(k, q, a, env, t, s, a0, a1, job, fr);
+                            int a1, MgFrameJob& job, Frame* fr, const MgScratch& sc) {
+        mg_env_logic_coop<EPPolicy>(c, k, q, a, env, t, s, a0, a1, job, fr, sc);
     }
     template <class Ctx>
     static MG_HD void compose(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f, const MgScratch&) {
@@ -200,6 +299,7 @@ struct SSPolicyT {
     static constexpr int kWarpExtra = (int)((sizeof(MgSSWarpMem) + 127) / 128 * 128);
     static constexpr int kCtaExtra = (int)((sizeof(MgSSCtaTables) + 127) / 128 * 128);
     // instruction / latency-bound frames: TW warps share one env (more warps per base buffer hide more latency)
+    static constexpr int kStageReserve = 16 * 1024;
     static constexpr int kTeamWarps = TW, kMaxThreads = TW <= 2 ? 512 : 256 * TW;
     static constexpr int kFrameBuf = 0;         // no staging buffer: the frame is a masked copy of the base buffer
     static constexpr bool kDirectStore = true;  // ... written straight to the observation with 128-bit stores

@@ -31,7 +31,9 @@ torch.cuda.synchronize()
 print(f"launch: {e0.elapsed_time(e1) * 1e3:.1f} us for {T} steps x {n} envs = {e0.elapsed_time(e1) * 1e3 / T:.2f} us/step")
 b = trace.cpu().numpy().astype(np.int64)
 for nm, i0, i1 in (("step start -> logic done", 3, 4), ("logic done -> emit start", 4, 5), ("emit (or compose->issue)", 5, 6),
-                   ("emit: update base", 8, 9), ("emit: lit + lut", 9, 10), ("emit: masked copy", 10, 11)):
+                   ("emit: update base", 8, 9), ("emit: lit + lut", 9, 10), ("emit: masked copy", 10, 11),
+                   ("reset: path generation", 12, 13), ("reset: rest", 13, 14)):
     if b[:, i0].any() and b[:, i1].any():
-        d = (b[:, i1] - b[:, i0]) / 1e3
+        sel = (b[:, i0] > 0) & (b[:, i1] > 0)
+        d = (b[sel, i1] - b[sel, i0]) / 1e3
         print(f"  {nm:28s} mean {d.mean():7.2f} us  p50 {np.median(d):7.2f}  p95 {np.percentile(d, 95):7.2f}  max {d.max():7.2f}")

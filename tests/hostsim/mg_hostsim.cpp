@@ -14,11 +14,15 @@
 
 namespace {
 struct HostCtx {
+    static constexpr int kLanes = 1;
     int lane = 0, nl = 1;
     void sync() {}
     void stamp(int) {}
     void store16(MgVec16* p, const MgVec16& v, bool) { *p = v; }
     void atomic_or(uint32_t* p, uint32_t v) { *p |= v; }
+    uint32_t reduce_min(uint32_t v) { return v; }
+    uint32_t reduce_or(uint32_t v) { return v; }
+    uint32_t shfl(uint32_t v, int) { return v; }
     uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31u)); }
     void copy_frame(uint8_t* dst, const uint8_t* src) { memcpy(dst, src, MG_FRAME_BYTES); }
 };
