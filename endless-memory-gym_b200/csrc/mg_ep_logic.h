@@ -96,7 +96,7 @@ MG_HD bool mg_ep_prev(const MgEPState& s, int x, int y, int& px, int& py) {
 // EndlessMysteryPath.add_path_segment: draws the start row (first segment only), the end row, then the A* path.
 // Called by every lane of the warp (mg_mp_generate_coop); the stream in the record advances even when it fails.
 template <class Ctx>
-MG_HD_NOINLINE bool mg_ep_add_segment_coop(Ctx& c, MgEPState& s, MgGenMem& m, const MgGenCta& tab) {
+MG_HD_NOINLINE bool mg_ep_add_segment_coop(Ctx c, MgEPState& s, MgGenMem& m, const MgGenCta& tab) {
     const int ns = s.n_segments;
     if (ns >= MG_EP_MAXSEG) return false;
     const int g7 = MG_MP_CELLS;
@@ -183,7 +183,7 @@ MG_HD int mg_ep_bar_height(int stamina, int max_visible, bool at_reset) {
 }
 
 template <class Ctx>
-MG_HD_NOINLINE void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, double* gt, MgGenMem& m,
+MG_HD_NOINLINE void mg_ep_reset_coop(Ctx c, const MgEPK& k, MgEPState& s, MgEPFrame& f, double* gt, MgGenMem& m,
                                      const MgGenCta& tab) {
     c.stamp(12);
     if (c.lane == 0) {

@@ -262,7 +262,8 @@ MG_HD void mg_ep_restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgEPF
 // with per-surface alpha (SDL BlitNtoNSurfaceAlphaKey: d += trunc((0 - d) * A / 255)).
 struct MgSSDrawK {
     int n_layers;
-    int layers[6];
+    const int32_t* layers;  // painter's order of this frame (points into the kernel parameters: no local copy)
+    int spot_li, bar_li;  // where the spotlight layer / the top bar sit in that order
     int cb_x, cb_w;
     int show_last_action;
     int has_coin_layer;   // coin_surface is None when num_coins == 0
@@ -328,10 +329,12 @@ MG_HD uint32_t mg_ss_bg(int kind, int x, int y) {
 
 // top bar (searing_spotlights.py:372-389, 465-468, 222-224, 518-523), y < 4
 MG_HD uint32_t mg_ss_bar(const MgSSDrawK& k, const MgSSFrame& f, int x) {
-    const uint32_t act[3] = {120u | (120u << 8) | (120u << 16), 116u | (1u << 8) | (113u << 16), 255u | (94u << 8) | (14u << 16)};
     uint32_t c = 50u | (50u << 8) | (50u << 16);
     if (x < 42) c = 0x0000FF00u;  // green health
-    if (k.show_last_action && x >= 42) c = act[x < 63 ? f.bar_c0 : f.bar_c1];
+    if (k.show_last_action && x >= 42) {
+        const int which = x < 63 ? f.bar_c0 : f.bar_c1;  // no action grey, negative purple, positive orange
+        c = which == 0 ? (120u | (120u << 8) | (120u << 16)) : (which == 1 ? (116u | (1u << 8) | (113u << 16)) : (255u | (94u << 8) | (14u << 16)));
+    }
     // health lost: red from the left; beyond the health half it only survives until the action boxes are repainted
     if ((x < f.red_w_max && (x < 42 || !k.show_last_action)) || x < f.red_now) c = 0x000000FFu;
     if (f.coin_bar && x >= k.cb_x && x < k.cb_x + k.cb_w) c = f.coin_bar == 1 ? (255u | (255u << 8)) : (50u | (50u << 8) | (50u << 16));
@@ -523,7 +526,7 @@ MG_HD void mg_ss_draw_layer(Ctx& c, uint8_t* base, const MgAssetView& a, const M
 
 // the whole base buffer from scratch (after a reset, a background change, or in a non-default layer order): cold
 template <class Ctx>
-MG_HD_NOINLINE void mg_ss_rebuild_base(Ctx& c, uint8_t* base, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f) {
+MG_HD_NOINLINE void mg_ss_rebuild_base(Ctx c, uint8_t* base, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f) {
     uint32_t c_even, c_odd;
     mg_ss_bg_colours(f.bg_kind, 0, c_even, c_odd);
     mg_ss_fill_bg(c, base, c_even, c_odd);
@@ -540,7 +543,7 @@ template <class Ctx>
 MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
                              int spot_li, bool simple) {
     uint8_t* base = wm->base;
-    const MgSSBaseDesc d = wm->desc;
+    const MgSSBaseDesc& d = wm->desc;  // read in place; lane 0 rewrites it after the last sync below
     const int half = a.hdr->agent_dim >> 1;
     bool same_rest = simple && d.valid && d.coin_above == f.coin_above && d.bg_kind == f.bg_kind && d.exit_x == f.exit_x && d.exit_y == f.exit_y &&
                      d.exit_open == f.exit_open && d.n_coins == f.n_coins;
@@ -651,7 +654,7 @@ MG_HD void mg_ss_masked_copy_t(Ctx& c, uint8_t* out, const MgSSWarpMem* wm, cons
 
 // the cold variants: alpha == 0 (plain copy, the reset frame) and the dimming ramp
 template <class Ctx>
-MG_HD_NOINLINE void mg_ss_masked_copy_cold(Ctx& c, uint8_t* out, MgSSWarpMem* wm, const MgSSCtaTables* t, int alpha,
+MG_HD_NOINLINE void mg_ss_masked_copy_cold(Ctx c, uint8_t* out, MgSSWarpMem* wm, const MgSSCtaTables* t, int alpha,
                                            bool stream) {
     if (alpha == 0) {
         const MgVec16* src = reinterpret_cast<const MgVec16*>(wm->base);
@@ -670,7 +673,7 @@ MG_HD_NOINLINE void mg_ss_masked_copy_cold(Ctx& c, uint8_t* out, MgSSWarpMem* wm
 
 // non-default layer orders: pixels of the sprites painted ABOVE the spotlight layer are never dimmed (cold)
 template <class Ctx>
-MG_HD_NOINLINE void mg_ss_lit_over(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+MG_HD_NOINLINE void mg_ss_lit_over(Ctx c, MgSSWarpMem* wm, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
                                    int spot_li) {
     for (int li = spot_li + 1; li < k.n_layers; ++li) {
         int L = k.layers[li];
@@ -697,7 +700,7 @@ MG_HD_NOINLINE void mg_ss_lit_over(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a
 
 // black_background: every spotlight has a white 1-px outline (pygame_assets.py:112-113) (cold)
 template <class Ctx>
-MG_HD_NOINLINE void mg_ss_outlines(Ctx& c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+MG_HD_NOINLINE void mg_ss_outlines(Ctx c, uint8_t* buf, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
                                    int spot_li) {
     // 3b. black_background: white 1-px outlines on the spotlight surface (pygame_assets.py:112-113). An outline
     //     pixel survives unless a LATER spotlight's disc is drawn over it; it is blended like any non-key pixel:
@@ -739,11 +742,7 @@ MG_HD_NOINLINE void mg_ss_outlines(Ctx& c, uint8_t* buf, const MgAssetView& a, c
 template <class Ctx>
 MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
                       MgSSWarpMem* wm, const MgSSCtaTables* tables, bool stream) {
-    int spot_li = 1, bar_li = 0;
-    for (int li = 0; li < k.n_layers; ++li) {
-        if (k.layers[li] == 1) spot_li = li;
-        if (k.layers[li] == 2) bar_li = li;
-    }
+    const int spot_li = k.spot_li, bar_li = k.bar_li;
     // the reference's default order: bg, coins, exit, agent, SPOT, bar
     const bool simple = spot_li == k.n_layers - 2 && bar_li == k.n_layers - 1;
     // 1. every layer but the spotlight layer (kept across frames, patched where it changed)

@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     constexpr int kStateBytes = (int)sizeof(State);
     constexpr int kWords = kStateBytes / 8;             // 8-byte words per record
     constexpr int kPerLane = (kWords + kTeam - 1) / kTeam;  // words each thread moves
-    constexpr int kSlot = ((kStateBytes + 2 * (int)sizeof(Frame) + (int)sizeof(MgFrameJob) + 16 + 127) / 128) * 128;
+    constexpr int kFrames = P::kDirectStore ? 2 : 3;  // this step's (up to two) frames + the one being un-patched
+    constexpr int kSlot = ((kStateBytes + kFrames * (int)sizeof(Frame) + (int)sizeof(MgFrameJob) + 16 + 127) / 128) * 128;
     extern __shared__ __align__(128) uint8_t smem[];
 
     const int lane = threadIdx.x % kTeam, team = threadIdx.x / kTeam, nteams = blockDim.x / kTeam;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     const MgScratch scratch{wextra, cextra};
     State* st = reinterpret_cast<State*>(slot);
     Frame* fr = reinterpret_cast<Frame*>(slot + kStateBytes);
-    MgFrameJob* job = reinterpret_cast<MgFrameJob*>(slot + kStateBytes + 2 * sizeof(Frame));
+    MgFrameJob* job = reinterpret_cast<MgFrameJob*>(slot + kStateBytes + kFrames * sizeof(Frame));
     uint64_t* bar = reinterpret_cast<uint64_t*>(slot + kSlot - 8);
     uint32_t* grab = reinterpret_cast<uint32_t*>(slot + kSlot - 16);  // next env index, broadcast to the team
 
@@ -241,7 +242,8 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     }
 
     bool pending = false;  // a bulk store is still reading `buf`; `prev` is the patch to undo afterwards
-    Frame prev;
+    Frame* const prev = fr + (kFrames - 1);  // kept in the team's shared slot (a per-thread copy would live in local memory)
+    static_assert(sizeof(Frame) % 4 == 0, "frame descriptions are copied word-wise");
     while (env < q.n) {
         uint64_t* s64 = reinterpret_cast<uint64_t*>(st);
 #pragma unroll
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
                 if (pending) {
                     if (lane == 0) mg_bulk_wait_read();
                     ctx.sync();
-                    P::restore(ctx, buf, view, k, prev, scratch);
+                    P::restore(ctx, buf, view, k, *prev, scratch);
                     ctx.sync();
                 }
                 P::compose(ctx, buf, view, k, f, scratch);
@@ -337,7 +339,8 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
                     if (trow) trow[6] = mg_now();
                 }
                 pending = true;
-                prev = f;
+                for (int w = lane; w < (int)(sizeof(Frame) / 4); w += kTeam)
+                    reinterpret_cast<uint32_t*>(prev)[w] = reinterpret_cast<const uint32_t*>(&f)[w];
             }
             ctx.sync();  // job / frame slots are reused by the next step
         }
@@ -397,7 +400,7 @@ static int plan_launch(int n, int wpc_req, int default_wpc, bool balance, MgLaun
     }
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     constexpr int kSlot =
-        (((int)sizeof(typename P::State) + 2 * (int)sizeof(typename P::Frame) + (int)sizeof(MgFrameJob) + 16 + 127) / 128) * 128;
+        (((int)sizeof(typename P::State) + (P::kDirectStore ? 2 : 3) * (int)sizeof(typename P::Frame) + (int)sizeof(MgFrameJob) + 16 + 127) / 128) * 128;
     const int per_warp = P::kFrameBuf + kSlot + P::kWarpExtra;
     int wmax = 10;
     while (wmax > 1 && wmax * 32 * P::kTeamWarps > P::kMaxThreads) wmax--;

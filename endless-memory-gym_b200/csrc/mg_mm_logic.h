@@ -113,19 +113,19 @@ MG_HD int mg_mm_show_entry(const MgMMState& s, int e) {
 MG_HD_NOINLINE void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, double* gt) {
     const int size = k.size;
     const bool endless = k.p.variant == MG_MM_ENDLESS;
-    MgRng r = s.rng;
+    MgRngR r = mg_rr_load(s.rng);  // the stream stays in registers for the whole reset
     s.ep_reward = 0.0;
     s.ep_len = 0;
     s.t = 0;
     s.total_completed = 0;
     s.live = 1;
     s.tiles_on = 0;
-    int tile_id = (int)mg_integers(r, 0, size * size);
+    int tile_id = mg_rr_integers(r, 0, size * size);
     int i = tile_id / size, j = tile_id % size;
     int cx = MG_TILE * i + k.origin + MG_TILE / 2, cy = MG_TILE * j + k.origin + MG_TILE / 2;
     if (endless || k.p.variant == MG_MM_B) {  // spawn offset, endless_mortar_mayhem.py:224, mortar_mayhem_b.py:167
-        int o0 = (int)mg_integers(r, -2, 2);
-        int o1 = (int)mg_integers(r, -2, 2);
+        int o0 = mg_rr_integers(r, -2, 2);
+        int o1 = mg_rr_integers(r, -2, 2);
         cx += o0;
         cy += o1;
     }
@@ -140,9 +140,9 @@ MG_HD_NOINLINE void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, 
     int n;
     if (endless) {
         n = k.p.initial_command_count;
-        for (int c = 0; c < n; ++c) s.commands[c] = (uint8_t)mg_integers(r, 0, k.p.allowed_commands);
+        for (int c = 0; c < n; ++c) s.commands[c] = (uint8_t)mg_rr_integers(r, 0, k.p.allowed_commands);
     } else {
-        n = mg_choice(r, k.p.command_count);
+        n = mg_rr_choice(r, k.p.command_count);
         int simx = px, simy = py;
         for (int c = 0; c < n; ++c) {
             // available_commands: the first `allowed_commands` commands that keep the target inside the arena
@@ -154,11 +154,11 @@ MG_HD_NOINLINE void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, 
             if (simy <= 0) valid &= ~0x148u;         // dy = -1: up, right_up, left_up
 #if defined(__CUDA_ARCH__)
             const int nv = __popc(valid);
-            const int q = (int)__fns(valid, 0u, (int)mg_integers(r, 0, nv) + 1);  // the pick-th set bit
+            const int q = (int)__fns(valid, 0u, mg_rr_integers(r, 0, nv) + 1);  // the pick-th set bit
 #else
             int nv = 0;
             for (uint32_t m = valid; m; m &= m - 1u) nv++;
-            int pick = (int)mg_integers(r, 0, nv), q = 0;
+            int pick = mg_rr_integers(r, 0, nv), q = 0;
             for (;; ++q)  // the pick-th set bit
                 if ((valid >> q) & 1u)
                     if (pick-- == 0) break;
@@ -178,8 +178,8 @@ MG_HD_NOINLINE void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, 
         s.show_len = 0;
         s.show_pos = 0;
     } else {
-        s.show_dur = (uint16_t)mg_choice(r, k.p.command_show_duration);
-        s.show_delay = (uint16_t)mg_choice(r, k.p.command_show_delay);
+        s.show_dur = (uint16_t)mg_rr_choice(r, k.p.command_show_duration);
+        s.show_delay = (uint16_t)mg_rr_choice(r, k.p.command_show_delay);
         s.show_len = (uint16_t)(n * (s.show_dur + s.show_delay));
         s.show_pos = 1;  // the first entry is consumed by the reset frame
     }
@@ -193,9 +193,9 @@ MG_HD_NOINLINE void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, 
     s.tx = (int8_t)tx;
     s.ty = (int8_t)ty;
     s.cc = s.cs = s.cv = 0;
-    s.E = (uint16_t)mg_choice(r, k.p.explosion_duration);
-    s.D = (uint16_t)mg_choice(r, k.p.explosion_delay);
-    s.rng = r;
+    s.E = (uint16_t)mg_rr_choice(r, k.p.explosion_duration);
+    s.D = (uint16_t)mg_rr_choice(r, k.p.explosion_delay);
+    mg_rr_store(r, s.rng);
     mg_mm_frame(k, s, cx, cy, 0, task_b ? -2 : mg_mm_show_entry(s, 0), f);
     if (gt) {
         gt[0] = (double)tx / 5.0;
@@ -377,9 +377,9 @@ MG_HD bool mg_mm_step_env(const MgMMK& k, MgMMState& s, int a0, int a1, double& 
 // right_down, right_up, left_down, left_up; written by every lane of the team
 template <class Ctx>
 MG_HD void mg_mm_write_vector(Ctx& c, const MgMMState& s, float* vec) {
-    const uint8_t slot[9] = {1, 4, 2, 3, 0, 5, 6, 7, 8};  // Command.COMMANDS index -> one-hot slot
+    const uint64_t slot = 0x876503241ull;  // Command.COMMANDS index -> one-hot slot {1, 4, 2, 3, 0, 5, 6, 7, 8}, 4 bits each
     for (int i = c.lane; i < MG_MM_B_VECTOR; i += c.nl) {
         int cmd = i / 9, j = i - 9 * cmd;
-        vec[i] = (cmd < (int)s.n && slot[s.commands[cmd]] == j) ? 1.0f : 0.0f;
+        vec[i] = (cmd < (int)s.n && (int)((slot >> (4 * s.commands[cmd])) & 15u) == j) ? 1.0f : 0.0f;
     }
 }

@@ -264,6 +264,19 @@ extern "C" int mg_ss_check_params(const mg_ss_params* p) {
     return 0;
 }
 
+// where the spotlight layer and the top bar sit in both painter's orders (the kernel reads them per frame)
+static void ss_layer_indices(MgSSK* k) {
+    for (int alt = 0; alt < 2; ++alt) {
+        const int32_t* L = alt ? k->layers_alt : k->layers;
+        k->spot_li[alt] = 1;
+        k->bar_li[alt] = 0;
+        for (int li = 0; li < k->n_layers; ++li) {
+            if (L[li] == MG_SS_L_SPOT) k->spot_li[alt] = li;
+            if (L[li] == MG_SS_L_BAR) k->bar_li[alt] = li;
+        }
+    }
+}
+
 void mg_ss_derive(const mg_ss_params* p, MgSSK* k) {
     memset(k, 0, sizeof(*k));
     k->p = *p;
@@ -324,6 +337,7 @@ void mg_ss_derive(const mg_ss_params* p, MgSSK* k) {
         k->n_layers = n;
         k->cb_x = (int)(q * 2.75);
         k->cb_w = (int)(q * 0.5);
+        ss_layer_indices(k);
         return;
     }
     order[n++] = MG_SS_L_BG;
@@ -344,4 +358,5 @@ void mg_ss_derive(const mg_ss_params* p, MgSSK* k) {
         insert(sid++, MG_SS_L_AGENT);
     k->n_layers = n;
     for (int i = 0; i < n; ++i) k->layers[i] = k->layers_alt[i] = order[i];
+    ss_layer_indices(k);
 }

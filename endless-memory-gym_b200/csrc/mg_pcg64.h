@@ -7,6 +7,7 @@
 // rejection for ranges < 2^32, zero-width ranges draw nothing) and `distributions.c`
 // (`random_standard_uniform` = (next64 >> 11) * 2^-53).
 #pragma once
+#include "../../include/memgym_b200.h"
 #include "mg_common.h"
 
 typedef unsigned __int128 mg_u128;
@@ -95,19 +96,17 @@ MG_HD uint32_t mg_rr_next32(MgRngR& r) {
     r.buf = (uint32_t)(v >> 32);
     return (uint32_t)v;
 }
-// Generator.integers(lo, hi), 0 < hi - lo < 2^32 (same draw semantics as mg_integers)
+// Generator.integers(lo, hi), 0 < hi - lo < 2^32 (same draw semantics as mg_integers). Everything stays inline:
+// an out-of-line rejection path would take the stream's address and force it into local memory.
 MG_HD int mg_rr_integers(MgRngR& r, int lo, int hi) {
     const uint32_t rng = (uint32_t)(hi - 1 - lo);
     if (rng == 0) return lo;
     const uint32_t excl = rng + 1u;
     uint64_t m = (uint64_t)mg_rr_next32(r) * excl;
-    uint32_t left = (uint32_t)m;
-    if (left < excl) {
+    if ((uint32_t)m < excl) {  // Lemire rejection: probability < range / 2^32
         const uint32_t thr = (0xFFFFFFFFu - rng) % excl;
-        while (left < thr) {
-            m = (uint64_t)mg_rr_next32(r) * excl;
-            left = (uint32_t)m;
-        }
+        while ((uint32_t)m < thr) m = (uint64_t)mg_rr_next32(r) * excl;
     }
     return lo + (int)(m >> 32);
 }
+MG_HD int mg_rr_choice(MgRngR& r, const mg_choice_list& c) { return c.v[mg_rr_integers(r, 0, c.n)]; }

@@ -427,8 +427,11 @@ struct SSPolicyT {
 
     static MG_HD MgSSDrawK draw_k(const K& k, const Frame& f) {
         MgSSDrawK d;
+        const int alt = f.coin_above ? 1 : 0;
         d.n_layers = k.n_layers;
-        for (int i = 0; i < 6; ++i) d.layers[i] = f.coin_above ? k.layers_alt[i] : k.layers[i];
+        d.layers = alt ? k.layers_alt : k.layers;
+        d.spot_li = k.spot_li[alt];
+        d.bar_li = k.bar_li[alt];
         d.cb_x = k.cb_x;
         d.cb_w = k.cb_w;
         d.show_last_action = k.p.show_last_action;
@@ -445,7 +448,7 @@ struct SSPolicyT {
     }
     // terminal frames (one per episode): an out-of-line copy keeps the hot loop's code small
     template <class Ctx>
-    static MG_HD_NOINLINE void emit_cold(Ctx& c, uint8_t* dst, const MgAssetView& a, const K& k, const Frame& f,
+    static MG_HD_NOINLINE void emit_cold(Ctx c, uint8_t* dst, const MgAssetView& a, const K& k, const Frame& f,
                                          const MgScratch& sc) {
         mg_ss_emit(c, dst, a, draw_k(k, f), f, reinterpret_cast<MgSSWarpMem*>(sc.warp),
                    reinterpret_cast<const MgSSCtaTables*>(sc.cta), false);

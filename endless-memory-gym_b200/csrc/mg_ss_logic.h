@@ -32,6 +32,7 @@ struct MgSSK {
     int32_t n_layers;
     int32_t layers[6];          // painter's order (searing_spotlights.py:526-542), MG_SS_L_*
     int32_t layers_alt[6];      // Endless: the order while the coin is fresh (coin layer above the spotlights)
+    int32_t spot_li[2], bar_li[2];  // index of the spotlight layer / the top bar in layers ([0]) and layers_alt ([1])
     int32_t endless;            // Endless-SearingSpotlights-v0
     int32_t clamp_off;          // int(30 * SCALE)
     int32_t exit_d2max;         // largest integer d2 with sqrt(d2) <= exit_radius + agent radius (host-computed)
@@ -149,7 +150,7 @@ struct MgSSResetTmp {
 };
 
 template <class Ctx>
-MG_HD_NOINLINE void mg_ss_block_coop(Ctx& c, MgSSSampler& g, int x, int y, int r) {
+MG_HD_NOINLINE void mg_ss_block_coop(Ctx c, MgSSSampler& g, int x, int y, int r) {
     int y0 = y - r + 1 < 0 ? 0 : y - r + 1, y1 = y + r - 1 > MG_W - 1 ? MG_W - 1 : y + r - 1;
     for (int yy = y0 + c.lane; yy <= y1; yy += c.nl) {
         int dy = yy - y, rem = r * r - dy * dy - 1;  // need dx^2 <= rem
@@ -196,7 +197,7 @@ MG_HD int mg_ss_kth_free(uint64_t lo, uint64_t hi, int k) {
 }
 
 template <class Ctx>
-MG_HD_NOINLINE void mg_ss_sample_coop(Ctx& c, MgSSSampler& g, MgSSState& s, MgSSResetTmp& rt, int block_radius) {
+MG_HD_NOINLINE void mg_ss_sample_coop(Ctx c, MgSSSampler& g, MgSSState& s, MgSSResetTmp& rt, int block_radius) {
     if (c.lane < 28) {  // 28 lanes x 3 rows
         int n = 0;
         for (int q = 0; q < 3; ++q) n += MG_W - mg_popc64(g.lo[3 * c.lane + q]) - mg_popc64(g.hi[3 * c.lane + q]);
@@ -238,7 +239,7 @@ MG_HD_NOINLINE void mg_ss_sample_coop(Ctx& c, MgSSSampler& g, MgSSState& s, MgSS
 // num_coins; per coin cell + 2 offsets; exit cell + 2 offsets (searing_spotlights.py:354-414).
 // Called by every lane of the warp; `g` / `rt` are per-warp scratch.
 template <class Ctx>
-MG_HD_NOINLINE void mg_ss_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, MgSSSampler& g, MgSSResetTmp& rt) {
+MG_HD_NOINLINE void mg_ss_reset_env(Ctx c, const MgSSK& k, MgSSState& s, MgSSFrame& f, MgSSSampler& g, MgSSResetTmp& rt) {
     for (int y = c.lane; y < MG_W; y += c.nl) g.lo[y] = g.hi[y] = 0;
     if (c.lane == 0) {
         s.t = 0;
@@ -513,7 +514,7 @@ MG_HD void mg_ess_ground_truth(const MgSSK& k, const MgSSState& s, double* gt) {
 
 // _spawn_coin (:256-269): fresh sampler, only the OLD coin's surroundings blocked, sample(28) + two offsets
 template <class Ctx>
-MG_HD_NOINLINE void mg_ess_spawn_coin(Ctx& c, const MgSSK& k, MgSSState& s, MgSSSampler& g, MgSSResetTmp& rt, bool have_old) {
+MG_HD_NOINLINE void mg_ess_spawn_coin(Ctx c, const MgSSK& k, MgSSState& s, MgSSSampler& g, MgSSResetTmp& rt, bool have_old) {
     for (int y = c.lane; y < MG_W; y += c.nl) g.lo[y] = g.hi[y] = 0;
     if (c.lane == 0) rt.ok = 1;
     c.sync();
@@ -536,7 +537,7 @@ MG_HD_NOINLINE void mg_ess_spawn_coin(Ctx& c, const MgSSK& k, MgSSState& s, MgSS
 // reset(): RNG draw order — rotation; agent cell + 2 offsets; per initial spotlight radius, speed, 3 angles;
 // coin cell + 2 offsets (:294-407)
 template <class Ctx>
-MG_HD_NOINLINE void mg_ess_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, MgSSSampler& g, MgSSResetTmp& rt,
+MG_HD_NOINLINE void mg_ess_reset_env(Ctx c, const MgSSK& k, MgSSState& s, MgSSFrame& f, MgSSSampler& g, MgSSResetTmp& rt,
                             double* gt) {
     for (int y = c.lane; y < MG_W; y += c.nl) g.lo[y] = g.hi[y] = 0;
     if (c.lane == 0) {
