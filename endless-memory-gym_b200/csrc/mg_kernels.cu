@@ -95,6 +95,13 @@ __device__ __forceinline__ uint64_t mg_now() {
     return t;
 }
 
+// per-CTA words: the asset staging barrier and the work counter of the CTA-local dynamic env -> team scheduling
+#define MG_CTA_HDR_BYTES 128
+struct MgCtaHdr {
+    uint64_t stage_bar;
+    uint32_t next;
+};
+
 // execution context of mg_frame.h on the device: the 32 lanes of the warp that owns the env
 struct MgWarpCtx {
     static constexpr int kLanes = 32;  // lanes of a single-warp team (cooperative code sized at compile time)
@@ -144,7 +151,10 @@ struct MgWarpCtx {
 // ---- the kernel ----------------------------------------------------------------------------------
 // A "team" = the threads that own one env at a time: one warp, or P::kTeamWarps warps on a named barrier for
 // env types whose per-frame work is instruction-bound (more warps per frame buffer hide more latency).
-template <class P>
+// kRollout: the instantiation behind mg_*_rollout (n_steps consecutive steps per env, optional global work counter);
+// false = reset / single step (one pass over the batch, CTA-local scheduling only). Two instantiations keep each
+// kernel's code small and let the compiler drop the other mode's paths.
+template <class P, bool kRollout>
 __global__ void __launch_bounds__(P::kMaxThreads, 1)
     mg_env_kernel(const __grid_constant__ typename P::K k, const __grid_constant__ MgKIO q,
                   const uint8_t* __restrict__ assets, uint8_t* __restrict__ state) {
@@ -163,7 +173,8 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     uint8_t* slot = smem + (size_t)nteams * P::kFrameBuf + (size_t)team * kSlot;
     uint8_t* wextra = smem + (size_t)nteams * (P::kFrameBuf + kSlot) + (size_t)team * P::kWarpExtra;
     uint8_t* cextra = smem + (size_t)nteams * (P::kFrameBuf + kSlot + P::kWarpExtra);
-    uint8_t* stage = cextra + P::kCtaExtra;
+    MgCtaHdr* hdr = reinterpret_cast<MgCtaHdr*>(cextra + P::kCtaExtra);
+    uint8_t* stage = cextra + P::kCtaExtra + MG_CTA_HDR_BYTES;
     const MgScratch scratch{wextra, cextra};
     State* st = reinterpret_cast<State*>(slot);
     Frame* fr = reinterpret_cast<Frame*>(slot + kStateBytes);
@@ -179,34 +190,46 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     MgAssetView view = mg_asset_view(assets);
     MgWarpCtx ctx{lane, kTeam, mg_smem_u32(bar), 0u, mg_policy_evict_first(), nullptr, P::kTeamWarps > 1 ? team + 1 : 0};
     if (lane == 0) mg_mbar_init(ctx.bar, 1);
-    const int total_teams = gridDim.x * nteams;
-    int env = team * gridDim.x + blockIdx.x;  // consecutive envs on different SMs: remainders spread evenly
+    // This CTA owns envs blockIdx.x + j * gridDim.x (consecutive envs on different SMs: remainders spread
+    // evenly). Team i starts with j = i; every further j comes from a SHARED-MEMORY work counter, so a team
+    // held up by an auto-reset ends up with fewer envs and no global atomic sits on the step path.
+    const int G = gridDim.x;
+    int env = (int)blockIdx.x + team * G;
     const bool active = env < q.n;
     if (P::kFrameBuf && active && lane == 0) {  // background template -> this team's frame buffer (TMA, L2-resident source)
         mg_mbar_expect_tx(ctx.bar, MG_FRAME_BYTES);
         mg_bulk_load(buf, view.tmpl[0], MG_FRAME_BYTES, ctx.bar);
     }
-    const int stage_words = (int)(view.hdr->stage_bytes / 4);
-    const bool staged = stage_words * 4 <= q.stage_cap;
-    if (staged) {  // header, sprite lists, bitmaps, tables -> shared memory: compose never waits on L2
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(assets);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(stage);
-        for (int i = threadIdx.x; i < stage_words; i += blockDim.x) dst[i] = src[i];
+    // header, sprite lists, bitmaps, tables -> shared memory by one TMA bulk load: compose never waits on L2
+    const uint32_t stage_bytes = view.hdr->stage_bytes;
+    const bool staged = (int)stage_bytes <= q.stage_cap;
+    if (threadIdx.x == 0) {
+        hdr->next = (uint32_t)nteams;
+        const uint32_t sbar = mg_smem_u32(&hdr->stage_bar);
+        mg_mbar_init(sbar, 1);
+        if (staged) {
+            mg_mbar_expect_tx(sbar, stage_bytes);
+            mg_bulk_load(stage, assets, stage_bytes, sbar);
+        }
     }
     P::cta_init(cextra, threadIdx.x, blockDim.x);
     P::warp_init(wextra, lane);
     __syncthreads();
-    if (staged) view = mg_asset_view2(stage, assets);
+    if (staged) {
+        mg_mbar_wait(mg_smem_u32(&hdr->stage_bar), 0u);
+        view = mg_asset_view2(stage, assets);
+    }
     if (tracing) tr1 = mg_now();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");  // previous kernel's state / obs writes are visible
-    // dynamic scheduling: after its first (static) env a team takes the next unclaimed env from a global counter,
-    // so a team held up by an auto-reset ends up with fewer envs. The last team to leave re-arms the counter.
-    uint32_t* const sched = q.io.sched;
+    // Rollouts may pass a GLOBAL work counter instead (mg_rollout_io.sched): one atomic per env per T steps, and
+    // SMs that stream faster take more envs. The last team to leave re-arms it for the next launch.
+    uint32_t* const sched = kRollout ? q.sched : nullptr;
+    const int total_teams = G * nteams;
     const auto team_exit = [&]() {
         if (sched && lane == 0) {
             __threadfence();
-            if (atomicAdd(sched + 1, 1u) == (uint32_t)(gridDim.x * nteams) - 1u) {
+            if (atomicAdd(sched + 1, 1u) == (uint32_t)total_teams - 1u) {
                 sched[0] = 0u;
                 sched[1] = 0u;
                 __threadfence();
@@ -219,7 +242,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     }
     if (tracing) tr2 = mg_now();
 
-    const int T = q.n_steps;
+    const int T = kRollout ? q.n_steps : 1;
     const bool stepping = q.mode == MG_MODE_STEP;
     const uint64_t evict_first = ctx.policy;
     // ---- first record + first actions in flight while the template lands --------------------------------
@@ -228,8 +251,8 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     {
         const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)env * kStateBytes);
 #pragma unroll
-        for (int j = 0; j < kPerLane; ++j)
-            if (lane + kTeam * j < kWords) pre[j] = g[lane + kTeam * j];
+        for (int w = 0; w < kPerLane; ++w)
+            if (lane + kTeam * w < kWords) pre[w] = g[lane + kTeam * w];
         if (lane == 0 && stepping) {
             const int64_t* a = q.io.actions + (size_t)env * q.act_dims;
             act0 = a[0];
@@ -244,13 +267,15 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     bool pending = false;  // a bulk store is still reading `buf`; `prev` is the patch to undo afterwards
     Frame* const prev = fr + (kFrames - 1);  // kept in the team's shared slot (a per-thread copy would live in local memory)
     static_assert(sizeof(Frame) % 4 == 0, "frame descriptions are copied word-wise");
-    while (env < q.n) {
+    bool have = true;
+    while (have) {
         uint64_t* s64 = reinterpret_cast<uint64_t*>(st);
 #pragma unroll
-        for (int j = 0; j < kPerLane; ++j)
-            if (lane + kTeam * j < kWords) s64[lane + kTeam * j] = pre[j];
+        for (int w = 0; w < kPerLane; ++w)
+            if (lane + kTeam * w < kWords) s64[lane + kTeam * w] = pre[w];
         ctx.sync();
-        int nxt = env + total_teams;
+        int nxt = q.n;
+        bool have_next = false;
         for (int t = 0; t < T; ++t) {
             const int a0 = (int)act0, a1 = (int)act1;
             uint64_t* trow = tracing ? q.io.trace + (size_t)env * MG_TRACE_COLS : nullptr;
@@ -260,44 +285,26 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
                 asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
                 trow[0] = tr0, trow[1] = tr1, trow[2] = tr2, trow[3] = mg_now(), trow[7] = smid;
             }
-            // prefetch what the next iteration needs (next step's actions; on the env's last step the next
-            // env's record and first actions): the latency hides behind this step's work
-            uint32_t grabbed = 0;
-            if (t + 1 < T) {
+            if (t + 1 < T) {  // prefetch the next step's actions: the latency hides behind this step's work
                 if (lane == 0) {
                     const int64_t* a = q.io.actions + (size_t)(t + 1) * q.act_stride + (size_t)env * q.act_dims;
                     act0 = a[0];
                     if (q.act_dims > 1) act1 = a[1];
                 }
-            } else if (sched) {
-                // claim the next env now; the index is first needed after the logic below (latency hidden)
-                if (lane == 0) grabbed = atomicAdd(sched, 1u);
-            } else if (nxt < q.n) {
-                const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)nxt * kStateBytes);
-#pragma unroll
-                for (int j = 0; j < kPerLane; ++j)
-                    if (lane + kTeam * j < kWords) pre[j] = g[lane + kTeam * j];
-                if (lane == 0 && stepping) {
-                    const int64_t* a = q.io.actions + (size_t)nxt * q.act_dims;
-                    act0 = a[0];
-                    if (q.act_dims > 1) act1 = a[1];
-                }
-            }
-            P::logic(ctx, k, q, view, env, t, *st, a0, a1, *job, fr, scratch);
-            if (sched && t + 1 == T && P::kTeamWarps > 1 && lane == 0) *grab = grabbed;
-            ctx.sync();
-            if (trow && lane == 0) trow[4] = mg_now();
-            if (sched && t + 1 == T) {  // dynamic scheduling: the next env's record + first actions, prefetched now
-                if constexpr (P::kTeamWarps > 1)
-                    grabbed = *grab;
-                else
-                    grabbed = __shfl_sync(0xffffffffu, grabbed, 0);
-                nxt = total_teams + (int)grabbed;
-                if (nxt < q.n) {
+            } else {
+                // the env's last step: claim this team's next env — as LATE as possible, so that a team held up by
+                // an auto-reset ends up with fewer envs — and start fetching its record and first actions
+                if (lane == 0)
+                    *grab = sched ? (uint32_t)total_teams + atomicAdd(sched, 1u)
+                                  : (uint32_t)blockIdx.x + atomicAdd(&hdr->next, 1u) * (uint32_t)G;
+                ctx.sync();
+                nxt = (int)*grab;
+                have_next = nxt < q.n;
+                if (have_next) {
                     const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)nxt * kStateBytes);
 #pragma unroll
-                    for (int j = 0; j < kPerLane; ++j)
-                        if (lane + kTeam * j < kWords) pre[j] = g[lane + kTeam * j];
+                    for (int w = 0; w < kPerLane; ++w)
+                        if (lane + kTeam * w < kWords) pre[w] = g[lane + kTeam * w];
                     if (lane == 0 && stepping) {
                         const int64_t* a = q.io.actions + (size_t)nxt * q.act_dims;
                         act0 = a[0];
@@ -305,6 +312,9 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
                     }
                 }
             }
+            P::logic(ctx, k, q, view, env, t, *st, a0, a1, *job, fr, scratch);
+            ctx.sync();
+            if (trow && lane == 0) trow[4] = mg_now();
             const int nframes = job->nframes;
             for (int fi = 0; fi < nframes; ++fi) {
                 const Frame& f = fr[fi];  // lives in the team's shared slot until the next logic call
@@ -350,6 +360,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
             if (lane + kTeam * j < kWords) gw[lane + kTeam * j] = s64[lane + kTeam * j];
         ctx.sync();  // record slot is reused by the next env
         env = nxt;
+        have = have_next;
     }
     if (pending && lane == 0) mg_bulk_wait_read();  // shared memory must outlive the bulk read
     team_exit();
@@ -389,8 +400,9 @@ struct MgLaunchPlan {
 
 // grid geometry: one CTA per SM, `wpc` warps = frame buffers each. For rollouts (every warp runs all steps of
 // its envs) the warp count that balances envs per warp best is chosen; for single steps, the most buffers.
-template <class P>
-static int plan_launch(int n, int wpc_req, int default_wpc, bool balance, MgLaunchPlan* out) {
+template <class P, bool kRollout>
+static int plan_launch(int n, int wpc_req, int default_wpc, MgLaunchPlan* out) {
+    const bool balance = kRollout;
     int dev = 0, sms = 0, smem_max = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
         sms <= 0) {
@@ -404,7 +416,7 @@ static int plan_launch(int n, int wpc_req, int default_wpc, bool balance, MgLaun
     const int per_warp = P::kFrameBuf + kSlot + P::kWarpExtra;
     int wmax = 10;
     while (wmax > 1 && wmax * 32 * P::kTeamWarps > P::kMaxThreads) wmax--;
-    while (wmax > 1 && wmax * per_warp + P::kCtaExtra + P::kStageReserve > smem_max) wmax--;  // leave room to stage the assets
+    while (wmax > 1 && wmax * per_warp + P::kCtaExtra + MG_CTA_HDR_BYTES + P::kStageReserve > smem_max) wmax--;  // leave room to stage the assets
     int wpc = wpc_req ? wpc_req : default_wpc;
     if (wpc > wmax) wpc = wmax;
     if (!wpc_req && balance && n > sms * wmax) {
@@ -423,13 +435,13 @@ static int plan_launch(int n, int wpc_req, int default_wpc, bool balance, MgLaun
     if (wpc < 1) wpc = 1;
     int ctas = (n + wpc - 1) / wpc;
     if (ctas > sms) ctas = sms;
-    size_t smem = (size_t)wpc * per_warp + P::kCtaExtra;
+    size_t smem = (size_t)wpc * per_warp + P::kCtaExtra + MG_CTA_HDR_BYTES;
     // what is left of the SM's shared memory (up to 48 KB) stages the asset header + sprite pixel lists
     int stage_cap = smem_max - (int)smem;
     if (stage_cap > 48 * 1024) stage_cap = 48 * 1024;
     stage_cap &= ~127;
     smem += (size_t)stage_cap;
-    cudaError_t e = cudaFuncSetAttribute(mg_env_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mg_env_kernel<P, kRollout>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         mg_set_err(cudaGetErrorString(e));
         cudaGetLastError();
@@ -442,7 +454,7 @@ static int plan_launch(int n, int wpc_req, int default_wpc, bool balance, MgLaun
     return 0;
 }
 
-template <class P>
+template <class P, bool kRollout>
 static int launch_one(const typename P::K& k, const MgKIO& q, const MgLaunchPlan& plan, const void* assets, void* state,
                       void* stream) {
     cudaLaunchConfig_t cfg = {};
@@ -457,7 +469,7 @@ static int launch_one(const typename P::K& k, const MgKIO& q, const MgLaunchPlan
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = getenv("MG_DISABLE_PDL") ? 0 : 1;  // debugging / measurement switch
-    cudaError_t e = cudaLaunchKernelEx(&cfg, mg_env_kernel<P>, k, q, (const uint8_t*)assets, (uint8_t*)state);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mg_env_kernel<P, kRollout>, k, q, (const uint8_t*)assets, (uint8_t*)state);
     if (e != cudaSuccess) {
         mg_set_err(cudaGetErrorString(e));
         cudaGetLastError();
@@ -500,7 +512,7 @@ static int launch_env(const typename P::K& k, const void* assets, void* state, c
     }
     if (n == 0) return 0;
     MgLaunchPlan plan;
-    int rc = plan_launch<P>(n, (int)ios->warps_per_cta, default_wpc, false, &plan);
+    int rc = plan_launch<P, false>(n, (int)ios->warps_per_cta, default_wpc, &plan);
     if (rc) return rc;
     for (int t = 0; t < n_io; ++t) {
         MgKIO q;
@@ -513,7 +525,7 @@ static int launch_env(const typename P::K& k, const void* assets, void* state, c
         q.act_dims = act_dims;
         q.n_steps = 1;
         q.ring_n = 1;
-        rc = launch_one<P>(k, q, plan, assets, state, stream);
+        rc = launch_one<P, false>(k, q, plan, assets, state, stream);
         if (rc) return rc;
     }
     return 0;
@@ -534,7 +546,7 @@ static int launch_rollout(const typename P::K& k, const void* assets, void* stat
     }
     if (n == 0) return 0;
     MgLaunchPlan plan;
-    int rc = plan_launch<P>(n, (int)r->warps_per_cta, default_wpc, true, &plan);
+    int rc = plan_launch<P, true>(n, (int)r->warps_per_cta, default_wpc, &plan);
     if (rc) return rc;
     MgKIO q;
     memset(&q, 0, sizeof(q));
@@ -547,7 +559,7 @@ static int launch_rollout(const typename P::K& k, const void* assets, void* stat
     q.io.ground_truth = r->ground_truth;
     q.io.trace = r->trace;
     q.io.vector_obs = r->vector_obs;
-    q.io.sched = r->sched;
+    q.sched = r->sched;
     q.io.flags = r->flags | MG_FLAG_AUTORESET;  // a rollout without auto-reset would only idle finished envs
     q.mode = MG_MODE_STEP;
     q.n = n;
@@ -560,7 +572,7 @@ static int launch_rollout(const typename P::K& k, const void* assets, void* stat
     q.rew_stride = n;
     q.done_stride = n;
     q.info_stride = r->info_per_step ? (int64_t)n * MG_INFO_COLS : 0;
-    return launch_one<P>(k, q, plan, assets, state, stream);
+    return launch_one<P, true>(k, q, plan, assets, state, stream);
 }
 
 static int mm_act_dims(const mg_mm_params* p) { return mg_mm_is_grid(p->variant) ? 1 : 2; }

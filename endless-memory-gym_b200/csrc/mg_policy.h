@@ -30,6 +30,7 @@ struct MgKIO {
     // reward/done/info rows t (strides in elements; info_stride 0 = one shared info matrix)
     int32_t n_steps, ring_n;
     int64_t act_stride, obs_stride, rew_stride, done_stride, info_stride;
+    uint32_t* sched;  // rollout: global work counter (mg_rollout_io.sched) or nullptr = CTA-local scheduling
 };
 
 struct MgFrameJob {      // what the logic lane hands to the warp: up to two frames for this env-step
@@ -154,7 +155,7 @@ MG_HD void mg_env_logic_coop(Ctx& c, const typename E::K& k, const MgKIO& q, con
 
 struct MMPolicy {
     static constexpr int kWarpExtra = 0, kCtaExtra = 0;
-    static constexpr int kStageReserve = 16 * 1024;  // shared memory kept free for the staged asset prefix
+    static constexpr int kStageReserve = 8 * 1024;  // shared memory kept free for the staged asset prefix (7.4 KB by default)
     static constexpr int kTeamWarps = 1, kMaxThreads = 320;
     static constexpr int kFrameBuf = 21248;      // per-team TMA frame buffer (MG_FRAME_BYTES rounded up to 128)
     static constexpr bool kDirectStore = false;  // frames leave through cp.async.bulk from the frame buffer

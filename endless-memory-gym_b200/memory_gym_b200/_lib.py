@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmemgym_b200.so")
 
-MG_ABI_VERSION = 2
+MG_ABI_VERSION = 3
 MG_OBS_BYTES = 84 * 84 * 3
 MG_INFO_COLS = 10
 MG_GT_COLS = 4
@@ -104,7 +104,6 @@ class StepIO(C.Structure):
         ("actions", C.c_void_p), ("obs", C.c_void_p), ("final_obs", C.c_void_p), ("reward", C.c_void_p),
         ("done", C.c_void_p), ("info", C.c_void_p), ("ground_truth", C.c_void_p), ("reset_mask", C.c_void_p),
         ("flags", C.c_uint32), ("warps_per_cta", C.c_uint32), ("vector_obs", C.c_void_p), ("trace", C.c_void_p),
-        ("sched", C.c_void_p),
     ]
 
 

@@ -140,10 +140,9 @@ class MemoryGymVecEnv:
         self._io.info = self.info.data_ptr()
         self._io.ground_truth = self._gt_full.data_ptr() if self.has_ground_truth_info else None
         self._io.vector_obs = self.vector_obs.data_ptr() if self.task_b else None
-        # dynamic env -> warp scheduling (a warp held up by an auto-reset takes fewer envs): a work counter the
-        # kernels keep at zero between launches. MG_STATIC_SCHED=1 switches it off (measurement knob).
-        self._sched = None if os.environ.get("MG_STATIC_SCHED") else torch.zeros(2, dtype=torch.int32, device=dev)
-        self._io.sched = self._sched.data_ptr() if (self._sched is not None and dev.type == "cuda") else None
+        # rollouts: a global work counter the kernels keep at zero between launches (dynamic env -> warp scheduling
+        # across SMs). MG_LOCAL_SCHED=1 switches it off (measurement knob): every SM works through its own share.
+        self._sched = None if os.environ.get("MG_LOCAL_SCHED") else torch.zeros(2, dtype=torch.int32, device=dev)
         # stream_obs: write observations with an L2 evict-first policy. Default: on for rollout() (frames are
         # not re-read soon; measured +13 % HBM write throughput), off for step() (the policy reads obs next).
         self._stream_step = L.MG_FLAG_STREAM_OBS if stream_obs else 0
@@ -300,10 +299,10 @@ class MemoryGymVecEnv:
         r.info = info_out.data_ptr() if info_out is not None else self._io.info
         r.ground_truth = self._io.ground_truth
         r.vector_obs = self._io.vector_obs
+        r.sched = self._sched.data_ptr() if self._sched is not None else None
         r.n_steps, r.ring, r.info_per_step = T, obs_out.shape[0], int(info_out is not None)
         r.flags, r.warps_per_cta = L.MG_FLAG_AUTORESET | self._stream_rollout, self.warps_per_cta
         r.trace = getattr(self, "_trace_ptr", None)
-        r.sched = self._io.sched
         self._be.rollout(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(), r,
                          self.num_envs, self._be.stream(self.device))
 
@@ -328,7 +327,6 @@ class MemoryGymVecEnv:
                     else self._io.info
                 io.ground_truth = self._io.ground_truth
                 io.vector_obs = self._io.vector_obs
-                io.sched = self._io.sched
                 io.reset_mask = None
                 io.flags = self._io.flags
                 io.warps_per_cta = self._io.warps_per_cta

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 2
+#define MG_ABI_VERSION 3
 
 #define MG_SCREEN 84
 #define MG_OBS_BYTES (84 * 84 * 3) /* 21168 bytes per env, [x][y][c] */
@@ -224,9 +224,6 @@ typedef struct mg_step_io {
     uint64_t* trace;        /* nullable: [n][MG_TRACE_COLS] uint64, per-env phase timestamps (globaltimer ns):   */
                             /* 0 kernel entry, 1 prologue done, 2 dependency wait done, 3 record in smem,      */
                             /* 4 logic done, 5 frame composed, 6 bulk store issued, 7 SM id, 8.. env-type specific  */
-    uint32_t* sched;        /* nullable: [2] uint32, zeroed ONCE by the caller and then owned by the library: work      */
-                            /* counter for dynamic env -> warp scheduling (a warp held up by an auto-reset takes fewer */
-                            /* envs). Results never depend on it. One buffer per stream of launches.                   */
 } mg_step_io;
 
 /* A whole rollout in one launch: T = n_steps consecutive steps with given actions (the reference's bench.py
@@ -248,7 +245,10 @@ typedef struct mg_rollout_io {
     uint32_t pad0;
     uint64_t* trace;        /* nullable: [n][MG_TRACE_COLS] phase timestamps of each env's LAST step (see mg_step_io) */
     float* vector_obs;      /* nullable: [n][MG_MM_B_VECTOR], as in mg_step_io (state after the last step) */
-    uint32_t* sched;        /* nullable: [2] uint32, as in mg_step_io */
+    uint32_t* sched;        /* nullable: [2] uint32, zeroed ONCE by the caller and then owned by the library: a global   */
+                            /* work counter for env -> warp scheduling across SMs (SMs that stream faster take more   */
+                            /* envs). NULL = every SM works through its own share. Results never depend on it. One    */
+                            /* buffer per stream of launches.                                                          */
 } mg_rollout_io;
 
 /* ---- assets & seeding (host side) -------------------------------------------------------------- */

@@ -28,4 +28,4 @@ for _ in range(8):
 e1.record()
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / (8 * T)
-print(f"{env_id} n={n} sched={'dynamic' if env._sched is not None else 'static'}: {us:.2f} us/step = {n / us:.1f} M env-steps/s")
+print(f"{env_id} n={n}: {us:.2f} us/step = {n / us:.1f} M env-steps/s")
