@@ -543,33 +543,19 @@ template <class Ctx>
 MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
                              int spot_li, bool simple) {
     uint8_t* base = wm->base;
-    const MgSSBaseDesc& d = wm->desc;  // read in place; lane 0 rewrites it after the last sync below
     const int half = a.hdr->agent_dim >> 1;
-    bool same_rest = simple && d.valid && d.coin_above == f.coin_above && d.bg_kind == f.bg_kind && d.exit_x == f.exit_x && d.exit_y == f.exit_y &&
-                     d.exit_open == f.exit_open && d.n_coins == f.n_coins;
-    for (int q = 0; same_rest && q < (int)f.n_coins; ++q)
-        same_rest = d.coins[q][0] == f.coins[q][0] && d.coins[q][1] == f.coins[q][1];
-    const bool same_agent = d.sx == f.sx && d.sy == f.sy && d.srot == f.srot;
-    if (same_rest) {
-        if (!same_agent) {
-            // only the agent moved: put back what it covered, then draw it at its new pose
-            const MgSprite sp = a.hdr->sprite[MG_SPR_AGENT0 + d.srot];
-            const uint32_t* e = a.entries + sp.first;
-            for (int i = c.lane; i < (int)sp.count; i += c.nl) {
-                uint32_t v = e[i];
-                int x = d.sx - half + (int)(v & 255u), y = d.sy - half + (int)((v >> 8) & 255u);
-                if ((unsigned)x < (unsigned)MG_W && (unsigned)y < (unsigned)MG_W)
-                    mg_put_px(base, x, y, mg_ss_under_no_agent(a, k, f, spot_li, x, y));
-            }
-            c.sync();
-            mg_sprite_draw(c, base, a, MG_SPR_AGENT0 + f.srot, f.sx - half, f.sy - half);
-            c.sync();
-        }
-        mg_ss_draw_bar(c, base, k, f);  // the bar changes every step and sits on top
-        c.sync();
-    } else {
-        mg_ss_rebuild_base(c, base, a, k, f);
+    bool same_rest, same_agent;
+    int osx, osy, osrot;  // pose of the agent `base` shows
+    {
+        const MgSSBaseDesc& d = wm->desc;
+        same_rest = simple && d.valid && d.coin_above == f.coin_above && d.bg_kind == f.bg_kind && d.exit_x == f.exit_x &&
+                    d.exit_y == f.exit_y && d.exit_open == f.exit_open && d.n_coins == f.n_coins;
+        for (int q = 0; same_rest && q < (int)f.n_coins; ++q)
+            same_rest = d.coins[q][0] == f.coins[q][0] && d.coins[q][1] == f.coins[q][1];
+        osx = d.sx, osy = d.sy, osrot = d.srot;
+        same_agent = osx == f.sx && osy == f.sy && osrot == f.srot;
     }
+    c.sync();  // every thread has read the description: lane 0 may rewrite it (nobody reads it again this frame)
     if (c.lane == 0) {
         MgSSBaseDesc& w = wm->desc;
         w.valid = 1;
@@ -580,7 +566,74 @@ MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, cons
         w.coin_above = f.coin_above;
         for (int q = 0; q < (int)f.n_coins; ++q) w.coins[q][0] = f.coins[q][0], w.coins[q][1] = f.coins[q][1];
     }
-    c.sync();
+    if (!same_rest) {
+        mg_ss_rebuild_base(c, base, a, k, f);
+        return;
+    }
+    // Only the agent moved and the bar changed. In the `simple` order the layers under the spotlights are coins <
+    // exit < agent and the bar lies on top of everything, so three sets of pixels are written, pairwise disjoint —
+    // no ordering between them, the caller's sync before the copy is the only one needed:
+    //   (1) pixels of the old agent that the new agent does not cover: what lies underneath (exit, coins, background)
+    //   (2) the new agent        — both without rows y < 4: those belong to
+    //   (3) the top bar
+    if (!same_agent) {
+        if (f.coin_black) {  // an opaque coin layer under the agent (Endless, coin disabled): the generic way
+            const MgSprite sp = a.hdr->sprite[MG_SPR_AGENT0 + osrot];
+            const uint32_t* e = a.entries + sp.first;
+            for (int i = c.lane; i < (int)sp.count; i += c.nl) {
+                uint32_t v = e[i];
+                int x = osx - half + (int)(v & 255u), y = osy - half + (int)((v >> 8) & 255u);
+                if ((unsigned)x < (unsigned)MG_W && (unsigned)y < (unsigned)MG_W)
+                    mg_put_px(base, x, y, mg_ss_under_no_agent(a, k, f, spot_li, x, y));
+            }
+            c.sync();
+            mg_sprite_draw(c, base, a, MG_SPR_AGENT0 + f.srot, f.sx - half, f.sy - half);
+            c.sync();
+        } else {
+            const uint32_t* pal = reinterpret_cast<const uint32_t*>(a.palette);
+            // sprite boxes and dense bitmaps, hoisted out of the pixel loop (byte stores alias everything)
+            const int eslot = f.exit_open ? MG_SPR_EXIT_OPEN : MG_SPR_EXIT_CLOSED;
+            const MgSprite esp = a.hdr->sprite[eslot], csp = a.hdr->sprite[MG_SPR_COIN];
+            const MgSprite osp = a.hdr->sprite[MG_SPR_AGENT0 + osrot], nsp = a.hdr->sprite[MG_SPR_AGENT0 + f.srot];
+            const uint8_t* edense = a.base + a.hdr->dense_off[eslot];
+            const uint8_t* cdense = a.base + a.hdr->dense_off[MG_SPR_COIN];
+            const uint8_t* ndense = a.base + a.hdr->dense_off[MG_SPR_AGENT0 + f.srot];
+            const int ex0 = f.exit_x - (esp.w >> 1), ey0 = f.exit_y - (esp.h >> 1);
+            const int nx0 = f.sx - half, ny0 = f.sy - half, ox0 = osx - half, oy0 = osy - half;
+            const int ncoins = f.n_coins, bg_kind = f.bg_kind;
+            const uint32_t* eo = a.entries + osp.first;
+            for (int i = c.lane; i < (int)osp.count; i += c.nl) {
+                const uint32_t v = eo[i];
+                const int x = ox0 + (int)(v & 255u), y = oy0 + (int)((v >> 8) & 255u);
+                if ((unsigned)x >= (unsigned)MG_W || (unsigned)(y - 4) >= (unsigned)(MG_W - 4)) continue;
+                unsigned u = (unsigned)(x - nx0), w = (unsigned)(y - ny0);
+                if (u < (unsigned)nsp.w && w < (unsigned)nsp.h && ndense[w * nsp.w + u] != 255) continue;  // (2) covers it
+                uint32_t col = mg_ss_bg(bg_kind, x, y);
+                bool found = false;
+                u = (unsigned)(x - ex0), w = (unsigned)(y - ey0);
+                if (u < (unsigned)esp.w && w < (unsigned)esp.h) {
+                    const uint8_t pi = edense[w * esp.w + u];
+                    if (pi != 255) col = pal[pi] & 0x00FFFFFFu, found = true;
+                }
+                for (int q = ncoins - 1; q >= 0 && !found; --q) {  // the coin drawn last wins
+                    u = (unsigned)(x - (f.coins[q][0] - (csp.w >> 1))), w = (unsigned)(y - (f.coins[q][1] - (csp.h >> 1)));
+                    if (u < (unsigned)csp.w && w < (unsigned)csp.h) {
+                        const uint8_t pi = cdense[w * csp.w + u];
+                        if (pi != 255) col = pal[pi] & 0x00FFFFFFu, found = true;
+                    }
+                }
+                mg_put_px(base, x, y, col);
+            }
+            const uint32_t* en = a.entries + nsp.first;
+            for (int i = c.lane; i < (int)nsp.count; i += c.nl) {
+                const uint32_t v = en[i];
+                const int x = nx0 + (int)(v & 255u), y = ny0 + (int)((v >> 8) & 255u);
+                if ((unsigned)x >= (unsigned)MG_W || (unsigned)(y - 4) >= (unsigned)(MG_W - 4)) continue;
+                mg_put_px(base, x, y, pal[(v >> 16) & (MG_MAX_PALETTE - 1)]);
+            }
+        }
+    }
+    mg_ss_draw_bar(c, base, k, f);  // the bar changes every step and sits on top
 }
 
 // lit = pixel bits (index 84 * x + y, the frame's own order) covered by a spotlight disc drawn this step, on top
@@ -588,15 +641,22 @@ MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, cons
 // with shared-memory atomics (a run of <= 80 bits touches at most 4 words).
 template <class Ctx>
 MG_HD void mg_ss_build_lit(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const MgSSFrame& f, const uint32_t* init) {
-    for (int w = c.lane; w < MG_SS_LIT_WORDS; w += c.nl) wm->lit[w] = init ? init[w] : 0u;
+    {
+        MgVec16* l16 = reinterpret_cast<MgVec16*>(wm->lit);
+        const MgVec16* i16 = reinterpret_cast<const MgVec16*>(init);
+        const MgVec16 zero = {0u, 0u, 0u, 0u};
+        for (int w = c.lane; w < MG_SS_LIT_WORDS / 4; w += c.nl) l16[w] = init ? i16[w] : zero;
+    }
     c.sync();
     const int8_t* cols_all = (const int8_t*)(a.base + a.hdr->disc_off) + 2 * MG_MAX_DISC_R * (MG_MAX_DISC_R + 1);
-    for (int d = 0; d < (int)f.n_discs; ++d) {
+    // the team's warps take alternate discs; within a warp one lane per disc column
+    const int width = c.nl < 32 ? c.nl : 32, subs = c.nl / width, sub = c.lane / width, col0 = c.lane - sub * width;
+    for (int d = sub; d < (int)f.n_discs; d += subs) {
         const int r = f.disc_r[d], x0 = f.disc_x[d], y0 = f.disc_y[d];
         if (r < 1) continue;
         const int8_t* cols = cols_all + 2 * r * (r - 1);
         int xa = x0 - r < 0 ? 0 : x0 - r, xb = x0 + r > MG_W ? MG_W : x0 + r;
-        for (int x = xa + c.lane; x < xb; x += c.nl) {
+        for (int x = xa + col0; x < xb; x += width) {
             int ci = x - x0 + r;
             int ylo = y0 + (int)cols[2 * ci], yhi = y0 + (int)cols[2 * ci + 1];
             if (ylo < 0) ylo = 0;
@@ -609,6 +669,39 @@ MG_HD void mg_ss_build_lit(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const 
                 if (bh > 31) bh = 31;
                 c.atomic_or(&wm->lit[w], (0xFFFFFFFFu >> (31 - (bh - bl))) << bl);
             }
+        }
+    }
+}
+
+// The steady state of an episode (alpha == 255: dimmed = black): frame = base & mask(lit). One lane takes a GROUP of
+// three chunks = 48 bytes = exactly 16 pixels, so its lit bits are one aligned half-word of the flat bitmap and the
+// three chunk phases (0, 1, 2 bytes into a pixel) are compile-time: no index arithmetic, no funnel shift.
+template <class Ctx>
+MG_HD void mg_ss_masked_copy_black(Ctx& c, uint8_t* out, const MgSSWarpMem* wm, const MgSSCtaTables* t, bool stream) {
+    const MgVec16* src = reinterpret_cast<const MgVec16*>(wm->base);
+    MgVec16* dst = reinterpret_cast<MgVec16*>(out);
+    const uint16_t* lit16 = reinterpret_cast<const uint16_t*>(wm->lit);
+    constexpr int kGroups = MG_SS_CHUNKS / 3;  // 441
+    static_assert(MG_SS_CHUNKS % 3 == 0, "a frame is a whole number of 16-pixel groups");
+    for (int g0 = c.lane; g0 < kGroups; g0 += 2 * c.nl) {  // two groups per lane in flight: loads first, then stores
+        MgVec16 o[2][3];
+        MG_UNROLL
+        for (int u = 0; u < 2; ++u) {
+            const int g = g0 + u * c.nl;
+            if (g >= kGroups) break;
+            const uint32_t b = lit16[g];
+            MG_UNROLL
+            for (int ph = 0; ph < 3; ++ph) {
+                const MgVec16 m = t->mask[ph][(b >> (5 * ph)) & 63u], v = src[3 * g + ph];
+                o[u][ph].x = v.x & m.x, o[u][ph].y = v.y & m.y, o[u][ph].z = v.z & m.z, o[u][ph].w = v.w & m.w;
+            }
+        }
+        MG_UNROLL
+        for (int u = 0; u < 2; ++u) {
+            const int g = g0 + u * c.nl;
+            if (g >= kGroups) break;
+            MG_UNROLL
+            for (int ph = 0; ph < 3; ++ph) c.store16(dst + 3 * g + ph, o[u][ph], stream);
         }
     }
 }
@@ -761,7 +854,7 @@ MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDraw
     // 3. frame = lit ? base : base dimmed by alpha (SDL: d + trunc((0 - d) * A / 255))
     c.stamp(10);
     if (f.alpha == 255)
-        mg_ss_masked_copy_t<false>(c, out, wm, tables, stream);
+        mg_ss_masked_copy_black(c, out, wm, tables, stream);
     else
         mg_ss_masked_copy_cold(c, out, wm, tables, f.alpha, stream);
     c.stamp(11);

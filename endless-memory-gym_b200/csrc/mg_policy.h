@@ -360,6 +360,7 @@ struct SSPolicyT {
             }
         }
         c.sync();
+        c.stamp(12);
         if (tmp.action == 1) {
             if (c.lane == 0) wm->desc.valid = 0;
             if constexpr (kEndless)
@@ -376,6 +377,7 @@ struct SSPolicyT {
         if (tmp.action != 2) return;
         mg_ss_step_b(c, k, trig(a), s, tmp, fr[0]);
         c.sync();
+        c.stamp(13);
         MgESSCarry carry;  // lane 0's registers carry C1's results to C2
         if constexpr (kEndless) {
             if (c.lane == 0 && mg_ess_step_c1(k, s, tmp, carry)) {
@@ -403,6 +405,7 @@ struct SSPolicyT {
             }
         }
         c.sync();
+        c.stamp(14);
         if (tmp.action == 3) {
             // the terminal frame (if requested) must leave before the base buffer is borrowed by the sampler:
             // it is emitted here, out of order with respect to the generic frame loop

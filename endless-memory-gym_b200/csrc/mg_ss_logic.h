@@ -118,23 +118,29 @@ MG_HD void mg_ss_clamp_spawn(const MgSSK& k, int& x, int& y) {
 }
 
 MG_HD void mg_ss_frame_common(const MgSSState& s, int srot, MgSSFrame& f) {
+    // every load first, then the stores: record and frame share field types, so the compiler may not reorder
+    // them on its own and a single lane would pay one shared-memory round trip per field
+    const int16_t cx = s.cx, cy = s.cy, exit_x = s.exit_x, exit_y = s.exit_y, red_w_max = s.red_w_max;
+    const uint8_t exit_open = s.exit_open, alpha = s.alpha, bar_c0 = s.bar_c0, bar_c1 = s.bar_c1, coin_bar = s.coin_bar;
+    const int nc = s.n_coins;
     f.coin_above = 0;
     f.coin_black = 0;
-    f.sx = s.cx;
-    f.sy = s.cy;
+    f.sx = cx;
+    f.sy = cy;
     f.srot = (uint8_t)srot;
-    f.exit_x = s.exit_x;
-    f.exit_y = s.exit_y;
-    f.exit_open = s.exit_open;
-    f.alpha = s.alpha;
-    f.red_w_max = s.red_w_max;
-    f.bar_c0 = s.bar_c0;
-    f.bar_c1 = s.bar_c1;
-    f.coin_bar = s.coin_bar;
-    f.n_coins = s.n_coins;
-    for (int c = 0; c < (int)s.n_coins; ++c) {
-        f.coins[c][0] = s.coins[c][0];
-        f.coins[c][1] = s.coins[c][1];
+    f.exit_x = exit_x;
+    f.exit_y = exit_y;
+    f.exit_open = exit_open;
+    f.alpha = alpha;
+    f.red_w_max = red_w_max;
+    f.bar_c0 = bar_c0;
+    f.bar_c1 = bar_c1;
+    f.coin_bar = coin_bar;
+    f.n_coins = (uint8_t)nc;
+    for (int c = 0; c < nc; ++c) {
+        const int16_t x = s.coins[c][0], y = s.coins[c][1];
+        f.coins[c][0] = x;
+        f.coins[c][1] = y;
     }
 }
 

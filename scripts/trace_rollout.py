@@ -32,7 +32,8 @@ print(f"launch: {e0.elapsed_time(e1) * 1e3:.1f} us for {T} steps x {n} envs = {e
 b = trace.cpu().numpy().astype(np.int64)
 for nm, i0, i1 in (("step start -> logic done", 3, 4), ("logic done -> emit start", 4, 5), ("emit (or compose->issue)", 5, 6),
                    ("emit: update base", 8, 9), ("emit: lit + lut", 9, 10), ("emit: masked copy", 10, 11),
-                   ("reset: path generation", 12, 13), ("reset: rest", 13, 14)):
+                   ("12->13 (EP reset: path generation | SS: spotlights B)", 12, 13),
+                   ("13->14 (EP reset: rest | SS: logic C)", 13, 14), ("3->12 (SS: logic A)", 3, 12)):
     if b[:, i0].any() and b[:, i1].any():
         sel = (b[:, i0] > 0) & (b[:, i1] > 0)
         d = (b[sel, i1] - b[sel, i0]) / 1e3
