@@ -144,7 +144,7 @@ MG_HD void mg_ep_ground_truth(const MgEPState& s, double* gt) {
 MG_HD int mg_ep_floordiv12(int v) { return v >= 0 ? v / 12 : -((11 - v) / 12); }
 
 // frame description: _draw_surfaces + _draw_past_path (:111-160)
-MG_HD_NOINLINE void mg_ep_frame(const MgEPK& k, const MgEPState& s, int bar_h, MgEPFrame& f) {
+MG_HD void mg_ep_frame(const MgEPK& k, const MgEPState& s, int bar_h, MgEPFrame& f) {
     f.sx = k.agent_draw_x;
     f.sy = s.cy - k.agent_half;
     f.srot = s.rot;
@@ -183,7 +183,7 @@ MG_HD int mg_ep_bar_height(int stamina, int max_visible, bool at_reset) {
 }
 
 template <class Ctx>
-MG_HD_NOINLINE void mg_ep_reset_coop(Ctx c, const MgEPK& k, MgEPState& s, MgEPFrame& f, double* gt, MgGenMem& m,
+MG_HD void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, double* gt, MgGenMem& m,
                                      const MgGenCta& tab) {
     c.stamp(12);
     if (c.lane == 0) {
@@ -226,7 +226,7 @@ MG_HD_NOINLINE void mg_ep_reset_coop(Ctx c, const MgEPK& k, MgEPState& s, MgEPFr
 
 // step(), first half (one lane): the move. Returns true when the path needs another segment before the second
 // half runs (the warp then generates it cooperatively).
-MG_HD_NOINLINE bool mg_ep_step_pre(const MgEPK& k, MgEPState& s, int action) {
+MG_HD bool mg_ep_step_pre(const MgEPK& k, MgEPState& s, int action) {
     const int start_y = mg_ep_start_y(s.seg[0]);
     if (!s.off_path) {
         // Discrete(4) -> [0,0], [2,0], [0,1], [0,2] (:283-291); CharacterController.step, no boundary
@@ -256,7 +256,7 @@ MG_HD_NOINLINE bool mg_ep_step_pre(const MgEPK& k, MgEPState& s, int action) {
 }
 
 // step(), second half (one lane). `capped`: a segment was needed but the record is full
-MG_HD_NOINLINE bool mg_ep_step_post(const MgEPK& k, MgEPState& s, bool capped, double& reward_out, double* info,
+MG_HD bool mg_ep_step_post(const MgEPK& k, MgEPState& s, bool capped, double& reward_out, double* info,
                                     MgEPFrame& f, double* gt) {
     double reward = 0.0;
     bool done = false;

@@ -110,7 +110,7 @@ MG_HD int mg_mm_show_entry(const MgMMState& s, int e) {
 }
 
 // reset(): RNG draw order is part of the contract (mortar_mayhem.py:238,174,150-183,247-248,262-263)
-MG_HD_NOINLINE void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, double* gt) {
+MG_HD void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, double* gt) {
     const int size = k.size;
     const bool endless = k.p.variant == MG_MM_ENDLESS;
     MgRngR r = mg_rr_load(s.rng);  // the stream stays in registers for the whole reset

@@ -281,7 +281,7 @@ MG_HD void mg_mp_draw(const MgMPK& k, const MgMPState& s, int cross, MgMPDraw& d
 
 // reset(): called by every lane of the warp (uniform draws on a register copy of the stream, lane 0 writes)
 template <class Ctx>
-MG_HD_NOINLINE void mg_mp_reset_coop(Ctx c, const MgMPK& k, MgMPState& s, MgMPDraw& d, MgGenMem& m, const MgGenCta& tab) {
+MG_HD void mg_mp_reset_coop(Ctx& c, const MgMPK& k, MgMPState& s, MgMPDraw& d, MgGenMem& m, const MgGenCta& tab) {
     const int g = MG_MP_CELLS;
     MgRngR r = mg_rr_load(s.rng);
     const int side = mg_rr_choice(r, k.p.cardinal_origin_choice);

@@ -41,13 +41,17 @@ struct MgFrameJob {      // what the logic lane hands to the warp: up to two fra
 // One env, one call: reset (mode RESET) or step (+ auto-reset) — the same control flow for every env type.
 // `E` supplies reset_env / step_env. a0/a1 are this env's (prefetched) action components.
 template <class E>
-MG_HDN void mg_env_logic(const typename E::K& k, const MgKIO& q, const MgAssetView& a, int env, int t,
+MG_HD void mg_env_logic(const typename E::K& k, const MgKIO& q, const MgAssetView& a, int env, int t,
                          typename E::State& s, int a0, int a1, MgFrameJob& job, typename E::Frame* fr) {
     double* const reward_out = q.io.reward + (size_t)t * q.rew_stride + env;
     uint8_t* const done_out = q.io.done + (size_t)t * q.done_stride + env;
     double* const info_out = q.io.info + (size_t)t * q.info_stride + MG_INFO_COLS * (size_t)env;
     double* gt = q.io.ground_truth ? q.io.ground_truth + MG_GT_COLS * (size_t)env : nullptr;
     job.nframes = 0;
+    // ONE call site for the reset (a fresh episode or the auto-reset of a finished one): the reset is inlined, so the
+    // option block `k` is read through constant-bank operands instead of a pointer into parameter space
+    bool reset_now = false;
+    int at = 0;
     if (q.mode == MG_MODE_RESET) {
         if (q.io.reset_mask && !q.io.reset_mask[env]) return;
         if (q.rng4) {  // env.reset(seed=s): a fresh PCG64 stream
@@ -59,29 +63,26 @@ MG_HDN void mg_env_logic(const typename E::K& k, const MgKIO& q, const MgAssetVi
             s.rng.buf = 0;
             s.rng.has_buf = 0;
         }
-        E::reset_env(k, a, s, fr[0], gt);
-        job.nframes = 1;
-        job.to_final[0] = 0;
-        return;
-    }
-    if (!s.live) {  // finished (or never reset): the step is ignored
+        reset_now = true;
+    } else if (!s.live) {  // finished (or never reset): the step is ignored
         *reward_out = 0.0;
         *done_out = 1;
         return;
-    }
-    double reward;
-    bool done = E::step_env(k, a, s, a0, a1, reward, info_out, fr[0], gt);
-    *reward_out = reward;
-    *done_out = done ? 1 : 0;
-    job.nframes = 1;
-    job.to_final[0] = 0;
-    if (done && (q.io.flags & MG_FLAG_AUTORESET)) {
-        int at = 0;
-        if (q.io.final_obs) {  // terminal frame -> final_obs, first frame of the next episode -> obs
-            job.to_final[0] = 1;
-            at = 1;
+    } else {
+        double reward;
+        bool done = E::step_env(k, a, s, a0, a1, reward, info_out, fr[0], gt);
+        *reward_out = reward;
+        *done_out = done ? 1 : 0;
+        job.nframes = 1;
+        job.to_final[0] = 0;
+        if (done && (q.io.flags & MG_FLAG_AUTORESET)) {
+            if (q.io.final_obs) at = 1;  // terminal frame -> final_obs, first frame of the next episode -> obs
+            reset_now = true;
         }
+    }
+    if (reset_now) {
         E::reset_env(k, a, s, fr[at], gt);
+        job.to_final[0] = at;
         job.to_final[at] = 0;
         job.nframes = at + 1;
     }
@@ -132,20 +133,16 @@ MG_HD void mg_env_logic_coop(Ctx& c, const typename E::K& k, const MgKIO& q, con
     c.sync();
     const int action = m.action;
     if (action == 0) return;
-    if (action == 1) {
-        E::reset_coop(c, k, a, s, fr[0], gt, sc);
-        if (c.lane == 0) {
-            job.nframes = 1;
-            job.to_final[0] = 0;
-        }
-        return;
-    }
-    const bool done = E::step_coop(c, k, a, s, a0, a1, reward_out, done_out, info_out, fr[0], gt, sc);
+    bool reset_now = action == 1;
     int at = 0;
-    if (done && (q.io.flags & MG_FLAG_AUTORESET)) {
-        if (q.io.final_obs) at = 1;  // terminal frame -> final_obs, first frame of the next episode -> obs
-        E::reset_coop(c, k, a, s, fr[at], gt, sc);
+    if (action == 2) {
+        const bool done = E::step_coop(c, k, a, s, a0, a1, reward_out, done_out, info_out, fr[0], gt, sc);
+        if (done && (q.io.flags & MG_FLAG_AUTORESET)) {
+            if (q.io.final_obs) at = 1;  // terminal frame -> final_obs, first frame of the next episode -> obs
+            reset_now = true;
+        }
     }
+    if (reset_now) E::reset_coop(c, k, a, s, fr[at], gt, sc);  // the one (inlined) call site
     if (c.lane == 0) {
         job.to_final[0] = at;
         job.to_final[at] = 0;
@@ -361,55 +358,44 @@ struct SSPolicyT {
         }
         c.sync();
         c.stamp(12);
-        if (tmp.action == 1) {
-            if (c.lane == 0) wm->desc.valid = 0;
-            if constexpr (kEndless)
-                mg_ess_reset_env(c, k, s, fr[0], g, rt, gt);
-            else
-                mg_ss_reset_env(c, k, s, fr[0], g, rt);
+        if (tmp.action == 2) {
+            mg_ss_step_b(c, k, trig(a), s, tmp, fr[0]);
+            c.sync();
+            c.stamp(13);
+            MgESSCarry carry;  // lane 0's registers carry C1's results to C2
+            if constexpr (kEndless) {
+                if (c.lane == 0 && mg_ess_step_c1(k, s, tmp, carry)) {
+                    tmp.action = 4;  // coin collected: the team respawns it on the (now invalid) base buffer
+                    wm->desc.valid = 0;
+                }
+                c.sync();
+                if (tmp.action == 4) mg_ess_spawn_coin(c, k.clamp_off, s, g, rt, true);
+            }
             if (c.lane == 0) {
+                double reward;
+                bool done;
+                if constexpr (kEndless)
+                    done = mg_ess_step_c2(k, s, tmp, carry, reward, info_out, fr[0], gt);
+                else
+                    done = mg_ss_step_c(k, s, tmp, reward, info_out, fr[0]);
+                *reward_out = reward;
+                *done_out = done ? 1 : 0;
                 job.nframes = 1;
                 job.to_final[0] = 0;
+                tmp.action = 0;
+                if (done && (q.io.flags & MG_FLAG_AUTORESET)) {
+                    tmp.action = 3;  // auto-reset: every lane joins the cooperative reset below
+                    if (q.io.final_obs) job.to_final[0] = 1;  // terminal frame -> final_obs, next episode's first -> obs
+                }
             }
             c.sync();
-            return;
+            c.stamp(14);
         }
-        if (tmp.action != 2) return;
-        mg_ss_step_b(c, k, trig(a), s, tmp, fr[0]);
-        c.sync();
-        c.stamp(13);
-        MgESSCarry carry;  // lane 0's registers carry C1's results to C2
-        if constexpr (kEndless) {
-            if (c.lane == 0 && mg_ess_step_c1(k, s, tmp, carry)) {
-                tmp.action = 4;  // coin collected: the team respawns it on the (now invalid) base buffer
-                wm->desc.valid = 0;
-            }
-            c.sync();
-            if (tmp.action == 4) mg_ess_spawn_coin(c, k, s, g, rt, true);
-        }
-        if (c.lane == 0) {
-            double reward;
-            bool done;
-            if constexpr (kEndless)
-                done = mg_ess_step_c2(k, s, tmp, carry, reward, info_out, fr[0], gt);
-            else
-                done = mg_ss_step_c(k, s, tmp, reward, info_out, fr[0]);
-            *reward_out = reward;
-            *done_out = done ? 1 : 0;
-            job.nframes = 1;
-            job.to_final[0] = 0;
-            tmp.action = 0;
-            if (done && (q.io.flags & MG_FLAG_AUTORESET)) {
-                tmp.action = 3;  // auto-reset: every lane joins the cooperative reset below
-                if (q.io.final_obs) job.to_final[0] = 1;  // terminal frame -> final_obs, next episode's first -> obs
-            }
-        }
-        c.sync();
-        c.stamp(14);
-        if (tmp.action == 3) {
-            // the terminal frame (if requested) must leave before the base buffer is borrowed by the sampler:
-            // it is emitted here, out of order with respect to the generic frame loop
-            const int at = q.io.final_obs ? 1 : 0;
+        // ONE (inlined) call site for the reset: a fresh episode (1) or the auto-reset of a finished one (3)
+        if (tmp.action == 1 || tmp.action == 3) {
+            // auto-reset: the terminal frame (if requested) must leave before the base buffer is borrowed by the
+            // sampler: it is emitted here, out of order with respect to the generic frame loop
+            const int at = (tmp.action == 3 && q.io.final_obs) ? 1 : 0;
             if (at) {
                 emit_cold(c, q.io.final_obs + (size_t)env * MG_FRAME_BYTES, a, k, fr[0], sc);
                 c.sync();
@@ -420,7 +406,7 @@ struct SSPolicyT {
             else
                 mg_ss_reset_env(c, k, s, fr[at], g, rt);
             if (c.lane == 0) {
-                // frame 0 (terminal) has already been written: hand only the reset frame to the frame loop
+                // a terminal frame has already been written: hand only the reset frame to the frame loop
                 if (at) fr[0] = fr[1];
                 job.to_final[0] = 0;
                 job.nframes = 1;

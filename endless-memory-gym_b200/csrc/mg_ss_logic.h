@@ -55,9 +55,10 @@ MG_HD int mg_popc64(uint64_t v) {
 
 // ---- spotlights -------------------------------------------------------------------------------------
 // Spotlight.__init__: radius, speed, then the three angle draws
-MG_HD_NOINLINE void mg_ss_new_spot(const MgSSK& k, MgRng& r, MgSSSpot& sp) {
-    sp.radius = (uint8_t)mg_integers(r, k.spot_rlo, k.spot_rhi);
-    sp.speed = mg_uniform(r, k.p.spot_min_speed, k.p.spot_max_speed);
+// (the option values arrive by value: an out-of-line function would read them through a pointer into parameter space)
+MG_HD_NOINLINE void mg_ss_new_spot_v(int rlo, int rhi, double smin, double smax, MgRng& r, MgSSSpot& sp) {
+    sp.radius = (uint8_t)mg_integers(r, rlo, rhi);
+    sp.speed = mg_uniform(r, smin, smax);
     sp.t = 0.0;
     sp.done = 0;
     int start = (int)mg_integers(r, 0, 360);
@@ -66,6 +67,10 @@ MG_HD_NOINLINE void mg_ss_new_spot(const MgSSK& k, MgRng& r, MgSSSpot& sp) {
     sp.a_start = (uint16_t)mg_pymod(start, 360);
     sp.a_target = (uint16_t)mg_pymod(target, 360);
     sp.a_offset = (uint16_t)mg_pymod(offset, 360);
+}
+
+MG_HD void mg_ss_new_spot(const MgSSK& k, MgRng& r, MgSSSpot& sp) {
+    mg_ss_new_spot_v(k.spot_rlo, k.spot_rhi, k.p.spot_min_speed, k.p.spot_max_speed, r, sp);
 }
 
 // centre + Vector2(spawn_radius, 0).rotate(angle)
@@ -105,8 +110,7 @@ MG_HD bool mg_ss_advance_spot(const MgSSK& k, const double* trig, MgSSSpot& sp, 
     return mg_within(dx * dx + dy * dy, (int)sp.radius + k.radius);
 }
 
-MG_HD void mg_ss_clamp_spawn(const MgSSK& k, int& x, int& y) {
-    const int o = k.clamp_off;
+MG_HD void mg_ss_clamp_spawn(int o, int& x, int& y) {
     if (x < o)
         x = o;
     else if (x > MG_W - o)
@@ -245,7 +249,7 @@ MG_HD_NOINLINE void mg_ss_sample_coop(Ctx c, MgSSSampler& g, MgSSState& s, MgSSR
 // num_coins; per coin cell + 2 offsets; exit cell + 2 offsets (searing_spotlights.py:354-414).
 // Called by every lane of the warp; `g` / `rt` are per-warp scratch.
 template <class Ctx>
-MG_HD_NOINLINE void mg_ss_reset_env(Ctx c, const MgSSK& k, MgSSState& s, MgSSFrame& f, MgSSSampler& g, MgSSResetTmp& rt) {
+MG_HD void mg_ss_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, MgSSSampler& g, MgSSResetTmp& rt) {
     for (int y = c.lane; y < MG_W; y += c.nl) g.lo[y] = g.hi[y] = 0;
     if (c.lane == 0) {
         s.t = 0;
@@ -296,7 +300,7 @@ MG_HD_NOINLINE void mg_ss_reset_env(Ctx c, const MgSSK& k, MgSSState& s, MgSSFra
         if (c.lane == 0 && rt.ok) {
             int x = rt.x + (int)mg_integers(s.rng, 2, 4);
             int y = rt.y + (int)mg_integers(s.rng, 2, 4);
-            mg_ss_clamp_spawn(k, x, y);
+            mg_ss_clamp_spawn(k.clamp_off, x, y);
             if (q < nc) {
                 s.coins[s.n_coins][0] = (int16_t)x;
                 s.coins[s.n_coins][1] = (int16_t)y;
@@ -331,7 +335,7 @@ struct MgSSStepTmp {
 };
 
 // A: agent move, top-bar bookkeeping, light dimming, spawn, and WHICH spotlights are drawn this step
-MG_HD_NOINLINE void mg_ss_step_a(const MgSSK& k, MgSSState& s, int a0, int a1, MgSSStepTmp& tmp) {
+MG_HD void mg_ss_step_a(const MgSSK& k, MgSSState& s, int a0, int a1, MgSSStepTmp& tmp) {
     int cx = s.cx, cy = s.cy, rot = s.rot;
     // walkable_rect = (0, 16 * SCALE, 84, 84 - 16 * SCALE)
     mg_move_clamped(cx, cy, rot, a0, a1, k.step_axis, k.step_diag, k.radius, 0, 4, MG_W, MG_W);
@@ -390,7 +394,7 @@ MG_HD void mg_ss_step_b(Ctx& c, const MgSSK& k, const double* trig, MgSSState& s
 }
 
 // C: health, coins, exit, done, episode statistics, frame description
-MG_HD_NOINLINE bool mg_ss_step_c(const MgSSK& k, MgSSState& s, const MgSSStepTmp& tmp, double& reward_out, double* info,
+MG_HD bool mg_ss_step_c(const MgSSK& k, MgSSState& s, const MgSSStepTmp& tmp, double& reward_out, double* info,
                                  MgSSFrame& f) {
     const int cx = tmp.cx, cy = tmp.cy, rot = s.rot, nd = tmp.n_proc;
     double reward = 0.0;
@@ -520,7 +524,7 @@ MG_HD void mg_ess_ground_truth(const MgSSK& k, const MgSSState& s, double* gt) {
 
 // _spawn_coin (:256-269): fresh sampler, only the OLD coin's surroundings blocked, sample(28) + two offsets
 template <class Ctx>
-MG_HD_NOINLINE void mg_ess_spawn_coin(Ctx c, const MgSSK& k, MgSSState& s, MgSSSampler& g, MgSSResetTmp& rt, bool have_old) {
+MG_HD_NOINLINE void mg_ess_spawn_coin(Ctx c, int clamp_off, MgSSState& s, MgSSSampler& g, MgSSResetTmp& rt, bool have_old) {
     for (int y = c.lane; y < MG_W; y += c.nl) g.lo[y] = g.hi[y] = 0;
     if (c.lane == 0) rt.ok = 1;
     c.sync();
@@ -532,7 +536,7 @@ MG_HD_NOINLINE void mg_ess_spawn_coin(Ctx c, const MgSSK& k, MgSSState& s, MgSSS
     if (c.lane == 0) {
         int x = rt.x + (int)mg_integers(s.rng, 2, 4);
         int y = rt.y + (int)mg_integers(s.rng, 2, 4);
-        mg_ss_clamp_spawn(k, x, y);
+        mg_ss_clamp_spawn(clamp_off, x, y);
         s.coins[0][0] = (int16_t)x;
         s.coins[0][1] = (int16_t)y;
         s.n_coins = 1;
@@ -543,7 +547,7 @@ MG_HD_NOINLINE void mg_ess_spawn_coin(Ctx c, const MgSSK& k, MgSSState& s, MgSSS
 // reset(): RNG draw order — rotation; agent cell + 2 offsets; per initial spotlight radius, speed, 3 angles;
 // coin cell + 2 offsets (:294-407)
 template <class Ctx>
-MG_HD_NOINLINE void mg_ess_reset_env(Ctx c, const MgSSK& k, MgSSState& s, MgSSFrame& f, MgSSSampler& g, MgSSResetTmp& rt,
+MG_HD void mg_ess_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, MgSSSampler& g, MgSSResetTmp& rt,
                             double* gt) {
     for (int y = c.lane; y < MG_W; y += c.nl) g.lo[y] = g.hi[y] = 0;
     if (c.lane == 0) {
@@ -589,7 +593,7 @@ MG_HD_NOINLINE void mg_ess_reset_env(Ctx c, const MgSSK& k, MgSSState& s, MgSSFr
         s.exit_x = s.exit_y = -100;
     }
     c.sync();
-    if (k.p.coin_enabled) mg_ess_spawn_coin(c, k, s, g, rt, false);
+    if (k.p.coin_enabled) mg_ess_spawn_coin(c, k.clamp_off, s, g, rt, false);
     if (c.lane == 0) {
         if (k.p.black_background) s.bg_blue = 2;
         s.live = rt.ok ? 1 : 0;
@@ -608,7 +612,7 @@ struct MgESSCarry {
     double reward;
     int32_t red_now, bg_red, spot_done;
 };
-MG_HD_NOINLINE bool mg_ess_step_c1(const MgSSK& k, MgSSState& s, const MgSSStepTmp& tmp, MgESSCarry& cy) {
+MG_HD bool mg_ess_step_c1(const MgSSK& k, MgSSState& s, const MgSSStepTmp& tmp, MgESSCarry& cy) {
     const int cx = tmp.cx, cyy = tmp.cy, nd = tmp.n_proc;
     double reward = 0.0, r = 0.0;
     int hit = 0;
@@ -657,7 +661,7 @@ MG_HD_NOINLINE bool mg_ess_step_c1(const MgSSK& k, MgSSState& s, const MgSSStepT
 }
 
 // C2 (one lane): time limits, top bar, episode statistics, frame description, ground truth
-MG_HD_NOINLINE bool mg_ess_step_c2(const MgSSK& k, MgSSState& s, const MgSSStepTmp& tmp, const MgESSCarry& cy,
+MG_HD bool mg_ess_step_c2(const MgSSK& k, MgSSState& s, const MgSSStepTmp& tmp, const MgESSCarry& cy,
                                    double& reward_out, double* info, MgSSFrame& f, double* gt) {
     const double reward = cy.reward;
     bool done = cy.spot_done != 0;
