@@ -224,7 +224,9 @@ struct MgSSState {
     int16_t coins[MG_SS_MAXCOINS][2];
     MgSSSpot spots[MG_SS_MAXSPOTS];
     int32_t coin_t;            // Endless: steps since the coin (re)spawned
-    uint8_t pad1[76];
+    uint32_t scene_ver;        // bumped whenever anything but the agent / top bar / spotlights changes on screen
+    uint32_t scene_last;       // (bg kind, coin layer order, coins left, exit open) of the last frame
+    uint8_t pad1[68];
 };
 
 struct MgSSFrame {
@@ -240,6 +242,7 @@ struct MgSSFrame {
     int16_t coins[MG_SS_MAXCOINS][2];
     int16_t disc_x[MG_SS_MAXSPOTS], disc_y[MG_SS_MAXSPOTS];
     uint8_t disc_r[MG_SS_MAXSPOTS];
+    uint32_t scene_ver;   // MgSSState::scene_ver when the frame was described: equal = only agent / bar / spotlights moved
 };
 
 // frame description produced by the env logic and consumed by the rasteriser (MM family)

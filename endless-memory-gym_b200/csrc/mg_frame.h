@@ -412,10 +412,10 @@ MG_HD void mg_ss_bg_run(uint8_t* buf, int x, int ylo, int yhi, uint32_t c_even, 
 struct MgSSBaseDesc {  // what `base` currently shows
     int32_t valid;
     int32_t lut_alpha;  // alpha the dim LUT was built for (-1: none)
-    int16_t sx, sy, exit_x, exit_y;
-    uint8_t srot, bg_kind, exit_open, n_coins;
-    uint8_t coin_above, pad[3];  // which painter's order `base` was built in
-    int16_t coins[MG_SS_MAXCOINS][2];
+    uint32_t scene_ver;  // MgSSFrame::scene_ver of the frame `base` was last brought up to date with
+    int16_t sx, sy;      // ... and the agent pose it shows
+    int32_t srot;
+    int32_t env;         // whose scene it is (versions of different envs are unrelated)
 };
 
 #define MG_SS_LIT_WORDS 224  // 84 * 84 = 7056 pixel bits (x-major, like the frame bytes) = 220.5 words, padded
@@ -548,10 +548,7 @@ MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, cons
     int osx, osy, osrot;  // pose of the agent `base` shows
     {
         const MgSSBaseDesc& d = wm->desc;
-        same_rest = simple && d.valid && d.coin_above == f.coin_above && d.bg_kind == f.bg_kind && d.exit_x == f.exit_x &&
-                    d.exit_y == f.exit_y && d.exit_open == f.exit_open && d.n_coins == f.n_coins;
-        for (int q = 0; same_rest && q < (int)f.n_coins; ++q)
-            same_rest = d.coins[q][0] == f.coins[q][0] && d.coins[q][1] == f.coins[q][1];
+        same_rest = simple && d.valid && d.scene_ver == f.scene_ver;
         osx = d.sx, osy = d.sy, osrot = d.srot;
         same_agent = osx == f.sx && osy == f.sy && osrot == f.srot;
     }
@@ -559,12 +556,8 @@ MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, cons
     if (c.lane == 0) {
         MgSSBaseDesc& w = wm->desc;
         w.valid = 1;
+        w.scene_ver = f.scene_ver;
         w.sx = f.sx, w.sy = f.sy, w.srot = f.srot;
-        w.bg_kind = f.bg_kind;
-        w.exit_x = f.exit_x, w.exit_y = f.exit_y, w.exit_open = f.exit_open;
-        w.n_coins = f.n_coins;
-        w.coin_above = f.coin_above;
-        for (int q = 0; q < (int)f.n_coins; ++q) w.coins[q][0] = f.coins[q][0], w.coins[q][1] = f.coins[q][1];
     }
     if (!same_rest) {
         mg_ss_rebuild_base(c, base, a, k, f);

@@ -310,6 +310,7 @@ struct SSPolicyT {
             MgSSWarpMem* wm = reinterpret_cast<MgSSWarpMem*>(warp);
             wm->desc.valid = 0;
             wm->desc.lut_alpha = -1;
+            wm->desc.env = -1;
         }
     }
     typedef MgSSK K;
@@ -335,6 +336,10 @@ struct SSPolicyT {
         if (c.lane == 0) {
             job.nframes = 0;
             tmp.action = 0;
+            if (wm->desc.env != env) {  // the team moved on to another env: its base buffer shows a foreign scene
+                wm->desc.valid = 0;
+                wm->desc.env = env;
+            }
             if (q.mode == MG_MODE_RESET) {
                 if (!(q.io.reset_mask && !q.io.reset_mask[env])) {
                     if (q.rng4) {  // env.reset(seed=s): a fresh PCG64 stream

@@ -148,6 +148,17 @@ MG_HD void mg_ss_frame_common(const MgSSState& s, int srot, MgSSFrame& f) {
     }
 }
 
+// Stamps the frame with the scene version: the rasteriser patches its base buffer instead of rebuilding it while
+// the version stands still (coins and exit only ever change through the fields compared here, or across a reset).
+MG_HD void mg_ss_scene_stamp(MgSSState& s, MgSSFrame& f, bool force) {
+    const uint32_t now = (uint32_t)f.bg_kind | ((uint32_t)f.coin_above << 8) | ((uint32_t)f.n_coins << 16) | ((uint32_t)f.exit_open << 24);
+    uint32_t ver = s.scene_ver;
+    if (force || now != s.scene_last) ver++;
+    s.scene_last = now;
+    s.scene_ver = ver;
+    f.scene_ver = ver;
+}
+
 MG_HD uint8_t mg_ss_bg_kind(const MgSSState& s, int red) {
     uint8_t st = red ? s.bg_red : s.bg_blue;
     return st == 0 ? (uint8_t)(red ? 1 : 0) : (st == 1 ? (uint8_t)2 : (uint8_t)3);
@@ -320,6 +331,7 @@ MG_HD void mg_ss_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, M
         f.n_discs = 0;
         f.red_now = 0;
         f.bg_kind = mg_ss_bg_kind(s, 0);
+        mg_ss_scene_stamp(s, f, true);
     }
     c.sync();
 }
@@ -489,6 +501,7 @@ MG_HD bool mg_ss_step_c(const MgSSK& k, MgSSState& s, const MgSSStepTmp& tmp, do
     f.n_discs = (uint8_t)nd;
     f.red_now = (int16_t)red_now;
     f.bg_kind = mg_ss_bg_kind(s, bg_red);
+    mg_ss_scene_stamp(s, f, false);
     if (done) {
         s.live = 0;
         if (info) {
@@ -601,6 +614,7 @@ MG_HD void mg_ess_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, 
         f.n_discs = 0;
         f.red_now = 0;
         f.bg_kind = mg_ss_bg_kind(s, 0);
+        mg_ss_scene_stamp(s, f, true);
         if (gt) mg_ess_ground_truth(k, s, gt);
     }
     c.sync();
@@ -680,6 +694,7 @@ MG_HD bool mg_ess_step_c2(const MgSSK& k, MgSSState& s, const MgSSStepTmp& tmp, 
     f.n_discs = (uint8_t)tmp.n_proc;
     f.red_now = (int16_t)cy.red_now;
     f.bg_kind = mg_ss_bg_kind(s, cy.bg_red);
+    mg_ss_scene_stamp(s, f, false);
     double g4[4];
     mg_ess_ground_truth(k, s, g4);
     if (gt)
