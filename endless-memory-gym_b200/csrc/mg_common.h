@@ -19,6 +19,18 @@
 #define MG_UNROLL
 #endif
 
+MG_HD int mg_popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+
+// branch layout hints: cold blocks leave the hot instruction stream (the single-lane phases are I-cache-miss-bound)
+#define MG_LIKELY(x) __builtin_expect(!!(x), 1)
+#define MG_UNLIKELY(x) __builtin_expect(!!(x), 0)
+
 #define MG_W 84                       // screen: int(336 * 0.25), mortar_mayhem.py:13,73
 #define MG_COL_BYTES (MG_W * 3)       // one x-column of the [x][y][c] frame = 252 contiguous bytes
 #define MG_FRAME_BYTES (MG_W * MG_W * 3)  // 21168 = 1323 * 16
@@ -226,7 +238,8 @@ struct MgSSState {
     int32_t coin_t;            // Endless: steps since the coin (re)spawned
     uint32_t scene_ver;        // bumped whenever anything but the agent / top bar / spotlights changes on screen
     uint32_t scene_last;       // (bg kind, coin layer order, coins left, exit open) of the last frame
-    uint8_t pad1[68];
+    uint32_t done_mask;        // bit i = spots[i].done (the removal pass of the next step reads one word, not n bytes)
+    uint8_t pad1[64];
 };
 
 struct MgSSFrame {

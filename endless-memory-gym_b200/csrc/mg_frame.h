@@ -559,7 +559,7 @@ MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, cons
         w.scene_ver = f.scene_ver;
         w.sx = f.sx, w.sy = f.sy, w.srot = f.srot;
     }
-    if (!same_rest) {
+    if (MG_UNLIKELY(!same_rest)) {
         mg_ss_rebuild_base(c, base, a, k, f);
         return;
     }
@@ -570,7 +570,7 @@ MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, cons
     //   (2) the new agent        — both without rows y < 4: those belong to
     //   (3) the top bar
     if (!same_agent) {
-        if (f.coin_black) {  // an opaque coin layer under the agent (Endless, coin disabled): the generic way
+        if (MG_UNLIKELY(f.coin_black)) {  // an opaque coin layer under the agent (Endless, coin disabled): the generic way
             const MgSprite sp = a.hdr->sprite[MG_SPR_AGENT0 + osrot];
             const uint32_t* e = a.entries + sp.first;
             for (int i = c.lane; i < (int)sp.count; i += c.nl) {
@@ -836,9 +836,9 @@ MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDraw
     mg_ss_update_base(c, wm, a, k, f, spot_li, simple);
     c.stamp(9);
     // 2. which pixels stay undimmed: the colour-keyed discs, and whatever is painted above the spotlight layer
-    if (f.alpha != 0) {
+    if (MG_LIKELY(f.alpha != 0)) {
         mg_ss_build_lit(c, wm, a, f, bar_li > spot_li ? tables->bar_lit : nullptr);
-        if (!simple) {
+        if (MG_UNLIKELY(!simple)) {
             c.sync();
             mg_ss_lit_over(c, wm, a, k, f, spot_li);
         }
@@ -846,11 +846,11 @@ MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDraw
     c.sync();
     // 3. frame = lit ? base : base dimmed by alpha (SDL: d + trunc((0 - d) * A / 255))
     c.stamp(10);
-    if (f.alpha == 255)
+    if (MG_LIKELY(f.alpha == 255))
         mg_ss_masked_copy_black(c, out, wm, tables, stream);
     else
         mg_ss_masked_copy_cold(c, out, wm, tables, f.alpha, stream);
     c.stamp(11);
     // 3b. black_background: white 1-px outlines on the spotlight surface
-    if (k.border && f.alpha != 0 && a.hdr->ring_off) mg_ss_outlines(c, out, a, k, f, spot_li);
+    if (MG_UNLIKELY(k.border && f.alpha != 0 && a.hdr->ring_off)) mg_ss_outlines(c, out, a, k, f, spot_li);
 }

@@ -111,7 +111,7 @@ struct MgWarpCtx {
     uint64_t* trow;   // this env's trace row (mg_step_io.trace) or nullptr
     int bar_id;       // named barrier of this team (teams of more than one warp), 0 = a single warp
     __device__ __forceinline__ void stamp(int col) {
-        if (trow && lane == 0) trow[col] = mg_now();
+        if (MG_UNLIKELY(trow != nullptr) && lane == 0) trow[col] = mg_now();
     }
     // all threads of the team that owns the env (one warp, or kTeamWarps warps on a named barrier)
     __device__ __forceinline__ void sync() {
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
             const int a0 = (int)act0, a1 = (int)act1;
             uint64_t* trow = tracing ? q.io.trace + (size_t)env * MG_TRACE_COLS : nullptr;
             ctx.trow = trow;
-            if (trow && lane == 0) {
+            if (MG_UNLIKELY(trow != nullptr) && lane == 0) {
                 unsigned smid;
                 asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
                 trow[0] = tr0, trow[1] = tr1, trow[2] = tr2, trow[3] = mg_now(), trow[7] = smid;
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
             }
             P::logic(ctx, k, q, view, env, t, *st, a0, a1, *job, fr, scratch);
             ctx.sync();
-            if (trow && lane == 0) trow[4] = mg_now();
+            if (MG_UNLIKELY(trow != nullptr) && lane == 0) trow[4] = mg_now();
             const int nframes = job->nframes;
             for (int fi = 0; fi < nframes; ++fi) {
                 const Frame& f = fr[fi];  // lives in the team's shared slot until the next logic call

@@ -52,13 +52,6 @@ MG_HD void mg_gen_cta_init(MgGenCta* t, int tid, int nthreads) {
     for (int i = tid; i < MG_MP_SQRT_N; i += nthreads) t->sqrt_d2[i] = sqrt((double)i);
 }
 
-MG_HD int mg_popc32(uint32_t v) {
-#if defined(__CUDA_ARCH__)
-    return __popc(v);
-#else
-    return __builtin_popcount(v);
-#endif
-}
 // the n-th (0-based) set bit of a 32-bit mask
 MG_HD int mg_nth_set_bit(uint32_t mask, int n) {
 #if defined(__CUDA_ARCH__)

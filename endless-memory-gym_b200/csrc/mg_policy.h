@@ -80,7 +80,7 @@ MG_HD void mg_env_logic(const typename E::K& k, const MgKIO& q, const MgAssetVie
             reset_now = true;
         }
     }
-    if (reset_now) {
+    if (MG_UNLIKELY(reset_now)) {
         E::reset_env(k, a, s, fr[at], gt);
         job.to_final[0] = at;
         job.to_final[at] = 0;
@@ -142,7 +142,7 @@ MG_HD void mg_env_logic_coop(Ctx& c, const typename E::K& k, const MgKIO& q, con
             reset_now = true;
         }
     }
-    if (reset_now) E::reset_coop(c, k, a, s, fr[at], gt, sc);  // the one (inlined) call site
+    if (MG_UNLIKELY(reset_now)) E::reset_coop(c, k, a, s, fr[at], gt, sc);  // the one (inlined) call site
     if (c.lane == 0) {
         job.to_final[0] = at;
         job.to_final[at] = 0;
@@ -336,7 +336,7 @@ struct SSPolicyT {
         if (c.lane == 0) {
             job.nframes = 0;
             tmp.action = 0;
-            if (wm->desc.env != env) {  // the team moved on to another env: its base buffer shows a foreign scene
+            if (MG_UNLIKELY(wm->desc.env != env)) {  // the team moved on to another env: its base buffer shows a foreign scene
                 wm->desc.valid = 0;
                 wm->desc.env = env;
             }
@@ -363,7 +363,7 @@ struct SSPolicyT {
         }
         c.sync();
         c.stamp(12);
-        if (tmp.action == 2) {
+        if (MG_LIKELY(tmp.action == 2)) {
             mg_ss_step_b(c, k, trig(a), s, tmp, fr[0]);
             c.sync();
             c.stamp(13);
@@ -374,7 +374,7 @@ struct SSPolicyT {
                     wm->desc.valid = 0;
                 }
                 c.sync();
-                if (tmp.action == 4) mg_ess_spawn_coin(c, k.clamp_off, s, g, rt, true);
+                if (MG_UNLIKELY(tmp.action == 4)) mg_ess_spawn_coin(c, k.clamp_off, s, g, rt, true);
             }
             if (c.lane == 0) {
                 double reward;
@@ -397,7 +397,7 @@ struct SSPolicyT {
             c.stamp(14);
         }
         // ONE (inlined) call site for the reset: a fresh episode (1) or the auto-reset of a finished one (3)
-        if (tmp.action == 1 || tmp.action == 3) {
+        if (MG_UNLIKELY(tmp.action == 1 || tmp.action == 3)) {
             // auto-reset: the terminal frame (if requested) must leave before the base buffer is borrowed by the
             // sampler: it is emitted here, out of order with respect to the generic frame loop
             const int at = (tmp.action == 3 && q.io.final_obs) ? 1 : 0;

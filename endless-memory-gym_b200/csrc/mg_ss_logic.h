@@ -298,6 +298,7 @@ MG_HD void mg_ss_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, M
         int a0 = k.p.light_threshold < 0 ? 0 : (k.p.light_threshold > 255 ? 255 : k.p.light_threshold);
         s.alpha = (uint8_t)(k.p.light_dim_off_duration > 0 ? 0 : a0);
         s.n_spots = 0;
+        s.done_mask = 0;
         for (int i = 0; i < k.p.initial_spawns; ++i) mg_ss_new_spot(k, s.rng, s.spots[s.n_spots++]);
         s.coins_collected = 0;
         rt.nc = mg_choice(s.rng, k.p.num_coins);
@@ -342,8 +343,8 @@ struct MgSSStepTmp {
     int32_t action;   // what the logic lane decided for this call: 0 idle, 1 reset, 2 step
     int32_t cx, cy;   // agent centre after the move
     int32_t n_proc;   // spotlights drawn this step
+    int32_t hits;     // how many of them contain the agent (is_agent_inside)
     uint8_t proc[MG_SS_MAXSPOTS];  // their indices in s.spots
-    uint8_t hitf[MG_SS_MAXSPOTS];  // is_agent_inside per drawn spotlight
 };
 
 // A: agent move, top-bar bookkeeping, light dimming, spawn, and WHICH spotlights are drawn this step
@@ -379,29 +380,44 @@ MG_HD void mg_ss_step_a(const MgSSK& k, MgSSState& s, int a0, int a1, MgSSStepTm
         s.spawn_timer = 0;
     }
     // `for spot in self.spotlights: if spot.done: self.spotlights.remove(spot) else: draw + hit test`
-    int np = 0;
-    for (int i = 0; i < (int)s.n_spots; ++i) {
-        if (s.spots[i].done) {
-            for (int j = i; j + 1 < (int)s.n_spots; ++j) s.spots[j] = s.spots[j + 1];
-            s.n_spots--;
+    int np = 0, n = s.n_spots;
+    uint32_t mask = s.done_mask;  // bit i = spots[i].done: the pass runs on registers
+    for (int i = 0; i < n; ++i) {
+        if ((mask >> i) & 1u) {
+            for (int j = i; j + 1 < n; ++j) s.spots[j] = s.spots[j + 1];
+            const uint32_t low = (1u << i) - 1u;
+            mask = (mask & low) | ((mask >> 1) & ~low);
+            n--;
             // the element that slid into slot i is skipped this step, exactly like list.remove inside `for`
         } else {
             tmp.proc[np++] = (uint8_t)i;
         }
     }
+    s.n_spots = (uint8_t)n;
+    s.done_mask = mask;
     tmp.n_proc = np;
 }
 
 // B: Spotlight.draw + is_agent_inside for every drawn spotlight (lane j takes the j-th one)
 template <class Ctx>
 MG_HD void mg_ss_step_b(Ctx& c, const MgSSK& k, const double* trig, MgSSState& s, MgSSStepTmp& tmp, MgSSFrame& f) {
+    uint32_t done_bits = 0, hits = 0;
     for (int j = c.lane; j < tmp.n_proc; j += c.nl) {
-        MgSSSpot& sp = s.spots[tmp.proc[j]];
+        const int idx = tmp.proc[j];
+        MgSSSpot& sp = s.spots[idx];
         int dx, dy;
-        tmp.hitf[j] = mg_ss_advance_spot(k, trig, sp, tmp.cx, tmp.cy, dx, dy) ? 1 : 0;
+        if (mg_ss_advance_spot(k, trig, sp, tmp.cx, tmp.cy, dx, dy)) hits |= 1u << j;
+        if (sp.done) done_bits |= 1u << idx;
         f.disc_x[j] = (int16_t)dx;
         f.disc_y[j] = (int16_t)dy;
         f.disc_r[j] = sp.radius;
+    }
+    // at most MG_SS_MAXSPOTS = 32 spotlights: they all sit on the lanes of the team's first warp
+    done_bits = c.reduce_or(done_bits);
+    hits = c.reduce_or(hits);
+    if (c.lane == 0) {
+        s.done_mask |= done_bits;
+        tmp.hits = mg_popc32(hits);
     }
 }
 
@@ -412,8 +428,7 @@ MG_HD bool mg_ss_step_c(const MgSSK& k, MgSSState& s, const MgSSStepTmp& tmp, do
     double reward = 0.0;
     double r = 0.0;
     bool spot_done = false;
-    int hit = 0;
-    for (int j = 0; j < nd; ++j) hit += tmp.hitf[j];
+    const int hit = tmp.hits;
     int red_now = 0, bg_red = 0;
     if (hit > 0) {
         s.hp = s.hp - k.p.spot_damage;
@@ -598,6 +613,7 @@ MG_HD void mg_ess_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, 
         int a0 = k.p.light_threshold < 0 ? 0 : (k.p.light_threshold > 255 ? 255 : k.p.light_threshold);
         s.alpha = (uint8_t)(k.p.light_dim_off_duration > 0 ? 0 : a0);
         s.n_spots = 0;
+        s.done_mask = 0;
         for (int i = 0; i < k.p.initial_spawns; ++i) mg_ss_new_spot(k, s.rng, s.spots[s.n_spots++]);
         s.coins_collected = 0;
         s.num_coins = 1;
@@ -627,10 +643,9 @@ struct MgESSCarry {
     int32_t red_now, bg_red, spot_done;
 };
 MG_HD bool mg_ess_step_c1(const MgSSK& k, MgSSState& s, const MgSSStepTmp& tmp, MgESSCarry& cy) {
-    const int cx = tmp.cx, cyy = tmp.cy, nd = tmp.n_proc;
+    const int cx = tmp.cx, cyy = tmp.cy;
     double reward = 0.0, r = 0.0;
-    int hit = 0;
-    for (int j = 0; j < nd; ++j) hit += tmp.hitf[j];
+    const int hit = tmp.hits;
     cy.red_now = 0;
     cy.bg_red = 0;
     cy.spot_done = 0;
