@@ -268,15 +268,14 @@ def main():
     Ke = min(Ke, POOL)
     a_host = acts[:Ke].cpu().pin_memory()
     obs_h = torch.empty((2, n, 84, 84, 3), dtype=torch.uint8).pin_memory()
-    rew_h = torch.empty((2, n), dtype=torch.float64).pin_memory()
-    done_h = torch.empty((2, n), dtype=torch.bool).pin_memory()
+    res_h = torch.empty((2, 9 * n), dtype=torch.uint8).pin_memory()  # reward f64[n] + done u8[n]: env.results
+    rew_h = [res_h[b][:8 * n].view(torch.float64) for b in range(2)]
     a_dev = torch.empty_like(env._actions_dev)
     copy_stream = torch.cuda.Stream(device=dev)
     ev_step = [torch.cuda.Event() for _ in range(2)]
     ev_copy = [torch.cuda.Event() for _ in range(2)]
     obs_d = [torch.empty((n, 84, 84, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
-    rew_d = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(2)]
-    done_d = [torch.empty(n, dtype=torch.bool, device=dev) for _ in range(2)]
+    res_d = [torch.empty(9 * n, dtype=torch.uint8, device=dev) for _ in range(2)]
     checksum = 0.0
 
     def e2e_loop(steps):
@@ -285,15 +284,13 @@ def main():
             b = t & 1
             a_dev.copy_(a_host[t % Ke], non_blocking=True)             # H2D actions (pinned)
             torch.cuda.current_stream().wait_event(ev_copy[b])         # slot b's previous D2H has drained
-            _, r, d, _, _ = env.step(a_dev, obs_out=obs_d[b])
-            rew_d[b].copy_(r)
-            done_d[b].copy_(d)
+            env.step(a_dev, obs_out=obs_d[b])
+            res_d[b].copy_(env.results)                                # reward + done of this step (one buffer)
             ev_step[b].record()
             with torch.cuda.stream(copy_stream):                       # D2H of step t overlaps step t+1
                 copy_stream.wait_event(ev_step[b])
                 obs_h[b].copy_(obs_d[b], non_blocking=True)
-                rew_h[b].copy_(rew_d[b], non_blocking=True)
-                done_h[b].copy_(done_d[b], non_blocking=True)
+                res_h[b].copy_(res_d[b], non_blocking=True)
                 ev_copy[b].record()
             if t >= 1:                                                 # consume step t-1's results on the host
                 ev_copy[1 - b].synchronize()
@@ -312,6 +309,33 @@ def main():
         e2e_s = float(tm.item())
     e2e_value = total * Ke / e2e_s / 1e6
 
+    # ---- the same loop for a consumer that lives on the GPU (the intended use: the policy reads obs in HBM): actions
+    # still come from pinned host memory and reward + done still go back to the host every step; observations stay
+    def e2e_device_obs(steps):
+        nonlocal checksum
+        for t in range(steps):
+            b = t & 1
+            a_dev.copy_(a_host[t % Ke], non_blocking=True)
+            env.step(a_dev, obs_out=obs_d[b])
+            res_h[b].copy_(env.results, non_blocking=True)
+            ev_copy[b].record()
+            if t >= 1:
+                ev_copy[1 - b].synchronize()
+                checksum += float(rew_h[1 - b][0])
+        torch.cuda.synchronize()
+
+    e2e_device_obs(3)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_device_obs(4 * Ke)
+    barrier()
+    e2e_dev_s = time.perf_counter() - t0
+    if dist is not None:
+        tm = torch.tensor([e2e_dev_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e_dev_s = float(tm.item())
+    e2e_dev_value = total * 4 * Ke / e2e_dev_s / 1e6
+
     if rank == 0:
         peaks = {}
         try:
@@ -320,6 +344,14 @@ def main():
             pass
         peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
         b_alg = alg_bytes_per_env_step(spec.family, n_act, POOL)
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+        traffic = None
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.env)
+            if cap and cap["envs"] == n and cap["steps_per_launch"] == POOL:
+                traffic = cap["dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            pass
         launches = -(-K // POOL)
         kernel_ms = ms / launches  # launches back to back on one stream: event time / launches = launch duration
         achieved = n * b_alg * K / (ms * 1e-3) / 1e9
@@ -344,10 +376,14 @@ def main():
             "e2e": {"value": e2e_value, "unit": "M env-steps/s", "h2d_bytes_per_step": n * n_act * 8,
                     "d2h_bytes_per_step": n * (OBS_BYTES + 8 + 1), "steps": Ke,
                     "note": "actions pinned-host->device and obs+reward+done device->pinned-host every step "
-                            "(D2H of step t overlaps step t+1); PCIe-bound"},
+                            "(D2H of step t overlaps step t+1); PCIe-bound",
+                    "device_obs": {"value": e2e_dev_value, "unit": "M env-steps/s", "h2d_bytes_per_step": n * n_act * 8,
+                                   "d2h_bytes_per_step": n * (8 + 1),
+                                   "note": "same public step() loop with the observations consumed in HBM (GPU-resident "
+                                           "policy): actions from pinned host memory, reward+done back to the host"}},
             "gpu_launches": -(-K // POOL),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "mg_env_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "mg_env_kernel",
                          "alg_bytes_per_env_step": b_alg, "kernel_ms": kernel_ms, "env_steps_per_launch": n * POOL},
             "cpu_baseline": cpu,
             "clocks": clocks,

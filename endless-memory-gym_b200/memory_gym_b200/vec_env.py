@@ -121,8 +121,10 @@ class MemoryGymVecEnv:
         self.state = torch.zeros((n, self.spec_.state_bytes), dtype=torch.uint8, device=dev)
         self.obs = torch.zeros((n, 84, 84, 3), dtype=torch.uint8, device=dev)
         self.final_obs = torch.zeros((n, 84, 84, 3), dtype=torch.uint8, device=dev) if final_obs else None
-        self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
-        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        # reward (f64) and done (u8) share one allocation: `results` moves both to the host with a single copy
+        self.results = torch.zeros(9 * n, dtype=torch.uint8, device=dev)
+        self.reward = self.results[:8 * n].view(torch.float64)
+        self.done = self.results[8 * n:]
         self.truncated = torch.zeros(n, dtype=torch.bool, device=dev)
         self.info = torch.zeros((n, L.MG_INFO_COLS), dtype=torch.float64, device=dev)
         # the library writes [n][MG_GT_COLS]; the env publishes the columns its reference counterpart has
@@ -134,6 +136,17 @@ class MemoryGymVecEnv:
         self._actions_dev = torch.zeros((n, len(nvec)) if len(nvec) > 1 else (n,), dtype=torch.int64, device=dev)
         self._io = L.StepIO()
         self._io.obs = self.obs.data_ptr()
+        # step() hot path: the views it returns are built once (they alias the library's output buffers)
+        self._done_bool = self.done.view(torch.bool)
+        self._info_views = {"episode": self.info, "_episode": self._done_bool}
+        for k_, col in self.spec_.info_keys.items():
+            self._info_views[k_] = self.info[:, col]
+        if self.final_obs is not None:
+            self._info_views["final_observation"] = self.final_obs
+        if self.has_ground_truth_info:
+            self._info_views["ground_truth"] = self.ground_truth
+            self._info_views["final_ground_truth"] = self.info[:, L.MG_INFO_GT0:L.MG_INFO_GT0 + self.spec_.gt_dim]
+        self._step_fn = None
         self._io.final_obs = self.final_obs.data_ptr() if final_obs else None
         self._io.reward = self.reward.data_ptr()
         self._io.done = self.done.data_ptr()
@@ -153,6 +166,7 @@ class MemoryGymVecEnv:
         self._params = None
         self._params_key = None
         self._assets = None
+        self._assets_ptr = self._state_ptr = 0
         self._seeded = False
         self.max_episode_steps = None
 
@@ -172,6 +186,7 @@ class MemoryGymVecEnv:
             off = (-raw.data_ptr()) % 128
             self._assets = raw[off:off + blob.shape[0]]
             self._assets.copy_(torch.from_numpy(blob))
+            self._assets_ptr, self._state_ptr = self._assets.data_ptr(), self.state.data_ptr()
             if self.device.type == "cuda":
                 torch.cuda.synchronize(self.device)  # the kernels' prologue reads the blob before stream order applies
             self._params, self._params_key = params, key
@@ -251,18 +266,9 @@ class MemoryGymVecEnv:
                 raise ValueError("obs_out must be a contiguous uint8[N,84,84,3] tensor on the env's device")
             obs = obs_out
         self._io.obs = obs.data_ptr()
-        self._be.step(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(), self._io,
+        self._be.step(self.spec_.family, self._params, self._assets_ptr, self._state_ptr, self._io,
                       self.num_envs, self._be.stream(self.device))
-        done = self.done.view(torch.bool)
-        info = {"episode": self.info, "_episode": done}
-        for k, col in self.spec_.info_keys.items():
-            info[k] = self.info[:, col]
-        if self.final_obs is not None:
-            info["final_observation"] = self.final_obs
-        if self.has_ground_truth_info:
-            info["ground_truth"] = self.ground_truth
-            info["final_ground_truth"] = self.info[:, L.MG_INFO_GT0:L.MG_INFO_GT0 + self.spec_.gt_dim]
-        return self._wrap_obs(obs), self.reward, done, self.truncated, info
+        return self._wrap_obs(obs), self.reward, self._done_bool, self.truncated, dict(self._info_views)
 
     def _check_rollout_buffers(self, actions, obs_out, reward_out, done_out, info_out):
         if self._params is None:
