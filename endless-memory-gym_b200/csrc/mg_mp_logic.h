@@ -161,24 +161,49 @@ MG_HD uint64_t mg_mp_generate_coop(Ctx& c, MgRngR& r, int sx, int sy, int ex, in
         key[j] = cell == start ? (uint32_t)start : MG_GEN_NOKEY;  // order 0, g 0
         prev[j] = MG_GEN_NOPREV;
     }
+    // A cell's key is MG_GEN_NOKEY unless it is on the open list, so the two scans need no membership test; the
+    // uniform `open` mask only steers the (uniform) control flow of the relaxation.
     uint64_t open = 1ull << start, closed = 0;
     uint32_t counter = 1, head_key = (uint32_t)start;
     double fh = 0.0;  // f of open[0]
     bool need_head = false;
     uint64_t path = 0;
+    int cur = start;
+    uint32_t gc = 0;
+    // relax the edge cur -> v (one draw per neighbour that is neither closed nor a wall)
+    const auto relax = [&](int v) {
+        const uint64_t vbit = 1ull << v;
+        if ((closed | wall) & vbit) return;
+        const uint32_t cost = gc + (uint32_t)mg_rr_integers(r, 1, 9);
+        const bool is_open = (open & vbit) != 0;
+        MG_UNROLL
+        for (int j = 0; j < PER; ++j) {
+            if (c.lane + NL * j != v) continue;  // the lane that owns cell v
+            if (is_open) {
+                // a cheaper way to an open node: g_cost is NOT updated (reference bug, :712), so f stays what it
+                // was; only the predecessor changes
+                if (cost < ((key[j] >> 6) & 511u)) prev[j] = (uint32_t)cur;
+            } else {
+                key[j] = (counter << 15) | (cost << 6) | (uint32_t)v;
+                f[j] = (double)cost + h[j];
+                prev[j] = (uint32_t)cur;
+            }
+        }
+        if (!is_open) {
+            counter++;
+            open |= vbit;
+        }
+    };
     for (;;) {
         if (!open) return 0;
         if (need_head) {  // open[0] was taken: the open node inserted first is the new head
             uint32_t best = MG_GEN_NOKEY;
-    MG_UNROLL
-            for (int j = 0; j < PER; ++j) {
-                const int cell = c.lane + NL * j;
-                if (cell < MG_MP_NODES && ((open >> cell) & 1ull) && key[j] < best) best = key[j];
-            }
+            MG_UNROLL
+            for (int j = 0; j < PER; ++j) best = key[j] < best ? key[j] : best;
             head_key = c.reduce_min(best);
             const int head = (int)(head_key & 63u), hj = head / NL;
             double fl = 0.0;
-    MG_UNROLL
+            MG_UNROLL
             for (int j = 0; j < PER; ++j)
                 if (j == hj) fl = f[j];
             fh = mg_f64_make(c.shfl(mg_f64_lo(fl), head % NL), c.shfl(mg_f64_hi(fl), head % NL));
@@ -186,46 +211,26 @@ MG_HD uint64_t mg_mp_generate_coop(Ctx& c, MgRngR& r, int sx, int sy, int ex, in
         }
         // the first node of the list with f < f(open[0]), else open[0] (:685-690)
         uint32_t cand = MG_GEN_NOKEY;
-    MG_UNROLL
-        for (int j = 0; j < PER; ++j) {
-            const int cell = c.lane + NL * j;
-            if (cell < MG_MP_NODES && ((open >> cell) & 1ull) && f[j] < fh && key[j] < cand) cand = key[j];
-        }
+        MG_UNROLL
+        for (int j = 0; j < PER; ++j)
+            if (f[j] < fh && key[j] < cand) cand = key[j];
         cand = c.reduce_min(cand);
         const uint32_t cur_key = cand == MG_GEN_NOKEY ? head_key : cand;
-        const int cur = (int)(cur_key & 63u), gc = (int)((cur_key >> 6) & 511u);
+        cur = (int)(cur_key & 63u);
+        gc = (cur_key >> 6) & 511u;
         if (cur_key == head_key) need_head = true;
         if (cur == end) break;
         open &= ~(1ull << cur);
         closed |= 1ull << cur;
-        const int ci = cur / n, cj = cur % n;
+        MG_UNROLL
+        for (int j = 0; j < PER; ++j)
+            if (c.lane + NL * j == cur) key[j] = MG_GEN_NOKEY;  // off the open list
+        const int ci = cur / n, cj = cur - n * ci;
         // neighbours in Node.add_neighbors order (+x, -x, +y, -y), pygame_assets.py:465-472
-        MG_NOUNROLL
-        for (int q = 0; q < 4; ++q) {
-            const int vi = ci + (q == 0 ? 1 : (q == 1 ? -1 : 0)), vj = cj + (q == 2 ? 1 : (q == 3 ? -1 : 0));
-            if ((unsigned)vi >= (unsigned)n || (unsigned)vj >= (unsigned)n) continue;
-            const int v = mg_mp_id(vi, vj);
-            if (((closed | wall) >> v) & 1ull) continue;
-            const uint32_t cost = (uint32_t)(gc + mg_rr_integers(r, 1, 9));
-            const bool is_open = ((open >> v) & 1ull) != 0;
-    MG_UNROLL
-            for (int j = 0; j < PER; ++j) {
-                if (c.lane + NL * j != v) continue;  // the lane that owns cell v
-                if (is_open) {
-                    // a cheaper way to an open node: g_cost is NOT updated (reference bug, :712), so f stays
-                    // what it was; only the predecessor changes
-                    if (cost < ((key[j] >> 6) & 511u)) prev[j] = (uint32_t)cur;
-                } else {
-                    key[j] = (counter << 15) | (cost << 6) | (uint32_t)v;
-                    f[j] = (double)cost + h[j];
-                    prev[j] = (uint32_t)cur;
-                }
-            }
-            if (!is_open) {
-                counter++;
-                open |= 1ull << v;
-            }
-        }
+        if (ci < n - 1) relax(cur + n);
+        if (ci > 0) relax(cur - n);
+        if (cj < n - 1) relax(cur + 1);
+        if (cj > 0) relax(cur - 1);
     }
     // walk back from the end node: each predecessor comes from the lane that owns the cell
     for (int at = end; at != MG_GEN_NOPREV;) {
