@@ -207,3 +207,43 @@ def test_rollout_equals_step_loop(env_id):
         if t >= T - 3:
             assert torch.equal(o, ring[t % 3]), t
     assert dn.any() and torch.equal(a.state, b.state)
+
+
+@pytest.mark.parametrize("env_id", ["MortarMayhem-v0", "Endless-MysteryPath-v0", "SearingSpotlights-v0"])
+def test_rollout_scheduling_modes(env_id):
+    """A rollout gives the same bytes whether the envs are handed to the warps through the global work counter
+    (mg_rollout_io.sched) or through each CTA's shared-memory counter (sched = NULL), launch after launch
+    (the global counter is re-armed by the kernel itself)."""
+    n, T = 3000, 40
+    a = mg.make(env_id, num_envs=n, device=DEV)
+    b = mg.make(env_id, num_envs=n, device=DEV)
+    b._sched = None  # CTA-local scheduling
+    acts = _random_actions(a, T, 9)
+    a.reset(seed=3)
+    b.reset(seed=3)
+    bufs = []
+    for env in (a, b):
+        ring = torch.zeros((T, n, 84, 84, 3), dtype=torch.uint8, device=DEV)
+        rew = torch.zeros((T, n), dtype=torch.float64, device=DEV)
+        dn = torch.zeros((T, n), dtype=torch.bool, device=DEV)
+        for _ in range(3):
+            env.rollout(acts, ring, rew, dn)
+        bufs.append((ring, rew, dn))
+    assert all(torch.equal(x, y) for x, y in zip(*bufs)) and torch.equal(a.state, b.state)
+    assert bufs[0][2].any()
+    if a._sched is not None:
+        assert int(a._sched.abs().sum()) == 0  # re-armed
+
+
+def test_results_buffer_aliases_reward_and_done():
+    """`results` = reward (f64[N]) followed by done (u8[N]) in one allocation: one copy moves both to the host."""
+    n = 257
+    env = mg.make("MortarMayhem-Grid-v0", num_envs=n, device=DEV)
+    env.reset(seed=1)
+    acts = _random_actions(env, 60, 5)
+    for t in range(60):
+        _, r, d, _, _ = env.step(acts[t])
+        raw = env.results.cpu().numpy()
+        assert np.array_equal(raw[:8 * n].view(np.float64), r.cpu().numpy())
+        assert np.array_equal(raw[8 * n:].astype(bool), d.cpu().numpy())
+    assert d.dtype == torch.bool and r.dtype == torch.float64
