@@ -139,6 +139,7 @@ def lib():
     L.mg_last_error.restype = C.c_char_p
     L.mg_device_info.argtypes = [C.POINTER(i32)] * 3 + [C.POINTER(C.c_size_t)]
     L.mg_seed_pcg64.argtypes = [vp, i32, vp]
+    L.mg_obs_to_policy_bf16.argtypes = [vp, vp, i32, vp]
     L.mg_selftest_pcg64_host.argtypes = [vp, vp, vp, vp, i32, vp, vp]
     for fam, P in (("mm", MMParams), ("mp", MPParams), ("ss", SSParams), ("ep", EPParams)):
         getattr(L, f"mg_{fam}_check_params").argtypes = [C.POINTER(P)]

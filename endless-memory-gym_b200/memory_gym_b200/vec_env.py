@@ -340,6 +340,22 @@ class MemoryGymVecEnv:
         self._be.step_many(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(),
                            self._many_ios, T, self.num_envs, self._be.stream(self.device))
 
+    def policy_obs(self, obs=None, out=None):
+        """The consumer step (``mg_obs_to_policy_bf16``): ``obs`` uint8[N,84,84,3] (default: this env's observation
+        buffer) -> bf16[N,3,84,84] = ``obs.permute(0, 3, 1, 2) / 255``, bit-identical to torch's float32 division and
+        cast, by one streaming kernel on the current stream."""
+        src = self.obs if obs is None else obs
+        if src.dtype != torch.uint8 or src.device != self.device or not src.is_contiguous() or tuple(src.shape[1:]) != (84, 84, 3):
+            raise ValueError("obs must be a contiguous uint8[N,84,84,3] tensor on the env's device")
+        n = src.shape[0]
+        if out is None:
+            out = torch.empty((n, 3, 84, 84), dtype=torch.bfloat16, device=self.device)
+        elif out.dtype != torch.bfloat16 or out.device != self.device or not out.is_contiguous() or tuple(out.shape) != (n, 3, 84, 84):
+            raise ValueError("out must be a contiguous bfloat16[N,3,84,84] tensor on the env's device")
+        L.check(self._be.lib.mg_obs_to_policy_bf16(src.data_ptr(), out.data_ptr(), n, self._be.stream(self.device)),
+                "mg_obs_to_policy_bf16")
+        return out
+
     def render(self):
         """``rgb_array`` of the reference (mortar_mayhem.py:396): the observation transposed to [y][x][c]."""
         return self.obs.permute(0, 2, 1, 3)

@@ -333,6 +333,12 @@ int mg_mp_check_params(const mg_mp_params* p);
 int mg_ss_check_params(const mg_ss_params* p);
 int mg_ep_check_params(const mg_ep_params* p);
 
+/* The consumer step right after the env step (what every training loop on the reference does on the host:
+ * `obs.astype(float32) / 255`, channels first): obs uint8 [n][84][84][3] -> out bf16 [n][3][84][84] with
+ * out[i][c][x][y] = bf16_rn(float(obs[i][x][y][c]) / 255.0f), i.e. obs.permute(0, 3, 1, 2) / 255 bit for bit.
+ * Both pointers 16-byte aligned device memory; asynchronous on `stream`. */
+int mg_obs_to_policy_bf16(const uint8_t* obs, void* out, int n, void* stream);
+
 /* Library / device introspection. */
 int mg_abi_version(void);
 int mg_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin);

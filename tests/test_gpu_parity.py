@@ -247,3 +247,22 @@ def test_results_buffer_aliases_reward_and_done():
         assert np.array_equal(raw[:8 * n].view(np.float64), r.cpu().numpy())
         assert np.array_equal(raw[8 * n:].astype(bool), d.cpu().numpy())
     assert d.dtype == torch.bool and r.dtype == torch.float64
+
+
+@pytest.mark.parametrize("n", [1, 3, 300, 4096])
+def test_policy_obs_matches_torch(n):
+    """mg_obs_to_policy_bf16 == obs.permute(0, 3, 1, 2).float() / 255 -> bf16, bit for bit (fp tolerance: none)."""
+    env = mg.make("SearingSpotlights-v0", num_envs=n, device=DEV)
+    env.reset(seed=11)
+    acts = _random_actions(env, 12, 2)
+    for t in range(12):
+        obs = env.step(acts[t])[0]
+    want = (obs.permute(0, 3, 1, 2).to(torch.float32) / 255.0).to(torch.bfloat16).contiguous()
+    got = env.policy_obs()
+    assert got.shape == (n, 3, 84, 84) and got.dtype == torch.bfloat16
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+    rnd = torch.randint(0, 256, (n, 84, 84, 3), dtype=torch.uint8, device=DEV)  # every byte value
+    out = torch.empty((n, 3, 84, 84), dtype=torch.bfloat16, device=DEV)
+    env.policy_obs(rnd, out)
+    want = (rnd.permute(0, 3, 1, 2).to(torch.float32) / 255.0).to(torch.bfloat16).contiguous()
+    assert torch.equal(out.view(torch.int16), want.view(torch.int16))
