@@ -103,6 +103,7 @@ MG_HD_NOINLINE bool mg_ep_add_segment_coop(Ctx c, MgEPState& s, MgGenMem& m, con
     MgRngR r = mg_rr_load(s.rng);
     const int sy = ns == 0 ? mg_rr_integers(r, 0, g7) : mg_ep_end_y(s.seg[ns - 1]);
     const int ey = mg_rr_integers(r, 0, g7);
+    c.sync();  // every lane has read the record (stream, segment count) before lane 0 rewrites it below
     uint64_t nx[2] = {0, 0};
     const uint64_t mask = mg_mp_generate_coop(c, r, 0, sy, g7 - 1, ey, tab, nx);
     const uint64_t n0 = nx[0], n1 = nx[1];  // the end node's next is the transition tile: east = 0

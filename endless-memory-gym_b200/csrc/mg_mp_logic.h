@@ -282,6 +282,7 @@ template <class Ctx>
 MG_HD void mg_mp_reset_coop(Ctx& c, const MgMPK& k, MgMPState& s, MgMPDraw& d, MgGenMem& m, const MgGenCta& tab) {
     const int g = MG_MP_CELLS;
     MgRngR r = mg_rr_load(s.rng);
+    c.sync();  // every lane has its copy of the stream before lane 0 writes the advanced one back
     const int side = mg_rr_choice(r, k.p.cardinal_origin_choice);
     const int a = mg_rr_integers(r, 0, g);
     const int b = mg_rr_integers(r, 0, g);

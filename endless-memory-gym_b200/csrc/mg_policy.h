@@ -265,8 +265,10 @@ struct EPPolicy {
         MgGenMem& m = *reinterpret_cast<MgGenMem*>(sc.warp);
         if (c.lane == 0) m.flag = mg_ep_step_pre(k, s, a0) ? 1 : 0;
         c.sync();
+        const bool need = m.flag != 0;
+        c.sync();  // every lane has read the flag before lane 0 reuses the word for "done"
         bool capped = false;
-        if (m.flag) capped = !mg_ep_add_segment_coop(c, s, m, *reinterpret_cast<const MgGenCta*>(sc.cta));
+        if (need) capped = !mg_ep_add_segment_coop(c, s, m, *reinterpret_cast<const MgGenCta*>(sc.cta));
         if (c.lane == 0) {
             double reward;
             const bool done = mg_ep_step_post(k, s, capped, reward, info, f, gt);
@@ -336,6 +338,7 @@ struct SSPolicyT {
         if (c.lane == 0) {
             job.nframes = 0;
             tmp.action = 0;
+            tmp.post = 0;
             if (MG_UNLIKELY(wm->desc.env != env)) {  // the team moved on to another env: its base buffer shows a foreign scene
                 wm->desc.valid = 0;
                 wm->desc.env = env;
@@ -387,9 +390,9 @@ struct SSPolicyT {
                 *done_out = done ? 1 : 0;
                 job.nframes = 1;
                 job.to_final[0] = 0;
-                tmp.action = 0;
+                // (a word of its own: the other warp of the team may still be reading tmp.action above)
                 if (done && (q.io.flags & MG_FLAG_AUTORESET)) {
-                    tmp.action = 3;  // auto-reset: every lane joins the cooperative reset below
+                    tmp.post = 3;  // auto-reset: every lane joins the cooperative reset below
                     if (q.io.final_obs) job.to_final[0] = 1;  // terminal frame -> final_obs, next episode's first -> obs
                 }
             }
@@ -397,10 +400,10 @@ struct SSPolicyT {
             c.stamp(14);
         }
         // ONE (inlined) call site for the reset: a fresh episode (1) or the auto-reset of a finished one (3)
-        if (MG_UNLIKELY(tmp.action == 1 || tmp.action == 3)) {
+        if (MG_UNLIKELY(tmp.action == 1 || tmp.post == 3)) {
             // auto-reset: the terminal frame (if requested) must leave before the base buffer is borrowed by the
             // sampler: it is emitted here, out of order with respect to the generic frame loop
-            const int at = (tmp.action == 3 && q.io.final_obs) ? 1 : 0;
+            const int at = (tmp.post == 3 && q.io.final_obs) ? 1 : 0;
             if (at) {
                 emit_cold(c, q.io.final_obs + (size_t)env * MG_FRAME_BYTES, a, k, fr[0], sc);
                 c.sync();

@@ -340,7 +340,8 @@ MG_HD void mg_ss_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, M
 // step(), split so that the spotlights (the only per-step work that grows with the scene) advance in
 // parallel, one lane per spotlight: A (one lane) -> B (all lanes) -> C (one lane)
 struct MgSSStepTmp {
-    int32_t action;   // what the logic lane decided for this call: 0 idle, 1 reset, 2 step
+    int32_t action;   // what the logic lane decided for this call: 0 idle, 1 reset, 2 step (4: + coin respawn)
+    int32_t post;     // ... and after the step: 3 = auto-reset
     int32_t cx, cy;   // agent centre after the move
     int32_t n_proc;   // spotlights drawn this step
     int32_t hits;     // how many of them contain the agent (is_agent_inside)
