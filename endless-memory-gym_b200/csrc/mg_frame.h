@@ -524,9 +524,10 @@ MG_HD void mg_ss_draw_layer(Ctx& c, uint8_t* base, const MgAssetView& a, const M
     }
 }
 
-// the whole base buffer from scratch (after a reset, a background change, or in a non-default layer order): cold
+// the whole base buffer from scratch (after a reset, a background change, in a non-default layer order — and for
+// every frame of a single-step launch): inlined at its one call site, so assets and options stay in registers
 template <class Ctx>
-MG_HD_NOINLINE void mg_ss_rebuild_base(Ctx c, uint8_t* base, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f) {
+MG_HD void mg_ss_rebuild_base(Ctx& c, uint8_t* base, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f) {
     uint32_t c_even, c_odd;
     mg_ss_bg_colours(f.bg_kind, 0, c_even, c_odd);
     mg_ss_fill_bg(c, base, c_even, c_odd);
@@ -535,11 +536,17 @@ MG_HD_NOINLINE void mg_ss_rebuild_base(Ctx c, uint8_t* base, const MgAssetView& 
         if (k.layers[li] != 1) mg_ss_draw_layer(c, base, a, k, f, k.layers[li]);
 }
 
+// out-of-line copy for kernels that are short of registers (the endless variant)
+template <class Ctx>
+MG_HD_NOINLINE void mg_ss_rebuild_base_ool(Ctx c, uint8_t* base, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f) {
+    mg_ss_rebuild_base(c, base, a, k, f);
+}
+
 // Bring `base` up to date with frame f. `base` = every layer EXCEPT the spotlight layer, in painter's order
 // (layers above the spotlight layer are never dimmed: their pixels are forced lit in the mask instead).
 // `simple` = the reference's default order (coins, exit, agent below the spotlight layer, bar on top): then a
 // frame that only moved the agent is a small patch; any other order rebuilds.
-template <class Ctx>
+template <bool kRebuildOol, class Ctx>
 MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
                              int spot_li, bool simple) {
     uint8_t* base = wm->base;
@@ -560,7 +567,10 @@ MG_HD void mg_ss_update_base(Ctx& c, MgSSWarpMem* wm, const MgAssetView& a, cons
         w.sx = f.sx, w.sy = f.sy, w.srot = f.srot;
     }
     if (MG_UNLIKELY(!same_rest)) {
-        mg_ss_rebuild_base(c, base, a, k, f);
+        if constexpr (kRebuildOol)
+            mg_ss_rebuild_base_ool(c, base, a, k, f);
+        else
+            mg_ss_rebuild_base(c, base, a, k, f);
         return;
     }
     // Only the agent moved and the bar changed. In the `simple` order the layers under the spotlights are coins <
@@ -825,7 +835,7 @@ MG_HD_NOINLINE void mg_ss_outlines(Ctx c, uint8_t* buf, const MgAssetView& a, co
 }
 
 // One Searing-Spotlights frame -> `out` (the env's 21168 observation bytes in global memory)
-template <class Ctx>
+template <bool kRebuildOol, class Ctx>
 MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
                       MgSSWarpMem* wm, const MgSSCtaTables* tables, bool stream) {
     const int spot_li = k.spot_li, bar_li = k.bar_li;
@@ -833,7 +843,7 @@ MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDraw
     const bool simple = spot_li == k.n_layers - 2 && bar_li == k.n_layers - 1;
     // 1. every layer but the spotlight layer (kept across frames, patched where it changed)
     c.stamp(8);
-    mg_ss_update_base(c, wm, a, k, f, spot_li, simple);
+    mg_ss_update_base<kRebuildOol>(c, wm, a, k, f, spot_li, simple);
     c.stamp(9);
     // 2. which pixels stay undimmed: the colour-keyed discs, and whatever is painted above the spotlight layer
     if (MG_LIKELY(f.alpha != 0)) {

@@ -441,14 +441,14 @@ struct SSPolicyT {
     template <class Ctx>
     static MG_HD void emit(Ctx& c, uint8_t* dst, const MgAssetView& a, const K& k, const Frame& f, const MgScratch& sc,
                            bool stream) {
-        mg_ss_emit(c, dst, a, draw_k(k, f), f, reinterpret_cast<MgSSWarpMem*>(sc.warp),
+        mg_ss_emit<kEndless>(c, dst, a, draw_k(k, f), f, reinterpret_cast<MgSSWarpMem*>(sc.warp),
                    reinterpret_cast<const MgSSCtaTables*>(sc.cta), stream);
     }
     // terminal frames (one per episode): an out-of-line copy keeps the hot loop's code small
     template <class Ctx>
     static MG_HD_NOINLINE void emit_cold(Ctx c, uint8_t* dst, const MgAssetView& a, const K& k, const Frame& f,
                                          const MgScratch& sc) {
-        mg_ss_emit(c, dst, a, draw_k(k, f), f, reinterpret_cast<MgSSWarpMem*>(sc.warp),
+        mg_ss_emit<kEndless>(c, dst, a, draw_k(k, f), f, reinterpret_cast<MgSSWarpMem*>(sc.warp),
                    reinterpret_cast<const MgSSCtaTables*>(sc.cta), false);
     }
     // unused with kDirectStore
