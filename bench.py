@@ -263,6 +263,27 @@ def main():
         ms = float(tm.item())
     value = total * K / (ms * 1e-3) / 1e6
 
+    # ---- the same steps as ONE LAUNCH PER STEP (mg_*_step, programmatic dependent launch between them): what a
+    # policy in the loop pays per step on the device, reported next to the rollout number
+    Ks = min(K, 8 * POOL)
+    for _ in range(2):
+        env.step_many(acts, ring, rew_buf, done_buf)
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    es0.record()
+    left = Ks
+    while left > 0:
+        c = min(left, POOL)
+        env.step_many(acts[:c], ring[:c], rew_buf[:c], done_buf[:c])
+        left -= c
+    es1.record()
+    barrier()
+    ms_single = es0.elapsed_time(es1)
+    if dist is not None:
+        tm = torch.tensor([ms_single], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms_single = float(tm.item())
+
     # ---- end to end through the public API with host buffers -------------------------------------------
     Ke = args.e2e_steps or min(K, 200)
     Ke = min(Ke, POOL)
@@ -381,6 +402,9 @@ def main():
                                    "d2h_bytes_per_step": n * (8 + 1),
                                    "note": "same public step() loop with the observations consumed in HBM (GPU-resident "
                                            "policy): actions from pinned host memory, reward+done back to the host"}},
+            "single_step": {"value": total * Ks / (ms_single * 1e-3) / 1e6, "unit": "M env-steps/s",
+                            "us_per_step": ms_single * 1e3 / Ks, "steps": Ks,
+                            "note": "one mg_*_step launch per step (policy-in-the-loop shape), device-timed, max over ranks"},
             "gpu_launches": -(-K // POOL),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "mg_env_kernel",

@@ -11,6 +11,7 @@
 // MG_EP_MAXFALL entries; reaching either cap ends the episode (done).
 #pragma once
 #include <math.h>
+#include <stddef.h>
 
 #include "../../include/memgym_b200.h"
 #include "mg_common.h"
@@ -92,6 +93,33 @@ MG_HD bool mg_ep_prev(const MgEPState& s, int x, int y, int& px, int& py) {
     }
     return false;
 }
+
+// ---- path generation ahead of time ("speculation") ---------------------------------------------------------
+// Only add_path_segment draws from the env's stream, so between two resets the stream stands still unless the agent
+// walks into a new segment. Rollout launches therefore run HELPER WARPS next to the env teams (mg_kernels.cu): after
+// a reset the team posts the stream it ended with, a helper generates the NEXT episode's three segments from it, and
+// the next reset adopts them if — and only if — the stream still is what the helper started from (bit-exact either
+// way; a stale or unfinished job is simply dropped). The hand-over lives in shared memory only.
+enum { MG_SPEC_EMPTY = 0, MG_SPEC_REQUESTED = 1, MG_SPEC_BUSY = 2, MG_SPEC_READY = 3 };
+struct MgEPSpec {
+    uint32_t state;   // MG_SPEC_*: EMPTY -> (team) REQUESTED -> (helper) BUSY -> READY -> (team) EMPTY
+    uint32_t pad;
+    MgRng before;     // the stream the three segments were (are to be) generated from
+    MgRng after;      // ... and the stream after them
+    MgEPSegment seg[3];
+};
+struct MgEPWarpMem {  // per-team scratch of the Endless Mystery Path kernels
+    MgGenMem gen;
+    int32_t helpers;  // helper warps in this launch (0: none, resets generate their own paths)
+    int32_t pad;
+    MgEPSpec spec;
+};
+// what a helper warp works on: the head of an env record (stream, segment count, the first three segments)
+#define MG_EP_HELPER_BYTES 384
+static_assert(offsetof(MgEPState, seg) + 3 * sizeof(MgEPSegment) <= MG_EP_HELPER_BYTES, "helper scratch too small");
+
+MG_HD uint32_t mg_vload_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+MG_HD void mg_vstore_u32(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 
 // EndlessMysteryPath.add_path_segment: draws the start row (first segment only), the end row, then the A* path.
 // Called by every lane of the warp (mg_mp_generate_coop); the stream in the record advances even when it fails.
@@ -183,9 +211,105 @@ MG_HD int mg_ep_bar_height(int stamina, int max_visible, bool at_reset) {
     return (int)((double)MG_W * (1.0 - ((double)v / (double)max_visible)));
 }
 
+// Team side of the speculation: true if the three segments of this reset were adopted from a helper
 template <class Ctx>
-MG_HD void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, double* gt, MgGenMem& m,
-                                     const MgGenCta& tab) {
+MG_HD bool mg_ep_spec_take(Ctx& c, MgEPState& s, MgEPSpec& sp) {
+    for (;;) {
+        const uint32_t st = c.shfl(mg_vload_u32(&sp.state), 0);  // lane 0's view, so the warp stays uniform
+        if (st == MG_SPEC_BUSY) {  // a helper is at it: it finishes within one generation, sooner than we would
+            c.nanosleep(256);
+            continue;
+        }
+        if (st == MG_SPEC_REQUESTED) {  // nobody picked it up: take it back (a helper may win the race)
+            uint32_t won = 0;
+            if (c.lane == 0) won = c.cas_u32(&sp.state, MG_SPEC_REQUESTED, MG_SPEC_EMPTY) == MG_SPEC_REQUESTED ? 1u : 0u;
+            if (c.shfl(won, 0)) return false;
+            continue;
+        }
+        if (st != MG_SPEC_READY) return false;
+        c.sync();         // lane 0's observation of READY is ordered before every lane's reads below
+        c.fence_block();  // the helper's results are visible after its READY
+        const bool match = sp.before.state_lo == s.rng.state_lo && sp.before.state_hi == s.rng.state_hi &&
+                           sp.before.inc_lo == s.rng.inc_lo && sp.before.inc_hi == s.rng.inc_hi &&
+                           sp.before.buf == s.rng.buf && sp.before.has_buf == s.rng.has_buf;
+        if (match) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(sp.seg);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(s.seg);
+            for (int w = c.lane; w < (int)(3 * sizeof(MgEPSegment) / 4); w += c.nl) dst[w] = src[w];
+            if (c.lane == 0) {
+                s.rng = sp.after;
+                s.n_segments = 3;
+            }
+        }
+        c.sync();
+        if (c.lane == 0) mg_vstore_u32(&sp.state, MG_SPEC_EMPTY);
+        c.sync();
+        return match;
+    }
+}
+
+// Team side, after a reset: ask for the next episode's segments (the slot is EMPTY here, see mg_ep_spec_take)
+template <class Ctx>
+MG_HD void mg_ep_spec_request(Ctx& c, const MgEPState& s, MgEPSpec& sp) {
+    if (c.lane == 0) {
+        sp.before = s.rng;
+        c.fence_block();
+        mg_vstore_u32(&sp.state, MG_SPEC_REQUESTED);
+    }
+}
+
+// Helper warp: serve the teams of this CTA until all of them have left. `hs` = this helper's MG_EP_HELPER_BYTES.
+template <class Ctx>
+MG_HD void mg_ep_helper_loop(Ctx& c, uint8_t* hs_bytes, uint8_t* wextra0, int wextra_stride, int nteams, int hidx,
+                             const uint32_t* teams_done, MgGenMem& m, const MgGenCta& tab) {
+    MgEPState& hs = *reinterpret_cast<MgEPState*>(hs_bytes);  // only its head is touched (n_segments <= 3)
+    int next = hidx % nteams;
+    for (;;) {
+        if (c.shfl(mg_vload_u32(teams_done), 0) >= (uint32_t)nteams) return;
+        MgEPSpec* job = nullptr;
+        for (int i = 0; i < nteams && !job; ++i) {
+            const int t = (next + i) % nteams;
+            MgEPSpec& sp = reinterpret_cast<MgEPWarpMem*>(wextra0 + (size_t)t * wextra_stride)->spec;
+            if (c.shfl(mg_vload_u32(&sp.state), 0) != MG_SPEC_REQUESTED) continue;
+            uint32_t won = 0;
+            if (c.lane == 0) won = c.cas_u32(&sp.state, MG_SPEC_REQUESTED, MG_SPEC_BUSY) == MG_SPEC_REQUESTED ? 1u : 0u;
+            if (c.shfl(won, 0)) {
+                job = &sp;
+                next = (t + 1) % nteams;
+            }
+        }
+        if (!job) {
+            c.nanosleep(512);
+            continue;
+        }
+        c.sync();
+        c.fence_block();  // the team's `before` is visible after its REQUESTED
+        if (c.lane == 0) {
+            hs.rng = job->before;
+            hs.n_segments = 0;
+        }
+        c.sync();
+        bool ok = true;
+        for (int q = 0; q < 3 && ok; ++q) ok = mg_ep_add_segment_coop(c, hs, m, tab);
+        if (ok) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(hs.seg);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(job->seg);
+            for (int w = c.lane; w < (int)(3 * sizeof(MgEPSegment) / 4); w += c.nl) dst[w] = src[w];
+            if (c.lane == 0) job->after = hs.rng;
+        }
+        c.sync();
+        if (c.lane == 0) {
+            c.fence_block();
+            // a failed generation ("No valid path found") is left to the env itself: the slot just empties
+            mg_vstore_u32(&job->state, ok ? MG_SPEC_READY : MG_SPEC_EMPTY);
+        }
+    }
+}
+
+template <class Ctx>
+MG_HD void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, double* gt, MgEPWarpMem& wm,
+                            const MgGenCta& tab) {
+    MgGenMem& m = wm.gen;
     c.stamp(12);
     if (c.lane == 0) {
         s.t = 0;
@@ -195,7 +319,9 @@ MG_HD void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, 
     }
     c.sync();
     bool ok = true;
-    for (int q = 0; q < 3 && ok; ++q) ok = mg_ep_add_segment_coop(c, s, m, tab);
+    const bool spec = wm.helpers > 0;
+    if (!(spec && mg_ep_spec_take(c, s, wm.spec)))
+        for (int q = 0; q < 3 && ok; ++q) ok = mg_ep_add_segment_coop(c, s, m, tab);
     c.stamp(13);
     if (c.lane == 0) {
         const int sy = ok ? mg_ep_start_y(s.seg[0]) : 0;
@@ -222,6 +348,7 @@ MG_HD void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, 
         if (gt) mg_ep_ground_truth(s, gt);
     }
     c.sync();
+    if (spec) mg_ep_spec_request(c, s, wm.spec);
     c.stamp(14);
 }
 

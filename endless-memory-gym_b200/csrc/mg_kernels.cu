@@ -100,6 +100,7 @@ __device__ __forceinline__ uint64_t mg_now() {
 struct MgCtaHdr {
     uint64_t stage_bar;
     uint32_t next;
+    uint32_t teams_done;  // teams that have left the kernel (helper warps leave when all have)
 };
 
 // execution context of mg_frame.h on the device: the 32 lanes of the warp that owns the env
@@ -134,6 +135,10 @@ struct MgWarpCtx {
     __device__ __forceinline__ uint32_t reduce_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
     __device__ __forceinline__ uint32_t reduce_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
     __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+    // shared-memory hand-over between warps of a CTA (teams <-> helper warps)
+    __device__ __forceinline__ uint32_t cas_u32(uint32_t* p, uint32_t cmp, uint32_t val) { return atomicCAS(p, cmp, val); }
+    __device__ __forceinline__ void fence_block() { __threadfence_block(); }
+    __device__ __forceinline__ void nanosleep(unsigned ns) { __nanosleep(ns); }
     __device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
     // whole-frame template -> this warp's frame buffer, by TMA
     __device__ __forceinline__ void copy_frame(uint8_t* dst, const uint8_t* src) {
@@ -168,7 +173,10 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     constexpr int kSlot = ((kStateBytes + kFrames * (int)sizeof(Frame) + (int)sizeof(MgFrameJob) + 16 + 127) / 128) * 128;
     extern __shared__ __align__(128) uint8_t smem[];
 
-    const int lane = threadIdx.x % kTeam, team = threadIdx.x / kTeam, nteams = blockDim.x / kTeam;
+    // helper warps (rollout launches of policies that have them) sit behind the teams and own no env
+    const int nhelp = (kRollout && P::kHelperWarps > 0) ? q.n_helpers : 0;
+    const int lane = threadIdx.x % kTeam, team = threadIdx.x / kTeam, nteams = blockDim.x / kTeam - nhelp;
+    const bool is_helper = team >= nteams;
     uint8_t* buf = smem + (size_t)team * P::kFrameBuf;
     uint8_t* slot = smem + (size_t)nteams * P::kFrameBuf + (size_t)team * kSlot;
     uint8_t* wextra = smem + (size_t)nteams * (P::kFrameBuf + kSlot) + (size_t)team * P::kWarpExtra;
@@ -189,13 +197,13 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     if (tracing) tr0 = mg_now();
     MgAssetView view = mg_asset_view(assets);
     MgWarpCtx ctx{lane, kTeam, mg_smem_u32(bar), 0u, mg_policy_evict_first(), nullptr, P::kTeamWarps > 1 ? team + 1 : 0};
-    if (lane == 0) mg_mbar_init(ctx.bar, 1);
+    if (lane == 0 && !is_helper) mg_mbar_init(ctx.bar, 1);
     // This CTA owns envs blockIdx.x + j * gridDim.x (consecutive envs on different SMs: remainders spread
     // evenly). Team i starts with j = i; every further j comes from a SHARED-MEMORY work counter, so a team
     // held up by an auto-reset ends up with fewer envs and no global atomic sits on the step path.
     const int G = gridDim.x;
     int env = (int)blockIdx.x + team * G;
-    const bool active = env < q.n;
+    const bool active = env < q.n && !is_helper;
     if (P::kFrameBuf && active && lane == 0) {  // background template -> this team's frame buffer (TMA, L2-resident source)
         mg_mbar_expect_tx(ctx.bar, MG_FRAME_BYTES);
         mg_bulk_load(buf, view.tmpl[0], MG_FRAME_BYTES, ctx.bar);
@@ -205,6 +213,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     const bool staged = (int)stage_bytes <= q.stage_cap;
     if (threadIdx.x == 0) {
         hdr->next = (uint32_t)nteams;
+        hdr->teams_done = 0u;
         const uint32_t sbar = mg_smem_u32(&hdr->stage_bar);
         mg_mbar_init(sbar, 1);
         if (staged) {
@@ -213,7 +222,10 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
         }
     }
     P::cta_init(cextra, threadIdx.x, blockDim.x);
-    P::warp_init(wextra, lane);
+    if (!is_helper) {
+        P::warp_init(wextra, lane);
+        if constexpr (P::kHelperWarps > 0) P::set_helpers(wextra, lane, nhelp);
+    }
     __syncthreads();
     if (staged) {
         mg_mbar_wait(mg_smem_u32(&hdr->stage_bar), 0u);
@@ -226,7 +238,15 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     // SMs that stream faster take more envs. The last team to leave re-arms it for the next launch.
     uint32_t* const sched = kRollout ? q.sched : nullptr;
     const int total_teams = G * nteams;
+    if constexpr (kRollout && P::kHelperWarps > 0) {
+        if (is_helper) {
+            MgWarpCtx hctx{lane, kTeam, 0u, 0u, 0ull, nullptr, 0};
+            P::helper_loop(hctx, cextra, smem + (size_t)nteams * (P::kFrameBuf + kSlot), nteams, team - nteams, &hdr->teams_done);
+            return;
+        }
+    }
     const auto team_exit = [&]() {
+        if (kRollout && P::kHelperWarps > 0 && lane == 0) atomicAdd(&hdr->teams_done, 1u);
         if (sched && lane == 0) {
             __threadfence();
             if (atomicAdd(sched + 1, 1u) == (uint32_t)total_teams - 1u) {
@@ -394,7 +414,7 @@ extern "C" int mg_device_info(int* sm_count, int* cc_major, int* cc_minor, size_
 }
 
 struct MgLaunchPlan {
-    int ctas, wpc, stage_cap;
+    int ctas, wpc, stage_cap, helpers;
     size_t smem;
 };
 
@@ -419,7 +439,9 @@ static int plan_launch(int n, int wpc_req, int default_wpc, MgLaunchPlan* out) {
     while (wmax > 1 && wmax * per_warp + P::kCtaExtra + MG_CTA_HDR_BYTES + P::kStageReserve > smem_max) wmax--;  // leave room to stage the assets
     int wpc = wpc_req ? wpc_req : default_wpc;
     if (wpc > wmax) wpc = wmax;
-    if (!wpc_req && balance && n > sms * wmax) {
+    // (policies with helper warps take every frame buffer they can get: their rollouts are scheduled dynamically
+    // and bound by the generation capacity of teams + helpers, not by rounds of envs per warp)
+    if (!wpc_req && balance && P::kHelperWarps == 0 && n > sms * wmax) {
         double best = -1.0;
         for (int w = wmax; w >= (wmax + 1) / 2; --w) {  // at least half the buffers stay in flight
             long warps = (long)sms * w;
@@ -447,6 +469,14 @@ static int plan_launch(int n, int wpc_req, int default_wpc, MgLaunchPlan* out) {
         cudaGetLastError();
         return (int)e;
     }
+    // helper warps fill the thread budget behind the teams (MG_HELPERS=0 switches them off: measurement knob)
+    int helpers = 0;
+    if (kRollout && P::kHelperWarps > 0 && !(getenv("MG_HELPERS") && atoi(getenv("MG_HELPERS")) == 0)) {
+        helpers = P::kMaxThreads / (32 * P::kTeamWarps) - wpc;
+        if (helpers > P::kHelperWarps) helpers = P::kHelperWarps;
+        if (helpers < 0) helpers = 0;
+    }
+    out->helpers = helpers;
     out->ctas = ctas;
     out->wpc = wpc;
     out->stage_cap = stage_cap;
@@ -459,7 +489,7 @@ static int launch_one(const typename P::K& k, const MgKIO& q, const MgLaunchPlan
                       void* stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.ctas);
-    cfg.blockDim = dim3(plan.wpc * 32 * P::kTeamWarps);
+    cfg.blockDim = dim3((plan.wpc + plan.helpers) * 32 * P::kTeamWarps);
     cfg.dynamicSmemBytes = plan.smem;
     cfg.stream = (cudaStream_t)stream;
     // programmatic dependent launch: this kernel's prologue (asset staging, template loads) may overlap
@@ -560,6 +590,7 @@ static int launch_rollout(const typename P::K& k, const void* assets, void* stat
     q.io.trace = r->trace;
     q.io.vector_obs = r->vector_obs;
     q.sched = r->sched;
+    q.n_helpers = plan.helpers;
     q.io.flags = r->flags | MG_FLAG_AUTORESET;  // a rollout without auto-reset would only idle finished envs
     q.mode = MG_MODE_STEP;
     q.n = n;

@@ -31,6 +31,7 @@ struct MgKIO {
     int32_t n_steps, ring_n;
     int64_t act_stride, obs_stride, rew_stride, done_stride, info_stride;
     uint32_t* sched;  // rollout: global work counter (mg_rollout_io.sched) or nullptr = CTA-local scheduling
+    int32_t n_helpers;  // rollout: helper warps behind the env teams of every CTA (policies with kHelperWarps > 0)
 };
 
 struct MgFrameJob {      // what the logic lane hands to the warp: up to two frames for this env-step
@@ -151,6 +152,7 @@ MG_HD void mg_env_logic_coop(Ctx& c, const typename E::K& k, const MgKIO& q, con
 }
 
 struct MMPolicy {
+    static constexpr int kHelperWarps = 0;
     static constexpr int kWarpExtra = 0, kCtaExtra = 0;
     static constexpr int kStageReserve = 8 * 1024;  // shared memory kept free for the staged asset prefix (7.4 KB by default)
     static constexpr int kTeamWarps = 1, kMaxThreads = 320;
@@ -190,6 +192,7 @@ struct MMPolicy {
 };
 
 struct MPPolicy {
+    static constexpr int kHelperWarps = 0;
     static constexpr int kWarpExtra = (int)((sizeof(MgGenMem) + 127) / 128 * 128);
     static constexpr int kCtaExtra = (int)((sizeof(MgGenCta) + 127) / 128 * 128);
     static constexpr int kStageReserve = 8 * 1024;
@@ -238,16 +241,34 @@ struct MPPolicy {
 };
 
 struct EPPolicy {
-    static constexpr int kWarpExtra = (int)((sizeof(MgGenMem) + 127) / 128 * 128);
-    static constexpr int kCtaExtra = (int)((sizeof(MgGenCta) + 127) / 128 * 128);
+    static constexpr int kHelperWarps = 7;  // rollout launches: path generation ahead of time (mg_ep_logic.h)
+    static constexpr int kWarpExtra = (int)((sizeof(MgEPWarpMem) + 127) / 128 * 128);
+    static constexpr int kGenCtaBytes = (int)((sizeof(MgGenCta) + 127) / 128 * 128);
+    static constexpr int kCtaExtra = kGenCtaBytes + kHelperWarps * MG_EP_HELPER_BYTES;
     static constexpr int kStageReserve = 8 * 1024;
-    static constexpr int kTeamWarps = 1, kMaxThreads = 320;
+    static constexpr int kTeamWarps = 1, kMaxThreads = 512;
     static constexpr int kFrameBuf = 21248;
     static constexpr bool kDirectStore = false;
     static MG_HD void cta_init(uint8_t* cta, int tid, int nthreads) {
         mg_gen_cta_init(reinterpret_cast<MgGenCta*>(cta), tid, nthreads);
     }
-    static MG_HD void warp_init(uint8_t*, int) {}
+    static MG_HD void warp_init(uint8_t* warp, int lane) {
+        if (lane == 0) {
+            MgEPWarpMem* wm = reinterpret_cast<MgEPWarpMem*>(warp);
+            wm->helpers = 0;
+            wm->spec.state = MG_SPEC_EMPTY;
+        }
+    }
+    static MG_HD void set_helpers(uint8_t* warp, int lane, int n) {
+        if (lane == 0) reinterpret_cast<MgEPWarpMem*>(warp)->helpers = n;
+    }
+    template <class Ctx>
+    static MG_HD void helper_loop(Ctx& c, uint8_t* cextra, uint8_t* wextra0, int nteams, int hidx, const uint32_t* teams_done) {
+        // a helper's hand-over words + scratch: its own MG_EP_HELPER_BYTES block behind the square-root table
+        uint8_t* mine = cextra + kGenCtaBytes + (size_t)hidx * MG_EP_HELPER_BYTES;
+        MgGenMem m{0, 0};
+        mg_ep_helper_loop(c, mine, wextra0, kWarpExtra, nteams, hidx, teams_done, m, *reinterpret_cast<const MgGenCta*>(cextra));
+    }
     typedef MgEPK K;
     typedef MgEPState State;
     typedef MgEPFrame Frame;
@@ -255,7 +276,7 @@ struct EPPolicy {
     static MG_HD bool restores_clean(const K& k) { return !k.p.show_background; }
     template <class Ctx>
     static MG_HD void reset_coop(Ctx& c, const K& k, const MgAssetView&, State& s, Frame& f, double* gt, const MgScratch& sc) {
-        mg_ep_reset_coop(c, k, s, f, gt, *reinterpret_cast<MgGenMem*>(sc.warp), *reinterpret_cast<const MgGenCta*>(sc.cta));
+        mg_ep_reset_coop(c, k, s, f, gt, *reinterpret_cast<MgEPWarpMem*>(sc.warp), *reinterpret_cast<const MgGenCta*>(sc.cta));
     }
     // the step may have to extend the path (add_path_segment, endless_mystery_path.py:300-302): the move runs on
     // one lane, the segment on the warp, the rest of the step on one lane again
@@ -296,6 +317,7 @@ struct EPPolicy {
 
 template <int TW, bool kEndless>
 struct SSPolicyT {
+    static constexpr int kHelperWarps = 0;
     static constexpr int kWarpExtra = (int)((sizeof(MgSSWarpMem) + 127) / 128 * 128);
     static constexpr int kCtaExtra = (int)((sizeof(MgSSCtaTables) + 127) / 128 * 128);
     // instruction / latency-bound frames: TW warps share one env (more warps per base buffer hide more latency)

@@ -23,6 +23,13 @@ struct HostCtx {
     uint32_t reduce_min(uint32_t v) { return v; }
     uint32_t reduce_or(uint32_t v) { return v; }
     uint32_t shfl(uint32_t v, int) { return v; }
+    uint32_t cas_u32(uint32_t* p, uint32_t cmp, uint32_t val) {
+        uint32_t old = *p;
+        if (old == cmp) *p = val;
+        return old;
+    }
+    void fence_block() {}
+    void nanosleep(unsigned) {}
     uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31u)); }
     void copy_frame(uint8_t* dst, const uint8_t* src) { memcpy(dst, src, MG_FRAME_BYTES); }
 };

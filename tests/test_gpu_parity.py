@@ -266,3 +266,24 @@ def test_policy_obs_matches_torch(n):
     env.policy_obs(rnd, out)
     want = (rnd.permute(0, 3, 1, 2).to(torch.float32) / 255.0).to(torch.bfloat16).contiguous()
     assert torch.equal(out.view(torch.int16), want.view(torch.int16))
+
+
+def test_emp_rollout_with_and_without_helper_warps(monkeypatch):
+    """Endless-MysteryPath rollouts run helper warps that generate the next episode's path ahead of time; a reset
+    adopts their result only when the env's stream still is what the helper started from. Same bytes either way."""
+    n, T = 2500, 120
+    outs = []
+    for helpers in ("1", "0"):
+        monkeypatch.setenv("MG_HELPERS", helpers)
+        env = mg.make("Endless-MysteryPath-v0", num_envs=n, device=DEV)
+        acts = _random_actions(env, T, 31)
+        env.reset(seed=8)
+        ring = torch.zeros((T, n, 84, 84, 3), dtype=torch.uint8, device=DEV)
+        rew = torch.zeros((T, n), dtype=torch.float64, device=DEV)
+        dn = torch.zeros((T, n), dtype=torch.bool, device=DEV)
+        env.rollout(acts, ring, rew, dn)
+        env.rollout(acts, ring, rew, dn)
+        torch.cuda.synchronize()
+        outs.append((ring, rew, dn, env.state.clone()))
+    assert all(torch.equal(x, y) for x, y in zip(*outs))
+    assert int(outs[0][2].sum()) > 3 * n  # several episodes per env: the hand-over was exercised
