@@ -222,3 +222,15 @@ def test_option_validation_and_loud_failure_without_gpu():
     with pytest.raises(L.MemGymError):
         be.check_params("ep", emp.to_struct(emp.process_reset_params({"stamina_level": 0})))
     assert C.sizeof(L.EPParams) == 8 * 4 + 7 * 8
+
+
+def test_consumer_step_rejects_bad_pointers_without_a_device():
+    """mg_obs_to_policy_bf16 validates its arguments before it touches the device (no compute without a GPU)."""
+    lib = L.lib()
+    assert lib.mg_obs_to_policy_bf16(None, None, 4, None) == -1
+    assert b"NULL" in lib.mg_last_error()
+    buf = np.zeros(84 * 84 * 3 * 9 + 64, np.uint8)
+    base = buf.ctypes.data + (-buf.ctypes.data) % 16
+    assert lib.mg_obs_to_policy_bf16(base + 1, base + 32, 1, None) == -1  # misaligned
+    assert b"aligned" in lib.mg_last_error()
+    assert lib.mg_obs_to_policy_bf16(base, base + 21168, 0, None) == 0            # empty batch: nothing to do
