@@ -834,17 +834,24 @@ MG_HD_NOINLINE void mg_ss_outlines(Ctx c, uint8_t* buf, const MgAssetView& a, co
     }
 }
 
-// One Searing-Spotlights frame -> `out` (the env's 21168 observation bytes in global memory)
+// One Searing-Spotlights frame -> `out` (the env's 21168 observation bytes in global memory), in two parts so that a
+// pipelined rollout can run the first one (the base-buffer patch) on one warp while the other warp already computes
+// the next step: mg_ss_emit_base, [barrier], mg_ss_emit_rest.
+MG_HD bool mg_ss_simple_order(const MgSSDrawK& k) { return k.spot_li == k.n_layers - 2 && k.bar_li == k.n_layers - 1; }
+
 template <bool kRebuildOol, class Ctx>
-MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
-                      MgSSWarpMem* wm, const MgSSCtaTables* tables, bool stream) {
-    const int spot_li = k.spot_li, bar_li = k.bar_li;
-    // the reference's default order: bg, coins, exit, agent, SPOT, bar
-    const bool simple = spot_li == k.n_layers - 2 && bar_li == k.n_layers - 1;
+MG_HD void mg_ss_emit_base(Ctx& c, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f, MgSSWarpMem* wm) {
     // 1. every layer but the spotlight layer (kept across frames, patched where it changed)
     c.stamp(8);
-    mg_ss_update_base<kRebuildOol>(c, wm, a, k, f, spot_li, simple);
+    mg_ss_update_base<kRebuildOol>(c, wm, a, k, f, k.spot_li, mg_ss_simple_order(k));
     c.stamp(9);
+}
+
+template <class Ctx>
+MG_HD void mg_ss_emit_rest(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+                           MgSSWarpMem* wm, const MgSSCtaTables* tables, bool stream) {
+    const int spot_li = k.spot_li, bar_li = k.bar_li;
+    const bool simple = mg_ss_simple_order(k);
     // 2. which pixels stay undimmed: the colour-keyed discs, and whatever is painted above the spotlight layer
     if (MG_LIKELY(f.alpha != 0)) {
         mg_ss_build_lit(c, wm, a, f, bar_li > spot_li ? tables->bar_lit : nullptr);
@@ -863,4 +870,11 @@ MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDraw
     c.stamp(11);
     // 3b. black_background: white 1-px outlines on the spotlight surface
     if (MG_UNLIKELY(k.border && f.alpha != 0 && a.hdr->ring_off)) mg_ss_outlines(c, out, a, k, f, spot_li);
+}
+
+template <bool kRebuildOol, class Ctx>
+MG_HD void mg_ss_emit(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+                      MgSSWarpMem* wm, const MgSSCtaTables* tables, bool stream) {
+    mg_ss_emit_base<kRebuildOol>(c, a, k, f, wm);
+    mg_ss_emit_rest(c, out, a, k, f, wm, tables, stream);  // (its first barrier orders the patch before the copy)
 }

@@ -296,7 +296,82 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
         ctx.sync();
         int nxt = q.n;
         bool have_next = false;
-        for (int t = 0; t < T; ++t) {
+        bool piped = false;
+        if constexpr (kRollout && P::kPipelined) {
+            // ---- pipelined rollout (two-warp teams): warp 0 computes step t + 1 while warp 1 patches the base buffer
+            // for frame t; then both build the lit bitmap and copy frame t out. Auto-resets run on the whole team
+            // between two frames. (Traced launches and never-reset envs take the plain loop below.)
+            piped = true;  // this instantiation carries no other step loop (register pressure); tracing is not available
+            if (!st->live) {  // never reset (or finished without auto-reset): the steps are ignored
+                if (lane == 0)
+                    for (int t = 0; t < T; ++t) {
+                        q.io.reward[(size_t)t * q.rew_stride + env] = 0.0;
+                        q.io.done[(size_t)t * q.done_stride + env] = 1;
+                    }
+            } else {
+                MgWarpCtx c32 = ctx;  // one warp of the team, warp-local barrier
+                c32.lane = lane & 31;
+                c32.nl = 32;
+                c32.bar_id = 0;
+                const int wsel = lane >> 5;
+                const bool stream = (q.io.flags & MG_FLAG_STREAM_OBS) != 0;
+                P::pipe_begin(ctx, env, scratch);
+                if (wsel == 0) {
+                    const int a0 = (int)act0, a1 = (int)act1;
+                    if (lane == 0 && T > 1) {
+                        const int64_t* a = q.io.actions + (size_t)q.act_stride + (size_t)env * q.act_dims;
+                        act0 = a[0];
+                        if (q.act_dims > 1) act1 = a[1];
+                    }
+                    P::pipe_step(c32, k, q, view, env, 0, *st, a0, a1, fr[0], scratch);
+                }
+                ctx.sync();
+                if (P::pipe_needs_deferred(scratch)) P::pipe_deferred(ctx, k, q, view, env, 0, *st, fr[0], scratch);
+                for (int t = 0; t < T; ++t) {
+                    const Frame& f = fr[t & 1];
+                    if (wsel == 0) {
+                        if (t + 1 < T) {
+                            const int a0 = (int)act0, a1 = (int)act1;
+                            if (lane == 0 && t + 2 < T) {
+                                const int64_t* a = q.io.actions + (size_t)(t + 2) * q.act_stride + (size_t)env * q.act_dims;
+                                act0 = a[0];
+                                if (q.act_dims > 1) act1 = a[1];
+                            }
+                            P::pipe_step(c32, k, q, view, env, t + 1, *st, a0, a1, fr[(t + 1) & 1], scratch);
+                        }
+                    } else {
+                        P::emit_base(c32, view, k, f, scratch);
+                    }
+                    ctx.sync();
+                    const bool deferred = t + 1 < T && P::pipe_needs_deferred(scratch);
+                    uint8_t* dst = q.io.obs + (size_t)(t % q.ring_n) * q.obs_stride + (size_t)env * MG_FRAME_BYTES;
+                    P::emit_rest(ctx, dst, view, k, f, scratch, stream);
+                    ctx.sync();
+                    if (deferred) P::pipe_deferred(ctx, k, q, view, env, t + 1, *st, fr[(t + 1) & 1], scratch);
+                }
+            }
+            {
+                // the team's next env: claimed after its last step; record + first actions fetched now
+                if (lane == 0)
+                    *grab = sched ? (uint32_t)total_teams + atomicAdd(sched, 1u)
+                                  : (uint32_t)blockIdx.x + atomicAdd(&hdr->next, 1u) * (uint32_t)G;
+                ctx.sync();
+                nxt = (int)*grab;
+                have_next = nxt < q.n;
+                if (have_next) {
+                    const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)nxt * kStateBytes);
+#pragma unroll
+                    for (int w = 0; w < kPerLane; ++w)
+                        if (lane + kTeam * w < kWords) pre[w] = g[lane + kTeam * w];
+                    if (lane == 0) {
+                        const int64_t* a = q.io.actions + (size_t)nxt * q.act_dims;
+                        act0 = a[0];
+                        if (q.act_dims > 1) act1 = a[1];
+                    }
+                }
+            }
+        }
+        for (int t = 0; t < ((kRollout && P::kPipelined) ? 0 : T); ++t) {
             const int a0 = (int)act0, a1 = (int)act1;
             uint64_t* trow = tracing ? q.io.trace + (size_t)env * MG_TRACE_COLS : nullptr;
             ctx.trow = trow;

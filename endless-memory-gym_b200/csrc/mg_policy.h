@@ -152,6 +152,7 @@ MG_HD void mg_env_logic_coop(Ctx& c, const typename E::K& k, const MgKIO& q, con
 }
 
 struct MMPolicy {
+    static constexpr bool kPipelined = false;
     static constexpr int kHelperWarps = 0;
     static constexpr int kWarpExtra = 0, kCtaExtra = 0;
     static constexpr int kStageReserve = 8 * 1024;  // shared memory kept free for the staged asset prefix (7.4 KB by default)
@@ -192,6 +193,7 @@ struct MMPolicy {
 };
 
 struct MPPolicy {
+    static constexpr bool kPipelined = false;
     static constexpr int kHelperWarps = 0;
     static constexpr int kWarpExtra = (int)((sizeof(MgGenMem) + 127) / 128 * 128);
     static constexpr int kCtaExtra = (int)((sizeof(MgGenCta) + 127) / 128 * 128);
@@ -241,6 +243,7 @@ struct MPPolicy {
 };
 
 struct EPPolicy {
+    static constexpr bool kPipelined = false;
     static constexpr int kHelperWarps = 7;  // rollout launches: path generation ahead of time (mg_ep_logic.h)
     static constexpr int kWarpExtra = (int)((sizeof(MgEPWarpMem) + 127) / 128 * 128);
     static constexpr int kGenCtaBytes = (int)((sizeof(MgGenCta) + 127) / 128 * 128);
@@ -443,6 +446,103 @@ struct SSPolicyT {
             }
             c.sync();
         }
+    }
+
+    // ---- pipelined rollouts (mg_kernels.cu): the first warp of the team computes step t + 1 while the second one
+    // patches the base buffer for frame t; both then build the lit bitmap and copy frame t out. Resets (and the
+    // endless variant, whose coin respawn borrows the base buffer mid-step) stay on the whole team.
+    static constexpr bool kPipelined = TW == 2;
+    template <class Ctx>
+    static MG_HD void pipe_begin(Ctx& c, int env, const MgScratch& sc) {
+        MgSSWarpMem* wm = reinterpret_cast<MgSSWarpMem*>(sc.warp);
+        if (c.lane == 0 && wm->desc.env != env) {  // the team moved on to another env: a foreign scene in the base buffer
+            wm->desc.valid = 0;
+            wm->desc.env = env;
+        }
+    }
+    // step(): A / B / C on ONE warp (`c` = its 32 lanes); the frame goes to `f`. What is left for the whole team is
+    // announced in tmp.post: 3 = auto-reset, 4 = (endless) the coin was collected — the respawn borrows the base
+    // buffer, so the step stops after C1 and pipe_deferred finishes it.
+    template <class Ctx>
+    static MG_HD void pipe_step(Ctx& c, const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0,
+                                int a1, Frame& f, const MgScratch& sc) {
+        MgSSStepTmp& tmp = *reinterpret_cast<MgSSStepTmp*>(reinterpret_cast<MgSSWarpMem*>(sc.warp)->step_tmp);
+        c.sync();  // every lane is done with the previous step's hand-over words
+        if (c.lane == 0) {
+            tmp.action = 2;
+            tmp.post = 0;
+            mg_ss_step_a(k, s, a0, a1, tmp);
+        }
+        c.sync();
+        mg_ss_step_b(c, k, trig(a), s, tmp, f);
+        c.sync();
+        if (c.lane == 0) {
+            if constexpr (kEndless) {
+                if (mg_ess_step_c1(k, s, tmp, tmp.carry)) {
+                    tmp.post = 4;
+                    return;
+                }
+            }
+            pipe_finish(k, q, env, t, s, tmp, f);
+        }
+    }
+    // C / C2 on one lane: rewards, done, episode statistics, the frame description
+    static MG_HD void pipe_finish(const K& k, const MgKIO& q, int env, int t, State& s, MgSSStepTmp& tmp, Frame& f) {
+        double* const info_out = q.io.info + (size_t)t * q.info_stride + MG_INFO_COLS * (size_t)env;
+        double reward;
+        bool done;
+        if constexpr (kEndless)
+            done = mg_ess_step_c2(k, s, tmp, tmp.carry, reward, info_out, f,
+                                  q.io.ground_truth ? q.io.ground_truth + MG_GT_COLS * (size_t)env : nullptr);
+        else
+            done = mg_ss_step_c(k, s, tmp, reward, info_out, f);
+        q.io.reward[(size_t)t * q.rew_stride + env] = reward;
+        q.io.done[(size_t)t * q.done_stride + env] = done ? 1 : 0;
+        tmp.post = done ? 3 : 0;  // a rollout always auto-resets
+    }
+    static MG_HD bool pipe_needs_deferred(const MgScratch& sc) {
+        return reinterpret_cast<const MgSSStepTmp*>(reinterpret_cast<const MgSSWarpMem*>(sc.warp)->step_tmp)->post != 0;
+    }
+    // what a step left for the whole team (between two frames, when nobody touches the base buffer): the coin respawn
+    // of the endless variant + the rest of that step, and the auto-reset. `f` holds the step's frame and, after an
+    // auto-reset, receives the first frame of the next episode.
+    template <class Ctx>
+    static MG_HD void pipe_deferred(Ctx& c, const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s,
+                                    Frame& f, const MgScratch& sc) {
+        MgSSWarpMem* wm = reinterpret_cast<MgSSWarpMem*>(sc.warp);
+        MgSSStepTmp& tmp = *reinterpret_cast<MgSSStepTmp*>(wm->step_tmp);
+        MgSSSampler& g = *reinterpret_cast<MgSSSampler*>(wm->base);
+        MgSSResetTmp& rt = *reinterpret_cast<MgSSResetTmp*>(wm->base + sizeof(MgSSSampler));
+        if constexpr (kEndless) {
+            if (tmp.post == 4) {
+                if (c.lane == 0) wm->desc.valid = 0;
+                mg_ess_spawn_coin(c, k.clamp_off, s, g, rt, true);
+                if (c.lane == 0) pipe_finish(k, q, env, t, s, tmp, f);
+                c.sync();
+            }
+        }
+        if (tmp.post == 3) {
+            if (q.io.final_obs) {
+                emit_cold(c, q.io.final_obs + (size_t)env * MG_FRAME_BYTES, a, k, f, sc);
+                c.sync();
+            }
+            if (c.lane == 0) wm->desc.valid = 0;
+            if constexpr (kEndless)
+                mg_ess_reset_env(c, k, s, f, g, rt, q.io.ground_truth ? q.io.ground_truth + MG_GT_COLS * (size_t)env : nullptr);
+            else
+                mg_ss_reset_env(c, k, s, f, g, rt);
+            c.sync();
+        }
+    }
+    template <class Ctx>
+    static MG_HD void emit_base(Ctx& c, const MgAssetView& a, const K& k, const Frame& f, const MgScratch& sc) {
+        mg_ss_emit_base<kEndless>(c, a, draw_k(k, f), f, reinterpret_cast<MgSSWarpMem*>(sc.warp));
+    }
+    template <class Ctx>
+    static MG_HD void emit_rest(Ctx& c, uint8_t* dst, const MgAssetView& a, const K& k, const Frame& f, const MgScratch& sc,
+                                bool stream) {
+        mg_ss_emit_rest(c, dst, a, draw_k(k, f), f, reinterpret_cast<MgSSWarpMem*>(sc.warp),
+                        reinterpret_cast<const MgSSCtaTables*>(sc.cta), stream);
     }
 
     static MG_HD MgSSDrawK draw_k(const K& k, const Frame& f) {

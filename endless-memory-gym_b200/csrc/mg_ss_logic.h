@@ -339,6 +339,11 @@ MG_HD void mg_ss_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, M
 
 // step(), split so that the spotlights (the only per-step work that grows with the scene) advance in
 // parallel, one lane per spotlight: A (one lane) -> B (all lanes) -> C (one lane)
+// C1 -> C2 of the endless variant (registers in the plain step; shared memory when the step is split in two)
+struct MgESSCarry {
+    double reward;
+    int32_t red_now, bg_red, spot_done;
+};
 struct MgSSStepTmp {
     int32_t action;   // what the logic lane decided for this call: 0 idle, 1 reset, 2 step (4: + coin respawn)
     int32_t post;     // ... and after the step: 3 = auto-reset
@@ -346,6 +351,7 @@ struct MgSSStepTmp {
     int32_t n_proc;   // spotlights drawn this step
     int32_t hits;     // how many of them contain the agent (is_agent_inside)
     uint8_t proc[MG_SS_MAXSPOTS];  // their indices in s.spots
+    MgESSCarry carry;
 };
 
 // A: agent move, top-bar bookkeeping, light dimming, spawn, and WHICH spotlights are drawn this step
@@ -639,10 +645,6 @@ MG_HD void mg_ess_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, 
 
 // C1 (one lane): health / background after the spotlights moved, and the coin hit test. Returns true when the
 // coin was collected: the warp then respawns it cooperatively (mg_ess_spawn_coin) before C2 runs.
-struct MgESSCarry {
-    double reward;
-    int32_t red_now, bg_red, spot_done;
-};
 MG_HD bool mg_ess_step_c1(const MgSSK& k, MgSSState& s, const MgSSStepTmp& tmp, MgESSCarry& cy) {
     const int cx = tmp.cx, cyy = tmp.cy;
     double reward = 0.0, r = 0.0;
