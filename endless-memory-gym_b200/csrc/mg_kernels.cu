@@ -326,7 +326,9 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
                     P::pipe_step(c32, k, q, view, env, 0, *st, a0, a1, fr[0], scratch);
                 }
                 ctx.sync();
-                if (P::pipe_needs_deferred(scratch)) P::pipe_deferred(ctx, k, q, view, env, 0, *st, fr[0], scratch);
+                const bool deferred0 = P::pipe_needs_deferred(scratch);
+                ctx.sync();  // (read by everyone before warp 0 starts the next step and rewrites the word)
+                if (deferred0) P::pipe_deferred(ctx, k, q, view, env, 0, *st, fr[0], scratch);
                 for (int t = 0; t < T; ++t) {
                     const Frame& f = fr[t & 1];
                     if (wsel == 0) {

@@ -521,7 +521,9 @@ struct SSPolicyT {
                 c.sync();
             }
         }
-        if (tmp.post == 3) {
+        const bool reset = tmp.post == 3;
+        c.sync();  // every thread has read the hand-over word: the next step's logic may rewrite it
+        if (reset) {
             if (q.io.final_obs) {
                 emit_cold(c, q.io.final_obs + (size_t)env * MG_FRAME_BYTES, a, k, f, sc);
                 c.sync();
