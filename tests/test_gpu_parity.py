@@ -287,3 +287,29 @@ def test_emp_rollout_with_and_without_helper_warps(monkeypatch):
         outs.append((ring, rew, dn, env.state.clone()))
     assert all(torch.equal(x, y) for x, y in zip(*outs))
     assert int(outs[0][2].sum()) > 3 * n  # several episodes per env: the hand-over was exercised
+
+
+@pytest.mark.parametrize("env_id", ["SearingSpotlights-v0", "Endless-SearingSpotlights-v0", "MortarMayhem-v0",
+                                    "Endless-MysteryPath-v0"])
+def test_rollout_final_obs_equals_step_loop(env_id):
+    """Terminal frames (final_obs) written inside a rollout launch — for Searing Spotlights from the deferred
+    auto-reset of the pipelined loop — equal what the step loop leaves behind."""
+    n, T = 600, 70
+    opts = {"max_steps": 25} if "SearingSpotlights" in env_id else None
+    a = mg.make(env_id, num_envs=n, device=DEV, final_obs=True)
+    b = mg.make(env_id, num_envs=n, device=DEV, final_obs=True)
+    acts = _random_actions(a, T, 123)
+    a.reset(seed=21, options=opts)
+    b.reset(seed=21, options=opts)
+    ring = torch.zeros((2, n, 84, 84, 3), dtype=torch.uint8, device=DEV)
+    rew = torch.zeros((T, n), dtype=torch.float64, device=DEV)
+    dn = torch.zeros((T, n), dtype=torch.bool, device=DEV)
+    a.rollout(acts, ring, rew, dn)
+    ever = torch.zeros(n, dtype=torch.bool, device=DEV)
+    for t in range(T):
+        o, r, d, _, _ = b.step(acts[t])
+        assert torch.equal(r, rew[t]) and torch.equal(d, dn[t]), t
+        ever |= d
+    assert ever.any()
+    assert torch.equal(o, ring[(T - 1) % 2])
+    assert torch.equal(a.final_obs[ever], b.final_obs[ever]) and torch.equal(a.state, b.state)
