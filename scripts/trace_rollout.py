@@ -1,4 +1,5 @@
-"""Measurement helper: phase timestamps of every env's LAST step inside a rollout launch (mg_rollout_io.trace)."""
+"""Measurement helper: phase timestamps of every env's LAST step inside a rollout launch (mg_rollout_io.trace).
+The pipelined Searing-Spotlights rollout kernels carry no stamps (only the launch time is printed for them)."""
 import os
 import sys
 
