@@ -296,12 +296,10 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
         ctx.sync();
         int nxt = q.n;
         bool have_next = false;
-        bool piped = false;
         if constexpr (kRollout && P::kPipelined) {
             // ---- pipelined rollout (two-warp teams): warp 0 computes step t + 1 while warp 1 patches the base buffer
             // for frame t; then both build the lit bitmap and copy frame t out. Auto-resets run on the whole team
-            // between two frames. (Traced launches and never-reset envs take the plain loop below.)
-            piped = true;  // this instantiation carries no other step loop (register pressure); tracing is not available
+            // between two frames. This instantiation carries no other step loop (register pressure): no trace stamps.
             if (!st->live) {  // never reset (or finished without auto-reset): the steps are ignored
                 if (lane == 0)
                     for (int t = 0; t < T; ++t) {
