@@ -37,7 +37,7 @@ struct HostCtx {
 // mirrors mg_env_kernel (mg_kernels.cu) with one "warp": env-major loop, all n_steps steps of an env back to
 // back, a persistent frame buffer and persistent per-warp scratch (so incremental paths are exercised)
 template <class P>
-int run_q(const typename P::K& k, const void* assets, void* state, MgKIO q) {
+int run_q(const typename P::K& k, const void* assets, void* state, MgKIO q, bool rollout = false) {
     typedef typename P::State State;
     typedef typename P::Frame Frame;
     const bool kCheckClean = P::restores_clean(k);
@@ -55,6 +55,35 @@ int run_q(const typename P::K& k, const void* assets, void* state, MgKIO q) {
     ctx.copy_frame(buf, view.tmpl[0]);
     for (int env = 0; env < q.n; ++env) {
         State* st = reinterpret_cast<State*>((uint8_t*)state + (size_t)env * sizeof(State));
+        if constexpr (P::kPipelined) {
+            // mirrors the pipelined rollout loop of mg_env_kernel<P, true>: step t + 1 is computed BEFORE frame t is
+            // rasterised, auto-resets (and the endless coin respawn) are deferred to the gap between two frames
+            if (rollout && st->live) {
+                const auto act = [&](int t, int& a0, int& a1) {
+                    const int64_t* a = q.io.actions + (size_t)t * q.act_stride + (size_t)env * q.act_dims;
+                    a0 = (int)a[0];
+                    a1 = q.act_dims > 1 ? (int)a[1] : 0;
+                };
+                Frame fr[2];
+                int a0, a1;
+                P::pipe_begin(ctx, env, scratch);
+                act(0, a0, a1);
+                P::pipe_step(ctx, k, q, view, env, 0, *st, a0, a1, fr[0], scratch);
+                if (P::pipe_needs_deferred(scratch)) P::pipe_deferred(ctx, k, q, view, env, 0, *st, fr[0], scratch);
+                for (int t = 0; t < q.n_steps; ++t) {
+                    if (t + 1 < q.n_steps) {
+                        act(t + 1, a0, a1);
+                        P::pipe_step(ctx, k, q, view, env, t + 1, *st, a0, a1, fr[(t + 1) & 1], scratch);
+                    }
+                    P::emit_base(ctx, view, k, fr[t & 1], scratch);
+                    const bool deferred = t + 1 < q.n_steps && P::pipe_needs_deferred(scratch);
+                    uint8_t* dst = q.io.obs + (size_t)(t % q.ring_n) * q.obs_stride + (size_t)env * MG_FRAME_BYTES;
+                    P::emit_rest(ctx, dst, view, k, fr[t & 1], scratch, false);
+                    if (deferred) P::pipe_deferred(ctx, k, q, view, env, t + 1, *st, fr[(t + 1) & 1], scratch);
+                }
+                continue;
+            }
+        }
         for (int t = 0; t < q.n_steps; ++t) {
             MgFrameJob job;
             Frame fr[2];
@@ -121,7 +150,7 @@ int run_rollout(const typename P::K& k, const void* assets, void* state, const m
     q.rew_stride = n;
     q.done_stride = n;
     q.info_stride = r->info_per_step ? (int64_t)n * MG_INFO_COLS : 0;
-    return run_q<P>(k, assets, state, q);
+    return run_q<P>(k, assets, state, q, true);
 }
 }  // namespace
 
