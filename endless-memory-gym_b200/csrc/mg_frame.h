@@ -847,21 +847,24 @@ MG_HD void mg_ss_emit_base(Ctx& c, const MgAssetView& a, const MgSSDrawK& k, con
     c.stamp(9);
 }
 
+// 2. which pixels stay undimmed: the colour-keyed discs, and whatever is painted above the spotlight layer
 template <class Ctx>
-MG_HD void mg_ss_emit_rest(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
-                           MgSSWarpMem* wm, const MgSSCtaTables* tables, bool stream) {
-    const int spot_li = k.spot_li, bar_li = k.bar_li;
-    const bool simple = mg_ss_simple_order(k);
-    // 2. which pixels stay undimmed: the colour-keyed discs, and whatever is painted above the spotlight layer
+MG_HD void mg_ss_emit_lit(Ctx& c, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f, MgSSWarpMem* wm,
+                          const MgSSCtaTables* tables) {
     if (MG_LIKELY(f.alpha != 0)) {
-        mg_ss_build_lit(c, wm, a, f, bar_li > spot_li ? tables->bar_lit : nullptr);
-        if (MG_UNLIKELY(!simple)) {
+        mg_ss_build_lit(c, wm, a, f, k.bar_li > k.spot_li ? tables->bar_lit : nullptr);
+        if (MG_UNLIKELY(!mg_ss_simple_order(k))) {
             c.sync();
-            mg_ss_lit_over(c, wm, a, k, f, spot_li);
+            mg_ss_lit_over(c, wm, a, k, f, k.spot_li);
         }
     }
-    c.sync();
-    // 3. frame = lit ? base : base dimmed by alpha (SDL: d + trunc((0 - d) * A / 255))
+}
+
+// 3. the copy (after a barrier: base buffer and lit bitmap are complete)
+template <class Ctx>
+MG_HD void mg_ss_emit_copy(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+                           MgSSWarpMem* wm, const MgSSCtaTables* tables, bool stream) {
+    // frame = lit ? base : base dimmed by alpha (SDL: d + trunc((0 - d) * A / 255))
     c.stamp(10);
     if (MG_LIKELY(f.alpha == 255))
         mg_ss_masked_copy_black(c, out, wm, tables, stream);
@@ -869,7 +872,15 @@ MG_HD void mg_ss_emit_rest(Ctx& c, uint8_t* out, const MgAssetView& a, const MgS
         mg_ss_masked_copy_cold(c, out, wm, tables, f.alpha, stream);
     c.stamp(11);
     // 3b. black_background: white 1-px outlines on the spotlight surface
-    if (MG_UNLIKELY(k.border && f.alpha != 0 && a.hdr->ring_off)) mg_ss_outlines(c, out, a, k, f, spot_li);
+    if (MG_UNLIKELY(k.border && f.alpha != 0 && a.hdr->ring_off)) mg_ss_outlines(c, out, a, k, f, k.spot_li);
+}
+
+template <class Ctx>
+MG_HD void mg_ss_emit_rest(Ctx& c, uint8_t* out, const MgAssetView& a, const MgSSDrawK& k, const MgSSFrame& f,
+                           MgSSWarpMem* wm, const MgSSCtaTables* tables, bool stream) {
+    mg_ss_emit_lit(c, a, k, f, wm, tables);
+    c.sync();
+    mg_ss_emit_copy(c, out, a, k, f, wm, tables, stream);
 }
 
 template <bool kRebuildOol, class Ctx>

@@ -153,6 +153,12 @@ struct MgWarpCtx {
     }
 };
 
+// pipelined Searing-Spotlights rollouts: 1 = the raster warp also builds the lit bitmap while the logic warp computes the
+// next step (measured: see profiles/r01b_summary.md), 0 = both warps build it after the barrier
+#ifndef MG_SS_LIT_EARLY
+#define MG_SS_LIT_EARLY 0
+#endif
+
 // ---- the kernel ----------------------------------------------------------------------------------
 // A "team" = the threads that own one env at a time: one warp, or P::kTeamWarps warps on a named barrier for
 // env types whose per-frame work is instruction-bound (more warps per frame buffer hide more latency).
@@ -340,12 +346,18 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
                             P::pipe_step(c32, k, q, view, env, t + 1, *st, a0, a1, fr[(t + 1) & 1], scratch);
                         }
                     } else {
-                        P::emit_base(c32, view, k, f, scratch);
+                        if (MG_SS_LIT_EARLY)
+                            P::emit_base_lit(c32, view, k, f, scratch);
+                        else
+                            P::emit_base(c32, view, k, f, scratch);
                     }
                     ctx.sync();
                     const bool deferred = t + 1 < T && P::pipe_needs_deferred(scratch);
                     uint8_t* dst = q.io.obs + (size_t)(t % q.ring_n) * q.obs_stride + (size_t)env * MG_FRAME_BYTES;
-                    P::emit_rest(ctx, dst, view, k, f, scratch, stream);
+                    if (MG_SS_LIT_EARLY)
+                        P::emit_copy(ctx, dst, view, k, f, scratch, stream);
+                    else
+                        P::emit_rest(ctx, dst, view, k, f, scratch, stream);
                     ctx.sync();
                     if (deferred) P::pipe_deferred(ctx, k, q, view, env, t + 1, *st, fr[(t + 1) & 1], scratch);
                 }

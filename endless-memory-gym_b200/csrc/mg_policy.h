@@ -540,6 +540,19 @@ struct SSPolicyT {
     static MG_HD void emit_base(Ctx& c, const MgAssetView& a, const K& k, const Frame& f, const MgScratch& sc) {
         mg_ss_emit_base<kEndless>(c, a, draw_k(k, f), f, reinterpret_cast<MgSSWarpMem*>(sc.warp));
     }
+    // variant of the split for the pipelined loop: the lit bitmap joins the base patch on the raster warp
+    template <class Ctx>
+    static MG_HD void emit_base_lit(Ctx& c, const MgAssetView& a, const K& k, const Frame& f, const MgScratch& sc) {
+        const MgSSDrawK d = draw_k(k, f);
+        mg_ss_emit_base<kEndless>(c, a, d, f, reinterpret_cast<MgSSWarpMem*>(sc.warp));
+        mg_ss_emit_lit(c, a, d, f, reinterpret_cast<MgSSWarpMem*>(sc.warp), reinterpret_cast<const MgSSCtaTables*>(sc.cta));
+    }
+    template <class Ctx>
+    static MG_HD void emit_copy(Ctx& c, uint8_t* dst, const MgAssetView& a, const K& k, const Frame& f, const MgScratch& sc,
+                                bool stream) {
+        mg_ss_emit_copy(c, dst, a, draw_k(k, f), f, reinterpret_cast<MgSSWarpMem*>(sc.warp),
+                        reinterpret_cast<const MgSSCtaTables*>(sc.cta), stream);
+    }
     template <class Ctx>
     static MG_HD void emit_rest(Ctx& c, uint8_t* dst, const MgAssetView& a, const K& k, const Frame& f, const MgScratch& sc,
                                 bool stream) {
