@@ -340,6 +340,16 @@ class MemoryGymVecEnv:
         self._be.step_many(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(),
                            self._many_ios, T, self.num_envs, self._be.stream(self.device))
 
+    def capture_step(self, obs_out=None):
+        """One CUDA graph for the whole host-driven step: actions pinned-host -> device, the step kernel, reward + done
+        device -> pinned-host. Returns a ``StepGraph``: write the actions into ``.actions_host``, call ``.replay()``
+        (asynchronous, one graph launch instead of three stream operations + the library call), wait on
+        ``.done_event`` before reading ``.results_host`` (reward f64[N] then done u8[N]); observations are in ``.obs``
+        on the device. The env must have been reset; reset() with other options invalidates the graph."""
+        if self._params is None:
+            raise L.MemGymError("capture_step() called before reset()")
+        return StepGraph(self, obs_out)
+
     def policy_obs(self, obs=None, out=None):
         """The consumer step (``mg_obs_to_policy_bf16``): ``obs`` uint8[N,84,84,3] (default: this env's observation
         buffer) -> bf16[N,3,84,84] = ``obs.permute(0, 3, 1, 2) / 255``, bit-identical to torch's float32 division and
@@ -377,6 +387,42 @@ class MemoryGymVecEnv:
         if self.task_b:
             self.vector_obs.copy_(sd["vector_obs"])
         self._seeded = True
+
+
+class StepGraph:
+    """See ``MemoryGymVecEnv.capture_step``."""
+
+    def __init__(self, env, obs_out=None):
+        self.env = env
+        n = env.num_envs
+        self.obs = env.obs if obs_out is None else obs_out
+        self.actions_host = torch.zeros_like(env._actions_dev, device="cpu").pin_memory()
+        self.results_host = torch.zeros(9 * n, dtype=torch.uint8).pin_memory()
+        self.done_event = torch.cuda.Event()
+        self._a_dev = torch.zeros_like(env._actions_dev)
+        # the warm-up below runs one real step: everything it touches is put back afterwards
+        keep = [(t, t.clone()) for t in (env.state, self.obs, env.results, env.info) + ((env.final_obs,) if env.final_obs is not None else ())]
+        side = torch.cuda.Stream(device=env.device)
+        side.wait_stream(torch.cuda.current_stream(env.device))
+        with torch.cuda.stream(side):
+            self._body()  # warm-up outside the capture (lazy initialisation in the library / driver)
+        torch.cuda.current_stream(env.device).wait_stream(side)
+        torch.cuda.synchronize(env.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        for t, saved in keep:
+            t.copy_(saved)
+        torch.cuda.synchronize(env.device)
+
+    def _body(self):
+        self._a_dev.copy_(self.actions_host, non_blocking=True)
+        self.env.step(self._a_dev, obs_out=self.obs)
+        self.results_host.copy_(self.env.results, non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        self.done_event.record()
 
 
 class MemoryGymEnv:

@@ -313,3 +313,25 @@ def test_rollout_final_obs_equals_step_loop(env_id):
     assert ever.any()
     assert torch.equal(o, ring[(T - 1) % 2])
     assert torch.equal(a.final_obs[ever], b.final_obs[ever]) and torch.equal(a.state, b.state)
+
+
+def test_step_graph_replay_equals_step():
+    """capture_step(): one CUDA graph = H2D of the actions + the step kernel + D2H of reward/done; its replays give
+    exactly what step() gives, and capturing does not advance the envs."""
+    n = 512
+    a = mg.make("MortarMayhem-v0", num_envs=n, device=DEV)
+    b = mg.make("MortarMayhem-v0", num_envs=n, device=DEV)
+    a.reset(seed=4)
+    b.reset(seed=4)
+    acts = _random_actions(a, 70, 6)
+    graph = a.capture_step()
+    assert torch.equal(a.state, b.state) and torch.equal(a.obs, b.obs)
+    for t in range(70):
+        graph.actions_host.copy_(acts[t].cpu())
+        graph.replay()
+        graph.done_event.synchronize()
+        o, r, d, _, _ = b.step(acts[t])
+        assert torch.equal(graph.obs, o), t
+        assert torch.equal(graph.results_host[:8 * n].view(torch.float64), r.cpu()), t
+        assert torch.equal(graph.results_host[8 * n:].bool(), d.cpu()), t
+    assert torch.equal(a.state, b.state)
