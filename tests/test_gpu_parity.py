@@ -335,3 +335,26 @@ def test_step_graph_replay_equals_step():
         assert torch.equal(graph.results_host[:8 * n].view(torch.float64), r.cpu()), t
         assert torch.equal(graph.results_host[8 * n:].bool(), d.cpu()), t
     assert torch.equal(a.state, b.state)
+
+
+@pytest.mark.parametrize("env_id", ["MortarMayhem-v0", "SearingSpotlights-v0", "Endless-SearingSpotlights-v0",
+                                    "Endless-MysteryPath-v0", "MysteryPath-v0"])
+def test_rollout_edge_geometries(env_id):
+    """Tiny batches and one- or two-step rollouts (more warps and helper warps than envs, a pipeline with nothing to
+    overlap, ring of one slot) still equal the step loop."""
+    for n, T, ring_n in ((1, 1, 1), (1, 2, 1), (2, 5, 2), (3, 33, 1), (149, 3, 3)):
+        a = mg.make(env_id, num_envs=n, device=DEV)
+        b = mg.make(env_id, num_envs=n, device=DEV)
+        acts = _random_actions(a, T, 50 + n)
+        a.reset(seed=n)
+        b.reset(seed=n)
+        ring = torch.zeros((ring_n, n, 84, 84, 3), dtype=torch.uint8, device=DEV)
+        rew = torch.zeros((T, n), dtype=torch.float64, device=DEV)
+        dn = torch.zeros((T, n), dtype=torch.bool, device=DEV)
+        a.rollout(acts, ring, rew, dn)
+        a.rollout(acts, ring, rew, dn)  # a second launch on the same records
+        for rep in range(2):
+            for t in range(T):
+                o, r, d, _, _ = b.step(acts[t])
+        assert torch.equal(r, rew[T - 1]) and torch.equal(d, dn[T - 1]), (n, T)
+        assert torch.equal(o, ring[(T - 1) % ring_n]) and torch.equal(a.state, b.state), (n, T)
