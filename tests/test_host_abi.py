@@ -234,3 +234,18 @@ def test_consumer_step_rejects_bad_pointers_without_a_device():
     assert lib.mg_obs_to_policy_bf16(base + 1, base + 32, 1, None) == -1  # misaligned
     assert b"aligned" in lib.mg_last_error()
     assert lib.mg_obs_to_policy_bf16(base, base + 21168, 0, None) == 0            # empty batch: nothing to do
+
+
+def test_product_never_touches_the_oracle_or_a_cpu_path():
+    """The shipped package (Python host + C/CUDA sources) neither imports nor links anything under oracle/ or
+    tests/hostsim, and make() refuses to run without the CUDA library / a CUDA device."""
+    pkg = os.path.join(ROOT, "endless-memory-gym_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cpp", ".h", "Makefile")):
+                continue
+            text = open(os.path.join(dirpath, f), errors="ignore").read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+            assert "memgym_oracle" not in text and "hostsim" not in text.replace("tests/hostsim", ""), f
+    mk = open(os.path.join(pkg, "csrc", "Makefile")).read()
+    assert "oracle" not in mk and "hostsim" not in mk
