@@ -358,3 +358,40 @@ def test_rollout_edge_geometries(env_id):
                 o, r, d, _, _ = b.step(acts[t])
         assert torch.equal(r, rew[T - 1]) and torch.equal(d, dn[T - 1]), (n, T)
         assert torch.equal(o, ring[(T - 1) % ring_n]) and torch.equal(a.state, b.state), (n, T)
+
+
+@pytest.mark.parametrize("env_id,opts", [
+    ("SearingSpotlights-v0", {"max_steps": 50, "coins_visible": True, "exit_visible": True, "agent_visible": True,
+                              "num_coins": [2, 4], "agent_health": 3, "spot_damage": 0.7, "initial_spawns": 6,
+                              "spot_min_radius": 12.0, "spot_max_radius": 20.0, "spot_min_speed": 0.01, "spot_max_speed": 0.03}),
+    ("SearingSpotlights-v0", {"max_steps": 45, "exit_visible": True, "hide_chessboard": True, "light_threshold": 100,
+                              "light_dim_off_duration": 3, "show_last_action": False, "visual_feedback": False,
+                              "initial_spawn_interval": 3, "spawn_interval_threshold": 2, "num_spawns": 9}),
+    ("SearingSpotlights-v0", {"max_steps": 40, "black_background": True, "num_coins": [3]}),
+    ("SearingSpotlights-v0", {"max_steps": 40, "sample_agent_position": False, "light_dim_off_duration": 0,
+                              "show_last_positive_reward": False, "agent_visible": True, "agent_scale": 0.4, "agent_speed": 5.0}),
+    ("Endless-SearingSpotlights-v0", {"max_steps": 55, "coins_visible": True, "agent_visible": True, "agent_health": 3,
+                                      "spot_damage": 0.7, "initial_spawns": 6, "spawn_interval": 7, "coin_scale": 1.0}),
+    ("Endless-SearingSpotlights-v0", {"steps_per_coin": 30, "hide_chessboard": True, "light_threshold": 100,
+                                      "light_dim_off_duration": 3, "visual_feedback": False, "coin_show_duration": 20}),
+    ("Endless-SearingSpotlights-v0", {"coin_enabled": False, "max_steps": 35, "agent_visible": True, "coins_visible": True}),
+    ("Endless-SearingSpotlights-v0", {"black_background": True, "steps_per_coin": 25}),
+])
+def test_pipelined_rollout_with_options_equals_step_loop(env_id, opts):
+    """The pipelined Searing-Spotlights rollout kernels under non-default layer orders, dimming ramps, outlines, opaque
+    coin layers ...: every frame, reward and done of a rollout equals the step loop (which the oracle tests pin)."""
+    n, T = 200, 90
+    a = mg.make(env_id, num_envs=n, device=DEV, final_obs=True)
+    b = mg.make(env_id, num_envs=n, device=DEV, final_obs=True)
+    acts = _random_actions(a, T, 17)
+    a.reset(seed=40, options=opts)
+    b.reset(seed=40, options=opts)
+    full = torch.zeros((T, n, 84, 84, 3), dtype=torch.uint8, device=DEV)
+    rew = torch.zeros((T, n), dtype=torch.float64, device=DEV)
+    dn = torch.zeros((T, n), dtype=torch.bool, device=DEV)
+    a.rollout(acts, full, rew, dn)
+    for t in range(T):
+        o, r, d, _, _ = b.step(acts[t])
+        assert torch.equal(o, full[t]), (t, int((o != full[t]).sum()))
+        assert torch.equal(r, rew[t]) and torch.equal(d, dn[t]), t
+    assert dn.any() and torch.equal(a.state, b.state) and torch.equal(a.final_obs, b.final_obs)
