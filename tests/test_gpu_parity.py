@@ -395,3 +395,37 @@ def test_pipelined_rollout_with_options_equals_step_loop(env_id, opts):
         assert torch.equal(o, full[t]), (t, int((o != full[t]).sum()))
         assert torch.equal(r, rew[t]) and torch.equal(d, dn[t]), t
     assert dn.any() and torch.equal(a.state, b.state) and torch.equal(a.final_obs, b.final_obs)
+
+
+@pytest.mark.parametrize("env_id,opts", [
+    ("Endless-MysteryPath-v0", {"camera_offset_scale": 1.7, "show_background": True, "show_stamina": True,
+                                "agent_speed": 13.0, "max_steps": 30, "agent_scale": 0.5}),
+    ("Endless-MysteryPath-v0", {"camera_offset_scale": 0.0, "stamina_level": 9, "reward_fall_off": -0.3,
+                                "reward_path_progress_dense": 0.02, "reward_step": -0.001}),
+    ("Endless-MysteryPath-v0", {"camera_offset_scale": 9.0, "agent_speed": 7.0, "stamina_level": 35,
+                                "show_stamina": True, "visual_feedback": False}),
+    ("MysteryPath-Grid-v0", {"max_steps": 30, "show_origin": True}),
+    ("Endless-MortarMayhem-v0", {"explosion_delay": [4], "explosion_duration": [2], "agent_speed": 5.0}),
+    ("MortarMayhemB-v0", {"command_count": [1, 3], "explosion_delay": [4], "explosion_duration": [2]}),
+])
+def test_rollout_with_options_equals_step_loop(env_id, opts):
+    """Rollout launches (helper warps for Endless Mystery Path, global work counter, record on chip) under option
+    sets equal the step loop frame by frame."""
+    n, T = 200, 100
+    a = mg.make(env_id, num_envs=n, device=DEV)
+    b = mg.make(env_id, num_envs=n, device=DEV)
+    acts = _random_actions(a, T, 19)
+    a.reset(seed=60, options=opts)
+    b.reset(seed=60, options=opts)
+    full = torch.zeros((T, n, 84, 84, 3), dtype=torch.uint8, device=DEV)
+    rew = torch.zeros((T, n), dtype=torch.float64, device=DEV)
+    dn = torch.zeros((T, n), dtype=torch.bool, device=DEV)
+    a.rollout(acts, full, rew, dn)
+    for t in range(T):
+        o, r, d, _, _ = b.step(acts[t])
+        o = o["visual_observation"] if isinstance(o, dict) else o
+        assert torch.equal(o, full[t]), (t, int((o != full[t]).sum()))
+        assert torch.equal(r, rew[t]) and torch.equal(d, dn[t]), t
+    assert dn.any() and torch.equal(a.state, b.state)
+    if a.task_b:
+        assert torch.equal(a.vector_obs, b.vector_obs)
