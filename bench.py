@@ -377,7 +377,7 @@ def main():
         kernel_ms = ms / launches  # launches back to back on one stream: event time / launches = launch duration
         achieved = n * b_alg * K / (ms * 1e-3) / 1e9
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # the CPU baseline is reported by the single-GPU run only
             v = cpu_throughput(args.env, 1, args.cpu_seconds) / 1e6
             cpu = {"value": v, "unit": "M env-steps/s", "cores": 1, "kind": "port",
                    "sample": f"{args.cpu_seconds:.0f} s of single-env stepping (reset; random actions until done) "
