@@ -181,7 +181,9 @@ struct MgEPState {
     int32_t bg_scroll;     // -bg_scroll of the reference: 0 <= v < 12, a multiple of the x velocity
     int32_t n_segments;
     int32_t cur_x;         // current_node: global column, row
-    uint8_t cur_y, rot, off_path, cross_on, live, dir, pad0[2];  // dir: target_direction 0 east, 1 north, 2 south
+    uint8_t cur_y, rot, off_path, cross_on, live, dir;  // dir: target_direction 0 east, 1 north, 2 south
+    uint8_t pending;  // 1 + start row while a helper warp still owes this record its path (only inside a step launch)
+    uint8_t pad0[1];
     int16_t cross_x, cross_y;  // fall_off_rect top-left
     uint16_t n_fall, pad1;
     int16_t fall[MG_EP_MAXFALL][2];  // fall_off_locations (normalised x, y)

@@ -103,7 +103,7 @@ MG_HD bool mg_ep_prev(const MgEPState& s, int x, int y, int& px, int& py) {
 enum { MG_SPEC_EMPTY = 0, MG_SPEC_REQUESTED = 1, MG_SPEC_BUSY = 2, MG_SPEC_READY = 3 };
 struct MgEPSpec {
     uint32_t state;   // MG_SPEC_*: EMPTY -> (team) REQUESTED -> (helper) BUSY -> READY -> (team) EMPTY
-    uint32_t pad;
+    int32_t env;      // single-step launches: the env whose (already written back) record waits for its path
     MgRng before;     // the stream the three segments were (are to be) generated from
     MgRng after;      // ... and the stream after them
     MgEPSegment seg[3];
@@ -111,7 +111,10 @@ struct MgEPSpec {
 struct MgEPWarpMem {  // per-team scratch of the Endless Mystery Path kernels
     MgGenMem gen;
     int32_t helpers;  // helper warps in this launch (0: none, resets generate their own paths)
-    int32_t pad;
+    int16_t offload;  // single-step launch: an auto-reset hands its path generation to a helper (mg_ep_reset_offload)
+    int16_t pad;
+    int32_t cur_env;  // the env this team works on
+    int32_t post_env; // >= 0: its record carries a pending path; post the job once the record is written back
     MgEPSpec spec;
 };
 // what a helper warp works on: the head of an env record (stream, segment count, the first three segments)
@@ -124,12 +127,13 @@ MG_HD void mg_vstore_u32(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile u
 // EndlessMysteryPath.add_path_segment: draws the start row (first segment only), the end row, then the A* path.
 // Called by every lane of the warp (mg_mp_generate_coop); the stream in the record advances even when it fails.
 template <class Ctx>
-MG_HD_NOINLINE bool mg_ep_add_segment_coop(Ctx c, MgEPState& s, MgGenMem& m, const MgGenCta& tab) {
+MG_HD_NOINLINE bool mg_ep_add_segment_coop(Ctx c, MgEPState& s, MgGenMem& m, const MgGenCta& tab, int forced_sy = -1) {
     const int ns = s.n_segments;
     if (ns >= MG_EP_MAXSEG) return false;
     const int g7 = MG_MP_CELLS;
     MgRngR r = mg_rr_load(s.rng);
-    const int sy = ns == 0 ? mg_rr_integers(r, 0, g7) : mg_ep_end_y(s.seg[ns - 1]);
+    // (forced_sy: the start row of the first segment was already drawn, see mg_ep_reset_offload)
+    const int sy = ns == 0 ? (forced_sy >= 0 ? forced_sy : mg_rr_integers(r, 0, g7)) : mg_ep_end_y(s.seg[ns - 1]);
     const int ey = mg_rr_integers(r, 0, g7);
     c.sync();  // every lane has read the record (stream, segment count) before lane 0 rewrites it below
     uint64_t nx[2] = {0, 0};
@@ -306,11 +310,138 @@ MG_HD void mg_ep_helper_loop(Ctx& c, uint8_t* hs_bytes, uint8_t* wextra0, int we
     }
 }
 
+// ---- single-step launches: the frame first, the path later ------------------------------------------------------
+// The first frame of an episode needs only the start row (the first draw of the first segment); the three A* runs
+// are what makes a reset 20x as long as a step. In a single-step launch an auto-reset therefore draws the start
+// row, finishes everything the frame needs, and leaves the path to a helper warp, which completes the record in
+// global memory before the kernel ends. The team moves on to its next env at once.
+template <class Ctx>
+MG_HD bool mg_ep_reset_offload(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, MgEPWarpMem& wm) {
+    if (c.shfl(mg_vload_u32(&wm.spec.state), 0) != MG_SPEC_EMPTY || wm.post_env >= 0) return false;  // slot in use: do it here
+    MgRngR r = mg_rr_load(s.rng);
+    const int sy = mg_rr_integers(r, 0, MG_MP_CELLS);
+    c.sync();
+    if (c.lane == 0) {
+        mg_rr_store(r, s.rng);
+        s.t = 0;
+        s.ep_len = 0;
+        s.ep_reward = 0.0;
+        s.n_segments = 0;
+        s.pending = (uint8_t)(1 + sy);
+        s.camera_x = k.camera_offset;
+        s.bg_scroll = 0;
+        s.rot = 6;
+        s.cx = 0 * MG_MP_TILE + k.radius;
+        s.cy = sy * MG_MP_TILE + k.radius;
+        s.cur_x = 0;
+        s.cur_y = (uint8_t)sy;
+        s.dir = 0;
+        s.off_path = 0;
+        s.num_fails = 0;
+        s.n_fall = 0;
+        s.stamina = k.p.stamina_level;
+        s.max_x = 0;
+        s.tiles_visited = 0;
+        s.cross_on = 0;
+        s.cross_x = s.cross_y = 0;
+        s.live = 1;
+        mg_ep_frame(k, s, mg_ep_bar_height(s.stamina, k.p.stamina_level, true), f);  // (no past-path tiles at x = 0)
+        wm.post_env = wm.cur_env;
+    }
+    c.sync();
+    return true;
+}
+
+// called by the kernel once the team's record is back in global memory
+template <class Ctx>
+MG_HD void mg_ep_post_offload(Ctx& c, MgEPWarpMem& wm) {
+    if (c.lane == 0 && wm.post_env >= 0) {
+        wm.spec.env = wm.post_env;
+        wm.post_env = -1;
+        c.fence_device();  // the record (written by every lane before the team's barrier) is visible device-wide
+        mg_vstore_u32(&wm.spec.state, MG_SPEC_REQUESTED);
+    }
+}
+
+// Helper warp of a single-step launch: completes pending records in global memory until every team has left and no
+// job is waiting.
+template <class Ctx>
+MG_HD void mg_ep_helper_offload_loop(Ctx& c, uint8_t* hs_bytes, uint8_t* wextra0, int wextra_stride, int nteams, int hidx,
+                                     const uint32_t* teams_done, MgGenMem& m, const MgGenCta& tab, uint8_t* state,
+                                     double* ground_truth) {
+    MgEPState& hs = *reinterpret_cast<MgEPState*>(hs_bytes);
+    int next = hidx % nteams;
+    for (;;) {
+        const bool all_left = c.shfl(mg_vload_u32(teams_done), 0) >= (uint32_t)nteams;  // (jobs are posted before a team leaves)
+        MgEPSpec* job = nullptr;
+        for (int i = 0; i < nteams && !job; ++i) {
+            const int t = (next + i) % nteams;
+            MgEPSpec& sp = reinterpret_cast<MgEPWarpMem*>(wextra0 + (size_t)t * wextra_stride)->spec;
+            if (c.shfl(mg_vload_u32(&sp.state), 0) != MG_SPEC_REQUESTED) continue;
+            uint32_t won = 0;
+            if (c.lane == 0) won = c.cas_u32(&sp.state, MG_SPEC_REQUESTED, MG_SPEC_BUSY) == MG_SPEC_REQUESTED ? 1u : 0u;
+            if (c.shfl(won, 0)) {
+                job = &sp;
+                next = (t + 1) % nteams;
+            }
+        }
+        if (!job) {
+            if (all_left) return;
+            c.nanosleep(256);
+            continue;
+        }
+        c.sync();
+        c.fence_device();
+        MgEPState* g = reinterpret_cast<MgEPState*>(state) + job->env;
+        const volatile MgEPState* gv = g;
+        const int sy = (int)gv->pending - 1;
+        if (c.lane == 0) {
+            hs.rng.state_lo = gv->rng.state_lo, hs.rng.state_hi = gv->rng.state_hi;
+            hs.rng.inc_lo = gv->rng.inc_lo, hs.rng.inc_hi = gv->rng.inc_hi;
+            hs.rng.buf = gv->rng.buf, hs.rng.has_buf = gv->rng.has_buf;
+            hs.n_segments = 0;
+        }
+        c.sync();
+        bool ok = true;
+        for (int q = 0; q < 3 && ok; ++q) ok = mg_ep_add_segment_coop(c, hs, m, tab, q == 0 ? sy : -1);
+        if (ok) {
+            if (c.lane == 0) hs.seg[0].reward_visited |= 1ull << mg_mp_id(0, sy);  // the first node yields no reward (:529)
+            c.sync();
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(hs.seg);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(g->seg);
+            for (int w = c.lane; w < (int)(3 * sizeof(MgEPSegment) / 4); w += c.nl) dst[w] = src[w];
+        }
+        if (c.lane == 0) {
+            g->rng = hs.rng;
+            g->n_segments = hs.n_segments;
+            if (ok) {
+                hs.cur_x = 0;
+                hs.cur_y = (uint8_t)sy;
+                hs.dir = 0;
+                mg_ep_update_direction(hs);
+                g->dir = hs.dir;
+                if (ground_truth) mg_ep_ground_truth(hs, ground_truth + MG_GT_COLS * (size_t)job->env);
+            } else {
+                g->live = 0;  // "No valid path found": the reference raises; here the env stays finished
+                if (ground_truth) mg_ep_ground_truth(hs, ground_truth + MG_GT_COLS * (size_t)job->env);
+            }
+            g->pending = 0;
+        }
+        c.sync();
+        if (c.lane == 0) {
+            c.fence_device();
+            mg_vstore_u32(&job->state, MG_SPEC_EMPTY);
+        }
+    }
+}
+
 template <class Ctx>
 MG_HD void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, double* gt, MgEPWarpMem& wm,
                             const MgGenCta& tab) {
     MgGenMem& m = wm.gen;
     c.stamp(12);
+    // (an agent wider than a tile would show past-path tiles in its very first frame: those need the path)
+    if (wm.helpers > 0 && wm.offload && k.radius < MG_MP_TILE && mg_ep_reset_offload(c, k, s, f, wm)) return;
     if (c.lane == 0) {
         s.t = 0;
         s.ep_len = 0;
@@ -319,7 +450,7 @@ MG_HD void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, 
     }
     c.sync();
     bool ok = true;
-    const bool spec = wm.helpers > 0;
+    const bool spec = wm.helpers > 0 && !wm.offload;
     if (!(spec && mg_ep_spec_take(c, s, wm.spec)))
         for (int q = 0; q < 3 && ok; ++q) ok = mg_ep_add_segment_coop(c, s, m, tab);
     c.stamp(13);

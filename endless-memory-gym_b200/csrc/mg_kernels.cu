@@ -138,6 +138,7 @@ struct MgWarpCtx {
     // shared-memory hand-over between warps of a CTA (teams <-> helper warps)
     __device__ __forceinline__ uint32_t cas_u32(uint32_t* p, uint32_t cmp, uint32_t val) { return atomicCAS(p, cmp, val); }
     __device__ __forceinline__ void fence_block() { __threadfence_block(); }
+    __device__ __forceinline__ void fence_device() { __threadfence(); }
     __device__ __forceinline__ void nanosleep(unsigned ns) { __nanosleep(ns); }
     __device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
     // whole-frame template -> this warp's frame buffer, by TMA
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     extern __shared__ __align__(128) uint8_t smem[];
 
     // helper warps (rollout launches of policies that have them) sit behind the teams and own no env
-    const int nhelp = (kRollout && P::kHelperWarps > 0) ? q.n_helpers : 0;
+    const int nhelp = P::kHelperWarps > 0 ? q.n_helpers : 0;
     const int lane = threadIdx.x % kTeam, team = threadIdx.x / kTeam, nteams = blockDim.x / kTeam - nhelp;
     const bool is_helper = team >= nteams;
     uint8_t* buf = smem + (size_t)team * P::kFrameBuf;
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     P::cta_init(cextra, threadIdx.x, blockDim.x);
     if (!is_helper) {
         P::warp_init(wextra, lane);
-        if constexpr (P::kHelperWarps > 0) P::set_helpers(wextra, lane, nhelp);
+        if constexpr (P::kHelperWarps > 0) P::set_helpers(wextra, lane, nhelp, !kRollout);
     }
     __syncthreads();
     if (staged) {
@@ -244,15 +245,19 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     // SMs that stream faster take more envs. The last team to leave re-arms it for the next launch.
     uint32_t* const sched = kRollout ? q.sched : nullptr;
     const int total_teams = G * nteams;
-    if constexpr (kRollout && P::kHelperWarps > 0) {
+    if constexpr (P::kHelperWarps > 0) {
         if (is_helper) {
             MgWarpCtx hctx{lane, kTeam, 0u, 0u, 0ull, nullptr, 0};
-            P::helper_loop(hctx, cextra, smem + (size_t)nteams * (P::kFrameBuf + kSlot), nteams, team - nteams, &hdr->teams_done);
+            uint8_t* const wextra0 = smem + (size_t)nteams * (P::kFrameBuf + kSlot);
+            if constexpr (kRollout)
+                P::helper_loop(hctx, cextra, wextra0, nteams, team - nteams, &hdr->teams_done);
+            else
+                P::helper_loop_step(hctx, cextra, wextra0, nteams, team - nteams, &hdr->teams_done, state, q.io.ground_truth);
             return;
         }
     }
     const auto team_exit = [&]() {
-        if (kRollout && P::kHelperWarps > 0 && lane == 0) atomicAdd(&hdr->teams_done, 1u);
+        if (P::kHelperWarps > 0 && nhelp > 0 && lane == 0) atomicAdd(&hdr->teams_done, 1u);
         if (sched && lane == 0) {
             __threadfence();
             if (atomicAdd(sched + 1, 1u) == (uint32_t)total_teams - 1u) {
@@ -466,6 +471,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
         for (int j = 0; j < kPerLane; ++j)
             if (lane + kTeam * j < kWords) gw[lane + kTeam * j] = s64[lane + kTeam * j];
         ctx.sync();  // record slot is reused by the next env
+        if constexpr (!kRollout && P::kHelperWarps > 0) P::after_writeback(ctx, wextra);  // (a pending path: post it now)
         env = nxt;
         have = have_next;
     }
@@ -558,7 +564,7 @@ static int plan_launch(int n, int wpc_req, int default_wpc, MgLaunchPlan* out) {
     }
     // helper warps fill the thread budget behind the teams (MG_HELPERS=0 switches them off: measurement knob)
     int helpers = 0;
-    if (kRollout && P::kHelperWarps > 0 && !(getenv("MG_HELPERS") && atoi(getenv("MG_HELPERS")) == 0)) {
+    if (P::kHelperWarps > 0 && !(getenv("MG_HELPERS") && atoi(getenv("MG_HELPERS")) == 0)) {
         helpers = P::kMaxThreads / (32 * P::kTeamWarps) - wpc;
         if (helpers > P::kHelperWarps) helpers = P::kHelperWarps;
         if (helpers < 0) helpers = 0;
@@ -631,6 +637,7 @@ static int launch_env(const typename P::K& k, const void* assets, void* state, c
     MgLaunchPlan plan;
     int rc = plan_launch<P, false>(n, (int)ios->warps_per_cta, default_wpc, &plan);
     if (rc) return rc;
+    if (mode != MG_MODE_STEP) plan.helpers = 0;  // helper warps finish AUTO-resets; a reset launch does its own
     for (int t = 0; t < n_io; ++t) {
         MgKIO q;
         memset(&q, 0, sizeof(q));
@@ -642,6 +649,7 @@ static int launch_env(const typename P::K& k, const void* assets, void* state, c
         q.act_dims = act_dims;
         q.n_steps = 1;
         q.ring_n = 1;
+        q.n_helpers = plan.helpers;
         rc = launch_one<P, false>(k, q, plan, assets, state, stream);
         if (rc) return rc;
     }

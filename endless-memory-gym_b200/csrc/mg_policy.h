@@ -259,11 +259,30 @@ struct EPPolicy {
         if (lane == 0) {
             MgEPWarpMem* wm = reinterpret_cast<MgEPWarpMem*>(warp);
             wm->helpers = 0;
+            wm->offload = 0;
+            wm->cur_env = -1;
+            wm->post_env = -1;
             wm->spec.state = MG_SPEC_EMPTY;
         }
     }
-    static MG_HD void set_helpers(uint8_t* warp, int lane, int n) {
-        if (lane == 0) reinterpret_cast<MgEPWarpMem*>(warp)->helpers = n;
+    // helper warps of this launch; `offload`: single-step launch (they finish auto-resets), else rollout (they work ahead)
+    static MG_HD void set_helpers(uint8_t* warp, int lane, int n, bool offload) {
+        if (lane == 0) {
+            reinterpret_cast<MgEPWarpMem*>(warp)->helpers = n;
+            reinterpret_cast<MgEPWarpMem*>(warp)->offload = offload ? 1 : 0;
+        }
+    }
+    template <class Ctx>
+    static MG_HD void after_writeback(Ctx& c, uint8_t* warp) {
+        mg_ep_post_offload(c, *reinterpret_cast<MgEPWarpMem*>(warp));
+    }
+    template <class Ctx>
+    static MG_HD void helper_loop_step(Ctx& c, uint8_t* cextra, uint8_t* wextra0, int nteams, int hidx,
+                                       const uint32_t* teams_done, uint8_t* state, double* ground_truth) {
+        uint8_t* mine = cextra + kGenCtaBytes + (size_t)hidx * MG_EP_HELPER_BYTES;
+        MgGenMem m{0, 0};
+        mg_ep_helper_offload_loop(c, mine, wextra0, kWarpExtra, nteams, hidx, teams_done, m,
+                                  *reinterpret_cast<const MgGenCta*>(cextra), state, ground_truth);
     }
     template <class Ctx>
     static MG_HD void helper_loop(Ctx& c, uint8_t* cextra, uint8_t* wextra0, int nteams, int hidx, const uint32_t* teams_done) {
@@ -306,6 +325,7 @@ struct EPPolicy {
     template <class Ctx>
     static MG_HD void logic(Ctx& c, const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0,
                             int a1, MgFrameJob& job, Frame* fr, const MgScratch& sc) {
+        if (c.lane == 0) reinterpret_cast<MgEPWarpMem*>(sc.warp)->cur_env = env;  // (read by lane 0 only)
         mg_env_logic_coop<EPPolicy>(c, k, q, a, env, t, s, a0, a1, job, fr, sc);
     }
     template <class Ctx>

@@ -29,6 +29,7 @@ struct HostCtx {
         return old;
     }
     void fence_block() {}
+    void fence_device() {}
     void nanosleep(unsigned) {}
     uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31u)); }
     void copy_frame(uint8_t* dst, const uint8_t* src) { memcpy(dst, src, MG_FRAME_BYTES); }
