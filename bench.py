@@ -3,18 +3,25 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--env ID] [--envs-per-gpu M] [--impl reference]
 
-A "step" is one pass of the hot path over the whole env batch: one `mg_*_step` kernel launch per GPU
-doing kinematics + state machine + in-kernel auto-reset + raster of N x 84x84x3 uint8 observations.
-Default workload = BASELINE.json configs[1]: MortarMayhem-v0, 4096 envs per GPU, default options,
-seeds 0..N-1, i.i.d. uniform random actions (pre-generated on the device), auto-reset on.
+A "step" is one pass of the hot path over the whole env batch: kinematics + state machine + in-kernel
+auto-reset + raster of N x 84x84x3 uint8 observations. Headline workload = BASELINE.json configs[1]:
+MortarMayhem-v0, 4096 envs per GPU, default options, seeds 0..N-1, i.i.d. uniform random actions
+(pre-generated on the device), auto-reset on. The timed launch is one `mg_*_rollout` of K steps (the
+reference's bench.py loop shape: pre-sampled random actions, reset when done); the timed region is R such
+launches back to back (R sized for >= 200 ms, `config.timed_launches`), entered behind launches that are
+already running so that no host latency sits between the two events. Every rank warms up the same way.
 
 Printed JSON line (rank 0):
   value     whole-job million env-steps/s, actions resident in HBM, device-timed (CUDA events on the
-            launching stream, barrier + synchronize on both sides, max over ranks).
+            launching stream, barrier + synchronize on both sides, max over ranks; `per_rank_ms` lists all).
   e2e       same metric through the public Python API with HOST buffers: every step copies the
             actions pinned-host -> device and observations + rewards + dones device -> pinned host.
-  roofline  the step kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
-  cpu_baseline  the CPU oracle (restated reference, PyGame is not installable here) on 1 host core.
+  roofline  the rollout kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+  configs   the other BASELINE.json configs (MysteryPath-v0 8192, SearingSpotlights-v0 8192,
+            Endless-MortarMayhem-v0 8192 per GPU = 65 536 on 8 GPUs), each timed the same way with its own
+            roofline fraction and single-step figure.
+  cpu_baseline  the CPU oracle (restated reference, PyGame is not installable here) on 1 host core; its
+            `config1` entry is BASELINE configs[0]: MortarMayhem-Grid-v0, 1 env, the reference bench.py loop.
 `--impl reference` times the reference's CPU path (the oracle port) on all host cores instead.
 """
 import argparse
@@ -172,19 +179,202 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def gather_ms(dist, dev, ms):
+    """(max over ranks, list of every rank's value) of a device-timed duration."""
+    import torch
+    if dist is None:
+        return ms, [ms]
+    mine = torch.tensor([ms], dtype=torch.float64, device=dev)
+    every = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(every, mine)
+    vals = [float(t.item()) for t in every]
+    return max(vals), vals
+
+
+def load_traffic():
+    """DRAM bytes per env-step of the rollout kernel from the committed `ncu --set full` captures."""
+    out = {}
+    for name in ("r01_traffic.json", "r02_traffic.json"):
+        try:
+            for env_id, cap in json.load(open(os.path.join(ROOT, "profiles", name))).items():
+                out[env_id] = dict(cap, file=name)
+        except (OSError, ValueError):
+            pass
+    return out
+
+
+class Timed:
+    """One BASELINE config on this rank's GPU: env batch, rollout buffers, and the three device-timed shapes."""
+
+    MIN_REGION_MS = 200.0   # timed region (>= 2 nvidia-smi samples at 100 ms)
+    MIN_WARM_S = 0.5        # warm-up: at least this long AND at least two passes over every ring slot, on EVERY rank
+
+    def __init__(self, mg, torch, dist, env_id, n, rank, world, dev, K, chunk, wpc=0):
+        self.torch, self.dist, self.dev, self.env_id, self.n, self.world, self.rank = torch, dist, dev, env_id, n, world, rank
+        self.spec = mg.spec(env_id)
+        self.total = n * world
+        self.env = mg.make_sharded(env_id, self.total, rank, world, device=dev, warps_per_cta=wpc)
+        self.K = K
+        self.L = min(K, chunk)                     # steps per rollout launch
+        self.launches_per_block = -(-K // self.L)  # launches that make up K steps
+        self.n_act = len(self.spec.action_nvec)
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        self.acts = torch.randint(0, self.spec.action_nvec[0], (self.L,) + tuple(self.env._actions_dev.shape),
+                                  generator=g, device=dev)
+        # obs go to a [L, N, 84, 84, 3] rollout buffer (step t of a launch -> slot t): every frame of a launch has
+        # its own address and the buffer is far larger than the 126 MB L2, so every frame reaches HBM
+        self.ring = torch.empty((self.L, n, 84, 84, 3), dtype=torch.uint8, device=dev)
+        self.rew = torch.empty((self.L, n), dtype=torch.float64, device=dev)
+        self.done = torch.empty((self.L, n), dtype=torch.bool, device=dev)
+        self.env.reset(seed=0)
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def block(self, many=False):
+        """K consecutive env steps: rollout launches of L steps (or, `many`, one step launch per step)."""
+        fn = self.env.step_many if many else self.env.rollout
+        left = self.K
+        while left > 0:
+            c = min(left, self.L)
+            fn(self.acts[:c], self.ring[:c], self.rew[:c], self.done[:c])
+            left -= c
+
+    def measure(self, many=False, on_start=None):
+        """R blocks of K steps between two CUDA events. Warm-up (same on every rank): >= 2 blocks and >= 0.5 s. The
+        start event is recorded behind two blocks that are still running, so the GPU never waits for the host inside
+        the timed region. Returns (ms max over ranks, per-rank ms, R)."""
+        torch = self.torch
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 2 or time.perf_counter() - t0 < self.MIN_WARM_S:
+            self.block(many)
+            reps += 1
+            if reps % 8 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        # size R from a short probe (device-timed, 4 blocks)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(4):
+            self.block(many)
+        p1.record()
+        torch.cuda.synchronize()
+        probe_ms = p0.elapsed_time(p1) / 4
+        R = max(3, int(self.MIN_REGION_MS / max(probe_ms, 1e-3)) + 1)
+        if self.dist is not None:  # the same R everywhere
+            r_t = torch.tensor([R], dtype=torch.int64, device=self.dev)
+            self.dist.all_reduce(r_t, op=self.dist.ReduceOp.MAX)
+            R = int(r_t.item())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        if on_start:
+            on_start()
+        self.block(many)
+        self.block(many)  # (still running when the timed launches are enqueued)
+        e0.record()
+        for _ in range(R):
+            self.block(many)
+        e1.record()
+        self.barrier()
+        ms, per_rank = gather_ms(self.dist, self.dev, e0.elapsed_time(e1))
+        return ms, per_rank, R
+
+    def b_alg(self, steps_per_launch):
+        return alg_bytes_per_env_step(self.spec.family, self.n_act, steps_per_launch)
+
+    def report(self, peak, traffic_tab, on_start=None):
+        """rollout + single-step figures of this config as the dicts the JSON line carries."""
+        ms, per_rank, R = self.measure(False, on_start)
+        ms_s, per_rank_s, R_s = self.measure(True)
+        K, n = self.K, self.n
+        steps = K * R
+        b = self.b_alg(self.L)
+        achieved = n * b * steps / (ms * 1e-3) / 1e9
+        cap = traffic_tab.get(self.env_id)
+        traffic = traffic_src = None
+        if cap and "dram_bytes_per_launch" in cap:
+            per_env_step = cap["dram_bytes_per_launch"] / (cap["envs"] * cap["steps_per_launch"])
+            traffic = per_env_step * n * self.L
+            traffic_src = (f"profiles/{cap['file']}: ncu --set full capture at {cap['envs']} envs x {cap['steps_per_launch']} "
+                           f"steps per launch = {per_env_step:.1f} B per env-step, scaled to this launch")
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak[0], "unit": "GB/s", "frac": achieved / peak[0],
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak[1],
+                "kernel": "mg_env_kernel<%sPolicy, true>" % {"mm": "MM", "mp": "MP", "ss": "SS", "ep": "EP"}[self.spec.family],
+                "alg_bytes_per_env_step": b, "alg_bytes_per_launch": b * n * self.L,
+                "kernel_ms": ms / (R * self.launches_per_block), "steps_per_launch": self.L,
+                "env_steps_per_launch": n * self.L}
+        single = {"value": self.total * K * R_s / (ms_s * 1e-3) / 1e6, "unit": "M env-steps/s",
+                  "us_per_step": ms_s * 1e3 / (K * R_s), "steps": K * R_s,
+                  "frac": n * self.b_alg(1) * K * R_s / (ms_s * 1e-3) / 1e9 / peak[0],
+                  "note": "one mg_*_step launch per step (policy-in-the-loop shape, programmatic dependent launch between "
+                          "them), device-timed, max over ranks"}
+        return {"value": self.total * steps / (ms * 1e-3) / 1e6, "ms": ms, "ms_per_step": ms / steps, "per_rank_ms": per_rank,
+                "timed_launches": R * self.launches_per_block, "timed_steps": steps, "roofline": roof, "single_step": single}
+
+
+def shard_check(mg, torch, dist, dev, rank, world, env_id="MortarMayhem-v0", n_chk=256, T=64, sample=32):
+    """Byte equality across shard boundaries ON THE HARDWARE: every rank rolls its shard of a small global batch
+    (global actions from one fixed seed) and hashes a sample of its envs; the next rank recomputes exactly those envs on
+    ITS GPU from a differently-cut shard (`env_offset`), and the hashes must agree. With one GPU the same check runs
+    between two shard cuts on that GPU."""
+    spec = mg.spec(env_id)
+    total = n_chk * max(world, 2)
+    g = torch.Generator(device="cpu").manual_seed(4321)
+    acts_all = torch.randint(0, spec.action_nvec[0], (T, total, len(spec.action_nvec)), generator=g).squeeze(-1)
+
+    def run(offset, count):
+        env = mg.make(env_id, num_envs=count, device=dev, env_offset=offset)
+        env.reset(seed=77)
+        a = acts_all[:, offset:offset + count].contiguous().to(dev)
+        ring = torch.zeros((T, count, 84, 84, 3), dtype=torch.uint8, device=dev)
+        rew = torch.zeros((T, count), dtype=torch.float64, device=dev)
+        dn = torch.zeros((T, count), dtype=torch.uint8, device=dev)
+        env.rollout(a, ring, rew, dn)
+        torch.cuda.synchronize()
+        return ring, rew, dn
+
+    def digest(ring, rew, dn, lo, hi):
+        parts = []
+        for x in (ring[:, lo:hi], rew[:, lo:hi].contiguous().view(torch.int64), dn[:, lo:hi]):
+            v = x.reshape(-1).to(torch.int64)
+            w = torch.arange(v.numel(), device=dev, dtype=torch.int64) * 2654435761 + 1
+            parts.append(int((v * w).sum().item()))  # wraps mod 2^64: a position-weighted checksum
+        return parts
+
+    # my shard [rank*n_chk, +n_chk): hash its first `sample` envs
+    mine = digest(*run(rank * n_chk, n_chk), 0, sample)
+    # the previous rank's sample, recomputed here from a shard that starts in the MIDDLE of its range
+    prev = (rank - 1) % max(world, 2)
+    redo = digest(*run(prev * n_chk, sample + 7), 0, sample)
+    if dist is None:
+        other = digest(*run(prev * n_chk, n_chk), 0, sample)
+        return "ok" if other == redo and mine != redo else "mismatch"
+    t_mine = torch.tensor(mine, dtype=torch.int64, device=dev)
+    every = [torch.zeros_like(t_mine) for _ in range(world)]
+    dist.all_gather(every, t_mine)
+    ok = [int(v) for v in every[prev].tolist()] == redo
+    flag = torch.tensor([0 if ok else 1], dtype=torch.int64, device=dev)
+    dist.all_reduce(flag)
+    return "ok" if int(flag.item()) == 0 else "mismatch"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100000)
-    ap.add_argument("--warmup", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=20, help="K: steps per timed block (one rollout launch when K <= --chunk)")
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--env", default="MortarMayhem-v0")
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--warps-per-cta", type=int, default=0)
-    ap.add_argument("--chunk", type=int, default=128, help="steps per mg_*_rollout launch (= slots of the obs buffer)")
+    ap.add_argument("--chunk", type=int, default=128, help="max steps per mg_*_rollout launch (= slots of the obs buffer)")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="headline workload only (skip the other BASELINE configs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -200,94 +390,39 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (memory_gym_b200 has no CPU path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()  # (nvidia-smi needs ~1 s for its first sample: started before the env batch is built)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    spec = mg.spec(args.env)
-    n = args.envs_per_gpu or (4096 if spec.family == "mm" and spec.variant != 2 else 8192)
-    total = n * world
-    env = mg.make_sharded(args.env, total, rank, world, device=dev, warps_per_cta=args.warps_per_cta)
+    def default_n(env_id):
+        sp = mg.spec(env_id)
+        return 4096 if sp.family == "mm" and sp.variant != 2 else 8192
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    traffic_tab = load_traffic()
+
     K, W = args.steps, args.warmup
-    n_act = len(spec.action_nvec)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    T = K + W
-    POOL = min(T, args.chunk)  # steps per rollout launch; i.i.d. action sets, cycled
-    acts = torch.randint(0, spec.action_nvec[0], (POOL,) + tuple(env._actions_dev.shape), generator=g, device=dev)
-    # obs go to a [chunk, N, 84, 84, 3] rollout buffer (step t of a launch -> slot t): every frame has its own
-    # address, the buffer (chunk x 86.7 MB) is far larger than the 126 MB L2, so every frame reaches HBM
-    ring_n = POOL
-    ring = torch.empty((ring_n, n, 84, 84, 3), dtype=torch.uint8, device=dev)
-    env.reset(seed=0)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # rollout buffers: rewards / dones per step of one action-pool cycle (overwritten cycle after cycle)
-    rew_buf = torch.empty((POOL, n), dtype=torch.float64, device=dev)
-    done_buf = torch.empty((POOL, n), dtype=torch.bool, device=dev)
-
-    def run_steps(count):
-        """`count` env steps through mg_*_step_many in chunks of <= POOL (one launch per step)."""
-        left = count
-        while left > 0:
-            c = min(left, POOL)
-            env.rollout(acts[:c], ring[:c], rew_buf[:c], done_buf[:c])
-            left -= c
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    run_steps(W)
-    if sampler:  # nvidia-smi needs ~1 s to deliver its first sample: keep the GPU busy until it does
-        t_spin = time.perf_counter()
-        while not sampler.rows and time.perf_counter() - t_spin < 5.0:
-            run_steps(POOL)
-            torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    if sampler:
-        sampler.mark_start()
-    e0.record()
-    run_steps(K)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    n = args.envs_per_gpu or default_n(args.env)
+    total = n * world
+    main_cfg = Timed(mg, torch, dist, args.env, n, rank, world, dev, K, args.chunk, args.warps_per_cta)
+    head = main_cfg.report(peak, traffic_tab, on_start=(sampler.mark_start if sampler else None))
     clocks = sampler.stop() if sampler else None
-    if dist is not None:
-        tm = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ms = float(tm.item())
-    value = total * K / (ms * 1e-3) / 1e6
-
-    # ---- the same steps as ONE LAUNCH PER STEP (mg_*_step, programmatic dependent launch between them): what a
-    # policy in the loop pays per step on the device, reported next to the rollout number
-    Ks = min(K, 8 * POOL)
-    for _ in range(2):
-        env.step_many(acts, ring, rew_buf, done_buf)
-    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    es0.record()
-    left = Ks
-    while left > 0:
-        c = min(left, POOL)
-        env.step_many(acts[:c], ring[:c], rew_buf[:c], done_buf[:c])
-        left -= c
-    es1.record()
-    barrier()
-    ms_single = es0.elapsed_time(es1)
-    if dist is not None:
-        tm = torch.tensor([ms_single], dtype=torch.float64, device=dev)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ms_single = float(tm.item())
+    env, spec, acts, n_act = main_cfg.env, main_cfg.spec, main_cfg.acts, main_cfg.n_act
+    barrier = main_cfg.barrier
+    POOL = main_cfg.L
 
     # ---- end to end through the public API with host buffers -------------------------------------------
-    Ke = args.e2e_steps or min(K, 200)
-    Ke = min(Ke, POOL)
-    a_host = acts[:Ke].cpu().pin_memory()
+    Ke = args.e2e_steps or min(max(K, 60), 200)
+    a_host = acts.cpu().pin_memory()
     obs_h = torch.empty((2, n, 84, 84, 3), dtype=torch.uint8).pin_memory()
     res_h = torch.empty((2, 9 * n), dtype=torch.uint8).pin_memory()  # reward f64[n] + done u8[n]: env.results
     rew_h = [res_h[b][:8 * n].view(torch.float64) for b in range(2)]
@@ -303,7 +438,7 @@ def main():
         nonlocal checksum
         for t in range(steps):
             b = t & 1
-            a_dev.copy_(a_host[t % Ke], non_blocking=True)             # H2D actions (pinned)
+            a_dev.copy_(a_host[t % POOL], non_blocking=True)           # H2D actions (pinned)
             torch.cuda.current_stream().wait_event(ev_copy[b])         # slot b's previous D2H has drained
             env.step(a_dev, obs_out=obs_d[b])
             res_d[b].copy_(env.results)                                # reward + done of this step (one buffer)
@@ -318,17 +453,20 @@ def main():
                 checksum += float(rew_h[1 - b][0]) + float(obs_h[1 - b][0, 42, 42, 0])
         torch.cuda.synchronize()
 
-    e2e_loop(3)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(Ke)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        tm = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        e2e_s = float(tm.item())
-    e2e_value = total * Ke / e2e_s / 1e6
+    def wall(fn, steps):
+        fn(3)
+        barrier()
+        t0 = time.perf_counter()
+        fn(steps)
+        barrier()
+        secs = time.perf_counter() - t0
+        if dist is not None:
+            tm = torch.tensor([secs], dtype=torch.float64, device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            secs = float(tm.item())
+        return total * steps / secs / 1e6
+
+    e2e_value = wall(e2e_loop, Ke)
 
     # ---- the same loop for a consumer that lives on the GPU (the intended use: the policy reads obs in HBM): actions
     # still come from pinned host memory and reward + done still go back to the host every step; observations stay
@@ -336,7 +474,7 @@ def main():
         nonlocal checksum
         for t in range(steps):
             b = t & 1
-            a_dev.copy_(a_host[t % Ke], non_blocking=True)
+            a_dev.copy_(a_host[t % POOL], non_blocking=True)
             env.step(a_dev, obs_out=obs_d[b])
             res_h[b].copy_(env.results, non_blocking=True)
             ev_copy[b].record()
@@ -345,70 +483,90 @@ def main():
                 checksum += float(rew_h[1 - b][0])
         torch.cuda.synchronize()
 
-    e2e_device_obs(3)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_device_obs(4 * Ke)
-    barrier()
-    e2e_dev_s = time.perf_counter() - t0
-    if dist is not None:
-        tm = torch.tensor([e2e_dev_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        e2e_dev_s = float(tm.item())
-    e2e_dev_value = total * 4 * Ke / e2e_dev_s / 1e6
+    e2e_dev_value = wall(e2e_device_obs, 20 * Ke)
+
+    # ---- ... and with the whole host-driven step captured as ONE CUDA graph (env.capture_step(): actions H2D, the
+    # step kernel, reward + done D2H): one graph launch per step instead of three stream operations + a library call
+    graphs = [env.capture_step(obs_out=obs_d[b]) for b in range(2)]
+    rew_g = [gr.results_host[:8 * n].view(torch.float64) for gr in graphs]
+
+    def e2e_device_obs_graph(steps):
+        nonlocal checksum
+        for t in range(steps):
+            b = t & 1
+            graphs[b].actions_host.copy_(a_host[t % POOL])             # the policy's actions land in pinned memory
+            graphs[b].replay()
+            if t >= 1:
+                graphs[1 - b].done_event.synchronize()
+                checksum += float(rew_g[1 - b][0])
+        torch.cuda.synchronize()
+
+    e2e_graph_value = wall(e2e_device_obs_graph, 20 * Ke)
+
+    # ---- the other BASELINE.json configs, each timed like the headline ------------------------------------
+    configs = []
+    if not args.no_configs:
+        del main_cfg.ring
+        for env_id in ("MysteryPath-v0", "SearingSpotlights-v0", "Endless-MortarMayhem-v0"):
+            if env_id == args.env:
+                continue
+            c = Timed(mg, torch, dist, env_id, default_n(env_id), rank, world, dev, K, args.chunk)
+            r = c.report(peak, traffic_tab)
+            configs.append({"workload": f"{env_id}, {c.n} envs/GPU x {world} GPU = {c.total} envs, default options, "
+                                        "seeds 0..N-1, uniform random actions, auto-reset on",
+                            "value": r["value"], "unit": "M env-steps/s", "ms_per_step": r["ms_per_step"],
+                            "timed_launches": r["timed_launches"], "per_rank_ms": r["per_rank_ms"],
+                            "roofline": r["roofline"], "single_step": r["single_step"]})
+            del c
+            torch.cuda.empty_cache()
+
+    check = shard_check(mg, torch, dist, dev, rank, world)
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        b_alg = alg_bytes_per_env_step(spec.family, n_act, POOL)
-        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
-        traffic = None
-        try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.env)
-            if cap and cap["envs"] == n and cap["steps_per_launch"] == POOL:
-                traffic = cap["dram_bytes_per_launch"]
-        except (OSError, ValueError, KeyError):
-            pass
-        launches = -(-K // POOL)
-        kernel_ms = ms / launches  # launches back to back on one stream: event time / launches = launch duration
-        achieved = n * b_alg * K / (ms * 1e-3) / 1e9
         cpu = None
         if not args.no_cpu and world == 1:  # the CPU baseline is reported by the single-GPU run only
             v = cpu_throughput(args.env, 1, args.cpu_seconds) / 1e6
+            v1 = cpu_throughput("MortarMayhem-Grid-v0", 1, min(args.cpu_seconds, 5.0)) / 1e6
             cpu = {"value": v, "unit": "M env-steps/s", "cores": 1, "kind": "port",
                    "sample": f"{args.cpu_seconds:.0f} s of single-env stepping (reset; random actions until done) "
-                             "with the CPU oracle = restated reference; PyGame is not installable in this image"}
+                             "with the CPU oracle = restated reference; PyGame is not installable in this image",
+                   "config1": {"workload": "MortarMayhem-Grid-v0, 1 env, CPU, reference bench.py loop shape (BASELINE "
+                                           "configs[0]; no GPU)", "value": v1, "unit": "M env-steps/s", "cores": 1,
+                               "kind": "port"}}
         line = {
-            "metric": METRIC, "value": value, "unit": "M env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic",
+            "metric": METRIC, "value": head["value"], "unit": "M env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{args.env}, {n} envs/GPU x {world} GPU, 84x84x3 uint8 obs, default options, "
                                    "seeds 0..N-1, uniform random actions, auto-reset on",
-                       "l2": f"each launch writes {ring_n} steps x {n * OBS_BYTES / 1e6:.1f} MB of obs to distinct slots "
-                             f"of a {ring_n * n * OBS_BYTES / 1e9:.1f} GB rollout buffer (>> 126 MB L2), no address rewritten "
+                       "l2": f"each launch writes {POOL} steps x {n * OBS_BYTES / 1e6:.1f} MB of obs to distinct slots "
+                             f"of a {POOL * n * OBS_BYTES / 1e9:.1f} GB rollout buffer (>> 126 MB L2), no address rewritten "
                              "within a launch",
-                       "steps_per_launch": ring_n,
+                       "steps_per_launch": POOL, "timed_launches": head["timed_launches"],
+                       "timed_steps": head["timed_steps"],
+                       "timing": "CUDA events around R back-to-back K-step rollout launches (R sized for >= 200 ms), the "
+                                 "start event enqueued behind 2 running launches; every rank warms up >= 0.5 s and >= 2 "
+                                 "passes over the rollout buffer; ms_per_step = ms / (K * R); max over ranks",
                        "parallelism": f"env shards x{world}, no collective on the step path",
                        "warps_per_cta": args.warps_per_cta or "default"},
+            "per_rank_ms": head["per_rank_ms"],
             "e2e": {"value": e2e_value, "unit": "M env-steps/s", "h2d_bytes_per_step": n * n_act * 8,
                     "d2h_bytes_per_step": n * (OBS_BYTES + 8 + 1), "steps": Ke,
                     "note": "actions pinned-host->device and obs+reward+done device->pinned-host every step "
                             "(D2H of step t overlaps step t+1); PCIe-bound",
                     "device_obs": {"value": e2e_dev_value, "unit": "M env-steps/s", "h2d_bytes_per_step": n * n_act * 8,
-                                   "d2h_bytes_per_step": n * (8 + 1),
+                                   "d2h_bytes_per_step": n * (8 + 1), "steps": 20 * Ke,
                                    "note": "same public step() loop with the observations consumed in HBM (GPU-resident "
-                                           "policy): actions from pinned host memory, reward+done back to the host"}},
-            "single_step": {"value": total * Ks / (ms_single * 1e-3) / 1e6, "unit": "M env-steps/s",
-                            "us_per_step": ms_single * 1e3 / Ks, "steps": Ks,
-                            "note": "one mg_*_step launch per step (policy-in-the-loop shape), device-timed, max over ranks"},
-            "gpu_launches": -(-K // POOL),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "mg_env_kernel",
-                         "alg_bytes_per_env_step": b_alg, "kernel_ms": kernel_ms, "env_steps_per_launch": n * POOL},
+                                           "policy): actions from pinned host memory, reward+done back to the host"},
+                    "device_obs_graph": {"value": e2e_graph_value, "unit": "M env-steps/s",
+                                         "h2d_bytes_per_step": n * n_act * 8, "d2h_bytes_per_step": n * (8 + 1),
+                                         "steps": 20 * Ke,
+                                         "note": "as device_obs with env.capture_step(): one CUDA-graph launch per step"}},
+            "single_step": head["single_step"],
+            "gpu_launches": head["timed_launches"],
+            "roofline": head["roofline"],
+            "configs": configs,
+            "shard_check": check,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

@@ -31,6 +31,7 @@
 #include "mg_ep_logic.h"
 #include "mg_ss_logic.h"
 #include "mg_params_host.h"
+#include "mg_device_host.h"
 #include "mg_policy.h"
 
 
@@ -513,17 +514,28 @@ struct MgLaunchPlan {
 
 // grid geometry: one CTA per SM, `wpc` warps = frame buffers each. For rollouts (every warp runs all steps of
 // its envs) the warp count that balances envs per warp best is chosen; for single steps, the most buffers.
+// The plan of a (device, batch size, requested warps, helper switch) combination is computed once per thread and the
+// kernel's shared-memory opt-in is raised once per device: a step launch does no driver query.
 template <class P, bool kRollout>
-static int plan_launch(int n, int wpc_req, int default_wpc, MgLaunchPlan* out) {
+static int plan_launch(int dev, int n, int wpc_req, int default_wpc, bool no_helpers, MgLaunchPlan* out) {
+    struct Entry {
+        int dev, n, wpc_req, no_helpers;
+        MgLaunchPlan plan;
+    };
+    static thread_local Entry cache[4] = {{-1, 0, 0, 0, {}}, {-1, 0, 0, 0, {}}, {-1, 0, 0, 0, {}}, {-1, 0, 0, 0, {}}};
+    static thread_local int cache_next = 0;
+    for (int i = 0; i < 4; ++i)
+        if (cache[i].dev == dev && cache[i].n == n && cache[i].wpc_req == wpc_req && cache[i].no_helpers == (int)no_helpers) {
+            *out = cache[i].plan;
+            return 0;
+        }
     const bool balance = kRollout;
-    int dev = 0, sms = 0, smem_max = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        sms <= 0) {
-        cudaGetLastError();
+    const MgDevInfo* di = mg_dev_info(dev);
+    if (!di) {
         mg_set_err("no usable CUDA device");
         return MG_ENODEV;
     }
-    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int sms = di->sms, smem_max = di->smem_optin;
     constexpr int kSlot =
         (((int)sizeof(typename P::State) + (P::kDirectStore ? 2 : 3) * (int)sizeof(typename P::Frame) + (int)sizeof(MgFrameJob) + 16 + 127) / 128) * 128;
     const int per_warp = P::kFrameBuf + kSlot + P::kWarpExtra;
@@ -556,15 +568,20 @@ static int plan_launch(int n, int wpc_req, int default_wpc, MgLaunchPlan* out) {
     if (stage_cap > 48 * 1024) stage_cap = 48 * 1024;
     stage_cap &= ~127;
     smem += (size_t)stage_cap;
-    cudaError_t e = cudaFuncSetAttribute(mg_env_kernel<P, kRollout>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        mg_set_err(cudaGetErrorString(e));
-        cudaGetLastError();
-        return (int)e;
+    // the kernel may use the device's whole opt-in shared memory: set once per device (the attribute is per device)
+    static std::atomic<int> optin_set[MG_MAX_DEVICES];
+    if (!optin_set[dev].load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(mg_env_kernel<P, kRollout>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+        if (e != cudaSuccess) {
+            mg_set_err(cudaGetErrorString(e));
+            cudaGetLastError();
+            return (int)e;
+        }
+        optin_set[dev].store(1, std::memory_order_release);
     }
-    // helper warps fill the thread budget behind the teams (MG_HELPERS=0 switches them off: measurement knob)
+    // helper warps fill the thread budget behind the teams (MG_FLAG_NO_HELPERS switches them off: measurement knob)
     int helpers = 0;
-    if (P::kHelperWarps > 0 && !(getenv("MG_HELPERS") && atoi(getenv("MG_HELPERS")) == 0)) {
+    if (P::kHelperWarps > 0 && !no_helpers) {
         helpers = P::kMaxThreads / (32 * P::kTeamWarps) - wpc;
         if (helpers > P::kHelperWarps) helpers = P::kHelperWarps;
         if (helpers < 0) helpers = 0;
@@ -574,6 +591,9 @@ static int plan_launch(int n, int wpc_req, int default_wpc, MgLaunchPlan* out) {
     out->wpc = wpc;
     out->stage_cap = stage_cap;
     out->smem = smem;
+    Entry& slot = cache[cache_next];
+    cache_next = (cache_next + 1) & 3;
+    slot.dev = dev, slot.n = n, slot.wpc_req = wpc_req, slot.no_helpers = (int)no_helpers, slot.plan = *out;
     return 0;
 }
 
@@ -591,7 +611,7 @@ static int launch_one(const typename P::K& k, const MgKIO& q, const MgLaunchPlan
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = getenv("MG_DISABLE_PDL") ? 0 : 1;  // debugging / measurement switch
+    cfg.numAttrs = (q.io.flags & MG_FLAG_NO_PDL) ? 0 : 1;  // debugging / measurement switch
     cudaError_t e = cudaLaunchKernelEx(&cfg, mg_env_kernel<P, kRollout>, k, q, (const uint8_t*)assets, (uint8_t*)state);
     if (e != cudaSuccess) {
         mg_set_err(cudaGetErrorString(e));
@@ -634,8 +654,13 @@ static int launch_env(const typename P::K& k, const void* assets, void* state, c
         }
     }
     if (n == 0) return 0;
+    MgDeviceGuard guard(state);
+    if (!guard.ok) {
+        mg_set_err("no usable CUDA device");
+        return MG_ENODEV;
+    }
     MgLaunchPlan plan;
-    int rc = plan_launch<P, false>(n, (int)ios->warps_per_cta, default_wpc, &plan);
+    int rc = plan_launch<P, false>(guard.dev, n, (int)ios->warps_per_cta, default_wpc, (ios->flags & MG_FLAG_NO_HELPERS) != 0, &plan);
     if (rc) return rc;
     if (mode != MG_MODE_STEP) plan.helpers = 0;  // helper warps finish AUTO-resets; a reset launch does its own
     for (int t = 0; t < n_io; ++t) {
@@ -670,8 +695,13 @@ static int launch_rollout(const typename P::K& k, const void* assets, void* stat
         return MG_EINVAL;
     }
     if (n == 0) return 0;
+    MgDeviceGuard guard(state);
+    if (!guard.ok) {
+        mg_set_err("no usable CUDA device");
+        return MG_ENODEV;
+    }
     MgLaunchPlan plan;
-    int rc = plan_launch<P, true>(n, (int)r->warps_per_cta, default_wpc, &plan);
+    int rc = plan_launch<P, true>(guard.dev, n, (int)r->warps_per_cta, default_wpc, (r->flags & MG_FLAG_NO_HELPERS) != 0, &plan);
     if (rc) return rc;
     MgKIO q;
     memset(&q, 0, sizeof(q));
@@ -701,14 +731,33 @@ static int launch_rollout(const typename P::K& k, const void* assets, void* stat
     return launch_one<P, true>(k, q, plan, assets, state, stream);
 }
 
+// Option validation + derivation of the kernel's option block happen once per option set and thread: a step call
+// whose mg_*_params bytes equal the previous call's reuses the derived block.
+template <class Params, class K>
+static int mg_cached_k(const Params* p, int (*check)(const Params*), void (*derive)(const Params*, K*), const K** out) {
+    static thread_local Params last;
+    static thread_local K k;
+    static thread_local bool valid = false;
+    if (!p) return check(p);
+    if (!valid || memcmp(&last, p, sizeof(Params)) != 0) {
+        valid = false;
+        if (check(p)) return MG_EINVAL;
+        derive(p, &k);
+        memcpy(&last, p, sizeof(Params));
+        valid = true;
+    }
+    *out = &k;
+    return 0;
+}
+
 static int mm_act_dims(const mg_mm_params* p) { return mg_mm_is_grid(p->variant) ? 1 : 2; }
 static int mp_act_dims(const mg_mp_params* p) { return p->variant == MG_MP_GRID ? 1 : 2; }
 
 extern "C" int mg_mm_reset(const mg_mm_params* p, const void* assets, void* state, const uint64_t* rng4,
                            const mg_step_io* io, int n, void* stream) {
-    if (mg_mm_check_params(p)) return MG_EINVAL;
-    MgMMK k;
-    mg_mm_derive(p, &k);
+    const MgMMK* kp;
+    if (mg_cached_k(p, mg_mm_check_params, mg_mm_derive, &kp)) return MG_EINVAL;
+    const MgMMK& k = *kp;
     return launch_env<MMPolicy>(k, assets, state, rng4, io, 1, n, MG_MODE_RESET, mm_act_dims(p), stream, 10);
 }
 extern "C" int mg_mm_step(const mg_mm_params* p, const void* assets, void* state, const mg_step_io* io, int n,
@@ -717,24 +766,24 @@ extern "C" int mg_mm_step(const mg_mm_params* p, const void* assets, void* state
 }
 extern "C" int mg_mm_step_many(const mg_mm_params* p, const void* assets, void* state, const mg_step_io* ios,
                                int n_steps, int n, void* stream) {
-    if (mg_mm_check_params(p)) return MG_EINVAL;
-    MgMMK k;
-    mg_mm_derive(p, &k);
+    const MgMMK* kp;
+    if (mg_cached_k(p, mg_mm_check_params, mg_mm_derive, &kp)) return MG_EINVAL;
+    const MgMMK& k = *kp;
     return launch_env<MMPolicy>(k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, mm_act_dims(p), stream, 10);
 }
 extern "C" int mg_mm_rollout(const mg_mm_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
                              void* stream) {
-    if (mg_mm_check_params(p)) return MG_EINVAL;
-    MgMMK k;
-    mg_mm_derive(p, &k);
+    const MgMMK* kp;
+    if (mg_cached_k(p, mg_mm_check_params, mg_mm_derive, &kp)) return MG_EINVAL;
+    const MgMMK& k = *kp;
     return launch_rollout<MMPolicy>(k, assets, state, r, n, mm_act_dims(p), stream, 10);
 }
 
 extern "C" int mg_mp_reset(const mg_mp_params* p, const void* assets, void* state, const uint64_t* rng4,
                            const mg_step_io* io, int n, void* stream) {
-    if (mg_mp_check_params(p)) return MG_EINVAL;
-    MgMPK k;
-    mg_mp_derive(p, &k);
+    const MgMPK* kp;
+    if (mg_cached_k(p, mg_mp_check_params, mg_mp_derive, &kp)) return MG_EINVAL;
+    const MgMPK& k = *kp;
     return launch_env<MPPolicy>(k, assets, state, rng4, io, 1, n, MG_MODE_RESET, mp_act_dims(p), stream, 10);
 }
 extern "C" int mg_mp_step(const mg_mp_params* p, const void* assets, void* state, const mg_step_io* io, int n,
@@ -743,24 +792,24 @@ extern "C" int mg_mp_step(const mg_mp_params* p, const void* assets, void* state
 }
 extern "C" int mg_mp_step_many(const mg_mp_params* p, const void* assets, void* state, const mg_step_io* ios,
                                int n_steps, int n, void* stream) {
-    if (mg_mp_check_params(p)) return MG_EINVAL;
-    MgMPK k;
-    mg_mp_derive(p, &k);
+    const MgMPK* kp;
+    if (mg_cached_k(p, mg_mp_check_params, mg_mp_derive, &kp)) return MG_EINVAL;
+    const MgMPK& k = *kp;
     return launch_env<MPPolicy>(k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, mp_act_dims(p), stream, 10);
 }
 extern "C" int mg_mp_rollout(const mg_mp_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
                              void* stream) {
-    if (mg_mp_check_params(p)) return MG_EINVAL;
-    MgMPK k;
-    mg_mp_derive(p, &k);
+    const MgMPK* kp;
+    if (mg_cached_k(p, mg_mp_check_params, mg_mp_derive, &kp)) return MG_EINVAL;
+    const MgMPK& k = *kp;
     return launch_rollout<MPPolicy>(k, assets, state, r, n, mp_act_dims(p), stream, 10);
 }
 
 extern "C" int mg_ep_reset(const mg_ep_params* p, const void* assets, void* state, const uint64_t* rng4,
                            const mg_step_io* io, int n, void* stream) {
-    if (mg_ep_check_params(p)) return MG_EINVAL;
-    MgEPK k;
-    mg_ep_derive(p, &k);
+    const MgEPK* kp;
+    if (mg_cached_k(p, mg_ep_check_params, mg_ep_derive, &kp)) return MG_EINVAL;
+    const MgEPK& k = *kp;
     return launch_env<EPPolicy>(k, assets, state, rng4, io, 1, n, MG_MODE_RESET, 1, stream, 10);
 }
 extern "C" int mg_ep_step(const mg_ep_params* p, const void* assets, void* state, const mg_step_io* io, int n,
@@ -769,16 +818,16 @@ extern "C" int mg_ep_step(const mg_ep_params* p, const void* assets, void* state
 }
 extern "C" int mg_ep_step_many(const mg_ep_params* p, const void* assets, void* state, const mg_step_io* ios,
                                int n_steps, int n, void* stream) {
-    if (mg_ep_check_params(p)) return MG_EINVAL;
-    MgEPK k;
-    mg_ep_derive(p, &k);
+    const MgEPK* kp;
+    if (mg_cached_k(p, mg_ep_check_params, mg_ep_derive, &kp)) return MG_EINVAL;
+    const MgEPK& k = *kp;
     return launch_env<EPPolicy>(k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, 1, stream, 10);
 }
 extern "C" int mg_ep_rollout(const mg_ep_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
                              void* stream) {
-    if (mg_ep_check_params(p)) return MG_EINVAL;
-    MgEPK k;
-    mg_ep_derive(p, &k);
+    const MgEPK* kp;
+    if (mg_cached_k(p, mg_ep_check_params, mg_ep_derive, &kp)) return MG_EINVAL;
+    const MgEPK& k = *kp;
     return launch_rollout<EPPolicy>(k, assets, state, r, n, 1, stream, 10);
 }
 
@@ -789,9 +838,9 @@ extern "C" int mg_ep_rollout(const mg_ep_params* p, const void* assets, void* st
 
 extern "C" int mg_ss_reset(const mg_ss_params* p, const void* assets, void* state, const uint64_t* rng4,
                            const mg_step_io* io, int n, void* stream) {
-    if (mg_ss_check_params(p)) return MG_EINVAL;
-    MgSSK k;
-    mg_ss_derive(p, &k);
+    const MgSSK* kp;
+    if (mg_cached_k(p, mg_ss_check_params, mg_ss_derive, &kp)) return MG_EINVAL;
+    const MgSSK& k = *kp;
     MG_SS_DISPATCH(launch_env, k, assets, state, rng4, io, 1, n, MG_MODE_RESET, 2, stream, 10);
 }
 extern "C" int mg_ss_step(const mg_ss_params* p, const void* assets, void* state, const mg_step_io* io, int n,
@@ -800,15 +849,15 @@ extern "C" int mg_ss_step(const mg_ss_params* p, const void* assets, void* state
 }
 extern "C" int mg_ss_step_many(const mg_ss_params* p, const void* assets, void* state, const mg_step_io* ios,
                                int n_steps, int n, void* stream) {
-    if (mg_ss_check_params(p)) return MG_EINVAL;
-    MgSSK k;
-    mg_ss_derive(p, &k);
+    const MgSSK* kp;
+    if (mg_cached_k(p, mg_ss_check_params, mg_ss_derive, &kp)) return MG_EINVAL;
+    const MgSSK& k = *kp;
     MG_SS_DISPATCH(launch_env, k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, 2, stream, 10);
 }
 extern "C" int mg_ss_rollout(const mg_ss_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
                              void* stream) {
-    if (mg_ss_check_params(p)) return MG_EINVAL;
-    MgSSK k;
-    mg_ss_derive(p, &k);
+    const MgSSK* kp;
+    if (mg_cached_k(p, mg_ss_check_params, mg_ss_derive, &kp)) return MG_EINVAL;
+    const MgSSK& k = *kp;
     MG_SS_DISPATCH(launch_rollout, k, assets, state, r, n, 2, stream, 10);
 }

@@ -15,6 +15,7 @@
 
 #include "../../include/memgym_b200.h"
 #include "mg_common.h"
+#include "mg_device_host.h"
 
 void mg_set_err(const char* msg);  // mg_params_host.cpp
 
@@ -124,14 +125,20 @@ extern "C" int mg_obs_to_policy_bf16(const uint8_t* obs, void* out, int n, void*
         return MG_EINVAL;
     }
     if (n == 0) return 0;
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
-        cudaGetLastError();
+    MgDeviceGuard guard(obs);
+    const MgDevInfo* di = guard.ok ? mg_dev_info(guard.dev) : nullptr;
+    if (!di) {
         mg_set_err("no usable CUDA device");
         return MG_ENODEV;
     }
+    const int sms = di->sms;
     const size_t smem = 2 * kBuf + kOutBuf + kLutBytes + 16;
-    cudaError_t e = cudaFuncSetAttribute(mg_policy_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static std::atomic<int> optin_set[MG_MAX_DEVICES];
+    cudaError_t e = cudaSuccess;
+    if (!optin_set[guard.dev].load(std::memory_order_acquire)) {
+        e = cudaFuncSetAttribute(mg_policy_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) optin_set[guard.dev].store(1, std::memory_order_release);
+    }
     if (e == cudaSuccess) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(n < 2 * sms ? n : 2 * sms);  // two persistent CTAs per SM

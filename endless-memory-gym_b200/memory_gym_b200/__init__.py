@@ -33,29 +33,45 @@ def make(env_id, num_envs=None, device="cuda", **kwargs):
     return MemoryGymVecEnv(env_id, num_envs, device=device, **kwargs)
 
 
-def make_sharded(env_id, total_envs, rank, world_size, device=None, **kwargs):
+def make_sharded(env_id, total_envs, rank, world_size, device=None, local_rank=None, **kwargs):
     """One shard of an env batch split over ``world_size`` GPUs (one process per GPU).
 
     Envs are independent, so a shard is just a contiguous slice ``[rank*n, (rank+1)*n)`` of the global
     batch; global env ``g`` is seeded with ``seed + g`` whatever the number of shards, so the
-    concatenated result is identical to a single-GPU run. No collective is on the step path."""
+    concatenated result is identical to a single-GPU run. No collective is on the step path.
+
+    ``device`` defaults to ``cuda:<local_rank>``; ``local_rank`` defaults to ``$LOCAL_RANK`` (torchrun) and,
+    without it, to ``rank`` modulo the number of visible GPUs. The library launches on the device that owns
+    the env records, so the caller's current CUDA device does not matter."""
     if total_envs % world_size:
         raise ValueError("total_envs must be divisible by world_size")
     n = total_envs // world_size
     if device is None:
-        device = f"cuda:{rank}"
+        if local_rank is None:
+            import os
+            import torch
+            env_lr = os.environ.get("LOCAL_RANK")
+            local_rank = int(env_lr) if env_lr is not None else rank % max(1, torch.cuda.device_count())
+        device = f"cuda:{int(local_rank)}"
     return MemoryGymVecEnv(env_id, n, device=device, env_offset=rank * n, **kwargs)
 
 
-def _register_with_gymnasium():  # pragma: no cover - gymnasium is absent from the build image
+def _register_with_gymnasium():
+    """Register the reference's own id strings (memory_gym/__init__.py:13-60) with gymnasium when it is importable:
+    ``gym.make("MortarMayhem-v0")`` then returns the single-instance, reference-protocol env of this package. An id that
+    is already registered (the reference package was imported first) is left alone; ``B200-<id>`` always names this
+    implementation."""
     try:
         from gymnasium.envs.registration import register, registry
-    except Exception:  # noqa: BLE001
-        return
+    except Exception:  # noqa: BLE001  (gymnasium is absent from the build image)
+        return []
+    done = []
     for env_id in SPECS:
-        gid = "B200-" + env_id
-        if gid not in registry:
-            register(id=gid, entry_point=lambda env_id=env_id, **kw: MemoryGymEnv(env_id, **kw))
+        for gid in (env_id, "B200-" + env_id):
+            if gid not in registry:
+                register(id=gid, entry_point=lambda env_id=env_id, **kw: MemoryGymEnv(env_id, **kw))
+                done.append(gid)
+    return done
 
 
 _register_with_gymnasium()

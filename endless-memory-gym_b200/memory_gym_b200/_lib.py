@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmemgym_b200.so")
 
-MG_ABI_VERSION = 3
+MG_ABI_VERSION = 4
 MG_OBS_BYTES = 84 * 84 * 3
 MG_INFO_COLS = 10
 MG_GT_COLS = 4
@@ -24,6 +24,8 @@ MG_EP_STATE_BYTES = 2048
 MG_EP_MAX_SEGMENTS = 45
 MG_FLAG_AUTORESET = 1
 MG_FLAG_STREAM_OBS = 2
+MG_FLAG_NO_HELPERS = 4
+MG_FLAG_NO_PDL = 8
 MG_MM_CONTINUOUS, MG_MM_GRID, MG_MM_ENDLESS, MG_MM_B, MG_MM_B_GRID = 0, 1, 2, 3, 4
 MG_MP_CONTINUOUS, MG_MP_GRID = 0, 1
 MG_MM_B_VECTOR = 180

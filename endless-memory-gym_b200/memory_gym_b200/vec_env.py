@@ -27,6 +27,15 @@ class _CudaBackend:
 
     def __init__(self):
         self.lib = L.lib()
+        self._fn = {}
+
+    def fn(self, family, what):
+        """``mg_<family>_<what>`` of the library (resolved once)."""
+        key = (family, what)
+        f = self._fn.get(key)
+        if f is None:
+            f = self._fn[key] = getattr(self.lib, f"mg_{family}_{what}")
+        return f
 
     def check_device(self, device):
         if device.type != "cuda":
@@ -63,17 +72,17 @@ class _CudaBackend:
                 f"mg_{family}_reset")
 
     def step(self, family, params, assets, state, io, n, stream):
-        rc = getattr(self.lib, f"mg_{family}_step")(C.byref(params), assets, state, C.byref(io), n, stream)
+        rc = self.fn(family, "step")(C.byref(params), assets, state, C.byref(io), n, stream)
         if rc:
             L.check(rc, f"mg_{family}_step")
 
     def rollout(self, family, params, assets, state, rio, n, stream):
-        rc = getattr(self.lib, f"mg_{family}_rollout")(C.byref(params), assets, state, C.byref(rio), n, stream)
+        rc = self.fn(family, "rollout")(C.byref(params), assets, state, C.byref(rio), n, stream)
         if rc:
             L.check(rc, f"mg_{family}_rollout")
 
     def step_many(self, family, params, assets, state, ios, n_steps, n, stream):
-        rc = getattr(self.lib, f"mg_{family}_step_many")(C.byref(params), assets, state, ios, n_steps, n, stream)
+        rc = self.fn(family, "step_many")(C.byref(params), assets, state, ios, n_steps, n, stream)
         if rc:
             L.check(rc, f"mg_{family}_step_many")
 
@@ -160,7 +169,11 @@ class MemoryGymVecEnv:
         # not re-read soon; measured +13 % HBM write throughput), off for step() (the policy reads obs next).
         self._stream_step = L.MG_FLAG_STREAM_OBS if stream_obs else 0
         self._stream_rollout = L.MG_FLAG_STREAM_OBS if (stream_obs is None or stream_obs) else 0
-        self._io.flags = (L.MG_FLAG_AUTORESET if self.auto_reset else 0) | self._stream_step
+        # measurement knobs, read when the env is made and passed to the library as explicit flags (it reads no
+        # environment variable itself): MG_HELPERS=0 = no helper warps, MG_DISABLE_PDL = no programmatic dependent launch
+        self._knobs = (L.MG_FLAG_NO_HELPERS if os.environ.get("MG_HELPERS") == "0" else 0) | \
+                      (L.MG_FLAG_NO_PDL if os.environ.get("MG_DISABLE_PDL") else 0)
+        self._io.flags = (L.MG_FLAG_AUTORESET if self.auto_reset else 0) | self._stream_step | self._knobs
         self._io.warps_per_cta = self.warps_per_cta
         self.reset_params = None
         self._params = None
@@ -307,7 +320,7 @@ class MemoryGymVecEnv:
         r.vector_obs = self._io.vector_obs
         r.sched = self._sched.data_ptr() if self._sched is not None else None
         r.n_steps, r.ring, r.info_per_step = T, obs_out.shape[0], int(info_out is not None)
-        r.flags, r.warps_per_cta = L.MG_FLAG_AUTORESET | self._stream_rollout, self.warps_per_cta
+        r.flags, r.warps_per_cta = L.MG_FLAG_AUTORESET | self._stream_rollout | self._knobs, self.warps_per_cta
         r.trace = getattr(self, "_trace_ptr", None)
         self._be.rollout(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(), r,
                          self.num_envs, self._be.stream(self.device))
@@ -401,7 +414,8 @@ class StepGraph:
         self.done_event = torch.cuda.Event()
         self._a_dev = torch.zeros_like(env._actions_dev)
         # the warm-up below runs one real step: everything it touches is put back afterwards
-        keep = [(t, t.clone()) for t in (env.state, self.obs, env.results, env.info) + ((env.final_obs,) if env.final_obs is not None else ())]
+        touched = (env.state, self.obs, env.results, env.info, env.final_obs, env.vector_obs, env._gt_full)
+        keep = [(t, t.clone()) for t in touched if t is not None]
         side = torch.cuda.Stream(device=env.device)
         side.wait_stream(torch.cuda.current_stream(env.device))
         with torch.cuda.stream(side):

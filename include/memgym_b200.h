@@ -30,8 +30,11 @@
  *
  * Conventions
  *   - every pointer marked "device" is CUDA device memory owned by the caller (e.g. a torch tensor);
- *     the library never allocates or frees device memory and keeps no global state.
+ *     the library never allocates or frees device memory; its only process state are per-thread caches of
+ *     launch geometry and derived option blocks (no environment variable is read).
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream). Calls are asynchronous.
+ *   - launches run on the device that owns `state` (looked up from the pointer), whatever the caller's
+ *     current device is; `stream` and every other device pointer must belong to that device.
  *   - return value: 0 on success, a cudaError_t (> 0) from the launch, or a negative MG_E* code for
  *     bad arguments. No exceptions cross this boundary.
  *   - there is NO CPU implementation behind the reset/step symbols: without a CUDA device they fail.
@@ -46,7 +49,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 3
+#define MG_ABI_VERSION 4
 
 #define MG_SCREEN 84
 #define MG_OBS_BYTES (84 * 84 * 3) /* 21168 bytes per env, [x][y][c] */
@@ -85,6 +88,8 @@ extern "C" {
                              /* its terminal frame and ignores further steps until mg_*_reset.                    */
 
 #define MG_FLAG_STREAM_OBS 2u /* write observations with an L2 evict-first policy (they are not re-read soon) */
+#define MG_FLAG_NO_HELPERS 4u /* measurement knob: Endless-MysteryPath launches without path-generation helper warps */
+#define MG_FLAG_NO_PDL 8u     /* measurement knob: launch without programmatic dependent launch */
 
 typedef struct mg_choice_list {
     int32_t n;
