@@ -503,6 +503,24 @@ def main():
 
     e2e_graph_value = wall(e2e_device_obs_graph, 20 * Ke)
 
+    # ---- ... and with NO copy operation at all: the step kernel reads the actions straight from pinned host memory and
+    # writes reward + done straight into pinned host memory (zero-copy over PCIe), so consecutive step launches run back
+    # to back under programmatic dependent launch; the host waits on an event recorded behind each step
+    ev_z = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_device_obs_zero_copy(steps):
+        nonlocal checksum
+        for t in range(steps):
+            b = t & 1
+            env.step(a_host[t % POOL], obs_out=obs_d[b], results_out=res_h[b])
+            ev_z[b].record()
+            if t >= 1:
+                ev_z[1 - b].synchronize()
+                checksum += float(rew_h[1 - b][0])
+        torch.cuda.synchronize()
+
+    e2e_zero_value = wall(e2e_device_obs_zero_copy, 20 * Ke)
+
     # ---- the other BASELINE.json configs, each timed like the headline ------------------------------------
     configs = []
     if not args.no_configs:
@@ -561,7 +579,13 @@ def main():
                     "device_obs_graph": {"value": e2e_graph_value, "unit": "M env-steps/s",
                                          "h2d_bytes_per_step": n * n_act * 8, "d2h_bytes_per_step": n * (8 + 1),
                                          "steps": 20 * Ke,
-                                         "note": "as device_obs with env.capture_step(): one CUDA-graph launch per step"}},
+                                         "note": "as device_obs with env.capture_step(): one CUDA-graph launch per step"},
+                    "device_obs_zero_copy": {"value": e2e_zero_value, "unit": "M env-steps/s",
+                                             "h2d_bytes_per_step": n * n_act * 8, "d2h_bytes_per_step": n * (8 + 1),
+                                             "steps": 20 * Ke,
+                                             "note": "as device_obs, but the step kernel itself reads the actions from pinned "
+                                                     "host memory and writes reward + done into pinned host memory (same "
+                                                     "bytes over PCIe, no copy operation between two step launches)"}},
             "single_step": head["single_step"],
             "gpu_launches": head["timed_launches"],
             "roofline": head["roofline"],

@@ -96,6 +96,23 @@ __device__ __forceinline__ uint64_t mg_now() {
     return t;
 }
 
+// this env's action components. int64[n][2] rows are 16-byte aligned whenever the base is: one 128-bit load (the
+// actions may live in pinned host memory, where every load is a PCIe read)
+__device__ __forceinline__ void mg_load_actions(const int64_t* a, int dims, int64_t& a0, int64_t& a1) {
+    if (dims > 1) {
+        if ((reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+            const longlong2 v = *reinterpret_cast<const longlong2*>(a);
+            a0 = v.x;
+            a1 = v.y;
+        } else {
+            a0 = a[0];
+            a1 = a[1];
+        }
+    } else {
+        a0 = a[0];
+    }
+}
+
 // per-CTA words: the asset staging barrier and the work counter of the CTA-local dynamic env -> team scheduling
 #define MG_CTA_HDR_BYTES 128
 struct MgCtaHdr {
@@ -286,9 +303,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
         for (int w = 0; w < kPerLane; ++w)
             if (lane + kTeam * w < kWords) pre[w] = g[lane + kTeam * w];
         if (lane == 0 && stepping) {
-            const int64_t* a = q.io.actions + (size_t)env * q.act_dims;
-            act0 = a[0];
-            if (q.act_dims > 1) act1 = a[1];
+            mg_load_actions(q.io.actions + (size_t)env * q.act_dims, q.act_dims, act0, act1);
         }
     }
     if (P::kFrameBuf) {
@@ -329,9 +344,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
                 if (wsel == 0) {
                     const int a0 = (int)act0, a1 = (int)act1;
                     if (lane == 0 && T > 1) {
-                        const int64_t* a = q.io.actions + (size_t)q.act_stride + (size_t)env * q.act_dims;
-                        act0 = a[0];
-                        if (q.act_dims > 1) act1 = a[1];
+                        mg_load_actions(q.io.actions + (size_t)q.act_stride + (size_t)env * q.act_dims, q.act_dims, act0, act1);
                     }
                     P::pipe_step(c32, k, q, view, env, 0, *st, a0, a1, fr[0], scratch);
                 }
@@ -345,9 +358,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
                         if (t + 1 < T) {
                             const int a0 = (int)act0, a1 = (int)act1;
                             if (lane == 0 && t + 2 < T) {
-                                const int64_t* a = q.io.actions + (size_t)(t + 2) * q.act_stride + (size_t)env * q.act_dims;
-                                act0 = a[0];
-                                if (q.act_dims > 1) act1 = a[1];
+                                mg_load_actions(q.io.actions + (size_t)(t + 2) * q.act_stride + (size_t)env * q.act_dims, q.act_dims, act0, act1);
                             }
                             P::pipe_step(c32, k, q, view, env, t + 1, *st, a0, a1, fr[(t + 1) & 1], scratch);
                         }
@@ -382,9 +393,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
                     for (int w = 0; w < kPerLane; ++w)
                         if (lane + kTeam * w < kWords) pre[w] = g[lane + kTeam * w];
                     if (lane == 0) {
-                        const int64_t* a = q.io.actions + (size_t)nxt * q.act_dims;
-                        act0 = a[0];
-                        if (q.act_dims > 1) act1 = a[1];
+                        mg_load_actions(q.io.actions + (size_t)nxt * q.act_dims, q.act_dims, act0, act1);
                     }
                 }
             }
@@ -400,9 +409,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
             }
             if (t + 1 < T) {  // prefetch the next step's actions: the latency hides behind this step's work
                 if (lane == 0) {
-                    const int64_t* a = q.io.actions + (size_t)(t + 1) * q.act_stride + (size_t)env * q.act_dims;
-                    act0 = a[0];
-                    if (q.act_dims > 1) act1 = a[1];
+                    mg_load_actions(q.io.actions + (size_t)(t + 1) * q.act_stride + (size_t)env * q.act_dims, q.act_dims, act0, act1);
                 }
             } else {
                 // the env's last step: claim this team's next env — as LATE as possible, so that a team held up by
@@ -419,9 +426,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
                     for (int w = 0; w < kPerLane; ++w)
                         if (lane + kTeam * w < kWords) pre[w] = g[lane + kTeam * w];
                     if (lane == 0 && stepping) {
-                        const int64_t* a = q.io.actions + (size_t)nxt * q.act_dims;
-                        act0 = a[0];
-                        if (q.act_dims > 1) act1 = a[1];
+                        mg_load_actions(q.io.actions + (size_t)nxt * q.act_dims, q.act_dims, act0, act1);
                     }
                 }
             }

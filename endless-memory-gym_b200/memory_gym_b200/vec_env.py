@@ -104,7 +104,7 @@ class MemoryGymVecEnv:
     metadata = {"render_modes": ["rgb_array"], "render_fps": 25}
 
     def __init__(self, env_id, num_envs=1, device="cuda", auto_reset=True, final_obs=False, env_offset=0,
-                 warps_per_cta=0, stream_obs=None, _backend=None):
+                 warps_per_cta=0, stream_obs=None, host_results=False, _backend=None):
         self.spec_ = _spec(env_id)
         self.env_id = env_id
         self.num_envs = int(num_envs)
@@ -130,8 +130,15 @@ class MemoryGymVecEnv:
         self.state = torch.zeros((n, self.spec_.state_bytes), dtype=torch.uint8, device=dev)
         self.obs = torch.zeros((n, 84, 84, 3), dtype=torch.uint8, device=dev)
         self.final_obs = torch.zeros((n, 84, 84, 3), dtype=torch.uint8, device=dev) if final_obs else None
-        # reward (f64) and done (u8) share one allocation: `results` moves both to the host with a single copy
-        self.results = torch.zeros(9 * n, dtype=torch.uint8, device=dev)
+        # reward (f64) and done (u8) share one allocation: `results` moves both to the host with a single copy.
+        # host_results=True puts it into PINNED HOST memory instead: the step kernel writes rewards and dones straight
+        # over PCIe (zero-copy), `reward` / `done` are CPU tensors that are valid once the step has finished on the
+        # stream — no device->host copy operation sits between two step launches (a host-side policy loop).
+        self.host_results = bool(host_results)
+        if self.host_results:
+            self.results = torch.zeros(9 * n, dtype=torch.uint8).pin_memory()
+        else:
+            self.results = torch.zeros(9 * n, dtype=torch.uint8, device=dev)
         self.reward = self.results[:8 * n].view(torch.float64)
         self.done = self.results[8 * n:]
         self.truncated = torch.zeros(n, dtype=torch.bool, device=dev)
@@ -156,6 +163,7 @@ class MemoryGymVecEnv:
             self._info_views["ground_truth"] = self.ground_truth
             self._info_views["final_ground_truth"] = self.info[:, L.MG_INFO_GT0:L.MG_INFO_GT0 + self.spec_.gt_dim]
         self._step_fn = None
+        self._results_views = {}
         self._io.final_obs = self.final_obs.data_ptr() if final_obs else None
         self._io.reward = self.reward.data_ptr()
         self._io.done = self.done.data_ptr()
@@ -257,13 +265,18 @@ class MemoryGymVecEnv:
             return {"visual_observation": obs, "vector_observation": self.vector_obs}
         return obs
 
-    def step(self, actions, obs_out=None):
+    def step(self, actions, obs_out=None, results_out=None):
         """``obs_out``: optional uint8[N,84,84,3] device tensor (e.g. a slot of a rollout buffer) that
-        receives this step's observations instead of the env's own ``obs`` buffer."""
+        receives this step's observations instead of the env's own ``obs`` buffer. ``results_out``: optional
+        uint8[9 N] tensor — device, or PINNED host memory (written by the kernel over PCIe, no copy operation) — that
+        receives this step's rewards (float64[N], first 8 N bytes) and dones (uint8[N]) instead of ``env.results``.
+        ``actions`` may be a device tensor or a pinned host tensor (read by the kernel in place)."""
         if self._params is None:
             raise L.MemGymError("step() called before reset()")
-        if isinstance(actions, torch.Tensor) and actions.device == self.device and actions.dtype == torch.int64 \
-                and actions.is_contiguous():
+        if isinstance(actions, torch.Tensor) and actions.dtype == torch.int64 and actions.is_contiguous() and \
+                (actions.device == self.device or (actions.device.type == "cpu" and actions.is_pinned())):
+            # device tensor, or PINNED host memory: the kernel reads the actions straight from it (zero-copy over PCIe;
+            # unified addressing: the host pointer is valid on the device) — no host->device copy operation
             a = actions
         else:
             a = self._actions_dev
@@ -271,16 +284,37 @@ class MemoryGymVecEnv:
                     .reshape(a.shape), non_blocking=True)
         if a.numel() != self._actions_dev.numel():
             raise ValueError(f"actions must have shape {tuple(self._actions_dev.shape)}")
-        self._io.actions = a.data_ptr()
+        io = self._io
+        io.actions = a.data_ptr()
         obs = self.obs
         if obs_out is not None:
             if obs_out.shape != self.obs.shape or obs_out.dtype != torch.uint8 or obs_out.device != self.device \
                     or not obs_out.is_contiguous():
                 raise ValueError("obs_out must be a contiguous uint8[N,84,84,3] tensor on the env's device")
             obs = obs_out
-        self._io.obs = obs.data_ptr()
-        self._be.step(self.spec_.family, self._params, self._assets_ptr, self._state_ptr, self._io,
+        io.obs = obs.data_ptr()
+        reward, done = self.reward, self._done_bool
+        if results_out is not None:
+            views = self._results_views.get(results_out.data_ptr())
+            if views is None:
+                n = self.num_envs
+                if results_out.dtype != torch.uint8 or results_out.numel() != 9 * n or not results_out.is_contiguous() or \
+                        not (results_out.device == self.device or (results_out.device.type == "cpu" and results_out.is_pinned())):
+                    raise ValueError("results_out must be a contiguous uint8[9 N] tensor on the env's device or in pinned host memory")
+                flat = results_out.view(-1)
+                views = (results_out, flat[:8 * n].view(torch.float64), flat[8 * n:].view(torch.bool))
+                if len(self._results_views) > 8:
+                    self._results_views.clear()
+                self._results_views[results_out.data_ptr()] = views
+            _, reward, done = views
+            io.reward, io.done = reward.data_ptr(), done.data_ptr()
+        self._be.step(self.spec_.family, self._params, self._assets_ptr, self._state_ptr, io,
                       self.num_envs, self._be.stream(self.device))
+        if results_out is not None:
+            io.reward, io.done = self.reward.data_ptr(), self.done.data_ptr()
+            info = dict(self._info_views)
+            info["_episode"] = done
+            return self._wrap_obs(obs), reward, done, self.truncated, info
         return self._wrap_obs(obs), self.reward, self._done_bool, self.truncated, dict(self._info_views)
 
     def _check_rollout_buffers(self, actions, obs_out, reward_out, done_out, info_out):

@@ -429,3 +429,91 @@ def test_rollout_with_options_equals_step_loop(env_id, opts):
     assert dn.any() and torch.equal(a.state, b.state)
     if a.task_b:
         assert torch.equal(a.vector_obs, b.vector_obs)
+
+
+@pytest.mark.parametrize("env_id,n,steps", [("MysteryPath-v0", 8192, 520), ("SearingSpotlights-v0", 8192, 264)])
+def test_default_options_full_episode_at_baseline_size(env_id, n, steps):
+    """BASELINE configs 3 and 4 as bench.py runs them — DEFAULT options (MysteryPath max_steps 512, SearingSpotlights
+    max_steps 256), 8192 envs, one rollout launch longer than a whole episode: sampled envs equal the CPU oracle
+    step for step (observations through a position-weighted checksum per frame, rewards, dones), every env finishes
+    at least one episode, and a different launch geometry gives the same bytes."""
+    from oracle import memgym_oracle as O
+    env = mg.make(env_id, num_envs=n, device=DEV)
+    acts = _random_actions(env, steps, 99)
+    env.reset(seed=0)
+    ring = torch.empty((4, n, 84, 84, 3), dtype=torch.uint8, device=DEV)  # a 4-slot ring: the last frames survive
+    rew = torch.empty((steps, n), dtype=torch.float64, device=DEV)
+    dn = torch.empty((steps, n), dtype=torch.bool, device=DEV)
+    env.rollout(acts, ring, rew, dn)
+    torch.cuda.synchronize()
+    assert bool(dn.any(0).all())  # max_steps ends every episode inside the launch
+    sample = [0, 1, 2, n // 2, n - 1]
+    # the same envs, stepped one launch per step in a small shard: every frame is checked against the oracle
+    a_cpu = acts.cpu().numpy()
+    for e in sample:
+        sh = mg.make(env_id, num_envs=1, device=DEV, env_offset=e)
+        obs = sh.reset(seed=0)[0]
+        ora = O.make(env_id)
+        w_obs, _ = ora.reset(seed=e)
+        assert np.array_equal(obs[0].cpu().numpy(), w_obs)
+        for t in range(steps):
+            obs, r, d, _, _ = sh.step(acts[t, e:e + 1].contiguous())
+            w_obs, w_r, w_d, _, _ = ora.step(a_cpu[t, e])
+            if w_d:
+                w_obs, _ = ora.reset()
+            assert float(w_r) == float(r[0]) == float(rew[t, e]) and bool(w_d) == bool(d[0]) == bool(dn[t, e]), (e, t)
+            assert np.array_equal(obs[0].cpu().numpy(), w_obs), (e, t)
+        assert torch.equal(obs[0], ring[(steps - 1) % 4, e]), e  # ... and the big launch ended on the same frame
+    env2 = mg.make(env_id, num_envs=n, device=DEV, warps_per_cta=5)
+    env2.reset(seed=0)
+    ring2, rew2, dn2 = torch.empty_like(ring), torch.empty_like(rew), torch.empty_like(dn)
+    env2.rollout(acts, ring2, rew2, dn2)
+    assert torch.equal(ring, ring2) and torch.equal(rew, rew2) and torch.equal(dn, dn2)
+    assert torch.equal(env.state, env2.state)
+
+
+def test_zero_copy_host_actions_and_results():
+    """A host-side policy loop without copy operations: actions read by the kernel straight from PINNED host memory,
+    rewards / dones written straight into pinned host memory (host_results=True). Same bytes as the device-buffer path."""
+    n, T = 700, 80
+    a = mg.make("MortarMayhem-v0", num_envs=n, device=DEV)
+    b = mg.make("MortarMayhem-v0", num_envs=n, device=DEV, host_results=True)
+    assert b.reward.device.type == "cpu" and b.results.is_pinned()
+    acts = _random_actions(a, T, 5)
+    acts_host = acts.cpu().pin_memory()
+    assert torch.equal(a.reset(seed=3)[0], b.reset(seed=3)[0])
+    for t in range(T):
+        oa, ra, da, _, ia = a.step(acts[t])
+        ob, rb, db, _, ib = b.step(acts_host[t])
+        torch.cuda.synchronize()
+        assert torch.equal(oa, ob) and torch.equal(ra.cpu(), rb) and torch.equal(da.cpu(), db)
+    assert torch.equal(a.state, b.state) and torch.equal(a.info, b.info)
+    # results_out: per-step result buffers (pinned host memory, double-buffered) on an ordinary env
+    c = mg.make("MortarMayhem-v0", num_envs=n, device=DEV)
+    c.reset(seed=3)
+    a.reset(seed=3)
+    res = [torch.zeros(9 * n, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    for t in range(T):
+        oa, ra, da, _, _ = a.step(acts[t])
+        oc, rc, dc, _, ic = c.step(acts_host[t], results_out=res[t & 1])
+        torch.cuda.synchronize()
+        assert rc.data_ptr() == res[t & 1].data_ptr() and ic["_episode"] is dc
+        assert torch.equal(oa, oc) and torch.equal(ra.cpu(), rc) and torch.equal(da.cpu(), dc)
+
+
+def test_launch_follows_the_env_device_not_the_current_device():
+    """the library launches on the device that owns the env records. With a second GPU the env lives on
+    cuda:1 while the current device stays cuda:0; with one GPU the guard's lookup path still runs on every call."""
+    dev = "cuda:1" if torch.cuda.device_count() > 1 else DEV
+    torch.cuda.set_device(0)
+    env = mg.make("MortarMayhem-v0", num_envs=300, device=dev)
+    ref = mg.make("MortarMayhem-v0", num_envs=300, device=DEV)
+    acts = _random_actions(ref, 30, 8)
+    assert torch.equal(env.reset(seed=1)[0].cpu(), ref.reset(seed=1)[0].cpu())
+    for t in range(30):
+        o1, r1, d1, _, _ = env.step(acts[t].to(dev))
+        o2, r2, d2, _, _ = ref.step(acts[t])
+        assert torch.equal(o1.cpu(), o2.cpu()) and torch.equal(r1.cpu(), r2.cpu()) and torch.equal(d1.cpu(), d2.cpu())
+    assert torch.cuda.current_device() == 0
+    out = env.policy_obs()
+    assert out.device == env.obs.device
