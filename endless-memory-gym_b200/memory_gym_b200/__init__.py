@@ -16,9 +16,9 @@ from __future__ import annotations
 from . import _lib
 from ._lib import LIB_PATH, MemGymError
 from .specs import NOT_BUILT, SPECS, spec
-from .vec_env import MemoryGymEnv, MemoryGymVecEnv
+from .vec_env import HostPipe, MemoryGymEnv, MemoryGymVecEnv
 
-__all__ = ["make", "make_sharded", "MemoryGymVecEnv", "MemoryGymEnv", "MemGymError", "SPECS", "NOT_BUILT", "spec",
+__all__ = ["make", "make_sharded", "MemoryGymVecEnv", "MemoryGymEnv", "HostPipe", "MemGymError", "SPECS", "NOT_BUILT", "spec",
            "LIB_PATH", "registered_ids"]
 
 

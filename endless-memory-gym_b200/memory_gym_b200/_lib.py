@@ -11,8 +11,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmemgym_b200.so")
 
-MG_ABI_VERSION = 4
+MG_ABI_VERSION = 5
 MG_OBS_BYTES = 84 * 84 * 3
+MG_DELTA_HDR_BYTES = 176
 MG_INFO_COLS = 10
 MG_GT_COLS = 4
 MG_MAX_CHOICES = 16
@@ -142,6 +143,10 @@ def lib():
     L.mg_device_info.argtypes = [C.POINTER(i32)] * 3 + [C.POINTER(C.c_size_t)]
     L.mg_seed_pcg64.argtypes = [vp, i32, vp]
     L.mg_obs_to_policy_bf16.argtypes = [vp, vp, i32, vp]
+    L.mg_obs_delta_stage_bytes.restype = C.c_size_t
+    L.mg_obs_delta_stage_bytes.argtypes = [i32]
+    L.mg_obs_delta_encode.argtypes = [vp, vp, i32, vp, i32, vp]
+    L.mg_obs_delta_decode.argtypes = [vp, vp, i32, i32, u64p]
     L.mg_selftest_pcg64_host.argtypes = [vp, vp, vp, vp, i32, vp, vp]
     for fam, P in (("mm", MMParams), ("mp", MPParams), ("ss", SSParams), ("ep", EPParams)):
         getattr(L, f"mg_{fam}_check_params").argtypes = [C.POINTER(P)]

@@ -397,6 +397,13 @@ class MemoryGymVecEnv:
             raise L.MemGymError("capture_step() called before reset()")
         return StepGraph(self, obs_out)
 
+    def host_pipe(self, threads=None, depth=2):
+        """Observations, rewards and dones in HOST memory every step — the reference's interface (numpy arrays on the
+        host) for a whole batch — without shipping whole frames over PCIe: see ``HostPipe``."""
+        if self._params is None:
+            raise L.MemGymError("host_pipe() called before reset()")
+        return HostPipe(self, threads, depth)
+
     def policy_obs(self, obs=None, out=None):
         """The consumer step (``mg_obs_to_policy_bf16``): ``obs`` uint8[N,84,84,3] (default: this env's observation
         buffer) -> bf16[N,3,84,84] = ``obs.permute(0, 3, 1, 2) / 255``, bit-identical to torch's float32 division and
@@ -471,6 +478,105 @@ class StepGraph:
     def replay(self):
         self.graph.replay()
         self.done_event.record()
+
+
+class HostPipe:
+    """Host-buffer stepping for a batched env: ``obs`` (uint8[N,84,84,3]), ``reward`` (float64[N]) and ``done``
+    (bool[N]) live in HOST memory and are brought up to date every step, like the arrays the reference returns.
+
+    Transport (``mg_obs_delta_encode`` / ``mg_obs_delta_decode``): the step kernel reads the actions from pinned host
+    memory and writes rewards / dones into pinned host memory (zero-copy); a second kernel compares the new frames with
+    the frames the host already holds and sends only the 16-byte chunks that changed, straight into pinned host memory;
+    worker threads of the library patch them into ``obs``. Lossless: ``obs`` equals the device observation bit for bit.
+
+    ``step(actions)`` = ``submit(actions)`` + ``collect()``. A loop whose actions do not depend on the newest
+    observation (pre-sampled / scripted actions, the reference's bench.py shape) may keep up to ``depth`` steps in
+    flight: ``submit`` step t+1 before ``collect``-ing step t, so the GPU and the link work while the host patches.
+    ``obs`` is updated IN PLACE by ``collect``; the views returned for rewards / dones belong to that step's slot and
+    are reused ``depth`` steps later."""
+
+    def __init__(self, env, threads=None, depth=2):
+        self.env = env
+        n = env.num_envs
+        self.depth = int(depth)
+        if self.depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.threads = int(threads) if threads else max(1, min(32, (os.cpu_count() or 1)))
+        self._lib = env._be.lib
+        self.obs = torch.zeros((n, 84, 84, 3), dtype=torch.uint8)            # the caller-facing host array
+        self._prev = torch.zeros((n, 84, 84, 3), dtype=torch.uint8, device=env.device)  # what the host holds, on the device
+        stage_bytes = int(self._lib.mg_obs_delta_stage_bytes(n))
+        self._stage = [torch.zeros(stage_bytes, dtype=torch.uint8).pin_memory() for _ in range(self.depth)]
+        self._res = [torch.zeros(9 * n, dtype=torch.uint8).pin_memory() for _ in range(self.depth)]
+        self._act = [torch.zeros_like(env._actions_dev, device="cpu").pin_memory() for _ in range(self.depth)]
+        self._ev = [torch.cuda.Event() for _ in range(self.depth)]
+        self._views = [(r[:8 * n].view(torch.float64), r[8 * n:].view(torch.bool)) for r in self._res]
+        self._head = self._tail = 0
+        self._bytes = C.c_uint64(0)
+        self.last_d2h_bytes = 0   # bytes that crossed the link for the step collected last (payload + headers + results)
+        self.total_d2h_bytes = 0
+        self.resync()
+
+    def _encode(self, slot, full):
+        env = self.env
+        L.check(self._lib.mg_obs_delta_encode(env.obs.data_ptr(), self._prev.data_ptr(), env.num_envs,
+                                              self._stage[slot].data_ptr(), int(full), env._be.stream(env.device)),
+                "mg_obs_delta_encode")
+        self._ev[slot].record(torch.cuda.current_stream(env.device))
+
+    def _decode(self, slot):
+        self._ev[slot].synchronize()
+        L.check(self._lib.mg_obs_delta_decode(self._stage[slot].data_ptr(), self.obs.data_ptr(), self.env.num_envs,
+                                              self.threads, C.byref(self._bytes)), "mg_obs_delta_decode")
+        self.last_d2h_bytes = int(self._bytes.value) + 9 * self.env.num_envs
+        self.total_d2h_bytes += self.last_d2h_bytes
+
+    def resync(self):
+        """Send the env's current observation as whole frames (after ``env.reset()``, or whenever ``env.obs`` was
+        produced outside this pipe)."""
+        if self._head != self._tail:
+            raise L.MemGymError("resync() with steps still in flight: collect() them first")
+        self._encode(0, True)
+        self._decode(0)
+        return self.obs
+
+    def reset(self, seed=None, options=None):
+        """``env.reset`` + the reset frames into the host array. Returns (obs, info) like the env."""
+        if self._head != self._tail:
+            raise L.MemGymError("reset() with steps still in flight: collect() them first")
+        _, info = self.env.reset(seed=seed, options=options)
+        self.resync()
+        return self.obs, info
+
+    def submit(self, actions):
+        """Enqueue one env step with host-side ``actions`` (int64; pinned memory is read in place)."""
+        if self._head - self._tail >= self.depth:
+            raise L.MemGymError(f"more than depth={self.depth} steps in flight: collect() first")
+        slot = self._head % self.depth
+        a = actions
+        if not (isinstance(a, torch.Tensor) and a.device.type == "cpu" and a.dtype == torch.int64 and a.is_contiguous()
+                and a.is_pinned()):
+            self._act[slot].copy_(torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a)
+                                  .reshape(self._act[slot].shape))
+            a = self._act[slot]
+        self.env.step(a, results_out=self._res[slot])
+        self._encode(slot, False)
+        self._head += 1
+
+    def collect(self):
+        """Wait for the oldest step in flight and bring the host arrays up to date with it. Returns
+        (obs, reward, done, truncated, info) with host tensors; ``info`` is the env's device-side episode matrix."""
+        if self._head == self._tail:
+            raise L.MemGymError("collect() without a submitted step")
+        slot = self._tail % self.depth
+        self._decode(slot)
+        self._tail += 1
+        reward, done = self._views[slot]
+        return self.obs, reward, done, torch.zeros_like(done), {"episode": self.env.info, "_episode": done}
+
+    def step(self, actions):
+        self.submit(actions)
+        return self.collect()
 
 
 class MemoryGymEnv:

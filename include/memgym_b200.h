@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 4
+#define MG_ABI_VERSION 5
 
 #define MG_SCREEN 84
 #define MG_OBS_BYTES (84 * 84 * 3) /* 21168 bytes per env, [x][y][c] */
@@ -343,6 +343,25 @@ int mg_ep_check_params(const mg_ep_params* p);
  * out[i][c][x][y] = bf16_rn(float(obs[i][x][y][c]) / 255.0f), i.e. obs.permute(0, 3, 1, 2) / 255 bit for bit.
  * Both pointers 16-byte aligned device memory; asynchronous on `stream`. */
 int mg_obs_to_policy_bf16(const uint8_t* obs, void* out, int n, void* stream);
+
+/* ---- observations into HOST buffers: lossless delta transport -----------------------------------------
+ * The reference returns every observation as a host array (`surfarray.array3d`, mortar_mayhem.py:270,367). A full
+ * device->host copy per step is PCIe-bound (21168 B per env-step); consecutive frames of an env differ in a few
+ * hundred pixels, so only 16-byte chunks that changed cross the link:
+ *   mg_obs_delta_encode  device: compares `obs` [n][84][84][3] with `prev` (device, same shape: the frames the host
+ *                        already holds; zero-initialise together with the host array), writes per env a change mask +
+ *                        count and the changed chunks straight into `stage` (PINNED host memory addressable by the
+ *                        device, 16-byte aligned, mg_obs_delta_stage_bytes(n) bytes) and updates `prev`. full != 0
+ *                        sends every chunk (resynchronisation). Asynchronous on `stream`.
+ *   mg_obs_delta_decode  host: after the stream reached the encode (event / synchronize), patches the changed chunks
+ *                        into `host_obs` [n][84][84][3] with `threads` worker threads; `host_obs` then equals `obs`
+ *                        bit for bit. bytes_out (nullable) receives the bytes that crossed the link for this step.
+ * Stage layout: n headers of MG_DELTA_HDR_BYTES {uint32 count, uint32 mask[42]}, then n regions of MG_OBS_BYTES
+ * holding env e's changed chunks in ascending order. A transport code only: nothing is rendered on the host. */
+#define MG_DELTA_HDR_BYTES 176
+size_t mg_obs_delta_stage_bytes(int n);
+int mg_obs_delta_encode(const uint8_t* obs, uint8_t* prev, int n, void* stage, int full, void* stream);
+int mg_obs_delta_decode(const void* stage, uint8_t* host_obs, int n, int threads, uint64_t* bytes_out);
 
 /* Library / device introspection. */
 int mg_abi_version(void);

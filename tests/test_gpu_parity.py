@@ -517,3 +517,79 @@ def test_launch_follows_the_env_device_not_the_current_device():
     assert torch.cuda.current_device() == 0
     out = env.policy_obs()
     assert out.device == env.obs.device
+
+
+def test_obs_delta_encoder_matches_stage_format():
+    """mg_obs_delta_encode against the numpy statement of the stage layout (tests/test_codec_host.py), and the host
+    decoder on the device-written stage: random frames, sparse changes, a forced full resync."""
+    import ctypes as C
+    from test_codec_host import decode, encode_numpy
+    from memory_gym_b200 import _lib as L
+    lib = L.lib()
+    n = 300
+    g = torch.Generator(device=DEV).manual_seed(2)
+    prev = torch.randint(0, 256, (n, 21168), dtype=torch.uint8, generator=g, device=DEV)
+    host = prev.cpu().numpy().copy()
+    stage = torch.zeros(int(lib.mg_obs_delta_stage_bytes(n)), dtype=torch.uint8).pin_memory()
+    for step in range(4):
+        cur = prev.clone()
+        if step != 1:  # step 1: nothing changed at all
+            m = torch.rand((n, 21168), generator=g, device=DEV) < (0.002 if step else 0.3)
+            cur[m] ^= 0x5A
+            cur[0, -1] ^= 1
+        prev_np = prev.cpu().numpy().copy()
+        full = step == 3
+        L.check(lib.mg_obs_delta_encode(cur.data_ptr(), prev.data_ptr(), n, stage.data_ptr(), int(full),
+                                        torch.cuda.current_stream().cuda_stream), "encode")
+        torch.cuda.synchronize()
+        assert torch.equal(prev, cur)  # the device copy of "what the host holds" is up to date
+        want = encode_numpy(cur.cpu().numpy(), prev_np, full)
+        got = stage.numpy()
+        nh = n * L.MG_DELTA_HDR_BYTES
+        hdr_w = want[:nh].view(np.uint32).reshape(n, -1)
+        hdr_g = got[:nh].view(np.uint32).reshape(n, -1)
+        assert np.array_equal(hdr_g[:, :43], hdr_w[:, :43])
+        for e in (0, 1, n // 2, n - 1):
+            k = 16 * int(hdr_w[e, 0])
+            lo = nh + e * L.MG_OBS_BYTES
+            assert np.array_equal(got[lo:lo + k], want[lo:lo + k]), (step, e)
+        rc, nbytes = decode(got, host, 8)
+        assert rc == 0 and np.array_equal(host, cur.cpu().numpy())
+        assert nbytes == 16 * int(hdr_w[:, 0].sum()) + nh
+
+
+@pytest.mark.parametrize("env_id,depth", [("MortarMayhem-v0", 1), ("MortarMayhem-v0", 2), ("SearingSpotlights-v0", 2),
+                                          ("Endless-MysteryPath-v0", 3), ("MortarMayhemB-Grid-v0", 2)])
+def test_host_pipe_host_arrays_equal_device(env_id, depth):
+    """HostPipe: observations / rewards / dones in HOST memory after every step (delta transport over PCIe, zero-copy
+    actions and results) equal the device-side step loop bit for bit — with `depth` steps in flight."""
+    n, T = 500, 90
+    a = mg.make(env_id, num_envs=n, device=DEV)
+    b = mg.make(env_id, num_envs=n, device=DEV)
+    acts = _random_actions(a, T, 17)
+    acts_host = acts.cpu()
+    obs_a = a.reset(seed=6)[0]
+    b.reset(seed=6)
+    pipe = b.host_pipe(threads=6, depth=depth)
+    vis = (lambda o: o["visual_observation"]) if a.task_b else (lambda o: o)
+    assert torch.equal(pipe.obs, vis(obs_a).cpu())
+    want = []
+    for t in range(T):
+        o, r, d, _, _ = a.step(acts[t])
+        want.append((vis(o).cpu(), r.cpu(), d.cpu()))
+    sent = 0
+    for t in range(T + depth - 1):
+        if t < T:
+            pipe.submit(acts_host[t] if t % 2 else acts_host[t].pin_memory())  # pinned and pageable action arrays
+        if t >= depth - 1:
+            o, r, d, _, _ = pipe.collect()
+            wo, wr, wd = want[t - depth + 1]
+            assert torch.equal(o, wo) and torch.equal(r, wr) and torch.equal(d, wd), t
+            sent += pipe.last_d2h_bytes
+    assert 0 < sent < T * n * 21168  # less than whole frames would have cost
+    # resets through the pipe, then more steps
+    o2, _ = pipe.reset(seed=9)
+    assert torch.equal(o2, vis(a.reset(seed=9)[0]).cpu())
+    o, r, d, _, _ = pipe.step(acts_host[0])
+    wo, wr, wd, _, _ = a.step(acts[0])
+    assert torch.equal(o, vis(wo).cpu()) and torch.equal(r, wr.cpu()) and torch.equal(d, wd.cpu())
