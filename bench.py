@@ -41,7 +41,7 @@ for p in (ROOT, os.path.join(ROOT, "endless-memory-gym_b200")):
 METRIC = "million env-steps/sec"
 OBS_BYTES = 84 * 84 * 3
 GRID_IDS = ("MortarMayhem-Grid-v0", "MortarMayhemB-Grid-v0", "MysteryPath-Grid-v0", "Endless-MysteryPath-v0")  # Discrete(4)
-STATE_BYTES = {"mm": 256, "mp": 128, "ss": 1024, "ep": 2048}
+STATE_BYTES = {"mm": 256, "mp": 128, "ss": 1152, "ep": 2048}
 
 
 def alg_bytes_per_env_step(family, n_act, steps_per_launch=1):

@@ -302,6 +302,17 @@ bool build_icons(Builder& b, bool legacy) {
     return true;
 }
 
+// the ground-truth ring of _build_debug_surface (mortar_mayhem.py:135): pygame.draw.circle(surface, (0, 255, 0), tile
+// centre, tile_dim // 2, int(8 * SCALE)); stored as a sprite whose centre pixel is (w >> 1, h >> 1)
+bool build_ring(Builder& b, bool legacy) {
+    const int r = (int)(56 * SCALE) / 2, w = (int)(8 * SCALE), dim = 2 * r + 2;
+    Surface s(dim, dim);
+    s.has_key = true;
+    s.key = 0;
+    mgr::circle(s, mgr::rgb(0, 255, 0), dim >> 1, dim >> 1, r, w, legacy);
+    return b.add_sprite(MG_SPR_RING, s);
+}
+
 // mystery_path.py:175-182
 bool build_cross(Builder& b) {
     double dim = 40 * SCALE;
@@ -347,6 +358,7 @@ extern "C" long mg_mm_build_assets(const mg_mm_params* p, int thick_circle_legac
     double agent_scale = (p->variant == MG_MM_GRID || p->variant == MG_MM_B_GRID) ? SCALE : p->agent_scale;
     if (!build_agent(b, agent_scale, thick_circle_legacy != 0)) return MG_EINVAL;
     if (!build_icons(b, thick_circle_legacy != 0)) return MG_EINVAL;
+    if (!build_ring(b, thick_circle_legacy != 0)) return MG_EINVAL;
     build_arena(b, 0, size, false);
     build_arena(b, 1, size, true);
     return b.serialize(host_out, capacity);

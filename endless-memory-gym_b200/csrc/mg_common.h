@@ -78,6 +78,7 @@ enum {
     MG_SPR_EXIT_CLOSED = 18,
     MG_SPR_EXIT_OPEN = 19,
     MG_SPR_COIN = 20,
+    MG_SPR_RING = 21,    // ground-truth render: green ring on the target tile (mortar_mayhem.py:135)
     MG_SPR_COUNT = 24
 };
 
@@ -137,7 +138,8 @@ struct MgMMState {
     uint16_t show_dur, show_delay;
     uint16_t show_base;    // index of the first command the queue shows
     uint8_t live;          // an episode is running (0 after make() and after an un-reset done)
-    uint8_t pad[1];
+    uint8_t clone_ahead;   // debug render: the cloned command queue runs one entry ahead of the real one (Endless, after
+                           // the list grew: endless_mortar_mayhem.py:321 re-clones before the step pops)
     uint8_t commands[MG_MM_MAXCMD];
 };
 
@@ -158,7 +160,9 @@ struct MgMPState {
     uint8_t cross_on;      // fall_off_surface alpha == 255
     uint8_t live;
     int8_t gx, gy;         // MysteryPath-Grid: agent.grid_position
-    uint8_t pad[30];
+    uint8_t pad0[6];
+    uint64_t wall_mask;    // bit (i*7+j): wall node (ground-truth render only: MysteryPath.wall_nodes)
+    uint8_t pad[16];
 };
 
 // ---- Endless Mystery Path record (2048 bytes) ---------------------------------------------------
@@ -203,7 +207,7 @@ struct MgEPFrame {
     uint8_t tile_y[MG_EP_MAXTILES];  // tile row 0..6
 };
 
-// ---- Searing Spotlights record (1024 bytes) -----------------------------------------------------
+// ---- Searing Spotlights record (1152 bytes) -----------------------------------------------------
 #define MG_SS_MAXSPOTS 32
 #define MG_SS_MAXCOINS 16
 struct MgSSSpot {       // Spotlight (pygame_assets.py:61-131); positions are recomputed from the angles
@@ -241,7 +245,17 @@ struct MgSSState {
     uint32_t scene_ver;        // bumped whenever anything but the agent / top bar / spotlights changes on screen
     uint32_t scene_last;       // (bg kind, coin layer order, coins left, exit open) of the last frame
     uint32_t done_mask;        // bit i = spots[i].done (the removal pass of the next step reads one word, not n bytes)
-    uint8_t pad1[64];
+    // What the env instance keeps ACROSS reset() in the reference: spotlight_surface is created once per instance and
+    // only repainted by step() (searing_spotlights.py:124-126, 208-216) — a reset frame still shows the discs of the last
+    // step (visible when light_dim_off_duration == 0) — and the sprite handle rotated_agent_surface / rect (:135, :462).
+    uint8_t last_n;            // discs on spotlight_surface
+    uint8_t hand_rot;          // sprite handle: rotation // 45 ...
+    uint8_t hand_has;          // ... exists (a step has run on this instance)
+    uint8_t pad1[1];
+    int16_t hand_x, hand_y;    // ... and its centre
+    int16_t last_x[MG_SS_MAXSPOTS], last_y[MG_SS_MAXSPOTS];
+    uint8_t last_r[MG_SS_MAXSPOTS];
+    uint8_t pad2[24];
 };
 
 struct MgSSFrame {
@@ -281,5 +295,5 @@ static_assert(sizeof(MgMPState) == 128, "MgMPState must be 128 bytes (MG_MP_STAT
 static_assert(sizeof(MgEPSegment) == 40, "MgEPSegment layout");
 static_assert(sizeof(MgEPState) == 2048, "MgEPState must be 2048 bytes (MG_EP_STATE_BYTES)");
 static_assert(sizeof(MgSSSpot) == 24, "MgSSSpot layout");
-static_assert(sizeof(MgSSState) == 1024, "MgSSState must be 1024 bytes (MG_SS_STATE_BYTES)");
+static_assert(sizeof(MgSSState) == 1152, "MgSSState must be 1152 bytes (MG_SS_STATE_BYTES)");
 static_assert(sizeof(MgAssetHeader) % 8 == 0, "MgAssetHeader alignment");

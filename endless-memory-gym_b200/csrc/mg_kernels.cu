@@ -470,6 +470,11 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
                 for (int w = lane; w < (int)(sizeof(Frame) / 4); w += kTeam)
                     reinterpret_cast<uint32_t*>(prev)[w] = reinterpret_cast<const uint32_t*>(&f)[w];
             }
+            if constexpr (!kRollout) {
+                // ground-truth render (render_mode="debug_rgb_array"): a cold path, painted from the frame that went to obs
+                if (MG_UNLIKELY(q.io.debug_obs != nullptr) && nframes > 0)
+                    P::emit_debug(ctx, q.io.debug_obs + (size_t)env * MG_DEBUG_BYTES, view, k, fr[nframes - 1], *st, scratch);
+            }
             ctx.sync();  // job / frame slots are reused by the next step
         }
         uint64_t* gw = reinterpret_cast<uint64_t*>(state + (size_t)env * kStateBytes);

@@ -193,6 +193,7 @@ MG_HD void mg_mm_reset_env(const MgMMK& k, MgMMState& s, MgMMFrame& f, double* g
     s.tx = (int8_t)tx;
     s.ty = (int8_t)ty;
     s.cc = s.cs = s.cv = 0;
+    s.clone_ahead = 0;  // _command_visualization_clone = copy of the full queue (mortar_mayhem.py:251)
     s.E = (uint16_t)mg_rr_choice(r, k.p.explosion_duration);
     s.D = (uint16_t)mg_rr_choice(r, k.p.explosion_delay);
     mg_rr_store(r, s.rng);
@@ -305,6 +306,7 @@ MG_HD bool mg_mm_step_env(const MgMMK& k, MgMMState& s, int a0, int a1, double& 
                     s.show_base = (uint16_t)(s.n - 1);
                     s.show_len = (uint16_t)(s.show_dur + s.show_delay);
                     s.show_pos = 0;
+                    s.clone_ahead = 1;  // re-cloned here, before any step pops the new queue (:321)
                 } else {
                     done = true;
                     success = 1;  // also when the last command failed (quirk A.9#1)
@@ -346,6 +348,14 @@ MG_HD bool mg_mm_step_env(const MgMMK& k, MgMMState& s, int a0, int a1, double& 
     s.ep_reward = s.ep_reward + reward;
     s.ep_len++;
     reward_out = reward;
+    if (!endless) {
+        // the sprite handle (rotated_agent_surface / rect, mortar_mayhem.py:291,295) = what this step drew; it is not
+        // refreshed by reset(), which only the ground-truth render shows (the endless variant keeps it above)
+        s.draw_cx = (int16_t)sx;
+        s.draw_cy = (int16_t)sy;
+        s.draw_rot = (uint8_t)srot;
+        s.has_draw = 1;
+    }
     mg_mm_frame(k, s, sx, sy, srot, icon, f);
     if (gt) {
         gt[0] = (double)s.tx / 5.0;

@@ -116,7 +116,7 @@ MG_HD double mg_f64_make(uint32_t lo, uint32_t hi) {
 // results are uniform.
 template <class Ctx>
 MG_HD uint64_t mg_mp_generate_coop(Ctx& c, MgRngR& r, int sx, int sy, int ex, int ey, const MgGenCta& tab,
-                                   uint64_t* next2 = nullptr) {
+                                   uint64_t* next2 = nullptr, uint64_t* wall_out = nullptr) {
     constexpr int n = MG_MP_CELLS, NL = Ctx::kLanes, PER = (MG_MP_NODES + NL - 1) / NL;
     // interior walls (:640-647): 16 draws in scan order
     uint64_t wall = 0;
@@ -259,6 +259,7 @@ MG_HD uint64_t mg_mp_generate_coop(Ctx& c, MgRngR& r, int sx, int sy, int ex, in
         next2[0] = (uint64_t)c.reduce_or((uint32_t)n0) | ((uint64_t)c.reduce_or((uint32_t)(n0 >> 32)) << 32);
         next2[1] = (uint64_t)c.reduce_or((uint32_t)n1) | ((uint64_t)c.reduce_or((uint32_t)(n1 >> 32)) << 32);
     }
+    if (wall_out) *wall_out = wall;  // MysteryPath.wall_nodes (uniform across the lanes)
     return path;
 }
 
@@ -296,8 +297,10 @@ MG_HD void mg_mp_reset_coop(Ctx& c, const MgMPK& k, MgMPState& s, MgMPDraw& d, M
     } else {
         sx = a, sy = g - 1, ex = b, ey = 0;
     }
-    const uint64_t mask = mg_mp_generate_coop(c, r, sx, sy, ex, ey, tab);
+    uint64_t walls = 0;
+    const uint64_t mask = mg_mp_generate_coop(c, r, sx, sy, ex, ey, tab, nullptr, &walls);
     if (c.lane == 0) {
+        s.wall_mask = walls;
         s.t = 0;
         s.ep_len = 0;
         s.ep_reward = 0.0;

@@ -9,6 +9,7 @@
 #include "mg_mp_logic.h"
 #include "mg_ep_logic.h"
 #include "mg_ss_logic.h"
+#include "mg_debug.h"
 
 #if defined(__CUDACC__)
 #define MG_HDN __host__ __device__
@@ -190,6 +191,12 @@ struct MMPolicy {
     static MG_HD void restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const K& k, const Frame& f, const MgScratch&) {
         mg_mm_restore(c, buf, a, f, k.origin, k.size, a.hdr->agent_dim >> 1, a.hdr->icon_x, a.hdr->icon_y);
     }
+    // the reference's B variants have no debug render (mortar_mayhem_b.py has no _build_debug_surface)
+    template <class Ctx>
+    static MG_HD void emit_debug(Ctx& c, uint8_t* out, const MgAssetView& a, const K& k, const Frame& f, const State& s,
+                                 const MgScratch&) {
+        if (!mg_mm_is_task_b(k.p.variant)) mg_mm_debug(c, out, a, k, f, s);
+    }
 };
 
 struct MPPolicy {
@@ -239,6 +246,11 @@ struct MPPolicy {
     template <class Ctx>
     static MG_HD void restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f, const MgScratch&) {
         mg_mp_restore(c, buf, a, f, a.hdr->agent_dim >> 1);
+    }
+    template <class Ctx>
+    static MG_HD void emit_debug(Ctx& c, uint8_t* out, const MgAssetView& a, const K&, const Frame& f, const State& s,
+                                 const MgScratch&) {
+        mg_mp_debug(c, out, a, f, s);
     }
 };
 
@@ -336,6 +348,9 @@ struct EPPolicy {
     static MG_HD void restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f, const MgScratch&) {
         mg_ep_restore(c, buf, a, f);
     }
+    // (Endless-MysteryPath's debug render is not built: the host API rejects render_mode="debug_rgb_array" for it)
+    template <class Ctx>
+    static MG_HD void emit_debug(Ctx&, uint8_t*, const MgAssetView&, const K&, const Frame&, const State&, const MgScratch&) {}
 };
 
 template <int TW, bool kEndless>
@@ -607,6 +622,11 @@ struct SSPolicyT {
                                          const MgScratch& sc) {
         mg_ss_emit<kEndless>(c, dst, a, draw_k(k, f), f, reinterpret_cast<MgSSWarpMem*>(sc.warp),
                    reinterpret_cast<const MgSSCtaTables*>(sc.cta), false);
+    }
+    template <class Ctx>
+    static MG_HD void emit_debug(Ctx& c, uint8_t* out, const MgAssetView& a, const K& k, const Frame& f, const State& s,
+                                 const MgScratch&) {
+        mg_ss_debug(c, out, a, draw_k(k, f), f, s, kEndless);
     }
     // unused with kDirectStore
     template <class Ctx>

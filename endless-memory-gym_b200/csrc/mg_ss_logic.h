@@ -256,6 +256,21 @@ MG_HD_NOINLINE void mg_ss_sample_coop(Ctx c, MgSSSampler& g, MgSSState& s, MgSSR
     c.sync();
 }
 
+// A reset frame shows spotlight_surface as the last step left it (the surface is only repainted by step()): invisible
+// while its alpha is 0, i.e. whenever light_dim_off_duration > 0.
+MG_HD void mg_ss_stale_discs(const MgSSState& s, MgSSFrame& f) {
+    int n = 0;
+    if (f.alpha != 0) {
+        n = s.last_n;
+        for (int j = 0; j < n; ++j) {
+            f.disc_x[j] = s.last_x[j];
+            f.disc_y[j] = s.last_y[j];
+            f.disc_r[j] = s.last_r[j];
+        }
+    }
+    f.n_discs = (uint8_t)n;
+}
+
 // reset(): RNG draw order — rotation; agent cell + 2 offsets; per initial spotlight radius, speed, 3 angles;
 // num_coins; per coin cell + 2 offsets; exit cell + 2 offsets (searing_spotlights.py:354-414).
 // Called by every lane of the warp; `g` / `rt` are per-warp scratch.
@@ -329,7 +344,7 @@ MG_HD void mg_ss_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, M
         if (k.p.black_background) s.bg_blue = 2;
         s.live = rt.ok ? 1 : 0;  // sampler exhausted: the reference raises; here the env stays finished
         mg_ss_frame_common(s, 0, f);  // the reset frame draws get_rotated_sprite(0)
-        f.n_discs = 0;
+        mg_ss_stale_discs(s, f);
         f.red_now = 0;
         f.bg_kind = mg_ss_bg_kind(s, 0);
         mg_ss_scene_stamp(s, f, true);
@@ -362,6 +377,10 @@ MG_HD void mg_ss_step_a(const MgSSK& k, MgSSState& s, int a0, int a1, MgSSStepTm
     s.cx = (int16_t)cx;
     s.cy = (int16_t)cy;
     s.rot = (uint8_t)rot;
+    s.hand_x = (int16_t)cx;  // rotated_agent_surface / rect (:462)
+    s.hand_y = (int16_t)cy;
+    s.hand_rot = (uint8_t)rot;
+    s.hand_has = 1;
     tmp.cx = cx;
     tmp.cy = cy;
     if (k.p.show_last_action) {  // the boxes show the PREVIOUS action, then last_action is updated
@@ -418,6 +437,9 @@ MG_HD void mg_ss_step_b(Ctx& c, const MgSSK& k, const double* trig, MgSSState& s
         f.disc_x[j] = (int16_t)dx;
         f.disc_y[j] = (int16_t)dy;
         f.disc_r[j] = sp.radius;
+        s.last_x[j] = (int16_t)dx;  // spotlight_surface keeps them until the next step repaints it
+        s.last_y[j] = (int16_t)dy;
+        s.last_r[j] = sp.radius;
     }
     // at most MG_SS_MAXSPOTS = 32 spotlights: they all sit on the lanes of the team's first warp
     done_bits = c.reduce_or(done_bits);
@@ -425,6 +447,7 @@ MG_HD void mg_ss_step_b(Ctx& c, const MgSSK& k, const double* trig, MgSSState& s
     if (c.lane == 0) {
         s.done_mask |= done_bits;
         tmp.hits = mg_popc32(hits);
+        s.last_n = (uint8_t)tmp.n_proc;
     }
 }
 
@@ -634,7 +657,7 @@ MG_HD void mg_ess_reset_env(Ctx& c, const MgSSK& k, MgSSState& s, MgSSFrame& f, 
         if (k.p.black_background) s.bg_blue = 2;
         s.live = rt.ok ? 1 : 0;
         mg_ess_frame(k, s, 0, f);  // the reset frame draws get_rotated_sprite(0)
-        f.n_discs = 0;
+        mg_ss_stale_discs(s, f);
         f.red_now = 0;
         f.bg_kind = mg_ss_bg_kind(s, 0);
         mg_ss_scene_stamp(s, f, true);

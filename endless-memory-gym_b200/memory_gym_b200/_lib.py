@@ -14,13 +14,15 @@ LIB_PATH = os.path.join(_HERE, "libmemgym_b200.so")
 MG_ABI_VERSION = 5
 MG_OBS_BYTES = 84 * 84 * 3
 MG_DELTA_HDR_BYTES = 176
+MG_DEBUG_DIM = 336
+MG_DEBUG_BYTES = 336 * 336 * 3
 MG_INFO_COLS = 10
 MG_GT_COLS = 4
 MG_MAX_CHOICES = 16
 MG_MM_MAX_COMMANDS = 152
 MG_MM_STATE_BYTES = 256
 MG_MP_STATE_BYTES = 128
-MG_SS_STATE_BYTES = 1024
+MG_SS_STATE_BYTES = 1152
 MG_EP_STATE_BYTES = 2048
 MG_EP_MAX_SEGMENTS = 45
 MG_FLAG_AUTORESET = 1
@@ -107,6 +109,7 @@ class StepIO(C.Structure):
         ("actions", C.c_void_p), ("obs", C.c_void_p), ("final_obs", C.c_void_p), ("reward", C.c_void_p),
         ("done", C.c_void_p), ("info", C.c_void_p), ("ground_truth", C.c_void_p), ("reset_mask", C.c_void_p),
         ("flags", C.c_uint32), ("warps_per_cta", C.c_uint32), ("vector_obs", C.c_void_p), ("trace", C.c_void_p),
+        ("debug_obs", C.c_void_p),
     ]
 
 

@@ -101,15 +101,22 @@ class MemoryGymVecEnv:
     Observation layout per env is pygame's ``surfarray.array3d``: ``[x][y][c]``.
     """
 
-    metadata = {"render_modes": ["rgb_array"], "render_fps": 25}
+    metadata = {"render_modes": ["rgb_array", "debug_rgb_array"], "render_fps": 25}
 
     def __init__(self, env_id, num_envs=1, device="cuda", auto_reset=True, final_obs=False, env_offset=0,
-                 warps_per_cta=0, stream_obs=None, host_results=False, _backend=None):
+                 warps_per_cta=0, stream_obs=None, host_results=False, render_mode=None, _backend=None):
         self.spec_ = _spec(env_id)
         self.env_id = env_id
         self.num_envs = int(num_envs)
         if self.num_envs < 1:
             raise ValueError("num_envs must be >= 1")
+        if render_mode not in (None, "rgb_array", "debug_rgb_array"):
+            raise ValueError(f"render_mode {render_mode!r}: the batched engine renders 'rgb_array' and 'debug_rgb_array'")
+        if render_mode == "debug_rgb_array" and env_id in ("MortarMayhemB-v0", "MortarMayhemB-Grid-v0",
+                                                             "Endless-MysteryPath-v0"):
+            # the reference's B variants have no _build_debug_surface at all; Endless-MysteryPath's is not built
+            raise L.MemGymError(f"render_mode='debug_rgb_array' is not available for {env_id}")
+        self.render_mode = render_mode
         self.device = torch.device(device)
         if self.device.type == "cuda" and self.device.index is None and torch.cuda.is_available():
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -170,6 +177,12 @@ class MemoryGymVecEnv:
         self._io.info = self.info.data_ptr()
         self._io.ground_truth = self._gt_full.data_ptr() if self.has_ground_truth_info else None
         self._io.vector_obs = self.vector_obs.data_ptr() if self.task_b else None
+        # render_mode="debug_rgb_array": every reset / step also paints the ground-truth render of the reference
+        # (_build_debug_surface, 336 x 336 x 3 per env, [y][x][c]) — as if render() were called once per reset / step
+        self.debug = None
+        if self.render_mode == "debug_rgb_array":
+            self.debug = torch.zeros((n, L.MG_DEBUG_DIM, L.MG_DEBUG_DIM, 3), dtype=torch.uint8, device=dev)
+            self._io.debug_obs = self.debug.data_ptr()
         # rollouts: a global work counter the kernels keep at zero between launches (dynamic env -> warp scheduling
         # across SMs). MG_LOCAL_SCHED=1 switches it off (measurement knob): every SM works through its own share.
         self._sched = None if os.environ.get("MG_LOCAL_SCHED") else torch.zeros(2, dtype=torch.int32, device=dev)
@@ -421,7 +434,10 @@ class MemoryGymVecEnv:
         return out
 
     def render(self):
-        """``rgb_array`` of the reference (mortar_mayhem.py:396): the observation transposed to [y][x][c]."""
+        """``rgb_array`` of the reference (mortar_mayhem.py:396): the observation transposed to [y][x][c];
+        ``debug_rgb_array`` (:397-399): the ground-truth render uint8[N,336,336,3] of the last reset / step."""
+        if self.render_mode == "debug_rgb_array":
+            return self.debug
         return self.obs.permute(0, 2, 1, 3)
 
     def close(self):
@@ -584,8 +600,9 @@ class MemoryGymEnv:
     numpy observations, Python float rewards, dict infos. Thin wrapper over ``MemoryGymVecEnv(num_envs=1,
     auto_reset=False)`` for drop-in use and for the parity tests; throughput comes from the batched class."""
 
-    def __init__(self, env_id, device="cuda", _backend=None):
-        self.vec = MemoryGymVecEnv(env_id, 1, device=device, auto_reset=False, _backend=_backend)
+    def __init__(self, env_id, device="cuda", render_mode=None, _backend=None):
+        self.vec = MemoryGymVecEnv(env_id, 1, device=device, auto_reset=False, render_mode=render_mode, _backend=_backend)
+        self.render_mode = render_mode
         self.action_space, self.observation_space = self.vec.action_space, self.vec.observation_space
         self.default_reset_parameters = self.vec.default_reset_parameters
         self.has_ground_truth_info = self.vec.has_ground_truth_info

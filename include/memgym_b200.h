@@ -53,6 +53,8 @@ extern "C" {
 
 #define MG_SCREEN 84
 #define MG_OBS_BYTES (84 * 84 * 3) /* 21168 bytes per env, [x][y][c] */
+#define MG_DEBUG_DIM 336           /* debug_rgb_array: the 84x84 ground-truth surface scaled 4x */
+#define MG_DEBUG_BYTES (336 * 336 * 3) /* per env, [y][x][c] like the reference's render() */
 #define MG_INFO_COLS 10            /* doubles per env in the info matrix */
 #define MG_GT_COLS 4               /* doubles per env in the ground-truth matrix */
 #define MG_TRACE_COLS 16
@@ -60,7 +62,7 @@ extern "C" {
 #define MG_MM_MAX_COMMANDS 152     /* capacity of the per-env command list */
 #define MG_MM_STATE_BYTES 256      /* one env record (Mortar Mayhem family) */
 #define MG_MP_STATE_BYTES 128      /* one env record (Mystery Path) */
-#define MG_SS_STATE_BYTES 1024     /* one env record (Searing Spotlights) */
+#define MG_SS_STATE_BYTES 1152     /* one env record (Searing Spotlights) */
 #define MG_EP_STATE_BYTES 2048     /* one env record (Endless Mystery Path) */
 #define MG_EP_MAX_SEGMENTS 45      /* capacity of the per-env path: 45 segments x 8 columns = 360 columns */
 
@@ -229,6 +231,10 @@ typedef struct mg_step_io {
     uint64_t* trace;        /* nullable: [n][MG_TRACE_COLS] uint64, per-env phase timestamps (globaltimer ns):   */
                             /* 0 kernel entry, 1 prologue done, 2 dependency wait done, 3 record in smem,      */
                             /* 4 logic done, 5 frame composed, 6 bulk store issued, 7 SM id, 8.. env-type specific  */
+    uint8_t* debug_obs;     /* nullable: [n][336][336][3] ([y][x][c]): render_mode="debug_rgb_array" of the reference     */
+                            /* (_build_debug_surface + transform.scale, e.g. mortar_mayhem.py:105-136, 397-399) for the   */
+                            /* frame written to obs, as if render() were called once after every reset() / step().        */
+                            /* Built for MM, MM-Grid, Endless-MM, MysteryPath(-Grid), (Endless-)SearingSpotlights.        */
 } mg_step_io;
 
 /* A whole rollout in one launch: T = n_steps consecutive steps with given actions (the reference's bench.py

@@ -75,6 +75,11 @@ CASES = {
     "ess_nocoin": ("Endless-SearingSpotlights-v0", {"coin_enabled": False, "max_steps": 70, "initial_spawns": 6,
                                                      "spot_min_speed": 0.01, "spot_max_speed": 0.03,
                                                      "agent_health": 3}, 4, 200),
+    # light_dim_off_duration == 0: the reset frame shows spotlight_surface as the previous episode's last step left it
+    "ss_dim0": ("SearingSpotlights-v0", {"light_dim_off_duration": 0, "light_threshold": 200, "max_steps": 45,
+                                          "agent_health": 3, "initial_spawns": 5}, 4, 260),
+    "ess_dim0": ("Endless-SearingSpotlights-v0", {"light_dim_off_duration": 0, "max_steps": 40, "black_background": True,
+                                                   "agent_visible": True, "steps_per_coin": 30}, 4, 220),
     "emp": ("Endless-MysteryPath-v0", None, 6, 700),
     "emp_opts": ("Endless-MysteryPath-v0", {"max_steps": 150, "show_background": True, "show_stamina": True,
                                              "camera_offset_scale": 2.3, "stamina_level": 12, "reward_fall_off": -0.1,

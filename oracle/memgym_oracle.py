@@ -59,8 +59,18 @@ def _paste(frame: np.ndarray, src: R.Surface, x: int, y: int) -> None:
 class _OracleEnv:
     """Seeding contract of gymnasium 0.29 ``Env.reset`` (seed given -> new PCG64; else continue)."""
 
+    render_mode = None  # "debug_rgb_array": render() returns the ground-truth composite (_build_debug_surface)
+
     def __init__(self):
         self._rng = None
+
+    def render(self):
+        """``render()`` of the reference in ``debug_rgb_array`` mode (e.g. mortar_mayhem.py:397-399): the 84x84 debug
+        surface scaled to 336x336 (``transform.scale`` = exact 4x pixel replication), returned as [y][x][c]. Like the
+        reference's, a call may consume state (the clone of the command queue): call it once per reset() / step()."""
+        assert self.render_mode == "debug_rgb_array"
+        obs = _frame_to_obs(self._debug_surface())           # [x][y][c] at 84x84
+        return np.repeat(np.repeat(obs.transpose(1, 0, 2), 4, 0), 4, 1)
 
     def _seed(self, seed):
         if seed is not None:
@@ -255,6 +265,7 @@ class MortarMayhemOracle(_OracleEnv):
             dur = int(rng.choice(p["command_show_duration"]))
             delay = int(rng.choice(p["command_show_delay"]))
             self.show = self._show_list(self.commands, dur, delay)
+            self.show_clone = list(self.show)  # "the clone is needed for render()" (:251)
             first = self.show.pop(0)
         d0 = assets.COMMAND_DELTAS[self.commands[0]]
         self.target = (self.pos[0] + d0[0], self.pos[1] + d0[1])
@@ -354,10 +365,33 @@ class MortarMayhemOracle(_OracleEnv):
         if done:
             info = {"reward": _seq_sum(self.rewards), "length": len(self.rewards), "success": success,
                     "commands_completed": (self.cc - 1 + success) / self.n}
+        self.handle = sprite  # rotated_agent_surface / rect (:291, :295): survives reset(), see _debug_surface
         return self._obs(self._render(icon, sprite)), reward, done, False, info
 
     # ---- frame -----------------------------------------------------------------------------------
+    handle = None      # pose of rotated_agent_surface/rect; None until the first step of the instance (:91)
+    show_clone = ()    # _command_visualization_clone
+
+    def _debug_surface(self):
+        """_build_debug_surface (mortar_mayhem.py:105-136; same code in mortar_mayhem_grid.py:104-135 and
+        endless_mortar_mayhem.py:114-145): arena, the sprite handle of the last step (it is not refreshed by reset():
+        right after a reset the agent is still drawn at the previous episode's last pose), the next entry of the
+        CLONED command queue while the real queue is non-empty, and a green ring (r = tile_dim // 2, width int(8 *
+        SCALE)) on the target tile."""
+        icon = None
+        if self.show:
+            icon = self.show_clone.pop(0)
+        sprite = self.handle if self.handle is not None else (self.cx, self.cy, 0)
+        surf = R.Surface(SCREEN, SCREEN)
+        surf.px[...] = self._compose(icon, sprite)
+        tx, ty = self._tile_centre(int(self.target[0]), int(self.target[1]))
+        R.circle(surf, (0, 255, 0), (tx, ty), TILE // 2, int(8 * SCALE))
+        return surf.px
+
     def _render(self, icon, sprite):
+        return _frame_to_obs(self._compose(icon, sprite))
+
+    def _compose(self, icon, sprite):
         frame = np.zeros((SCREEN, SCREEN), dtype=np.uint32)
         blue, red = assets.mortar_tile(SCALE, False), assets.mortar_tile(SCALE, True)
         redden = self.tiles_on and self.p["visual_feedback"]
@@ -373,7 +407,7 @@ class MortarMayhemOracle(_OracleEnv):
             surf = assets.command_icon("" if icon < 0 else assets.COMMAND_NAMES[icon], SCALE)
             pos = assets.command_blit_pos(SCALE, SCREEN)
             _paste(frame, surf, int(pos[0]), int(pos[1]))
-        return _frame_to_obs(frame)
+        return frame
 
 
 def _seq_sum(values):
@@ -514,6 +548,7 @@ class EndlessMortarMayhemOracle(MortarMayhemOracle):
         self.dur = int(rng.choice(p["command_show_duration"]))
         self.delay = int(rng.choice(p["command_show_delay"]))
         self.show = self._show_list(self.commands, self.dur, self.delay)
+        self.show_clone = list(self.show)
         first = self.show.pop(0)
         d0 = assets.COMMAND_DELTAS[self.commands[0]]
         self.target = ((self.pos[0] + d0[0]) % 6, (self.pos[1] + d0[1]) % 6)
@@ -557,6 +592,7 @@ class EndlessMortarMayhemOracle(MortarMayhemOracle):
                     self.n = len(self.commands)
                     self.cc = self.cs = self.cv = 0
                     self.show = self._show_list(new, self.dur, self.delay)
+                    self.show_clone = list(self.show)  # re-cloned (:321): render() now runs one entry AHEAD of step()
                 self.cs = 1
             if self.tiles_on:
                 if self.cv % self.E == 0 and self.cv > 0:
@@ -584,6 +620,7 @@ class EndlessMortarMayhemOracle(MortarMayhemOracle):
                     "ground_truth": self._gt()}
         # (within an episode the agent cannot move during a show phase, so the handle's pose equals
         # the live pose; only across a reset does it lag behind)
+        self.handle = self.stale
         return self._render(icon, self.stale), reward, done, False, info
 
 
@@ -786,20 +823,35 @@ class MysteryPathOracle(_OracleEnv):
         return self._render(cross=True), reward, done, False, info
 
     def _render(self, cross):
+        return _frame_to_obs(self._compose(cross, False))
+
+    def _debug_surface(self):
+        """_build_debug_surface (mystery_path.py:103-117, mystery_path_grid.py:102-116): the whole path (goal green,
+        origin blue, the rest white), the walls in red, the agent and the fall-off cross (its alpha is 0 after reset)."""
+        return self._compose(True, True)
+
+    def _compose(self, cross, debug):
         frame = np.zeros((SCREEN, SCREEN), dtype=np.uint32)
         t = int(self.TILE)
-        # MysteryPath.draw_to_surface (pygame_assets.py:749-758): path[0] is the goal, path[-1] the origin
+        # MysteryPath.draw_to_surface (pygame_assets.py:738-762): path[0] is the goal, path[-1] the origin
         last = len(self.path) - 1
         for k, (i, j) in enumerate(self.path):
-            if k == 0 and self.p["show_goal"]:
+            if k == 0 and (self.p["show_goal"] or debug):
                 frame[j * t:(j + 1) * t, i * t:(i + 1) * t] = R.map_rgb((0, 255, 0))
-            elif k == last and self.p["show_origin"]:
+            elif k == last and (self.p["show_origin"] or debug):
                 frame[j * t:(j + 1) * t, i * t:(i + 1) * t] = R.map_rgb((0, 0, 255))
+            elif 0 < k < last and debug:
+                frame[j * t:(j + 1) * t, i * t:(i + 1) * t] = R.map_rgb((255, 255, 255))
+        if debug:
+            for i in range(self.GRID):
+                for j in range(self.GRID):
+                    if self.walls[i][j]:
+                        frame[j * t:(j + 1) * t, i * t:(i + 1) * t] = R.map_rgb((255, 0, 0))
         sp = self.sprites[self.rotation // 45]
         _paste(frame, sp, self.cx - (sp.w >> 1), self.cy - (sp.h >> 1))
         if cross and self.cross_alpha == 255:
             _paste(frame, assets.fall_off_cross(SCALE), self.cross_x, self.cross_y)
-        return _frame_to_obs(frame)
+        return frame
 
 
 class GridMysteryPathOracle(MysteryPathOracle):
@@ -962,6 +1014,11 @@ class SearingSpotlightsOracle(_OracleEnv):
         # the two tiled backgrounds are built once per instance and mutated in place by reset/step
         # (hide_chessboard -> white, black_background -> black): sticky across resets
         self.bg_state = {"blue": "chess", "red": "chess"}
+        # spotlight_surface is created once per instance (:124-126) and only repainted by step() (:208-216): after a
+        # reset it still shows the discs of the previous episode's last step. They are invisible while the surface's
+        # alpha is 0 (light_dim_off_duration > 0) and visible in the reset frame when light_dim_off_duration == 0.
+        self.surface_discs = []
+        self.handle = None  # pose of rotated_agent_surface / rect (:135, :462): not refreshed by reset()
 
     # ---- GridPositionSampler -----------------------------------------------------------------------
     def _sample(self, rng, block_radius):
@@ -1057,7 +1114,7 @@ class SearingSpotlightsOracle(_OracleEnv):
         self.bg = "blue"
         if p["black_background"]:
             self.bg_state["blue"] = "black"
-        return self._render([], 0), {}
+        return self._render(self.surface_discs, 0), {}
 
     # ---- step --------------------------------------------------------------------------------------
     def step(self, action):
@@ -1166,6 +1223,8 @@ class SearingSpotlightsOracle(_OracleEnv):
             info = {"reward": _seq_sum(self.rewards), "length": len(self.rewards),
                     "agent_health": self.hp / self.agent_health,
                     "coins_collected": self.coins_collected / self.num_coins, "success": success}
+        self.surface_discs = discs
+        self.handle = (self.cx, self.cy, self.rotation)
         return self._render(discs, self.rotation), reward, done, False, info
 
     # ---- frame (searing_spotlights.py:526-543 / 419-437) ---------------------------------------------
@@ -1190,10 +1249,22 @@ class SearingSpotlightsOracle(_OracleEnv):
             sid += 1
         return layers
 
-    def _render(self, discs, sprite_rot):
+    DEBUG_LAYERS = ["bg", "spot", "exit", "coin", "agent", "bar"]
+
+    def _debug_surface(self):
+        """_build_debug_surface (searing_spotlights.py:157-185, endless_searing_spotlights.py:150-177): background, the
+        spotlight surface as step() left it (with its current alpha), then exit, coins, the sprite handle of the last
+        step (not refreshed by reset()) and the top bar — everything the agent may not see is drawn above the light."""
+        pose = self.handle if self.handle is not None else (self.cx, self.cy, 0)
+        obs = self._render(self.surface_discs, pose[2], layers=self.DEBUG_LAYERS, pose=pose, debug=True)
+        px = obs.astype(np.uint32)
+        return ((px[..., 0] << 16) | (px[..., 1] << 8) | px[..., 2]).T  # back to the [y][x] pixel array
+
+    def _render(self, discs, sprite_rot, layers=None, pose=None, debug=False):
         p = self.p
         dst = R.Surface(SCREEN, SCREEN)
-        for layer in self._layer_order():
+        ax, ay = (self.cx, self.cy) if pose is None else (pose[0], pose[1])
+        for layer in (layers if layers is not None else self._layer_order()):
             if layer == "bg":
                 st = self.bg_state[self.bg]
                 if st == "chess":
@@ -1202,7 +1273,7 @@ class SearingSpotlightsOracle(_OracleEnv):
                 else:
                     dst.px[...] = R.map_rgb((255, 255, 255)) if st == "white" else 0
             elif layer == "coin":
-                if getattr(self, "coin_layer_opaque", False):
+                if getattr(self, "coin_layer_opaque", False) and not debug:
                     dst.px[...] = 0
                 elif self.num_coins > 0:
                     cs = R.Surface(SCREEN, SCREEN)
@@ -1217,7 +1288,7 @@ class SearingSpotlightsOracle(_OracleEnv):
                 R.blit(es, dst, (self.exit[0] - (es.w >> 1), self.exit[1] - (es.h >> 1)))
             elif layer == "agent":
                 sp = self.sprites[sprite_rot // 45]
-                R.blit(sp, dst, (self.cx - (sp.w >> 1), self.cy - (sp.h >> 1)))
+                R.blit(sp, dst, (ax - (sp.w >> 1), ay - (sp.h >> 1)))
             elif layer == "spot":
                 ss = R.Surface(SCREEN, SCREEN)
                 ss.colorkey = R.map_rgb((255, 0, 0))
@@ -1317,7 +1388,7 @@ class EndlessSearingSpotlightsOracle(SearingSpotlightsOracle):
         self.bg = "blue"
         if p["black_background"]:
             self.bg_state["blue"] = "black"
-        return self._render([], 0), {"ground_truth": self._gt()}
+        return self._render(self.surface_discs, 0), {"ground_truth": self._gt()}
 
     def step(self, action):
         p = self.p
@@ -1397,6 +1468,8 @@ class EndlessSearingSpotlightsOracle(SearingSpotlightsOracle):
             info = {"reward": _seq_sum(self.rewards), "length": len(self.rewards),
                     "agent_health": self.hp / self.agent_health, "coins_collected": self.coins_collected,
                     "ground_truth": self._gt()}
+        self.surface_discs = discs
+        self.handle = (self.cx, self.cy, self.rotation)
         return self._render(discs, self.rotation), reward, done, False, info
 
     # ---- frame (:376-391 / 463-478): the coin layer sits above the spotlights while the coin is fresh ----
@@ -1416,12 +1489,15 @@ class EndlessSearingSpotlightsOracle(SearingSpotlightsOracle):
             sid += 1
         return layers
 
-    def _render(self, discs, sprite_rot):
-        # coin_surface is a fresh opaque black surface when the coin is disabled (never filled / colour-keyed)
+    DEBUG_LAYERS = ["bg", "spot", "coin", "agent", "bar"]
+
+    def _render(self, discs, sprite_rot, layers=None, pose=None, debug=False):
+        # coin_surface is a fresh opaque black surface when the coin is disabled (never filled / colour-keyed);
+        # the debug render builds its own colour-keyed coin surface (:157-162)
         self.num_coins = 1
         self.coins = [self.coin] if self.p["coin_enabled"] else []
         self.coin_layer_opaque = not self.p["coin_enabled"]
-        return super()._render(discs, sprite_rot)
+        return super()._render(discs, sprite_rot, layers, pose, debug)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -1663,5 +1739,7 @@ ORACLES = {
 }
 
 
-def make(env_id):
-    return ORACLES[env_id]()
+def make(env_id, render_mode=None):
+    env = ORACLES[env_id]()
+    env.render_mode = render_mode
+    return env

@@ -108,6 +108,8 @@ int run_q(const typename P::K& k, const void* assets, void* state, MgKIO q, bool
                 // the buffer must be clean again: catches any compose/restore asymmetry (envs with an un-patch path)
                 if (kCheckClean && memcmp(buf, view.tmpl[0], MG_FRAME_BYTES) != 0) return -100;
             }
+            if (!rollout && q.io.debug_obs && job.nframes > 0)  // like the kernel: the ground-truth render of the obs frame
+                P::emit_debug(ctx, q.io.debug_obs + (size_t)env * MG_DEBUG_BYTES, view, k, fr[job.nframes - 1], *st, scratch);
         }
     }
     return 0;

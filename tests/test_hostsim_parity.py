@@ -8,7 +8,7 @@ from hostsim_util import HostSimBackend
 from replay_util import replay_golden_batched, replay_golden_single, rollout_vs_oracle
 
 CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts", "ss_black",
-         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts", "ess", "ess_opts", "ess_black", "ess_nocoin",
+         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts", "ess", "ess_opts", "ess_black", "ess_nocoin", "ss_dim0", "ess_dim0",
          "emp", "emp_opts", "emp_nopast", "emp_cam"]
 
 

@@ -7,7 +7,7 @@ from oracle import memgym_oracle as O
 from golden_util import action_for, crc, load_case, visual
 
 CASES = ["mm", "mm_opts", "mmgrid", "emm", "emm_opts", "mp", "mp_opts", "ss", "ss_opts", "ss_black",
-         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts", "ess", "ess_opts", "ess_black", "ess_nocoin",
+         "mmb", "mmb_opts", "mmbgrid", "mpgrid", "mpgrid_opts", "ess", "ess_opts", "ess_black", "ess_nocoin", "ss_dim0", "ess_dim0",
          "emp", "emp_opts", "emp_nopast", "emp_cam"]
 
 
