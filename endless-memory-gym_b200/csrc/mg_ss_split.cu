@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(64) mg_ss_logic_kernel(const __grid_constant__
     const MgAssetView view = mg_asset_view(assets);
     const double* trig = (const double*)(view.base + view.hdr->trig_off);
     MgLaneCtx c;
-    MgSSState s;  // thread-local copy of the record (local memory, L1-resident)
+    alignas(16) MgSSState s;  // thread-local copy of the record (local memory, L1-resident)
     {
         const uint4* g = reinterpret_cast<const uint4*>(state + (size_t)env * sizeof(MgSSState));
         uint4* l = reinterpret_cast<uint4*>(&s);
@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(64) mg_ss_logic_kernel(const __grid_constant__
 }
 
 // ---- raster: persistent teams turn descriptions into frames -------------------------------------------------------------
-constexpr int kRasterTeamBytes = ((int)sizeof(MgSSWarpMem) + 2 * MG_SS_DESC_BYTES + 16 + 127) / 128 * 128;
+constexpr int kWarpMemBytes = ((int)sizeof(MgSSWarpMem) + 15) / 16 * 16;  // (the descriptions behind it are read 16 bytes at a time)
+constexpr int kRasterTeamBytes = (kWarpMemBytes + 2 * MG_SS_DESC_BYTES + 16 + 127) / 128 * 128;
 constexpr int kRasterCtaBytes = ((int)sizeof(MgSSCtaTables) + 127) / 128 * 128 + MG_CTA_HDR_BYTES;
 
 template <int TW, bool kEndless>
@@ -162,8 +163,8 @@ __global__ void __launch_bounds__(TW * 32 * 9 > 1024 ? 1024 : TW * 32 * 9, 1)
     const int lane = threadIdx.x % kTeam, team = threadIdx.x / kTeam;
     uint8_t* const tmem = smem + (size_t)team * kRasterTeamBytes;
     MgSSWarpMem* const wm = reinterpret_cast<MgSSWarpMem*>(tmem);
-    MgSSDesc* const dbuf = reinterpret_cast<MgSSDesc*>(tmem + sizeof(MgSSWarpMem));
-    uint32_t* const grab = reinterpret_cast<uint32_t*>(tmem + sizeof(MgSSWarpMem) + 2 * MG_SS_DESC_BYTES);
+    MgSSDesc* const dbuf = reinterpret_cast<MgSSDesc*>(tmem + kWarpMemBytes);
+    uint32_t* const grab = reinterpret_cast<uint32_t*>(tmem + kWarpMemBytes + 2 * MG_SS_DESC_BYTES);
     uint8_t* const cextra = smem + (size_t)nteams * kRasterTeamBytes;
     MgSSCtaTables* const tables = reinterpret_cast<MgSSCtaTables*>(cextra);
     MgCtaHdr* const hdr = reinterpret_cast<MgCtaHdr*>(cextra + kRasterCtaBytes - MG_CTA_HDR_BYTES);

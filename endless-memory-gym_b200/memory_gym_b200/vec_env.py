@@ -198,10 +198,10 @@ class MemoryGymVecEnv:
             self._knobs |= (int(os.environ["MG_SS_TW"]) & 7) << 8
         self._io.flags = (L.MG_FLAG_AUTORESET if self.auto_reset else 0) | self._stream_step | self._knobs
         # Searing Spotlights: frame descriptions of the two-kernel path (state machine one lane per env, then the
-        # rasteriser) live in a scratch buffer; MG_SS_FUSED=1 keeps the single fused kernel (measurement knob)
+        # rasteriser) live in a scratch buffer; opt-in with MG_SS_SPLIT=1 (measured slower than the fused kernel: profiles/r02_ss.md)
         self._scratch = None
         self._scratch_steps = 0
-        self._ss_split = self.spec_.family == "ss" and not os.environ.get("MG_SS_FUSED") and self.device.type == "cuda"
+        self._ss_split = self.spec_.family == "ss" and bool(os.environ.get("MG_SS_SPLIT")) and self.device.type == "cuda"
         if self._ss_split and self.render_mode != "debug_rgb_array":
             self._ensure_scratch(1)
             self._io.scratch, self._io.scratch_bytes = self._scratch.data_ptr(), self._scratch.numel()

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/r02d_pytest.log
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/r02d_pytest.log
 for tw in 2 3 4; do
   MG_SS_TW=$tw timeout 300 python bench.py --env SearingSpotlights-v0 --steps 20 --warmup 5 --no-cpu --no-configs 2>&1 | tail -1 > gpurun_out/r02d_ss_tw$tw.json
 done
