@@ -9,7 +9,7 @@
 #if defined(__CUDACC__)
 #define MG_HD __host__ __device__ __forceinline__
 // one out-of-line copy: keeps the (rarely taken, single-lane) reset / RNG paths small in the I-cache
-#define MG_HD_NOINLINE inline __host__ __device__ __noinline__
+#define MG_HD_NOINLINE __host__ __device__ __noinline__
 #define MG_NOUNROLL _Pragma("unroll 1")
 #define MG_UNROLL _Pragma("unroll")
 #else

@@ -32,11 +32,145 @@
 #include "mg_ss_logic.h"
 #include "mg_params_host.h"
 #include "mg_device_host.h"
-#include "mg_ss_split.h"
 #include "mg_policy.h"
 
 
-#include "mg_device.cuh"
+// ---- PTX wrappers (TMA bulk copies, mbarrier, proxy fence) ---------------------------------------
+__device__ __forceinline__ uint32_t mg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mg_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mg_bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)),
+                 "r"(mg_smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mg_bulk_store_hint(void* gdst, const void* ssrc, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(
+                     __cvta_generic_to_global(gdst)),
+                 "r"(mg_smem_u32(ssrc)), "r"(bytes), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t mg_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void mg_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void mg_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the newest `keep` bulk groups have fully completed (their global writes are performed)
+__device__ __forceinline__ void mg_bulk_wait_done(int keep) {
+    if (keep <= 0)
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    else if (keep == 1)
+        asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+    else if (keep == 2)
+        asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+    else
+        asm volatile("cp.async.bulk.wait_group 3;" ::: "memory");
+}
+__device__ __forceinline__ void mg_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mg_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mg_bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(mg_smem_u32(sdst)),
+        "l"(__cvta_generic_to_global(gsrc)), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void mg_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ uint64_t mg_now() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// this env's action components. int64[n][2] rows are 16-byte aligned whenever the base is: one 128-bit load (the
+// actions may live in pinned host memory, where every load is a PCIe read)
+__device__ __forceinline__ void mg_load_actions(const int64_t* a, int dims, int64_t& a0, int64_t& a1) {
+    if (dims > 1) {
+        if ((reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+            const longlong2 v = *reinterpret_cast<const longlong2*>(a);
+            a0 = v.x;
+            a1 = v.y;
+        } else {
+            a0 = a[0];
+            a1 = a[1];
+        }
+    } else {
+        a0 = a[0];
+    }
+}
+
+// per-CTA words: the asset staging barrier and the work counter of the CTA-local dynamic env -> team scheduling
+#define MG_CTA_HDR_BYTES 128
+struct MgCtaHdr {
+    uint64_t stage_bar;
+    uint32_t next;
+    uint32_t teams_done;  // teams that have left the kernel (helper warps leave when all have)
+};
+
+// execution context of mg_frame.h on the device: the 32 lanes of the warp that owns the env
+struct MgWarpCtx {
+    static constexpr int kLanes = 32;  // lanes of a single-warp team (cooperative code sized at compile time)
+    int lane, nl;
+    uint32_t bar, phase;
+    uint64_t policy;  // L2 evict-first cache policy
+    uint64_t* trow;   // this env's trace row (mg_step_io.trace) or nullptr
+    int bar_id;       // named barrier of this team (teams of more than one warp), 0 = a single warp
+    __device__ __forceinline__ void stamp(int col) {
+        if (MG_UNLIKELY(trow != nullptr) && lane == 0) trow[col] = mg_now();
+    }
+    // all threads of the team that owns the env (one warp, or kTeamWarps warps on a named barrier)
+    __device__ __forceinline__ void sync() {
+        if (bar_id == 0)
+            __syncwarp();
+        else
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nl) : "memory");
+    }
+    // 128-bit store to global memory; `stream` = L2 evict-first (the frame is not re-read soon)
+    __device__ __forceinline__ void store16(MgVec16* p, const MgVec16& v, bool stream) {
+        if (stream)
+            asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(__cvta_generic_to_global(p)),
+                         "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
+                         : "memory");
+        else
+            *p = v;
+    }
+    __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
+    // warp reductions (single-warp teams only): every lane gets the result
+    __device__ __forceinline__ uint32_t reduce_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
+    __device__ __forceinline__ uint32_t reduce_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
+    __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+    // shared-memory hand-over between warps of a CTA (teams <-> helper warps)
+    __device__ __forceinline__ uint32_t cas_u32(uint32_t* p, uint32_t cmp, uint32_t val) { return atomicCAS(p, cmp, val); }
+    __device__ __forceinline__ void fence_block() { __threadfence_block(); }
+    __device__ __forceinline__ void fence_device() { __threadfence(); }
+    __device__ __forceinline__ void nanosleep(unsigned ns) { __nanosleep(ns); }
+    __device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
+    // whole-frame template -> this warp's frame buffer, by TMA
+    __device__ __forceinline__ void copy_frame(uint8_t* dst, const uint8_t* src) {
+        mg_fence_proxy_async();  // earlier generic-proxy accesses to dst are ordered before the async write
+        sync();
+        if (lane == 0) {
+            mg_mbar_expect_tx(bar, MG_FRAME_BYTES);
+            mg_bulk_load(dst, src, MG_FRAME_BYTES, bar);
+        }
+        mg_mbar_wait(bar, phase);
+        phase ^= 1u;
+    }
+};
 
 // pipelined Searing-Spotlights rollouts: 1 = the raster warp also builds the lit bitmap while the logic warp computes the
 // next step (measured: see profiles/r01b_summary.md), 0 = both warps build it after the barrier
@@ -557,33 +691,6 @@ static int launch_env(const typename P::K& k, const void* assets, void* state, c
     return 0;
 }
 
-// the kernel-side view of a mg_rollout_io (strides of the [T][n] buffers)
-static void rollout_kio(const mg_rollout_io* r, int n, int act_dims, MgKIO* out) {
-    MgKIO& q = *out;
-    memset(&q, 0, sizeof(q));
-    q.io.actions = r->actions;
-    q.io.obs = r->obs;
-    q.io.final_obs = r->final_obs;
-    q.io.reward = r->reward;
-    q.io.done = r->done;
-    q.io.info = r->info;
-    q.io.ground_truth = r->ground_truth;
-    q.io.trace = r->trace;
-    q.io.vector_obs = r->vector_obs;
-    q.sched = r->sched;
-    q.io.flags = r->flags | MG_FLAG_AUTORESET;  // a rollout without auto-reset would only idle finished envs
-    q.mode = MG_MODE_STEP;
-    q.n = n;
-    q.act_dims = act_dims;
-    q.n_steps = r->n_steps;
-    q.ring_n = r->ring;
-    q.act_stride = (int64_t)n * act_dims;
-    q.obs_stride = (int64_t)n * MG_FRAME_BYTES;
-    q.rew_stride = n;
-    q.done_stride = n;
-    q.info_stride = r->info_per_step ? (int64_t)n * MG_INFO_COLS : 0;
-}
-
 // rollout: ONE launch runs all n_steps steps
 template <class P>
 static int launch_rollout(const typename P::K& k, const void* assets, void* state, const mg_rollout_io* r, int n,
@@ -607,9 +714,30 @@ static int launch_rollout(const typename P::K& k, const void* assets, void* stat
     int rc = plan_launch<P, true>(guard.dev, n, (int)r->warps_per_cta, default_wpc, (r->flags & MG_FLAG_NO_HELPERS) != 0, &plan);
     if (rc) return rc;
     MgKIO q;
-    rollout_kio(r, n, act_dims, &q);
+    memset(&q, 0, sizeof(q));
+    q.io.actions = r->actions;
+    q.io.obs = r->obs;
+    q.io.final_obs = r->final_obs;
+    q.io.reward = r->reward;
+    q.io.done = r->done;
+    q.io.info = r->info;
+    q.io.ground_truth = r->ground_truth;
+    q.io.trace = r->trace;
+    q.io.vector_obs = r->vector_obs;
+    q.sched = r->sched;
     q.n_helpers = plan.helpers;
+    q.io.flags = r->flags | MG_FLAG_AUTORESET;  // a rollout without auto-reset would only idle finished envs
+    q.mode = MG_MODE_STEP;
+    q.n = n;
     q.stage_cap = plan.stage_cap;
+    q.act_dims = act_dims;
+    q.n_steps = r->n_steps;
+    q.ring_n = r->ring;
+    q.act_stride = (int64_t)n * act_dims;
+    q.obs_stride = (int64_t)n * MG_FRAME_BYTES;
+    q.rew_stride = n;
+    q.done_stride = n;
+    q.info_stride = r->info_per_step ? (int64_t)n * MG_INFO_COLS : 0;
     return launch_one<P, true>(k, q, plan, assets, state, stream);
 }
 
@@ -729,43 +857,11 @@ extern "C" int mg_ss_step(const mg_ss_params* p, const void* assets, void* state
                           void* stream) {
     return mg_ss_step_many(p, assets, state, io, 1, n, stream);
 }
-// Two-kernel path (mg_ss_split.cu) for calls that bring a scratch buffer: one lane per env for the state machine, then
-// the rasteriser. The debug render and the trace live in the fused kernel only.
-static int ss_tw(uint32_t flags) { return (int)((flags >> MG_FLAG_SS_TW_SHIFT) & 7u); }
-
 extern "C" int mg_ss_step_many(const mg_ss_params* p, const void* assets, void* state, const mg_step_io* ios,
                                int n_steps, int n, void* stream) {
     const MgSSK* kp;
     if (mg_cached_k(p, mg_ss_check_params, mg_ss_derive, &kp)) return MG_EINVAL;
     const MgSSK& k = *kp;
-    bool split = ios != nullptr && n_steps >= 1 && n > 0;
-    for (int t = 0; split && t < n_steps; ++t) split = ios[t].scratch && !ios[t].debug_obs && !ios[t].trace;
-    if (split) {
-        if (check_common(assets, state, n)) return MG_EINVAL;
-        for (int t = 0; t < n_steps; ++t) {
-            const mg_step_io* io = ios + t;
-            if (!io->obs || !io->actions || !io->reward || !io->done || !io->info) {
-                mg_set_err("mg_step_io: obs, actions, reward, done, info must be non-NULL");
-                return MG_EINVAL;
-            }
-            if (((uintptr_t)io->obs & 15) || (io->final_obs && ((uintptr_t)io->final_obs & 15))) {
-                mg_set_err("alignment: obs/final_obs must be 16-byte aligned");
-                return MG_EINVAL;
-            }
-            MgKIO q;
-            memset(&q, 0, sizeof(q));
-            q.io = *io;
-            q.mode = MG_MODE_STEP;
-            q.n = n;
-            q.act_dims = 2;
-            q.n_steps = 1;
-            q.ring_n = 1;
-            int rc = mg_ss_split_launch(k, q, assets, state, io->scratch, (size_t)io->scratch_bytes, ss_tw(io->flags),
-                                        (io->flags & MG_FLAG_NO_PDL) != 0, stream);
-            if (rc) return rc;
-        }
-        return 0;
-    }
     MG_SS_DISPATCH(launch_env, k, assets, state, nullptr, ios, n_steps, n, MG_MODE_STEP, 2, stream, 10);
 }
 extern "C" int mg_ss_rollout(const mg_ss_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
@@ -773,20 +869,5 @@ extern "C" int mg_ss_rollout(const mg_ss_params* p, const void* assets, void* st
     const MgSSK* kp;
     if (mg_cached_k(p, mg_ss_check_params, mg_ss_derive, &kp)) return MG_EINVAL;
     const MgSSK& k = *kp;
-    if (r && r->scratch && !r->trace && n > 0) {
-        if (check_common(assets, state, n)) return MG_EINVAL;
-        if (!r->actions || !r->obs || !r->reward || !r->done || !r->info || r->n_steps < 1 || r->ring < 1) {
-            mg_set_err("mg_rollout_io: actions, obs, reward, done, info must be non-NULL; n_steps, ring >= 1");
-            return MG_EINVAL;
-        }
-        if (((uintptr_t)r->obs & 15) || (r->final_obs && ((uintptr_t)r->final_obs & 15))) {
-            mg_set_err("alignment: obs/final_obs must be 16-byte aligned");
-            return MG_EINVAL;
-        }
-        MgKIO q;
-        rollout_kio(r, n, 2, &q);
-        return mg_ss_split_launch(k, q, assets, state, r->scratch, (size_t)r->scratch_bytes, ss_tw(r->flags),
-                                  (r->flags & MG_FLAG_NO_PDL) != 0, stream);
-    }
     MG_SS_DISPATCH(launch_rollout, k, assets, state, r, n, 2, stream, 10);
 }

@@ -437,10 +437,7 @@ struct SSPolicyT {
                     wm->desc.valid = 0;
                 }
                 c.sync();
-                if (MG_UNLIKELY(tmp.action == 4)) {
-                    mg_ess_spawn_coin(c, k.clamp_off, s, g, rt, true);
-                    if (c.lane == 0) s.scene_last = ~0u;  // the coin moved (the two-kernel path relies on the version alone)
-                }
+                if (MG_UNLIKELY(tmp.action == 4)) mg_ess_spawn_coin(c, k.clamp_off, s, g, rt, true);
             }
             if (c.lane == 0) {
                 double reward;
@@ -555,10 +552,7 @@ struct SSPolicyT {
             if (tmp.post == 4) {
                 if (c.lane == 0) wm->desc.valid = 0;
                 mg_ess_spawn_coin(c, k.clamp_off, s, g, rt, true);
-                if (c.lane == 0) {
-                    s.scene_last = ~0u;
-                    pipe_finish(k, q, env, t, s, tmp, f);
-                }
+                if (c.lane == 0) pipe_finish(k, q, env, t, s, tmp, f);
                 c.sync();
             }
         }

@@ -109,7 +109,7 @@ class StepIO(C.Structure):
         ("actions", C.c_void_p), ("obs", C.c_void_p), ("final_obs", C.c_void_p), ("reward", C.c_void_p),
         ("done", C.c_void_p), ("info", C.c_void_p), ("ground_truth", C.c_void_p), ("reset_mask", C.c_void_p),
         ("flags", C.c_uint32), ("warps_per_cta", C.c_uint32), ("vector_obs", C.c_void_p), ("trace", C.c_void_p),
-        ("debug_obs", C.c_void_p), ("scratch", C.c_void_p), ("scratch_bytes", C.c_uint64),
+        ("debug_obs", C.c_void_p),
     ]
 
 
@@ -119,7 +119,7 @@ class RolloutIO(C.Structure):
         ("done", C.c_void_p), ("info", C.c_void_p), ("ground_truth", C.c_void_p),
         ("n_steps", C.c_int32), ("ring", C.c_int32), ("info_per_step", C.c_int32), ("flags", C.c_uint32),
         ("warps_per_cta", C.c_uint32), ("pad0", C.c_uint32), ("trace", C.c_void_p), ("vector_obs", C.c_void_p),
-        ("sched", C.c_void_p), ("scratch", C.c_void_p), ("scratch_bytes", C.c_uint64),
+        ("sched", C.c_void_p),
     ]
 
 
@@ -146,8 +146,6 @@ def lib():
     L.mg_device_info.argtypes = [C.POINTER(i32)] * 3 + [C.POINTER(C.c_size_t)]
     L.mg_seed_pcg64.argtypes = [vp, i32, vp]
     L.mg_obs_to_policy_bf16.argtypes = [vp, vp, i32, vp]
-    L.mg_ss_scratch_bytes.restype = C.c_size_t
-    L.mg_ss_scratch_bytes.argtypes = [i32, i32]
     L.mg_obs_delta_stage_bytes.restype = C.c_size_t
     L.mg_obs_delta_stage_bytes.argtypes = [i32]
     L.mg_obs_delta_encode.argtypes = [vp, vp, i32, vp, i32, vp]

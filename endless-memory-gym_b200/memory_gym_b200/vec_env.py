@@ -194,17 +194,7 @@ class MemoryGymVecEnv:
         # environment variable itself): MG_HELPERS=0 = no helper warps, MG_DISABLE_PDL = no programmatic dependent launch
         self._knobs = (L.MG_FLAG_NO_HELPERS if os.environ.get("MG_HELPERS") == "0" else 0) | \
                       (L.MG_FLAG_NO_PDL if os.environ.get("MG_DISABLE_PDL") else 0)
-        if os.environ.get("MG_SS_TW"):  # measurement knob: warps per raster team of the two-kernel SS path
-            self._knobs |= (int(os.environ["MG_SS_TW"]) & 7) << 8
         self._io.flags = (L.MG_FLAG_AUTORESET if self.auto_reset else 0) | self._stream_step | self._knobs
-        # Searing Spotlights: frame descriptions of the two-kernel path (state machine one lane per env, then the
-        # rasteriser) live in a scratch buffer; opt-in with MG_SS_SPLIT=1 (measured slower than the fused kernel: profiles/r02_ss.md)
-        self._scratch = None
-        self._scratch_steps = 0
-        self._ss_split = self.spec_.family == "ss" and bool(os.environ.get("MG_SS_SPLIT")) and self.device.type == "cuda"
-        if self._ss_split and self.render_mode != "debug_rgb_array":
-            self._ensure_scratch(1)
-            self._io.scratch, self._io.scratch_bytes = self._scratch.data_ptr(), self._scratch.numel()
         self._io.warps_per_cta = self.warps_per_cta
         self.reset_params = None
         self._params = None
@@ -213,17 +203,6 @@ class MemoryGymVecEnv:
         self._assets_ptr = self._state_ptr = 0
         self._seeded = False
         self.max_episode_steps = None
-
-    def _ensure_scratch(self, n_steps):
-        if self._scratch is None or n_steps > self._scratch_steps:
-            need = int(self._be.lib.mg_ss_scratch_bytes(self.num_envs, int(n_steps)))
-            if self._scratch is not None:
-                self._keep_alive = getattr(self, "_keep_alive", []) + [self._scratch]  # (a captured graph may still use it)
-            self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
-            self._scratch_steps = int(n_steps)
-            self._many_key = None  # (cached step_many io lists point at the old buffer)
-            self._io.scratch, self._io.scratch_bytes = self._scratch.data_ptr(), self._scratch.numel()
-        return self._scratch
 
     # ---- reference-compatible helpers ----------------------------------------------------------------
     def process_reset_params(self, reset_params):
@@ -390,9 +369,6 @@ class MemoryGymVecEnv:
         r.n_steps, r.ring, r.info_per_step = T, obs_out.shape[0], int(info_out is not None)
         r.flags, r.warps_per_cta = L.MG_FLAG_AUTORESET | self._stream_rollout | self._knobs, self.warps_per_cta
         r.trace = getattr(self, "_trace_ptr", None)
-        if self._ss_split:
-            sc = self._ensure_scratch(T)
-            r.scratch, r.scratch_bytes = sc.data_ptr(), sc.numel()
         self._be.rollout(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(), r,
                          self.num_envs, self._be.stream(self.device))
 
@@ -420,7 +396,6 @@ class MemoryGymVecEnv:
                 io.reset_mask = None
                 io.flags = self._io.flags
                 io.warps_per_cta = self._io.warps_per_cta
-                io.scratch, io.scratch_bytes = self._io.scratch, self._io.scratch_bytes
             self._many_key, self._many_ios = key, ios
         self._be.step_many(self.spec_.family, self._params, self._assets.data_ptr(), self.state.data_ptr(),
                            self._many_ios, T, self.num_envs, self._be.stream(self.device))

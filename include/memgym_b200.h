@@ -92,7 +92,6 @@ extern "C" {
 #define MG_FLAG_STREAM_OBS 2u /* write observations with an L2 evict-first policy (they are not re-read soon) */
 #define MG_FLAG_NO_HELPERS 4u /* measurement knob: Endless-MysteryPath launches without path-generation helper warps */
 #define MG_FLAG_NO_PDL 8u     /* measurement knob: launch without programmatic dependent launch */
-#define MG_FLAG_SS_TW_SHIFT 8 /* measurement knob: bits 8..10 = warps per raster team of the two-kernel SS path (0 = default) */
 
 typedef struct mg_choice_list {
     int32_t n;
@@ -236,9 +235,6 @@ typedef struct mg_step_io {
                             /* (_build_debug_surface + transform.scale, e.g. mortar_mayhem.py:105-136, 397-399) for the   */
                             /* frame written to obs, as if render() were called once after every reset() / step().        */
                             /* Built for MM, MM-Grid, Endless-MM, MysteryPath(-Grid), (Endless-)SearingSpotlights.        */
-    void* scratch;          /* nullable: device scratch of >= mg_ss_scratch_bytes(n, 1) bytes, 16-byte aligned. Searing   */
-    uint64_t scratch_bytes; /* Spotlights only: with it a step runs as two kernels (one lane per env for the state machine, */
-                            /* then the rasteriser); without it (or with debug_obs / trace) as the fused kernel. Same bytes. */
 } mg_step_io;
 
 /* A whole rollout in one launch: T = n_steps consecutive steps with given actions (the reference's bench.py
@@ -264,8 +260,6 @@ typedef struct mg_rollout_io {
                             /* work counter for env -> warp scheduling across SMs (SMs that stream faster take more   */
                             /* envs). NULL = every SM works through its own share. Results never depend on it. One    */
                             /* buffer per stream of launches.                                                          */
-    void* scratch;          /* nullable: as in mg_step_io, >= mg_ss_scratch_bytes(n, n_steps) bytes                          */
-    uint64_t scratch_bytes;
 } mg_rollout_io;
 
 /* ---- assets & seeding (host side) -------------------------------------------------------------- */
@@ -342,9 +336,6 @@ int mg_ep_step_many(const mg_ep_params* p, const void* assets, void* state, cons
 
 int mg_ep_rollout(const mg_ep_params* p, const void* assets, void* state, const mg_rollout_io* r, int n,
                   void* stream);
-
-/* Scratch bytes of the two-kernel Searing Spotlights path for n envs and n_steps steps per call (frame descriptions). */
-size_t mg_ss_scratch_bytes(int n, int n_steps);
 
 /* Option validation without a device: 0 if the reset/step kernels accept `p`, else MG_EINVAL with
  * mg_last_error() naming the offending field. */

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     text = open(os.path.join(ROOT, "include", "memgym_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     names = sorted(set(re.findall(r"\b(mg_[a-z0-9_]+)\s*\(", text)))
-    assert len(names) == 34
+    assert len(names) == 33
     lib = L.lib()
     for n in names:
         assert hasattr(lib, n), n
@@ -37,7 +37,7 @@ def test_struct_sizes_match_header():
     # sizes the C side asserts (mg_common.h static_asserts) and ctypes mirrors
     assert C.sizeof(L.ChoiceList) == 4 + 4 * L.MG_MAX_CHOICES
     assert C.sizeof(L.MMParams) == 24 + 5 * 68 + 4 + 5 * 8  # 4 bytes padding before the doubles
-    assert C.sizeof(L.StepIO) == 8 * 8 + 8 + 8 + 8 + 8 + 16  # ... flags + warps_per_cta, vector_obs, trace, debug_obs, scratch
+    assert C.sizeof(L.StepIO) == 8 * 8 + 8 + 8 + 8 + 8  # ... flags + warps_per_cta, vector_obs, trace, debug_obs
 
 
 def test_seed_sequence_matches_numpy():
