@@ -25,5 +25,18 @@ for env_id in ids:
     dn = torch.zeros((T, n), dtype=torch.bool, device=dev)
     env.rollout(acts, ring, rew, dn)
     env.policy_obs()
+    # round 2: zero-copy host actions / results, the delta transport (HostPipe), the ground-truth render
+    pipe = env.host_pipe(threads=4, depth=2)
+    a_host = acts.cpu().pin_memory()
+    for t in range(6):
+        pipe.submit(a_host[t])
+        if t:
+            pipe.collect()
+    pipe.collect()
+    if env_id not in ("MortarMayhemB-v0", "Endless-MysteryPath-v0"):
+        dbg = mg.make(env_id, num_envs=40, device=dev, render_mode="debug_rgb_array")
+        dbg.reset(seed=0, options=opts)
+        for t in range(12):
+            dbg.step(acts[t][:40].contiguous())
     torch.cuda.synchronize()
     print("ran", env_id, "dones", int(dn.sum()), flush=True)
