@@ -6,5 +6,5 @@ timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 tail -1 gpurun_out/r02m_d2h_n$N.json
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02m_bench_n$N.json 2> gpurun_out/r02m_bench_n$N.err
 tail -c 300 gpurun_out/r02m_bench_n$N.json; tail -3 gpurun_out/r02m_bench_n$N.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 20 --warmup 5 --no-configs > gpurun_out/r02m_bench_n2.json 2> gpurun_out/r02m_bench_n2.err
+if [ "$N" != "2" ]; then timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 20 --warmup 5 --no-configs > gpurun_out/r02m_bench_n2.json 2> gpurun_out/r02m_bench_n2.err; fi
 nproc > gpurun_out/r02m_host.txt; nvidia-smi topo -m >> gpurun_out/r02m_host.txt 2>&1
