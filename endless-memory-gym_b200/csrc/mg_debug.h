@@ -15,6 +15,7 @@
 #include "mg_frame.h"
 #include "mg_mm_logic.h"
 #include "mg_mp_logic.h"
+#include "mg_ep_logic.h"
 #include "mg_ss_logic.h"
 
 #define MG_DEBUG_ROW_WORDS (MG_DEBUG_DIM * 3 / 4)  // 252 32-bit words per output row
@@ -98,6 +99,42 @@ MG_HD_NOINLINE void mg_mp_debug(Ctx c, uint8_t* out, const MgAssetView& a, const
     if (d.f.cross) {
         c.sync();
         mg_dbg_sprite(c, out, a, MG_SPR_CROSS, d.f.cross_x, d.f.cross_y);
+    }
+}
+
+// ---- Endless Mystery Path: background, the WHOLE path generated so far (white, alpha 200), agent, cross, stamina bar ----
+// EndlessMysteryPath.gen_surface (pygame_assets.py:544-557) is colour-keyed and blended with alpha 200 at (-camera_x, 0).
+template <class Ctx>
+MG_HD_NOINLINE void mg_ep_debug(Ctx c, uint8_t* out, const MgAssetView& a, const MgEPK& k, const MgEPFrame& f,
+                                const MgEPState& s) {
+    const int x0 = (int)(-s.camera_x);  // blit destination: floats are C-cast
+    for (int p = c.lane; p < MG_W * MG_W; p += c.nl) {
+        const int y = p / MG_W, x = p - MG_W * y;
+        uint32_t r = 0u, g = 0u, b = 0u;
+        if (f.bg_off > -1000) {  // icy tiles with a 1-px frame (draw_column_tile_surface), columns starting at bg_off
+            const unsigned u = (unsigned)(x - f.bg_off) % 12u, v = (unsigned)y % 12u;
+            const bool edge = u == 0u || u == 11u || v == 0u || v == 11u;
+            r = edge ? 210u : 125u, g = edge ? 210u : 177u, b = edge ? 210u : 250u;
+        }
+        const int sxp = x - x0;
+        if (sxp >= 0 && mg_ep_on_path(s, sxp / 12, y / 12)) {  // d + trunc((255 - d) * 200 / 255)
+            r += (255u - r) * 200u / 255u;
+            g += (255u - g) * 200u / 255u;
+            b += (255u - b) * 200u / 255u;
+        }
+        mg_dbg_put(out, x, y, r | (g << 8) | (b << 16));
+    }
+    c.sync();
+    mg_dbg_sprite(c, out, a, MG_SPR_AGENT0 + f.srot, f.sx, f.sy);
+    if (f.cross) {
+        c.sync();
+        mg_dbg_sprite(c, out, a, MG_SPR_CROSS, f.cross_x, f.cross_y);
+    }
+    c.sync();
+    const int bar_h = mg_ep_bar_height(s.stamina, k.p.stamina_level, false);  // always drawn here (:181)
+    for (int i = c.lane; i < 4 * MG_W; i += c.nl) {
+        const int x = MG_W - 4 + i / MG_W, y = i % MG_W;
+        mg_dbg_put(out, x, y, y < bar_h ? 0x000000FFu : 0x0000FF00u);
     }
 }
 

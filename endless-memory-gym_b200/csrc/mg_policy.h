@@ -348,9 +348,11 @@ struct EPPolicy {
     static MG_HD void restore(Ctx& c, uint8_t* buf, const MgAssetView& a, const K&, const Frame& f, const MgScratch&) {
         mg_ep_restore(c, buf, a, f);
     }
-    // (Endless-MysteryPath's debug render is not built: the host API rejects render_mode="debug_rgb_array" for it)
     template <class Ctx>
-    static MG_HD void emit_debug(Ctx&, uint8_t*, const MgAssetView&, const K&, const Frame&, const State&, const MgScratch&) {}
+    static MG_HD void emit_debug(Ctx& c, uint8_t* out, const MgAssetView& a, const K& k, const Frame& f, const State& s,
+                                 const MgScratch&) {
+        mg_ep_debug(c, out, a, k, f, s);
+    }
 };
 
 template <int TW, bool kEndless>

@@ -112,9 +112,8 @@ class MemoryGymVecEnv:
             raise ValueError("num_envs must be >= 1")
         if render_mode not in (None, "rgb_array", "debug_rgb_array"):
             raise ValueError(f"render_mode {render_mode!r}: the batched engine renders 'rgb_array' and 'debug_rgb_array'")
-        if render_mode == "debug_rgb_array" and env_id in ("MortarMayhemB-v0", "MortarMayhemB-Grid-v0",
-                                                             "Endless-MysteryPath-v0"):
-            # the reference's B variants have no _build_debug_surface at all; Endless-MysteryPath's is not built
+        if render_mode == "debug_rgb_array" and env_id in ("MortarMayhemB-v0", "MortarMayhemB-Grid-v0"):
+            # the reference's B variants have no _build_debug_surface at all
             raise L.MemGymError(f"render_mode='debug_rgb_array' is not available for {env_id}")
         self.render_mode = render_mode
         self.device = torch.device(device)
@@ -183,6 +182,7 @@ class MemoryGymVecEnv:
         if self.render_mode == "debug_rgb_array":
             self.debug = torch.zeros((n, L.MG_DEBUG_DIM, L.MG_DEBUG_DIM, 3), dtype=torch.uint8, device=dev)
             self._io.debug_obs = self.debug.data_ptr()
+
         # rollouts: a global work counter the kernels keep at zero between launches (dynamic env -> warp scheduling
         # across SMs). MG_LOCAL_SCHED=1 switches it off (measurement knob): every SM works through its own share.
         self._sched = None if os.environ.get("MG_LOCAL_SCHED") else torch.zeros(2, dtype=torch.int32, device=dev)
@@ -194,6 +194,10 @@ class MemoryGymVecEnv:
         # environment variable itself): MG_HELPERS=0 = no helper warps, MG_DISABLE_PDL = no programmatic dependent launch
         self._knobs = (L.MG_FLAG_NO_HELPERS if os.environ.get("MG_HELPERS") == "0" else 0) | \
                       (L.MG_FLAG_NO_PDL if os.environ.get("MG_DISABLE_PDL") else 0)
+        if self.render_mode == "debug_rgb_array":
+            # (Endless-MysteryPath: the render shows the whole path, so an auto-reset generates it inline instead of
+            # handing it to helper warps that finish after the frame)
+            self._knobs |= L.MG_FLAG_NO_HELPERS
         self._io.flags = (L.MG_FLAG_AUTORESET if self.auto_reset else 0) | self._stream_step | self._knobs
         self._io.warps_per_cta = self.warps_per_cta
         self.reset_params = None

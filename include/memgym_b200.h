@@ -234,7 +234,8 @@ typedef struct mg_step_io {
     uint8_t* debug_obs;     /* nullable: [n][336][336][3] ([y][x][c]): render_mode="debug_rgb_array" of the reference     */
                             /* (_build_debug_surface + transform.scale, e.g. mortar_mayhem.py:105-136, 397-399) for the   */
                             /* frame written to obs, as if render() were called once after every reset() / step().        */
-                            /* Built for MM, MM-Grid, Endless-MM, MysteryPath(-Grid), (Endless-)SearingSpotlights.        */
+                            /* Every env type whose reference class has one (the MortarMayhemB variants do not); Endless-   */
+                            /* MysteryPath: launch with MG_FLAG_NO_HELPERS (the render needs the finished path).            */
 } mg_step_io;
 
 /* A whole rollout in one launch: T = n_steps consecutive steps with given actions (the reference's bench.py

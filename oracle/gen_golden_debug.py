@@ -41,6 +41,10 @@ CASES = {
                                            "spot_min_speed": 0.008, "spot_max_speed": 0.02, "show_last_action": False,
                                            "num_coins": [2]}, 3, 240),
     "ess": ("Endless-SearingSpotlights-v0", {"steps_per_coin": 80}, 4, 420),
+    "emp": ("Endless-MysteryPath-v0", None, 4, 420),
+    "emp_opts": ("Endless-MysteryPath-v0", {"max_steps": 150, "show_background": True, "show_stamina": True,
+                                             "camera_offset_scale": 2.3, "stamina_level": 12, "agent_speed": 5.0,
+                                             "visual_feedback": False}, 3, 300),
     "ess_nocoin": ("Endless-SearingSpotlights-v0", {"coin_enabled": False, "max_steps": 60, "initial_spawns": 6,
                                                      "agent_health": 3, "black_background": True}, 3, 160),
 }

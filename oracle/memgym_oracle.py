@@ -1682,6 +1682,45 @@ class EndlessMysteryPathOracle(_OracleEnv):
         self.bar_height = int(SCREEN * (1 - (min(self.stamina, self.max_visible_stamina) / self.max_visible_stamina)))
         return self._render(), reward, done, False, info
 
+    def _debug_surface(self):
+        """_build_debug_surface (endless_mystery_path.py:162-182): scrolling background (if shown), the WHOLE path
+        generated so far (EndlessMysteryPath.gen_surface, pygame_assets.py:544-557: white tiles on a colour-keyed surface
+        with alpha 200) at -camera_x, the agent, the fall-off cross and — always — the stamina bar."""
+        T = self.TILE
+        dst = R.Surface(SCREEN, SCREEN)
+        self._draw_background(dst)
+        n = len(self.segments)
+        path = R.Surface((self.GRID * n + n) * T, self.GRID * T)
+        path.colorkey = 0
+        path.alpha = 200
+        for nodes in self.segments:
+            for x, y in nodes:
+                R.fill_rect(path, R.map_rgb((255, 255, 255)), x * T, y * T, T, T)
+        R.blit(path, dst, (-self.camera_x, 0))
+        sp = self.sprites[self.rotation // 45]
+        R.blit(sp, dst, (self.agent_draw_x, self.cy - (sp.h >> 1)))
+        if self.cross_alpha == 255:
+            R.blit(assets.fall_off_cross(SCALE), dst, (self.cross_x, self.cross_y))
+        bar = R.Surface(int(16 * SCALE), SCREEN)
+        R.fill(bar, (0, 255, 0))
+        R.rect(bar, (255, 0, 0), (0, 0, 16 * SCALE, self.bar_height))
+        R.blit(bar, dst, (SCREEN - 16 * SCALE, 0))
+        return dst.px
+
+    def _draw_background(self, dst):
+        p = self.p
+        T = self.TILE
+        if p["show_background"]:
+            col = R.Surface(T, T * self.GRID)  # draw_column_tile_surface (pygame_assets.py:801-818)
+            for i in range(self.GRID):
+                R.fill_rect(col, R.map_rgb((125, 177, 250)), 0, i * T, T, T)
+                tile = R.Surface(T, T)
+                R.fill(tile, (125, 177, 250))
+                R.rect(tile, (210, 210, 210), (0, 0, T, T), 1)
+                R.blit(tile, col, (0, i * T))
+            for i in range(math.ceil(SCREEN / T) + 2):
+                R.blit(col, dst, (i * T + self.bg_scroll - T, 0))
+
     # ---- _draw_surfaces / _draw_past_path (:111-160) ---------------------------------------------------
     def _render(self):
         p = self.p

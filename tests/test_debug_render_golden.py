@@ -12,7 +12,7 @@ from oracle import memgym_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 DBG_CASES = ["mm", "mm_opts", "mmgrid", "emm", "mp", "mp_opts", "mpgrid", "ss", "ss_opts", "ss_black", "ess",
-             "ess_nocoin"]
+             "ess_nocoin", "emp", "emp_opts"]
 
 
 def load_dbg(name):
@@ -125,7 +125,7 @@ def test_debug_render_mode_surface():
     assert "debug_rgb_array" in mg.MemoryGymVecEnv.metadata["render_modes"]
     import hostsim_util
     be = hostsim_util.HostSimBackend()
-    for env_id in ("MortarMayhemB-v0", "Endless-MysteryPath-v0"):
+    for env_id in ("MortarMayhemB-v0", "MortarMayhemB-Grid-v0"):
         with pytest.raises(mg.MemGymError):
             mg.MemoryGymVecEnv(env_id, 2, device="cpu", render_mode="debug_rgb_array", _backend=be)
     with pytest.raises(ValueError):
