@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -78,7 +79,18 @@ static void work(Job& j) {
     }
 }
 
-// A fixed pool of workers parked on a condition variable between jobs; the calling thread works too.
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+}
+
+// A fixed pool of workers; the calling thread works too. A host-pipe loop hands over a job every ~150 us, so a worker
+// SPINS for the next job for a short while (kSpinNs) before it parks on a condition variable: a wake-up through the
+// kernel costs 30-50 us, a quarter of the job. Every worker checks in for every job, so none can touch a job after
+// run() has returned.
 class Pool {
    public:
     static Pool& get() {
@@ -90,62 +102,68 @@ class Pool {
         if (threads < 1) threads = 1;
         if (threads > 256) threads = 256;
         grow(threads - 1);
-        {
+        job_ = &j;
+        want_ = threads - 1;
+        pending_.store((int)workers_.size(), std::memory_order_relaxed);
+        epoch_.fetch_add(1);  // (sequentially consistent with parked_: either this thread sees the parked worker or the
+        if (parked_.load() > 0) {  //  worker sees the new epoch before it sleeps)
             std::lock_guard<std::mutex> g(mu_);
-            job_ = &j;
-            want_ = threads - 1;
-            running_ = threads - 1;
-            ++epoch_;
+            cv_.notify_all();
         }
-        cv_.notify_all();
         work(j);
-        std::unique_lock<std::mutex> g(mu_);
-        done_cv_.wait(g, [&] { return running_ == 0; });
+        while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();
         job_ = nullptr;
     }
 
    private:
+    static constexpr long kSpinNs = 400 * 1000;
     Pool() = default;
     ~Pool() {
+        stop_.store(true, std::memory_order_release);
         {
             std::lock_guard<std::mutex> g(mu_);
-            stop_ = true;
-            ++epoch_;
+            cv_.notify_all();
         }
-        cv_.notify_all();
         for (auto& t : workers_) t.join();
     }
     void grow(int n) {
         while ((int)workers_.size() < n) {
             const int id = (int)workers_.size();
-            workers_.emplace_back([this, id] { loop(id); });
+            const uint64_t start = epoch_.load(std::memory_order_relaxed);  // (a new worker joins from the NEXT job on)
+            workers_.emplace_back([this, id, start] { loop(id, start); });
         }
     }
-    void loop(int id) {
-        uint64_t seen = 0;
+    void loop(int id, uint64_t seen) {
         for (;;) {
-            Job* j;
-            {
+            uint64_t e;
+            auto t0 = std::chrono::steady_clock::now();
+            int spins = 0;
+            while ((e = epoch_.load(std::memory_order_acquire)) == seen) {
+                if (stop_.load(std::memory_order_acquire)) return;
+                cpu_relax();
+                if (++spins < 256) continue;
+                spins = 0;
+                if (std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count() < kSpinNs)
+                    continue;
                 std::unique_lock<std::mutex> g(mu_);
-                cv_.wait(g, [&] { return stop_ || (epoch_ != seen && id < want_); });
-                if (stop_) return;
-                seen = epoch_;
-                j = job_;
+                parked_.fetch_add(1);
+                cv_.wait_for(g, std::chrono::milliseconds(50), [&] { return stop_.load() || epoch_.load() != seen; });
+                parked_.fetch_sub(1, std::memory_order_release);
+                t0 = std::chrono::steady_clock::now();
             }
-            work(*j);
-            {
-                std::lock_guard<std::mutex> g(mu_);
-                if (--running_ == 0) done_cv_.notify_one();
-            }
+            seen = e;
+            if (id < want_) work(*job_);
+            pending_.fetch_sub(1, std::memory_order_release);
         }
     }
     std::mutex mu_, run_mu_;
-    std::condition_variable cv_, done_cv_;
+    std::condition_variable cv_;
     std::vector<std::thread> workers_;
     Job* job_ = nullptr;
-    uint64_t epoch_ = 0;
-    int want_ = 0, running_ = 0;
-    bool stop_ = false;
+    int want_ = 0;
+    std::atomic<uint64_t> epoch_{0};
+    std::atomic<int> pending_{0}, parked_{0};
+    std::atomic<bool> stop_{false};
 };
 }  // namespace
 

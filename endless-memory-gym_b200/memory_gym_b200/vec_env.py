@@ -170,6 +170,10 @@ class MemoryGymVecEnv:
             self._info_views["final_ground_truth"] = self.info[:, L.MG_INFO_GT0:L.MG_INFO_GT0 + self.spec_.gt_dim]
         self._step_fn = None
         self._results_views = {}
+        self._step_c = self._be.fn(self.spec_.family, "step") if hasattr(self._be, "fn") else None
+        self._io_ref = C.byref(self._io)
+        self._obs_ptr, self._reward_ptr, self._done_ptr = self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr()
+        self._params_ref = None
         self._io.final_obs = self.final_obs.data_ptr() if final_obs else None
         self._io.reward = self.reward.data_ptr()
         self._io.done = self.done.data_ptr()
@@ -228,6 +232,7 @@ class MemoryGymVecEnv:
             if self.device.type == "cuda":
                 torch.cuda.synchronize(self.device)  # the kernels' prologue reads the blob before stream order applies
             self._params, self._params_key = params, key
+            self._params_ref = C.byref(params)
         self.reset_params = p
         self.max_episode_steps = self._max_episode_steps(p)
 
@@ -333,6 +338,15 @@ class MemoryGymVecEnv:
             info["_episode"] = done
             return self._wrap_obs(obs), reward, done, self.truncated, info
         return self._wrap_obs(obs), self.reward, self._done_bool, self.truncated, dict(self._info_views)
+
+    def _launch_step_ptrs(self, actions_ptr, reward_ptr, done_ptr, stream):
+        """One step launch from raw pointers (validated by the caller): the lean path behind ``HostPipe.submit``."""
+        io = self._io
+        io.actions, io.obs, io.reward, io.done = actions_ptr, self._obs_ptr, reward_ptr, done_ptr
+        rc = self._step_c(self._params_ref, self._assets_ptr, self._state_ptr, self._io_ref, self.num_envs, stream)
+        io.reward, io.done = self._reward_ptr, self._done_ptr
+        if rc:
+            L.check(rc, f"mg_{self.spec_.family}_step")
 
     def _check_rollout_buffers(self, actions, obs_out, reward_out, done_out, info_out):
         if self._params is None:
@@ -533,24 +547,35 @@ class HostPipe:
         self._act = [torch.zeros_like(env._actions_dev, device="cpu").pin_memory() for _ in range(self.depth)]
         self._ev = [torch.cuda.Event() for _ in range(self.depth)]
         self._views = [(r[:8 * n].view(torch.float64), r[8 * n:].view(torch.bool)) for r in self._res]
+        self._truncated = torch.zeros(n, dtype=torch.bool)
         self._head = self._tail = 0
         self._bytes = C.c_uint64(0)
+        self._bytes_ref = C.byref(self._bytes)
+        self._res_ptrs = [(r.data_ptr(), r.data_ptr() + 8 * n) for r in self._res]
+        self._stage_ptrs = [t.data_ptr() for t in self._stage]
+        self._obs_dev_ptr, self._prev_ptr, self._obs_host_ptr = env.obs.data_ptr(), self._prev.data_ptr(), self.obs.data_ptr()
+        self._pinned_ok = {}   # data_ptr -> numel of action tensors already validated (pinned, int64, contiguous)
+        self._n_act = env._actions_dev.numel()
         self.last_d2h_bytes = 0   # bytes that crossed the link for the step collected last (payload + headers + results)
         self.total_d2h_bytes = 0
         self.resync()
 
-    def _encode(self, slot, full):
+    def _encode(self, slot, full, stream=None):
         env = self.env
-        L.check(self._lib.mg_obs_delta_encode(env.obs.data_ptr(), self._prev.data_ptr(), env.num_envs,
-                                              self._stage[slot].data_ptr(), int(full), env._be.stream(env.device)),
-                "mg_obs_delta_encode")
-        self._ev[slot].record(torch.cuda.current_stream(env.device))
+        cur = torch.cuda.current_stream(env.device)
+        rc = self._lib.mg_obs_delta_encode(self._obs_dev_ptr, self._prev_ptr, env.num_envs, self._stage_ptrs[slot], int(full),
+                                           cur.cuda_stream if stream is None else stream)
+        if rc:
+            L.check(rc, "mg_obs_delta_encode")
+        self._ev[slot].record(cur)
 
     def _decode(self, slot):
         self._ev[slot].synchronize()
-        L.check(self._lib.mg_obs_delta_decode(self._stage[slot].data_ptr(), self.obs.data_ptr(), self.env.num_envs,
-                                              self.threads, C.byref(self._bytes)), "mg_obs_delta_decode")
-        self.last_d2h_bytes = int(self._bytes.value) + 9 * self.env.num_envs
+        rc = self._lib.mg_obs_delta_decode(self._stage_ptrs[slot], self._obs_host_ptr, self.env.num_envs, self.threads,
+                                           self._bytes_ref)
+        if rc:
+            L.check(rc, "mg_obs_delta_decode")
+        self.last_d2h_bytes = self._bytes.value + 9 * self.env.num_envs
         self.total_d2h_bytes += self.last_d2h_bytes
 
     def resync(self):
@@ -576,13 +601,26 @@ class HostPipe:
             raise L.MemGymError(f"more than depth={self.depth} steps in flight: collect() first")
         slot = self._head % self.depth
         a = actions
-        if not (isinstance(a, torch.Tensor) and a.device.type == "cpu" and a.dtype == torch.int64 and a.is_contiguous()
-                and a.is_pinned()):
-            self._act[slot].copy_(torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a)
-                                  .reshape(self._act[slot].shape))
-            a = self._act[slot]
-        self.env.step(a, results_out=self._res[slot])
-        self._encode(slot, False)
+        ptr = a.data_ptr() if isinstance(a, torch.Tensor) else 0
+        if self._pinned_ok.get(ptr) != self._n_act:
+            if isinstance(a, torch.Tensor) and a.device.type == "cpu" and a.dtype == torch.int64 and a.is_contiguous() \
+                    and a.numel() == self._n_act and a.is_pinned():
+                if len(self._pinned_ok) > 4096:
+                    self._pinned_ok.clear()
+                self._pinned_ok[ptr] = self._n_act   # (pinned memory comes from its own allocator: the address stays pinned)
+            else:
+                self._act[slot].copy_(torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a)
+                                      .reshape(self._act[slot].shape))
+                a = self._act[slot]
+                ptr = a.data_ptr()
+        env = self.env
+        if env._params is None:
+            raise L.MemGymError("submit() called before reset()")
+        stream = torch.cuda.current_stream(env.device).cuda_stream
+        rp, dp = self._res_ptrs[slot]
+        env._launch_step_ptrs(ptr, rp, dp, stream)
+        self._keep_actions = a  # (alive until the next submit: the kernel reads it in place)
+        self._encode(slot, False, stream)
         self._head += 1
 
     def collect(self):
@@ -594,7 +632,7 @@ class HostPipe:
         self._decode(slot)
         self._tail += 1
         reward, done = self._views[slot]
-        return self.obs, reward, done, torch.zeros_like(done), {"episode": self.env.info, "_episode": done}
+        return self.obs, reward, done, self._truncated, {"episode": self.env.info, "_episode": done}
 
     def step(self, actions):
         self.submit(actions)
