@@ -311,8 +311,38 @@ class Timed:
                   "frac": n * self.b_alg(1) * K * R_s / (ms_s * 1e-3) / 1e9 / peak[0],
                   "note": "one mg_*_step launch per step (policy-in-the-loop shape, programmatic dependent launch between "
                           "them), device-timed, max over ranks"}
+        long_run = self.long_launches(peak)
         return {"value": self.total * steps / (ms * 1e-3) / 1e6, "ms": ms, "ms_per_step": ms / steps, "per_rank_ms": per_rank,
-                "timed_launches": R * self.launches_per_block, "timed_steps": steps, "roofline": roof, "single_step": single}
+                "timed_launches": R * self.launches_per_block, "timed_steps": steps, "roofline": roof, "single_step": single,
+                "long_launches": long_run}
+
+    def long_launches(self, peak, steps_per_launch=128):
+        """The same rollout with `steps_per_launch` steps per launch (the shape round 1 reported): what the kernel sustains
+        when launch boundaries are rare (Searing Spotlights rebuilds its base buffers, Endless-MysteryPath loses its
+        speculative paths at every launch boundary)."""
+        torch = self.torch
+        if self.K >= steps_per_launch:
+            return None
+        K0, L0, lpb0 = self.K, self.L, self.launches_per_block
+        keep = (self.acts, self.ring, self.rew, self.done)
+        try:
+            self.K = self.L = steps_per_launch
+            self.launches_per_block = 1
+            g = torch.Generator(device=self.dev).manual_seed(4321 + self.rank)
+            self.acts = torch.randint(0, self.spec.action_nvec[0], (self.L,) + tuple(self.env._actions_dev.shape),
+                                      generator=g, device=self.dev)
+            self.ring = torch.empty((self.L, self.n, 84, 84, 3), dtype=torch.uint8, device=self.dev)
+            self.rew = torch.empty((self.L, self.n), dtype=torch.float64, device=self.dev)
+            self.done = torch.empty((self.L, self.n), dtype=torch.bool, device=self.dev)
+            ms, per_rank, R = self.measure(False)
+            steps = self.K * R
+            b = self.b_alg(self.L)
+            achieved = self.n * b * steps / (ms * 1e-3) / 1e9
+            return {"steps_per_launch": self.L, "timed_launches": R, "value": self.total * steps / (ms * 1e-3) / 1e6,
+                    "unit": "M env-steps/s", "frac": achieved / peak[0], "per_rank_ms": per_rank}
+        finally:
+            self.K, self.L, self.launches_per_block = K0, L0, lpb0
+            self.acts, self.ring, self.rew, self.done = keep
 
 
 def shard_check(mg, torch, dist, dev, rank, world, env_id="MortarMayhem-v0", n_chk=256, T=64, sample=32):
@@ -559,7 +589,7 @@ def main():
                                         "seeds 0..N-1, uniform random actions, auto-reset on",
                             "value": r["value"], "unit": "M env-steps/s", "ms_per_step": r["ms_per_step"],
                             "timed_launches": r["timed_launches"], "per_rank_ms": r["per_rank_ms"],
-                            "roofline": r["roofline"], "single_step": r["single_step"]})
+                            "roofline": r["roofline"], "single_step": r["single_step"], "long_launches": r["long_launches"]})
             del c
             torch.cuda.empty_cache()
 
@@ -620,6 +650,7 @@ def main():
                                                      "host memory and writes reward + done into pinned host memory (same "
                                                      "bytes over PCIe, no copy operation between two step launches)"}},
             "single_step": head["single_step"],
+            "long_launches": head["long_launches"],
             "gpu_launches": head["timed_launches"],
             "roofline": head["roofline"],
             "configs": configs,

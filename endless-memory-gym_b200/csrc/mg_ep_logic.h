@@ -422,7 +422,16 @@ MG_HD void mg_ep_helper_offload_loop(Ctx& c, uint8_t* hs_bytes, uint8_t* wextra0
                 g->dir = hs.dir;
                 if (ground_truth) mg_ep_ground_truth(hs, ground_truth + MG_GT_COLS * (size_t)job->env);
             } else {
-                g->live = 0;  // "No valid path found": the reference raises; here the env stays finished
+                // "No valid path found": the reference raises; here the env stays finished, in the same state the inline
+                // reset leaves behind (node (0, 0), no direction): nothing of the helper's scratch record is read
+                // uninitialised
+                g->live = 0;
+                hs.cur_x = 0;
+                hs.cur_y = 0;
+                hs.dir = 0;
+                g->cur_x = 0;
+                g->cur_y = 0;
+                g->dir = 0;
                 if (ground_truth) mg_ep_ground_truth(hs, ground_truth + MG_GT_COLS * (size_t)job->env);
             }
             g->pending = 0;
