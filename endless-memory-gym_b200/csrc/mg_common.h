@@ -195,6 +195,29 @@ struct MgEPState {
     MgEPSegment seg[MG_EP_MAXSEG];
 };
 
+// Behind every Endless-Mystery-Path record (MG_EP_STATE_BYTES = sizeof(MgEPState) + sizeof(MgEPSpecRec)): the path
+// segments of the NEXT episodes, generated ahead of their resets by the helper warps of the rollout kernels
+// (mg_ep_logic.h) — a ring of MG_EP_AHEAD episodes, each generated from the stream its predecessor ends with. The env's
+// team never copies this part with the record; both sides go through global memory.
+#define MG_EP_AHEAD 4
+struct MgEPSpecSlot {
+    MgRng before;        // the stream the reset must find for this episode to be adopted
+    MgRng after;         // the stream after the segments generated so far (all three: what the reset leaves behind)
+    MgEPSegment seg[3];
+};
+struct MgEPSpecRec {
+    uint32_t hword;     // chain << 12 | episodes produced (mod 256) << 4 | segments of the next one << 2 | MG_CHAIN_*;
+                        // advanced by the helper lane with CAS only, rewritten by the team when it starts a new chain
+    uint32_t tword;     // chain << 12 | episodes consumed (mod 256); written by the team only
+    uint32_t adopted;   // statistics: resets of this env that adopted their path from here (team)
+    uint32_t work_ns;   // statistics: duration of the helper lane's last turn for this env (device builds)
+    MgRng base;         // the stream the chain's first episode starts from (team)
+    uint8_t pad0[8];
+    MgEPSpecSlot slot[MG_EP_AHEAD];
+    uint8_t pad1[160];
+};
+static_assert(sizeof(MgEPSpecSlot) == 200 && sizeof(MgEPSpecRec) == 1024, "MgEPSpecRec must be 1024 bytes");
+
 #define MG_EP_MAXTILES 72
 struct MgEPFrame {
     int32_t sx, sy, srot;       // sprite top-left on screen, sprite index
@@ -293,7 +316,7 @@ static_assert(sizeof(MgRng) == 40, "MgRng layout");
 static_assert(sizeof(MgMMState) == 256, "MgMMState must be 256 bytes (MG_MM_STATE_BYTES)");
 static_assert(sizeof(MgMPState) == 128, "MgMPState must be 128 bytes (MG_MP_STATE_BYTES)");
 static_assert(sizeof(MgEPSegment) == 40, "MgEPSegment layout");
-static_assert(sizeof(MgEPState) == 2048, "MgEPState must be 2048 bytes (MG_EP_STATE_BYTES)");
+static_assert(sizeof(MgEPState) + sizeof(MgEPSpecRec) == MG_EP_STATE_BYTES, "MgEPState + MgEPSpecRec must be MG_EP_STATE_BYTES");
 static_assert(sizeof(MgSSSpot) == 24, "MgSSSpot layout");
 static_assert(sizeof(MgSSState) == 1152, "MgSSState must be 1152 bytes (MG_SS_STATE_BYTES)");
 static_assert(sizeof(MgAssetHeader) % 8 == 0, "MgAssetHeader alignment");

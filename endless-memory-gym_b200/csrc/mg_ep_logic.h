@@ -96,17 +96,30 @@ MG_HD bool mg_ep_prev(const MgEPState& s, int x, int y, int& px, int& py) {
 
 // ---- path generation ahead of time ("speculation") ---------------------------------------------------------
 // Only add_path_segment draws from the env's stream, so between two resets the stream stands still unless the agent
-// walks into a new segment. Rollout launches therefore run HELPER WARPS next to the env teams (mg_kernels.cu): after
-// a reset the team posts the stream it ended with, a helper generates the NEXT episode's three segments from it, and
-// the next reset adopts them if — and only if — the stream still is what the helper started from (bit-exact either
-// way; a stale or unfinished job is simply dropped). The hand-over lives in shared memory only.
-enum { MG_SPEC_EMPTY = 0, MG_SPEC_REQUESTED = 1, MG_SPEC_BUSY = 2, MG_SPEC_READY = 3 };
+// walks into a new segment. The three segments of the next episodes can therefore be generated ahead: episode 1 from
+// the stream a reset leaves behind, episode 2 from the stream episode 1's segments leave behind, ... A reset adopts
+// the oldest episode of this CHAIN if — and only if — the env's stream is what that episode was generated from
+// (bit-exact either way); otherwise it generates inline and starts a new chain from the stream it ends with.
+//
+// Rollout launches run HELPER WARPS next to the env teams (mg_kernels.cu) that extend the chains with ONE ENV PER
+// LANE (mg_mp_generate_lane): 32 paths per warp-instruction, where the cooperative generator of a reset keeps a
+// whole warp busy for ~60 us per episode. The chain lives in the MgEPSpecRec behind the record, in GLOBAL memory,
+// so it survives the launch; progress is published segment by segment.
+//   team    consumes: slot[consumed % MG_EP_AHEAD] when produced > consumed and slot.before == stream, consumed + 1;
+//           starts a new chain (base = stream, chain id + 1, counters 0) after an inline reset / a mid-episode segment
+//   helper  (each env has ONE helper lane per launch: no helper-helper races) produces into slot[produced %
+//           MG_EP_AHEAD] while produced - consumed < MG_EP_AHEAD; writes the data first, then advances hword by CAS:
+//           a chain the team has replaced meanwhile makes the CAS fail and the data is never looked at
+enum { MG_CHAIN_IDLE = 0, MG_CHAIN_ACTIVE = 1, MG_CHAIN_FAILED = 3 };
+MG_HD uint32_t mg_chain_id(uint32_t w) { return w >> 12; }
+MG_HD uint32_t mg_chain_count(uint32_t w) { return (w >> 4) & 255u; }   // hword: produced
+MG_HD uint32_t mg_chain_nseg(uint32_t w) { return (w >> 2) & 3u; }
+MG_HD uint32_t mg_chain_consumed(uint32_t t) { return t & 255u; }        // tword
+// single-step launches hand an auto-reset's path to a helper warp through shared memory (mg_ep_reset_offload)
+enum { MG_SPEC_EMPTY = 0, MG_SPEC_REQUESTED = 1, MG_SPEC_BUSY = 2 };
 struct MgEPSpec {
-    uint32_t state;   // MG_SPEC_*: EMPTY -> (team) REQUESTED -> (helper) BUSY -> READY -> (team) EMPTY
-    int32_t env;      // single-step launches: the env whose (already written back) record waits for its path
-    MgRng before;     // the stream the three segments were (are to be) generated from
-    MgRng after;      // ... and the stream after them
-    MgEPSegment seg[3];
+    uint32_t state;   // MG_SPEC_*: EMPTY -> (team) REQUESTED -> (helper) BUSY -> EMPTY
+    int32_t env;      // the env whose (already written back) record waits for its path
 };
 struct MgEPWarpMem {  // per-team scratch of the Endless Mystery Path kernels
     MgGenMem gen;
@@ -115,11 +128,19 @@ struct MgEPWarpMem {  // per-team scratch of the Endless Mystery Path kernels
     int16_t pad;
     int32_t cur_env;  // the env this team works on
     int32_t post_env; // >= 0: its record carries a pending path; post the job once the record is written back
+    uint8_t* state;   // the batch's records (rollouts: where the MgEPSpecRec of an env lives)
     MgEPSpec spec;
 };
-// what a helper warp works on: the head of an env record (stream, segment count, the first three segments)
+// what a helper warp of a single-step launch works on: the head of an env record (stream, segment count, the
+// first three segments)
 #define MG_EP_HELPER_BYTES 384
 static_assert(offsetof(MgEPState, seg) + 3 * sizeof(MgEPSegment) <= MG_EP_HELPER_BYTES, "helper scratch too small");
+// per-lane scratch of a rollout helper warp: uint16 info[49][32] + uint8 list[49][32] (mg_mp_generate_lane)
+#define MG_EP_LANE_WARP_BYTES (MG_MP_NODES * 32 * 3)
+
+MG_HD MgEPSpecRec* mg_ep_spec_of(uint8_t* state, int env) {
+    return reinterpret_cast<MgEPSpecRec*>(state + (size_t)env * MG_EP_STATE_BYTES + sizeof(MgEPState));
+}
 
 MG_HD uint32_t mg_vload_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 MG_HD void mg_vstore_u32(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
@@ -215,97 +236,168 @@ MG_HD int mg_ep_bar_height(int stamina, int max_visible, bool at_reset) {
     return (int)((double)MG_W * (1.0 - ((double)v / (double)max_visible)));
 }
 
-// Team side of the speculation: true if the three segments of this reset were adopted from a helper
-template <class Ctx>
-MG_HD bool mg_ep_spec_take(Ctx& c, MgEPState& s, MgEPSpec& sp) {
-    for (;;) {
-        const uint32_t st = c.shfl(mg_vload_u32(&sp.state), 0);  // lane 0's view, so the warp stays uniform
-        if (st == MG_SPEC_BUSY) {  // a helper is at it: it finishes within one generation, sooner than we would
-            c.nanosleep(256);
-            continue;
-        }
-        if (st == MG_SPEC_REQUESTED) {  // nobody picked it up: take it back (a helper may win the race)
-            uint32_t won = 0;
-            if (c.lane == 0) won = c.cas_u32(&sp.state, MG_SPEC_REQUESTED, MG_SPEC_EMPTY) == MG_SPEC_REQUESTED ? 1u : 0u;
-            if (c.shfl(won, 0)) return false;
-            continue;
-        }
-        if (st != MG_SPEC_READY) return false;
-        c.sync();         // lane 0's observation of READY is ordered before every lane's reads below
-        c.fence_block();  // the helper's results are visible after its READY
-        const bool match = sp.before.state_lo == s.rng.state_lo && sp.before.state_hi == s.rng.state_hi &&
-                           sp.before.inc_lo == s.rng.inc_lo && sp.before.inc_hi == s.rng.inc_hi &&
-                           sp.before.buf == s.rng.buf && sp.before.has_buf == s.rng.has_buf;
-        if (match) {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(sp.seg);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(s.seg);
-            for (int w = c.lane; w < (int)(3 * sizeof(MgEPSegment) / 4); w += c.nl) dst[w] = src[w];
-            if (c.lane == 0) {
-                s.rng = sp.after;
-                s.n_segments = 3;
-            }
-        }
-        c.sync();
-        if (c.lane == 0) mg_vstore_u32(&sp.state, MG_SPEC_EMPTY);
-        c.sync();
-        return match;
-    }
+MG_HD bool mg_ep_stream_eq(const volatile MgRng& a, const MgRng& b) {
+    return a.state_lo == b.state_lo && a.state_hi == b.state_hi && a.inc_lo == b.inc_lo && a.inc_hi == b.inc_hi &&
+           a.buf == b.buf && a.has_buf == b.has_buf;
+}
+MG_HD void mg_ep_stream_put(volatile MgRng& d, const MgRng& s) {
+    d.state_lo = s.state_lo, d.state_hi = s.state_hi, d.inc_lo = s.inc_lo, d.inc_hi = s.inc_hi;
+    d.buf = s.buf, d.has_buf = s.has_buf;
 }
 
-// Team side, after a reset: ask for the next episode's segments (the slot is EMPTY here, see mg_ep_spec_take)
+// Team side, lane 0: the slot the next reset may adopt, or nullptr (nothing produced yet / another chain)
+MG_HD MgEPSpecSlot* mg_ep_chain_head(MgEPSpecRec* g, uint32_t& tword) {
+    const uint32_t h = mg_vload_u32(&g->hword);
+    tword = mg_vload_u32(&g->tword);
+    if ((h & 3u) == MG_CHAIN_IDLE || mg_chain_id(h) != mg_chain_id(tword)) return nullptr;
+    if (((mg_chain_count(h) - mg_chain_consumed(tword)) & 255u) == 0u) return nullptr;
+    return &g->slot[mg_chain_consumed(tword) % MG_EP_AHEAD];
+}
+
+// Team side, at a reset: true if the three segments were adopted from the env's chain
 template <class Ctx>
-MG_HD void mg_ep_spec_request(Ctx& c, const MgEPState& s, MgEPSpec& sp) {
+MG_HD bool mg_ep_gspec_take(Ctx& c, MgEPState& s, MgEPWarpMem& wm) {
+    MgEPSpecRec* const g = mg_ep_spec_of(wm.state, (int)c.shfl((uint32_t)wm.cur_env, 0));
+    uint32_t idx = 0xFFu, tword = 0;
     if (c.lane == 0) {
-        sp.before = s.rng;
-        c.fence_block();
-        mg_vstore_u32(&sp.state, MG_SPEC_REQUESTED);
+        MgEPSpecSlot* sl = mg_ep_chain_head(g, tword);
+        if (sl) {
+            c.fence_device();  // the helper's data is visible after its count
+            if (mg_ep_stream_eq(sl->before, s.rng)) idx = (uint32_t)(sl - g->slot);
+        }
+    }
+    idx = c.shfl(idx, 0);
+    if (idx == 0xFFu) return false;
+    MgEPSpecSlot* const sl = &g->slot[idx];
+    const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>(sl->seg);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s.seg);
+    for (int w = c.lane; w < (int)(3 * sizeof(MgEPSegment) / 4); w += c.nl) dst[w] = src[w];
+    c.sync();  // every lane has read the slot before lane 0 hands it back to the helper
+    if (c.lane == 0) {
+        const volatile MgRng& a = sl->after;
+        s.rng.state_lo = a.state_lo, s.rng.state_hi = a.state_hi;
+        s.rng.buf = a.buf, s.rng.has_buf = a.has_buf;  // (same increment)
+        s.n_segments = 3;
+        g->adopted = g->adopted + 1u;
+        c.fence_device();
+        mg_vstore_u32(&g->tword, (tword & ~255u) | ((mg_chain_consumed(tword) + 1u) & 255u));
+    }
+    c.sync();
+    return true;
+}
+
+// Team side: start a new chain from the stream as it is now (what was generated ahead is stale or missing)
+template <class Ctx>
+MG_HD void mg_ep_gspec_post(Ctx& c, const MgEPState& s, MgEPWarpMem& wm) {
+    if (c.lane != 0) return;
+    MgEPSpecRec* const g = mg_ep_spec_of(wm.state, wm.cur_env);
+    const uint32_t chain = (mg_chain_id(mg_vload_u32(&g->tword)) + 1u) & 0xFFFFFu;
+    mg_ep_stream_put(g->base, s.rng);
+    mg_vstore_u32(&g->tword, chain << 12);
+    c.fence_device();
+    mg_vstore_u32(&g->hword, (chain << 12) | MG_CHAIN_ACTIVE);
+}
+
+// Team side, when it takes an env over: a record without a chain (first rollout after construction), or whose chain
+// head was generated for another stream (a reset launch re-seeded the env), gets a new one
+template <class Ctx>
+MG_HD void mg_ep_gspec_sync(Ctx& c, const MgEPState& s, MgEPWarpMem& wm) {
+    if (c.lane != 0 || !s.live) return;
+    MgEPSpecRec* const g = mg_ep_spec_of(wm.state, wm.cur_env);
+    uint32_t tword;
+    const MgEPSpecSlot* sl = mg_ep_chain_head(g, tword);
+    const bool idle = (mg_vload_u32(&g->hword) & 3u) == MG_CHAIN_IDLE;
+    if (idle || (sl && !mg_ep_stream_eq(sl->before, s.rng))) mg_ep_gspec_post(c, s, wm);
+}
+
+// Helper side, ONE LANE: does the chain of record g have room for another segment? (hword as read by the caller)
+MG_HD bool mg_ep_chain_wants(MgEPSpecRec* g, uint32_t h) {
+    if ((h & 3u) != MG_CHAIN_ACTIVE) return false;
+    const uint32_t t = mg_vload_u32(&g->tword);
+    if (mg_chain_id(t) != mg_chain_id(h)) return false;  // the team is about to replace the chain
+    return ((mg_chain_count(h) - mg_chain_consumed(t)) & 255u) < (uint32_t)MG_EP_AHEAD;
+}
+
+// Helper side, ONE LANE: generate up to max_new segments for the chain (hword = h) of record g. Progress is published
+// after every segment; it stops when the chain is full, fails, is replaced by the team, or the launch ends (m.stop).
+template <class Ctx>
+MG_HD void mg_ep_lane_work(Ctx& c, MgEPSpecRec* g, uint32_t h, const double* sqrt_d2, const MgLaneMem& m,
+                           int max_new = 1) {
+    while (max_new-- > 0 && mg_ep_chain_wants(g, h)) {
+        const uint32_t produced = mg_chain_count(h);
+        const int nseg = (int)mg_chain_nseg(h);
+        MgEPSpecSlot* const sl = &g->slot[produced % MG_EP_AHEAD];
+        // the stream to continue from: the slot's own progress, else what the previous episode (or the chain's base) ends with
+        const volatile MgRng& from =
+            nseg > 0 ? sl->after : (produced == 0 ? g->base : g->slot[(produced + MG_EP_AHEAD - 1u) % MG_EP_AHEAD].after);
+        MgRngR r;
+        r.lo = from.state_lo, r.hi = from.state_hi, r.ilo = from.inc_lo, r.ihi = from.inc_hi, r.buf = from.buf, r.has = from.has_buf;
+        if (nseg == 0) {
+            volatile MgRng& b = sl->before;
+            b.state_lo = r.lo, b.state_hi = r.hi, b.inc_lo = r.ilo, b.inc_hi = r.ihi, b.buf = r.buf, b.has_buf = r.has;
+        }
+        // EndlessMysteryPath.add_path_segment, as in mg_ep_add_segment_coop
+        const int sy = nseg == 0 ? mg_rr_integers(r, 0, MG_MP_CELLS)
+                                 : (int)((*reinterpret_cast<const volatile uint64_t*>(&sl->seg[nseg - 1].path) >> 60) & 7ull);
+        const int ey = mg_rr_integers(r, 0, MG_MP_CELLS);
+        uint64_t nx[2];
+        bool stopped;
+        const uint64_t mask = mg_mp_generate_lane(r, 0, sy, MG_MP_CELLS - 1, ey, sqrt_d2, m, nx, stopped);
+        if (stopped) return;  // (what is published stays valid: the next launch resumes from it)
+        uint32_t next;
+        if (!mask) {
+            // "No valid path found": the reset will find out by itself (the reference raises there)
+            next = (h & ~3u) | MG_CHAIN_FAILED;
+        } else {
+            volatile uint64_t* sg = reinterpret_cast<volatile uint64_t*>(&sl->seg[nseg]);
+            sg[0] = mask | ((uint64_t)sy << 56) | ((uint64_t)ey << 60);
+            sg[1] = 0;
+            sg[2] = 0;
+            sg[3] = nx[0];
+            sg[4] = nx[1];
+            volatile MgRng& a = sl->after;
+            a.state_lo = r.lo, a.state_hi = r.hi, a.inc_lo = r.ilo, a.inc_hi = r.ihi, a.buf = r.buf, a.has_buf = r.has;
+            c.fence_device();
+            next = nseg < 2 ? (h & ~(3u << 2)) | ((uint32_t)(nseg + 1) << 2)
+                            : (h & ~0xFFCu) | (((produced + 1u) & 255u) << 4);  // the episode is complete
+        }
+        if (c.cas_u32(&g->hword, h, next) != h) return;  // the team has started another chain meanwhile
+        if (!mask) return;
+        h = next;
     }
 }
 
-// Helper warp: serve the teams of this CTA until all of them have left. `hs` = this helper's MG_EP_HELPER_BYTES.
+// Helper warp of a rollout launch. Lane `first` of the launch's `step` helper lanes owns envs first, first + step, ...
+// (consecutive envs sit on the lanes of one warp: they are visited, and consume, at about the same time). ONE segment
+// per turn: lanes whose chain got room meanwhile join at the next segment boundary.
 template <class Ctx>
-MG_HD void mg_ep_helper_loop(Ctx& c, uint8_t* hs_bytes, uint8_t* wextra0, int wextra_stride, int nteams, int hidx,
-                             const uint32_t* teams_done, MgGenMem& m, const MgGenCta& tab) {
-    MgEPState& hs = *reinterpret_cast<MgEPState*>(hs_bytes);  // only its head is touched (n_segments <= 3)
-    int next = hidx % nteams;
+MG_HD void mg_ep_lane_helper_loop(Ctx& c, uint8_t* state, int n, int first, int step, const uint32_t* teams_done,
+                                  int nteams, const double* sqrt_d2, const MgLaneMem& m) {
+    const int count = first < n ? (n - first + step - 1) / step : 0;
+    int rot = 0;
     for (;;) {
-        if (c.shfl(mg_vload_u32(teams_done), 0) >= (uint32_t)nteams) return;
-        MgEPSpec* job = nullptr;
-        for (int i = 0; i < nteams && !job; ++i) {
-            const int t = (next + i) % nteams;
-            MgEPSpec& sp = reinterpret_cast<MgEPWarpMem*>(wextra0 + (size_t)t * wextra_stride)->spec;
-            if (c.shfl(mg_vload_u32(&sp.state), 0) != MG_SPEC_REQUESTED) continue;
-            uint32_t won = 0;
-            if (c.lane == 0) won = c.cas_u32(&sp.state, MG_SPEC_REQUESTED, MG_SPEC_BUSY) == MG_SPEC_REQUESTED ? 1u : 0u;
-            if (c.shfl(won, 0)) {
-                job = &sp;
-                next = (t + 1) % nteams;
+        if (mg_vload_u32(teams_done) >= (uint32_t)nteams) return;  // the launch is over: the chains wait
+        MgEPSpecRec* g = nullptr;
+        uint32_t h = 0;
+        for (int i = 0; i < count && !g; ++i) {
+            int j = rot + i;
+            if (j >= count) j -= count;
+            MgEPSpecRec* cand = mg_ep_spec_of(state, first + j * step);
+            h = mg_vload_u32(&cand->hword);
+            if (mg_ep_chain_wants(cand, h)) {
+                g = cand;
+                rot = j + 1 < count ? j + 1 : 0;
             }
         }
-        if (!job) {
-            c.nanosleep(512);
+        if (!c.reduce_or(g ? 1u : 0u)) {
+            c.nanosleep(2000);
             continue;
         }
-        c.sync();
-        c.fence_block();  // the team's `before` is visible after its REQUESTED
-        if (c.lane == 0) {
-            hs.rng = job->before;
-            hs.n_segments = 0;
-        }
-        c.sync();
-        bool ok = true;
-        for (int q = 0; q < 3 && ok; ++q) ok = mg_ep_add_segment_coop(c, hs, m, tab);
-        if (ok) {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(hs.seg);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(job->seg);
-            for (int w = c.lane; w < (int)(3 * sizeof(MgEPSegment) / 4); w += c.nl) dst[w] = src[w];
-            if (c.lane == 0) job->after = hs.rng;
-        }
-        c.sync();
-        if (c.lane == 0) {
-            c.fence_block();
-            // a failed generation ("No valid path found") is left to the env itself: the slot just empties
-            mg_vstore_u32(&job->state, ok ? MG_SPEC_READY : MG_SPEC_EMPTY);
+        if (g) {
+            c.fence_device();  // the team's writes are visible after its words
+            const uint64_t t0 = c.now_ns();
+            mg_ep_lane_work(c, g, h, sqrt_d2, m, 1);
+            g->work_ns = (uint32_t)(c.now_ns() - t0);
         }
     }
 }
@@ -392,7 +484,7 @@ MG_HD void mg_ep_helper_offload_loop(Ctx& c, uint8_t* hs_bytes, uint8_t* wextra0
         }
         c.sync();
         c.fence_device();
-        MgEPState* g = reinterpret_cast<MgEPState*>(state) + job->env;
+        MgEPState* g = reinterpret_cast<MgEPState*>(state + (size_t)job->env * MG_EP_STATE_BYTES);
         const volatile MgEPState* gv = g;
         const int sy = (int)gv->pending - 1;
         if (c.lane == 0) {
@@ -460,7 +552,8 @@ MG_HD void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, 
     c.sync();
     bool ok = true;
     const bool spec = wm.helpers > 0 && !wm.offload;
-    if (!(spec && mg_ep_spec_take(c, s, wm.spec)))
+    const bool adopted = spec && mg_ep_gspec_take(c, s, wm);
+    if (!adopted)
         for (int q = 0; q < 3 && ok; ++q) ok = mg_ep_add_segment_coop(c, s, m, tab);
     c.stamp(13);
     if (c.lane == 0) {
@@ -488,7 +581,7 @@ MG_HD void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, 
         if (gt) mg_ep_ground_truth(s, gt);
     }
     c.sync();
-    if (spec) mg_ep_spec_request(c, s, wm.spec);
+    if (spec && ok && !adopted) mg_ep_gspec_post(c, s, wm);  // (an adopted episode: its chain goes on)
     c.stamp(14);
 }
 

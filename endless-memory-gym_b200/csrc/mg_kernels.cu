@@ -158,6 +158,7 @@ struct MgWarpCtx {
     __device__ __forceinline__ void fence_block() { __threadfence_block(); }
     __device__ __forceinline__ void fence_device() { __threadfence(); }
     __device__ __forceinline__ void nanosleep(unsigned ns) { __nanosleep(ns); }
+    __device__ __forceinline__ uint64_t now_ns() { return mg_now(); }
     __device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
     // whole-frame template -> this warp's frame buffer, by TMA
     __device__ __forceinline__ void copy_frame(uint8_t* dst, const uint8_t* src) {
@@ -178,6 +179,20 @@ struct MgWarpCtx {
 #define MG_SS_LIT_EARLY 0
 #endif
 
+// distance between two env records: the record itself unless the policy keeps more behind it (P::kRecordBytes)
+template <class P, class = void>
+struct MgRecordBytes {
+    static constexpr int value = (int)sizeof(typename P::State);
+};
+template <class P>
+struct MgRecordBytes<P, decltype((void)P::kRecordBytes)> {
+    static constexpr int value = P::kRecordBytes;
+};
+template <class P>
+__host__ __device__ constexpr int mg_record_bytes() {
+    return MgRecordBytes<P>::value;
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------
 // A "team" = the threads that own one env at a time: one warp, or P::kTeamWarps warps on a named barrier for
 // env types whose per-frame work is instruction-bound (more warps per frame buffer hide more latency).
@@ -192,6 +207,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     typedef typename P::Frame Frame;
     constexpr int kTeam = 32 * P::kTeamWarps;          // threads per team
     constexpr int kStateBytes = (int)sizeof(State);
+    constexpr int kRecordBytes = mg_record_bytes<P>();  // distance between two records (>= kStateBytes)
     constexpr int kWords = kStateBytes / 8;             // 8-byte words per record
     constexpr int kPerLane = (kWords + kTeam - 1) / kTeam;  // words each thread moves
     constexpr int kFrames = P::kDirectStore ? 2 : 3;  // this step's (up to two) frames + the one being un-patched
@@ -249,7 +265,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     P::cta_init(cextra, threadIdx.x, blockDim.x);
     if (!is_helper) {
         P::warp_init(wextra, lane);
-        if constexpr (P::kHelperWarps > 0) P::set_helpers(wextra, lane, nhelp, !kRollout);
+        if constexpr (P::kHelperWarps > 0) P::set_helpers(wextra, lane, nhelp, !kRollout, state);
     }
     __syncthreads();
     if (staged) {
@@ -268,7 +284,8 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
             MgWarpCtx hctx{lane, kTeam, 0u, 0u, 0ull, nullptr, 0};
             uint8_t* const wextra0 = smem + (size_t)nteams * (P::kFrameBuf + kSlot);
             if constexpr (kRollout)
-                P::helper_loop(hctx, cextra, wextra0, nteams, team - nteams, &hdr->teams_done);
+                P::helper_loop(hctx, cextra, nteams, team - nteams, nhelp, (int)blockIdx.x, (int)gridDim.x, &hdr->teams_done,
+                               state, q.n);
             else
                 P::helper_loop_step(hctx, cextra, wextra0, nteams, team - nteams, &hdr->teams_done, state, q.io.ground_truth);
             return;
@@ -298,7 +315,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     uint64_t pre[kPerLane];
     int64_t act0 = 0, act1 = 0;
     {
-        const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)env * kStateBytes);
+        const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)env * kRecordBytes);
 #pragma unroll
         for (int w = 0; w < kPerLane; ++w)
             if (lane + kTeam * w < kWords) pre[w] = g[lane + kTeam * w];
@@ -388,7 +405,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
                 nxt = (int)*grab;
                 have_next = nxt < q.n;
                 if (have_next) {
-                    const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)nxt * kStateBytes);
+                    const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)nxt * kRecordBytes);
 #pragma unroll
                     for (int w = 0; w < kPerLane; ++w)
                         if (lane + kTeam * w < kWords) pre[w] = g[lane + kTeam * w];
@@ -421,7 +438,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
                 nxt = (int)*grab;
                 have_next = nxt < q.n;
                 if (have_next) {
-                    const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)nxt * kStateBytes);
+                    const uint64_t* g = reinterpret_cast<const uint64_t*>(state + (size_t)nxt * kRecordBytes);
 #pragma unroll
                     for (int w = 0; w < kPerLane; ++w)
                         if (lane + kTeam * w < kWords) pre[w] = g[lane + kTeam * w];
@@ -477,7 +494,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
             }
             ctx.sync();  // job / frame slots are reused by the next step
         }
-        uint64_t* gw = reinterpret_cast<uint64_t*>(state + (size_t)env * kStateBytes);
+        uint64_t* gw = reinterpret_cast<uint64_t*>(state + (size_t)env * kRecordBytes);
 #pragma unroll
         for (int j = 0; j < kPerLane; ++j)
             if (lane + kTeam * j < kWords) gw[lane + kTeam * j] = s64[lane + kTeam * j];
@@ -593,7 +610,8 @@ static int plan_launch(int dev, int n, int wpc_req, int default_wpc, bool no_hel
     int helpers = 0;
     if (P::kHelperWarps > 0 && !no_helpers) {
         helpers = P::kMaxThreads / (32 * P::kTeamWarps) - wpc;
-        if (helpers > P::kHelperWarps) helpers = P::kHelperWarps;
+        const int most = kRollout ? P::kRolloutHelpers : P::kHelperWarps;
+        if (helpers > most) helpers = most;
         if (helpers < 0) helpers = 0;
     }
     out->helpers = helpers;

@@ -263,6 +263,150 @@ MG_HD uint64_t mg_mp_generate_coop(Ctx& c, MgRngR& r, int sx, int sy, int ex, in
     return path;
 }
 
+// ---- one-lane-per-env path generator ---------------------------------------------------------------------
+// The same MysteryPath.__init__ for ONE thread: the helper warps of the Endless-MysteryPath rollouts run it with a
+// different env on every lane (32 paths per warp-instruction instead of one: the cooperative generator above spends
+// ~7000 warp-instructions per path, most of them waiting for the stream). The open list is the reference's list
+// itself, in insertion order: "open[0]" is list[0], "the first open node with f < f(open[0])" a scan from list[1].
+// Per-lane scratch: element i of a lane at base[i * stride] (the helper warps interleave the lanes of a warp in
+// shared memory; the host tests pass stride 1).
+struct MgLaneMem {
+    uint16_t* info;  // per cell: g cost << 6 | predecessor (63 = none); valid for cells that were ever open
+    uint8_t* list;   // open list: cells in insertion order
+    int stride;      // elements between two consecutive entries of one lane
+    const volatile uint32_t* stop;  // optional: give up as soon as *stop >= stop_at (the launch is ending)
+    uint32_t stop_at;
+};
+#define MG_LANE_NOPREV 63u
+// the cells within one step (8-neighbourhood) of a set of cells, the set included
+MG_HD uint64_t mg_mp_dilate8(uint64_t w) {
+    const uint64_t col0 = 0x0040810204081ull;  // j == 0 of every row i (bits 7 i)
+    const uint64_t full = (1ull << MG_MP_NODES) - 1ull;
+    uint64_t d = w | ((w << 1) & ~col0) | ((w >> 1) & ~(col0 << (MG_MP_CELLS - 1)));
+    d |= (d << MG_MP_CELLS) | (d >> MG_MP_CELLS);
+    return d & full;
+}
+// Returns the path mask (0: no path, or stopped early — `stopped` tells which); next2 as in mg_mp_generate_coop.
+MG_HD uint64_t mg_mp_generate_lane(MgRngR& r, int sx, int sy, int ex, int ey, const double* sqrt_d2, const MgLaneMem& m,
+                                   uint64_t* next2, bool& stopped) {
+    constexpr int n = MG_MP_CELLS;
+    stopped = false;
+    uint64_t wall = 0;
+    MG_NOUNROLL
+    for (int id = mg_mp_id(1, 1); id <= mg_mp_id(n - 3, n - 3); ++id) {
+        const int j = id % n;
+        if (j < 1 || j > n - 3) continue;
+        if (mg_rr_integers(r, 0, 100) < 33) wall |= 1ull << id;
+    }
+    const int start = mg_mp_id(sx, sy), end = mg_mp_id(ex, ey);
+    const uint64_t bad = (1ull << start) | (1ull << end) | mg_mp_nbr4(sx, sy) | mg_mp_nbr4(ex, ey) | mg_mp_dilate8(wall);
+    // the 24 ring cells in scan order: row 0, the two ends of rows 1..5, row 6
+    uint32_t taken = (uint32_t)(bad & 0x7Full) | ((uint32_t)((bad >> 42) & 0x7Full) << 17);
+    MG_UNROLL
+    for (int i = 1; i <= n - 2; ++i) {
+        taken |= (uint32_t)((bad >> (n * i)) & 1ull) << (7 + 2 * (i - 1));
+        taken |= (uint32_t)((bad >> (n * i + n - 1)) & 1ull) << (8 + 2 * (i - 1));
+    }
+    uint32_t elig = ~taken & 0xFFFFFFu;
+    int nring = mg_popc32(elig);
+    const int picks = mg_rr_integers(r, 0, 2) ? 8 : 4;
+    MG_NOUNROLL
+    for (int q = 0; q < picks && nring > 0; ++q) {
+        const int b = mg_nth_set_bit(elig, mg_rr_integers(r, 0, nring));
+        wall |= 1ull << mg_mp_ring_id(b);
+        elig &= ~(1u << b);
+        nring--;
+    }
+    const int S = m.stride;
+    uint64_t open = 1ull << start, closed = 0;
+    int nopen = 1;
+    m.list[0] = (uint8_t)start;
+    m.info[start * S] = (uint16_t)MG_LANE_NOPREV;  // g = 0
+    const auto f_of = [&](int cell, uint32_t g) {
+        const int dx = cell / n - ex, dy = cell % n - ey;
+        return (double)g + sqrt_d2[dx * dx + dy * dy];
+    };
+    int cur = start;
+    MG_NOUNROLL
+    for (;;) {
+        if (nopen == 0) return 0;
+        if (m.stop && *m.stop >= m.stop_at) {
+            stopped = true;
+            return 0;
+        }
+        const int head = m.list[0];
+        const double fh = f_of(head, (uint32_t)m.info[head * S] >> 6);
+        int pick = 0;
+        MG_NOUNROLL
+        for (int i = 1; i < nopen; ++i) {
+            const int c = m.list[i * S];
+            if (f_of(c, (uint32_t)m.info[c * S] >> 6) < fh) {
+                pick = i;
+                break;
+            }
+        }
+        cur = m.list[pick * S];
+        if (cur == end) break;
+        const uint32_t gc = (uint32_t)m.info[cur * S] >> 6;
+        nopen--;
+        MG_NOUNROLL
+        for (int i = pick; i < nopen; ++i) m.list[i * S] = m.list[(i + 1) * S];  // list.remove keeps the order
+        open &= ~(1ull << cur);
+        closed |= 1ull << cur;
+        const int ci = cur / n, cj = cur - n * ci;
+        // neighbours in Node.add_neighbors order (+x, -x, +y, -y), pygame_assets.py:465-472
+        MG_NOUNROLL
+        for (int d = 0; d < 4; ++d) {
+            int v;
+            if (d == 0) {
+                if (ci >= n - 1) continue;
+                v = cur + n;
+            } else if (d == 1) {
+                if (ci <= 0) continue;
+                v = cur - n;
+            } else if (d == 2) {
+                if (cj >= n - 1) continue;
+                v = cur + 1;
+            } else {
+                if (cj <= 0) continue;
+                v = cur - 1;
+            }
+            const uint64_t vbit = 1ull << v;
+            if ((closed | wall) & vbit) continue;
+            const uint32_t cost = gc + (uint32_t)mg_rr_integers(r, 1, 9);
+            if (open & vbit) {
+                // a cheaper way to an open node: only the predecessor changes (g_cost is not updated, :712)
+                const uint32_t old = m.info[v * S];
+                if (cost < (old >> 6)) m.info[v * S] = (uint16_t)((old & ~63u) | (uint32_t)cur);
+            } else {
+                m.info[v * S] = (uint16_t)((cost << 6) | (uint32_t)cur);
+                m.list[nopen * S] = (uint8_t)v;
+                nopen++;
+                open |= vbit;
+            }
+        }
+    }
+    uint64_t path = 0, n0 = 0, n1 = 0;
+    MG_NOUNROLL
+    for (int at = end;;) {
+        path |= 1ull << at;
+        const uint32_t a = (uint32_t)m.info[at * S] & 63u;
+        if (a == MG_LANE_NOPREV) break;
+        const int ax = (int)a / n, ay = (int)a % n, bx = at / n, by = at % n;  // a -> at on the path
+        const uint64_t code = bx == ax + 1 ? 0u : (by == ay - 1 ? 1u : (by == ay + 1 ? 2u : 3u));
+        if (a >> 5)
+            n1 |= code << (2 * (a & 31));
+        else
+            n0 |= code << (2 * (a & 31));
+        at = (int)a;
+    }
+    if (next2) {
+        next2[0] = n0;
+        next2[1] = n1;
+    }
+    return path;
+}
+
 MG_HD void mg_mp_draw(const MgMPK& k, const MgMPState& s, int cross, MgMPDraw& d) {
     d.f.sx = s.cx;
     d.f.sy = s.cy;

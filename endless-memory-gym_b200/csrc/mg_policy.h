@@ -154,7 +154,7 @@ MG_HD void mg_env_logic_coop(Ctx& c, const typename E::K& k, const MgKIO& q, con
 
 struct MMPolicy {
     static constexpr bool kPipelined = false;
-    static constexpr int kHelperWarps = 0;
+    static constexpr int kHelperWarps = 0, kRolloutHelpers = 0;
     static constexpr int kWarpExtra = 0, kCtaExtra = 0;
     static constexpr int kStageReserve = 8 * 1024;  // shared memory kept free for the staged asset prefix (7.4 KB by default)
     static constexpr int kTeamWarps = 1, kMaxThreads = 320;
@@ -201,7 +201,7 @@ struct MMPolicy {
 
 struct MPPolicy {
     static constexpr bool kPipelined = false;
-    static constexpr int kHelperWarps = 0;
+    static constexpr int kHelperWarps = 0, kRolloutHelpers = 0;
     static constexpr int kWarpExtra = (int)((sizeof(MgGenMem) + 127) / 128 * 128);
     static constexpr int kCtaExtra = (int)((sizeof(MgGenCta) + 127) / 128 * 128);
     static constexpr int kStageReserve = 8 * 1024;
@@ -256,11 +256,16 @@ struct MPPolicy {
 
 struct EPPolicy {
     static constexpr bool kPipelined = false;
-    static constexpr int kHelperWarps = 7;  // rollout launches: path generation ahead of time (mg_ep_logic.h)
+    static constexpr int kHelperWarps = 7;    // single-step launches: warps that finish the paths of auto-resets
+    static constexpr int kRolloutHelpers = 2;  // rollout launches: warps that generate paths ahead, one env per lane
+    static constexpr int kRecordBytes = MG_EP_STATE_BYTES;  // record + the MgEPSpecRec behind it
     static constexpr int kWarpExtra = (int)((sizeof(MgEPWarpMem) + 127) / 128 * 128);
     static constexpr int kGenCtaBytes = (int)((sizeof(MgGenCta) + 127) / 128 * 128);
-    static constexpr int kCtaExtra = kGenCtaBytes + kHelperWarps * MG_EP_HELPER_BYTES;
-    static constexpr int kStageReserve = 8 * 1024;
+    static constexpr int kHelperBytes = kHelperWarps * MG_EP_HELPER_BYTES > kRolloutHelpers * MG_EP_LANE_WARP_BYTES
+                                            ? kHelperWarps * MG_EP_HELPER_BYTES
+                                            : kRolloutHelpers * MG_EP_LANE_WARP_BYTES;
+    static constexpr int kCtaExtra = kGenCtaBytes + (kHelperBytes + 127) / 128 * 128;
+    static constexpr int kStageReserve = 5 * 1024;
     static constexpr int kTeamWarps = 1, kMaxThreads = 512;
     static constexpr int kFrameBuf = 21248;
     static constexpr bool kDirectStore = false;
@@ -274,14 +279,16 @@ struct EPPolicy {
             wm->offload = 0;
             wm->cur_env = -1;
             wm->post_env = -1;
+            wm->state = nullptr;
             wm->spec.state = MG_SPEC_EMPTY;
         }
     }
     // helper warps of this launch; `offload`: single-step launch (they finish auto-resets), else rollout (they work ahead)
-    static MG_HD void set_helpers(uint8_t* warp, int lane, int n, bool offload) {
+    static MG_HD void set_helpers(uint8_t* warp, int lane, int n, bool offload, uint8_t* state) {
         if (lane == 0) {
             reinterpret_cast<MgEPWarpMem*>(warp)->helpers = n;
             reinterpret_cast<MgEPWarpMem*>(warp)->offload = offload ? 1 : 0;
+            reinterpret_cast<MgEPWarpMem*>(warp)->state = state;
         }
     }
     template <class Ctx>
@@ -296,12 +303,19 @@ struct EPPolicy {
         mg_ep_helper_offload_loop(c, mine, wextra0, kWarpExtra, nteams, hidx, teams_done, m,
                                   *reinterpret_cast<const MgGenCta*>(cextra), state, ground_truth);
     }
+    // rollout helper warp `hidx` of `nhelp` in CTA `cta` of `nctas`: one env per lane
     template <class Ctx>
-    static MG_HD void helper_loop(Ctx& c, uint8_t* cextra, uint8_t* wextra0, int nteams, int hidx, const uint32_t* teams_done) {
-        // a helper's hand-over words + scratch: its own MG_EP_HELPER_BYTES block behind the square-root table
-        uint8_t* mine = cextra + kGenCtaBytes + (size_t)hidx * MG_EP_HELPER_BYTES;
-        MgGenMem m{0, 0};
-        mg_ep_helper_loop(c, mine, wextra0, kWarpExtra, nteams, hidx, teams_done, m, *reinterpret_cast<const MgGenCta*>(cextra));
+    static MG_HD void helper_loop(Ctx& c, uint8_t* cextra, int nteams, int hidx, int nhelp, int cta, int nctas,
+                                  const uint32_t* teams_done, uint8_t* state, int n) {
+        uint8_t* mine = cextra + kGenCtaBytes + (size_t)hidx * MG_EP_LANE_WARP_BYTES;
+        MgLaneMem m;
+        m.info = reinterpret_cast<uint16_t*>(mine) + c.lane;
+        m.list = mine + MG_MP_NODES * 32 * 2 + c.lane;
+        m.stride = 32;
+        m.stop = teams_done;
+        m.stop_at = (uint32_t)nteams;
+        mg_ep_lane_helper_loop(c, state, n, (cta * nhelp + hidx) * 32 + c.lane, nctas * nhelp * 32, teams_done, nteams,
+                               reinterpret_cast<const MgGenCta*>(cextra)->sqrt_d2, m);
     }
     typedef MgEPK K;
     typedef MgEPState State;
@@ -323,7 +337,12 @@ struct EPPolicy {
         const bool need = m.flag != 0;
         c.sync();  // every lane has read the flag before lane 0 reuses the word for "done"
         bool capped = false;
-        if (need) capped = !mg_ep_add_segment_coop(c, s, m, *reinterpret_cast<const MgGenCta*>(sc.cta));
+        if (need) {
+            capped = !mg_ep_add_segment_coop(c, s, m, *reinterpret_cast<const MgGenCta*>(sc.cta));
+            // the stream has moved: what was generated ahead for the next reset is stale, ask again
+            MgEPWarpMem& wm = *reinterpret_cast<MgEPWarpMem*>(sc.warp);
+            if (wm.helpers > 0 && !wm.offload) mg_ep_gspec_post(c, s, wm);
+        }
         if (c.lane == 0) {
             double reward;
             const bool done = mg_ep_step_post(k, s, capped, reward, info, f, gt);
@@ -337,7 +356,11 @@ struct EPPolicy {
     template <class Ctx>
     static MG_HD void logic(Ctx& c, const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0,
                             int a1, MgFrameJob& job, Frame* fr, const MgScratch& sc) {
-        if (c.lane == 0) reinterpret_cast<MgEPWarpMem*>(sc.warp)->cur_env = env;  // (read by lane 0 only)
+        MgEPWarpMem& wm = *reinterpret_cast<MgEPWarpMem*>(sc.warp);
+        if (c.lane == 0) {
+            wm.cur_env = env;  // (read by lane 0 only)
+            if (t == 0 && wm.helpers > 0 && !wm.offload) mg_ep_gspec_sync(c, s, wm);  // the team takes this env over
+        }
         mg_env_logic_coop<EPPolicy>(c, k, q, a, env, t, s, a0, a1, job, fr, sc);
     }
     template <class Ctx>
@@ -357,7 +380,7 @@ struct EPPolicy {
 
 template <int TW, bool kEndless>
 struct SSPolicyT {
-    static constexpr int kHelperWarps = 0;
+    static constexpr int kHelperWarps = 0, kRolloutHelpers = 0;
     static constexpr int kWarpExtra = (int)((sizeof(MgSSWarpMem) + 127) / 128 * 128);
     static constexpr int kCtaExtra = (int)((sizeof(MgSSCtaTables) + 127) / 128 * 128);
     // instruction / latency-bound frames: TW warps share one env (more warps per base buffer hide more latency)

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmemgym_b200.so")
 
-MG_ABI_VERSION = 5
+MG_ABI_VERSION = 6
 MG_OBS_BYTES = 84 * 84 * 3
 MG_DELTA_HDR_BYTES = 176
 MG_DEBUG_DIM = 336
@@ -23,7 +23,7 @@ MG_MM_MAX_COMMANDS = 152
 MG_MM_STATE_BYTES = 256
 MG_MP_STATE_BYTES = 128
 MG_SS_STATE_BYTES = 1152
-MG_EP_STATE_BYTES = 2048
+MG_EP_STATE_BYTES = 3072
 MG_EP_MAX_SEGMENTS = 45
 MG_FLAG_AUTORESET = 1
 MG_FLAG_STREAM_OBS = 2

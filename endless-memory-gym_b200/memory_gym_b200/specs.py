@@ -24,6 +24,8 @@ class EnvSpec:
         self.default_reset_parameters = defaults
         self.action_nvec = action_nvec  # [3, 3] = MultiDiscrete([3, 3]); [4] = Discrete(4)
         self.state_bytes = state_bytes
+        # the env record proper; Endless-MysteryPath keeps a 256-byte look-ahead block behind it (MgEPSpecRec)
+        self.record_bytes = 2048 if family == "ep" else state_bytes
         self.info_keys = info_keys      # name -> column of the info matrix
         self._check = check
         self.has_ground_truth_info = has_ground_truth

@@ -212,6 +212,12 @@ class MemoryGymVecEnv:
         self._seeded = False
         self.max_episode_steps = None
 
+    @property
+    def records(self):
+        """The env records proper (`state` minus what the engine keeps behind a record for its own use: the paths
+        Endless-MysteryPath rollouts generate ahead of a reset). Two envs with equal records behave identically."""
+        return self.state[:, :self.spec_.record_bytes]
+
     # ---- reference-compatible helpers ----------------------------------------------------------------
     def process_reset_params(self, reset_params):
         return self.spec_.process_reset_params(reset_params)

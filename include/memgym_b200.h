@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 5
+#define MG_ABI_VERSION 6
 
 #define MG_SCREEN 84
 #define MG_OBS_BYTES (84 * 84 * 3) /* 21168 bytes per env, [x][y][c] */
@@ -63,7 +63,7 @@ extern "C" {
 #define MG_MM_STATE_BYTES 256      /* one env record (Mortar Mayhem family) */
 #define MG_MP_STATE_BYTES 128      /* one env record (Mystery Path) */
 #define MG_SS_STATE_BYTES 1152     /* one env record (Searing Spotlights) */
-#define MG_EP_STATE_BYTES 2048     /* one env record (Endless Mystery Path) */
+#define MG_EP_STATE_BYTES 3072     /* one env record (Endless Mystery Path): 2048 + the 1024-byte look-ahead block */
 #define MG_EP_MAX_SEGMENTS 45      /* capacity of the per-env path: 45 segments x 8 columns = 360 columns */
 
 #define MG_EINVAL (-1)  /* bad argument / unsupported option value */

@@ -31,9 +31,35 @@ struct HostCtx {
     void fence_block() {}
     void fence_device() {}
     void nanosleep(unsigned) {}
+    uint64_t now_ns() { return 0; }
     uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31u)); }
     void copy_frame(uint8_t* dst, const uint8_t* src) { memcpy(dst, src, MG_FRAME_BYTES); }
 };
+
+template <class P, class = void>
+struct RecordBytes {
+    static constexpr size_t value = sizeof(typename P::State);
+};
+template <class P>
+struct RecordBytes<P, decltype((void)P::kRecordBytes)> {
+    static constexpr size_t value = (size_t)P::kRecordBytes;
+};
+template <class P>
+constexpr size_t record_bytes() {
+    return RecordBytes<P>::value;
+}
+
+// one turn of the "helper lane" that owns `env` (mg_ep_lane_helper_loop, minus the polling)
+void ep_helper_turn(const uint8_t* cextra, uint8_t* state, int env, int max_new) {
+    MgEPSpecRec* g = mg_ep_spec_of(state, env);
+    const uint32_t h = g->hword;
+    if (!mg_ep_chain_wants(g, h)) return;
+    uint16_t info[MG_MP_NODES];
+    uint8_t list[MG_MP_NODES];
+    MgLaneMem m{info, list, 1, nullptr, 0u};
+    HostCtx ctx;
+    mg_ep_lane_work(ctx, g, h, reinterpret_cast<const MgGenCta*>(cextra)->sqrt_d2, m, max_new);
+}
 
 // mirrors mg_env_kernel (mg_kernels.cu) with one "warp": env-major loop, all n_steps steps of an env back to
 // back, a persistent frame buffer and persistent per-warp scratch (so incremental paths are exercised)
@@ -54,8 +80,16 @@ int run_q(const typename P::K& k, const void* assets, void* state, MgKIO q, bool
     const MgScratch scratch{wx, cx};
     HostCtx ctx;
     ctx.copy_frame(buf, view.tmpl[0]);
+    constexpr size_t kRecord = record_bytes<P>();
+    // Endless Mystery Path rollouts: the kernel's helper warps generate the next episode's path ahead of the reset,
+    // one env per lane (mg_ep_lane_work). Here ONE "helper lane" gets a turn after some of the steps and sometimes
+    // does a single segment only, so that adopted, resumed, stale and missing episodes all occur.
+    constexpr bool kLaneHelper = std::is_same<P, EPPolicy>::value;
+    if constexpr (kLaneHelper) {
+        if (rollout && !getenv("MG_HOSTSIM_NO_HELPER")) P::set_helpers(wx, 0, 1, false, (uint8_t*)state);
+    }
     for (int env = 0; env < q.n; ++env) {
-        State* st = reinterpret_cast<State*>((uint8_t*)state + (size_t)env * sizeof(State));
+        State* st = reinterpret_cast<State*>((uint8_t*)state + (size_t)env * kRecord);
         if constexpr (P::kPipelined) {
             // mirrors the pipelined rollout loop of mg_env_kernel<P, true>: step t + 1 is computed BEFORE frame t is
             // rasterised, auto-resets (and the endless coin respawn) are deferred to the gap between two frames
@@ -95,6 +129,9 @@ int run_q(const typename P::K& k, const void* assets, void* state, MgKIO q, bool
                 if (q.act_dims > 1) a1 = (int)a[1];
             }
             P::logic(ctx, k, q, view, env, t, *st, a0, a1, job, fr, scratch);
+            if constexpr (kLaneHelper) {
+                if (rollout && (env + t) % 3 != 0) ep_helper_turn(cx, (uint8_t*)state, env, (env + 2 * t) % 5 == 0 ? 1 : 2);
+            }
             for (int fi = 0; fi < job.nframes; ++fi) {
                 uint8_t* dst = job.to_final[fi] ? q.io.final_obs + (size_t)env * MG_FRAME_BYTES
                                                 : q.io.obs + (size_t)(t % q.ring_n) * q.obs_stride + (size_t)env * MG_FRAME_BYTES;

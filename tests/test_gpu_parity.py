@@ -198,7 +198,7 @@ def test_rollout_equals_step_loop(env_id):
     c.reset(seed=5, options=opts)
     ring2, rew2, dn2, inf2 = torch.zeros_like(ring), torch.zeros_like(rew), torch.zeros_like(dn), torch.zeros_like(inf)
     c.step_many(acts, ring2, rew2, dn2, inf2)
-    assert torch.equal(ring, ring2) and torch.equal(rew, rew2) and torch.equal(dn, dn2) and torch.equal(c.state, a.state)
+    assert torch.equal(ring, ring2) and torch.equal(rew, rew2) and torch.equal(dn, dn2) and torch.equal(c.records, a.records)
     assert torch.equal(inf[dn], inf2[dn])
     for t in range(T):
         o, r, d, _, info = b.step(acts[t])
@@ -206,7 +206,7 @@ def test_rollout_equals_step_loop(env_id):
         assert torch.equal(info["episode"][d], inf[t][d]), t
         if t >= T - 3:
             assert torch.equal(o, ring[t % 3]), t
-    assert dn.any() and torch.equal(a.state, b.state)
+    assert dn.any() and torch.equal(a.records, b.records)
 
 
 @pytest.mark.parametrize("env_id", ["MortarMayhem-v0", "Endless-MysteryPath-v0", "SearingSpotlights-v0"])
@@ -229,7 +229,7 @@ def test_rollout_scheduling_modes(env_id):
         for _ in range(3):
             env.rollout(acts, ring, rew, dn)
         bufs.append((ring, rew, dn))
-    assert all(torch.equal(x, y) for x, y in zip(*bufs)) and torch.equal(a.state, b.state)
+    assert all(torch.equal(x, y) for x, y in zip(*bufs)) and torch.equal(a.records, b.records)
     assert bufs[0][2].any()
     if a._sched is not None:
         assert int(a._sched.abs().sum()) == 0  # re-armed
@@ -284,7 +284,7 @@ def test_emp_rollout_with_and_without_helper_warps(monkeypatch):
         env.rollout(acts, ring, rew, dn)
         env.rollout(acts, ring, rew, dn)
         torch.cuda.synchronize()
-        outs.append((ring, rew, dn, env.state.clone()))
+        outs.append((ring, rew, dn, env.records.clone()))
     assert all(torch.equal(x, y) for x, y in zip(*outs))
     assert int(outs[0][2].sum()) > 3 * n  # several episodes per env: the hand-over was exercised
 
@@ -312,7 +312,7 @@ def test_rollout_final_obs_equals_step_loop(env_id):
         ever |= d
     assert ever.any()
     assert torch.equal(o, ring[(T - 1) % 2])
-    assert torch.equal(a.final_obs[ever], b.final_obs[ever]) and torch.equal(a.state, b.state)
+    assert torch.equal(a.final_obs[ever], b.final_obs[ever]) and torch.equal(a.records, b.records)
 
 
 def test_step_graph_replay_equals_step():
@@ -325,7 +325,7 @@ def test_step_graph_replay_equals_step():
     b.reset(seed=4)
     acts = _random_actions(a, 70, 6)
     graph = a.capture_step()
-    assert torch.equal(a.state, b.state) and torch.equal(a.obs, b.obs)
+    assert torch.equal(a.records, b.records) and torch.equal(a.obs, b.obs)
     for t in range(70):
         graph.actions_host.copy_(acts[t].cpu())
         graph.replay()
@@ -334,7 +334,7 @@ def test_step_graph_replay_equals_step():
         assert torch.equal(graph.obs, o), t
         assert torch.equal(graph.results_host[:8 * n].view(torch.float64), r.cpu()), t
         assert torch.equal(graph.results_host[8 * n:].bool(), d.cpu()), t
-    assert torch.equal(a.state, b.state)
+    assert torch.equal(a.records, b.records)
 
 
 @pytest.mark.parametrize("env_id", ["MortarMayhem-v0", "SearingSpotlights-v0", "Endless-SearingSpotlights-v0",
@@ -357,7 +357,7 @@ def test_rollout_edge_geometries(env_id):
             for t in range(T):
                 o, r, d, _, _ = b.step(acts[t])
         assert torch.equal(r, rew[T - 1]) and torch.equal(d, dn[T - 1]), (n, T)
-        assert torch.equal(o, ring[(T - 1) % ring_n]) and torch.equal(a.state, b.state), (n, T)
+        assert torch.equal(o, ring[(T - 1) % ring_n]) and torch.equal(a.records, b.records), (n, T)
 
 
 @pytest.mark.parametrize("env_id,opts", [
@@ -394,7 +394,7 @@ def test_pipelined_rollout_with_options_equals_step_loop(env_id, opts):
         o, r, d, _, _ = b.step(acts[t])
         assert torch.equal(o, full[t]), (t, int((o != full[t]).sum()))
         assert torch.equal(r, rew[t]) and torch.equal(d, dn[t]), t
-    assert dn.any() and torch.equal(a.state, b.state) and torch.equal(a.final_obs, b.final_obs)
+    assert dn.any() and torch.equal(a.records, b.records) and torch.equal(a.final_obs, b.final_obs)
 
 
 @pytest.mark.parametrize("env_id,opts", [
@@ -426,7 +426,7 @@ def test_rollout_with_options_equals_step_loop(env_id, opts):
         o = o["visual_observation"] if isinstance(o, dict) else o
         assert torch.equal(o, full[t]), (t, int((o != full[t]).sum()))
         assert torch.equal(r, rew[t]) and torch.equal(d, dn[t]), t
-    assert dn.any() and torch.equal(a.state, b.state)
+    assert dn.any() and torch.equal(a.records, b.records)
     if a.task_b:
         assert torch.equal(a.vector_obs, b.vector_obs)
 
@@ -469,7 +469,7 @@ def test_default_options_full_episode_at_baseline_size(env_id, n, steps):
     ring2, rew2, dn2 = torch.empty_like(ring), torch.empty_like(rew), torch.empty_like(dn)
     env2.rollout(acts, ring2, rew2, dn2)
     assert torch.equal(ring, ring2) and torch.equal(rew, rew2) and torch.equal(dn, dn2)
-    assert torch.equal(env.state, env2.state)
+    assert torch.equal(env.records, env2.records)
 
 
 def test_zero_copy_host_actions_and_results():
@@ -487,7 +487,7 @@ def test_zero_copy_host_actions_and_results():
         ob, rb, db, _, ib = b.step(acts_host[t])
         torch.cuda.synchronize()
         assert torch.equal(oa, ob) and torch.equal(ra.cpu(), rb) and torch.equal(da.cpu(), db)
-    assert torch.equal(a.state, b.state) and torch.equal(a.info, b.info)
+    assert torch.equal(a.records, b.records) and torch.equal(a.info, b.info)
     # results_out: per-step result buffers (pinned host memory, double-buffered) on an ordinary env
     c = mg.make("MortarMayhem-v0", num_envs=n, device=DEV)
     c.reset(seed=3)
