@@ -41,7 +41,7 @@ for p in (ROOT, os.path.join(ROOT, "endless-memory-gym_b200")):
 METRIC = "million env-steps/sec"
 OBS_BYTES = 84 * 84 * 3
 GRID_IDS = ("MortarMayhem-Grid-v0", "MortarMayhemB-Grid-v0", "MysteryPath-Grid-v0", "Endless-MysteryPath-v0")  # Discrete(4)
-STATE_BYTES = {"mm": 256, "mp": 128, "ss": 1152, "ep": 2048}
+STATE_BYTES = {"mm": 256, "mp": 128, "ss": 1152, "ep": 2048}  # (ep: the record proper; its look-ahead block is not streamed)
 
 
 def alg_bytes_per_env_step(family, n_act, steps_per_launch=1):
@@ -580,7 +580,9 @@ def main():
     configs = []
     if not args.no_configs:
         del main_cfg.ring
-        for env_id in ("MysteryPath-v0", "SearingSpotlights-v0", "Endless-MortarMayhem-v0"):
+        # (the three BASELINE configs, then the two endless env types BASELINE does not list: same shape)
+        for env_id in ("MysteryPath-v0", "SearingSpotlights-v0", "Endless-MortarMayhem-v0", "Endless-MysteryPath-v0",
+                       "Endless-SearingSpotlights-v0"):
             if env_id == args.env:
                 continue
             c = Timed(mg, torch, dist, env_id, default_n(env_id), rank, world, dev, K, args.chunk)

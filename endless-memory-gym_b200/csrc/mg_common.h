@@ -199,11 +199,20 @@ struct MgEPState {
 // segments of the NEXT episodes, generated ahead of their resets by the helper warps of the rollout kernels
 // (mg_ep_logic.h) — a ring of MG_EP_AHEAD episodes, each generated from the stream its predecessor ends with. The env's
 // team never copies this part with the record; both sides go through global memory.
-#define MG_EP_AHEAD 4
+#define MG_EP_AHEAD 8
 struct MgEPSpecSlot {
     MgRng before;        // the stream the reset must find for this episode to be adopted
     MgRng after;         // the stream after the segments generated so far (all three: what the reset leaves behind)
     MgEPSegment seg[3];
+};
+struct MgEPResume {      // a segment's noisy A* stopped at the end of a launch (mg_mp_generate_lane), resumed by the next
+    uint32_t tag;        // the hword the search belongs to (0: none): same chain, episode and segment, or it is dropped
+    uint8_t nopen, sy, ey, pad0;
+    uint64_t wall, open, closed;
+    uint64_t rng_lo, rng_hi;  // the stream as it was when the search stopped (same increment as the chain)
+    uint32_t rng_buf, rng_has;
+    uint64_t blob[19];   // the lane's scratch, packed: uint16 info[49], then uint8 list[49] (moved as 19 independent words)
+    uint8_t pad1[48];
 };
 struct MgEPSpecRec {
     uint32_t hword;     // chain << 12 | episodes produced (mod 256) << 4 | segments of the next one << 2 | MG_CHAIN_*;
@@ -214,9 +223,11 @@ struct MgEPSpecRec {
     MgRng base;         // the stream the chain's first episode starts from (team)
     uint8_t pad0[8];
     MgEPSpecSlot slot[MG_EP_AHEAD];
-    uint8_t pad1[160];
+    MgEPResume resume;  // the helper lane's search in progress (helper)
+    uint8_t pad1[128];
 };
-static_assert(sizeof(MgEPSpecSlot) == 200 && sizeof(MgEPSpecRec) == 1024, "MgEPSpecRec must be 1024 bytes");
+static_assert(sizeof(MgEPSpecSlot) == 200 && sizeof(MgEPResume) == 256 && sizeof(MgEPSpecRec) == 2048,
+              "MgEPSpecRec must be 2048 bytes");
 
 #define MG_EP_MAXTILES 72
 struct MgEPFrame {

@@ -123,9 +123,9 @@ struct MgEPSpec {
 };
 struct MgEPWarpMem {  // per-team scratch of the Endless Mystery Path kernels
     MgGenMem gen;
-    int32_t helpers;  // helper warps in this launch (0: none, resets generate their own paths)
-    int16_t offload;  // single-step launch: an auto-reset hands its path generation to a helper (mg_ep_reset_offload)
-    int16_t pad;
+    int32_t pad;
+    int16_t ahead;    // this launch runs helper warps that generate paths ahead (mg_ep_lane_helper_loop): chains are live
+    int16_t offload;  // single-step launch with helper warps that finish an auto-reset's path (mg_ep_reset_offload)
     int32_t cur_env;  // the env this team works on
     int32_t post_env; // >= 0: its record carries a pending path; post the job once the record is written back
     uint8_t* state;   // the batch's records (rollouts: where the MgEPSpecRec of an env lives)
@@ -254,31 +254,36 @@ MG_HD MgEPSpecSlot* mg_ep_chain_head(MgEPSpecRec* g, uint32_t& tword) {
     return &g->slot[mg_chain_consumed(tword) % MG_EP_AHEAD];
 }
 
-// Team side, at a reset: true if the three segments were adopted from the env's chain
+// Team side, at a reset: true if the three segments were adopted from the env's chain. The slot is read as 50
+// independent words spread over the lanes (a chain of dependent global loads would cost the team ~1 us each).
 template <class Ctx>
 MG_HD bool mg_ep_gspec_take(Ctx& c, MgEPState& s, MgEPWarpMem& wm) {
+    static_assert(sizeof(MgRng) == 40 && offsetof(MgEPSpecSlot, after) == 40 && offsetof(MgEPSpecSlot, seg) == 80, "slot layout");
     MgEPSpecRec* const g = mg_ep_spec_of(wm.state, (int)c.shfl((uint32_t)wm.cur_env, 0));
-    uint32_t idx = 0xFFu, tword = 0;
-    if (c.lane == 0) {
-        MgEPSpecSlot* sl = mg_ep_chain_head(g, tword);
-        if (sl) {
-            c.fence_device();  // the helper's data is visible after its count
-            if (mg_ep_stream_eq(sl->before, s.rng)) idx = (uint32_t)(sl - g->slot);
-        }
+    const uint32_t h = c.shfl(mg_vload_u32(&g->hword), 0), tword = c.shfl(mg_vload_u32(&g->tword), 0);
+    if ((h & 3u) == MG_CHAIN_IDLE || mg_chain_id(h) != mg_chain_id(tword)) return false;
+    if (((mg_chain_count(h) - mg_chain_consumed(tword)) & 255u) == 0u) return false;
+    MgEPSpecSlot* const sl = &g->slot[mg_chain_consumed(tword) % MG_EP_AHEAD];
+    c.fence_device();  // the helper's data is visible after its count
+    const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>(sl);
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(&s.rng);
+    uint32_t differs = 0;
+    for (int w = c.lane; w < 10; w += c.nl) differs |= src[w] != mine[w] ? 1u : 0u;  // slot.before == stream?
+    if (c.reduce_or(differs)) return false;
+    c.sync();
+    uint32_t* rng = reinterpret_cast<uint32_t*>(&s.rng);
+    uint32_t* seg = reinterpret_cast<uint32_t*>(s.seg);
+    for (int w = 10 + c.lane; w < 50; w += c.nl) {
+        const uint32_t v = src[w];
+        if (w < 20)
+            rng[w - 10] = v;  // slot.after (same increment)
+        else
+            seg[w - 20] = v;
     }
-    idx = c.shfl(idx, 0);
-    if (idx == 0xFFu) return false;
-    MgEPSpecSlot* const sl = &g->slot[idx];
-    const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>(sl->seg);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(s.seg);
-    for (int w = c.lane; w < (int)(3 * sizeof(MgEPSegment) / 4); w += c.nl) dst[w] = src[w];
     c.sync();  // every lane has read the slot before lane 0 hands it back to the helper
     if (c.lane == 0) {
-        const volatile MgRng& a = sl->after;
-        s.rng.state_lo = a.state_lo, s.rng.state_hi = a.state_hi;
-        s.rng.buf = a.buf, s.rng.has_buf = a.has_buf;  // (same increment)
         s.n_segments = 3;
-        g->adopted = g->adopted + 1u;
+        c.atomic_inc(&g->adopted);
         c.fence_device();
         mg_vstore_u32(&g->tword, (tword & ~255u) | ((mg_chain_consumed(tword) + 1u) & 255u));
     }
@@ -286,16 +291,19 @@ MG_HD bool mg_ep_gspec_take(Ctx& c, MgEPState& s, MgEPWarpMem& wm) {
     return true;
 }
 
-// Team side: start a new chain from the stream as it is now (what was generated ahead is stale or missing)
+// Owner side (one thread): start a new chain from `stream` (what was generated ahead is stale or missing)
 template <class Ctx>
-MG_HD void mg_ep_gspec_post(Ctx& c, const MgEPState& s, MgEPWarpMem& wm) {
-    if (c.lane != 0) return;
-    MgEPSpecRec* const g = mg_ep_spec_of(wm.state, wm.cur_env);
+MG_HD void mg_ep_chain_start(Ctx& c, MgEPSpecRec* g, const MgRng& stream) {
     const uint32_t chain = (mg_chain_id(mg_vload_u32(&g->tword)) + 1u) & 0xFFFFFu;
-    mg_ep_stream_put(g->base, s.rng);
+    mg_ep_stream_put(g->base, stream);
     mg_vstore_u32(&g->tword, chain << 12);
     c.fence_device();
     mg_vstore_u32(&g->hword, (chain << 12) | MG_CHAIN_ACTIVE);
+}
+// Team side: ... from the env's stream as it is now
+template <class Ctx>
+MG_HD void mg_ep_gspec_post(Ctx& c, const MgEPState& s, MgEPWarpMem& wm) {
+    if (c.lane == 0) mg_ep_chain_start(c, mg_ep_spec_of(wm.state, wm.cur_env), s.rng);
 }
 
 // Team side, when it takes an env over: a record without a chain (first rollout after construction), or whose chain
@@ -327,23 +335,51 @@ MG_HD void mg_ep_lane_work(Ctx& c, MgEPSpecRec* g, uint32_t h, const double* sqr
         const uint32_t produced = mg_chain_count(h);
         const int nseg = (int)mg_chain_nseg(h);
         MgEPSpecSlot* const sl = &g->slot[produced % MG_EP_AHEAD];
-        // the stream to continue from: the slot's own progress, else what the previous episode (or the chain's base) ends with
-        const volatile MgRng& from =
-            nseg > 0 ? sl->after : (produced == 0 ? g->base : g->slot[(produced + MG_EP_AHEAD - 1u) % MG_EP_AHEAD].after);
+        MgEPResume& rs = g->resume;
         MgRngR r;
-        r.lo = from.state_lo, r.hi = from.state_hi, r.ilo = from.inc_lo, r.ihi = from.inc_hi, r.buf = from.buf, r.has = from.has_buf;
-        if (nseg == 0) {
-            volatile MgRng& b = sl->before;
-            b.state_lo = r.lo, b.state_hi = r.hi, b.inc_lo = r.ilo, b.inc_hi = r.ihi, b.buf = r.buf, b.has_buf = r.has;
+        MgLaneSearch st;
+        int sy, ey;
+        const bool resume = *reinterpret_cast<const volatile uint32_t*>(&rs.tag) == h;
+        if (resume) {
+            // this very segment's search was stopped by the end of an earlier launch: carry on where it stopped
+            const volatile MgRng& inc = g->base;
+            r.lo = rs.rng_lo, r.hi = rs.rng_hi, r.ilo = inc.inc_lo, r.ihi = inc.inc_hi, r.buf = rs.rng_buf, r.has = rs.rng_has;
+            sy = rs.sy, ey = rs.ey;
+            st.wall = rs.wall, st.open = rs.open, st.closed = rs.closed, st.nopen = rs.nopen;
+            uint64_t blob[MG_LANE_BLOB_WORDS];
+            MG_UNROLL
+            for (int w = 0; w < MG_LANE_BLOB_WORDS; ++w) blob[w] = rs.blob[w];
+            mg_lane_unpack(blob, m);
+        } else {
+            // the stream to continue from: the slot's own progress, else what the previous episode (or the chain's base) ends with
+            const volatile MgRng& from =
+                nseg > 0 ? sl->after : (produced == 0 ? g->base : g->slot[(produced + MG_EP_AHEAD - 1u) % MG_EP_AHEAD].after);
+            r.lo = from.state_lo, r.hi = from.state_hi, r.ilo = from.inc_lo, r.ihi = from.inc_hi, r.buf = from.buf, r.has = from.has_buf;
+            if (nseg == 0) {
+                volatile MgRng& b = sl->before;
+                b.state_lo = r.lo, b.state_hi = r.hi, b.inc_lo = r.ilo, b.inc_hi = r.ihi, b.buf = r.buf, b.has_buf = r.has;
+            }
+            // EndlessMysteryPath.add_path_segment, as in mg_ep_add_segment_coop
+            sy = nseg == 0 ? mg_rr_integers(r, 0, MG_MP_CELLS)
+                           : (int)((*reinterpret_cast<const volatile uint64_t*>(&sl->seg[nseg - 1].path) >> 60) & 7ull);
+            ey = mg_rr_integers(r, 0, MG_MP_CELLS);
         }
-        // EndlessMysteryPath.add_path_segment, as in mg_ep_add_segment_coop
-        const int sy = nseg == 0 ? mg_rr_integers(r, 0, MG_MP_CELLS)
-                                 : (int)((*reinterpret_cast<const volatile uint64_t*>(&sl->seg[nseg - 1].path) >> 60) & 7ull);
-        const int ey = mg_rr_integers(r, 0, MG_MP_CELLS);
         uint64_t nx[2];
         bool stopped;
-        const uint64_t mask = mg_mp_generate_lane(r, 0, sy, MG_MP_CELLS - 1, ey, sqrt_d2, m, nx, stopped);
-        if (stopped) return;  // (what is published stays valid: the next launch resumes from it)
+        const uint64_t mask = mg_mp_generate_lane(r, 0, sy, MG_MP_CELLS - 1, ey, sqrt_d2, m, nx, stopped, st, resume);
+        if (stopped) {
+            // the launch is ending: park the search behind the record (the next launch's helper lane resumes it)
+            rs.nopen = (uint8_t)st.nopen, rs.sy = (uint8_t)sy, rs.ey = (uint8_t)ey;
+            rs.wall = st.wall, rs.open = st.open, rs.closed = st.closed;
+            rs.rng_lo = r.lo, rs.rng_hi = r.hi, rs.rng_buf = r.buf, rs.rng_has = r.has;
+            uint64_t blob[MG_LANE_BLOB_WORDS];
+            mg_lane_pack(m, blob);
+            MG_UNROLL
+            for (int w = 0; w < MG_LANE_BLOB_WORDS; ++w) rs.blob[w] = blob[w];
+            c.fence_device();
+            *reinterpret_cast<volatile uint32_t*>(&rs.tag) = h;
+            return;
+        }
         uint32_t next;
         if (!mask) {
             // "No valid path found": the reset will find out by itself (the reference raises there)
@@ -372,11 +408,11 @@ MG_HD void mg_ep_lane_work(Ctx& c, MgEPSpecRec* g, uint32_t h, const double* sqr
 // per turn: lanes whose chain got room meanwhile join at the next segment boundary.
 template <class Ctx>
 MG_HD void mg_ep_lane_helper_loop(Ctx& c, uint8_t* state, int n, int first, int step, const uint32_t* teams_done,
-                                  int nteams, const double* sqrt_d2, const MgLaneMem& m) {
+                                  int stop_at, const double* sqrt_d2, const MgLaneMem& m) {
     const int count = first < n ? (n - first + step - 1) / step : 0;
     int rot = 0;
     for (;;) {
-        if (mg_vload_u32(teams_done) >= (uint32_t)nteams) return;  // the launch is over: the chains wait
+        if (mg_vload_u32(teams_done) >= (uint32_t)stop_at) return;  // the launch is over: the chains wait
         MgEPSpecRec* g = nullptr;
         uint32_t h = 0;
         for (int i = 0; i < count && !g; ++i) {
@@ -513,6 +549,8 @@ MG_HD void mg_ep_helper_offload_loop(Ctx& c, uint8_t* hs_bytes, uint8_t* wextra0
                 mg_ep_update_direction(hs);
                 g->dir = hs.dir;
                 if (ground_truth) mg_ep_ground_truth(hs, ground_truth + MG_GT_COLS * (size_t)job->env);
+                // the episodes after this one: a new chain from the stream this reset ends with
+                mg_ep_chain_start(c, mg_ep_spec_of(state, job->env), hs.rng);
             } else {
                 // "No valid path found": the reference raises; here the env stays finished, in the same state the inline
                 // reset leaves behind (node (0, 0), no direction): nothing of the helper's scratch record is read
@@ -541,8 +579,6 @@ MG_HD void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, 
                             const MgGenCta& tab) {
     MgGenMem& m = wm.gen;
     c.stamp(12);
-    // (an agent wider than a tile would show past-path tiles in its very first frame: those need the path)
-    if (wm.helpers > 0 && wm.offload && k.radius < MG_MP_TILE && mg_ep_reset_offload(c, k, s, f, wm)) return;
     if (c.lane == 0) {
         s.t = 0;
         s.ep_len = 0;
@@ -550,9 +586,13 @@ MG_HD void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, 
         s.n_segments = 0;
     }
     c.sync();
+    // 1. the episode generated ahead, if the stream still is what it was generated from
+    const bool adopted = wm.ahead && mg_ep_gspec_take(c, s, wm);
+    // 2. single-step launches: the frame now, the path by a helper warp before the kernel ends
+    // (an agent wider than a tile would show past-path tiles in its very first frame: those need the path)
+    if (!adopted && wm.offload && k.radius < MG_MP_TILE && mg_ep_reset_offload(c, k, s, f, wm)) return;
+    // 3. here and now
     bool ok = true;
-    const bool spec = wm.helpers > 0 && !wm.offload;
-    const bool adopted = spec && mg_ep_gspec_take(c, s, wm);
     if (!adopted)
         for (int q = 0; q < 3 && ok; ++q) ok = mg_ep_add_segment_coop(c, s, m, tab);
     c.stamp(13);
@@ -581,7 +621,7 @@ MG_HD void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, 
         if (gt) mg_ep_ground_truth(s, gt);
     }
     c.sync();
-    if (spec && ok && !adopted) mg_ep_gspec_post(c, s, wm);  // (an adopted episode: its chain goes on)
+    if (wm.ahead && ok && !adopted) mg_ep_gspec_post(c, s, wm);  // (an adopted episode: its chain goes on)
     c.stamp(14);
 }
 

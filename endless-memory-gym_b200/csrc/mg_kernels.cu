@@ -149,6 +149,7 @@ struct MgWarpCtx {
             *p = v;
     }
     __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
+    __device__ __forceinline__ void atomic_inc(uint32_t* p) { atomicAdd(p, 1u); }
     // warp reductions (single-warp teams only): every lane gets the result
     __device__ __forceinline__ uint32_t reduce_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
     __device__ __forceinline__ uint32_t reduce_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
     P::cta_init(cextra, threadIdx.x, blockDim.x);
     if (!is_helper) {
         P::warp_init(wextra, lane);
-        if constexpr (P::kHelperWarps > 0) P::set_helpers(wextra, lane, nhelp, !kRollout, state);
+        if constexpr (P::kHelperWarps > 0) P::set_helpers(wextra, lane, q.n_lane_helpers, nhelp - q.n_lane_helpers, state);
     }
     __syncthreads();
     if (staged) {
@@ -283,11 +284,12 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
         if (is_helper) {
             MgWarpCtx hctx{lane, kTeam, 0u, 0u, 0ull, nullptr, 0};
             uint8_t* const wextra0 = smem + (size_t)nteams * (P::kFrameBuf + kSlot);
-            if constexpr (kRollout)
-                P::helper_loop(hctx, cextra, nteams, team - nteams, nhelp, (int)blockIdx.x, (int)gridDim.x, &hdr->teams_done,
-                               state, q.n);
-            else
-                P::helper_loop_step(hctx, cextra, wextra0, nteams, team - nteams, &hdr->teams_done, state, q.io.ground_truth);
+            const int hidx = team - nteams, nlane = q.n_lane_helpers;
+            if (hidx < nlane)
+                P::helper_loop(hctx, cextra, nteams, hidx, nlane, (int)blockIdx.x, (int)gridDim.x, &hdr->teams_done,
+                               kRollout ? nteams : 1, state, q.n);
+            else if constexpr (!kRollout)
+                P::helper_loop_step(hctx, cextra, wextra0, nteams, hidx - nlane, &hdr->teams_done, state, q.io.ground_truth);
             return;
         }
     }
@@ -703,6 +705,7 @@ static int launch_env(const typename P::K& k, const void* assets, void* state, c
         q.n_steps = 1;
         q.ring_n = 1;
         q.n_helpers = plan.helpers;
+        q.n_lane_helpers = plan.helpers < P::kRolloutHelpers ? plan.helpers : P::kRolloutHelpers;
         rc = launch_one<P, false>(k, q, plan, assets, state, stream);
         if (rc) return rc;
     }
@@ -744,6 +747,7 @@ static int launch_rollout(const typename P::K& k, const void* assets, void* stat
     q.io.vector_obs = r->vector_obs;
     q.sched = r->sched;
     q.n_helpers = plan.helpers;
+    q.n_lane_helpers = plan.helpers;
     q.io.flags = r->flags | MG_FLAG_AUTORESET;  // a rollout without auto-reset would only idle finished envs
     q.mode = MG_MODE_STEP;
     q.n = n;

@@ -274,8 +274,9 @@ struct MgLaneMem {
     uint16_t* info;  // per cell: g cost << 6 | predecessor (63 = none); valid for cells that were ever open
     uint8_t* list;   // open list: cells in insertion order
     int stride;      // elements between two consecutive entries of one lane
-    const volatile uint32_t* stop;  // optional: give up as soon as *stop >= stop_at (the launch is ending)
+    const volatile uint32_t* stop;  // optional: stop as soon as *stop >= stop_at (the launch is ending)
     uint32_t stop_at;
+    int budget;      // node expansions this call may do before it stops (< 0: no limit; the CPU tests stop mid-search)
 };
 #define MG_LANE_NOPREV 63u
 // the cells within one step (8-neighbourhood) of a set of cells, the set included
@@ -286,51 +287,109 @@ MG_HD uint64_t mg_mp_dilate8(uint64_t w) {
     d |= (d << MG_MP_CELLS) | (d >> MG_MP_CELLS);
     return d & full;
 }
+// the lane's scratch <-> 19 packed words (uint16 info[49], then uint8 list[49]): a parked search moves through
+// registers so that its global loads / stores are independent of each other
+#define MG_LANE_BLOB_WORDS 19
+MG_HD void mg_lane_pack(const MgLaneMem& m, uint64_t* blob) {
+    const int S = m.stride;
+    MG_UNROLL
+    for (int w = 0; w < 12; ++w)
+        blob[w] = (uint64_t)m.info[(4 * w) * S] | ((uint64_t)m.info[(4 * w + 1) * S] << 16) |
+                  ((uint64_t)m.info[(4 * w + 2) * S] << 32) | ((uint64_t)m.info[(4 * w + 3) * S] << 48);
+    uint64_t v = (uint64_t)m.info[48 * S];
+    MG_UNROLL
+    for (int k = 0; k < 6; ++k) v |= (uint64_t)m.list[k * S] << (16 + 8 * k);
+    blob[12] = v;
+    MG_UNROLL
+    for (int w = 13; w < MG_LANE_BLOB_WORDS; ++w) {
+        v = 0;
+        MG_UNROLL
+        for (int k = 0; k < 8; ++k) {
+            const int i = 6 + 8 * (w - 13) + k;
+            if (i < MG_MP_NODES) v |= (uint64_t)m.list[i * S] << (8 * k);
+        }
+        blob[w] = v;
+    }
+}
+MG_HD void mg_lane_unpack(const uint64_t* blob, const MgLaneMem& m) {
+    const int S = m.stride;
+    MG_UNROLL
+    for (int w = 0; w < 12; ++w) {
+        MG_UNROLL
+        for (int k = 0; k < 4; ++k) m.info[(4 * w + k) * S] = (uint16_t)(blob[w] >> (16 * k));
+    }
+    m.info[48 * S] = (uint16_t)blob[12];
+    MG_UNROLL
+    for (int k = 0; k < 6; ++k) m.list[k * S] = (uint8_t)(blob[12] >> (16 + 8 * k));
+    MG_UNROLL
+    for (int w = 13; w < MG_LANE_BLOB_WORDS; ++w) {
+        MG_UNROLL
+        for (int k = 0; k < 8; ++k) {
+            const int i = 6 + 8 * (w - 13) + k;
+            if (i < MG_MP_NODES) m.list[i * S] = (uint8_t)(blob[w] >> (8 * k));
+        }
+    }
+}
+
+// The search in progress, minus the per-lane scratch: what a stopped lane saves and a resumed lane reloads
+struct MgLaneSearch {
+    uint64_t wall, open, closed;
+    int32_t nopen;
+};
 // Returns the path mask (0: no path, or stopped early — `stopped` tells which); next2 as in mg_mp_generate_coop.
+// resume: `st` and the scratch hold a search stopped earlier (same start / end, the stream `r` as it was then);
+// when it stops again they hold what the next call needs.
 MG_HD uint64_t mg_mp_generate_lane(MgRngR& r, int sx, int sy, int ex, int ey, const double* sqrt_d2, const MgLaneMem& m,
-                                   uint64_t* next2, bool& stopped) {
+                                   uint64_t* next2, bool& stopped, MgLaneSearch& st, bool resume = false) {
     constexpr int n = MG_MP_CELLS;
     stopped = false;
-    uint64_t wall = 0;
-    MG_NOUNROLL
-    for (int id = mg_mp_id(1, 1); id <= mg_mp_id(n - 3, n - 3); ++id) {
-        const int j = id % n;
-        if (j < 1 || j > n - 3) continue;
-        if (mg_rr_integers(r, 0, 100) < 33) wall |= 1ull << id;
-    }
-    const int start = mg_mp_id(sx, sy), end = mg_mp_id(ex, ey);
-    const uint64_t bad = (1ull << start) | (1ull << end) | mg_mp_nbr4(sx, sy) | mg_mp_nbr4(ex, ey) | mg_mp_dilate8(wall);
-    // the 24 ring cells in scan order: row 0, the two ends of rows 1..5, row 6
-    uint32_t taken = (uint32_t)(bad & 0x7Full) | ((uint32_t)((bad >> 42) & 0x7Full) << 17);
-    MG_UNROLL
-    for (int i = 1; i <= n - 2; ++i) {
-        taken |= (uint32_t)((bad >> (n * i)) & 1ull) << (7 + 2 * (i - 1));
-        taken |= (uint32_t)((bad >> (n * i + n - 1)) & 1ull) << (8 + 2 * (i - 1));
-    }
-    uint32_t elig = ~taken & 0xFFFFFFu;
-    int nring = mg_popc32(elig);
-    const int picks = mg_rr_integers(r, 0, 2) ? 8 : 4;
-    MG_NOUNROLL
-    for (int q = 0; q < picks && nring > 0; ++q) {
-        const int b = mg_nth_set_bit(elig, mg_rr_integers(r, 0, nring));
-        wall |= 1ull << mg_mp_ring_id(b);
-        elig &= ~(1u << b);
-        nring--;
-    }
     const int S = m.stride;
-    uint64_t open = 1ull << start, closed = 0;
-    int nopen = 1;
-    m.list[0] = (uint8_t)start;
-    m.info[start * S] = (uint16_t)MG_LANE_NOPREV;  // g = 0
+    const int start = mg_mp_id(sx, sy), end = mg_mp_id(ex, ey);
+    uint64_t wall, open, closed;
+    int nopen;
+    if (resume) {
+        wall = st.wall, open = st.open, closed = st.closed, nopen = st.nopen;
+    } else {
+        wall = 0;
+        MG_NOUNROLL
+        for (int id = mg_mp_id(1, 1); id <= mg_mp_id(n - 3, n - 3); ++id) {
+            const int j = id % n;
+            if (j < 1 || j > n - 3) continue;
+            if (mg_rr_integers(r, 0, 100) < 33) wall |= 1ull << id;
+        }
+        const uint64_t bad = (1ull << start) | (1ull << end) | mg_mp_nbr4(sx, sy) | mg_mp_nbr4(ex, ey) | mg_mp_dilate8(wall);
+        // the 24 ring cells in scan order: row 0, the two ends of rows 1..5, row 6
+        uint32_t taken = (uint32_t)(bad & 0x7Full) | ((uint32_t)((bad >> 42) & 0x7Full) << 17);
+        MG_UNROLL
+        for (int i = 1; i <= n - 2; ++i) {
+            taken |= (uint32_t)((bad >> (n * i)) & 1ull) << (7 + 2 * (i - 1));
+            taken |= (uint32_t)((bad >> (n * i + n - 1)) & 1ull) << (8 + 2 * (i - 1));
+        }
+        uint32_t elig = ~taken & 0xFFFFFFu;
+        int nring = mg_popc32(elig);
+        const int picks = mg_rr_integers(r, 0, 2) ? 8 : 4;
+        MG_NOUNROLL
+        for (int q = 0; q < picks && nring > 0; ++q) {
+            const int b = mg_nth_set_bit(elig, mg_rr_integers(r, 0, nring));
+            wall |= 1ull << mg_mp_ring_id(b);
+            elig &= ~(1u << b);
+            nring--;
+        }
+        open = 1ull << start, closed = 0;
+        nopen = 1;
+        m.list[0] = (uint8_t)start;
+        m.info[start * S] = (uint16_t)MG_LANE_NOPREV;  // g = 0
+    }
     const auto f_of = [&](int cell, uint32_t g) {
         const int dx = cell / n - ex, dy = cell % n - ey;
         return (double)g + sqrt_d2[dx * dx + dy * dy];
     };
-    int cur = start;
+    int cur = start, budget = m.budget;
     MG_NOUNROLL
     for (;;) {
         if (nopen == 0) return 0;
-        if (m.stop && *m.stop >= m.stop_at) {
+        if ((m.stop && *m.stop >= m.stop_at) || budget-- == 0) {
+            st.wall = wall, st.open = open, st.closed = closed, st.nopen = nopen;
             stopped = true;
             return 0;
         }

@@ -32,7 +32,8 @@ struct MgKIO {
     int32_t n_steps, ring_n;
     int64_t act_stride, obs_stride, rew_stride, done_stride, info_stride;
     uint32_t* sched;  // rollout: global work counter (mg_rollout_io.sched) or nullptr = CTA-local scheduling
-    int32_t n_helpers;  // rollout: helper warps behind the env teams of every CTA (policies with kHelperWarps > 0)
+    int32_t n_helpers;  // helper warps behind the env teams of every CTA (policies with kHelperWarps > 0)
+    int32_t n_lane_helpers;  // ... of which the first n_lane_helpers generate paths ahead (EPPolicy)
 };
 
 struct MgFrameJob {      // what the logic lane hands to the warp: up to two frames for this env-step
@@ -256,16 +257,15 @@ struct MPPolicy {
 
 struct EPPolicy {
     static constexpr bool kPipelined = false;
-    static constexpr int kHelperWarps = 7;    // single-step launches: warps that finish the paths of auto-resets
-    static constexpr int kRolloutHelpers = 2;  // rollout launches: warps that generate paths ahead, one env per lane
+    static constexpr int kRolloutHelpers = 2;  // warps that generate paths ahead, one env per lane (every launch)
+    static constexpr int kOffloadHelpers = 3;  // single-step launches: warps that finish the paths of auto-resets
+    static constexpr int kHelperWarps = kRolloutHelpers + kOffloadHelpers;
     static constexpr int kRecordBytes = MG_EP_STATE_BYTES;  // record + the MgEPSpecRec behind it
-    static constexpr int kWarpExtra = (int)((sizeof(MgEPWarpMem) + 127) / 128 * 128);
+    static constexpr int kWarpExtra = (int)((sizeof(MgEPWarpMem) + 63) / 64 * 64);
     static constexpr int kGenCtaBytes = (int)((sizeof(MgGenCta) + 127) / 128 * 128);
-    static constexpr int kHelperBytes = kHelperWarps * MG_EP_HELPER_BYTES > kRolloutHelpers * MG_EP_LANE_WARP_BYTES
-                                            ? kHelperWarps * MG_EP_HELPER_BYTES
-                                            : kRolloutHelpers * MG_EP_LANE_WARP_BYTES;
-    static constexpr int kCtaExtra = kGenCtaBytes + (kHelperBytes + 127) / 128 * 128;
-    static constexpr int kStageReserve = 5 * 1024;
+    static constexpr int kLaneBytes = kRolloutHelpers * MG_EP_LANE_WARP_BYTES;
+    static constexpr int kCtaExtra = kGenCtaBytes + (kLaneBytes + kOffloadHelpers * MG_EP_HELPER_BYTES + 127) / 128 * 128;
+    static constexpr int kStageReserve = 4608;  // (the default assets stage 4480 bytes)
     static constexpr int kTeamWarps = 1, kMaxThreads = 512;
     static constexpr int kFrameBuf = 21248;
     static constexpr bool kDirectStore = false;
@@ -275,7 +275,7 @@ struct EPPolicy {
     static MG_HD void warp_init(uint8_t* warp, int lane) {
         if (lane == 0) {
             MgEPWarpMem* wm = reinterpret_cast<MgEPWarpMem*>(warp);
-            wm->helpers = 0;
+            wm->ahead = 0;
             wm->offload = 0;
             wm->cur_env = -1;
             wm->post_env = -1;
@@ -283,11 +283,11 @@ struct EPPolicy {
             wm->spec.state = MG_SPEC_EMPTY;
         }
     }
-    // helper warps of this launch; `offload`: single-step launch (they finish auto-resets), else rollout (they work ahead)
-    static MG_HD void set_helpers(uint8_t* warp, int lane, int n, bool offload, uint8_t* state) {
+    // helper warps of this launch: n_lane generate ahead, n_offload finish the paths of auto-resets (single steps)
+    static MG_HD void set_helpers(uint8_t* warp, int lane, int n_lane, int n_offload, uint8_t* state) {
         if (lane == 0) {
-            reinterpret_cast<MgEPWarpMem*>(warp)->helpers = n;
-            reinterpret_cast<MgEPWarpMem*>(warp)->offload = offload ? 1 : 0;
+            reinterpret_cast<MgEPWarpMem*>(warp)->ahead = n_lane > 0 ? 1 : 0;
+            reinterpret_cast<MgEPWarpMem*>(warp)->offload = n_offload > 0 ? 1 : 0;
             reinterpret_cast<MgEPWarpMem*>(warp)->state = state;
         }
     }
@@ -298,7 +298,7 @@ struct EPPolicy {
     template <class Ctx>
     static MG_HD void helper_loop_step(Ctx& c, uint8_t* cextra, uint8_t* wextra0, int nteams, int hidx,
                                        const uint32_t* teams_done, uint8_t* state, double* ground_truth) {
-        uint8_t* mine = cextra + kGenCtaBytes + (size_t)hidx * MG_EP_HELPER_BYTES;
+        uint8_t* mine = cextra + kGenCtaBytes + kLaneBytes + (size_t)hidx * MG_EP_HELPER_BYTES;
         MgGenMem m{0, 0};
         mg_ep_helper_offload_loop(c, mine, wextra0, kWarpExtra, nteams, hidx, teams_done, m,
                                   *reinterpret_cast<const MgGenCta*>(cextra), state, ground_truth);
@@ -306,15 +306,16 @@ struct EPPolicy {
     // rollout helper warp `hidx` of `nhelp` in CTA `cta` of `nctas`: one env per lane
     template <class Ctx>
     static MG_HD void helper_loop(Ctx& c, uint8_t* cextra, int nteams, int hidx, int nhelp, int cta, int nctas,
-                                  const uint32_t* teams_done, uint8_t* state, int n) {
+                                  const uint32_t* teams_done, int stop_at, uint8_t* state, int n) {
         uint8_t* mine = cextra + kGenCtaBytes + (size_t)hidx * MG_EP_LANE_WARP_BYTES;
         MgLaneMem m;
         m.info = reinterpret_cast<uint16_t*>(mine) + c.lane;
         m.list = mine + MG_MP_NODES * 32 * 2 + c.lane;
         m.stride = 32;
         m.stop = teams_done;
-        m.stop_at = (uint32_t)nteams;
-        mg_ep_lane_helper_loop(c, state, n, (cta * nhelp + hidx) * 32 + c.lane, nctas * nhelp * 32, teams_done, nteams,
+        m.stop_at = (uint32_t)stop_at;  // rollouts: every team has left; single steps: the first has (parking overlaps the rest)
+        m.budget = -1;
+        mg_ep_lane_helper_loop(c, state, n, (cta * nhelp + hidx) * 32 + c.lane, nctas * nhelp * 32, teams_done, stop_at,
                                reinterpret_cast<const MgGenCta*>(cextra)->sqrt_d2, m);
     }
     typedef MgEPK K;
@@ -341,7 +342,7 @@ struct EPPolicy {
             capped = !mg_ep_add_segment_coop(c, s, m, *reinterpret_cast<const MgGenCta*>(sc.cta));
             // the stream has moved: what was generated ahead for the next reset is stale, ask again
             MgEPWarpMem& wm = *reinterpret_cast<MgEPWarpMem*>(sc.warp);
-            if (wm.helpers > 0 && !wm.offload) mg_ep_gspec_post(c, s, wm);
+            if (wm.ahead) mg_ep_gspec_post(c, s, wm);
         }
         if (c.lane == 0) {
             double reward;
@@ -359,7 +360,8 @@ struct EPPolicy {
         MgEPWarpMem& wm = *reinterpret_cast<MgEPWarpMem*>(sc.warp);
         if (c.lane == 0) {
             wm.cur_env = env;  // (read by lane 0 only)
-            if (t == 0 && wm.helpers > 0 && !wm.offload) mg_ep_gspec_sync(c, s, wm);  // the team takes this env over
+            // rollouts: the team takes this env over for many steps (single steps leave a missing chain to the next reset)
+            if (t == 0 && wm.ahead && !wm.offload && q.n_steps > 1) mg_ep_gspec_sync(c, s, wm);
         }
         mg_env_logic_coop<EPPolicy>(c, k, q, a, env, t, s, a0, a1, job, fr, sc);
     }

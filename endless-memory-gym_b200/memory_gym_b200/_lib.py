@@ -23,7 +23,7 @@ MG_MM_MAX_COMMANDS = 152
 MG_MM_STATE_BYTES = 256
 MG_MP_STATE_BYTES = 128
 MG_SS_STATE_BYTES = 1152
-MG_EP_STATE_BYTES = 3072
+MG_EP_STATE_BYTES = 4096
 MG_EP_MAX_SEGMENTS = 45
 MG_FLAG_AUTORESET = 1
 MG_FLAG_STREAM_OBS = 2

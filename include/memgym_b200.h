@@ -63,7 +63,7 @@ extern "C" {
 #define MG_MM_STATE_BYTES 256      /* one env record (Mortar Mayhem family) */
 #define MG_MP_STATE_BYTES 128      /* one env record (Mystery Path) */
 #define MG_SS_STATE_BYTES 1152     /* one env record (Searing Spotlights) */
-#define MG_EP_STATE_BYTES 3072     /* one env record (Endless Mystery Path): 2048 + the 1024-byte look-ahead block */
+#define MG_EP_STATE_BYTES 4096     /* one env record (Endless Mystery Path): 2048 + the 2048-byte look-ahead block */
 #define MG_EP_MAX_SEGMENTS 45      /* capacity of the per-env path: 45 segments x 8 columns = 360 columns */
 
 #define MG_EINVAL (-1)  /* bad argument / unsupported option value */

@@ -1,0 +1,33 @@
+"""Endless-MysteryPath single-step launches (env.step): time per step and how many auto-resets adopt a path generated
+ahead. Usage: python scripts/emp_step_stats.py [n] [steps]"""
+import sys
+import os
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "endless-memory-gym_b200"))
+import torch
+import memory_gym_b200 as mg
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 600
+dev = torch.device("cuda:0")
+env = mg.make("Endless-MysteryPath-v0", num_envs=n, device=dev)
+env.reset(seed=1)
+g = torch.Generator(device=dev).manual_seed(3)
+acts = torch.randint(0, 4, (T, n), generator=g, device=dev)
+for phase in ("cold (no chains yet)", "warm"):
+    spec0 = env.state[:, 2048:2064].clone().view(torch.int32)
+    dones = torch.zeros((), dtype=torch.int64, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for t in range(T):
+        _, _, d, _, _ = env.step(acts[t])
+        dones += d.sum()
+    e1.record()
+    torch.cuda.synchronize()
+    spec1 = env.state[:, 2048:2064].clone().view(torch.int32)
+    adopted = int((spec1[:, 2] - spec0[:, 2]).sum())
+    chains = int(((spec1[:, 1] >> 12) - (spec0[:, 1] >> 12)).sum())
+    ahead = ((spec1[:, 0] >> 4) - spec1[:, 1]) & 255
+    print(f"{phase}: {e0.elapsed_time(e1) * 1e3 / T:.1f} us per step (host loop included), resets={int(dones)} adopted={adopted} "
+          f"({adopted / max(1, int(dones)):.3f}) new chains={chains}; episodes ahead now: "
+          f"{[int((ahead == k).sum()) for k in range(9)]}", flush=True)

@@ -13,7 +13,7 @@ dev = torch.device("cuda:0")
 env_id = sys.argv[1] if len(sys.argv) > 1 else "MortarMayhem-v0"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 wpc = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-T = 64
+T = int(sys.argv[4]) if len(sys.argv) > 4 else 64
 
 
 def bw_refs():

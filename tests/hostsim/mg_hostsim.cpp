@@ -20,6 +20,7 @@ struct HostCtx {
     void stamp(int) {}
     void store16(MgVec16* p, const MgVec16& v, bool) { *p = v; }
     void atomic_or(uint32_t* p, uint32_t v) { *p |= v; }
+    void atomic_inc(uint32_t* p) { *p += 1; }
     uint32_t reduce_min(uint32_t v) { return v; }
     uint32_t reduce_or(uint32_t v) { return v; }
     uint32_t shfl(uint32_t v, int) { return v; }
@@ -49,14 +50,17 @@ constexpr size_t record_bytes() {
     return RecordBytes<P>::value;
 }
 
+int g_ep_resumed = 0;  // helper turns that resumed a parked search (test statistics)
+
 // one turn of the "helper lane" that owns `env` (mg_ep_lane_helper_loop, minus the polling)
-void ep_helper_turn(const uint8_t* cextra, uint8_t* state, int env, int max_new) {
+void ep_helper_turn(const uint8_t* cextra, uint8_t* state, int env, int max_new, int budget) {
     MgEPSpecRec* g = mg_ep_spec_of(state, env);
     const uint32_t h = g->hword;
     if (!mg_ep_chain_wants(g, h)) return;
+    if (g->resume.tag == h) g_ep_resumed++;
     uint16_t info[MG_MP_NODES];
     uint8_t list[MG_MP_NODES];
-    MgLaneMem m{info, list, 1, nullptr, 0u};
+    MgLaneMem m{info, list, 1, nullptr, 0u, budget};  // budget >= 0: the search stops after that many expansions
     HostCtx ctx;
     mg_ep_lane_work(ctx, g, h, reinterpret_cast<const MgGenCta*>(cextra)->sqrt_d2, m, max_new);
 }
@@ -83,7 +87,8 @@ int run_q(const typename P::K& k, const void* assets, void* state, MgKIO q, bool
     constexpr size_t kRecord = record_bytes<P>();
     // Endless Mystery Path rollouts: the kernel's helper warps generate the next episode's path ahead of the reset,
     // one env per lane (mg_ep_lane_work). Here ONE "helper lane" gets a turn after some of the steps and sometimes
-    // does a single segment only, so that adopted, resumed, stale and missing episodes all occur.
+    // does a single segment only or stops in the middle of a search (and resumes it at its next turn), so that adopted, resumed,
+    // stale and missing episodes all occur.
     constexpr bool kLaneHelper = std::is_same<P, EPPolicy>::value;
     if constexpr (kLaneHelper) {
         if (rollout && !getenv("MG_HOSTSIM_NO_HELPER")) P::set_helpers(wx, 0, 1, false, (uint8_t*)state);
@@ -130,7 +135,8 @@ int run_q(const typename P::K& k, const void* assets, void* state, MgKIO q, bool
             }
             P::logic(ctx, k, q, view, env, t, *st, a0, a1, job, fr, scratch);
             if constexpr (kLaneHelper) {
-                if (rollout && (env + t) % 3 != 0) ep_helper_turn(cx, (uint8_t*)state, env, (env + 2 * t) % 5 == 0 ? 1 : 2);
+                if (rollout && (env + t) % 3 != 0)
+                    ep_helper_turn(cx, (uint8_t*)state, env, (env + 2 * t) % 5 == 0 ? 1 : 2, (env * 7 + t) % 4 == 0 ? 3 + t % 9 : -1);
             }
             for (int fi = 0; fi < job.nframes; ++fi) {
                 uint8_t* dst = job.to_final[fi] ? q.io.final_obs + (size_t)env * MG_FRAME_BYTES
@@ -223,6 +229,7 @@ extern "C" int mgsim_ep(const mg_ep_params* p, const void* assets, void* state, 
     mg_ep_derive(p, &k);
     return run<EPPolicy>(k, assets, state, rng4, io, n, mode, 1);
 }
+extern "C" int mgsim_ep_resumed() { return g_ep_resumed; }
 extern "C" int mgsim_ep_rollout(const mg_ep_params* p, const void* assets, void* state, const mg_rollout_io* r, int n) {
     if (mg_ep_check_params(p)) return MG_EINVAL;
     MgEPK k;

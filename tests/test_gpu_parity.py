@@ -289,6 +289,43 @@ def test_emp_rollout_with_and_without_helper_warps(monkeypatch):
     assert int(outs[0][2].sum()) > 3 * n  # several episodes per env: the hand-over was exercised
 
 
+def test_emp_resets_adopt_paths_generated_ahead():
+    """Endless-MysteryPath: the helper warps keep a chain of episodes ahead of every env (MgEPSpecRec behind the
+    record: hword, tword, adopted). In steady state nearly every auto-reset adopts its path from there — in rollouts of
+    any launch length and in single-step launches (where a search stopped by the end of a launch is parked and
+    resumed by the next) — and the bytes equal the launches without helper warps (the test above, the step-loop tests)."""
+    n = 4096
+    env = mg.make("Endless-MysteryPath-v0", num_envs=n, device=DEV)
+    env.reset(seed=5)
+
+    def spec():
+        return env.state[:, 2048:2060].clone().view(torch.int32)
+
+    for K, launches in ((20, 24), (5, 60)):
+        acts = _random_actions(env, K, 7 + K)
+        ring = torch.zeros((min(K, 4), n, 84, 84, 3), dtype=torch.uint8, device=DEV)
+        rew = torch.zeros((K, n), dtype=torch.float64, device=DEV)
+        dn = torch.zeros((K, n), dtype=torch.bool, device=DEV)
+        for _ in range(launches // 2):
+            env.rollout(acts, ring, rew, dn)
+        before, resets = spec(), 0
+        for _ in range(launches):
+            env.rollout(acts, ring, rew, dn)
+            resets += int(dn.sum())
+        adopted = int((spec()[:, 2] - before[:, 2]).sum())
+        assert resets > n and adopted > 0.8 * resets, (K, resets, adopted)
+    acts = _random_actions(env, 120, 3)
+    before, resets = spec(), 0
+    for t in range(120):
+        _, _, d, _, _ = env.step(acts[t])
+        resets += int(d.sum())
+    after = spec()
+    adopted = int((after[:, 2] - before[:, 2]).sum())
+    assert resets > n and adopted > 0.95 * resets, (resets, adopted)
+    ahead = ((after[:, 0] >> 4) - after[:, 1]) & 255
+    assert int(ahead.max()) <= 8 and float((ahead >= 6).float().mean()) > 0.8  # the chains stay (nearly) full
+
+
 @pytest.mark.parametrize("env_id", ["SearingSpotlights-v0", "Endless-SearingSpotlights-v0", "MortarMayhem-v0",
                                     "Endless-MysteryPath-v0"])
 def test_rollout_final_obs_equals_step_loop(env_id):
