@@ -221,7 +221,8 @@ struct MgEPSpecRec {
     uint32_t adopted;   // statistics: resets of this env that adopted their path from here (team)
     uint32_t work_ns;   // statistics: duration of the helper lane's last turn for this env (device builds)
     MgRng base;         // the stream the chain's first episode starts from (team)
-    uint8_t pad0[8];
+    uint32_t missed_empty;  // statistics: resets that found no finished episode in the chain (team)
+    uint32_t missed_stale;  // statistics: resets whose stream was not the one the episode was generated from (team)
     MgEPSpecSlot slot[MG_EP_AHEAD];
     MgEPResume resume;  // the helper lane's search in progress (helper)
     uint8_t pad1[128];

@@ -261,15 +261,21 @@ MG_HD bool mg_ep_gspec_take(Ctx& c, MgEPState& s, MgEPWarpMem& wm) {
     static_assert(sizeof(MgRng) == 40 && offsetof(MgEPSpecSlot, after) == 40 && offsetof(MgEPSpecSlot, seg) == 80, "slot layout");
     MgEPSpecRec* const g = mg_ep_spec_of(wm.state, (int)c.shfl((uint32_t)wm.cur_env, 0));
     const uint32_t h = c.shfl(mg_vload_u32(&g->hword), 0), tword = c.shfl(mg_vload_u32(&g->tword), 0);
-    if ((h & 3u) == MG_CHAIN_IDLE || mg_chain_id(h) != mg_chain_id(tword)) return false;
-    if (((mg_chain_count(h) - mg_chain_consumed(tword)) & 255u) == 0u) return false;
+    if ((h & 3u) == MG_CHAIN_IDLE || mg_chain_id(h) != mg_chain_id(tword) ||
+        ((mg_chain_count(h) - mg_chain_consumed(tword)) & 255u) == 0u) {
+        if (c.lane == 0) c.atomic_inc(&g->missed_empty);
+        return false;
+    }
     MgEPSpecSlot* const sl = &g->slot[mg_chain_consumed(tword) % MG_EP_AHEAD];
     c.fence_device();  // the helper's data is visible after its count
     const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>(sl);
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(&s.rng);
     uint32_t differs = 0;
     for (int w = c.lane; w < 10; w += c.nl) differs |= src[w] != mine[w] ? 1u : 0u;  // slot.before == stream?
-    if (c.reduce_or(differs)) return false;
+    if (c.reduce_or(differs)) {
+        if (c.lane == 0) c.atomic_inc(&g->missed_stale);
+        return false;
+    }
     c.sync();
     uint32_t* rng = reinterpret_cast<uint32_t*>(&s.rng);
     uint32_t* seg = reinterpret_cast<uint32_t*>(s.seg);
@@ -405,7 +411,10 @@ MG_HD void mg_ep_lane_work(Ctx& c, MgEPSpecRec* g, uint32_t h, const double* sqr
 
 // Helper warp of a rollout launch. Lane `first` of the launch's `step` helper lanes owns envs first, first + step, ...
 // (consecutive envs sit on the lanes of one warp: they are visited, and consume, at about the same time). ONE segment
-// per turn: lanes whose chain got room meanwhile join at the next segment boundary.
+// per turn: lanes whose chain got room meanwhile join at the next segment boundary, so that the walls of a segment are
+// drawn by all lanes together and the searches run in step. (Turns of 16 node expansions with lanes joining at every
+// turn were measured too: 204 instead of 229 M env-steps/s — every turn then pays the wall phase of the few lanes
+// that begin, profiles/r02_emp_lookahead.md.)
 template <class Ctx>
 MG_HD void mg_ep_lane_helper_loop(Ctx& c, uint8_t* state, int n, int first, int step, const uint32_t* teams_done,
                                   int stop_at, const double* sqrt_d2, const MgLaneMem& m) {

@@ -2,7 +2,7 @@
 lane's turn takes, and the rollout throughput, per launch length. Usage: python scripts/emp_lookahead_stats.py [n]"""
 import sys
 import os
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "endless-memory-gym_b200"))
+sys.path.insert(0, os.environ.get("MG_PKG_DIR") or os.path.join(os.path.dirname(__file__), "..", "endless-memory-gym_b200"))
 import torch
 import memory_gym_b200 as mg
 

@@ -2,7 +2,7 @@
 ahead. Usage: python scripts/emp_step_stats.py [n] [steps]"""
 import sys
 import os
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "endless-memory-gym_b200"))
+sys.path.insert(0, os.environ.get("MG_PKG_DIR") or os.path.join(os.path.dirname(__file__), "..", "endless-memory-gym_b200"))
 import torch
 import memory_gym_b200 as mg
 
@@ -14,7 +14,7 @@ env.reset(seed=1)
 g = torch.Generator(device=dev).manual_seed(3)
 acts = torch.randint(0, 4, (T, n), generator=g, device=dev)
 for phase in ("cold (no chains yet)", "warm"):
-    spec0 = env.state[:, 2048:2064].clone().view(torch.int32)
+    spec0 = env.state[:, 2048:2112].clone().view(torch.int32)
     dones = torch.zeros((), dtype=torch.int64, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -24,10 +24,11 @@ for phase in ("cold (no chains yet)", "warm"):
         dones += d.sum()
     e1.record()
     torch.cuda.synchronize()
-    spec1 = env.state[:, 2048:2064].clone().view(torch.int32)
+    spec1 = env.state[:, 2048:2112].clone().view(torch.int32)
     adopted = int((spec1[:, 2] - spec0[:, 2]).sum())
     chains = int(((spec1[:, 1] >> 12) - (spec0[:, 1] >> 12)).sum())
     ahead = ((spec1[:, 0] >> 4) - spec1[:, 1]) & 255
     print(f"{phase}: {e0.elapsed_time(e1) * 1e3 / T:.1f} us per step (host loop included), resets={int(dones)} adopted={adopted} "
-          f"({adopted / max(1, int(dones)):.3f}) new chains={chains}; episodes ahead now: "
+          f"({adopted / max(1, int(dones)):.3f}) new chains={chains} missed: empty {int((spec1[:, 14] - spec0[:, 14]).sum())} "
+          f"stale {int((spec1[:, 15] - spec0[:, 15]).sum())}; episodes ahead now: "
           f"{[int((ahead == k).sum()) for k in range(9)]}", flush=True)

@@ -293,8 +293,10 @@ def test_emp_resets_adopt_paths_generated_ahead():
     """Endless-MysteryPath: the helper warps keep a chain of episodes ahead of every env (MgEPSpecRec behind the
     record: hword, tword, adopted). In steady state nearly every auto-reset adopts its path from there — in rollouts of
     any launch length and in single-step launches (where a search stopped by the end of a launch is parked and
-    resumed by the next) — and the bytes equal the launches without helper warps (the test above, the step-loop tests)."""
-    n = 4096
+    resumed by the next) — and the bytes equal the launches without helper warps (the test above, the step-loop tests).
+    (One helper lane per env produces an episode in ~300 us: batches of fewer than ~8192 envs per GPU step an env more
+    often than that and adopt less — 63 % at 4096 envs.)"""
+    n = 8192
     env = mg.make("Endless-MysteryPath-v0", num_envs=n, device=DEV)
     env.reset(seed=5)
 
