@@ -6,7 +6,8 @@
 A "step" is one pass of the hot path over the whole env batch: kinematics + state machine + in-kernel
 auto-reset + raster of N x 84x84x3 uint8 observations. Headline workload = BASELINE.json configs[1]:
 MortarMayhem-v0, 4096 envs per GPU, default options, seeds 0..N-1, i.i.d. uniform random actions
-(pre-generated on the device), auto-reset on. The timed launch is one `mg_*_rollout` of K steps (the
+(pre-generated on the device: a pool of up to 8 distinct K-step blocks, cycled, small enough to stay in L2 like
+actions a policy has just written), auto-reset on. The timed launch is one `mg_*_rollout` of K steps (the
 reference's bench.py loop shape: pre-sampled random actions, reset when done); the timed region is R such
 launches back to back (R sized for >= 200 ms, `config.timed_launches`), entered behind launches that are
 already running so that no host latency sits between the two events. Every rank warms up the same way.
@@ -219,14 +220,26 @@ class Timed:
         self.launches_per_block = -(-K // self.L)  # launches that make up K steps
         self.n_act = len(self.spec.action_nvec)
         g = torch.Generator(device=dev).manual_seed(1234 + rank)
-        self.acts = torch.randint(0, self.spec.action_nvec[0], (self.L,) + tuple(self.env._actions_dev.shape),
+        # uniform random actions: a pool of distinct action blocks, cycled (ONE 20-step block replayed launch after launch
+        # makes every env repeat the same 20 actions for ever)
+        self.pool = torch.randint(0, self.spec.action_nvec[0], (self.n_blocks(),) + (self.L,) + tuple(self.env._actions_dev.shape),
                                   generator=g, device=dev)
+        self.acts = self.pool[0]
+        self.blk = 0
         # obs go to a [L, N, 84, 84, 3] rollout buffer (step t of a launch -> slot t): every frame of a launch has
         # its own address and the buffer is far larger than the 126 MB L2, so every frame reaches HBM
         self.ring = torch.empty((self.L, n, 84, 84, 3), dtype=torch.uint8, device=dev)
         self.rew = torch.empty((self.L, n), dtype=torch.float64, device=dev)
         self.done = torch.empty((self.L, n), dtype=torch.bool, device=dev)
         self.env.reset(seed=0)
+
+    ACTION_BLOCKS = 0  # --action-blocks: 0 = up to 8 distinct blocks within ACTION_POOL_BYTES
+    ACTION_POOL_BYTES = 12 << 20  # the pool stays L2-resident, like actions a policy has just written (a 21 MB pool is
+                                  # evicted by the 1.7 GB of frames of every launch: -3.5 % for MortarMayhem, measured)
+
+    def n_blocks(self):
+        block_bytes = self.L * self.n * self.n_act * 8
+        return Timed.ACTION_BLOCKS or max(1, min(8, Timed.ACTION_POOL_BYTES // block_bytes))
 
     def barrier(self):
         if self.dist is not None:
@@ -239,7 +252,8 @@ class Timed:
         left = self.K
         while left > 0:
             c = min(left, self.L)
-            fn(self.acts[:c], self.ring[:c], self.rew[:c], self.done[:c])
+            fn(self.pool[self.blk % self.pool.shape[0]][:c], self.ring[:c], self.rew[:c], self.done[:c])
+            self.blk += 1
             left -= c
 
     def measure(self, many=False, on_start=None):
@@ -282,13 +296,34 @@ class Timed:
         ms, per_rank = gather_ms(self.dist, self.dev, e0.elapsed_time(e1))
         return ms, per_rank, R
 
+    def lookahead_counters(self):
+        """Endless-MysteryPath: the statistics words of the look-ahead block behind every record (MgEPSpecRec): resets
+        that adopted a path generated ahead, resets that found none ready / a stale one. None for other env types."""
+        if self.spec.family != "ep":
+            return None
+        w = self.env.state[:, 2048:2112].clone().view(self.torch.int32)
+        return [int(w[:, 2].sum()), int(w[:, 14].sum()), int(w[:, 15].sum())]
+
+    @staticmethod
+    def lookahead_delta(a, b):
+        if a is None:
+            return None
+        adopted, empty, stale = (y - x for x, y in zip(a, b))
+        tot = max(1, adopted + empty + stale)
+        return {"resets": adopted + empty + stale, "adopted": adopted, "adopted_frac": adopted / tot, "missed_empty": empty,
+                "missed_stale": stale}
+
     def b_alg(self, steps_per_launch):
         return alg_bytes_per_env_step(self.spec.family, self.n_act, steps_per_launch)
 
     def report(self, peak, traffic_tab, on_start=None):
         """rollout + single-step figures of this config as the dicts the JSON line carries."""
+        c0 = self.lookahead_counters()
         ms, per_rank, R = self.measure(False, on_start)
+        c1 = self.lookahead_counters()
+        done_rate = float(self.done.float().mean())  # auto-resets per env-step in the last timed launch
         ms_s, per_rank_s, R_s = self.measure(True)
+        c2 = self.lookahead_counters()
         K, n = self.K, self.n
         steps = K * R
         b = self.b_alg(self.L)
@@ -314,7 +349,10 @@ class Timed:
         long_run = self.long_launches(peak)
         return {"value": self.total * steps / (ms * 1e-3) / 1e6, "ms": ms, "ms_per_step": ms / steps, "per_rank_ms": per_rank,
                 "timed_launches": R * self.launches_per_block, "timed_steps": steps, "roofline": roof, "single_step": single,
-                "long_launches": long_run}
+                "long_launches": long_run, "resets_per_env_step": done_rate,
+                "lookahead": None if c0 is None else {"rollout": self.lookahead_delta(c0, c1), "single_step": self.lookahead_delta(c1, c2),
+                                                      "note": "Endless-MysteryPath: auto-resets (warm-up included) that adopted a "
+                                                              "path generated ahead by the helper warps"}}
 
     def long_launches(self, peak, steps_per_launch=128):
         """The same rollout with `steps_per_launch` steps per launch (the shape round 1 reported): what the kernel sustains
@@ -324,13 +362,14 @@ class Timed:
         if self.K >= steps_per_launch:
             return None
         K0, L0, lpb0 = self.K, self.L, self.launches_per_block
-        keep = (self.acts, self.ring, self.rew, self.done)
+        keep = (self.acts, self.ring, self.rew, self.done, self.pool)
         try:
             self.K = self.L = steps_per_launch
             self.launches_per_block = 1
             g = torch.Generator(device=self.dev).manual_seed(4321 + self.rank)
-            self.acts = torch.randint(0, self.spec.action_nvec[0], (self.L,) + tuple(self.env._actions_dev.shape),
+            self.pool = torch.randint(0, self.spec.action_nvec[0], (self.n_blocks(),) + (self.L,) + tuple(self.env._actions_dev.shape),
                                       generator=g, device=self.dev)
+            self.acts = self.pool[0]
             self.ring = torch.empty((self.L, self.n, 84, 84, 3), dtype=torch.uint8, device=self.dev)
             self.rew = torch.empty((self.L, self.n), dtype=torch.float64, device=self.dev)
             self.done = torch.empty((self.L, self.n), dtype=torch.bool, device=self.dev)
@@ -342,7 +381,7 @@ class Timed:
                     "unit": "M env-steps/s", "frac": achieved / peak[0], "per_rank_ms": per_rank}
         finally:
             self.K, self.L, self.launches_per_block = K0, L0, lpb0
-            self.acts, self.ring, self.rew, self.done = keep
+            self.acts, self.ring, self.rew, self.done, self.pool = keep
 
 
 def shard_check(mg, torch, dist, dev, rank, world, env_id="MortarMayhem-v0", n_chk=256, T=64, sample=32):
@@ -404,8 +443,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--action-blocks", type=int, default=0, help="distinct blocks of random actions the launches cycle through "
+                    "(0: up to 8 blocks within 12 MB; 1: replay one block, the round-1 behaviour)")
     ap.add_argument("--no-configs", action="store_true", help="headline workload only (skip the other BASELINE configs)")
     args = ap.parse_args()
+    Timed.ACTION_BLOCKS = max(0, args.action_blocks)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -591,7 +633,9 @@ def main():
                                         "seeds 0..N-1, uniform random actions, auto-reset on",
                             "value": r["value"], "unit": "M env-steps/s", "ms_per_step": r["ms_per_step"],
                             "timed_launches": r["timed_launches"], "per_rank_ms": r["per_rank_ms"],
-                            "roofline": r["roofline"], "single_step": r["single_step"], "long_launches": r["long_launches"]})
+                            "roofline": r["roofline"], "single_step": r["single_step"], "long_launches": r["long_launches"],
+                            "resets_per_env_step": r["resets_per_env_step"],
+                            **({"lookahead": r["lookahead"]} if r["lookahead"] else {})})
             del c
             torch.cuda.empty_cache()
 
@@ -653,6 +697,8 @@ def main():
                                                      "bytes over PCIe, no copy operation between two step launches)"}},
             "single_step": head["single_step"],
             "long_launches": head["long_launches"],
+            "resets_per_env_step": head["resets_per_env_step"],
+            **({"lookahead": head["lookahead"]} if head["lookahead"] else {}),
             "gpu_launches": head["timed_launches"],
             "roofline": head["roofline"],
             "configs": configs,

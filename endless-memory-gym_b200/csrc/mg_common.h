@@ -215,9 +215,9 @@ struct MgEPResume {      // a segment's noisy A* stopped at the end of a launch 
     uint8_t pad1[48];
 };
 struct MgEPSpecRec {
-    uint32_t hword;     // chain << 12 | episodes produced (mod 256) << 4 | segments of the next one << 2 | MG_CHAIN_*;
+    uint32_t hword;     // chain << 13 | MG_CHAIN_FRESH | episodes produced (mod 256) << 4 | segments of the next one << 2 | MG_CHAIN_*;
                         // advanced by the helper lane with CAS only, rewritten by the team when it starts a new chain
-    uint32_t tword;     // chain << 12 | episodes consumed (mod 256); written by the team only
+    uint32_t tword;     // chain << 13 | episodes consumed (mod 256); written by the team only
     uint32_t adopted;   // statistics: resets of this env that adopted their path from here (team)
     uint32_t work_ns;   // statistics: duration of the helper lane's last turn for this env (device builds)
     MgRng base;         // the stream the chain's first episode starts from (team)

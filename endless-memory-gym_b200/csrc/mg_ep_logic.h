@@ -111,7 +111,8 @@ MG_HD bool mg_ep_prev(const MgEPState& s, int x, int y, int& px, int& py) {
 //           MG_EP_AHEAD] while produced - consumed < MG_EP_AHEAD; writes the data first, then advances hword by CAS:
 //           a chain the team has replaced meanwhile makes the CAS fail and the data is never looked at
 enum { MG_CHAIN_IDLE = 0, MG_CHAIN_ACTIVE = 1, MG_CHAIN_FAILED = 3 };
-MG_HD uint32_t mg_chain_id(uint32_t w) { return w >> 12; }
+#define MG_CHAIN_FRESH (1u << 12)  // hword: no episode of this chain is complete yet (the first one starts from `base`)
+MG_HD uint32_t mg_chain_id(uint32_t w) { return w >> 13; }
 MG_HD uint32_t mg_chain_count(uint32_t w) { return (w >> 4) & 255u; }   // hword: produced
 MG_HD uint32_t mg_chain_nseg(uint32_t w) { return (w >> 2) & 3u; }
 MG_HD uint32_t mg_chain_consumed(uint32_t t) { return t & 255u; }        // tword
@@ -300,11 +301,11 @@ MG_HD bool mg_ep_gspec_take(Ctx& c, MgEPState& s, MgEPWarpMem& wm) {
 // Owner side (one thread): start a new chain from `stream` (what was generated ahead is stale or missing)
 template <class Ctx>
 MG_HD void mg_ep_chain_start(Ctx& c, MgEPSpecRec* g, const MgRng& stream) {
-    const uint32_t chain = (mg_chain_id(mg_vload_u32(&g->tword)) + 1u) & 0xFFFFFu;
+    const uint32_t chain = (mg_chain_id(mg_vload_u32(&g->tword)) + 1u) & 0x7FFFFu;
     mg_ep_stream_put(g->base, stream);
-    mg_vstore_u32(&g->tword, chain << 12);
+    mg_vstore_u32(&g->tword, chain << 13);
     c.fence_device();
-    mg_vstore_u32(&g->hword, (chain << 12) | MG_CHAIN_ACTIVE);
+    mg_vstore_u32(&g->hword, (chain << 13) | MG_CHAIN_FRESH | MG_CHAIN_ACTIVE);
 }
 // Team side: ... from the env's stream as it is now
 template <class Ctx>
@@ -359,7 +360,7 @@ MG_HD void mg_ep_lane_work(Ctx& c, MgEPSpecRec* g, uint32_t h, const double* sqr
         } else {
             // the stream to continue from: the slot's own progress, else what the previous episode (or the chain's base) ends with
             const volatile MgRng& from =
-                nseg > 0 ? sl->after : (produced == 0 ? g->base : g->slot[(produced + MG_EP_AHEAD - 1u) % MG_EP_AHEAD].after);
+                nseg > 0 ? sl->after : ((h & MG_CHAIN_FRESH) ? g->base : g->slot[(produced + MG_EP_AHEAD - 1u) % MG_EP_AHEAD].after);
             r.lo = from.state_lo, r.hi = from.state_hi, r.ilo = from.inc_lo, r.ihi = from.inc_hi, r.buf = from.buf, r.has = from.has_buf;
             if (nseg == 0) {
                 volatile MgRng& b = sl->before;
@@ -401,7 +402,7 @@ MG_HD void mg_ep_lane_work(Ctx& c, MgEPSpecRec* g, uint32_t h, const double* sqr
             a.state_lo = r.lo, a.state_hi = r.hi, a.inc_lo = r.ilo, a.inc_hi = r.ihi, a.buf = r.buf, a.has_buf = r.has;
             c.fence_device();
             next = nseg < 2 ? (h & ~(3u << 2)) | ((uint32_t)(nseg + 1) << 2)
-                            : (h & ~0xFFCu) | (((produced + 1u) & 255u) << 4);  // the episode is complete
+                            : (h & ~(0xFFCu | MG_CHAIN_FRESH)) | (((produced + 1u) & 255u) << 4);  // the episode is complete
         }
         if (c.cas_u32(&g->hword, h, next) != h) return;  // the team has started another chain meanwhile
         if (!mask) return;
@@ -421,7 +422,8 @@ MG_HD void mg_ep_lane_helper_loop(Ctx& c, uint8_t* state, int n, int first, int 
     const int count = first < n ? (n - first + step - 1) / step : 0;
     int rot = 0;
     for (;;) {
-        if (mg_vload_u32(teams_done) >= (uint32_t)stop_at) return;  // the launch is over: the chains wait
+        // the launch is over: the chains wait (m.not_before only keeps a search that is under way going a little longer)
+        if (mg_vload_u32(teams_done) >= (uint32_t)stop_at) return;
         MgEPSpecRec* g = nullptr;
         uint32_t h = 0;
         for (int i = 0; i < count && !g; ++i) {

@@ -194,6 +194,14 @@ __host__ __device__ constexpr int mg_record_bytes() {
     return MgRecordBytes<P>::value;
 }
 
+// Single-step launches: a path search that is under way when the env teams are done goes on until the launch is this
+// old (or the segment is finished). Without it a fast launch leaves the helper lanes ~30 us, the slowest searches fall
+// behind their envs and one reset per launch finds its chain empty — the whole launch then waits ~60 us for one
+// cooperative generation (env.step() loop, 8192 envs: 117 us per step without, 87 us with; profiles/r02_emp_lookahead.md)
+#ifndef MG_EP_STEP_HELPER_NS
+#define MG_EP_STEP_HELPER_NS 40000
+#endif
+
 // ---- the kernel ----------------------------------------------------------------------------------
 // A "team" = the threads that own one env at a time: one warp, or P::kTeamWarps warps on a named barrier for
 // env types whose per-frame work is instruction-bound (more warps per frame buffer hide more latency).
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(P::kMaxThreads, 1)
             const int hidx = team - nteams, nlane = q.n_lane_helpers;
             if (hidx < nlane)
                 P::helper_loop(hctx, cextra, nteams, hidx, nlane, (int)blockIdx.x, (int)gridDim.x, &hdr->teams_done,
-                               kRollout ? nteams : 1, state, q.n);
+                               kRollout ? nteams : 1, kRollout ? 0u : (uint32_t)MG_EP_STEP_HELPER_NS, state, q.n);
             else if constexpr (!kRollout)
                 P::helper_loop_step(hctx, cextra, wextra0, nteams, hidx - nlane, &hdr->teams_done, state, q.io.ground_truth);
             return;

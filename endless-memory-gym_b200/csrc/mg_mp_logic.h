@@ -277,7 +277,21 @@ struct MgLaneMem {
     const volatile uint32_t* stop;  // optional: stop as soon as *stop >= stop_at (the launch is ending)
     uint32_t stop_at;
     int budget;      // node expansions this call may do before it stops (< 0: no limit; the CPU tests stop mid-search)
+    uint64_t not_before;  // ... but not before this time (mg_lane_now_ns; 0: no such limit)
 };
+// the device's nanosecond timer (the CPU harness has no notion of a launch that ends)
+MG_HD uint64_t mg_lane_now_ns() {
+#if defined(__CUDA_ARCH__)
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#else
+    return ~0ull;
+#endif
+}
+MG_HD bool mg_lane_must_stop(const MgLaneMem& m) {
+    return m.stop && *m.stop >= m.stop_at && (m.not_before == 0 || mg_lane_now_ns() >= m.not_before);
+}
 #define MG_LANE_NOPREV 63u
 // the cells within one step (8-neighbourhood) of a set of cells, the set included
 MG_HD uint64_t mg_mp_dilate8(uint64_t w) {
@@ -388,7 +402,7 @@ MG_HD uint64_t mg_mp_generate_lane(MgRngR& r, int sx, int sy, int ex, int ey, co
     MG_NOUNROLL
     for (;;) {
         if (nopen == 0) return 0;
-        if ((m.stop && *m.stop >= m.stop_at) || budget-- == 0) {
+        if (mg_lane_must_stop(m) || budget-- == 0) {
             st.wall = wall, st.open = open, st.closed = closed, st.nopen = nopen;
             stopped = true;
             return 0;

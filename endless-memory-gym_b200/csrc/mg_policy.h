@@ -306,7 +306,7 @@ struct EPPolicy {
     // rollout helper warp `hidx` of `nhelp` in CTA `cta` of `nctas`: one env per lane
     template <class Ctx>
     static MG_HD void helper_loop(Ctx& c, uint8_t* cextra, int nteams, int hidx, int nhelp, int cta, int nctas,
-                                  const uint32_t* teams_done, int stop_at, uint8_t* state, int n) {
+                                  const uint32_t* teams_done, int stop_at, uint32_t min_ns, uint8_t* state, int n) {
         uint8_t* mine = cextra + kGenCtaBytes + (size_t)hidx * MG_EP_LANE_WARP_BYTES;
         MgLaneMem m;
         m.info = reinterpret_cast<uint16_t*>(mine) + c.lane;
@@ -315,6 +315,7 @@ struct EPPolicy {
         m.stop = teams_done;
         m.stop_at = (uint32_t)stop_at;  // rollouts: every team has left; single steps: the first has (parking overlaps the rest)
         m.budget = -1;
+        m.not_before = min_ns ? c.now_ns() + min_ns : 0;
         mg_ep_lane_helper_loop(c, state, n, (cta * nhelp + hidx) * 32 + c.lane, nctas * nhelp * 32, teams_done, stop_at,
                                reinterpret_cast<const MgGenCta*>(cextra)->sqrt_d2, m);
     }

@@ -32,7 +32,7 @@ for K in (5, 20, 128):
     ms = e0.elapsed_time(e1)
     spec1 = env.state[:, 2048:2064].clone().view(torch.int32)
     adopted = int((spec1[:, 2] - spec0[:, 2]).sum())
-    tickets = int(((spec1[:, 1] >> 12) - (spec0[:, 1] >> 12)).sum())
+    tickets = int(((spec1[:, 1] >> 13) - (spec0[:, 1] >> 13)).sum())
     work = spec1[:, 3].float()
     print(f"K={K:4d} launches={launches} {n * K * launches / ms / 1e3:7.1f} M env-steps/s  resets={int(dones)} adopted={adopted} "
           f"({adopted / max(1, int(dones)):.3f}) new chains={tickets} helper turn us: median {work.median().item() / 1e3:.0f} "

@@ -60,7 +60,7 @@ void ep_helper_turn(const uint8_t* cextra, uint8_t* state, int env, int max_new,
     if (g->resume.tag == h) g_ep_resumed++;
     uint16_t info[MG_MP_NODES];
     uint8_t list[MG_MP_NODES];
-    MgLaneMem m{info, list, 1, nullptr, 0u, budget};  // budget >= 0: the search stops after that many expansions
+    MgLaneMem m{info, list, 1, nullptr, 0u, budget, 0};  // budget >= 0: the search stops after that many expansions
     HostCtx ctx;
     mg_ep_lane_work(ctx, g, h, reinterpret_cast<const MgGenCta*>(cextra)->sqrt_d2, m, max_new);
 }

@@ -115,6 +115,34 @@ def test_rollout_equals_step_loop_hostsim(env_id, opts, backend):
         # the rollout's resets adopted paths generated ahead by the "helper lane" (MgEPSpecRec: hword, tword, adopted),
         # the step loop generated all of its paths inline: same bytes either way
         words = a.state[:, 2048:2060].contiguous().view(torch.int32)
-        assert (words[:, 2] >= 2).all() and ((words[:, 0] >> 12) >= 1).all()
+        assert (words[:, 2] >= 2).all() and ((words[:, 0] >> 13) >= 1).all()
         assert backend.sim.mgsim_ep_resumed() > 10  # searches stopped mid-way were parked and resumed
         assert (b.state[:, 2048:] == 0).all()
+
+
+def test_emp_lookahead_chain_outlives_its_counters_hostsim(backend):
+    """Endless-MysteryPath: a look-ahead chain lives for hundreds of episodes, its produced / consumed counters are
+    8 bits wide. Past the wrap the helper must still continue from the previous episode's stream (not from the chain's
+    base): no reset may ever find an episode generated from another stream, and the bytes stay those of the step loop."""
+    import numpy as np
+    import torch
+    import memory_gym_b200 as mg
+    env_id, n, T = "Endless-MysteryPath-v0", 2, 9000
+    a = mg.MemoryGymVecEnv(env_id, n, device="cpu", _backend=backend)
+    b = mg.MemoryGymVecEnv(env_id, n, device="cpu", _backend=backend)
+    acts = torch.as_tensor(np.random.default_rng(5).integers(0, 4, (T, n)))
+    a.reset(seed=3)
+    b.reset(seed=3)
+    ring = torch.zeros((4, n, 84, 84, 3), dtype=torch.uint8)
+    rew, dn = torch.zeros((T, n), dtype=torch.float64), torch.zeros((T, n), dtype=torch.bool)
+    inf = torch.zeros((T, n, mg._lib.MG_INFO_COLS), dtype=torch.float64)
+    a.rollout(acts, ring, rew, dn, inf)
+    for t in range(T):
+        o, r, d, _, info = b.step(acts[t])
+        assert torch.equal(r, rew[t]) and torch.equal(d, dn[t]), t
+        assert torch.equal(info["episode"][d], inf[t][d]), t
+    assert torch.equal(o, ring[(T - 1) % 4]) and torch.equal(a.records, b.records)
+    words = a.state[:, 2048:2112].contiguous().view(torch.int32)
+    assert (dn.sum(0) > 280).all()                  # more episodes per env than the counters can count
+    assert (words[:, 2] > 256).all()                # ... most of them adopted from ONE long-lived chain
+    assert (words[:, 15] == 0).all(), words[:, 12:16]  # missed_stale: never an episode from the wrong stream
