@@ -346,7 +346,8 @@ MG_HD void mg_ep_lane_work(Ctx& c, MgEPSpecRec* g, uint32_t h, const double* sqr
         MgRngR r;
         MgLaneSearch st;
         int sy, ey;
-        const bool resume = *reinterpret_cast<const volatile uint32_t*>(&rs.tag) == h;
+        // (nopen: a record that was never zero-initialised must not send the search outside its scratch)
+        const bool resume = *reinterpret_cast<const volatile uint32_t*>(&rs.tag) == h && rs.nopen <= MG_MP_NODES;
         if (resume) {
             // this very segment's search was stopped by the end of an earlier launch: carry on where it stopped
             const volatile MgRng& inc = g->base;

@@ -288,6 +288,9 @@ int mg_selftest_pcg64_host(uint64_t* state4, uint32_t* has_buf2, const int64_t* 
 
 /* ---- environment entry points ------------------------------------------------------------------ */
 /* state: device, n * MG_*_STATE_BYTES bytes, opaque to the caller (zero-initialise once = "make").
+ *        Endless Mystery Path: the second half of a record (MG_EP_STATE_BYTES = 2048 + 2048) holds the paths of the
+ *        env's next episodes, generated ahead of their resets by helper warps of the step / rollout launches; a reset
+ *        adopts one only if the env's stream is the stream it was generated from, so results never depend on it.
  * rng4:  device, nullable: [n][4] uint64 from mg_seed_pcg64; where given (and selected by
  *        reset_mask) the env's PCG64 stream is re-seeded before the reset draws, exactly like
  *        `env.reset(seed=s)`; NULL continues each env's stream like `env.reset()`. */

@@ -289,6 +289,34 @@ def test_emp_rollout_with_and_without_helper_warps(monkeypatch):
     assert int(outs[0][2].sum()) > 3 * n  # several episodes per env: the hand-over was exercised
 
 
+def test_emp_results_do_not_depend_on_the_lookahead_block():
+    """The second half of an Endless-MysteryPath record (the episodes generated ahead) is a cache: a reset adopts an
+    episode only if its stream matches. Overwriting that half with random bytes — chains that claim to be active, parked
+    searches, counters — must change nothing but the adoption statistics."""
+    n, K = 3000, 40
+    outs = []
+    for scramble in (False, True):
+        env = mg.make("Endless-MysteryPath-v0", num_envs=n, device=DEV)
+        env.reset(seed=21)
+        acts = _random_actions(env, K, 9)
+        ring = torch.zeros((K, n, 84, 84, 3), dtype=torch.uint8, device=DEV)
+        rew = torch.zeros((K, n), dtype=torch.float64, device=DEV)
+        dn = torch.zeros((K, n), dtype=torch.bool, device=DEV)
+        g = torch.Generator(device=DEV).manual_seed(77)
+        for launch in range(4):
+            if scramble and launch in (0, 2):
+                env.state[:, 2048:] = torch.randint(0, 256, (n, 2048), generator=g, device=DEV, dtype=torch.uint8)
+            env.rollout(acts, ring, rew, dn)
+        for t in range(6):
+            if scramble and t == 2:
+                env.state[:, 2048:] = torch.randint(0, 256, (n, 2048), generator=g, device=DEV, dtype=torch.uint8)
+            o, r, d, _, _ = env.step(acts[t])
+        torch.cuda.synchronize()
+        outs.append((ring.clone(), rew.clone(), dn.clone(), o.clone(), r.clone(), env.records.clone()))
+    assert all(torch.equal(x, y) for x, y in zip(*outs))
+    assert int(outs[0][2].sum()) > n
+
+
 def test_emp_resets_adopt_paths_generated_ahead():
     """Endless-MysteryPath: the helper warps keep a chain of episodes ahead of every env (MgEPSpecRec behind the
     record: hword, tword, adopted). In steady state nearly every auto-reset adopts its path from there — in rollouts of
