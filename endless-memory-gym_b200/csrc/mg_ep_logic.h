@@ -258,7 +258,7 @@ MG_HD MgEPSpecSlot* mg_ep_chain_head(MgEPSpecRec* g, uint32_t& tword) {
 // Team side, at a reset: true if the three segments were adopted from the env's chain. The slot is read as 50
 // independent words spread over the lanes (a chain of dependent global loads would cost the team ~1 us each).
 template <class Ctx>
-MG_HD bool mg_ep_gspec_take(Ctx& c, MgEPState& s, MgEPWarpMem& wm) {
+MG_HD bool mg_ep_chain_take(Ctx& c, MgEPState& s, MgEPWarpMem& wm) {
     static_assert(sizeof(MgRng) == 40 && offsetof(MgEPSpecSlot, after) == 40 && offsetof(MgEPSpecSlot, seg) == 80, "slot layout");
     MgEPSpecRec* const g = mg_ep_spec_of(wm.state, (int)c.shfl((uint32_t)wm.cur_env, 0));
     const uint32_t h = c.shfl(mg_vload_u32(&g->hword), 0), tword = c.shfl(mg_vload_u32(&g->tword), 0);
@@ -309,20 +309,20 @@ MG_HD void mg_ep_chain_start(Ctx& c, MgEPSpecRec* g, const MgRng& stream) {
 }
 // Team side: ... from the env's stream as it is now
 template <class Ctx>
-MG_HD void mg_ep_gspec_post(Ctx& c, const MgEPState& s, MgEPWarpMem& wm) {
+MG_HD void mg_ep_chain_restart(Ctx& c, const MgEPState& s, MgEPWarpMem& wm) {
     if (c.lane == 0) mg_ep_chain_start(c, mg_ep_spec_of(wm.state, wm.cur_env), s.rng);
 }
 
 // Team side, when it takes an env over: a record without a chain (first rollout after construction), or whose chain
 // head was generated for another stream (a reset launch re-seeded the env), gets a new one
 template <class Ctx>
-MG_HD void mg_ep_gspec_sync(Ctx& c, const MgEPState& s, MgEPWarpMem& wm) {
+MG_HD void mg_ep_chain_check(Ctx& c, const MgEPState& s, MgEPWarpMem& wm) {
     if (c.lane != 0 || !s.live) return;
     MgEPSpecRec* const g = mg_ep_spec_of(wm.state, wm.cur_env);
     uint32_t tword;
     const MgEPSpecSlot* sl = mg_ep_chain_head(g, tword);
     const bool idle = (mg_vload_u32(&g->hword) & 3u) == MG_CHAIN_IDLE;
-    if (idle || (sl && !mg_ep_stream_eq(sl->before, s.rng))) mg_ep_gspec_post(c, s, wm);
+    if (idle || (sl && !mg_ep_stream_eq(sl->before, s.rng))) mg_ep_chain_restart(c, s, wm);
 }
 
 // Helper side, ONE LANE: does the chain of record g have room for another segment? (hword as read by the caller)
@@ -599,7 +599,7 @@ MG_HD void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, 
     }
     c.sync();
     // 1. the episode generated ahead, if the stream still is what it was generated from
-    const bool adopted = wm.ahead && mg_ep_gspec_take(c, s, wm);
+    const bool adopted = wm.ahead && mg_ep_chain_take(c, s, wm);
     // 2. single-step launches: the frame now, the path by a helper warp before the kernel ends
     // (an agent wider than a tile would show past-path tiles in its very first frame: those need the path)
     if (!adopted && wm.offload && k.radius < MG_MP_TILE && mg_ep_reset_offload(c, k, s, f, wm)) return;
@@ -633,7 +633,7 @@ MG_HD void mg_ep_reset_coop(Ctx& c, const MgEPK& k, MgEPState& s, MgEPFrame& f, 
         if (gt) mg_ep_ground_truth(s, gt);
     }
     c.sync();
-    if (wm.ahead && ok && !adopted) mg_ep_gspec_post(c, s, wm);  // (an adopted episode: its chain goes on)
+    if (wm.ahead && ok && !adopted) mg_ep_chain_restart(c, s, wm);  // (an adopted episode: its chain goes on)
     c.stamp(14);
 }
 

@@ -343,7 +343,7 @@ struct EPPolicy {
             capped = !mg_ep_add_segment_coop(c, s, m, *reinterpret_cast<const MgGenCta*>(sc.cta));
             // the stream has moved: what was generated ahead for the next reset is stale, ask again
             MgEPWarpMem& wm = *reinterpret_cast<MgEPWarpMem*>(sc.warp);
-            if (wm.ahead) mg_ep_gspec_post(c, s, wm);
+            if (wm.ahead) mg_ep_chain_restart(c, s, wm);
         }
         if (c.lane == 0) {
             double reward;
@@ -362,7 +362,7 @@ struct EPPolicy {
         if (c.lane == 0) {
             wm.cur_env = env;  // (read by lane 0 only)
             // rollouts: the team takes this env over for many steps (single steps leave a missing chain to the next reset)
-            if (t == 0 && wm.ahead && !wm.offload && q.n_steps > 1) mg_ep_gspec_sync(c, s, wm);
+            if (t == 0 && wm.ahead && !wm.offload && q.n_steps > 1) mg_ep_chain_check(c, s, wm);
         }
         mg_env_logic_coop<EPPolicy>(c, k, q, a, env, t, s, a0, a1, job, fr, sc);
     }
