@@ -101,10 +101,11 @@ MG_HD bool mg_ep_prev(const MgEPState& s, int x, int y, int& px, int& py) {
 // the oldest episode of this CHAIN if — and only if — the env's stream is what that episode was generated from
 // (bit-exact either way); otherwise it generates inline and starts a new chain from the stream it ends with.
 //
-// Rollout launches run HELPER WARPS next to the env teams (mg_kernels.cu) that extend the chains with ONE ENV PER
+// Step and rollout launches run HELPER WARPS next to the env teams (mg_kernels.cu) that extend the chains with ONE ENV PER
 // LANE (mg_mp_generate_lane): 32 paths per warp-instruction, where the cooperative generator of a reset keeps a
 // whole warp busy for ~60 us per episode. The chain lives in the MgEPSpecRec behind the record, in GLOBAL memory,
-// so it survives the launch; progress is published segment by segment.
+// so it survives the launch; progress is published segment by segment, and a search cut off by the end of a launch is
+// parked there too (MgEPResume). The counters are 8 bits wide and wrap; a chain lives for thousands of episodes.
 //   team    consumes: slot[consumed % MG_EP_AHEAD] when produced > consumed and slot.before == stream, consumed + 1;
 //           starts a new chain (base = stream, chain id + 1, counters 0) after an inline reset / a mid-episode segment
 //   helper  (each env has ONE helper lane per launch: no helper-helper races) produces into slot[produced %
