@@ -15,6 +15,9 @@
 // Stage layout (host, pinned, 16-byte aligned): n headers of MG_DELTA_HDR_BYTES = {uint32 count, uint32 mask[42],
 // pad}, then n payload regions of MG_OBS_BYTES (env e's changed chunks in ascending chunk order at the start of
 // region e). A pure transport code: every frame is rendered on the GPU; the host only copies bytes.
+//
+// mg_obs_delta_scatter goes one step further when the caller's host array itself is pinned: the changed chunks are
+// written to their final place in it, and the host does nothing at all.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -84,7 +87,90 @@ __global__ void __launch_bounds__(32 * kWarps)
         if (lane == 0) hdr[0] = count;
     }
 }
+
+// The same comparison, but the changed chunks go STRAIGHT TO THEIR PLACE in the caller's host array (pinned, device-
+// addressable): no stage, no header, nothing left to do on the host. `counter` (device memory, nullable) accumulates the
+// payload bytes written.
+__global__ void __launch_bounds__(32 * kWarps)
+    mg_obs_delta_scatter_kernel(const uint8_t* __restrict__ obs, uint8_t* __restrict__ prev, int n, uint8_t* __restrict__ host_obs,
+                                int full, unsigned long long* __restrict__ counter) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the step kernel's frames are visible
+    uint32_t total = 0;
+    for (int e = warp; e < n; e += nwarps) {
+        const uint8_t* cur = obs + (size_t)e * MG_FRAME_BYTES;
+        uint8_t* old = prev + (size_t)e * MG_FRAME_BYTES;
+        uint8_t* out = host_obs + (size_t)e * MG_FRAME_BYTES;
+        for (int it0 = 0; it0 < kIters; it0 += 4) {
+            uint4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = (it0 + u) * 32 + lane;
+                if (it0 + u < kIters && i < kChunks) {
+                    a[u] = ld16(cur + 16 * i);
+                    b[u] = ld16(old + 16 * i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int it = it0 + u, i = it * 32 + lane;
+                if (it >= kIters) break;
+                const bool diff = i < kChunks && (full || a[u].x != b[u].x || a[u].y != b[u].y || a[u].z != b[u].z || a[u].w != b[u].w);
+                if (diff) {
+                    *reinterpret_cast<uint4*>(out + 16 * i) = a[u];  // host memory: PCIe write
+                    *reinterpret_cast<uint4*>(old + 16 * i) = a[u];
+                    total++;
+                }
+            }
+        }
+    }
+    if (counter) {
+        total = __reduce_add_sync(0xffffffffu, total);
+        if (lane == 0 && total) atomicAdd(counter, 16ull * total);
+    }
+}
 }  // namespace
+
+extern "C" int mg_obs_delta_scatter(const uint8_t* obs, uint8_t* prev, int n, uint8_t* host_obs, int full, uint64_t* counter,
+                                    void* stream) {
+    if (!obs || !prev || !host_obs || n < 0) {
+        mg_set_err("mg_obs_delta_scatter: NULL pointer or negative n");
+        return MG_EINVAL;
+    }
+    if (((uintptr_t)obs & 15) || ((uintptr_t)prev & 15) || ((uintptr_t)host_obs & 15) || ((uintptr_t)counter & 7)) {
+        mg_set_err("mg_obs_delta_scatter: obs, prev and host_obs must be 16-byte aligned (counter: 8)");
+        return MG_EINVAL;
+    }
+    if (n == 0) return 0;
+    MgDeviceGuard guard(obs);
+    const MgDevInfo* di = guard.ok ? mg_dev_info(guard.dev) : nullptr;
+    if (!di) {
+        mg_set_err("no usable CUDA device");
+        return MG_ENODEV;
+    }
+    int ctas = (n + kWarps - 1) / kWarps;
+    const int cap = 4 * di->sms;
+    if (ctas > cap) ctas = cap;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(32 * kWarps);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mg_obs_delta_scatter_kernel, obs, prev, n, host_obs, full,
+                                       reinterpret_cast<unsigned long long*>(counter));
+    if (e != cudaSuccess) {
+        mg_set_err(cudaGetErrorString(e));
+        cudaGetLastError();
+        return (int)e;
+    }
+    return 0;
+}
 
 extern "C" size_t mg_obs_delta_stage_bytes(int n) {
     return n < 0 ? 0 : (size_t)n * (MG_DELTA_HDR_BYTES + MG_OBS_BYTES);

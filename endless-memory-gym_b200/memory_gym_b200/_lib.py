@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmemgym_b200.so")
 
-MG_ABI_VERSION = 6
+MG_ABI_VERSION = 7
 MG_OBS_BYTES = 84 * 84 * 3
 MG_DELTA_HDR_BYTES = 176
 MG_DEBUG_DIM = 336
@@ -150,6 +150,7 @@ def lib():
     L.mg_obs_delta_stage_bytes.argtypes = [i32]
     L.mg_obs_delta_encode.argtypes = [vp, vp, i32, vp, i32, vp]
     L.mg_obs_delta_decode.argtypes = [vp, vp, i32, i32, u64p]
+    L.mg_obs_delta_scatter.argtypes = [vp, vp, i32, vp, i32, vp, vp]
     L.mg_selftest_pcg64_host.argtypes = [vp, vp, vp, vp, i32, vp, vp]
     for fam, P in (("mm", MMParams), ("mp", MPParams), ("ss", SSParams), ("ep", EPParams)):
         getattr(L, f"mg_{fam}_check_params").argtypes = [C.POINTER(P)]

@@ -434,12 +434,12 @@ class MemoryGymVecEnv:
             raise L.MemGymError("capture_step() called before reset()")
         return StepGraph(self, obs_out)
 
-    def host_pipe(self, threads=None, depth=2):
+    def host_pipe(self, threads=None, depth=2, mode="auto"):
         """Observations, rewards and dones in HOST memory every step — the reference's interface (numpy arrays on the
         host) for a whole batch — without shipping whole frames over PCIe: see ``HostPipe``."""
         if self._params is None:
             raise L.MemGymError("host_pipe() called before reset()")
-        return HostPipe(self, threads, depth)
+        return HostPipe(self, threads, depth, mode)
 
     def policy_obs(self, obs=None, out=None):
         """The consumer step (``mg_obs_to_policy_bf16``): ``obs`` uint8[N,84,84,3] (default: this env's observation
@@ -524,31 +524,57 @@ class HostPipe:
     """Host-buffer stepping for a batched env: ``obs`` (uint8[N,84,84,3]), ``reward`` (float64[N]) and ``done``
     (bool[N]) live in HOST memory and are brought up to date every step, like the arrays the reference returns.
 
-    Transport (``mg_obs_delta_encode`` / ``mg_obs_delta_decode``): the step kernel reads the actions from pinned host
-    memory and writes rewards / dones into pinned host memory (zero-copy); a second kernel compares the new frames with
-    the frames the host already holds and sends only the 16-byte chunks that changed, straight into pinned host memory;
-    worker threads of the library patch them into ``obs``. Lossless: ``obs`` equals the device observation bit for bit.
+    Transport: the step kernel reads the actions from pinned host memory and writes rewards / dones into pinned host
+    memory (zero-copy); a second kernel compares the new frames with the frames the host already holds and sends only
+    the 16-byte chunks that changed. Lossless: ``obs`` equals the device observation bit for bit. Two modes:
+
+    * ``mode="direct"`` (``mg_obs_delta_scatter``): the host arrays are pinned and the kernel writes every
+      changed chunk to its place in them — the host does nothing but wait for the step's event. One host array per step
+      in flight (``depth`` of them, used in turn; ``obs`` is the array of the step collected last and stays untouched
+      until ``depth`` further steps have been collected).
+    * ``mode="patch"`` (``mg_obs_delta_encode`` / ``mg_obs_delta_decode``): the chunks go densely packed into a pinned
+      stage and worker threads of the library patch them into ONE pageable host array, in place.
+    * ``mode="auto"`` (default): "patch" while this rank has at least 10 host cores for the patching (measured on
+      B200 boxes, MortarMayhem-v0 x 4096 envs per GPU, M env-steps/s whole job, direct / patch: 1 GPU + 16 cores 20 / 29,
+      2 GPUs + 24 cores 37 / 47, 4 GPUs + 32 cores 49 / 37, 8 GPUs + 32 cores 48 / 29), else "direct": scattered 16-byte
+      writes drain more slowly over PCIe than packed ones, but they cost no host core.
 
     ``step(actions)`` = ``submit(actions)`` + ``collect()``. A loop whose actions do not depend on the newest
     observation (pre-sampled / scripted actions, the reference's bench.py shape) may keep up to ``depth`` steps in
-    flight: ``submit`` step t+1 before ``collect``-ing step t, so the GPU and the link work while the host patches.
-    ``obs`` is updated IN PLACE by ``collect``; the views returned for rewards / dones belong to that step's slot and
-    are reused ``depth`` steps later."""
+    flight: ``submit`` step t+1 before ``collect``-ing step t. The views returned for rewards / dones belong to that
+    step's slot and are reused ``depth`` steps later."""
 
-    def __init__(self, env, threads=None, depth=2):
+    AUTO_MIN_CORES = 10   # "auto": host cores per rank from which patching on the host beats direct writes
+
+    def __init__(self, env, threads=None, depth=2, mode="auto"):
         self.env = env
         n = env.num_envs
         self.depth = int(depth)
         if self.depth < 1:
             raise ValueError("depth must be >= 1")
+        if mode not in ("auto", "direct", "patch"):
+            raise ValueError("mode must be 'auto', 'direct' or 'patch'")
         # worker threads of the host decoder: the host's cores, shared among the ranks of this node (torchrun)
         ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-        self.threads = int(threads) if threads else max(1, min(32, (os.cpu_count() or 1) // ranks_here))
+        cores = max(1, (os.cpu_count() or 1) // ranks_here)
+        if mode == "auto":
+            mode = "patch" if cores >= self.AUTO_MIN_CORES else "direct"
+        self.mode = mode
+        self.threads = int(threads) if threads else max(1, min(32, cores))
         self._lib = env._be.lib
-        self.obs = torch.zeros((n, 84, 84, 3), dtype=torch.uint8)            # the caller-facing host array
-        self._prev = torch.zeros((n, 84, 84, 3), dtype=torch.uint8, device=env.device)  # what the host holds, on the device
-        stage_bytes = int(self._lib.mg_obs_delta_stage_bytes(n))
-        self._stage = [torch.zeros(stage_bytes, dtype=torch.uint8).pin_memory() for _ in range(self.depth)]
+        if mode == "direct":
+            # one pinned host array + the device-side mirror of what it holds, per step in flight
+            self._obs_h = [torch.zeros((n, 84, 84, 3), dtype=torch.uint8).pin_memory() for _ in range(self.depth)]
+            self._prevs = [torch.zeros((n, 84, 84, 3), dtype=torch.uint8, device=env.device) for _ in range(self.depth)]
+            self._counter = torch.zeros(1, dtype=torch.int64, device=env.device)   # payload bytes written so far
+            self.obs = self._obs_h[0]
+            self._stage = []
+        else:
+            self.obs = torch.zeros((n, 84, 84, 3), dtype=torch.uint8)            # the caller-facing host array
+            self._prev = torch.zeros((n, 84, 84, 3), dtype=torch.uint8, device=env.device)  # what the host holds, on the device
+            stage_bytes = int(self._lib.mg_obs_delta_stage_bytes(n))
+            self._stage = [torch.zeros(stage_bytes, dtype=torch.uint8).pin_memory() for _ in range(self.depth)]
+            self._prev_ptr, self._obs_host_ptr = self._prev.data_ptr(), self.obs.data_ptr()
         self._res = [torch.zeros(9 * n, dtype=torch.uint8).pin_memory() for _ in range(self.depth)]
         self._act = [torch.zeros_like(env._actions_dev, device="cpu").pin_memory() for _ in range(self.depth)]
         self._ev = [torch.cuda.Event() for _ in range(self.depth)]
@@ -559,36 +585,59 @@ class HostPipe:
         self._bytes_ref = C.byref(self._bytes)
         self._res_ptrs = [(r.data_ptr(), r.data_ptr() + 8 * n) for r in self._res]
         self._stage_ptrs = [t.data_ptr() for t in self._stage]
-        self._obs_dev_ptr, self._prev_ptr, self._obs_host_ptr = env.obs.data_ptr(), self._prev.data_ptr(), self.obs.data_ptr()
+        self._obs_dev_ptr = env.obs.data_ptr()
         self._pinned_ok = {}   # data_ptr -> numel of action tensors already validated (pinned, int64, contiguous)
         self._n_act = env._actions_dev.numel()
-        self.last_d2h_bytes = 0   # bytes that crossed the link for the step collected last (payload + headers + results)
-        self.total_d2h_bytes = 0
+        self.last_d2h_bytes = 0   # patch mode: bytes that crossed the link for the step collected last
+        self._total_d2h_bytes = 0
+        self._steps = 0
         self.resync()
+
+    @property
+    def total_d2h_bytes(self):
+        """Bytes that have crossed the link device -> host so far (changed chunks, headers in patch mode, results).
+        Direct mode reads a device-side counter: this synchronises."""
+        if self.mode == "direct":
+            return int(self._counter.item()) + 9 * self.env.num_envs * self._steps
+        return self._total_d2h_bytes
 
     def _encode(self, slot, full, stream=None):
         env = self.env
         cur = torch.cuda.current_stream(env.device)
-        rc = self._lib.mg_obs_delta_encode(self._obs_dev_ptr, self._prev_ptr, env.num_envs, self._stage_ptrs[slot], int(full),
-                                           cur.cuda_stream if stream is None else stream)
+        st = cur.cuda_stream if stream is None else stream
+        if self.mode == "direct":
+            rc = self._lib.mg_obs_delta_scatter(self._obs_dev_ptr, self._prevs[slot].data_ptr(), env.num_envs,
+                                                self._obs_h[slot].data_ptr(), int(full), self._counter.data_ptr(), st)
+        else:
+            rc = self._lib.mg_obs_delta_encode(self._obs_dev_ptr, self._prev_ptr, env.num_envs, self._stage_ptrs[slot], int(full), st)
         if rc:
-            L.check(rc, "mg_obs_delta_encode")
+            L.check(rc, "mg_obs_delta_scatter" if self.mode == "direct" else "mg_obs_delta_encode")
         self._ev[slot].record(cur)
 
     def _decode(self, slot):
         self._ev[slot].synchronize()
+        if self.mode == "direct":
+            self.obs = self._obs_h[slot]   # (already up to date: the kernel wrote the changed chunks in place)
+            return
         rc = self._lib.mg_obs_delta_decode(self._stage_ptrs[slot], self._obs_host_ptr, self.env.num_envs, self.threads,
                                            self._bytes_ref)
         if rc:
             L.check(rc, "mg_obs_delta_decode")
         self.last_d2h_bytes = self._bytes.value + 9 * self.env.num_envs
-        self.total_d2h_bytes += self.last_d2h_bytes
+        self._total_d2h_bytes += self.last_d2h_bytes
 
     def resync(self):
         """Send the env's current observation as whole frames (after ``env.reset()``, or whenever ``env.obs`` was
         produced outside this pipe)."""
         if self._head != self._tail:
             raise L.MemGymError("resync() with steps still in flight: collect() them first")
+        if self.mode == "direct":
+            for slot in range(self.depth):   # every host array in the rotation holds the current frame afterwards
+                self._encode(slot, True)
+            for slot in range(self.depth):
+                self._ev[slot].synchronize()
+            self.obs = self._obs_h[(self._tail - 1) % self.depth]
+            return self.obs
         self._encode(0, True)
         self._decode(0)
         return self.obs
@@ -631,12 +680,14 @@ class HostPipe:
 
     def collect(self):
         """Wait for the oldest step in flight and bring the host arrays up to date with it. Returns
-        (obs, reward, done, truncated, info) with host tensors; ``info`` is the env's device-side episode matrix."""
+        (obs, reward, done, truncated, info) with host tensors; ``info`` is the env's device-side episode matrix.
+        Direct mode: ``obs`` is this step's own host array (``depth`` arrays are used in turn)."""
         if self._head == self._tail:
             raise L.MemGymError("collect() without a submitted step")
         slot = self._tail % self.depth
         self._decode(slot)
         self._tail += 1
+        self._steps += 1
         reward, done = self._views[slot]
         return self.obs, reward, done, self._truncated, {"episode": self.env.info, "_episode": done}
 

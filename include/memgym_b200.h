@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 6
+#define MG_ABI_VERSION 7
 
 #define MG_SCREEN 84
 #define MG_OBS_BYTES (84 * 84 * 3) /* 21168 bytes per env, [x][y][c] */
@@ -372,6 +372,14 @@ int mg_obs_to_policy_bf16(const uint8_t* obs, void* out, int n, void* stream);
 size_t mg_obs_delta_stage_bytes(int n);
 int mg_obs_delta_encode(const uint8_t* obs, uint8_t* prev, int n, void* stage, int full, void* stream);
 int mg_obs_delta_decode(const void* stage, uint8_t* host_obs, int n, int threads, uint64_t* bytes_out);
+/*   mg_obs_delta_scatter device: the same comparison, but every changed chunk is written to ITS PLACE in `host_obs`
+ *                        [n][84][84][3] (PINNED host memory addressable by the device, 16-byte aligned) and in `prev`:
+ *                        once the stream has reached it, `host_obs` equals `obs` bit for bit and the host has nothing
+ *                        left to do. `prev` must mirror what THIS host array holds (one prev per host array when several
+ *                        are used in turn). counter (nullable, DEVICE memory, 8-byte aligned): payload bytes written are
+ *                        added to it. Asynchronous on `stream`. */
+int mg_obs_delta_scatter(const uint8_t* obs, uint8_t* prev, int n, uint8_t* host_obs, int full, uint64_t* counter,
+                         void* stream);
 
 /* Library / device introspection. */
 int mg_abi_version(void);

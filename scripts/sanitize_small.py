@@ -26,13 +26,14 @@ for env_id in ids:
     env.rollout(acts, ring, rew, dn)
     env.policy_obs()
     # round 2: zero-copy host actions / results, the delta transport (HostPipe), the ground-truth render
-    pipe = env.host_pipe(threads=4, depth=2)
     a_host = acts.cpu().pin_memory()
-    for t in range(6):
-        pipe.submit(a_host[t])
-        if t:
-            pipe.collect()
-    pipe.collect()
+    for mode in ("patch", "direct"):
+        pipe = env.host_pipe(threads=4, depth=2, mode=mode)
+        for t in range(6):
+            pipe.submit(a_host[t])
+            if t:
+                pipe.collect()
+        pipe.collect()
     if env_id not in ("MortarMayhemB-v0", "Endless-MysteryPath-v0"):
         dbg = mg.make(env_id, num_envs=40, device=dev, render_mode="debug_rgb_array")
         dbg.reset(seed=0, options=opts)

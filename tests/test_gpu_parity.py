@@ -625,11 +625,13 @@ def test_obs_delta_encoder_matches_stage_format():
         assert nbytes == 16 * int(hdr_w[:, 0].sum()) + nh
 
 
+@pytest.mark.parametrize("mode", ["direct", "patch"])
 @pytest.mark.parametrize("env_id,depth", [("MortarMayhem-v0", 1), ("MortarMayhem-v0", 2), ("SearingSpotlights-v0", 2),
                                           ("Endless-MysteryPath-v0", 3), ("MortarMayhemB-Grid-v0", 2)])
-def test_host_pipe_host_arrays_equal_device(env_id, depth):
+def test_host_pipe_host_arrays_equal_device(env_id, depth, mode):
     """HostPipe: observations / rewards / dones in HOST memory after every step (delta transport over PCIe, zero-copy
-    actions and results) equal the device-side step loop bit for bit — with `depth` steps in flight."""
+    actions and results) equal the device-side step loop bit for bit — with `depth` steps in flight; changed chunks
+    written by the GPU straight to their place in pinned host arrays ("direct") or patched in by host threads ("patch")."""
     n, T = 500, 90
     a = mg.make(env_id, num_envs=n, device=DEV)
     b = mg.make(env_id, num_envs=n, device=DEV)
@@ -637,14 +639,14 @@ def test_host_pipe_host_arrays_equal_device(env_id, depth):
     acts_host = acts.cpu()
     obs_a = a.reset(seed=6)[0]
     b.reset(seed=6)
-    pipe = b.host_pipe(threads=6, depth=depth)
+    pipe = b.host_pipe(threads=6, depth=depth, mode=mode)
     vis = (lambda o: o["visual_observation"]) if a.task_b else (lambda o: o)
     assert torch.equal(pipe.obs, vis(obs_a).cpu())
     want = []
     for t in range(T):
         o, r, d, _, _ = a.step(acts[t])
         want.append((vis(o).cpu(), r.cpu(), d.cpu()))
-    sent = 0
+    sent0 = pipe.total_d2h_bytes
     for t in range(T + depth - 1):
         if t < T:
             pipe.submit(acts_host[t] if t % 2 else acts_host[t].pin_memory())  # pinned and pageable action arrays
@@ -652,8 +654,7 @@ def test_host_pipe_host_arrays_equal_device(env_id, depth):
             o, r, d, _, _ = pipe.collect()
             wo, wr, wd = want[t - depth + 1]
             assert torch.equal(o, wo) and torch.equal(r, wr) and torch.equal(d, wd), t
-            sent += pipe.last_d2h_bytes
-    assert 0 < sent < T * n * 21168  # less than whole frames would have cost
+    assert 0 < pipe.total_d2h_bytes - sent0 < T * n * 21168  # less than whole frames would have cost
     # resets through the pipe, then more steps
     o2, _ = pipe.reset(seed=9)
     assert torch.equal(o2, vis(a.reset(seed=9)[0]).cpu())
