@@ -247,15 +247,6 @@ MG_HD void mg_ep_stream_put(volatile MgRng& d, const MgRng& s) {
     d.buf = s.buf, d.has_buf = s.has_buf;
 }
 
-// Team side, lane 0: the slot the next reset may adopt, or nullptr (nothing produced yet / another chain)
-MG_HD MgEPSpecSlot* mg_ep_chain_head(MgEPSpecRec* g, uint32_t& tword) {
-    const uint32_t h = mg_vload_u32(&g->hword);
-    tword = mg_vload_u32(&g->tword);
-    if ((h & 3u) == MG_CHAIN_IDLE || mg_chain_id(h) != mg_chain_id(tword)) return nullptr;
-    if (((mg_chain_count(h) - mg_chain_consumed(tword)) & 255u) == 0u) return nullptr;
-    return &g->slot[mg_chain_consumed(tword) % MG_EP_AHEAD];
-}
-
 // Team side, at a reset: true if the three segments were adopted from the env's chain. The slot is read as 50
 // independent words spread over the lanes (a chain of dependent global loads would cost the team ~1 us each).
 template <class Ctx>
@@ -312,18 +303,6 @@ MG_HD void mg_ep_chain_start(Ctx& c, MgEPSpecRec* g, const MgRng& stream) {
 template <class Ctx>
 MG_HD void mg_ep_chain_restart(Ctx& c, const MgEPState& s, MgEPWarpMem& wm) {
     if (c.lane == 0) mg_ep_chain_start(c, mg_ep_spec_of(wm.state, wm.cur_env), s.rng);
-}
-
-// Team side, when it takes an env over: a record without a chain (first rollout after construction), or whose chain
-// head was generated for another stream (a reset launch re-seeded the env), gets a new one
-template <class Ctx>
-MG_HD void mg_ep_chain_check(Ctx& c, const MgEPState& s, MgEPWarpMem& wm) {
-    if (c.lane != 0 || !s.live) return;
-    MgEPSpecRec* const g = mg_ep_spec_of(wm.state, wm.cur_env);
-    uint32_t tword;
-    const MgEPSpecSlot* sl = mg_ep_chain_head(g, tword);
-    const bool idle = (mg_vload_u32(&g->hword) & 3u) == MG_CHAIN_IDLE;
-    if (idle || (sl && !mg_ep_stream_eq(sl->before, s.rng))) mg_ep_chain_restart(c, s, wm);
 }
 
 // Helper side, ONE LANE: does the chain of record g have room for another segment? (hword as read by the caller)

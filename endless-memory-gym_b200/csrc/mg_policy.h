@@ -359,11 +359,10 @@ struct EPPolicy {
     static MG_HD void logic(Ctx& c, const K& k, const MgKIO& q, const MgAssetView& a, int env, int t, State& s, int a0,
                             int a1, MgFrameJob& job, Frame* fr, const MgScratch& sc) {
         MgEPWarpMem& wm = *reinterpret_cast<MgEPWarpMem*>(sc.warp);
-        if (c.lane == 0) {
-            wm.cur_env = env;  // (read by lane 0 only)
-            // rollouts: the team takes this env over for many steps (single steps leave a missing chain to the next reset)
-            if (t == 0 && wm.ahead && !wm.offload && q.n_steps > 1) mg_ep_chain_check(c, s, wm);
-        }
+        // (a record whose chain is missing or stale — first launch, re-seeded by a reset launch — is left to its next
+        // auto-reset, which then generates inline and starts the chain: looking at the chain every time a team takes an
+        // env over cost the team 1-5 us of dependent global loads per visit)
+        if (c.lane == 0) wm.cur_env = env;  // (read by lane 0 only)
         mg_env_logic_coop<EPPolicy>(c, k, q, a, env, t, s, a0, a1, job, fr, sc);
     }
     template <class Ctx>

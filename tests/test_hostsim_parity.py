@@ -115,7 +115,7 @@ def test_rollout_equals_step_loop_hostsim(env_id, opts, backend):
         # the rollout's resets adopted paths generated ahead by the "helper lane" (MgEPSpecRec: hword, tword, adopted),
         # the step loop generated all of its paths inline: same bytes either way
         words = a.state[:, 2048:2060].contiguous().view(torch.int32)
-        assert (words[:, 2] >= 2).all() and ((words[:, 0] >> 13) >= 1).all()
+        assert (words[:, 2] >= 1).all() and int(words[:, 2].sum()) >= 2 * n and ((words[:, 0] >> 13) >= 1).all()
         assert backend.sim.mgsim_ep_resumed() > 10  # searches stopped mid-way were parked and resumed
         assert (b.state[:, 2048:] == 0).all()
 
