@@ -289,6 +289,43 @@ def test_emp_rollout_with_and_without_helper_warps(monkeypatch):
     assert int(outs[0][2].sum()) > 3 * n  # several episodes per env: the hand-over was exercised
 
 
+@pytest.mark.parametrize("options", [None, {"camera_offset_scale": 1.7, "show_background": True, "show_stamina": True,
+                                             "agent_speed": 13.0, "max_steps": 30, "agent_scale": 0.5}])
+def test_emp_rollout_launches_vs_oracle(options):
+    """Endless-MysteryPath through ROLLOUT launches of a full-size batch (20 steps each; from the second episode on most
+    resets adopt paths the helper warps generated ahead, one env per lane): a sample of the envs against independent
+    oracle instances, every frame, reward and done."""
+    from oracle import memgym_oracle as O
+    n, m, K, launches = 4096, 16, 20, 24
+    env = mg.make("Endless-MysteryPath-v0", num_envs=n, device=DEV)
+    obs, _ = env.reset(seed=300, options=options)
+    sample = [7 + 255 * i for i in range(m)]  # spread over the CTAs / helper warps
+    oras = [O.make("Endless-MysteryPath-v0") for _ in sample]
+    for e, o in zip(sample, oras):
+        assert np.array_equal(obs[e].cpu().numpy(), o.reset(seed=300 + e, options=options)[0])
+    rng = np.random.default_rng(12)
+    ring = torch.zeros((K, n, 84, 84, 3), dtype=torch.uint8, device=DEV)
+    rew = torch.zeros((K, n), dtype=torch.float64, device=DEV)
+    dn = torch.zeros((K, n), dtype=torch.bool, device=DEV)
+    idx = torch.as_tensor(sample, device=DEV)
+    spec0 = env.state[idx, 2048:2060].clone().view(torch.int32)
+    episodes = 0
+    for launch in range(launches):
+        a = rng.integers(0, 4, size=(K, n))
+        env.rollout(torch.as_tensor(a, device=DEV), ring, rew, dn)
+        got, r, d = ring[:, idx].cpu().numpy(), rew[:, idx].cpu().numpy(), dn[:, idx].cpu().numpy()
+        for t in range(K):
+            for j, (e, o) in enumerate(zip(sample, oras)):
+                w_obs, w_r, w_d, _, _ = o.step(int(a[t][e]))
+                assert float(w_r) == r[t][j] and bool(w_d) == bool(d[t][j]), (launch, t, e)
+                if w_d:
+                    episodes += 1
+                    w_obs, _ = o.reset(options=options)
+                assert np.array_equal(got[t][j], w_obs), (launch, t, e)
+    adopted = int((env.state[idx, 2048:2060].clone().view(torch.int32)[:, 2] - spec0[:, 2]).sum())
+    assert episodes > 5 * m and adopted > episodes // 3, (episodes, adopted)  # the adopted paths are the reference's paths
+
+
 def test_emp_results_do_not_depend_on_the_lookahead_block():
     """The second half of an Endless-MysteryPath record (the episodes generated ahead) is a cache: a reset adopts an
     episode only if its stream matches. Overwriting that half with random bytes — chains that claim to be active, parked
