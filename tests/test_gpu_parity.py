@@ -326,6 +326,19 @@ def test_emp_rollout_launches_vs_oracle(options):
     assert episodes > 5 * m and adopted > episodes // 3, (episodes, adopted)  # the adopted paths are the reference's paths
 
 
+def test_emp_lookahead_survives_a_random_mix_of_operations():
+    """scripts/emp_stress.py: rollouts of random length, single steps, step_many, masked re-seeding resets, full resets and
+    restored snapshots in random order, on an env with helper warps and on one without: identical bytes after every
+    operation (adopted, missing and stale look-ahead episodes all occur)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "emp_stress.py"), "1500", "90", "5"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().splitlines()[-1].startswith("ok: 90 operations"), out.stdout + out.stderr
+
+
 def test_emp_results_do_not_depend_on_the_lookahead_block():
     """The second half of an Endless-MysteryPath record (the episodes generated ahead) is a cache: a reset adopts an
     episode only if its stream matches. Overwriting that half with random bytes — chains that claim to be active, parked
