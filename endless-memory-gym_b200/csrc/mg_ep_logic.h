@@ -238,10 +238,6 @@ MG_HD int mg_ep_bar_height(int stamina, int max_visible, bool at_reset) {
     return (int)((double)MG_W * (1.0 - ((double)v / (double)max_visible)));
 }
 
-MG_HD bool mg_ep_stream_eq(const volatile MgRng& a, const MgRng& b) {
-    return a.state_lo == b.state_lo && a.state_hi == b.state_hi && a.inc_lo == b.inc_lo && a.inc_hi == b.inc_hi &&
-           a.buf == b.buf && a.has_buf == b.has_buf;
-}
 MG_HD void mg_ep_stream_put(volatile MgRng& d, const MgRng& s) {
     d.state_lo = s.state_lo, d.state_hi = s.state_hi, d.inc_lo = s.inc_lo, d.inc_hi = s.inc_hi;
     d.buf = s.buf, d.has_buf = s.has_buf;
